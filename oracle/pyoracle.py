@@ -1,0 +1,163 @@
+"""TEST INFRASTRUCTURE — ctypes access to the two CPU checkers built by oracle/Makefile.
+
+    Oracle("port")       -> oracle/liblcg_oracle.so      (our C restatement, lcg_oracle.c)
+    Oracle("reference")  -> oracle/_ref/liblcg_ref.so    (the unmodified reference CPU/OpenMP library + ref_shim.cpp)
+
+Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference) may import this module.
+Nothing here reads /root/reference at run time: the reference library is prebuilt and travels with the repo.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PORT_SO = os.path.join(HERE, "liblcg_oracle.so")
+REF_SO = os.path.join(HERE, "_ref", "liblcg_ref.so")
+
+# solver ids (reference util.h:32-64, 187-221)
+LCG_CG, LCG_PCG, LCG_CGS, LCG_BICGSTAB, LCG_BICGSTAB2, LCG_PG, LCG_SPG = range(7)
+CLCG_BICG, CLCG_BICG_SYM, CLCG_CGS, CLCG_BICGSTAB, CLCG_TFQMR, CLCG_PCG, CLCG_PBICG = range(7)
+
+
+class LcgPara(C.Structure):
+    """lcg_para, reference util.h:95-148 (64 bytes, offsets 0/8/16/24/32/40/48/56)."""
+    _fields_ = [("max_iterations", C.c_int), ("epsilon", C.c_double), ("abs_diff", C.c_int),
+                ("restart_epsilon", C.c_double), ("step", C.c_double), ("sigma", C.c_double),
+                ("beta", C.c_double), ("maxi_m", C.c_int)]
+
+
+class ClcgPara(C.Structure):
+    """clcg_para, reference util.h:247-273 (24 bytes)."""
+    _fields_ = [("max_iterations", C.c_int), ("epsilon", C.c_double), ("abs_diff", C.c_int)]
+
+
+def default_para(**kw) -> LcgPara:
+    p = LcgPara(0, 1e-6, 0, 1e-6, 1.0, 0.95, 0.9, 10)  # defparam, util.h:153
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def default_cpara(**kw) -> ClcgPara:
+    p = ClcgPara(0, 1e-6, 0)  # defparam2, util.h:278
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+@dataclass
+class SolveResult:
+    ret: int
+    iters: int          # k passed to the last progress call
+    calls: int          # number of progress calls
+    residual: float     # residual passed to the last progress call
+    seconds: float      # wall time inside the solver call
+    x: np.ndarray
+    history: np.ndarray
+
+
+def build(verbose: bool = False) -> None:
+    """(Re)build the checkers.  The reference part is skipped by the Makefile when /root/reference is absent."""
+    r = subprocess.run(["make", "-C", HERE], capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout, r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError("oracle build failed")
+
+
+def have_reference() -> bool:
+    return os.path.exists(REF_SO)
+
+
+def _p(a, t):
+    return None if a is None else a.ctypes.data_as(C.POINTER(t))
+
+
+class Oracle:
+    def __init__(self, kind: str = "port"):
+        self.kind = kind
+        if kind == "port":
+            path, self.pfx = PORT_SO, "lcgoracle_"
+        elif kind == "reference":
+            path, self.pfx = REF_SO, "lcgref_"
+        else:
+            raise ValueError(kind)
+        if not os.path.exists(path):
+            if kind == "port":
+                build()
+            else:
+                raise FileNotFoundError(path)
+        self.lib = C.CDLL(path)
+        self._solve = getattr(self.lib, self.pfx + "solve")
+        self._solve.restype = C.c_int
+        self._csolve = getattr(self.lib, self.pfx + "csolve")
+        self._csolve.restype = C.c_int
+        getattr(self.lib, self.pfx + "num_threads").restype = C.c_int
+
+    def num_threads(self) -> int:
+        return int(getattr(self.lib, self.pfx + "num_threads")())
+
+    def set_time(self, t: int) -> None:
+        """Pin the seed clcg_vecrnd() derives from time(0) (reference lcg_complex.cpp:118-127)."""
+        getattr(self.lib, self.pfx + "set_time")(C.c_long(t))
+
+    def vecrnd(self, n: int) -> np.ndarray:
+        out = np.empty(n, dtype=np.complex128)
+        getattr(self.lib, self.pfx + "vecrnd")(_p(out, C.c_double), C.c_int(n))
+        return out
+
+    def spmv(self, A, x):
+        y = np.empty_like(x)
+        if np.iscomplexobj(A["val"]):
+            raise ValueError("use cspmv")
+        getattr(self.lib, self.pfx + "spmv")(C.c_int(A["n"]), _p(A["row_ptr"], C.c_int), _p(A["col"], C.c_int),
+                                              _p(A["val"], C.c_double), _p(x, C.c_double), _p(y, C.c_double))
+        return y
+
+    def cspmv(self, A, x, transpose=False, conjugate=False):
+        y = np.empty_like(x)
+        getattr(self.lib, self.pfx + "cspmv")(C.c_int(A["n"]), _p(A["row_ptr"], C.c_int), _p(A["col"], C.c_int),
+                                               _p(A["val"], C.c_double), _p(x, C.c_double), _p(y, C.c_double),
+                                               C.c_int(int(transpose)), C.c_int(int(conjugate)))
+        return y
+
+    def solve(self, solver_id, A, b, x0=None, para=None, low=None, hig=None, diag=None,
+              progress=True, stop_at=-1, hist_cap=0) -> SolveResult:
+        """Real solve.  A = dict(n,row_ptr,col,val).  PCG uses Jacobi z = r/diag (diag required)."""
+        n = A["n"]
+        x = np.zeros(n, dtype=np.float64) if x0 is None else np.array(x0, dtype=np.float64, copy=True)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        hist = np.zeros(max(hist_cap, 1), dtype=np.float64)
+        out = (C.c_int * 2)()
+        dout = (C.c_double * 2)()
+        para = para if para is not None else default_para()
+        ret = self._solve(C.c_int(solver_id), C.c_int(n), _p(A["row_ptr"], C.c_int), _p(A["col"], C.c_int),
+                          _p(A["val"], C.c_double), _p(x, C.c_double), _p(b, C.c_double),
+                          _p(low, C.c_double), _p(hig, C.c_double), _p(diag, C.c_double), C.byref(para),
+                          C.c_int(int(progress)), C.c_int(stop_at), _p(hist, C.c_double), C.c_int(hist_cap), out, dout)
+        return SolveResult(ret, out[0], out[1], dout[0], dout[1], x, hist[:min(out[1], hist_cap)].copy())
+
+    def csolve(self, solver_id, A, b, x0=None, para=None, diag=None, progress=True, stop_at=-1, hist_cap=0) -> SolveResult:
+        """Complex solve.  `diag` (complex Jacobi diagonal) is only understood by the port (CLCG_PCG)."""
+        n = A["n"]
+        x = np.zeros(n, dtype=np.complex128) if x0 is None else np.array(x0, dtype=np.complex128, copy=True)
+        b = np.ascontiguousarray(b, dtype=np.complex128)
+        val = np.ascontiguousarray(A["val"], dtype=np.complex128)
+        hist = np.zeros(max(hist_cap, 1), dtype=np.float64)
+        out = (C.c_int * 2)()
+        dout = (C.c_double * 2)()
+        para = para if para is not None else default_cpara()
+        args = [C.c_int(solver_id), C.c_int(n), _p(A["row_ptr"], C.c_int), _p(A["col"], C.c_int),
+                _p(val, C.c_double), _p(x, C.c_double), _p(b, C.c_double)]
+        if self.kind == "port":
+            args.append(_p(diag, C.c_double))
+        elif solver_id == CLCG_PCG:
+            raise ValueError("the reference has no buildable CPU complex PCG (Eigen only)")
+        args += [C.byref(para), C.c_int(int(progress)), C.c_int(stop_at), _p(hist, C.c_double), C.c_int(hist_cap), out, dout]
+        ret = self._csolve(*args)
+        return SolveResult(ret, out[0], out[1], dout[0], dout[1], x, hist[:min(out[1], hist_cap)].copy())
