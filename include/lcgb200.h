@@ -1,0 +1,206 @@
+/*
+ * lcgb200.h — C ABI of liblcgb200.so, the B200-native (sm_100a) replacement for the iteration loops of
+ * liblcg's CUDA solvers.  Plain pointers and sizes only; no C++ types, no torch types.
+ *
+ * Every entry point cites the reference interface it replaces (paths under YiZhangCUG/liblcg src/lib).
+ * The C++ drop-in headers in include/lcg_b200/ (lcg_cuda.h, clcg_cuda.h, lcg.h, clcg.h) re-declare the
+ * reference's own function names (with their default arguments) as inline forwards to these symbols.
+ *
+ * Two ways in:
+ *   1. Reference-shaped calls (lcgb200_solver_cuda & co.): same arguments, same meaning, same return codes
+ *      as lcg_solver_cuda & co.  m and B are HOST arrays (the reference copies them itself,
+ *      lcg_cuda.cu:110-111,210).  Any user Ax / Mx callback works (generic path: the user's SpMV, then our
+ *      fused vector kernels).  Passing the exported sentinel callbacks lcgb200_csr_ax / lcgb200_jacobi_mx
+ *      (lcgb200_csr_cax / lcgb200_jacobi_cmx for complex) with `instance` = an lcgb200_csr_t switches to the
+ *      built-in fused CSR operator: SpMV fused with its dot products, no cuSPARSE/cuBLAS anywhere.
+ *   2. Handle-shaped calls (lcgb200_solve / lcgb200_csolve): the same engine for callers whose vectors
+ *      already live on the device, plus iteration statistics.
+ */
+#ifndef LCGB200_H
+#define LCGB200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Opaque CUDA library types, declared exactly as cublas_v2.h / cusparse.h declare them so that this header
+ * can be used with or without those headers. */
+struct cublasContext;
+struct cusparseContext;
+struct cusparseDnVecDescr;
+typedef struct cublasContext* lcgb200_cublas_t;       /* == cublasHandle_t */
+typedef struct cusparseContext* lcgb200_cusparse_t;   /* == cusparseHandle_t */
+typedef struct cusparseDnVecDescr* lcgb200_dnvec_t;   /* == cusparseDnVecDescr_t */
+
+/* ---- parameter blocks: byte-identical to the reference (util.h:95-148, util.h:247-273) ---- */
+typedef struct lcgb200_para {
+	int max_iterations;      /* 0 = until convergence */
+	double epsilon;          /* (0,1); test is on SQUARED norms: |r|^2/max(|m|^2,1) <= eps (lcg.cpp:208-209) */
+	int abs_diff;            /* 1: sqrt(|r|^2)/n <= eps */
+	double restart_epsilon;  /* BICGSTAB2 */
+	double step;             /* PG / SPG initial step */
+	double sigma;            /* SPG */
+	double beta;             /* SPG */
+	int maxi_m;              /* SPG history length */
+} lcgb200_para;
+
+typedef struct lcgb200_cpara {
+	int max_iterations;
+	double epsilon;
+	int abs_diff;
+} lcgb200_cpara;
+
+/* ---- solver ids (util.h:32-64, util.h:187-221) ---- */
+enum { LCGB200_CG = 0, LCGB200_PCG, LCGB200_CGS, LCGB200_BICGSTAB, LCGB200_BICGSTAB2, LCGB200_PG, LCGB200_SPG };
+enum { LCGB200_CBICG = 0, LCGB200_CBICG_SYM, LCGB200_CCGS, LCGB200_CBICGSTAB, LCGB200_CTFQMR, LCGB200_CPCG, LCGB200_CPBICG };
+
+/* ---- return codes: the exact integers of lcg_return_enum / clcg_return_enum (util.h:69-90, 226-242) ---- */
+enum {
+	LCGB200_CONVERGENCE = 0, LCGB200_STOP = 1, LCGB200_ALREADY_OPTIMIZIED = 2,
+	LCGB200_UNKNOWN_ERROR = -1024, LCGB200_INVILAD_VARIABLE_SIZE = -1023, LCGB200_INVILAD_MAX_ITERATIONS = -1022,
+	LCGB200_INVILAD_EPSILON = -1021, LCGB200_INVILAD_RESTART_EPSILON = -1020, LCGB200_REACHED_MAX_ITERATIONS = -1019,
+	LCGB200_NULL_PRECONDITION_MATRIX = -1018, LCGB200_NAN_VALUE = -1017, LCGB200_INVALID_POINTER = -1016,
+	LCGB200_INVALID_LAMBDA = -1015, LCGB200_INVALID_SIGMA = -1014, LCGB200_INVALID_BETA = -1013,
+	LCGB200_INVALID_MAXIM = -1012, LCGB200_SIZE_NOT_MATCH = -1011,
+	/* complex enum: same names shifted (util.h:226-242).  The complex solvers return the REAL enum's
+	 * LCG_REACHED_MAX_ITERATIONS (-1019, clcg.cpp:164 / clcg_cuda.cu:193) and so do we. */
+	LCGB200_C_REACHED_MAX_ITERATIONS = -1020, LCGB200_C_NAN_VALUE = -1019, LCGB200_C_INVALID_POINTER = -1018,
+	LCGB200_C_SIZE_NOT_MATCH = -1017, LCGB200_C_UNKNOWN_SOLVER = -1016
+};
+
+/* ---- callback typedefs: source-compatible with lcg_cuda.h:45-46,61-62 and clcg_cuda.h:45-46,61-62 ---- */
+typedef void (*lcgb200_axfunc_cuda_ptr)(void* instance, lcgb200_cublas_t cub_handle, lcgb200_cusparse_t cus_handle,
+	lcgb200_dnvec_t x, lcgb200_dnvec_t prod_Ax, const int n_size, const int nz_size);
+typedef int (*lcgb200_progress_cuda_ptr)(void* instance, const double* m_dev, const double converge,
+	const lcgb200_para* param, const int n_size, const int nz_size, const int k);
+/* oper_t is a cusparseOperation_t: 0 = N, 1 = T, 2 = H */
+typedef void (*lcgb200_caxfunc_cuda_ptr)(void* instance, lcgb200_cublas_t cub_handle, lcgb200_cusparse_t cus_handle,
+	lcgb200_dnvec_t x, lcgb200_dnvec_t prod_Ax, const int n_size, const int nz_size, int oper_t);
+/* m_dev points at n_size cuDoubleComplex (interleaved re,im doubles) */
+typedef int (*lcgb200_cprogress_cuda_ptr)(void* instance, const void* m_dev, const double converge,
+	const lcgb200_cpara* param, const int n_size, const int nz_size, const int k);
+/* host-side (CPU API) callbacks: lcg.h:37-38,53-54 */
+typedef void (*lcgb200_axfunc_ptr)(void* instance, const double* x, double* prod_Ax, const int n_size);
+typedef int (*lcgb200_progress_ptr)(void* instance, const double* m, const double converge,
+	const lcgb200_para* param, const int n_size, const int k);
+
+/* =====================================================================================================
+ * Built-in CSR operator (new; the reference leaves the matrix to the caller — sample8.cu:80-103)
+ * ===================================================================================================== */
+typedef struct lcgb200_csr_s* lcgb200_csr_t;
+
+enum { LCGB200_REAL = 0, LCGB200_COMPLEX = 1 };
+enum { LCGB200_HOST = 0, LCGB200_DEVICE = 1 };
+enum {
+	LCGB200_CSR_TRANSPOSE = 1,   /* also store A^T (needed by complex BiCG's A^H d2, clcg.cpp:188) */
+	LCGB200_CSR_JACOBI = 2       /* extract diag(A) at creation (replaces lcg_smDcsr_get_diagonal, algebra_cuda.cu:40-57,
+	                                 lcg_complex_cuda.cu:46-63) so lcgb200_jacobi_mx can be used */
+};
+
+/* Copies the CSR arrays (int32 row_ptr[n+1], int32 col[nnz], double|double2 val[nnz], base 0) to the current
+ * device and builds the row tiles the SpMV kernel streams.  `location` says where the three arrays live. */
+int lcgb200_csr_create(lcgb200_csr_t* out, int n, int nnz, const int* row_ptr, const int* col, const void* val,
+	int value_type, int location, unsigned flags);
+/* Rectangular variant for a row block of a partitioned matrix: n_rows local rows, columns index an extended
+ * vector of n_cols >= n_rows entries (local entries first, then ghost entries). */
+int lcgb200_csr_create_rect(lcgb200_csr_t* out, int n_rows, int n_cols, int nnz, const int* row_ptr, const int* col,
+	const void* val, int value_type, int location, unsigned flags);
+int lcgb200_csr_destroy(lcgb200_csr_t A);
+/* user pointer handed to the progress callback as `instance` when the sentinel operator is used */
+int lcgb200_csr_set_user(lcgb200_csr_t A, void* user_instance);
+/* diag(A) to a HOST array of n values (double or interleaved complex) */
+int lcgb200_csr_get_diagonal(lcgb200_csr_t A, void* diag_host);
+/* y = op(A) x on device vectors; op: 0 = N, 1 = T, 2 = H (T/H need LCGB200_CSR_TRANSPOSE).  stream = cudaStream_t */
+int lcgb200_csr_spmv(lcgb200_csr_t A, const void* x_dev, void* y_dev, int op, void* stream);
+/* y = A x fused with the dot products the solvers take from it: dots[0] = w.y (w = x if w_dev is NULL),
+ * dots[1] = y.y, dots[2] = x.y (real: plain sums; complex: conj-first inner products, 2 doubles each).
+ * dots_dev receives 3 (real) or 6 (complex) doubles.  This is exactly the kernel the solvers launch. */
+int lcgb200_csr_spmv_dot(lcgb200_csr_t A, const void* x_dev, void* y_dev, const void* w_dev, double* dots_dev, void* stream);
+/* bytes the SpMV kernel must move per launch by SURVEY.md §8(d): nnz*(S+4) + (n+1)*4 + 2*n*S */
+long long lcgb200_csr_spmv_bytes(lcgb200_csr_t A);
+int lcgb200_csr_info(lcgb200_csr_t A, int* n_rows, int* n_cols, int* nnz, int* n_tiles, int* lanes_per_row);
+
+/* Sentinel callbacks: never called; their ADDRESS selects the built-in operator.  instance = lcgb200_csr_t. */
+void lcgb200_csr_ax(void* instance, lcgb200_cublas_t, lcgb200_cusparse_t, lcgb200_dnvec_t x, lcgb200_dnvec_t Ax, const int n, const int nz);
+void lcgb200_jacobi_mx(void* instance, lcgb200_cublas_t, lcgb200_cusparse_t, lcgb200_dnvec_t x, lcgb200_dnvec_t Mx, const int n, const int nz);
+void lcgb200_csr_cax(void* instance, lcgb200_cublas_t, lcgb200_cusparse_t, lcgb200_dnvec_t x, lcgb200_dnvec_t Ax, const int n, const int nz, int oper_t);
+void lcgb200_jacobi_cmx(void* instance, lcgb200_cublas_t, lcgb200_cusparse_t, lcgb200_dnvec_t x, lcgb200_dnvec_t Mx, const int n, const int nz, int oper_t);
+
+/* =====================================================================================================
+ * Reference-shaped entry points
+ * ===================================================================================================== */
+/* replaces lcg_solver_cuda (lcg_cuda.h:81-83, lcg_cuda.cu:40-58).  The reference only dispatches CG and CGS
+ * here (anything else -> CG); we additionally accept BICGSTAB and BICGSTAB2 (CPU-only in the reference,
+ * lcg.cpp:629-1034).  m, B: HOST arrays of n_size doubles; m is overwritten in place on every exit. */
+int lcgb200_solver_cuda(lcgb200_axfunc_cuda_ptr Afp, lcgb200_progress_cuda_ptr Pfp, double* m, const double* B,
+	const int n_size, const int nz_size, const lcgb200_para* param, void* instance,
+	lcgb200_cublas_t cub_handle, lcgb200_cusparse_t cus_handle, int solver_id);
+/* replaces lcg_solver_preconditioned_cuda (lcg_cuda.h:104-106, lcg_cuda.cu:64-69); solver_id ignored as there */
+int lcgb200_solver_preconditioned_cuda(lcgb200_axfunc_cuda_ptr Afp, lcgb200_axfunc_cuda_ptr Mfp, lcgb200_progress_cuda_ptr Pfp,
+	double* m, const double* B, const int n_size, const int nz_size, const lcgb200_para* param, void* instance,
+	lcgb200_cublas_t cub_handle, lcgb200_cusparse_t cus_handle, int solver_id);
+/* replaces lcg_solver_constrained_cuda (lcg_cuda.h:129-131, lcg_cuda.cu:76-81).  The reference's CUDA lpg is
+ * broken; semantics follow the CPU lpg / lspg (lcg.cpp:1054-1447). */
+int lcgb200_solver_constrained_cuda(lcgb200_axfunc_cuda_ptr Afp, lcgb200_progress_cuda_ptr Pfp, double* m, const double* B,
+	const double* low, const double* hig, const int n_size, const int nz_size, const lcgb200_para* param, void* instance,
+	lcgb200_cublas_t cub_handle, lcgb200_cusparse_t cus_handle, int solver_id);
+/* replaces clcg_solver_cuda (clcg_cuda.h:81-83, clcg_cuda.cu:42-60): BICG, BICG_SYM as there, plus CGS,
+ * BICGSTAB, TFQMR (CPU-only in the reference, clcg.cpp:366-882).  m, B: HOST cuDoubleComplex arrays. */
+int lcgb200_csolver_cuda(lcgb200_caxfunc_cuda_ptr Afp, lcgb200_cprogress_cuda_ptr Pfp, void* m, const void* B,
+	const int n_size, const int nz_size, const lcgb200_cpara* param, void* instance,
+	lcgb200_cublas_t cub_handle, lcgb200_cusparse_t cus_handle, int solver_id);
+/* replaces clcg_solver_preconditioned_cuda (clcg_cuda.h:103-105, clcg_cuda.cu:70-84): CLCG_PCG only */
+int lcgb200_csolver_preconditioned_cuda(lcgb200_caxfunc_cuda_ptr Afp, lcgb200_caxfunc_cuda_ptr Mfp, lcgb200_cprogress_cuda_ptr Pfp,
+	void* m, const void* B, const int n_size, const int nz_size, const lcgb200_cpara* param, void* instance,
+	lcgb200_cublas_t cub_handle, lcgb200_cusparse_t cus_handle, int solver_id);
+
+/* =====================================================================================================
+ * Handle-shaped entry points (same engine; vectors may already be on the device)
+ * ===================================================================================================== */
+typedef struct lcgb200_info {
+	int iterations;        /* k handed to the last convergence check (what the reference reports through Pfp) */
+	int checks;            /* number of loop-head convergence checks performed */
+	int spmv_launches;     /* SpMV kernels launched (including skipped no-op launches after convergence) */
+	int kernel_launches;   /* all kernels of ours launched by this call */
+	double residual;       /* residual at the last check (the `converge` value of the callbacks) */
+	double device_ms;      /* CUDA-event time from the first to the last kernel of the solve */
+	double total_ms;       /* host wall time of the whole call, copies included */
+} lcgb200_info;
+
+enum {
+	LCGB200_VEC_DEVICE = 1,   /* m, B (low, hig) are device pointers */
+	LCGB200_USE_JACOBI = 2    /* PCG: built-in Jacobi z = r/diag (needs LCGB200_CSR_JACOBI) */
+};
+
+/* real solvers on the built-in operator: solver_id in LCGB200_CG..LCGB200_SPG (low/hig only for PG, SPG) */
+int lcgb200_solve(lcgb200_csr_t A, int solver_id, double* m, const double* B, const double* low, const double* hig,
+	const lcgb200_para* param, lcgb200_progress_cuda_ptr Pfp, unsigned flags, void* stream, lcgb200_info* info);
+/* complex solvers on the built-in operator: solver_id in LCGB200_CBICG..LCGB200_CPCG */
+int lcgb200_csolve(lcgb200_csr_t A, int solver_id, void* m, const void* B, const lcgb200_cpara* param,
+	lcgb200_cprogress_cuda_ptr Pfp, unsigned flags, void* stream, lcgb200_info* info);
+
+/* =====================================================================================================
+ * Settings / diagnostics
+ * ===================================================================================================== */
+/* seed used for the random shadow residual of complex CGS/BICGSTAB/TFQMR; 0 = time(0) as the reference does
+ * (lcg_complex.cpp:118-127).  The sequence is libc srand()/rand(), drawn on the host, like the reference. */
+void lcgb200_set_shadow_seed(long seed);
+/* residual definition of the complex solvers: 0 (default) = reference CPU (|r|^4/max(|m|^4,1), clcg.cpp:112-147),
+ * 1 = reference CUDA (|r|^2/max(|m|,1)^2, clcg_cuda.cu:145-176) */
+void lcgb200_set_complex_residual_mode(int mode);
+/* iterations enqueued between two host polls of the device convergence flag when no progress callback is set */
+void lcgb200_set_poll_interval(int iterations);
+const char* lcgb200_last_error(void);
+int lcgb200_version(void);
+/* device helpers used by tests / bench: fill CSR rows [row0,row1) of a g^3 stencil directly on the device.
+ * kind: 0 = 7pt Poisson, 1 = 27pt Poisson, 2 = 7pt convection-diffusion.  Pass NULL arrays
+ * to only get the nnz count of the row range in *nnz_out. */
+int lcgb200_gen_stencil(int kind, int g, long long row0, long long row1, int* row_ptr_dev, int* col_dev, double* val_dev,
+	long long col_offset, long long* nnz_out, void* stream);
+/* b[row0..row1) = (A x*)[row0..row1) with x*[i] = uint32(i*2654435761)/2^32, summed left to right per row */
+int lcgb200_gen_rhs(int kind, int g, long long row0, long long row1, double* b_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LCGB200_H */

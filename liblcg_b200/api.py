@@ -1,0 +1,260 @@
+"""Host-side mirror of liblcg's CUDA solver interface on top of the C ABI (include/lcgb200.h).
+
+Names, argument meaning and return codes follow the reference (lcg_cuda.h:81-131, clcg_cuda.h:81-105):
+`lcg_solver_cuda`, `lcg_solver_preconditioned_cuda`, `lcg_solver_constrained_cuda`, `clcg_solver_cuda`,
+`clcg_solver_preconditioned_cuda` take HOST arrays m (in/out) and B, a parameter block and callbacks.
+The matrix lives in a `CsrOperator` (the built-in fused operator); pass `CSR_AX` / `JACOBI_MX` as the Ax / Mx
+callbacks and the operator as `instance`, exactly like a C++ caller passes lcgb200_csr_ax and the handle.
+
+PyTorch is only used by callers for device memory and streams; nothing here imports it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import LcgPara, ClcgPara, Info, PROGRESS, CPROGRESS
+
+# solver ids (reference util.h:32-64, 187-221)
+LCG_CG, LCG_PCG, LCG_CGS, LCG_BICGSTAB, LCG_BICGSTAB2, LCG_PG, LCG_SPG = range(7)
+CLCG_BICG, CLCG_BICG_SYM, CLCG_CGS, CLCG_BICGSTAB, CLCG_TFQMR, CLCG_PCG, CLCG_PBICG = range(7)
+
+# return codes (reference util.h:69-90)
+LCG_CONVERGENCE, LCG_STOP, LCG_ALREADY_OPTIMIZIED = 0, 1, 2
+LCG_UNKNOWN_ERROR, LCG_INVILAD_VARIABLE_SIZE, LCG_INVILAD_MAX_ITERATIONS, LCG_INVILAD_EPSILON = -1024, -1023, -1022, -1021
+LCG_INVILAD_RESTART_EPSILON, LCG_REACHED_MAX_ITERATIONS, LCG_NULL_PRECONDITION_MATRIX, LCG_NAN_VALUE = -1020, -1019, -1018, -1017
+LCG_INVALID_POINTER, LCG_INVALID_LAMBDA, LCG_INVALID_SIGMA, LCG_INVALID_BETA, LCG_INVALID_MAXIM, LCG_SIZE_NOT_MATCH = -1016, -1015, -1014, -1013, -1012, -1011
+CLCG_REACHED_MAX_ITERATIONS, CLCG_NAN_VALUE, CLCG_INVALID_POINTER, CLCG_SIZE_NOT_MATCH, CLCG_UNKNOWN_SOLVER = -1020, -1019, -1018, -1017, -1016
+
+REAL, COMPLEX = 0, 1
+HOST, DEVICE = 0, 1
+CSR_TRANSPOSE, CSR_JACOBI = 1, 2
+VEC_DEVICE, USE_JACOBI = 1, 2
+
+
+class _Sentinel:
+    def __init__(self, symbol):
+        self.symbol = symbol
+
+    @property
+    def address(self):
+        return _lib.fn_addr(self.symbol)
+
+
+CSR_AX = _Sentinel("lcgb200_csr_ax")
+JACOBI_MX = _Sentinel("lcgb200_jacobi_mx")
+CSR_CAX = _Sentinel("lcgb200_csr_cax")
+JACOBI_CMX = _Sentinel("lcgb200_jacobi_cmx")
+
+
+def lcg_default_parameters(**kw) -> LcgPara:
+    """defparam (reference util.h:153)."""
+    p = LcgPara(0, 1e-6, 0, 1e-6, 1.0, 0.95, 0.9, 10)
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def clcg_default_parameters(**kw) -> ClcgPara:
+    """defparam2 (reference util.h:278)."""
+    p = ClcgPara(0, 1e-6, 0)
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def last_error() -> str:
+    return (_lib.load().lcgb200_last_error() or b"").decode()
+
+
+def set_shadow_seed(seed: int) -> None:
+    _lib.load().lcgb200_set_shadow_seed(seed)
+
+
+def set_complex_residual_mode(mode: int) -> None:
+    _lib.load().lcgb200_set_complex_residual_mode(mode)
+
+
+def set_poll_interval(n: int) -> None:
+    _lib.load().lcgb200_set_poll_interval(n)
+
+
+def _ptr(a):
+    """Raw address of a numpy array / torch tensor / int / None."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    raise TypeError(type(a))
+
+
+class CsrOperator:
+    """Built-in CSR operator handle (lcgb200_csr_t).  Arrays may be numpy (host) or torch CUDA tensors (device)."""
+
+    def __init__(self, row_ptr, col, val, n_cols=None, transpose=False, jacobi=False):
+        lib = _lib.load()
+        on_dev = hasattr(val, "data_ptr")
+        if on_dev:
+            cx = val.is_complex() or (val.dim() == 2 and val.shape[-1] == 2)
+            n = row_ptr.numel() - 1
+            nnz = col.numel()
+        else:
+            row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int32)
+            col = np.ascontiguousarray(col, dtype=np.int32)
+            cx = np.iscomplexobj(val)
+            val = np.ascontiguousarray(val, dtype=np.complex128 if cx else np.float64)
+            n = len(row_ptr) - 1
+            nnz = len(col)
+        self.n, self.nnz, self.complex = n, nnz, bool(cx)
+        self.n_cols = n if n_cols is None else n_cols
+        flags = (CSR_TRANSPOSE if transpose else 0) | (CSR_JACOBI if jacobi else 0)
+        h = C.c_void_p()
+        rc = lib.lcgb200_csr_create_rect(C.byref(h), n, self.n_cols, nnz, _ptr(row_ptr), _ptr(col), _ptr(val),
+                                         COMPLEX if cx else REAL, DEVICE if on_dev else HOST, flags)
+        if rc != 0:
+            raise RuntimeError(f"lcgb200_csr_create failed ({rc}): {last_error()}")
+        self.handle = h
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "handle", None):
+            _lib.load().lcgb200_csr_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self):
+        v = [C.c_int() for _ in range(5)]
+        _lib.load().lcgb200_csr_info(self.handle, *[C.byref(x) for x in v])
+        return dict(zip(("n_rows", "n_cols", "nnz", "n_tiles", "lanes_per_row"), (x.value for x in v)))
+
+    def spmv_bytes(self) -> int:
+        return int(_lib.load().lcgb200_csr_spmv_bytes(self.handle))
+
+    def diagonal(self) -> np.ndarray:
+        out = np.empty(self.n, dtype=np.complex128 if self.complex else np.float64)
+        rc = _lib.load().lcgb200_csr_get_diagonal(self.handle, out.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(f"get_diagonal failed ({rc})")
+        return out
+
+    def spmv(self, x_dev, y_dev, op=0, stream=None):
+        rc = _lib.load().lcgb200_csr_spmv(self.handle, _ptr(x_dev), _ptr(y_dev), op, stream)
+        if rc != 0:
+            raise RuntimeError(f"spmv failed ({rc}): {last_error()}")
+
+    def spmv_dot(self, x_dev, y_dev, w_dev, dots_dev, stream=None):
+        rc = _lib.load().lcgb200_csr_spmv_dot(self.handle, _ptr(x_dev), _ptr(y_dev), _ptr(w_dev), _ptr(dots_dev), stream)
+        if rc != 0:
+            raise RuntimeError(f"spmv_dot failed ({rc}): {last_error()}")
+
+
+@dataclass
+class Result:
+    ret: int
+    iterations: int
+    residual: float
+    info: Info
+
+
+def _wrap_progress(Pfp, complex_):
+    """Python callable (instance, m_dev_ptr, converge, param, n, nz, k) -> int  =>  C callback."""
+    if Pfp is None:
+        return None, None
+    proto = CPROGRESS if complex_ else PROGRESS
+
+    def tramp(instance, m_dev, converge, param, n, nz, k):
+        return int(Pfp(instance, m_dev, converge, param.contents, n, nz, k) or 0)
+
+    cb = proto(tramp)
+    return cb, C.cast(cb, C.c_void_p)
+
+
+def _afp_addr(Afp):
+    if Afp is None:
+        return None
+    if isinstance(Afp, _Sentinel):
+        return Afp.address
+    if isinstance(Afp, int):
+        return Afp
+    return C.cast(Afp, C.c_void_p).value
+
+
+def _instance(instance):
+    return instance.handle if isinstance(instance, CsrOperator) else instance
+
+
+# ---------------------------------------------------------------------------------- reference-shaped calls
+def lcg_solver_cuda(Afp, Pfp, m, B, n_size, nz_size, param, instance, cub_handle=None, cus_handle=None, solver_id=LCG_CG) -> int:
+    """lcg_solver_cuda (reference lcg_cuda.h:81-83).  m (in/out) and B are host float64 arrays."""
+    cb, cbp = _wrap_progress(Pfp, False)
+    return _lib.load().lcgb200_solver_cuda(_afp_addr(Afp), cbp, _ptr(m), _ptr(B), n_size, nz_size,
+                                           C.byref(param) if param is not None else None, _instance(instance),
+                                           cub_handle, cus_handle, solver_id)
+
+
+def lcg_solver_preconditioned_cuda(Afp, Mfp, Pfp, m, B, n_size, nz_size, param, instance, cub_handle=None, cus_handle=None,
+                                   solver_id=LCG_PCG) -> int:
+    """lcg_solver_preconditioned_cuda (reference lcg_cuda.h:104-106)."""
+    cb, cbp = _wrap_progress(Pfp, False)
+    return _lib.load().lcgb200_solver_preconditioned_cuda(_afp_addr(Afp), _afp_addr(Mfp), cbp, _ptr(m), _ptr(B), n_size, nz_size,
+                                                          C.byref(param) if param is not None else None, _instance(instance),
+                                                          cub_handle, cus_handle, solver_id)
+
+
+def lcg_solver_constrained_cuda(Afp, Pfp, m, B, low, hig, n_size, nz_size, param, instance, cub_handle=None, cus_handle=None,
+                                solver_id=LCG_PG) -> int:
+    """lcg_solver_constrained_cuda (reference lcg_cuda.h:129-131)."""
+    cb, cbp = _wrap_progress(Pfp, False)
+    return _lib.load().lcgb200_solver_constrained_cuda(_afp_addr(Afp), cbp, _ptr(m), _ptr(B), _ptr(low), _ptr(hig), n_size, nz_size,
+                                                       C.byref(param) if param is not None else None, _instance(instance),
+                                                       cub_handle, cus_handle, solver_id)
+
+
+def clcg_solver_cuda(Afp, Pfp, m, B, n_size, nz_size, param, instance, cub_handle=None, cus_handle=None, solver_id=CLCG_BICG) -> int:
+    """clcg_solver_cuda (reference clcg_cuda.h:81-83).  m, B: host complex128 arrays."""
+    cb, cbp = _wrap_progress(Pfp, True)
+    return _lib.load().lcgb200_csolver_cuda(_afp_addr(Afp), cbp, _ptr(m), _ptr(B), n_size, nz_size,
+                                            C.byref(param) if param is not None else None, _instance(instance),
+                                            cub_handle, cus_handle, solver_id)
+
+
+def clcg_solver_preconditioned_cuda(Afp, Mfp, Pfp, m, B, n_size, nz_size, param, instance, cub_handle=None, cus_handle=None,
+                                    solver_id=CLCG_PCG) -> int:
+    """clcg_solver_preconditioned_cuda (reference clcg_cuda.h:103-105)."""
+    cb, cbp = _wrap_progress(Pfp, True)
+    return _lib.load().lcgb200_csolver_preconditioned_cuda(_afp_addr(Afp), _afp_addr(Mfp), cbp, _ptr(m), _ptr(B), n_size, nz_size,
+                                                           C.byref(param) if param is not None else None, _instance(instance),
+                                                           cub_handle, cus_handle, solver_id)
+
+
+# ------------------------------------------------------------------------------------- handle-shaped calls
+def solve(A: CsrOperator, solver_id, m, B, low=None, hig=None, param=None, Pfp=None, device=False, jacobi=False, stream=None) -> Result:
+    """lcgb200_solve: real solvers on the built-in operator; m/B numpy (host) or CUDA tensors (device=True)."""
+    cb, cbp = _wrap_progress(Pfp, False)
+    info = Info()
+    flags = (VEC_DEVICE if device else 0) | (USE_JACOBI if jacobi else 0)
+    rc = _lib.load().lcgb200_solve(A.handle, solver_id, _ptr(m), _ptr(B), _ptr(low), _ptr(hig),
+                                   C.byref(param) if param is not None else None, cbp, flags, stream, C.byref(info))
+    return Result(rc, info.iterations, info.residual, info)
+
+
+def csolve(A: CsrOperator, solver_id, m, B, param=None, Pfp=None, device=False, jacobi=False, stream=None) -> Result:
+    """lcgb200_csolve: complex solvers on the built-in operator."""
+    cb, cbp = _wrap_progress(Pfp, True)
+    info = Info()
+    flags = (VEC_DEVICE if device else 0) | (USE_JACOBI if jacobi else 0)
+    rc = _lib.load().lcgb200_csolve(A.handle, solver_id, _ptr(m), _ptr(B), C.byref(param) if param is not None else None,
+                                    cbp, flags, stream, C.byref(info))
+    return Result(rc, info.iterations, info.residual, info)

@@ -1,0 +1,718 @@
+// capi.cu — the extern "C" boundary (include/lcgb200.h): CSR handle management, parameter validation in the
+// reference's order, host<->device staging of m/B as the reference does it (lcg_cuda.cu:110-111,210), and the
+// adaptors that let user Ax/Mx callbacks (cuSPARSE descriptors) drive the same engine.
+#include "solvers.cuh"
+#include <dlfcn.h>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+using namespace lcgb200;
+
+namespace lcgb200 {
+const char* last_error();
+}
+
+// ------------------------------------------------------------------------------------------------ helpers
+namespace {
+
+struct ApiFailure { int code; };
+
+template <class T> T* dev_alloc(size_t count)
+{
+	T* p = nullptr;
+	LCG_CUDA_CHECK(cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T)));
+	return p;
+}
+
+int pick_lpr(long long nnz, long long rows)
+{
+	const double avg = rows > 0 ? (double)nnz / (double)rows : 0.0;
+	if (avg <= 10.0) return 1;
+	if (avg <= 20.0) return 2;
+	if (avg <= 40.0) return 4;
+	if (avg <= 80.0) return 8;
+	if (avg <= 160.0) return 16;
+	return 32;
+}
+
+// greedy row tiles: consecutive rows whose non-zeros, counted from the 4-aligned start, fit the staging buffer
+void build_tiles(const int* rp, int n_rows, int tile_nnz, std::vector<int4>& tiles)
+{
+	tiles.clear();
+	int r = 0;
+	while (r < n_rows)
+	{
+		const int k0 = rp[r] & ~3;
+		int r1 = r;
+		while (r1 < n_rows && r1 - r < kTileRows && rp[r1 + 1] - k0 <= tile_nnz) r1++;
+		if (r1 == r) r1 = r + 1;   // a single row longer than the buffer: the kernel streams it from global memory
+		tiles.push_back(make_int4(r, r1, k0, rp[r1]));
+		r = r1;
+	}
+}
+
+__global__ void k_diag_real(int n, const int* rp, const int* ci, const double* v, double* d)
+{	// first entry with col == row, like lcg_smDcsr_get_diagonal_device (algebra_cuda.cu:40-57); 0 when absent
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	double out = 0.0;
+	for (int k = rp[i]; k < rp[i + 1]; k++) if (ci[k] == i) { out = v[k]; break; }
+	d[i] = out;
+}
+__global__ void k_diag_cplx(int n, const int* rp, const int* ci, const double2* v, double2* d)
+{	// lcg_complex_cuda.cu:46-63
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	double2 out = make_double2(0.0, 0.0);
+	for (int k = rp[i]; k < rp[i + 1]; k++) if (ci[k] == i) { out = v[k]; break; }
+	d[i] = out;
+}
+
+template <class T>
+void host_transpose(int n_rows, int n_cols, const int* rp, const int* ci, const T* v, std::vector<int>& trp, std::vector<int>& tci, std::vector<T>& tv)
+{
+	const int nnz = rp[n_rows];
+	trp.assign((size_t)n_cols + 1, 0); tci.resize((size_t)nnz); tv.resize((size_t)nnz);
+	for (int k = 0; k < nnz; k++) trp[(size_t)ci[k] + 1]++;
+	for (int i = 0; i < n_cols; i++) trp[(size_t)i + 1] += trp[(size_t)i];
+	std::vector<int> fill(trp.begin(), trp.end() - 1);
+	for (int i = 0; i < n_rows; i++)
+		for (int k = rp[i]; k < rp[i + 1]; k++) { int d = fill[(size_t)ci[k]]++; tci[(size_t)d] = i; tv[(size_t)d] = v[k]; }
+}
+
+constexpr int kPad = 16;   // elements of zero padding behind col/val so that 128-bit tile loads never run off the end
+
+template <class T>
+void upload_csr(int n_rows, int nnz, const int* rp_h, const int* ci, const T* v, bool src_device,
+	int** d_rp, int** d_ci, void** d_v, int4** d_tiles, int* n_tiles, int tile_nnz)
+{
+	*d_rp = dev_alloc<int>((size_t)n_rows + 1 + kPad);
+	*d_ci = dev_alloc<int>((size_t)nnz + kPad);
+	T* dv = dev_alloc<T>((size_t)nnz + kPad);
+	*d_v = dv;
+	LCG_CUDA_CHECK(cudaMemset(*d_ci + nnz, 0, kPad * sizeof(int)));
+	LCG_CUDA_CHECK(cudaMemset(dv + nnz, 0, kPad * sizeof(T)));
+	LCG_CUDA_CHECK(cudaMemcpy(*d_rp, rp_h, ((size_t)n_rows + 1) * sizeof(int), cudaMemcpyHostToDevice));
+	const cudaMemcpyKind kind = src_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+	LCG_CUDA_CHECK(cudaMemcpy(*d_ci, ci, (size_t)nnz * sizeof(int), kind));
+	LCG_CUDA_CHECK(cudaMemcpy(dv, v, (size_t)nnz * sizeof(T), kind));
+	std::vector<int4> tiles;
+	build_tiles(rp_h, n_rows, tile_nnz, tiles);
+	*n_tiles = (int)tiles.size();
+	*d_tiles = dev_alloc<int4>(tiles.size());
+	LCG_CUDA_CHECK(cudaMemcpy(*d_tiles, tiles.data(), tiles.size() * sizeof(int4), cudaMemcpyHostToDevice));
+}
+
+template <class T>
+void create_typed(CsrHandle* h, const int* row_ptr, const int* col, const T* val, int location, int tile_nnz)
+{
+	const bool dev = (location == LCGB200_DEVICE);
+	std::vector<int> rp_h((size_t)h->n_rows + 1);
+	if (dev) LCG_CUDA_CHECK(cudaMemcpy(rp_h.data(), row_ptr, rp_h.size() * sizeof(int), cudaMemcpyDeviceToHost));
+	else std::memcpy(rp_h.data(), row_ptr, rp_h.size() * sizeof(int));
+	if (rp_h[0] != 0 || rp_h[(size_t)h->n_rows] != h->nnz) { set_error_msg("row_ptr[0] must be 0 and row_ptr[n] must equal nnz"); throw ApiFailure{LCGB200_SIZE_NOT_MATCH}; }
+	for (int i = 0; i < h->n_rows; i++) if (rp_h[(size_t)i + 1] < rp_h[(size_t)i]) { set_error_msg("row_ptr must be non-decreasing"); throw ApiFailure{LCGB200_SIZE_NOT_MATCH}; }
+	upload_csr<T>(h->n_rows, h->nnz, rp_h.data(), col, val, dev, &h->row_ptr, &h->col, &h->val, &h->tiles, &h->n_tiles, tile_nnz);
+	h->lpr = pick_lpr(h->nnz, h->n_rows);
+	if (h->flags & LCGB200_CSR_TRANSPOSE)
+	{
+		std::vector<int> ci_h; std::vector<T> v_h;
+		const int* cip = col; const T* vp = val;
+		if (dev)
+		{
+			ci_h.resize((size_t)h->nnz); v_h.resize((size_t)h->nnz);
+			LCG_CUDA_CHECK(cudaMemcpy(ci_h.data(), col, (size_t)h->nnz * sizeof(int), cudaMemcpyDeviceToHost));
+			LCG_CUDA_CHECK(cudaMemcpy(v_h.data(), val, (size_t)h->nnz * sizeof(T), cudaMemcpyDeviceToHost));
+			cip = ci_h.data(); vp = v_h.data();
+		}
+		std::vector<int> trp, tci; std::vector<T> tv;
+		host_transpose<T>(h->n_rows, h->n_cols, rp_h.data(), cip, vp, trp, tci, tv);
+		upload_csr<T>(h->n_cols, h->nnz, trp.data(), tci.data(), tv.data(), false, &h->t_row_ptr, &h->t_col, &h->t_val, &h->t_tiles, &h->t_n_tiles, tile_nnz);
+		h->t_lpr = pick_lpr(h->nnz, h->n_cols);
+	}
+	if (h->flags & LCGB200_CSR_JACOBI)
+	{
+		T* d = dev_alloc<T>((size_t)h->n_rows);
+		h->diag = d;
+		const int grid = (h->n_rows + 255) / 256;
+		if (sizeof(T) == sizeof(double)) k_diag_real<<<grid, 256>>>(h->n_rows, h->row_ptr, h->col, (const double*)h->val, (double*)d);
+		else k_diag_cplx<<<grid, 256>>>(h->n_rows, h->row_ptr, h->col, (const double2*)h->val, (double2*)d);
+		LCG_CUDA_CHECK(cudaGetLastError());
+		LCG_CUDA_CHECK(cudaDeviceSynchronize());
+	}
+}
+
+void destroy_handle(CsrHandle* h)
+{
+	if (!h) return;
+	cudaFree(h->row_ptr); cudaFree(h->col); cudaFree(h->val); cudaFree(h->tiles);
+	cudaFree(h->t_row_ptr); cudaFree(h->t_col); cudaFree(h->t_val); cudaFree(h->t_tiles);
+	cudaFree(h->diag); cudaFree(h->ws);
+	cudaFree(h->d_state); cudaFree(h->d_partials);
+	if (h->h_state) cudaFreeHost(h->h_state);
+	if (h->h_state2) cudaFreeHost(h->h_state2);
+	for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+	delete h;
+}
+
+// ---- cuSPARSE dense-vector descriptors for user callbacks: resolved lazily, never touched by the built-in path
+struct CusparseShim {
+	void* lib = nullptr;
+	int (*create)(lcgb200_dnvec_t*, long long, void*, int) = nullptr;   // cusparseCreateDnVec(descr*, int64 size, void* values, cudaDataType)
+	int (*destroy)(lcgb200_dnvec_t) = nullptr;
+	bool load()
+	{
+		if (create) return true;
+		const char* names[] = {"libcusparse.so.12", "libcusparse.so"};
+		for (const char* nm : names) { lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+		if (!lib) { set_error_msg("user Ax callbacks need libcusparse (cusparseCreateDnVec) and it could not be loaded"); return false; }
+		create = (int (*)(lcgb200_dnvec_t*, long long, void*, int))dlsym(lib, "cusparseCreateDnVec");
+		destroy = (int (*)(lcgb200_dnvec_t))dlsym(lib, "cusparseDestroyDnVec");
+		return create && destroy;
+	}
+};
+CusparseShim g_cusparse;
+
+struct DescrCache {
+	int n; int dtype;   // CUDA_R_64F = 1, CUDA_C_64F = 5
+	std::vector<std::pair<const void*, lcgb200_dnvec_t>> items;
+	lcgb200_dnvec_t get(const void* p)
+	{
+		for (auto& it : items) if (it.first == p) return it.second;
+		lcgb200_dnvec_t d = nullptr;
+		if (g_cusparse.create(&d, (long long)n, const_cast<void*>(p), dtype) != 0) { set_error_msg("cusparseCreateDnVec failed"); throw CudaFailure(); }
+		items.emplace_back(p, d);
+		return d;
+	}
+	~DescrCache() { for (auto& it : items) g_cusparse.destroy(it.second); }
+};
+
+// ---- parameter validation, in the order the reference performs it ------------------------------------
+int check_real(int solver_id, int n, const lcgb200_para& p, const void* m, const void* B, const void* lo, const void* hi)
+{
+	switch (solver_id)
+	{
+		case LCGB200_BICGSTAB2:	// lcg.cpp:819-825
+			if (n <= 0) return LCGB200_INVILAD_VARIABLE_SIZE;
+			if (p.max_iterations < 0) return LCGB200_INVILAD_MAX_ITERATIONS;
+			if (p.epsilon <= 0.0) return LCGB200_INVILAD_EPSILON;
+			if (p.restart_epsilon <= 0.0 || p.epsilon >= 1.0) return LCGB200_INVILAD_RESTART_EPSILON;
+			break;
+		case LCGB200_PG:	// lcg.cpp:1062-1065
+			if (n <= 0) return LCGB200_INVILAD_VARIABLE_SIZE;
+			if (p.max_iterations < 0) return LCGB200_INVILAD_MAX_ITERATIONS;
+			if (p.epsilon <= 0.0) return LCGB200_INVILAD_EPSILON;
+			if (p.step <= 0.0 || p.epsilon >= 1.0) return LCGB200_INVALID_LAMBDA;
+			break;
+		case LCGB200_SPG:	// lcg.cpp:1232-1238
+			if (n <= 0) return LCGB200_INVILAD_VARIABLE_SIZE;
+			if (p.max_iterations < 0) return LCGB200_INVILAD_MAX_ITERATIONS;
+			if (p.epsilon <= 0.0 || p.epsilon >= 1.0) return LCGB200_INVILAD_EPSILON;
+			if (p.step <= 0.0) return LCGB200_INVALID_LAMBDA;
+			if (p.sigma <= 0.0 || p.sigma >= 1.0) return LCGB200_INVALID_SIGMA;
+			if (p.beta <= 0.0 || p.beta >= 1.0) return LCGB200_INVALID_BETA;
+			if (p.maxi_m <= 0) return LCGB200_INVALID_MAXIM;
+			break;
+		default:	// lcg.cpp:150-152
+			if (n <= 0) return LCGB200_INVILAD_VARIABLE_SIZE;
+			if (p.max_iterations < 0) return LCGB200_INVILAD_MAX_ITERATIONS;
+			if (p.epsilon <= 0.0 || p.epsilon >= 1.0) return LCGB200_INVILAD_EPSILON;
+	}
+	if (!m || !B) return LCGB200_INVALID_POINTER;
+	if ((solver_id == LCGB200_PG || solver_id == LCGB200_SPG) && (!lo || !hi)) return LCGB200_INVALID_POINTER;
+	return 0;
+}
+
+int check_cplx(int n, const lcgb200_cpara& p, const void* m, const void* B)
+{	// clcg.cpp:84-89
+	if (n <= 0) return LCGB200_INVILAD_VARIABLE_SIZE;
+	if (p.max_iterations < 0) return LCGB200_INVILAD_MAX_ITERATIONS;
+	if (p.epsilon <= 0.0 || p.epsilon >= 1.0) return LCGB200_INVILAD_EPSILON;
+	if (!m || !B) return LCGB200_C_INVALID_POINTER;
+	return 0;
+}
+
+const lcgb200_para kDefPara = {0, 1e-6, 0, 1e-6, 1.0, 0.95, 0.9, 10};	// defparam, util.h:153
+const lcgb200_cpara kDefCPara = {0, 1e-6, 0};				// defparam2, util.h:278
+
+inline double now_ms()
+{
+	using namespace std::chrono;
+	return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+// One solve, real.  `h` may be null (callback operator).  m/B/lo/hi live on the host unless dev_vecs.
+int do_solve_real(CsrHandle* h, Operator<double>& A, int solver_id, double* m, const double* B, const double* lo, const double* hi,
+	const lcgb200_para& para, int n, int n_ext, long long n_global,
+	const std::function<ProgressFn(const double* m_dev)>& make_pf, bool dev_vecs, cudaStream_t stream, lcgb200_info* info)
+{
+	const double t0 = now_ms();
+	Engine E(stream, h);
+	E.n_local = (size_t)n;
+	const bool constrained = (solver_id == LCGB200_PG || solver_id == LCGB200_SPG);
+	// m can be used in place only if it is a device vector, 16-byte aligned, and needs no ghost tail
+	const bool m_inplace = dev_vecs && n_ext == n && ((reinterpret_cast<uintptr_t>(m) & 15) == 0);
+	const bool b_inplace = dev_vecs && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+	const bool box_inplace = dev_vecs && constrained && ((reinterpret_cast<uintptr_t>(lo) & 15) == 0) && ((reinterpret_cast<uintptr_t>(hi) & 15) == 0);
+	const size_t vec_bytes = (((size_t)n_ext * sizeof(double)) + 255) & ~size_t(255);
+	int nvec = real_vector_count(solver_id) + (m_inplace ? 0 : 1) + (b_inplace ? 0 : 1) + ((constrained && !box_inplace) ? 2 : 0);
+	E.reserve(vec_bytes * (size_t)nvec);
+	double* d_m = m; const double* d_B = B; const double* d_lo = lo; const double* d_hi = hi;
+	const cudaMemcpyKind in_kind = dev_vecs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+	if (!m_inplace)
+	{
+		d_m = E.alloc<double>((size_t)n_ext);
+		LCG_CUDA_CHECK(cudaMemcpyAsync(d_m, m, (size_t)n * sizeof(double), in_kind, stream));
+	}
+	if (!b_inplace)
+	{
+		double* t = E.alloc<double>((size_t)n_ext);
+		LCG_CUDA_CHECK(cudaMemcpyAsync(t, B, (size_t)n * sizeof(double), in_kind, stream));
+		d_B = t;
+	}
+	if (constrained && !box_inplace)
+	{
+		double* t1 = E.alloc<double>((size_t)n_ext); double* t2 = E.alloc<double>((size_t)n_ext);
+		LCG_CUDA_CHECK(cudaMemcpyAsync(t1, lo, (size_t)n * sizeof(double), in_kind, stream));
+		LCG_CUDA_CHECK(cudaMemcpyAsync(t2, hi, (size_t)n * sizeof(double), in_kind, stream));
+		d_lo = t1; d_hi = t2;
+	}
+	DevState init;
+	std::memset(&init, 0, sizeof(init));
+	init.eps = para.epsilon; init.restart_eps = para.restart_epsilon; init.sigma = para.sigma; init.ls_beta = para.beta;
+	init.n_global = n_global; init.abs_diff = para.abs_diff; init.max_it = para.max_iterations;
+	init.sc[SC_STEP] = para.step;
+	init.ret = RC_UNKNOWN;
+	E.start(init);
+	E.pf = make_pf(d_m);
+	int ret = solve_real(E, A, solver_id, d_m, d_B, d_lo, d_hi, para, (size_t)n, (size_t)n_ext);
+	const double dev_ms = E.device_ms();
+	if (!m_inplace)
+	{
+		const cudaMemcpyKind out_kind = dev_vecs ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+		LCG_CUDA_CHECK(cudaMemcpyAsync(m, d_m, (size_t)n * sizeof(double), out_kind, stream));
+		LCG_CUDA_CHECK(cudaStreamSynchronize(stream));
+	}
+	if (info)
+	{
+		info->iterations = E.h_st->k_report; info->checks = E.h_st->checks; info->spmv_launches = E.spmv_launches;
+		info->kernel_launches = E.launches; info->residual = E.h_st->residual; info->device_ms = dev_ms; info->total_ms = now_ms() - t0;
+	}
+	return ret;
+}
+
+int do_solve_cplx(CsrHandle* h, Operator<double2>& A, int solver_id, double2* m, const double2* B, const lcgb200_cpara& para,
+	int n, int n_ext, long long n_global, const std::function<ProgressFn(const double2* m_dev)>& make_pf, bool dev_vecs,
+	cudaStream_t stream, lcgb200_info* info)
+{
+	const double t0 = now_ms();
+	Engine E(stream, h);
+	E.n_local = (size_t)n;
+	const bool m_inplace = dev_vecs && n_ext == n && ((reinterpret_cast<uintptr_t>(m) & 15) == 0);
+	const bool b_inplace = dev_vecs && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+	const size_t vec_bytes = (((size_t)n_ext * sizeof(double2)) + 255) & ~size_t(255);
+	int nvec = complex_vector_count(solver_id) + (m_inplace ? 0 : 1) + (b_inplace ? 0 : 1);
+	E.reserve(vec_bytes * (size_t)nvec);
+	double2* d_m = m; const double2* d_B = B;
+	const cudaMemcpyKind in_kind = dev_vecs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+	if (!m_inplace) { d_m = E.alloc<double2>((size_t)n_ext); LCG_CUDA_CHECK(cudaMemcpyAsync(d_m, m, (size_t)n * sizeof(double2), in_kind, stream)); }
+	if (!b_inplace) { double2* t = E.alloc<double2>((size_t)n_ext); LCG_CUDA_CHECK(cudaMemcpyAsync(t, B, (size_t)n * sizeof(double2), in_kind, stream)); d_B = t; }
+	DevState init;
+	std::memset(&init, 0, sizeof(init));
+	init.eps = para.epsilon; init.n_global = n_global; init.abs_diff = para.abs_diff; init.max_it = para.max_iterations;
+	init.cres_mode = settings().cres_mode;
+	init.ret = RC_UNKNOWN;
+	E.start(init);
+	E.pf = make_pf(d_m);
+	int ret = solve_complex(E, A, solver_id, d_m, d_B, para, (size_t)n, (size_t)n_ext);
+	const double dev_ms = E.device_ms();
+	if (!m_inplace)
+	{
+		const cudaMemcpyKind out_kind = dev_vecs ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+		LCG_CUDA_CHECK(cudaMemcpyAsync(m, d_m, (size_t)n * sizeof(double2), out_kind, stream));
+		LCG_CUDA_CHECK(cudaStreamSynchronize(stream));
+	}
+	if (info)
+	{
+		info->iterations = E.h_st->k_report; info->checks = E.h_st->checks; info->spmv_launches = E.spmv_launches;
+		info->kernel_launches = E.launches; info->residual = E.h_st->residual; info->device_ms = dev_ms; info->total_ms = now_ms() - t0;
+	}
+	return ret;
+}
+
+template <class F> int guarded(F&& f)
+{
+	try { return f(); }
+	catch (const ApiFailure& a) { return a.code; }
+	catch (const CudaFailure&) { return LCGB200_UNKNOWN_ERROR; }
+	catch (const std::exception& e) { set_error_msg(e.what()); return LCGB200_UNKNOWN_ERROR; }
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+const char* lcgb200_last_error(void) { return lcgb200::last_error(); }
+int lcgb200_version(void) { return 100; }
+void lcgb200_set_shadow_seed(long seed) { settings().shadow_seed = seed; }
+void lcgb200_set_complex_residual_mode(int mode) { settings().cres_mode = mode ? 1 : 0; }
+void lcgb200_set_poll_interval(int it) { settings().poll = it > 0 ? it : 1; }
+
+// sentinels: recognised by address, never executed on the fused path
+void lcgb200_csr_ax(void*, lcgb200_cublas_t, lcgb200_cusparse_t, lcgb200_dnvec_t, lcgb200_dnvec_t, const int, const int) {}
+void lcgb200_jacobi_mx(void*, lcgb200_cublas_t, lcgb200_cusparse_t, lcgb200_dnvec_t, lcgb200_dnvec_t, const int, const int) {}
+void lcgb200_csr_cax(void*, lcgb200_cublas_t, lcgb200_cusparse_t, lcgb200_dnvec_t, lcgb200_dnvec_t, const int, const int, int) {}
+void lcgb200_jacobi_cmx(void*, lcgb200_cublas_t, lcgb200_cusparse_t, lcgb200_dnvec_t, lcgb200_dnvec_t, const int, const int, int) {}
+
+int lcgb200_csr_create_rect(lcgb200_csr_t* out, int n_rows, int n_cols, int nnz, const int* row_ptr, const int* col,
+	const void* val, int value_type, int location, unsigned flags)
+{
+	if (!out) return LCGB200_INVALID_POINTER;
+	*out = nullptr;
+	if (n_rows <= 0 || n_cols < n_rows || nnz < 0) return LCGB200_INVILAD_VARIABLE_SIZE;
+	if (!row_ptr || (nnz > 0 && (!col || !val))) return LCGB200_INVALID_POINTER;
+	CsrHandle* h = new CsrHandle();
+	int rc = guarded([&]() {
+		h->value_type = value_type; h->n_rows = n_rows; h->n_cols = n_cols; h->nnz = nnz; h->n_global = n_rows; h->flags = flags;
+		LCG_CUDA_CHECK(cudaGetDevice(&h->device));
+		if (value_type == LCGB200_REAL) create_typed<double>(h, row_ptr, col, (const double*)val, location, kTileNnzReal);
+		else create_typed<double2>(h, row_ptr, col, (const double2*)val, location, kTileNnzCplx);
+		return 0;
+	});
+	if (rc != 0) { destroy_handle(h); return rc; }
+	*out = reinterpret_cast<lcgb200_csr_t>(h);
+	return 0;
+}
+
+int lcgb200_csr_create(lcgb200_csr_t* out, int n, int nnz, const int* row_ptr, const int* col, const void* val,
+	int value_type, int location, unsigned flags)
+{
+	return lcgb200_csr_create_rect(out, n, n, nnz, row_ptr, col, val, value_type, location, flags);
+}
+
+int lcgb200_csr_destroy(lcgb200_csr_t A) { destroy_handle(reinterpret_cast<CsrHandle*>(A)); return 0; }
+
+int lcgb200_csr_set_user(lcgb200_csr_t A, void* user)
+{
+	if (!A) return LCGB200_INVALID_POINTER;
+	reinterpret_cast<CsrHandle*>(A)->user = user; return 0;
+}
+
+int lcgb200_csr_get_diagonal(lcgb200_csr_t A, void* diag_host)
+{
+	CsrHandle* h = reinterpret_cast<CsrHandle*>(A);
+	if (!h || !diag_host) return LCGB200_INVALID_POINTER;
+	if (!h->diag) return LCGB200_NULL_PRECONDITION_MATRIX;
+	const size_t es = h->value_type == LCGB200_REAL ? sizeof(double) : sizeof(double2);
+	return guarded([&]() { LCG_CUDA_CHECK(cudaMemcpy(diag_host, h->diag, es * (size_t)h->n_rows, cudaMemcpyDeviceToHost)); return 0; });
+}
+
+int lcgb200_csr_info(lcgb200_csr_t A, int* n_rows, int* n_cols, int* nnz, int* n_tiles, int* lanes_per_row)
+{
+	CsrHandle* h = reinterpret_cast<CsrHandle*>(A);
+	if (!h) return LCGB200_INVALID_POINTER;
+	if (n_rows) *n_rows = h->n_rows; if (n_cols) *n_cols = h->n_cols; if (nnz) *nnz = h->nnz;
+	if (n_tiles) *n_tiles = h->n_tiles; if (lanes_per_row) *lanes_per_row = h->lpr;
+	return 0;
+}
+
+long long lcgb200_csr_spmv_bytes(lcgb200_csr_t A)
+{
+	CsrHandle* h = reinterpret_cast<CsrHandle*>(A);
+	if (!h) return 0;
+	const long long S = h->value_type == LCGB200_REAL ? 8 : 16;
+	return (long long)h->nnz * (S + 4) + ((long long)h->n_rows + 1) * 4 + 2LL * h->n_rows * S;
+}
+
+}  // extern "C"
+
+// ---- stand-alone SpMV launchers (tests / bench / ncu) ----------------------------------------------------
+namespace {
+
+// dots[0] = w.y, dots[1] = y.y, dots[2] = x.y
+struct EpiProbeReal {
+	static constexpr int NRED = 3;
+	static constexpr bool ACTIVE = true;
+	const double* w; double* out;
+	__device__ void begin(const DevState*) {}
+	__device__ void row(int i, double yi, double xi, double* acc) const
+	{
+		acc[0] = fma(w ? w[i] : xi, yi, acc[0]); acc[1] = fma(yi, yi, acc[1]); acc[2] = fma(xi, yi, acc[2]);
+	}
+	__device__ void finish(DevState*, const double* tot) const { out[0] = tot[0]; out[1] = tot[1]; out[2] = tot[2]; }
+};
+struct EpiProbeCplx {
+	static constexpr int NRED = 6;
+	static constexpr bool ACTIVE = true;
+	const double2* w; double* out;
+	__device__ void begin(const DevState*) {}
+	__device__ void row(int i, double2 yi, double2 xi, double* acc) const
+	{
+		double2 wi = w ? w[i] : xi;
+		acc[0] += wi.x * yi.x + wi.y * yi.y; acc[1] += wi.x * yi.y - wi.y * yi.x;
+		acc[2] += yi.x * yi.x + yi.y * yi.y;
+		acc[4] += xi.x * yi.x + xi.y * yi.y; acc[5] += xi.x * yi.y - xi.y * yi.x;
+	}
+	__device__ void finish(DevState*, const double* tot) const { for (int i = 0; i < 6; i++) out[i] = tot[i]; }
+};
+
+void ensure_state(CsrHandle* h, cudaStream_t s)
+{
+	Engine E(s, h);   // allocates the cached state block on first use
+	DevState init; std::memset(&init, 0, sizeof(init));
+	E.start(init);
+}
+
+}  // namespace
+
+extern "C" {
+
+int lcgb200_csr_spmv(lcgb200_csr_t A, const void* x, void* y, int op, void* stream)
+{
+	CsrHandle* h = reinterpret_cast<CsrHandle*>(A);
+	if (!h || !x || !y) return LCGB200_INVALID_POINTER;
+	if (op != 0 && !h->t_row_ptr) return LCGB200_NULL_PRECONDITION_MATRIX;
+	cudaStream_t s = (cudaStream_t)stream;
+	return guarded([&]() {
+		ensure_state(h, s);
+		if (h->value_type == LCGB200_REAL)
+		{
+			if (op == 0) launch_spmv<double, false>(h->view<double>(), (const double*)x, (double*)y, EpiNone<double>{}, h->d_state, h->d_partials, s);
+			else launch_spmv<double, false>(h->tview<double>(), (const double*)x, (double*)y, EpiNone<double>{}, h->d_state, h->d_partials, s);
+		}
+		else
+		{
+			if (op == 0) launch_spmv<double2, false>(h->view<double2>(), (const double2*)x, (double2*)y, EpiNone<double2>{}, h->d_state, h->d_partials, s);
+			else if (op == 1) launch_spmv<double2, false>(h->tview<double2>(), (const double2*)x, (double2*)y, EpiNone<double2>{}, h->d_state, h->d_partials, s);
+			else launch_spmv<double2, true>(h->tview<double2>(), (const double2*)x, (double2*)y, EpiNone<double2>{}, h->d_state, h->d_partials, s);
+		}
+		LCG_CUDA_CHECK(cudaGetLastError());
+		return 0;
+	});
+}
+
+int lcgb200_csr_spmv_dot(lcgb200_csr_t A, const void* x, void* y, const void* w, double* dots_dev, void* stream)
+{
+	CsrHandle* h = reinterpret_cast<CsrHandle*>(A);
+	if (!h || !x || !y || !dots_dev) return LCGB200_INVALID_POINTER;
+	cudaStream_t s = (cudaStream_t)stream;
+	return guarded([&]() {
+		ensure_state(h, s);
+		if (h->value_type == LCGB200_REAL)
+			launch_spmv<double, false>(h->view<double>(), (const double*)x, (double*)y, EpiProbeReal{(const double*)w, dots_dev}, h->d_state, h->d_partials, s);
+		else
+			launch_spmv<double2, false>(h->view<double2>(), (const double2*)x, (double2*)y, EpiProbeCplx{(const double2*)w, dots_dev}, h->d_state, h->d_partials, s);
+		LCG_CUDA_CHECK(cudaGetLastError());
+		return 0;
+	});
+}
+
+// ------------------------------------------------------------------------------------------ handle-shaped
+int lcgb200_solve(lcgb200_csr_t Ah, int solver_id, double* m, const double* B, const double* low, const double* hig,
+	const lcgb200_para* param, lcgb200_progress_cuda_ptr Pfp, unsigned flags, void* stream, lcgb200_info* info)
+{
+	CsrHandle* h = reinterpret_cast<CsrHandle*>(Ah);
+	if (!h) return LCGB200_INVALID_POINTER;
+	if (h->value_type != LCGB200_REAL) return LCGB200_SIZE_NOT_MATCH;
+	const lcgb200_para para = param ? *param : kDefPara;
+	if (solver_id < LCGB200_CG || solver_id > LCGB200_SPG) solver_id = LCGB200_CGS;	// lcg.cpp:76-78
+	int rc = check_real(solver_id, h->n_rows, para, m, B, low, hig);
+	if (rc) return rc;
+	if (solver_id == LCGB200_PCG && !((flags & LCGB200_USE_JACOBI) && h->diag)) return LCGB200_NULL_PRECONDITION_MATRIX;
+	return guarded([&]() {
+		Operator<double> A; A.h = h;
+		if (solver_id == LCGB200_PCG) A.diag = (const double*)h->diag;
+		auto make_pf = [&](const double* m_dev) -> ProgressFn {
+			if (!Pfp) return ProgressFn();
+			return [=](double res, int k) { return Pfp(h->user, m_dev, res, &para, h->n_rows, h->nnz, k); };
+		};
+		return do_solve_real(h, A, solver_id, m, B, low, hig, para, h->n_rows, h->n_cols, h->n_global, make_pf,
+			(flags & LCGB200_VEC_DEVICE) != 0, (cudaStream_t)stream, info);
+	});
+}
+
+int lcgb200_csolve(lcgb200_csr_t Ah, int solver_id, void* m, const void* B, const lcgb200_cpara* param,
+	lcgb200_cprogress_cuda_ptr Pfp, unsigned flags, void* stream, lcgb200_info* info)
+{
+	CsrHandle* h = reinterpret_cast<CsrHandle*>(Ah);
+	if (!h) return LCGB200_C_INVALID_POINTER;
+	if (h->value_type != LCGB200_COMPLEX) return LCGB200_C_SIZE_NOT_MATCH;
+	const lcgb200_cpara para = param ? *param : kDefCPara;
+	if (solver_id < LCGB200_CBICG || solver_id > LCGB200_CPCG) solver_id = LCGB200_CCGS;	// clcg.cpp:68-70
+	int rc = check_cplx(h->n_rows, para, m, B);
+	if (rc) return rc;
+	if (solver_id == LCGB200_CBICG && !h->t_row_ptr) { set_error_msg("CLCG_BICG needs the transposed operator: create the handle with LCGB200_CSR_TRANSPOSE"); return LCGB200_C_UNKNOWN_SOLVER; }
+	if (solver_id == LCGB200_CPCG && !((flags & LCGB200_USE_JACOBI) && h->diag)) return LCGB200_NULL_PRECONDITION_MATRIX;
+	return guarded([&]() {
+		Operator<double2> A; A.h = h;
+		if (solver_id == LCGB200_CPCG) A.diag = (const double2*)h->diag;
+		auto make_pf = [&](const double2* m_dev) -> ProgressFn {
+			if (!Pfp) return ProgressFn();
+			return [=](double res, int k) { return Pfp(h->user, m_dev, res, &para, h->n_rows, h->nnz, k); };
+		};
+		return do_solve_cplx(h, A, solver_id, (double2*)m, (const double2*)B, para, h->n_rows, h->n_cols, h->n_global, make_pf,
+			(flags & LCGB200_VEC_DEVICE) != 0, (cudaStream_t)stream, info);
+	});
+}
+
+// --------------------------------------------------------------------------------------- reference-shaped
+static int ref_real(lcgb200_axfunc_cuda_ptr Afp, lcgb200_axfunc_cuda_ptr Mfp, lcgb200_progress_cuda_ptr Pfp, double* m, const double* B,
+	const double* low, const double* hig, const int n, const int nz, const lcgb200_para* param, void* instance,
+	lcgb200_cublas_t cub, lcgb200_cusparse_t cus, int solver_id)
+{
+	const lcgb200_para para = param ? *param : kDefPara;
+	int rc = check_real(solver_id, n, para, m, B, low, hig);
+	if (rc) return rc;
+	const bool builtin = (Afp == lcgb200_csr_ax);
+	if (!builtin && (!cub || !cus)) return LCGB200_INVALID_POINTER;	// lcg_cuda.cu:97-98
+	if (!Afp) return LCGB200_INVALID_POINTER;
+	if (builtin)
+	{
+		CsrHandle* h = reinterpret_cast<CsrHandle*>(instance);
+		if (!h) return LCGB200_INVALID_POINTER;
+		if (h->value_type != LCGB200_REAL || h->n_rows != n) return LCGB200_SIZE_NOT_MATCH;
+		if (solver_id == LCGB200_PCG)
+		{
+			if (Mfp == lcgb200_jacobi_mx) { if (!h->diag) return LCGB200_NULL_PRECONDITION_MATRIX; }
+			else if (!Mfp) return LCGB200_INVALID_POINTER;
+		}
+		return guarded([&]() {
+			Operator<double> A; A.h = h;
+			DescrCache dc{n, 1, {}};
+			if (solver_id == LCGB200_PCG)
+			{
+				if (Mfp == lcgb200_jacobi_mx) A.diag = (const double*)h->diag;
+				else
+				{
+					if (!g_cusparse.load()) throw ApiFailure{LCGB200_UNKNOWN_ERROR};
+					A.precond = [&](const double* x, double* y, int) { Mfp(h->user, cub, cus, dc.get(x), dc.get(y), n, nz); };
+				}
+			}
+			auto make_pf = [&](const double* m_dev) -> ProgressFn {
+				if (!Pfp) return ProgressFn();
+				return [=](double res, int k) { return Pfp(h->user, m_dev, res, &para, n, nz, k); };
+			};
+			return do_solve_real(h, A, solver_id, m, B, low, hig, para, n, h->n_cols, h->n_global, make_pf, false, nullptr, nullptr);
+		});
+	}
+	if (solver_id == LCGB200_PCG && (!Mfp || Mfp == lcgb200_jacobi_mx)) return LCGB200_INVALID_POINTER;
+	return guarded([&]() {
+		if (!g_cusparse.load()) throw ApiFailure{LCGB200_UNKNOWN_ERROR};
+		DescrCache dc{n, 1, {}};
+		Operator<double> A;
+		A.apply = [&](const double* x, double* y, int) { Afp(instance, cub, cus, dc.get(x), dc.get(y), n, nz); };
+		if (solver_id == LCGB200_PCG) A.precond = [&](const double* x, double* y, int) { Mfp(instance, cub, cus, dc.get(x), dc.get(y), n, nz); };
+		auto make_pf = [&](const double* m_dev) -> ProgressFn {
+			if (!Pfp) return ProgressFn();
+			return [=](double res, int k) { return Pfp(instance, m_dev, res, &para, n, nz, k); };
+		};
+		return do_solve_real(nullptr, A, solver_id, m, B, low, hig, para, n, n, n, make_pf, false, nullptr, nullptr);
+	});
+}
+
+int lcgb200_solver_cuda(lcgb200_axfunc_cuda_ptr Afp, lcgb200_progress_cuda_ptr Pfp, double* m, const double* B,
+	const int n_size, const int nz_size, const lcgb200_para* param, void* instance,
+	lcgb200_cublas_t cub, lcgb200_cusparse_t cus, int solver_id)
+{
+	// lcg_cuda.cu:40-58: CG and CGS, anything else -> CG.  BICGSTAB / BICGSTAB2 are accepted as an extension.
+	int id = LCGB200_CG;
+	if (solver_id == LCGB200_CGS || solver_id == LCGB200_BICGSTAB || solver_id == LCGB200_BICGSTAB2) id = solver_id;
+	return ref_real(Afp, nullptr, Pfp, m, B, nullptr, nullptr, n_size, nz_size, param, instance, cub, cus, id);
+}
+
+int lcgb200_solver_preconditioned_cuda(lcgb200_axfunc_cuda_ptr Afp, lcgb200_axfunc_cuda_ptr Mfp, lcgb200_progress_cuda_ptr Pfp,
+	double* m, const double* B, const int n_size, const int nz_size, const lcgb200_para* param, void* instance,
+	lcgb200_cublas_t cub, lcgb200_cusparse_t cus, int)
+{
+	return ref_real(Afp, Mfp, Pfp, m, B, nullptr, nullptr, n_size, nz_size, param, instance, cub, cus, LCGB200_PCG);
+}
+
+int lcgb200_solver_constrained_cuda(lcgb200_axfunc_cuda_ptr Afp, lcgb200_progress_cuda_ptr Pfp, double* m, const double* B,
+	const double* low, const double* hig, const int n_size, const int nz_size, const lcgb200_para* param, void* instance,
+	lcgb200_cublas_t cub, lcgb200_cusparse_t cus, int solver_id)
+{
+	// lcg.cpp:126-137: PG and SPG, anything else -> PG (the reference's CUDA build only has the broken lpg)
+	const int id = (solver_id == LCGB200_SPG) ? LCGB200_SPG : LCGB200_PG;
+	return ref_real(Afp, nullptr, Pfp, m, B, low, hig, n_size, nz_size, param, instance, cub, cus, id);
+}
+
+static int ref_cplx(lcgb200_caxfunc_cuda_ptr Afp, lcgb200_caxfunc_cuda_ptr Mfp, lcgb200_cprogress_cuda_ptr Pfp, void* m, const void* B,
+	const int n, const int nz, const lcgb200_cpara* param, void* instance, lcgb200_cublas_t cub, lcgb200_cusparse_t cus, int solver_id)
+{
+	const lcgb200_cpara para = param ? *param : kDefCPara;
+	int rc = check_cplx(n, para, m, B);
+	if (rc) return rc;
+	const bool builtin = (Afp == lcgb200_csr_cax);
+	if (!builtin && (!cub || !cus)) return LCGB200_INVALID_POINTER;	// clcg_cuda.cu:100-101 (returns the LCG_ constant)
+	if (!Afp) return LCGB200_INVALID_POINTER;
+	if (builtin)
+	{
+		CsrHandle* h = reinterpret_cast<CsrHandle*>(instance);
+		if (!h) return LCGB200_INVALID_POINTER;
+		if (h->value_type != LCGB200_COMPLEX || h->n_rows != n) return LCGB200_C_SIZE_NOT_MATCH;
+		if (solver_id == LCGB200_CBICG && !h->t_row_ptr) { set_error_msg("CLCG_BICG needs LCGB200_CSR_TRANSPOSE"); return LCGB200_C_UNKNOWN_SOLVER; }
+		if (solver_id == LCGB200_CPCG)
+		{
+			if (Mfp == lcgb200_jacobi_cmx) { if (!h->diag) return LCGB200_NULL_PRECONDITION_MATRIX; }
+			else if (!Mfp) return LCGB200_INVALID_POINTER;
+		}
+		return guarded([&]() {
+			Operator<double2> A; A.h = h;
+			DescrCache dc{n, 5, {}};
+			if (solver_id == LCGB200_CPCG)
+			{
+				if (Mfp == lcgb200_jacobi_cmx) A.diag = (const double2*)h->diag;
+				else
+				{
+					if (!g_cusparse.load()) throw ApiFailure{LCGB200_UNKNOWN_ERROR};
+					A.precond = [&](const double2* x, double2* y, int) { Mfp(h->user, cub, cus, dc.get(x), dc.get(y), n, nz, 0); };
+				}
+			}
+			auto make_pf = [&](const double2* m_dev) -> ProgressFn {
+				if (!Pfp) return ProgressFn();
+				return [=](double res, int k) { return Pfp(h->user, m_dev, res, &para, n, nz, k); };
+			};
+			return do_solve_cplx(h, A, solver_id, (double2*)m, (const double2*)B, para, n, h->n_cols, h->n_global, make_pf, false, nullptr, nullptr);
+		});
+	}
+	if (solver_id == LCGB200_CPCG && (!Mfp || Mfp == lcgb200_jacobi_cmx)) return LCGB200_INVALID_POINTER;
+	return guarded([&]() {
+		if (!g_cusparse.load()) throw ApiFailure{LCGB200_UNKNOWN_ERROR};
+		DescrCache dc{n, 5, {}};
+		Operator<double2> A;
+		A.apply = [&](const double2* x, double2* y, int op) { Afp(instance, cub, cus, dc.get(x), dc.get(y), n, nz, op); };
+		if (solver_id == LCGB200_CPCG) A.precond = [&](const double2* x, double2* y, int) { Mfp(instance, cub, cus, dc.get(x), dc.get(y), n, nz, 0); };
+		auto make_pf = [&](const double2* m_dev) -> ProgressFn {
+			if (!Pfp) return ProgressFn();
+			return [=](double res, int k) { return Pfp(instance, m_dev, res, &para, n, nz, k); };
+		};
+		return do_solve_cplx(nullptr, A, solver_id, (double2*)m, (const double2*)B, para, n, n, n, make_pf, false, nullptr, nullptr);
+	});
+}
+
+int lcgb200_csolver_cuda(lcgb200_caxfunc_cuda_ptr Afp, lcgb200_cprogress_cuda_ptr Pfp, void* m, const void* B,
+	const int n_size, const int nz_size, const lcgb200_cpara* param, void* instance,
+	lcgb200_cublas_t cub, lcgb200_cusparse_t cus, int solver_id)
+{
+	// clcg_cuda.cu:42-60 knows BICG and BICG_SYM and returns CLCG_UNKNOWN_SOLVER otherwise; we add the three
+	// solvers the reference only has on the CPU (clcg.cpp:366-882).
+	switch (solver_id)
+	{
+		case LCGB200_CBICG: case LCGB200_CBICG_SYM: case LCGB200_CCGS: case LCGB200_CBICGSTAB: case LCGB200_CTFQMR: break;
+		default: return LCGB200_C_UNKNOWN_SOLVER;
+	}
+	return ref_cplx(Afp, nullptr, Pfp, m, B, n_size, nz_size, param, instance, cub, cus, solver_id);
+}
+
+int lcgb200_csolver_preconditioned_cuda(lcgb200_caxfunc_cuda_ptr Afp, lcgb200_caxfunc_cuda_ptr Mfp, lcgb200_cprogress_cuda_ptr Pfp,
+	void* m, const void* B, const int n_size, const int nz_size, const lcgb200_cpara* param, void* instance,
+	lcgb200_cublas_t cub, lcgb200_cusparse_t cus, int solver_id)
+{
+	if (solver_id != LCGB200_CPCG) return LCGB200_C_UNKNOWN_SOLVER;	// clcg_cuda.cu:75-83
+	return ref_cplx(Afp, Mfp, Pfp, m, B, n_size, nz_size, param, instance, cub, cus, LCGB200_CPCG);
+}
+
+}  // extern "C"

@@ -1,0 +1,327 @@
+// common.cuh — device state block, deterministic single-pass grid reduction, vector access helpers and the
+// generic fused "vector update + reductions + scalar epilogue" kernel every solver step is built from.
+//
+// Design: all iteration scalars (alpha, beta, omega, the squared norms, the iteration counter t,
+// the return code) live in ONE device-resident struct.  The last block of each kernel finishes the reduction in
+// a fixed order (run-to-run deterministic) and runs the step's scalar epilogue — including the reference's
+// loop-head control (lcg.cpp:206-230): residual, convergence test, max-iteration test, t++.  Once `done` is set
+// every later kernel of the solve returns immediately, so the host may enqueue iterations ahead of the
+// convergence test without ever applying an extra update to the solution.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cmath>
+
+namespace lcgb200 {
+
+constexpr int kThreads = 256;        // threads per block, all kernels
+constexpr int kMaxBlocks = 148 * 8;  // persistent grids: multiples of the 148 SMs of a B200
+constexpr int kMaxRed = 8;           // max reduction slots per kernel
+constexpr int kNumSc = 40;
+
+// return codes (reference util.h:69-90)
+enum : int {
+	RC_CONVERGENCE = 0, RC_STOP = 1, RC_ALREADY = 2, RC_UNKNOWN = -1024, RC_BAD_SIZE = -1023, RC_BAD_MAXIT = -1022,
+	RC_BAD_EPS = -1021, RC_BAD_RESTART = -1020, RC_MAXIT = -1019, RC_NULL_PRECOND = -1018, RC_NAN = -1017,
+	RC_BAD_PTR = -1016, RC_BAD_LAMBDA = -1015, RC_BAD_SIGMA = -1014, RC_BAD_BETA = -1013, RC_BAD_MAXIM = -1012,
+	RC_C_NAN = -1019, RC_C_BAD_PTR = -1018, RC_C_UNKNOWN_SOLVER = -1016
+};
+
+// scalar register file of a solve (indices into DevState::sc); complex values take two consecutive slots
+enum : int {
+	SC_MMOD = 0,     // max(m.m, 1)            (complex: max(|m|^4, 1))
+	SC_RMOD,         // squared residual norm  (complex: |r|^4)
+	SC_RHO,          // CG: g.g | PCG: z.r | CGS/BICGSTAB: r.r0~   (+1 imag)
+	SC_RHO_I,
+	SC_ALPHA,        // (+1 imag)
+	SC_ALPHA_I,
+	SC_BETA,
+	SC_BETA_I,
+	SC_OMEGA,
+	SC_OMEGA_I,
+	SC_TMP0, SC_TMP1, SC_TMP2, SC_TMP3, SC_TMP4, SC_TMP5,
+	SC_STEP,         // PG alpha_k / SPG lambda_k
+	SC_LS_ALPHA,     // SPG line-search alpha
+	SC_QK,           // SPG objective of the trial point
+	SC_GD,           // SPG g.d
+	SC_THETA, SC_TAO, SC_ETA, SC_ETA_I, SC_RKM, SC_RKM2,  // TFQMR
+	SC_PART0,        // partial sums carried between the halves of a split (callback-preconditioned) update
+	SC_PART1, SC_PART2, SC_PART3
+};
+
+struct DevState {
+	double sc[kNumSc];
+	double red[kMaxRed];      // totals of the last reduction (multi-GPU: all-reduced in place before finish)
+	double residual;          // value handed to the progress callback
+	double eps, restart_eps, sigma, ls_beta;
+	long long n_global;       // n of the whole system (the abs_diff test divides by it)
+	int abs_diff, max_it, cres_mode, multi;
+	int t;                    // the reference's iteration counter
+	int k_report;             // t at the last loop head (what Pfp receives)
+	int done, ret;
+	int checks;               // number of loop heads executed (host detects new heads by watching it)
+	int flag;                 // solver-specific (BICGSTAB2 half-step convergence, SPG line-search accept)
+	int half;                 // TFQMR half-step index / BICGSTAB2 restart marker
+	unsigned int ticket;
+	unsigned int pad;
+};
+
+__device__ __forceinline__ int st_done(const DevState* st) { return *((volatile const int*)&st->done); }
+
+// ---- reference loop head, real solvers (lcg.cpp:206-230) -------------------------------------------------
+__device__ __forceinline__ void loop_head_real(DevState* st, double sq_res, double m_mod)
+{
+	const double residual = st->abs_diff ? sqrt(sq_res) / (double)st->n_global : sq_res / m_mod;
+	st->residual = residual;
+	st->k_report = st->t;
+	st->checks++;
+	if (residual <= st->eps) { st->ret = RC_CONVERGENCE; st->done = 1; return; }
+	if (st->max_it > 0 && st->t + 1 > st->max_it) { st->ret = RC_MAXIT; st->done = 1; return; }
+	st->t++;
+}
+
+// "already optimised" test before the loop (lcg.cpp:185-203); falls through into the first loop head
+__device__ __forceinline__ void first_head_real(DevState* st, double sq_res, double m_mod)
+{
+	double r;
+	bool hit = false;
+	if (st->abs_diff && (r = sqrt(sq_res) / (double)st->n_global) <= st->eps) hit = true;
+	else if ((r = sq_res / m_mod) <= st->eps) hit = true;
+	if (hit) { st->residual = r; st->k_report = 0; st->checks++; st->ret = RC_ALREADY; st->done = 1; return; }
+	loop_head_real(st, sq_res, m_mod);
+}
+
+// ---- complex residual (clcg.cpp:112-147 CPU definition, or clcg_cuda.cu:145-176 when cres_mode = 1) -----
+// rr = ||r||^2, mm = ||m||^2 (plain real sums).  CPU: rk_square = |<r,r>|^2 = rr^2, m_square = max(mm^2, 1).
+__device__ __forceinline__ double cplx_res_abs(const DevState* st, double rr)
+{
+	if (st->cres_mode == 0) return sqrt(rr * rr) / (double)st->n_global;   // sqrt(rk_square)/n
+	return sqrt(rr) / (double)st->n_global;                                // rk_mod/n (nrm2)
+}
+__device__ __forceinline__ double cplx_res_rel(const DevState* st, double rr, double mm)
+{
+	if (st->cres_mode == 0) { double msq = mm * mm; if (msq < 1.0) msq = 1.0; return rr * rr / msq; }
+	double mn = sqrt(mm); if (mn < 1.0) mn = 1.0;
+	double rn = sqrt(rr);
+	return rn * rn / (mn * mn);
+}
+
+__device__ __forceinline__ void loop_head_cplx(DevState* st, double rr, double mm)
+{
+	const double residual = st->abs_diff ? cplx_res_abs(st, rr) : cplx_res_rel(st, rr, mm);
+	st->residual = residual;
+	st->k_report = st->t;
+	st->checks++;
+	if (residual <= st->eps) { st->ret = RC_CONVERGENCE; st->done = 1; return; }
+	if (st->max_it > 0 && st->t + 1 > st->max_it) { st->ret = RC_MAXIT; st->done = 1; return; }
+	st->t++;
+}
+
+// clcg.cpp:123-141: the relative test is also tried when abs_diff is set and the absolute one fails
+__device__ __forceinline__ void first_head_cplx(DevState* st, double rr, double mm)
+{
+	double r;
+	bool hit = false;
+	if (st->abs_diff && (r = cplx_res_abs(st, rr)) <= st->eps) hit = true;
+	else if ((r = cplx_res_rel(st, rr, mm)) <= st->eps) hit = true;
+	if (hit) { st->residual = r; st->k_report = 0; st->checks++; st->ret = RC_ALREADY; st->done = 1; return; }
+	loop_head_cplx(st, rr, mm);
+}
+
+// ---- complex arithmetic on double2 (x = re, y = im) ------------------------------------------------------
+typedef double2 zc;
+__device__ __forceinline__ zc zmk(double r, double i) { return make_double2(r, i); }
+__device__ __forceinline__ zc zadd(zc a, zc b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ zc zsub(zc a, zc b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ zc zmul(zc a, zc b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ zc zconj(zc a) { return make_double2(a.x, -a.y); }
+__device__ __forceinline__ zc zscale(double s, zc a) { return make_double2(s * a.x, s * a.y); }
+__device__ __forceinline__ double znorm2(zc a) { return a.x * a.x + a.y * a.y; }
+// Smith's algorithm, the same scaling strategy libgcc's __divdc3 uses for finite operands
+__device__ __forceinline__ zc zdiv(zc a, zc b)
+{
+	double ratio, denom, re, im;
+	if (fabs(b.x) < fabs(b.y)) { ratio = b.x / b.y; denom = b.x * ratio + b.y; re = (a.x * ratio + a.y) / denom; im = (a.y * ratio - a.x) / denom; }
+	else { ratio = b.y / b.x; denom = b.y * ratio + b.x; re = (a.y * ratio + a.x) / denom; im = (a.y - a.x * ratio) / denom; }
+	return make_double2(re, im);
+}
+__device__ __forceinline__ zc sc_ldz(const DevState* st, int i) { return make_double2(st->sc[i], st->sc[i + 1]); }
+__device__ __forceinline__ void sc_stz(DevState* st, int i, zc v) { st->sc[i] = v.x; st->sc[i + 1] = v.y; }
+
+// ---- streaming global access ------------------------------------------------------------------------------
+// matrix streams (read once): bypass L1 allocation so L1 stays available for the gathered x
+__device__ __forceinline__ int4 ldg_stream_i4(const int4* p)
+{
+	int4 r;
+	asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+	return r;
+}
+__device__ __forceinline__ double2 ldg_stream_d2(const double2* p)
+{
+	double2 r;
+	asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+	return r;
+}
+__device__ __forceinline__ double ld_cg(const double* p) { return __ldcg(p); }
+
+// W consecutive doubles as one access (W = 2 -> one 128-bit transaction)
+template <int W> struct DV { double v[W]; };
+template <int W> __device__ __forceinline__ DV<W> dv_load(const double* p);
+template <> __device__ __forceinline__ DV<1> dv_load<1>(const double* p) { DV<1> r; r.v[0] = *p; return r; }
+template <> __device__ __forceinline__ DV<2> dv_load<2>(const double* p)
+{
+	double2 t = *reinterpret_cast<const double2*>(p); DV<2> r; r.v[0] = t.x; r.v[1] = t.y; return r;
+}
+template <int W> __device__ __forceinline__ void dv_store(double* p, const DV<W>& a);
+template <> __device__ __forceinline__ void dv_store<1>(double* p, const DV<1>& a) { *p = a.v[0]; }
+template <> __device__ __forceinline__ void dv_store<2>(double* p, const DV<2>& a)
+{
+	*reinterpret_cast<double2*>(p) = make_double2(a.v[0], a.v[1]);
+}
+
+// ---- deterministic grid reduction -------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+
+// Block-reduce acc[0..NRED), publish per-block partials, elect the last block, and let it total the partials
+// in a fixed order.  Returns true in exactly one thread of the whole grid (thread 0 of the last block), with
+// tot[] holding the grid totals.  partials must hold gridDim.x * NRED doubles.
+template <int NRED>
+__device__ __forceinline__ bool grid_reduce(const double* acc, double* partials, unsigned int* ticket, double* tot)
+{
+	__shared__ double s_red[kMaxRed][kThreads / 32];
+	__shared__ int s_last;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+	for (int r = 0; r < NRED; r++)
+	{
+		double v = warp_sum(acc[r]);
+		if (lane == 0) s_red[r][warp] = v;
+	}
+	__syncthreads();
+	if (warp == 0)
+	{
+#pragma unroll
+		for (int r = 0; r < NRED; r++)
+		{
+			double v = (lane < kThreads / 32) ? s_red[r][lane] : 0.0;
+			v = warp_sum(v);
+			if (lane == 0) partials[(size_t)blockIdx.x * NRED + r] = v;
+		}
+	}
+	if (threadIdx.x == 0)
+	{
+		__threadfence();
+		unsigned int prev = atomicAdd(ticket, 1u);
+		s_last = (prev == gridDim.x - 1) ? 1 : 0;
+	}
+	__syncthreads();
+	if (!s_last) return false;
+	__threadfence();
+#pragma unroll
+	for (int r = 0; r < NRED; r++)
+	{
+		double v = 0.0;
+		for (int b = threadIdx.x; b < (int)gridDim.x; b += kThreads) v += ld_cg(partials + (size_t)b * NRED + r);
+		v = warp_sum(v);
+		if (lane == 0) s_red[r][warp] = v;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+#pragma unroll
+		for (int r = 0; r < NRED; r++)
+		{
+			double v = 0.0;
+#pragma unroll
+			for (int w = 0; w < kThreads / 32; w++) v += s_red[r][w];
+			tot[r] = v;
+		}
+		*ticket = 0u;
+		return true;
+	}
+	return false;
+}
+
+struct OpBase {
+	__device__ __forceinline__ bool active(const DevState*) const { return true; }
+	__device__ __forceinline__ void begin(const DevState*) {}
+	__device__ __forceinline__ void finish(DevState*, const double*) const {}
+};
+
+// ---- the generic fused vector kernel ----------------------------------------------------------------------
+// Op interface:
+//   static constexpr int NRED;      number of double reduction slots (0 = pure update, no grid reduction)
+//   static constexpr int W;         elements per access on the main path (2 for real vectors, 1 for complex)
+//   __device__ void begin(const DevState*);                       load scalars into the (kernel-local) op copy
+//   __device__ bool active(const DevState*);                      false -> the whole kernel is a no-op (OpBase: true)
+//   template<int V> __device__ void elem(size_t i, double* acc);  process V elements starting at i
+//   __device__ void finish(DevState*, const double* tot);         scalar epilogue (one thread of the grid)
+template <class Op>
+__global__ void __launch_bounds__(kThreads) k_vec(Op op_in, size_t n, DevState* st, double* partials)
+{
+	if (st_done(st)) return;
+	Op op = op_in;
+	if (!op.active(st)) return;
+	op.begin(st);
+	double acc[Op::NRED > 0 ? Op::NRED : 1];
+#pragma unroll
+	for (int r = 0; r < (Op::NRED > 0 ? Op::NRED : 1); r++) acc[r] = 0.0;
+	constexpr int W = Op::W;
+	const size_t npack = n / W;
+	const size_t stride = (size_t)gridDim.x * kThreads;
+	for (size_t p = (size_t)blockIdx.x * kThreads + threadIdx.x; p < npack; p += stride) op.template elem<W>(p * W, acc);
+	if (W > 1)
+	{
+		const size_t tail = npack * W + (size_t)blockIdx.x * kThreads + threadIdx.x;
+		if (tail < n) op.template elem<1>(tail, acc);
+	}
+	if (Op::NRED > 0)
+	{
+		double tot[Op::NRED > 0 ? Op::NRED : 1];
+		if (grid_reduce<(Op::NRED > 0 ? Op::NRED : 1)>(acc, partials, &st->ticket, tot))
+		{
+			if (st->multi) { for (int r = 0; r < Op::NRED; r++) st->red[r] = tot[r]; }
+			else op.finish(st, tot);
+		}
+	}
+}
+
+// multi-GPU: scalar epilogue after the totals in st->red have been all-reduced across ranks
+template <class Op>
+__global__ void k_finish(Op op_in, DevState* st)
+{
+	if (st_done(st)) return;
+	Op op = op_in;
+	if (!op.active(st)) return;
+	op.begin(st);
+	double tot[kMaxRed];
+	for (int r = 0; r < kMaxRed; r++) tot[r] = st->red[r];
+	op.finish(st, tot);
+}
+
+inline int vec_grid(size_t n, int w)
+{
+	size_t packs = (n + w - 1) / w;
+	size_t blocks = (packs + kThreads - 1) / kThreads;
+	if (blocks < 1) blocks = 1;
+	if (blocks > (size_t)kMaxBlocks) blocks = kMaxBlocks;
+	return (int)blocks;
+}
+
+#define LCG_CUDA_CHECK(call)                                                                        \
+	do {                                                                                            \
+		cudaError_t e__ = (call);                                                                   \
+		if (e__ != cudaSuccess) { lcgb200::set_error(#call, e__, __FILE__, __LINE__); throw lcgb200::CudaFailure(); } \
+	} while (0)
+
+struct CudaFailure {};
+void set_error(const char* what, cudaError_t e, const char* file, int line);
+void set_error_msg(const char* msg);
+
+}  // namespace lcgb200

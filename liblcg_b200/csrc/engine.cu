@@ -1,0 +1,179 @@
+// engine.cu — non-template parts of the solve engine (state upload/readback, host loop, error plumbing).
+#include "engine.cuh"
+#include <cstring>
+#include <string>
+#include <mutex>
+
+namespace lcgb200 {
+
+static thread_local std::string g_err;
+void set_error(const char* what, cudaError_t e, const char* file, int line)
+{
+	char buf[1024];
+	snprintf(buf, sizeof(buf), "%s failed: %s (%s:%d)", what, cudaGetErrorString(e), file, line);
+	g_err = buf;
+}
+void set_error_msg(const char* msg) { g_err = msg; }
+const char* last_error() { return g_err.c_str(); }
+
+Settings& settings() { static Settings s; return s; }
+
+Engine::Engine(cudaStream_t s, CsrHandle* h) : stream(s), cache(h)
+{
+	if (h)
+	{
+		comm = h->comm;
+		if (!h->d_state)
+		{
+			LCG_CUDA_CHECK(cudaMalloc(&h->d_state, sizeof(DevState)));
+			LCG_CUDA_CHECK(cudaMallocHost(&h->h_state, sizeof(DevState)));
+			LCG_CUDA_CHECK(cudaMallocHost(&h->h_state2, sizeof(DevState)));
+			LCG_CUDA_CHECK(cudaMalloc(&h->d_partials, sizeof(double) * kMaxBlocks * kMaxRed));
+			for (int i = 0; i < 4; i++) LCG_CUDA_CHECK(cudaEventCreate(&h->ev[i]));
+		}
+		d_st = h->d_state; h_st = h->h_state; h_st2 = h->h_state2; d_partials = h->d_partials;
+		for (int i = 0; i < 4; i++) ev[i] = h->ev[i];
+		ws = (char*)h->ws; ws_cap = h->ws_bytes;
+	}
+	else
+	{
+		own_state = true;
+		LCG_CUDA_CHECK(cudaMalloc(&d_st, sizeof(DevState)));
+		LCG_CUDA_CHECK(cudaMallocHost(&h_st, sizeof(DevState)));
+		LCG_CUDA_CHECK(cudaMallocHost(&h_st2, sizeof(DevState)));
+		LCG_CUDA_CHECK(cudaMalloc(&d_partials, sizeof(double) * kMaxBlocks * kMaxRed));
+		for (int i = 0; i < 4; i++) LCG_CUDA_CHECK(cudaEventCreate(&ev[i]));
+	}
+}
+
+Engine::~Engine()
+{
+	if (own_state)
+	{
+		cudaFree(d_st); cudaFreeHost(h_st); cudaFreeHost(h_st2); cudaFree(d_partials);
+		for (int i = 0; i < 4; i++) if (ev[i]) cudaEventDestroy(ev[i]);
+	}
+	if (own_ws && ws) cudaFree(ws);
+}
+
+void Engine::reserve(size_t bytes)
+{
+	bytes = (bytes + 255) & ~size_t(255);
+	ws_off = 0;
+	if (cache)
+	{
+		if (cache->ws_bytes < bytes)
+		{
+			if (cache->ws) { LCG_CUDA_CHECK(cudaFree(cache->ws)); cache->ws = nullptr; cache->ws_bytes = 0; }
+			LCG_CUDA_CHECK(cudaMalloc(&cache->ws, bytes));
+			cache->ws_bytes = bytes;
+		}
+		ws = (char*)cache->ws; ws_cap = cache->ws_bytes;
+	}
+	else
+	{
+		if (ws && own_ws) { cudaFree(ws); ws = nullptr; }
+		LCG_CUDA_CHECK(cudaMalloc((void**)&ws, bytes));
+		ws_cap = bytes; own_ws = true;
+	}
+}
+
+void Engine::start(const DevState& init)
+{
+	*h_st = init;
+	h_st->multi = multi() ? 1 : 0;
+	LCG_CUDA_CHECK(cudaMemcpyAsync(d_st, h_st, sizeof(DevState), cudaMemcpyHostToDevice, stream));
+	LCG_CUDA_CHECK(cudaEventRecord(ev[2], stream));
+	seen_checks = 0;
+	launches = 0; spmv_launches = 0;
+	final_ret = RC_UNKNOWN;
+}
+
+void Engine::read_state()
+{
+	LCG_CUDA_CHECK(cudaMemcpyAsync(h_st, d_st, sizeof(DevState), cudaMemcpyDeviceToHost, stream));
+	LCG_CUDA_CHECK(cudaStreamSynchronize(stream));
+}
+
+double Engine::device_ms()
+{
+	LCG_CUDA_CHECK(cudaEventRecord(ev[3], stream));
+	LCG_CUDA_CHECK(cudaEventSynchronize(ev[3]));
+	float ms = 0.f;
+	LCG_CUDA_CHECK(cudaEventElapsedTime(&ms, ev[2], ev[3]));
+	return (double)ms;
+}
+
+bool Engine::sync_always()
+{
+	read_state();
+	if (h_st->checks != seen_checks)
+	{
+		seen_checks = h_st->checks;
+		if (pf)
+		{
+			int stop = pf(h_st->residual, h_st->k_report);
+			// the "already optimised" call ignores the callback's return value (lcg.cpp:189-192)
+			if (stop && !(h_st->done && h_st->ret == RC_ALREADY)) { final_ret = RC_STOP; return true; }
+		}
+	}
+	if (h_st->done) { final_ret = h_st->ret; return true; }
+	return false;
+}
+
+bool Engine::sync_point()
+{
+	if (!pf) return false;
+	return sync_always();
+}
+
+int Engine::run(const std::function<bool()>& iterate)
+{
+	if (pf)
+	{	// one host round trip per loop head, exactly like the reference
+		while (true)
+		{
+			if (sync_always()) break;
+			if (iterate()) break;
+		}
+		LCG_CUDA_CHECK(cudaStreamSynchronize(stream));
+		return final_ret;
+	}
+	// No callback: enqueue `poll` iterations per batch, read the state back asynchronously, and look at the
+	// PREVIOUS batch's flag while the current one runs.  Kernels launched after `done` return immediately.
+	const int poll = settings().poll > 0 ? settings().poll : 1;
+	DevState* slot[2] = {h_st, h_st2};
+	bool pending[2] = {false, false};
+	int b = 0;
+	// the state after the init kernels (already optimised?)
+	LCG_CUDA_CHECK(cudaMemcpyAsync(slot[b], d_st, sizeof(DevState), cudaMemcpyDeviceToHost, stream));
+	LCG_CUDA_CHECK(cudaEventRecord(ev[b], stream));
+	pending[b] = true;
+	b ^= 1;
+	while (true)
+	{
+		bool ended = false;
+		for (int i = 0; i < poll && !ended; i++) ended = iterate();
+		if (ended) break;   // a host-driven step (SPG) saw the end itself
+		LCG_CUDA_CHECK(cudaMemcpyAsync(slot[b], d_st, sizeof(DevState), cudaMemcpyDeviceToHost, stream));
+		LCG_CUDA_CHECK(cudaEventRecord(ev[b], stream));
+		pending[b] = true;
+		const int o = b ^ 1;
+		if (pending[o])
+		{
+			LCG_CUDA_CHECK(cudaEventSynchronize(ev[o]));
+			pending[o] = false;
+			if (slot[o]->done) { final_ret = slot[o]->ret; break; }
+		}
+		b = o;
+	}
+	LCG_CUDA_CHECK(cudaStreamSynchronize(stream));
+	if (final_ret == RC_UNKNOWN || !pf)
+	{	// take the authoritative final state
+		LCG_CUDA_CHECK(cudaMemcpy(h_st, d_st, sizeof(DevState), cudaMemcpyDeviceToHost));
+		if (h_st->done) final_ret = h_st->ret;
+	}
+	return final_ret;
+}
+
+}  // namespace lcgb200

@@ -1,0 +1,159 @@
+// engine.cuh — host side of a solve: workspace, device state, kernel launch helpers, operator dispatch
+// (built-in CSR vs user callback) and the host loop that mirrors the reference's control flow
+// (lcg.cpp:206-230: Pfp -> converged? -> max iterations? -> t++ -> work) while keeping the scalars on the device.
+#pragma once
+#include <functional>
+#include <vector>
+#include <map>
+#include <chrono>
+#include "common.cuh"
+#include "csr.cuh"
+
+namespace lcgb200 {
+
+// ---- multi-GPU hooks (comm.cu) ---------------------------------------------------------------------------
+struct Comm {
+	virtual ~Comm() {}
+	virtual int rank() const = 0;
+	virtual int size() const = 0;
+	// sum-allreduce `count` doubles in place on the device, ordered on `s`
+	virtual void allreduce(double* dev, int count, cudaStream_t s) = 0;
+	// fill the ghost tail of an extended vector (elements [n_local, n_local + n_ghost)) from the owning ranks
+	virtual void halo(void* x_ext, int elem_bytes, cudaStream_t s) = 0;
+};
+
+// ---- handle behind lcgb200_csr_t ------------------------------------------------------------------------
+struct CsrHandle {
+	int value_type = 0;            // LCGB200_REAL / LCGB200_COMPLEX
+	int n_rows = 0, n_cols = 0, nnz = 0;
+	long long n_global = 0;        // rows of the whole (possibly partitioned) system
+	unsigned flags = 0;
+	int device = 0;
+	// device arrays (owned)
+	int* row_ptr = nullptr; int* col = nullptr; void* val = nullptr; int4* tiles = nullptr;
+	int n_tiles = 0, lpr = 1;
+	// transpose (optional)
+	int* t_row_ptr = nullptr; int* t_col = nullptr; void* t_val = nullptr; int4* t_tiles = nullptr;
+	int t_n_tiles = 0, t_lpr = 1;
+	void* diag = nullptr;          // Jacobi diagonal (optional), n_rows values
+	void* user = nullptr;          // instance handed to progress callbacks
+	Comm* comm = nullptr;          // set for a row block of a partitioned system
+	// cached workspace
+	void* ws = nullptr; size_t ws_bytes = 0;
+	DevState* d_state = nullptr; DevState* h_state = nullptr; DevState* h_state2 = nullptr; double* d_partials = nullptr;
+	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+
+	template <class T> CsrDev<T> view() const
+	{
+		CsrDev<T> v; v.n_rows = n_rows; v.n_cols = n_cols; v.nnz = nnz; v.n_tiles = n_tiles; v.lpr = lpr;
+		v.row_ptr = row_ptr; v.col = col; v.val = (const T*)val; v.tiles = tiles; return v;
+	}
+	template <class T> CsrDev<T> tview() const
+	{
+		CsrDev<T> v; v.n_rows = n_cols; v.n_cols = n_rows; v.nnz = nnz; v.n_tiles = t_n_tiles; v.lpr = t_lpr;
+		v.row_ptr = t_row_ptr; v.col = t_col; v.val = (const T*)t_val; v.tiles = t_tiles; return v;
+	}
+};
+
+// user-callback operator: y = op(A) x on raw device pointers (the API layer wraps descriptors around them)
+template <class T> using ApplyFn = std::function<void(const T* x, T* y, int op)>;
+// progress: (residual, k) -> nonzero to stop
+using ProgressFn = std::function<int(double, int)>;
+
+template <class T>
+struct Operator {
+	const CsrHandle* h = nullptr;   // built-in when non-null
+	ApplyFn<T> apply;               // otherwise
+	ApplyFn<T> precond;             // user M^-1 (generic path); empty when built-in Jacobi or none
+	const T* diag = nullptr;        // built-in Jacobi diagonal
+};
+
+struct Settings {
+	long shadow_seed = 0;
+	int cres_mode = 0;
+	int poll = 4;
+};
+Settings& settings();
+
+class Engine {
+public:
+	cudaStream_t stream = nullptr;
+	DevState* d_st = nullptr;
+	DevState* h_st = nullptr;     // pinned
+	DevState* h_st2 = nullptr;    // pinned (second poll slot)
+	double* d_partials = nullptr;
+	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+	Comm* comm = nullptr;
+	bool own_state = false;
+	int launches = 0, spmv_launches = 0;
+	ProgressFn pf;                 // empty = no progress callback
+	int seen_checks = 0;
+	int final_ret = RC_UNKNOWN;
+	// workspace arena
+	char* ws = nullptr; size_t ws_cap = 0, ws_off = 0; bool own_ws = false;
+	CsrHandle* cache = nullptr;    // handle whose cached buffers we borrow
+
+	Engine(cudaStream_t s, CsrHandle* h);
+	~Engine();
+
+	void reserve(size_t bytes);
+	template <class T> T* alloc(size_t count)
+	{
+		size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
+		if (ws_off + bytes > ws_cap) { set_error_msg("workspace overflow"); throw CudaFailure(); }
+		T* p = reinterpret_cast<T*>(ws + ws_off); ws_off += bytes; return p;
+	}
+
+	void start(const DevState& init);   // upload the initial state, record the start event
+	void read_state();                  // D2H of the state block + stream sync
+	double device_ms();                 // start..now on the stream (syncs)
+
+	bool multi() const { return comm != nullptr && comm->size() > 1; }
+
+	template <class Op> void vec(const Op& op, size_t n)
+	{
+		k_vec<Op><<<vec_grid(n, Op::W), kThreads, 0, stream>>>(op, n, d_st, d_partials);
+		launches++;
+		if (Op::NRED > 0 && multi()) finish_multi(op, Op::NRED);
+	}
+
+	template <class Op> void finish_multi(const Op& op, int nred)
+	{
+		comm->allreduce(reinterpret_cast<double*>(reinterpret_cast<char*>(d_st) + offsetof(DevState, red)), nred, stream);
+		k_finish<Op><<<1, 1, 0, stream>>>(op, d_st);
+		launches++;
+	}
+
+	// y = op(A) x with a fused per-row epilogue.  op: 0 = N, 1 = T, 2 = H.
+	template <class T, class Epi> void spmv(const Operator<T>& A, T* x, T* y, const Epi& epi, int op = 0)
+	{
+		if (A.h)
+		{
+			if (multi()) comm->halo(x, (int)sizeof(T), stream);
+			if (op == 0) launch_spmv<T, false, Epi>(A.h->template view<T>(), x, y, epi, d_st, d_partials, stream);
+			else if (op == 1) launch_spmv<T, false, Epi>(A.h->template tview<T>(), x, y, epi, d_st, d_partials, stream);
+			else launch_spmv<T, true, Epi>(A.h->template tview<T>(), x, y, epi, d_st, d_partials, stream);
+			launches++; spmv_launches++;
+			if (Epi::NRED > 0 && multi()) finish_multi(RowEpilogueOp<T, Epi>{epi, x, y}, Epi::NRED);
+		}
+		else
+		{
+			A.apply(x, y, op);
+			spmv_launches++;
+			if (Epi::ACTIVE) vec(RowEpilogueOp<T, Epi>{epi, x, y}, (size_t)n_local);
+		}
+	}
+
+	size_t n_local = 0;
+
+	// Pfp mode: read the state, deliver a new loop head to the callback.  Returns true when the solve is over
+	// (final_ret set).  Without a callback this is a no-op returning false (the device flags do the work).
+	bool sync_point();
+	// unconditional state read (SPG line search); returns true when the solve is over
+	bool sync_always();
+
+	// Host loop.  `iterate` enqueues one iteration and returns true if a sync point inside it ended the solve.
+	int run(const std::function<bool()>& iterate);
+};
+
+}  // namespace lcgb200

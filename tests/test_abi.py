@@ -1,0 +1,107 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads without a GPU and exports every symbol that
+include/lcgb200.h declares; parameter validation (which happens before any CUDA call) returns the reference's
+integers in the reference's order; the product package never touches the oracle."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "lcgb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = set(re.findall(r"\b(lcgb200_[a-z0-9_]+)\s*\(", src))
+    return sorted(names)
+
+
+def test_library_exports_every_declared_symbol():
+    from liblcg_b200 import _lib
+    lib = _lib.load()
+    names = header_functions()
+    assert len(names) >= 25
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/lcgb200.h but not exported"
+    # and the ctypes table covers the header (so tests call through typed prototypes)
+    assert set(names) == set(_lib.SYMBOLS), set(names) ^ set(_lib.SYMBOLS)
+
+
+def test_struct_layouts_match_reference():
+    from liblcg_b200._lib import LcgPara, ClcgPara
+    assert C.sizeof(LcgPara) == 64 and C.sizeof(ClcgPara) == 24     # util.h:95-148, 247-273
+    assert [getattr(LcgPara, f).offset for f, _ in LcgPara._fields_] == [0, 8, 16, 24, 32, 40, 48, 56]
+
+
+def test_validation_happens_before_any_gpu_work():
+    """Same order and integers as lcg_cuda.cu:91-98 / clcg_cuda.cu:94-101; none of these calls reaches CUDA."""
+    from liblcg_b200 import api
+    m = np.zeros(4)
+    b = np.ones(4)
+    P = api.lcg_default_parameters
+    fake = 0x1000  # non-null "instance"/handles: validation must fail before they are dereferenced
+    assert api.lcg_solver_cuda(api.CSR_AX, None, m, b, 0, 0, P(), fake) == api.LCG_INVILAD_VARIABLE_SIZE
+    assert api.lcg_solver_cuda(api.CSR_AX, None, m, b, 4, 0, P(max_iterations=-1), fake) == api.LCG_INVILAD_MAX_ITERATIONS
+    assert api.lcg_solver_cuda(api.CSR_AX, None, m, b, 4, 0, P(epsilon=0.0), fake) == api.LCG_INVILAD_EPSILON
+    assert api.lcg_solver_cuda(api.CSR_AX, None, m, b, 4, 0, P(epsilon=1.0), fake) == api.LCG_INVILAD_EPSILON
+    assert api.lcg_solver_cuda(api.CSR_AX, None, None, b, 4, 0, P(), fake) == api.LCG_INVALID_POINTER
+    assert api.lcg_solver_cuda(api.CSR_AX, None, m, None, 4, 0, P(), fake) == api.LCG_INVALID_POINTER
+    # a user callback (not the sentinel) with null cuBLAS/cuSPARSE handles -> LCG_INVALID_POINTER (lcg_cuda.cu:97-98)
+    user_cb = 0x2000
+    assert api.lcg_solver_cuda(user_cb, None, m, b, 4, 0, P(), None, None, None) == api.LCG_INVALID_POINTER
+    # constrained: lcg.cpp:1062-1070, 1232-1243
+    lo, hi = -np.ones(4), np.ones(4)
+    assert api.lcg_solver_constrained_cuda(api.CSR_AX, None, m, b, lo, hi, 4, 0, P(epsilon=1.0), fake) == api.LCG_INVALID_LAMBDA
+    assert api.lcg_solver_constrained_cuda(api.CSR_AX, None, m, b, lo, hi, 4, 0, P(step=0.0), fake) == api.LCG_INVALID_LAMBDA
+    assert api.lcg_solver_constrained_cuda(api.CSR_AX, None, m, b, None, hi, 4, 0, P(), fake) == api.LCG_INVALID_POINTER
+    assert api.lcg_solver_constrained_cuda(api.CSR_AX, None, m, b, lo, hi, 4, 0, P(sigma=1.0), fake, solver_id=api.LCG_SPG) == api.LCG_INVALID_SIGMA
+    assert api.lcg_solver_constrained_cuda(api.CSR_AX, None, m, b, lo, hi, 4, 0, P(beta=1.0), fake, solver_id=api.LCG_SPG) == api.LCG_INVALID_BETA
+    assert api.lcg_solver_constrained_cuda(api.CSR_AX, None, m, b, lo, hi, 4, 0, P(maxi_m=0), fake, solver_id=api.LCG_SPG) == api.LCG_INVALID_MAXIM
+    # BICGSTAB2's oddly placed epsilon test (lcg.cpp:821-822)
+    assert api.lcg_solver_cuda(api.CSR_AX, None, m, b, 4, 0, P(epsilon=1.0), fake, solver_id=api.LCG_BICGSTAB2) == api.LCG_INVILAD_RESTART_EPSILON
+    # complex
+    cm, cb = np.zeros(4, dtype=np.complex128), np.ones(4, dtype=np.complex128)
+    CP = api.clcg_default_parameters
+    assert api.clcg_solver_cuda(api.CSR_CAX, None, cm, cb, -1, 0, CP(), fake) == api.LCG_INVILAD_VARIABLE_SIZE
+    assert api.clcg_solver_cuda(api.CSR_CAX, None, cm, cb, 4, 0, CP(epsilon=2.0), fake) == api.LCG_INVILAD_EPSILON
+    assert api.clcg_solver_cuda(api.CSR_CAX, None, None, cb, 4, 0, CP(), fake) == api.CLCG_INVALID_POINTER
+    assert api.clcg_solver_cuda(api.CSR_CAX, None, cm, cb, 4, 0, CP(), fake, solver_id=api.CLCG_PCG) == api.CLCG_UNKNOWN_SOLVER
+    assert api.clcg_solver_preconditioned_cuda(api.CSR_CAX, api.JACOBI_CMX, None, cm, cb, 4, 0, CP(), fake, solver_id=api.CLCG_BICG) == api.CLCG_UNKNOWN_SOLVER
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under liblcg_b200/ may reference it (no CPU fallback)."""
+    pkg = os.path.join(ROOT, "liblcg_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if "build" in dirpath:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")) or f == "Makefile":
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "lcg_oracle" not in text and "pyoracle" not in text and "liblcg_ref" not in text, f
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from liblcg_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "SO_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(ImportError):
+        _lib.load()
+
+
+def test_no_gpu_means_error_not_fallback():
+    """Without a CUDA device the compute entry points must report an error code, never a result."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    from liblcg_b200 import api
+    rp = np.array([0, 1, 2], dtype=np.int32)
+    ci = np.array([0, 1], dtype=np.int32)
+    v = np.array([2.0, 2.0])
+    with pytest.raises(RuntimeError):
+        api.CsrOperator(rp, ci, v)

@@ -1,0 +1,417 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against the CPU oracle
+(oracle/lcg_oracle.c, pinned bit-for-bit to the reference) on the same inputs, and against the committed golden
+vectors generated from the unmodified reference.
+
+Tolerances (BASELINE.json north_star): identical return code; iteration count within max(1, 2 %) of the CPU
+solver; solution relative L2 difference <= 1e-8 in double precision — checked (a) after a pinned number of
+iterations (both sides stop on max_iterations, so the comparison does not depend on a threshold crossing) and
+(b) at convergence whenever both sides stopped at the same iteration.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from liblcg_b200 import api, stencil, io as lio
+
+pytestmark = pytest.mark.gpu
+
+REAL = ["CG", "PCG", "CGS", "BICGSTAB", "BICGSTAB2", "PG", "SPG"]
+CPLX = ["BICG", "BICG_SYM", "CGS", "BICGSTAB", "TFQMR"]
+SETTINGS = {"eps1e-6": dict(epsilon=1e-6), "eps1e-10": dict(epsilon=1e-10), "eps1e-6_abs": dict(epsilon=1e-6, abs_diff=1)}
+X_TOL = 1e-8          # solution rel-L2 tolerance (north_star)
+ITER_TOL = 0.02       # iteration-count tolerance (north_star)
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    torch.cuda.set_device(0)
+    return torch
+
+
+def rel(a, b):
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def iters_close(a, b):
+    return abs(a - b) <= max(1, int(np.ceil(ITER_TOL * b)))
+
+
+def to_dev(torch, a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def random_csr(rng, n, long_row=None, empty_every=0, cx=False):
+    """Ragged test matrix: row lengths 0..12, optional empty rows and one very long row (> one shared-memory tile)."""
+    lens = rng.integers(1, 13, size=n)
+    if empty_every:
+        lens[::empty_every] = 0
+    if long_row is not None:
+        lens[long_row[0]] = long_row[1]
+    rp = np.zeros(n + 1, dtype=np.int32)
+    np.cumsum(lens, out=rp[1:])
+    col = np.concatenate([np.sort(rng.choice(n, size=k, replace=False)) for k in lens if k > 0]).astype(np.int32)
+    val = rng.standard_normal(rp[-1])
+    if cx:
+        val = val + 1j * rng.standard_normal(rp[-1])
+    return dict(n=n, nnz=int(rp[-1]), row_ptr=rp, col=col, val=val)
+
+
+# ------------------------------------------------------------------------------------------------ SpMV
+@pytest.mark.parametrize("case", ["10K", "7pt", "27pt", "7pt_cd", "ragged", "ragged_long", "tiny"])
+def test_spmv_real_matches_oracle(torch_cuda, port, fixtures, case):
+    torch = torch_cuda
+    rng = np.random.default_rng(3)
+    if case == "10K":
+        A = fixtures["10K"]
+    elif case in stencil.KINDS:
+        A = stencil.make_system(case, 24 if case != "27pt" else 18)
+    elif case == "ragged":
+        A = random_csr(rng, 5000, empty_every=7)
+    elif case == "ragged_long":
+        A = random_csr(rng, 6000, long_row=(1234, 5000), empty_every=11)   # 5000 > 2048 staged non-zeros
+    else:
+        A = random_csr(rng, 3)
+    op = api.CsrOperator(A["row_ptr"], A["col"], A["val"])
+    x = rng.standard_normal(A["n"])
+    xd, yd = to_dev(torch, x), torch.empty(A["n"], dtype=torch.float64, device="cuda")
+    op.spmv(xd, yd)
+    torch.cuda.synchronize()
+    y_ref = port.spmv(A, x)
+    # same products, different summation order within a row: a few ulps of the row's magnitude
+    scale = port.spmv(dict(A, val=np.abs(A["val"])), np.abs(x)) + 1e-300
+    assert np.max(np.abs(yd.cpu().numpy() - y_ref) / scale) < 1e-14
+    # fused dots: w.y, y.y, x.y
+    w = rng.standard_normal(A["n"])
+    dots = torch.zeros(3, dtype=torch.float64, device="cuda")
+    op.spmv_dot(xd, yd, to_dev(torch, w), dots)
+    torch.cuda.synchronize()
+    d = dots.cpu().numpy()
+    ref = np.array([w @ y_ref, y_ref @ y_ref, x @ y_ref])
+    mag = np.array([np.abs(w) @ np.abs(y_ref), y_ref @ y_ref, np.abs(x) @ np.abs(y_ref)]) + 1e-300
+    assert np.max(np.abs(d - ref) / mag) < 1e-13
+    op.close()
+
+
+@pytest.mark.parametrize("opcode", [0, 1, 2])
+@pytest.mark.parametrize("case", ["10Kc", "ragged"])
+def test_spmv_complex_ops_match_oracle(torch_cuda, port, fixtures, case, opcode):
+    torch = torch_cuda
+    rng = np.random.default_rng(5)
+    A = fixtures["10Kc"] if case == "10Kc" else random_csr(rng, 4000, long_row=(17, 3000), empty_every=5, cx=True)
+    op = api.CsrOperator(A["row_ptr"], A["col"], A["val"], transpose=True)
+    x = rng.standard_normal(A["n"]) + 1j * rng.standard_normal(A["n"])
+    xd, yd = to_dev(torch, x), torch.empty(A["n"], dtype=torch.complex128, device="cuda")
+    op.spmv(xd, yd, op=opcode)
+    torch.cuda.synchronize()
+    y_ref = port.cspmv(A, x, transpose=opcode > 0, conjugate=opcode == 2)
+    scale = np.linalg.norm(y_ref) / np.sqrt(A["n"]) + 1e-300
+    assert np.max(np.abs(yd.cpu().numpy() - y_ref)) / scale < 1e-12
+    op.close()
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_device_stencil_generator_is_bit_exact(torch_cuda, kind):
+    torch = torch_cuda
+    from liblcg_b200 import _lib
+    lib = _lib.load()
+    g = 13
+    name = stencil.KINDS[kind]
+    for row0, row1 in ((0, g**3), (g * g * 3 + 5, g * g * 9 + 1)):
+        rp, ci, v = stencil.make_stencil(name, g, row0, row1)
+        nnz = C.c_longlong()
+        assert lib.lcgb200_gen_stencil(kind, g, row0, row1, None, None, None, 0, C.byref(nnz), None) == 0
+        assert nnz.value == len(ci)
+        drp = torch.empty(row1 - row0 + 1, dtype=torch.int32, device="cuda")
+        dci = torch.empty(nnz.value, dtype=torch.int32, device="cuda")
+        dv = torch.empty(nnz.value, dtype=torch.float64, device="cuda")
+        assert lib.lcgb200_gen_stencil(kind, g, row0, row1, drp.data_ptr(), dci.data_ptr(), dv.data_ptr(), 0, None, None) == 0
+        db = torch.empty(row1 - row0, dtype=torch.float64, device="cuda")
+        assert lib.lcgb200_gen_rhs(kind, g, row0, row1, db.data_ptr(), None) == 0
+        torch.cuda.synchronize()
+        assert np.array_equal(drp.cpu().numpy(), rp) and np.array_equal(dci.cpu().numpy(), ci) and np.array_equal(dv.cpu().numpy(), v)
+        full = stencil.make_system(name, g)
+        assert np.array_equal(db.cpu().numpy(), full["b"][row0:row1])
+
+
+# ------------------------------------------------------------------------------------------------ real solvers
+def gpu_real(A, sid, b, para, x0=None, low=None, hig=None, Pfp=None, op=None):
+    own = op is None
+    if own:
+        op = api.CsrOperator(A["row_ptr"], A["col"], A["val"], jacobi=True)
+    m = np.zeros(A["n"]) if x0 is None else np.array(x0, dtype=np.float64)
+    r = api.solve(op, sid, m, np.ascontiguousarray(b), low=low, hig=hig, param=para, Pfp=Pfp, jacobi=(sid == api.LCG_PCG))
+    if own:
+        op.close()
+    return r, m
+
+
+@pytest.mark.parametrize("setting", list(SETTINGS))
+@pytest.mark.parametrize("sid", range(7))
+def test_real_solvers_match_reference_counts(torch_cuda, golden, port, fixtures, setting, sid):
+    """config[0]: data/case_10K_A + case_10K_B (sample8.cu:133-145,241-243) under the three §8(c) settings."""
+    A = fixtures["10K"]
+    n = A["n"]
+    low, hig = np.full(n, -1e3), np.full(n, 1e3)
+    g = golden["real"][f"10K/{setting}/{REAL[sid]}"]
+    r, x = gpu_real(A, sid, A["b"], api.lcg_default_parameters(**SETTINGS[setting]), low=low, hig=hig)
+    assert r.ret == g["ret"], api.last_error()
+    assert iters_close(r.iterations, g["iters"]), (r.iterations, g["iters"])
+    if r.iterations == g["iters"]:
+        cpu = port.solve(sid, A, A["b"], para=po.default_para(**SETTINGS[setting]), low=low, hig=hig, diag=A["diag"])
+        assert rel(x, cpu.x) <= X_TOL
+        assert r.residual == pytest.approx(g["residual"], rel=1e-6)
+
+
+@pytest.mark.parametrize("k", [1, 10, 50])
+@pytest.mark.parametrize("sid", range(7))
+def test_real_solvers_pinned_iterations(torch_cuda, golden, port, fixtures, k, sid):
+    A = fixtures["10K"]
+    n = A["n"]
+    low, hig = np.full(n, -1e3), np.full(n, 1e3)
+    para = dict(epsilon=1e-300, max_iterations=k)
+    r, x = gpu_real(A, sid, A["b"], api.lcg_default_parameters(**para), low=low, hig=hig)
+    cpu = port.solve(sid, A, A["b"], para=po.default_para(**para), low=low, hig=hig, diag=A["diag"])
+    g = golden["real"][f"10K/maxit{k}/{REAL[sid]}"]
+    assert r.ret == cpu.ret == g["ret"] == api.LCG_REACHED_MAX_ITERATIONS
+    assert r.iterations == cpu.iters == k
+    assert rel(x, cpu.x) <= X_TOL
+    assert np.linalg.norm(x) == pytest.approx(g["xnorm"], rel=1e-8)
+    np.testing.assert_allclose(x[::golden["stride"]], g["xs"], rtol=1e-6, atol=1e-8 * g["xnorm"] / np.sqrt(n))
+    assert r.residual == pytest.approx(cpu.residual, rel=1e-7)
+
+
+@pytest.mark.parametrize("sid", [5, 6])
+def test_projected_solvers_with_active_box(torch_cuda, port, fixtures, sid):
+    A = fixtures["10K"]
+    n = A["n"]
+    low, hig = np.full(n, -10.0), np.full(n, 10.0)
+    para = dict(epsilon=1e-8, max_iterations=30)
+    r, x = gpu_real(A, sid, A["b"], api.lcg_default_parameters(**para), low=low, hig=hig)
+    cpu = port.solve(sid, A, A["b"], para=po.default_para(**para), low=low, hig=hig)
+    assert r.ret == cpu.ret and r.iterations == cpu.iters
+    assert np.all(x <= 10.0) and np.all(x >= -10.0)
+    assert np.array_equal(np.abs(x) == 10.0, np.abs(cpu.x) == 10.0)     # same active set
+    assert rel(x, cpu.x) <= 1e-7
+
+
+@pytest.mark.parametrize("sid", range(5))
+def test_warm_start_and_history(torch_cuda, port, fixtures, sid):
+    """Non-zero initial guess, progress callback called once per loop head with the reference's (k, residual)."""
+    A = fixtures["10K"]
+    rng = np.random.default_rng(11)
+    x0 = rng.standard_normal(A["n"])
+    para = dict(epsilon=1e-8, abs_diff=sid % 2, max_iterations=40)
+    hist = []
+
+    def Pfp(instance, m_dev, converge, param, n, nz, k):
+        hist.append((k, converge))
+        assert n == A["n"] and nz == A["nnz"] and param.epsilon == 1e-8
+        return 0
+
+    r, x = gpu_real(A, sid, A["b"], api.lcg_default_parameters(**para), x0=x0, Pfp=Pfp)
+    cpu = port.solve(sid, A, A["b"], x0=x0, para=po.default_para(**para), diag=A["diag"], hist_cap=256)
+    assert r.ret == cpu.ret and r.iterations == cpu.iters and len(hist) == cpu.calls
+    if not (sid == 4 and para["abs_diff"]):
+        assert [k for k, _ in hist] == list(range(cpu.calls))
+    np.testing.assert_allclose([c for _, c in hist], cpu.history, rtol=1e-6)
+    assert rel(x, cpu.x) <= X_TOL
+
+
+def test_progress_stop_and_already_optimised(torch_cuda, fixtures):
+    A = fixtures["10K"]
+    calls = []
+
+    def stop_at_5(instance, m_dev, converge, param, n, nz, k):
+        calls.append(k)
+        return 1 if k == 5 else 0
+
+    r, _ = gpu_real(A, api.LCG_CG, A["b"], api.lcg_default_parameters(), Pfp=stop_at_5)
+    assert r.ret == api.LCG_STOP and calls == [0, 1, 2, 3, 4, 5]
+    calls.clear()
+    r, x = gpu_real(A, api.LCG_CG, A["b"], api.lcg_default_parameters(), x0=A["answer"], Pfp=stop_at_5)
+    assert r.ret == api.LCG_ALREADY_OPTIMIZIED and calls == [0] and np.array_equal(x, A["answer"])
+    # without a callback: same results through the lazily polled path, for several poll intervals
+    for poll in (1, 3, 8):
+        api.set_poll_interval(poll)
+        r, _ = gpu_real(A, api.LCG_CG, A["b"], api.lcg_default_parameters())
+        assert r.ret == 0 and r.iterations == 59
+    api.set_poll_interval(4)
+
+
+def test_nan_is_reported(torch_cuda, fixtures):
+    A = fixtures["10K"]
+    b = A["b"].copy()
+    b[77] = np.nan
+    for sid in (0, 1, 2, 3):
+        r, _ = gpu_real(A, sid, b, api.lcg_default_parameters(max_iterations=20))
+        assert r.ret == api.LCG_NAN_VALUE
+
+
+@pytest.mark.parametrize("key", ["7pt/24/CG", "7pt/24/PCG", "7pt/24/CGS", "7pt/24/BICGSTAB", "27pt/16/CG", "27pt/16/PCG",
+                                 "7pt_cd/20/CGS", "7pt_cd/20/BICGSTAB", "7pt_cd/20/BICGSTAB2"])
+def test_stencil_solves_match_golden(torch_cuda, golden, port, key):
+    kind, g, name = key.split("/")
+    S = stencil.make_system(kind, int(g))
+    sid = REAL.index(name)
+    gd = golden["stencil"][key]
+    r, x = gpu_real(S, sid, S["b"], api.lcg_default_parameters(epsilon=1e-10))
+    assert r.ret == gd["ret"] and iters_close(r.iterations, gd["iters"])
+    if r.iterations == gd["iters"]:
+        assert np.linalg.norm(x) == pytest.approx(gd["xnorm"], rel=1e-8)
+    assert rel(x, S["x_star"]) < 1e-3
+
+
+@pytest.mark.parametrize("kind,g,sid", [("7pt", 64, 0), ("27pt", 48, 1), ("7pt_cd", 56, 3), ("7pt_cd", 56, 2)])
+def test_medium_stencils_against_cpu(torch_cuda, port, kind, g, sid):
+    """configs[2..4] at sizes the CPU oracle finishes in seconds."""
+    S = stencil.make_system(kind, g)
+    d = lio.csr_diagonal(S["row_ptr"], S["col"], S["val"])
+    para = dict(epsilon=1e-12)
+    r, x = gpu_real(S, sid, S["b"], api.lcg_default_parameters(**para))
+    cpu = port.solve(sid, S, S["b"], para=po.default_para(**para), diag=d)
+    assert r.ret == cpu.ret == 0
+    assert iters_close(r.iterations, cpu.iters), (r.iterations, cpu.iters)
+    pin = dict(epsilon=1e-300, max_iterations=25)
+    r2, x2 = gpu_real(S, sid, S["b"], api.lcg_default_parameters(**pin))
+    cpu2 = port.solve(sid, S, S["b"], para=po.default_para(**pin), diag=d)
+    assert r2.iterations == cpu2.iters == 25 and rel(x2, cpu2.x) <= X_TOL
+    if r.iterations == cpu.iters:
+        assert rel(x, cpu.x) <= X_TOL
+
+
+# ------------------------------------------------------------------------------- reference-shaped entry points
+def test_reference_shaped_calls_with_builtin_operator(torch_cuda, port, fixtures):
+    """The calls of sample8.cu:254,265,276 with lcgb200_csr_ax / lcgb200_jacobi_mx in place of cudaAx / cudaMx."""
+    A = fixtures["10K"]
+    n, nz = A["n"], A["nnz"]
+    op = api.CsrOperator(A["row_ptr"], A["col"], A["val"], jacobi=True)
+    assert np.array_equal(op.diagonal(), A["diag"])
+    para = api.lcg_default_parameters(epsilon=1e-10)
+    for sid, afunc in ((api.LCG_CG, api.lcg_solver_cuda), (api.LCG_CGS, api.lcg_solver_cuda)):
+        m = np.zeros(n)
+        ret = afunc(api.CSR_AX, None, m, A["b"], n, nz, para, op, solver_id=sid)
+        cpu = port.solve(sid, A, A["b"], para=po.default_para(epsilon=1e-10))
+        assert ret == 0 and rel(m, cpu.x) <= 1e-6   # both converged to the same threshold (not the same iterate)
+    # unknown id -> CG, like lcg_cuda.cu:52-54
+    m = np.zeros(n)
+    ks = []
+    ret = api.lcg_solver_cuda(api.CSR_AX, lambda i, md, c, p, nn, z, k: ks.append(k) or 0, m, A["b"], n, nz, para, op, solver_id=api.LCG_PG)
+    assert ret == 0 and ks[-1] == 100
+    m = np.zeros(n)
+    ret = api.lcg_solver_preconditioned_cuda(api.CSR_AX, api.JACOBI_MX, None, m, A["b"], n, nz, para, op)
+    cpu = port.solve(api.LCG_PCG, A, A["b"], para=po.default_para(epsilon=1e-10), diag=A["diag"])
+    assert ret == 0 and rel(m, cpu.x) <= 1e-6
+    low, hig = np.full(n, -1e3), np.full(n, 1e3)
+    m = np.zeros(n)
+    ret = api.lcg_solver_constrained_cuda(api.CSR_AX, None, m, A["b"], low, hig, n, nz, para, op, solver_id=api.LCG_PG)
+    cpu = port.solve(api.LCG_PG, A, A["b"], para=po.default_para(epsilon=1e-10), low=low, hig=hig)
+    assert ret == 0 and rel(m, cpu.x) <= 1e-6
+    # size mismatch between the handle and n_size
+    assert api.lcg_solver_cuda(api.CSR_AX, None, m, A["b"], n - 1, nz, para, op) == api.LCG_SIZE_NOT_MATCH
+    op.close()
+
+
+def test_device_resident_vectors(torch_cuda, port, fixtures):
+    torch = torch_cuda
+    A = fixtures["10K"]
+    op = api.CsrOperator(to_dev(torch, A["row_ptr"]), to_dev(torch, A["col"]), to_dev(torch, A["val"]), jacobi=True)
+    md = torch.zeros(A["n"], dtype=torch.float64, device="cuda")
+    bd = to_dev(torch, A["b"])
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        r = api.solve(op, api.LCG_PCG, md, bd, param=api.lcg_default_parameters(epsilon=1e-10), device=True, jacobi=True,
+                      stream=s.cuda_stream)
+    s.synchronize()
+    cpu = port.solve(api.LCG_PCG, A, A["b"], para=po.default_para(epsilon=1e-10), diag=A["diag"])
+    assert r.ret == 0 and iters_close(r.iterations, cpu.iters)
+    if r.iterations == cpu.iters:
+        assert rel(md.cpu().numpy(), cpu.x) <= X_TOL
+    assert r.info.kernel_launches > 0 and r.info.spmv_launches >= r.iterations
+    op.close()
+
+
+# ------------------------------------------------------------------------------------------------ complex
+def gpu_cplx(A, sid, b, para, Pfp=None, diag=False):
+    op = api.CsrOperator(A["row_ptr"], A["col"], A["val"], transpose=(sid == api.CLCG_BICG), jacobi=diag)
+    m = np.zeros(A["n"], dtype=np.complex128)
+    r = api.csolve(op, sid, m, np.ascontiguousarray(b), param=para, Pfp=Pfp, jacobi=diag)
+    op.close()
+    return r, m
+
+
+@pytest.mark.parametrize("fx,mode", [("10Kc", "abs"), ("10Kc", "rel"), ("1Kc", "abs")])
+@pytest.mark.parametrize("sid", range(5))
+def test_complex_solvers_match_reference_counts(torch_cuda, golden, port, fixtures, fx, mode, sid):
+    """config[1]: data/case_10K_cA + case_10K_cB (sample6.cpp:162-196 setting) and case_1K_cA (sample4.cpp:145-157)."""
+    g = golden["complex"][f"{fx}/{mode}/{CPLX[sid]}"]
+    Ac = fixtures[fx]
+    api.set_shadow_seed(golden["seed"])
+    para = dict(abs_diff=1 if mode == "abs" else 0)
+    r, x = gpu_cplx(Ac, sid, Ac["b"], api.clcg_default_parameters(**para))
+    assert r.ret == g["ret"], api.last_error()
+    if CPLX[sid] == "BICGSTAB":
+        # thousands of iterations of an erratic recurrence: rounding differences move the crossing; only sanity here
+        assert 0.5 * g["iters"] <= r.iterations <= 1.5 * g["iters"]
+    else:
+        assert iters_close(r.iterations, g["iters"]), (r.iterations, g["iters"])
+    assert rel(x, Ac["answer"]) < 5e-3
+
+
+@pytest.mark.parametrize("k", [1, 10, 50])
+@pytest.mark.parametrize("sid", range(5))
+def test_complex_solvers_pinned_iterations(torch_cuda, port, fixtures, k, sid):
+    Ac = fixtures["10Kc"]
+    api.set_shadow_seed(4242)
+    port.set_time(4242)
+    para = dict(epsilon=1e-300, max_iterations=k)
+    r, x = gpu_cplx(Ac, sid, Ac["b"], api.clcg_default_parameters(**para))
+    cpu = port.csolve(sid, Ac, Ac["b"], para=po.default_cpara(**para))
+    assert r.ret == cpu.ret == api.LCG_REACHED_MAX_ITERATIONS
+    assert r.iterations == cpu.iters == k
+    assert rel(x, cpu.x) <= X_TOL
+    assert r.residual == pytest.approx(cpu.residual, rel=1e-6)
+
+
+def test_complex_pcg_jacobi(torch_cuda, port, fixtures):
+    """config[1] PCG leg: complex Jacobi-PCG as in sample6.cpp:113-118,149-156 / sample10.cu:117,193."""
+    Ac = fixtures["10Kc"]
+    for para in (dict(abs_diff=1), dict(epsilon=1e-300, max_iterations=30)):
+        r, x = gpu_cplx(Ac, api.CLCG_PCG, Ac["b"], api.clcg_default_parameters(**para), diag=True)
+        cpu = port.csolve(po.CLCG_PCG, Ac, Ac["b"], diag=Ac["diag"], para=po.default_cpara(**para))
+        assert r.ret == cpu.ret and iters_close(r.iterations, cpu.iters)
+        if r.iterations == cpu.iters:
+            assert rel(x, cpu.x) <= X_TOL
+
+
+def test_complex_history_and_stop(torch_cuda, port, fixtures):
+    Ac = fixtures["1Kc"]
+    api.set_shadow_seed(99)
+    port.set_time(99)
+    for sid in (api.CLCG_BICG_SYM, api.CLCG_TFQMR):
+        hist = []
+        para = dict(epsilon=1e-300, max_iterations=24)
+        r, x = gpu_cplx(Ac, sid, Ac["b"], api.clcg_default_parameters(**para), Pfp=lambda i, m, c, p, n, nz, k: hist.append((k, c)) or 0)
+        cpu = port.csolve(sid, Ac, Ac["b"], para=po.default_cpara(**para), hist_cap=64)
+        assert len(hist) == cpu.calls and [k for k, _ in hist] == list(range(cpu.calls))
+        np.testing.assert_allclose([c for _, c in hist], cpu.history, rtol=1e-6)
+    r, _ = gpu_cplx(Ac, api.CLCG_BICG, Ac["b"], api.clcg_default_parameters(), Pfp=lambda i, m, c, p, n, nz, k: int(k == 3))
+    assert r.ret == api.LCG_STOP
+
+
+def test_complex_residual_mode_switch(torch_cuda, fixtures):
+    """Reference-CUDA residual definition (clcg_cuda.cu:145-176) behind a switch; default is the CPU definition."""
+    Ac = fixtures["1Kc"]
+    res = {}
+    for mode in (0, 1):
+        api.set_complex_residual_mode(mode)
+        got = []
+        gpu_cplx(Ac, api.CLCG_BICG_SYM, Ac["b"], api.clcg_default_parameters(epsilon=1e-300, max_iterations=3),
+                 Pfp=lambda i, m, c, p, n, nz, k: got.append(c) or 0)
+        res[mode] = got
+    api.set_complex_residual_mode(0)
+    # x0 = 0 -> max(|m|,1) = 1 at k = 0: CPU definition ||r||^4, CUDA definition ||r||^2
+    assert res[0][0] == pytest.approx(res[1][0] ** 2, rel=1e-12)
