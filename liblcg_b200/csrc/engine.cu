@@ -3,6 +3,7 @@
 #include <cstring>
 #include <string>
 #include <mutex>
+#include <cstdlib>
 
 namespace lcgb200 {
 
@@ -110,6 +111,11 @@ bool Engine::sync_always()
 	if (h_st->checks != seen_checks)
 	{
 		seen_checks = h_st->checks;
+		static const bool dbg = getenv("LCGB200_DEBUG_SCALARS") != nullptr;
+		if (dbg)
+			fprintf(stderr, "[lcgb200] k=%d res=%.6e rho=(%.6e,%.6e) alpha=(%.6e,%.6e) beta=(%.6e,%.6e) omega=(%.6e,%.6e) mm=%.6e rr=%.6e\n",
+				h_st->k_report, h_st->residual, h_st->sc[SC_RHO], h_st->sc[SC_RHO_I], h_st->sc[SC_ALPHA], h_st->sc[SC_ALPHA_I],
+				h_st->sc[SC_BETA], h_st->sc[SC_BETA_I], h_st->sc[SC_OMEGA], h_st->sc[SC_OMEGA_I], h_st->sc[SC_MMOD], h_st->sc[SC_RMOD]);
 		if (pf)
 		{
 			int stop = pf(h_st->residual, h_st->k_report);

@@ -46,7 +46,7 @@ def to_dev(torch, a):
 
 def random_csr(rng, n, long_row=None, empty_every=0, cx=False):
     """Ragged test matrix: row lengths 0..12, optional empty rows and one very long row (> one shared-memory tile)."""
-    lens = rng.integers(1, 13, size=n)
+    lens = rng.integers(1, min(13, n + 1), size=n)
     if empty_every:
         lens[::empty_every] = 0
     if long_row is not None:
