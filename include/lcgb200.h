@@ -165,6 +165,10 @@ typedef struct lcgb200_info {
 	double residual;       /* residual at the last check (the `converge` value of the callbacks) */
 	double device_ms;      /* CUDA-event time from the first to the last kernel of the solve */
 	double total_ms;       /* host wall time of the whole call, copies included */
+	/* filled when lcgb200_set_profile(1): CUDA-event time summed over the SpMV(+fused dot) launches and over the
+	 * fused vector kernels of this solve, and how many launches of each were timed */
+	double spmv_ms, vec_ms;
+	int spmv_timed, vec_timed;
 } lcgb200_info;
 
 enum {
@@ -190,6 +194,9 @@ void lcgb200_set_shadow_seed(long seed);
 void lcgb200_set_complex_residual_mode(int mode);
 /* iterations enqueued between two host polls of the device convergence flag when no progress callback is set */
 void lcgb200_set_poll_interval(int iterations);
+/* 1: bracket every kernel launch of a solve with CUDA events (per-kernel durations in lcgb200_info); costs a
+ * little throughput, so bench.py uses it only for its roofline pass */
+void lcgb200_set_profile(int on);
 const char* lcgb200_last_error(void);
 int lcgb200_version(void);
 /* device helpers used by tests / bench: fill CSR rows [row0,row1) of a g^3 stencil directly on the device.

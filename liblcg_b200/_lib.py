@@ -26,7 +26,8 @@ class ClcgPara(C.Structure):
 
 class Info(C.Structure):
     _fields_ = [("iterations", C.c_int), ("checks", C.c_int), ("spmv_launches", C.c_int), ("kernel_launches", C.c_int),
-                ("residual", C.c_double), ("device_ms", C.c_double), ("total_ms", C.c_double)]
+                ("residual", C.c_double), ("device_ms", C.c_double), ("total_ms", C.c_double),
+                ("spmv_ms", C.c_double), ("vec_ms", C.c_double), ("spmv_timed", C.c_int), ("vec_timed", C.c_int)]
 
 
 # callback prototypes (lcg_cuda.h:45-46,61-62; clcg_cuda.h:45-46,61-62)
@@ -61,6 +62,7 @@ SYMBOLS = {
     "lcgb200_set_shadow_seed": (None, [C.c_long]),
     "lcgb200_set_complex_residual_mode": (None, [_I]),
     "lcgb200_set_poll_interval": (None, [_I]),
+    "lcgb200_set_profile": (None, [_I]),
     "lcgb200_last_error": (C.c_char_p, []),
     "lcgb200_version": (_I, []),
     "lcgb200_gen_stencil": (_I, [_I, _I, _LL, _LL, _VP, _VP, _VP, _LL, C.POINTER(_LL), _VP]),

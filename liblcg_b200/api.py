@@ -82,6 +82,10 @@ def set_poll_interval(n: int) -> None:
     _lib.load().lcgb200_set_poll_interval(n)
 
 
+def set_profile(on: bool) -> None:
+    _lib.load().lcgb200_set_profile(1 if on else 0)
+
+
 def _ptr(a):
     """Raw address of a numpy array / torch tensor / int / None."""
     if a is None:

@@ -299,6 +299,8 @@ int do_solve_real(CsrHandle* h, Operator<double>& A, int solver_id, double* m, c
 	{
 		info->iterations = E.h_st->k_report; info->checks = E.h_st->checks; info->spmv_launches = E.spmv_launches;
 		info->kernel_launches = E.launches; info->residual = E.h_st->residual; info->device_ms = dev_ms; info->total_ms = now_ms() - t0;
+		double pms[2]; int pct[2]; E.prof_collect(pms, pct);
+		info->spmv_ms = pms[0]; info->vec_ms = pms[1]; info->spmv_timed = pct[0]; info->vec_timed = pct[1];
 	}
 	return ret;
 }
@@ -338,6 +340,8 @@ int do_solve_cplx(CsrHandle* h, Operator<double2>& A, int solver_id, double2* m,
 	{
 		info->iterations = E.h_st->k_report; info->checks = E.h_st->checks; info->spmv_launches = E.spmv_launches;
 		info->kernel_launches = E.launches; info->residual = E.h_st->residual; info->device_ms = dev_ms; info->total_ms = now_ms() - t0;
+		double pms[2]; int pct[2]; E.prof_collect(pms, pct);
+		info->spmv_ms = pms[0]; info->vec_ms = pms[1]; info->spmv_timed = pct[0]; info->vec_timed = pct[1];
 	}
 	return ret;
 }
@@ -360,6 +364,7 @@ int lcgb200_version(void) { return 100; }
 void lcgb200_set_shadow_seed(long seed) { settings().shadow_seed = seed; }
 void lcgb200_set_complex_residual_mode(int mode) { settings().cres_mode = mode ? 1 : 0; }
 void lcgb200_set_poll_interval(int it) { settings().poll = it > 0 ? it : 1; }
+void lcgb200_set_profile(int on) { settings().profile = on ? 1 : 0; }
 
 // sentinels: recognised by address, never executed on the fused path
 void lcgb200_csr_ax(void*, lcgb200_cublas_t, lcgb200_cusparse_t, lcgb200_dnvec_t, lcgb200_dnvec_t, const int, const int) {}

@@ -47,8 +47,34 @@ Engine::Engine(cudaStream_t s, CsrHandle* h) : stream(s), cache(h)
 	}
 }
 
+cudaEvent_t Engine::prof_begin(int cls)
+{
+	if (timed_used == timed.size())
+	{
+		if (timed.size() >= 8192) return nullptr;
+		Timed t; t.cls = cls;
+		if (cudaEventCreate(&t.a) != cudaSuccess || cudaEventCreate(&t.b) != cudaSuccess) return nullptr;
+		timed.push_back(t);
+	}
+	Timed& t = timed[timed_used++];
+	t.cls = cls;
+	cudaEventRecord(t.a, stream);
+	return t.b;
+}
+
+void Engine::prof_collect(double* ms, int* count)
+{
+	ms[0] = ms[1] = 0.0; count[0] = count[1] = 0;
+	for (size_t i = 0; i < timed_used; i++)
+	{
+		float e = 0.f;
+		if (cudaEventElapsedTime(&e, timed[i].a, timed[i].b) == cudaSuccess) { ms[timed[i].cls] += e; count[timed[i].cls]++; }
+	}
+}
+
 Engine::~Engine()
 {
+	for (auto& t : timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
 	if (own_state)
 	{
 		cudaFree(d_st); cudaFreeHost(h_st); cudaFreeHost(h_st2); cudaFree(d_partials);
@@ -87,6 +113,7 @@ void Engine::start(const DevState& init)
 	LCG_CUDA_CHECK(cudaEventRecord(ev[2], stream));
 	seen_checks = 0;
 	launches = 0; spmv_launches = 0;
+	profiling = settings().profile != 0; timed_used = 0;
 	final_ret = RC_UNKNOWN;
 }
 

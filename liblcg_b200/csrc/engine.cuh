@@ -72,6 +72,7 @@ struct Settings {
 	long shadow_seed = 0;
 	int cres_mode = 0;
 	int poll = 4;
+	int profile = 0;               // 1: bracket every kernel launch with CUDA events (bench roofline pass)
 };
 Settings& settings();
 
@@ -86,6 +87,13 @@ public:
 	Comm* comm = nullptr;
 	bool own_state = false;
 	int launches = 0, spmv_launches = 0;
+	// profile mode: event pairs around launches, class 0 = SpMV (+fused dots), 1 = fused vector kernels
+	struct Timed { cudaEvent_t a, b; int cls; };
+	std::vector<Timed> timed; size_t timed_used = 0;
+	bool profiling = false;
+	cudaEvent_t prof_begin(int cls);
+	void prof_end(cudaEvent_t e) { if (e) cudaEventRecord(e, stream); }
+	void prof_collect(double* ms, int* count);   // sums per class (2 entries each); call after a stream sync
 	ProgressFn pf;                 // empty = no progress callback
 	int seen_checks = 0;
 	int final_ret = RC_UNKNOWN;
@@ -112,7 +120,9 @@ public:
 
 	template <class Op> void vec(const Op& op, size_t n)
 	{
+		cudaEvent_t pe = profiling ? prof_begin(1) : nullptr;
 		k_vec<Op><<<vec_grid(n, Op::W), kThreads, 0, stream>>>(op, n, d_st, d_partials);
+		prof_end(pe);
 		launches++;
 		if (Op::NRED > 0 && multi()) finish_multi(op, Op::NRED);
 	}
@@ -130,9 +140,11 @@ public:
 		if (A.h)
 		{
 			if (multi()) comm->halo(x, (int)sizeof(T), stream);
+			cudaEvent_t pe = profiling ? prof_begin(0) : nullptr;
 			if (op == 0) launch_spmv<T, false, Epi>(A.h->template view<T>(), x, y, epi, d_st, d_partials, stream);
 			else if (op == 1) launch_spmv<T, false, Epi>(A.h->template tview<T>(), x, y, epi, d_st, d_partials, stream);
 			else launch_spmv<T, true, Epi>(A.h->template tview<T>(), x, y, epi, d_st, d_partials, stream);
+			prof_end(pe);
 			launches++; spmv_launches++;
 			if (Epi::NRED > 0 && multi()) finish_multi(RowEpilogueOp<T, Epi>{epi, x, y}, Epi::NRED);
 		}

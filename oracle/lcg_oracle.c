@@ -807,3 +807,60 @@ int lcgoracle_num_threads(void)
 	return 1;
 #endif
 }
+
+/* ================================================================ synthetic systems
+ * Host generator of the bench workloads for the CPU arms of bench.py (cpu_baseline, --impl reference): rows
+ * [row0,row1) of the g^3 7-point / 27-point Poisson or 7-point convection-diffusion matrix, columns ascending,
+ * Dirichlet truncation, and b = A x* with x*[i] = uint32(i*2654435761)/2^32 summed left to right.  Same
+ * definition as liblcg_b200/stencil.py (tests compare the two).  kind: 0 = 7pt, 1 = 27pt, 2 = 7pt_cd. */
+static int st_row(int kind, int g, long long row, long long* cols, double* vals)
+{
+	const long long gg = (long long)g * g;
+	const int x = (int)(row % g), y = (int)((row / g) % g), z = (int)(row / gg);
+	int cnt = 0;
+	if (kind == 1)
+	{
+		for (int dz = -1; dz <= 1; dz++) for (int dy = -1; dy <= 1; dy++) for (int dx = -1; dx <= 1; dx++)
+		{
+			const int zz = z + dz, yy = y + dy, xx = x + dx;
+			if (zz < 0 || zz >= g || yy < 0 || yy >= g || xx < 0 || xx >= g) continue;
+			cols[cnt] = ((long long)zz * g + yy) * g + xx;
+			vals[cnt] = (dz == 0 && dy == 0 && dx == 0) ? 26.0 : -1.0;
+			cnt++;
+		}
+		return cnt;
+	}
+	const double gx = kind == 2 ? 0.5 : 0.0, gy = kind == 2 ? 0.25 : 0.0, gz = kind == 2 ? 0.125 : 0.0;
+	if (z > 0) { cols[cnt] = row - gg; vals[cnt] = -1.0 - gz; cnt++; }
+	if (y > 0) { cols[cnt] = row - g; vals[cnt] = -1.0 - gy; cnt++; }
+	if (x > 0) { cols[cnt] = row - 1; vals[cnt] = -1.0 - gx; cnt++; }
+	cols[cnt] = row; vals[cnt] = 6.0; cnt++;
+	if (x < g - 1) { cols[cnt] = row + 1; vals[cnt] = -1.0 + gx; cnt++; }
+	if (y < g - 1) { cols[cnt] = row + g; vals[cnt] = -1.0 + gy; cnt++; }
+	if (z < g - 1) { cols[cnt] = row + gg; vals[cnt] = -1.0 + gz; cnt++; }
+	return cnt;
+}
+
+/* fills rp[0..rows] (and returns nnz); with ci/val/b non-null also the entries and the right-hand side */
+long long lcgoracle_gen_stencil(int kind, int g, long long row0, long long row1, int* rp, int* ci, double* val, double* b)
+{
+	const long long rows = row1 - row0;
+	long long cols[27]; double vals[27];
+	long long acc = 0;
+	for (long long r = 0; r < rows; r++) { rp[r] = (int)acc; acc += st_row(kind, g, row0 + r, cols, vals); }
+	rp[rows] = (int)acc;
+	if (!ci || !val) return acc;
+#pragma omp parallel for schedule(static) private(cols, vals)
+	for (long long r = 0; r < rows; r++)
+	{
+		const int c = st_row(kind, g, row0 + r, cols, vals);
+		double s = 0.0;
+		for (int j = 0; j < c; j++)
+		{
+			ci[rp[r] + j] = (int)cols[j]; val[rp[r] + j] = vals[j];
+			s += vals[j] * ((double)(unsigned int)((unsigned long long)cols[j] * 2654435761ull) / 4294967296.0);
+		}
+		if (b) b[r] = s;
+	}
+	return acc;
+}

@@ -161,3 +161,27 @@ class Oracle:
         args += [C.byref(para), C.c_int(int(progress)), C.c_int(stop_at), _p(hist, C.c_double), C.c_int(hist_cap), out, dout]
         ret = self._csolve(*args)
         return SolveResult(ret, out[0], out[1], dout[0], dout[1], x, hist[:min(out[1], hist_cap)].copy())
+
+
+_KINDS = {"7pt": 0, "27pt": 1, "7pt_cd": 2}
+
+
+def gen_system(kind: str, g: int, row0: int = 0, row1: int | None = None):
+    """Host (OpenMP) generator of the SURVEY §8(d) stencil systems — lcgoracle_gen_stencil in lcg_oracle.c.
+    Returns dict(n, nnz, row_ptr, col, val, b) for rows [row0,row1) with GLOBAL column indices."""
+    if not os.path.exists(PORT_SO):
+        build()
+    lib = C.CDLL(PORT_SO)
+    fn = lib.lcgoracle_gen_stencil
+    fn.restype = C.c_longlong
+    n = g ** 3
+    row1 = n if row1 is None else row1
+    rows = row1 - row0
+    rp = np.empty(rows + 1, dtype=np.int32)
+    k = C.c_int(_KINDS[kind])
+    nnz = fn(k, C.c_int(g), C.c_longlong(row0), C.c_longlong(row1), _p(rp, C.c_int), None, None, None)
+    ci = np.empty(nnz, dtype=np.int32)
+    val = np.empty(nnz, dtype=np.float64)
+    b = np.empty(rows, dtype=np.float64)
+    fn(k, C.c_int(g), C.c_longlong(row0), C.c_longlong(row1), _p(rp, C.c_int), _p(ci, C.c_int), _p(val, C.c_double), _p(b, C.c_double))
+    return dict(n=rows, nnz=int(nnz), row_ptr=rp, col=ci, val=val, b=b)
