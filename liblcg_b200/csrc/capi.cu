@@ -26,19 +26,39 @@ template <class T> T* dev_alloc(size_t count)
 	return p;
 }
 
+// lanes per row: the smallest power of two that leaves each lane at most ~7 entries of a mean-length row
 int pick_lpr(long long nnz, long long rows)
 {
 	const double avg = rows > 0 ? (double)nnz / (double)rows : 0.0;
-	if (avg <= 10.0) return 1;
-	if (avg <= 20.0) return 2;
-	if (avg <= 40.0) return 4;
-	if (avg <= 80.0) return 8;
-	if (avg <= 160.0) return 16;
-	return 32;
+	int lpr = 1;
+	while (lpr < 32 && avg > 7.0 * lpr) lpr *= 2;
+	return lpr;
 }
 
-// greedy row tiles: consecutive rows whose non-zeros, counted from the 4-aligned start, fit the staging buffer
-void build_tiles(const int* rp, int n_rows, int tile_nnz, std::vector<int4>& tiles)
+// rows per tile: a multiple of the block's row groups (kThreads / lpr) so that the compute phase of a typical
+// tile has no ragged last pass, as many multiples as the staging buffer holds at the mean row length
+int pick_tile_rows(long long nnz, long long rows, int lpr, int tile_nnz)
+{
+	const int ng = kThreads / lpr;
+	const double avg = rows > 0 ? (double)nnz / (double)rows : 1.0;
+	int passes = (int)((double)tile_nnz / (std::max(avg, 1.0) * ng));
+	if (passes < 1) passes = 1;
+	int cap = ng * passes;
+	if (cap > kTileRows) cap = (kTileRows / ng) * ng;
+	if (cap < 1) cap = kTileRows;
+	return cap;
+}
+
+// tiles per chunk: a CTA walks `chunk` consecutive tiles (~2048 rows) before jumping ahead by the grid stride
+int pick_chunk(int tile_rows)
+{
+	static const char* env = getenv("LCGB200_SPMV_CHUNK_ROWS");
+	const int target = env ? std::max(1, atoi(env)) : 2048;
+	return std::max(1, target / std::max(tile_rows, 1));
+}
+
+// greedy row tiles: consecutive rows (at most rows_cap) whose non-zeros, counted from the 4-aligned start, fit one stage
+void build_tiles(const int* rp, int n_rows, int tile_nnz, int rows_cap, std::vector<int4>& tiles)
 {
 	tiles.clear();
 	int r = 0;
@@ -46,7 +66,7 @@ void build_tiles(const int* rp, int n_rows, int tile_nnz, std::vector<int4>& til
 	{
 		const int k0 = rp[r] & ~3;
 		int r1 = r;
-		while (r1 < n_rows && r1 - r < kTileRows && rp[r1 + 1] - k0 <= tile_nnz) r1++;
+		while (r1 < n_rows && r1 - r < rows_cap && rp[r1 + 1] - k0 <= tile_nnz) r1++;
 		if (r1 == r) r1 = r + 1;   // a single row longer than the buffer: the kernel streams it from global memory
 		tiles.push_back(make_int4(r, r1, k0, rp[r1]));
 		r = r1;
@@ -86,7 +106,7 @@ constexpr int kPad = 16;   // elements of zero padding behind col/val so that 12
 
 template <class T>
 void upload_csr(int n_rows, int nnz, const int* rp_h, const int* ci, const T* v, bool src_device,
-	int** d_rp, int** d_ci, void** d_v, int4** d_tiles, int* n_tiles, int tile_nnz)
+	int** d_rp, int** d_ci, void** d_v, int4** d_tiles, int* n_tiles, int tile_nnz, int* lpr_out, int* chunk_out)
 {
 	*d_rp = dev_alloc<int>((size_t)n_rows + 1 + kPad);
 	*d_ci = dev_alloc<int>((size_t)nnz + kPad);
@@ -99,7 +119,10 @@ void upload_csr(int n_rows, int nnz, const int* rp_h, const int* ci, const T* v,
 	LCG_CUDA_CHECK(cudaMemcpy(*d_ci, ci, (size_t)nnz * sizeof(int), kind));
 	LCG_CUDA_CHECK(cudaMemcpy(dv, v, (size_t)nnz * sizeof(T), kind));
 	std::vector<int4> tiles;
-	build_tiles(rp_h, n_rows, tile_nnz, tiles);
+	const int lpr = pick_lpr(nnz, n_rows);
+	const int rows_cap = pick_tile_rows(nnz, n_rows, lpr, tile_nnz);
+	build_tiles(rp_h, n_rows, tile_nnz, rows_cap, tiles);
+	*lpr_out = lpr; *chunk_out = pick_chunk(rows_cap);
 	*n_tiles = (int)tiles.size();
 	*d_tiles = dev_alloc<int4>(tiles.size());
 	LCG_CUDA_CHECK(cudaMemcpy(*d_tiles, tiles.data(), tiles.size() * sizeof(int4), cudaMemcpyHostToDevice));
@@ -114,8 +137,7 @@ void create_typed(CsrHandle* h, const int* row_ptr, const int* col, const T* val
 	else std::memcpy(rp_h.data(), row_ptr, rp_h.size() * sizeof(int));
 	if (rp_h[0] != 0 || rp_h[(size_t)h->n_rows] != h->nnz) { set_error_msg("row_ptr[0] must be 0 and row_ptr[n] must equal nnz"); throw ApiFailure{LCGB200_SIZE_NOT_MATCH}; }
 	for (int i = 0; i < h->n_rows; i++) if (rp_h[(size_t)i + 1] < rp_h[(size_t)i]) { set_error_msg("row_ptr must be non-decreasing"); throw ApiFailure{LCGB200_SIZE_NOT_MATCH}; }
-	upload_csr<T>(h->n_rows, h->nnz, rp_h.data(), col, val, dev, &h->row_ptr, &h->col, &h->val, &h->tiles, &h->n_tiles, tile_nnz);
-	h->lpr = pick_lpr(h->nnz, h->n_rows);
+	upload_csr<T>(h->n_rows, h->nnz, rp_h.data(), col, val, dev, &h->row_ptr, &h->col, &h->val, &h->tiles, &h->n_tiles, tile_nnz, &h->lpr, &h->chunk);
 	if (h->flags & LCGB200_CSR_TRANSPOSE)
 	{
 		std::vector<int> ci_h; std::vector<T> v_h;
@@ -129,8 +151,7 @@ void create_typed(CsrHandle* h, const int* row_ptr, const int* col, const T* val
 		}
 		std::vector<int> trp, tci; std::vector<T> tv;
 		host_transpose<T>(h->n_rows, h->n_cols, rp_h.data(), cip, vp, trp, tci, tv);
-		upload_csr<T>(h->n_cols, h->nnz, trp.data(), tci.data(), tv.data(), false, &h->t_row_ptr, &h->t_col, &h->t_val, &h->t_tiles, &h->t_n_tiles, tile_nnz);
-		h->t_lpr = pick_lpr(h->nnz, h->n_cols);
+		upload_csr<T>(h->n_cols, h->nnz, trp.data(), tci.data(), tv.data(), false, &h->t_row_ptr, &h->t_col, &h->t_val, &h->t_tiles, &h->t_n_tiles, tile_nnz, &h->t_lpr, &h->t_chunk);
 	}
 	if (h->flags & LCGB200_CSR_JACOBI)
 	{

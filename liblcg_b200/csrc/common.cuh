@@ -18,6 +18,7 @@ namespace lcgb200 {
 constexpr int kThreads = 256;        // threads per block, all kernels
 constexpr int kMaxBlocks = 148 * 8;  // persistent grids: multiples of the 148 SMs of a B200
 constexpr int kMaxRed = 8;           // max reduction slots per kernel
+constexpr int kMaxWarps = 16;        // max warps per block of any kernel that uses grid_reduce
 constexpr int kNumSc = 40;
 
 // return codes (reference util.h:69-90)
@@ -189,14 +190,14 @@ __device__ __forceinline__ double warp_sum(double v)
 }
 
 // Block-reduce acc[0..NRED), publish per-block partials, elect the last block, and let it total the partials
-// in a fixed order.  Returns true in exactly one thread of the whole grid (thread 0 of the last block), with
+// in a fixed order (any block size that is a multiple of 32, up to kMaxWarps warps).  Returns true in exactly one thread of the whole grid (thread 0 of the last block), with
 // tot[] holding the grid totals.  partials must hold gridDim.x * NRED doubles.
 template <int NRED>
 __device__ __forceinline__ bool grid_reduce(const double* acc, double* partials, unsigned int* ticket, double* tot)
 {
-	__shared__ double s_red[kMaxRed][kThreads / 32];
+	__shared__ double s_red[kMaxRed][kMaxWarps];
 	__shared__ int s_last;
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (int)(blockDim.x >> 5);
 #pragma unroll
 	for (int r = 0; r < NRED; r++)
 	{
@@ -209,7 +210,7 @@ __device__ __forceinline__ bool grid_reduce(const double* acc, double* partials,
 #pragma unroll
 		for (int r = 0; r < NRED; r++)
 		{
-			double v = (lane < kThreads / 32) ? s_red[r][lane] : 0.0;
+			double v = (lane < nwarps) ? s_red[r][lane] : 0.0;
 			v = warp_sum(v);
 			if (lane == 0) partials[(size_t)blockIdx.x * NRED + r] = v;
 		}
@@ -227,7 +228,7 @@ __device__ __forceinline__ bool grid_reduce(const double* acc, double* partials,
 	for (int r = 0; r < NRED; r++)
 	{
 		double v = 0.0;
-		for (int b = threadIdx.x; b < (int)gridDim.x; b += kThreads) v += ld_cg(partials + (size_t)b * NRED + r);
+		for (int b = threadIdx.x; b < (int)gridDim.x; b += (int)blockDim.x) v += ld_cg(partials + (size_t)b * NRED + r);
 		v = warp_sum(v);
 		if (lane == 0) s_red[r][warp] = v;
 	}
@@ -238,8 +239,7 @@ __device__ __forceinline__ bool grid_reduce(const double* acc, double* partials,
 		for (int r = 0; r < NRED; r++)
 		{
 			double v = 0.0;
-#pragma unroll
-			for (int w = 0; w < kThreads / 32; w++) v += s_red[r][w];
+			for (int w = 0; w < nwarps; w++) v += s_red[r][w];
 			tot[r] = v;
 		}
 		*ticket = 0u;

@@ -4,28 +4,37 @@
 // Layout in HBM: int32 row_ptr[n+1], int32 col[nnz (+pad)], T val[nnz (+pad)], base 0, rows in
 // order — exactly the arrays the reference's samples hand to cusparseCreateCsr (sample8.cu:172-173) — plus one
 // int4 {row_begin, row_end, nnz_begin_aligned, nnz_end} per row tile.  A tile is a run of consecutive rows
-// whose non-zeros (from the 4-aligned start) fit the shared-memory staging buffer.
+// whose non-zeros (from the 4-aligned start) fit one shared-memory stage; the tile builder caps the row count
+// at a multiple of the row groups of a block so that the compute phase has no ragged last pass.
 //
-// Kernel: a persistent grid (multiple of 148 SMs) walks the tiles round-robin, so that at any moment all CTAs
-// work inside one narrow band of rows and the gathered x / written y of that band stay L2-resident.  Per tile:
-//   phase 1  col/val of the tile are streamed HBM -> shared memory with 128-bit coalesced loads that do not
-//            allocate in L1 (the matrix is read exactly once);
-//   phase 2  LPR lanes per row (1..32, picked from the mean row length) walk their row out of shared memory
-//            and gather x[col] through L1/L2; lanes of a warp sit on consecutive rows, so for banded/stencil
-//            matrices a warp-wide gather touches 2-3 lines instead of ~10;
-//   epilogue the row result feeds the fused reductions (p.Ap, r0~.Ap, As.s, As.As, ...) without re-reading y.
+// Kernel (sm_100a): a persistent grid (2 CTAs x 148 SMs), warp-specialised.
+//   producer  one elected thread of an extra warp streams the tile's col / val / row_ptr slices HBM -> shared
+//             memory with TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx, L2 evict-first hint: the
+//             matrix is read exactly once per SpMV and must not push the vectors out of L2) into a ring of
+//             kStages stages, running up to kStages-1 tiles ahead of the consumers;
+//   consumers 8 warps wait on the stage's "full" mbarrier, LPR lanes per row (1..32, picked from the mean row
+//             length) walk their row out of shared memory and gather x[col] through L1/L2 (lanes of a warp sit
+//             on consecutive rows, so for banded/stencil matrices a warp-wide gather touches 2-3 lines), then
+//             release the stage through its "empty" mbarrier.  No block-wide barrier in the steady state.
+//   epilogue  the row result feeds the fused reductions (p.Ap, r0~.Ap, As.s, As.As, ...) without re-reading y.
+// Tiles are dealt to CTAs in chunks of consecutive tiles: inside a chunk the gathered x of neighbouring rows is
+// re-used out of L1, and at any moment all CTAs work inside one band of rows, so the band's x stays L2-resident.
 #pragma once
 #include "common.cuh"
 
 namespace lcgb200 {
 
 constexpr int kTileNnzReal = 2048;   // staged non-zeros per tile: 16 KB val + 8 KB col
-constexpr int kTileNnzCplx = 2048;   // 32 KB val + 8 KB col
-constexpr int kTileRows = 1024;      // max rows per tile (bounds the row_ptr slice in shared memory)
+constexpr int kTileNnzCplx = 1024;   // 16 KB val + 4 KB col
+constexpr int kTileRows = 512;       // max rows per tile (bounds the row_ptr slice in shared memory)
+constexpr int kStages = 3;           // shared-memory ring depth (2 CTAs x 3 stages leave ~70 KB of L1 for the gathered x)
+constexpr int kGatherUnroll = 8;     // row entries per lane whose loads are issued back to back
+constexpr int kSpmvThreads = kThreads + 32;   // 8 consumer warps + 1 producer warp
+constexpr int kSpmvCtasPerSm = 2;
 
 template <class T>
 struct CsrDev {
-	int n_rows = 0, n_cols = 0, nnz = 0, n_tiles = 0, lpr = 1;
+	int n_rows = 0, n_cols = 0, nnz = 0, n_tiles = 0, lpr = 1, chunk = 1;
 	const int* row_ptr = nullptr;
 	const int* col = nullptr;
 	const T* val = nullptr;
@@ -35,6 +44,16 @@ struct CsrDev {
 template <class T> struct TileCfg;
 template <> struct TileCfg<double> { static constexpr int NNZ = kTileNnzReal; };
 template <> struct TileCfg<double2> { static constexpr int NNZ = kTileNnzCplx; };
+
+// shared-memory stage layout (bytes): val | col | row_ptr slice
+template <class T> struct StageCfg {
+	static constexpr int NNZ = TileCfg<T>::NNZ;
+	static constexpr int VAL_OFF = 0;
+	static constexpr int COL_OFF = NNZ * (int)sizeof(T);
+	static constexpr int ROW_OFF = COL_OFF + NNZ * 4;
+	static constexpr int BYTES = (ROW_OFF + (kTileRows + 8) * 4 + 127) & ~127;
+	static constexpr int TOTAL = BYTES * kStages;
+};
 
 __device__ __forceinline__ double mulacc(double acc, double a, double x) { return fma(a, x, acc); }
 __device__ __forceinline__ double2 mulacc(double2 acc, double2 a, double2 x)
@@ -57,24 +76,44 @@ __device__ __forceinline__ double2 tshfl_xor(double2 v, int o)
 __device__ __forceinline__ double tldg(const double* p) { return __ldg(p); }
 __device__ __forceinline__ double2 tldg(const double2* p) { return __ldg(p); }
 
-// stage 4 consecutive non-zeros (k is a multiple of 4) into shared memory
-__device__ __forceinline__ void stage4(const int* col, const double* val, int k, int* scol, double* sval, int s)
+// ---- mbarrier / TMA bulk-copy primitives (PTX ISA: mbarrier, cp.async.bulk) ---------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
-	int4 c = ldg_stream_i4(reinterpret_cast<const int4*>(col + k));
-	double2 v0 = ldg_stream_d2(reinterpret_cast<const double2*>(val + k));
-	double2 v1 = ldg_stream_d2(reinterpret_cast<const double2*>(val + k + 2));
-	*reinterpret_cast<int4*>(scol + s) = c;
-	*reinterpret_cast<double2*>(sval + s) = v0;
-	*reinterpret_cast<double2*>(sval + s + 2) = v1;
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void stage4(const int* col, const double2* val, int k, int* scol, double2* sval, int s)
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
-	int4 c = ldg_stream_i4(reinterpret_cast<const int4*>(col + k));
-	double2 v0 = ldg_stream_d2(val + k), v1 = ldg_stream_d2(val + k + 1);
-	double2 v2 = ldg_stream_d2(val + k + 2), v3 = ldg_stream_d2(val + k + 3);
-	*reinterpret_cast<int4*>(scol + s) = c;
-	sval[s] = v0; sval[s + 1] = v1; sval[s + 2] = v2; sval[s + 3] = v3;
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+	uint32_t ok;
+	do
+	{
+		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+			: "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+	} while (!ok);
+}
+__device__ __forceinline__ uint64_t l2_evict_first_policy()
+{
+	uint64_t pol;
+	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+	return pol;
+}
+// global -> shared bulk copy, completion counted in bytes on `bar`; dst/src 16-byte aligned, bytes % 16 == 0
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+		:: "r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
+// consumer-only barrier (the producer warp never joins it)
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" :: "n"(kThreads) : "memory"); }
 
 // Epi interface:
 //   static constexpr int NRED;
@@ -82,77 +121,143 @@ __device__ __forceinline__ void stage4(const int* col, const double2* val, int k
 //   __device__ void row(int i, T yi, T xi, double* acc);   called once per row by one lane (may write vectors)
 //   __device__ void finish(DevState*, const double* tot);
 template <class T, int LPR, bool CONJ, class Epi>
-__global__ void __launch_bounds__(kThreads) k_spmv(CsrDev<T> A, const T* __restrict__ x, T* __restrict__ y, Epi epi_in,
+__global__ void __launch_bounds__(kSpmvThreads, kSpmvCtasPerSm) k_spmv(CsrDev<T> A, const T* __restrict__ x, T* __restrict__ y, Epi epi_in,
 	DevState* st, double* partials)
 {
 	if (st_done(st)) return;
-	constexpr int TN = TileCfg<T>::NNZ;
-	__shared__ __align__(16) T sval[TN + 8];
-	__shared__ __align__(16) int scol[TN + 8];
-	__shared__ int srow[kTileRows + 1];
+	typedef StageCfg<T> SC;
+	constexpr int TN = SC::NNZ;
+	extern __shared__ __align__(128) unsigned char smem[];
+	__shared__ __align__(8) unsigned long long s_bar[2 * kStages];   // [0,S) full, [S,2S) empty
 	__shared__ T s_long[kThreads / 32];
 
+	const int tid = threadIdx.x;
+	const bool producer = tid >= kThreads;
+	if (tid == 0)
+	{
+		for (int s = 0; s < kStages; s++) { mbar_init(smem_u32(&s_bar[s]), 1); mbar_init(smem_u32(&s_bar[kStages + s]), kThreads / 32); }
+		mbar_fence_init();
+	}
+	__syncthreads();
+
 	Epi epi = epi_in;
-	epi.begin(st);
 	double acc[Epi::NRED > 0 ? Epi::NRED : 1];
 #pragma unroll
 	for (int r = 0; r < (Epi::NRED > 0 ? Epi::NRED : 1); r++) acc[r] = 0.0;
 
-	constexpr int NG = kThreads / LPR;          // row groups per block
-	const int group = threadIdx.x / LPR, lane = threadIdx.x % LPR;
+	const int n_chunks = (A.n_tiles + A.chunk - 1) / A.chunk;
 
-	for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x)
+	if (producer)
 	{
-		const int4 td = A.tiles[tile];
-		const int r0 = td.x, nrows = td.y - td.x, k0 = td.z, k1 = td.w;
-		if (k1 - k0 > TN)
-		{	// one row longer than the staging buffer: stream it straight from global memory
-			T part = tzero(T());
-			for (int k = A.row_ptr[r0] + threadIdx.x; k < k1; k += kThreads)
-			{
-				T a = A.val[k]; if (CONJ) a = tconj(a);
-				part = mulacc(part, a, tldg(x + A.col[k]));
-			}
-#pragma unroll
-			for (int o = 16; o > 0; o >>= 1) part = tadd(part, tshfl_xor(part, o));
-			if ((threadIdx.x & 31) == 0) s_long[threadIdx.x >> 5] = part;
-			__syncthreads();
-			if (threadIdx.x == 0)
-			{
-				T tot = s_long[0];
-				for (int w = 1; w < kThreads / 32; w++) tot = tadd(tot, s_long[w]);
-				y[r0] = tot;
-				epi.row(r0, tot, tldg(x + r0), acc);
-			}
-			__syncthreads();
-			continue;
-		}
-		// phase 1: stage the tile
-		for (int i = threadIdx.x; i <= nrows; i += kThreads) srow[i] = A.row_ptr[r0 + i] - k0;
-		for (int k = k0 + 4 * threadIdx.x; k < k1; k += 4 * kThreads) stage4(A.col, A.val, k, scol, sval, k - k0);
-		__syncthreads();
-		// phase 2: rows
-		for (int rb = 0; rb < nrows; rb += NG)
+		if (tid == kThreads)
 		{
-			const int r = rb + group;
-			int kb = 0, ke = 0;
-			if (r < nrows) { kb = srow[r]; ke = srow[r + 1]; }
-			T sum = tzero(T());
-#pragma unroll 4
-			for (int j = kb + lane; j < ke; j += LPR)
+			const uint64_t pol = l2_evict_first_policy();
+			int idx = 0;
+			for (int c = blockIdx.x; c < n_chunks; c += gridDim.x)
 			{
-				T a = sval[j]; if (CONJ) a = tconj(a);
-				sum = mulacc(sum, a, tldg(x + scol[j]));
-			}
-#pragma unroll
-			for (int o = LPR / 2; o > 0; o >>= 1) sum = tadd(sum, tshfl_xor(sum, o));
-			if (lane == 0 && r < nrows)
-			{
-				y[r0 + r] = sum;
-				epi.row(r0 + r, sum, tldg(x + r0 + r), acc);
+				const int t1 = min((c + 1) * A.chunk, A.n_tiles);
+				for (int tile = c * A.chunk; tile < t1; tile++)
+				{
+					const int4 td = __ldg(A.tiles + tile);
+					if (td.w - td.z > TN) continue;   // over-long row: the consumers stream it from global memory
+					const int s = idx % kStages, j = idx / kStages;
+					if (j > 0) mbar_wait(smem_u32(&s_bar[kStages + s]), (uint32_t)((j - 1) & 1));
+					const uint32_t cnt = (uint32_t)((td.w - td.z + 3) & ~3);
+					const int ra = td.x & ~3;
+					const uint32_t rcnt = (uint32_t)((td.y - ra + 1 + 3) & ~3);
+					const uint32_t full = smem_u32(&s_bar[s]);
+					const uint32_t base = smem_u32(smem + (size_t)s * SC::BYTES);
+					mbar_expect_tx(full, cnt * (uint32_t)(sizeof(T) + 4) + rcnt * 4u);
+					bulk_g2s(base + SC::VAL_OFF, A.val + td.z, cnt * (uint32_t)sizeof(T), full, pol);
+					bulk_g2s(base + SC::COL_OFF, A.col + td.z, cnt * 4u, full, pol);
+					bulk_g2s(base + SC::ROW_OFF, A.row_ptr + ra, rcnt * 4u, full, pol);
+					idx++;
+				}
 			}
 		}
-		__syncthreads();
+	}
+	else
+	{
+		epi.begin(st);
+		constexpr int NG = kThreads / LPR;          // row groups per block
+		const int group = tid / LPR, lane = tid % LPR;
+		int idx = 0;
+		for (int c = blockIdx.x; c < n_chunks; c += gridDim.x)
+		{
+			const int t1 = min((c + 1) * A.chunk, A.n_tiles);
+			for (int tile = c * A.chunk; tile < t1; tile++)
+			{
+				const int4 td = __ldg(A.tiles + tile);
+				const int r0 = td.x, nrows = td.y - td.x, k0 = td.z, k1 = td.w;
+				if (k1 - k0 > TN)
+				{	// one row longer than a stage: stream it straight from global memory
+					T part = tzero(T());
+					for (int k = A.row_ptr[r0] + tid; k < k1; k += kThreads)
+					{
+						T a = A.val[k]; if (CONJ) a = tconj(a);
+						part = mulacc(part, a, tldg(x + A.col[k]));
+					}
+#pragma unroll
+					for (int o = 16; o > 0; o >>= 1) part = tadd(part, tshfl_xor(part, o));
+					if ((tid & 31) == 0) s_long[tid >> 5] = part;
+					consumer_sync();
+					if (tid == 0)
+					{
+						T tot = s_long[0];
+						for (int w = 1; w < kThreads / 32; w++) tot = tadd(tot, s_long[w]);
+						y[r0] = tot;
+						epi.row(r0, tot, tldg(x + r0), acc);
+					}
+					consumer_sync();
+					continue;
+				}
+				const int s = idx % kStages;
+				mbar_wait(smem_u32(&s_bar[s]), (uint32_t)((idx / kStages) & 1));
+				const unsigned char* base = smem + (size_t)s * SC::BYTES;
+				const T* sval = reinterpret_cast<const T*>(base + SC::VAL_OFF);
+				const int* scol = reinterpret_cast<const int*>(base + SC::COL_OFF);
+				const int* srow = reinterpret_cast<const int*>(base + SC::ROW_OFF) + (r0 & 3);
+				for (int rb = 0; rb < nrows; rb += NG)
+				{
+					const int r = rb + group;
+					int kb = 0, ke = 0;
+					if (r < nrows) { kb = srow[r] - k0; ke = srow[r + 1] - k0; }
+					T sum = tzero(T());
+					// kGatherUnroll entries per lane at a time, all their loads issued before the first use: the row walk
+					// is bound by the latency of the gathered x (L2 for most stencil neighbours), not by issue slots
+					for (int j0 = kb + lane; j0 < ke; j0 += LPR * kGatherUnroll)
+					{
+						int cidx[kGatherUnroll]; T a[kGatherUnroll], xv[kGatherUnroll];
+#pragma unroll
+						for (int u = 0; u < kGatherUnroll; u++)
+						{
+							const int j = j0 + u * LPR;
+							const bool ok = j < ke;
+							cidx[u] = ok ? scol[j] : -1;
+							a[u] = ok ? sval[j] : tzero(T());
+						}
+#pragma unroll
+						for (int u = 0; u < kGatherUnroll; u++) xv[u] = cidx[u] >= 0 ? tldg(x + cidx[u]) : tzero(T());
+#pragma unroll
+						for (int u = 0; u < kGatherUnroll; u++)
+						{
+							if (CONJ) a[u] = tconj(a[u]);
+							sum = mulacc(sum, a[u], xv[u]);
+						}
+					}
+#pragma unroll
+					for (int o = LPR / 2; o > 0; o >>= 1) sum = tadd(sum, tshfl_xor(sum, o));
+					if (lane == 0 && r < nrows)
+					{
+						y[r0 + r] = sum;
+						epi.row(r0 + r, sum, tldg(x + r0 + r), acc);
+					}
+				}
+				__syncwarp();
+				if ((tid & 31) == 0) mbar_arrive(smem_u32(&s_bar[kStages + s]));
+				idx++;
+			}
+		}
 	}
 	if (Epi::NRED > 0)
 	{
@@ -187,25 +292,36 @@ struct EpiNone {
 	__device__ void finish(DevState*, const double*) {}
 };
 
-inline int spmv_grid(int n_tiles)
+int spmv_grid_limit();   // resident CTAs of k_spmv on the current device (SMs x kSpmvCtasPerSm), engine.cu
+
+template <class T, int LPR, bool CONJ, class Epi>
+inline void launch_spmv_lpr(const CsrDev<T>& A, const T* x, T* y, const Epi& epi, DevState* st, double* partials, cudaStream_t s)
 {
-	int g = n_tiles < kMaxBlocks ? n_tiles : kMaxBlocks;
-	return g < 1 ? 1 : g;
+	static bool configured = false;   // per instantiation
+	auto kern = k_spmv<T, LPR, CONJ, Epi>;
+	if (!configured)
+	{
+		cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, StageCfg<T>::TOTAL);
+		configured = true;
+	}
+	const int n_chunks = (A.n_tiles + A.chunk - 1) / A.chunk;
+	int grid = n_chunks < spmv_grid_limit() ? n_chunks : spmv_grid_limit();
+	if (grid < 1) grid = 1;
+	kern<<<grid, kSpmvThreads, StageCfg<T>::TOTAL, s>>>(A, x, y, epi, st, partials);
 }
 
 // launch with the lanes-per-row variant recorded in the handle
 template <class T, bool CONJ, class Epi>
 inline void launch_spmv(const CsrDev<T>& A, const T* x, T* y, const Epi& epi, DevState* st, double* partials, cudaStream_t s)
 {
-	const int grid = spmv_grid(A.n_tiles);
 	switch (A.lpr)
 	{
-		case 1: k_spmv<T, 1, CONJ, Epi><<<grid, kThreads, 0, s>>>(A, x, y, epi, st, partials); break;
-		case 2: k_spmv<T, 2, CONJ, Epi><<<grid, kThreads, 0, s>>>(A, x, y, epi, st, partials); break;
-		case 4: k_spmv<T, 4, CONJ, Epi><<<grid, kThreads, 0, s>>>(A, x, y, epi, st, partials); break;
-		case 8: k_spmv<T, 8, CONJ, Epi><<<grid, kThreads, 0, s>>>(A, x, y, epi, st, partials); break;
-		case 16: k_spmv<T, 16, CONJ, Epi><<<grid, kThreads, 0, s>>>(A, x, y, epi, st, partials); break;
-		default: k_spmv<T, 32, CONJ, Epi><<<grid, kThreads, 0, s>>>(A, x, y, epi, st, partials); break;
+		case 1: launch_spmv_lpr<T, 1, CONJ, Epi>(A, x, y, epi, st, partials, s); break;
+		case 2: launch_spmv_lpr<T, 2, CONJ, Epi>(A, x, y, epi, st, partials, s); break;
+		case 4: launch_spmv_lpr<T, 4, CONJ, Epi>(A, x, y, epi, st, partials, s); break;
+		case 8: launch_spmv_lpr<T, 8, CONJ, Epi>(A, x, y, epi, st, partials, s); break;
+		case 16: launch_spmv_lpr<T, 16, CONJ, Epi>(A, x, y, epi, st, partials, s); break;
+		default: launch_spmv_lpr<T, 32, CONJ, Epi>(A, x, y, epi, st, partials, s); break;
 	}
 }
 

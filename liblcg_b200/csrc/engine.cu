@@ -19,6 +19,21 @@ const char* last_error() { return g_err.c_str(); }
 
 Settings& settings() { static Settings s; return s; }
 
+int spmv_grid_limit()
+{
+	static int cached[64] = {0};
+	int dev = 0;
+	if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148 * kSpmvCtasPerSm;
+	if (!cached[dev])
+	{
+		int sms = 0;
+		if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+		cached[dev] = sms * kSpmvCtasPerSm;
+		if (cached[dev] > kMaxBlocks) cached[dev] = kMaxBlocks;
+	}
+	return cached[dev];
+}
+
 Engine::Engine(cudaStream_t s, CsrHandle* h) : stream(s), cache(h)
 {
 	if (h)

@@ -31,10 +31,10 @@ struct CsrHandle {
 	int device = 0;
 	// device arrays (owned)
 	int* row_ptr = nullptr; int* col = nullptr; void* val = nullptr; int4* tiles = nullptr;
-	int n_tiles = 0, lpr = 1;
+	int n_tiles = 0, lpr = 1, chunk = 1;
 	// transpose (optional)
 	int* t_row_ptr = nullptr; int* t_col = nullptr; void* t_val = nullptr; int4* t_tiles = nullptr;
-	int t_n_tiles = 0, t_lpr = 1;
+	int t_n_tiles = 0, t_lpr = 1, t_chunk = 1;
 	void* diag = nullptr;          // Jacobi diagonal (optional), n_rows values
 	void* user = nullptr;          // instance handed to progress callbacks
 	Comm* comm = nullptr;          // set for a row block of a partitioned system
@@ -45,12 +45,12 @@ struct CsrHandle {
 
 	template <class T> CsrDev<T> view() const
 	{
-		CsrDev<T> v; v.n_rows = n_rows; v.n_cols = n_cols; v.nnz = nnz; v.n_tiles = n_tiles; v.lpr = lpr;
+		CsrDev<T> v; v.n_rows = n_rows; v.n_cols = n_cols; v.nnz = nnz; v.n_tiles = n_tiles; v.lpr = lpr; v.chunk = chunk;
 		v.row_ptr = row_ptr; v.col = col; v.val = (const T*)val; v.tiles = tiles; return v;
 	}
 	template <class T> CsrDev<T> tview() const
 	{
-		CsrDev<T> v; v.n_rows = n_cols; v.n_cols = n_rows; v.nnz = nnz; v.n_tiles = t_n_tiles; v.lpr = t_lpr;
+		CsrDev<T> v; v.n_rows = n_cols; v.n_cols = n_rows; v.nnz = nnz; v.n_tiles = t_n_tiles; v.lpr = t_lpr; v.chunk = t_chunk;
 		v.row_ptr = t_row_ptr; v.col = t_col; v.val = (const T*)t_val; v.tiles = t_tiles; return v;
 	}
 };
