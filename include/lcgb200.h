@@ -120,6 +120,30 @@ int lcgb200_csr_spmv_dot(lcgb200_csr_t A, const void* x_dev, void* y_dev, const 
 long long lcgb200_csr_spmv_bytes(lcgb200_csr_t A);
 int lcgb200_csr_info(lcgb200_csr_t A, int* n_rows, int* n_cols, int* nnz, int* n_tiles, int* lanes_per_row);
 
+/* =====================================================================================================
+ * Row-partitioned systems over several GPUs (new; the reference is single-device — SURVEY.md §8(e)).
+ * One process per GPU.  Every rank creates its block with lcgb200_csr_create_rect (n_rows local rows; columns
+ * index the extended vector [n_rows local entries | ghost entries grouped by owning peer]) and attaches the
+ * exchange plan.  The solvers then run unchanged: before each SpMV the ghost entries are fetched from their
+ * owners (ncclSend/ncclRecv over NVLink), and each fused reduction is summed over the ranks (ncclAllReduce on
+ * 1-8 doubles) before its scalar epilogue.  m, B (low, hig) handed to lcgb200_solve are the rank's row slices.
+ * ===================================================================================================== */
+typedef struct lcgb200_comm_s* lcgb200_comm_t;
+#define LCGB200_COMM_ID_BYTES 128
+/* rank 0 draws the id (ncclGetUniqueId) and ships it to the other ranks by any means (MPI, torch.distributed, a file) */
+int lcgb200_comm_unique_id(void* id_out, int capacity);
+/* collective over all ranks; binds to the calling thread's current CUDA device */
+int lcgb200_comm_create(lcgb200_comm_t* out, int rank, int size, const void* unique_id);
+int lcgb200_comm_destroy(lcgb200_comm_t comm);
+int lcgb200_comm_stats(lcgb200_comm_t comm, int* halo_exchanges, int* allreduces);
+/* n_global: rows of the whole system (the abs_diff test divides by it, lcg.cpp:208).  For each of the n_peers
+ * neighbours: its rank, how many of MY entries it needs (send_counts) — their local row indices concatenated in
+ * send_idx (host array; a consecutive run is sent in place, anything else is packed by a gather kernel) — and how
+ * many ghost entries I receive from it (recv_counts), stored in peer order behind the local entries.
+ * sum(recv_counts) must equal n_cols - n_rows of the handle. */
+int lcgb200_csr_set_partition(lcgb200_csr_t A, lcgb200_comm_t comm, long long n_global, int n_peers, const int* peer_ranks,
+	const int* send_counts, const int* send_idx, const int* recv_counts);
+
 /* Sentinel callbacks: never called; their ADDRESS selects the built-in operator.  instance = lcgb200_csr_t. */
 void lcgb200_csr_ax(void* instance, lcgb200_cublas_t, lcgb200_cusparse_t, lcgb200_dnvec_t x, lcgb200_dnvec_t Ax, const int n, const int nz);
 void lcgb200_jacobi_mx(void* instance, lcgb200_cublas_t, lcgb200_cusparse_t, lcgb200_dnvec_t x, lcgb200_dnvec_t Mx, const int n, const int nz);

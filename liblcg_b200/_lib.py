@@ -48,6 +48,11 @@ SYMBOLS = {
     "lcgb200_csr_spmv_dot": (_I, [_VP, _VP, _VP, _VP, _VP, _VP]),
     "lcgb200_csr_spmv_bytes": (_LL, [_VP]),
     "lcgb200_csr_info": (_I, [_VP] + [C.POINTER(_I)] * 5),
+    "lcgb200_comm_unique_id": (_I, [_VP, _I]),
+    "lcgb200_comm_create": (_I, [C.POINTER(_VP), _I, _I, _VP]),
+    "lcgb200_comm_destroy": (_I, [_VP]),
+    "lcgb200_comm_stats": (_I, [_VP, C.POINTER(_I), C.POINTER(_I)]),
+    "lcgb200_csr_set_partition": (_I, [_VP, _VP, _LL, _I, _VP, _VP, _VP, _VP]),
     "lcgb200_csr_ax": (None, None),
     "lcgb200_jacobi_mx": (None, None),
     "lcgb200_csr_cax": (None, None),

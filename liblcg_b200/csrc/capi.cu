@@ -49,11 +49,11 @@ int pick_tile_rows(long long nnz, long long rows, int lpr, int tile_nnz)
 	return cap;
 }
 
-// tiles per chunk: a CTA walks `chunk` consecutive tiles (~2048 rows) before jumping ahead by the grid stride
+// tiles per chunk: a CTA walks `chunk` consecutive tiles (~512 rows: two grid lines of a 256^3 stencil; measured best on B200, profiles/sweep_r01.txt) before jumping ahead by the grid stride
 int pick_chunk(int tile_rows)
 {
 	static const char* env = getenv("LCGB200_SPMV_CHUNK_ROWS");
-	const int target = env ? std::max(1, atoi(env)) : 2048;
+	const int target = env ? std::max(1, atoi(env)) : 512;
 	return std::max(1, target / std::max(tile_rows, 1));
 }
 
@@ -572,6 +572,11 @@ int lcgb200_csolve(lcgb200_csr_t Ah, int solver_id, void* m, const void* B, cons
 	if (rc) return rc;
 	if (solver_id == LCGB200_CBICG && !h->t_row_ptr) { set_error_msg("CLCG_BICG needs the transposed operator: create the handle with LCGB200_CSR_TRANSPOSE"); return LCGB200_C_UNKNOWN_SOLVER; }
 	if (solver_id == LCGB200_CPCG && !((flags & LCGB200_USE_JACOBI) && h->diag)) return LCGB200_NULL_PRECONDITION_MATRIX;
+	if (h->comm && h->comm->size() > 1 && (solver_id == LCGB200_CCGS || solver_id == LCGB200_CBICGSTAB || solver_id == LCGB200_CTFQMR))
+	{	// their shadow residual is ONE rand() sequence over the whole vector (lcg_complex.cpp:118-127)
+		set_error_msg("complex CGS/BICGSTAB/TFQMR are single-GPU: the reference's random shadow residual is one host rand() sequence");
+		return LCGB200_C_UNKNOWN_SOLVER;
+	}
 	return guarded([&]() {
 		Operator<double2> A; A.h = h;
 		if (solver_id == LCGB200_CPCG) A.diag = (const double2*)h->diag;

@@ -1,0 +1,250 @@
+// comm.cu — multi-GPU plumbing for a row-partitioned system: one process per GPU, every rank
+// holds a block of consecutive rows of A and the matching slices of all vectors.  Two exchange steps exist on the
+// path, both stream-ordered so that the iteration stays asynchronous to the host:
+//   halo       before every SpMV the entries of the input vector that other ranks' rows reference are sent to
+//              them (ncclSend/ncclRecv in one group over NVLink) and land in the ghost tail of the extended vector
+//              [n_local local entries | ghosts of peer 0 | ghosts of peer 1 | ...];
+//   allreduce  the per-rank totals a fused kernel left in DevState::red are summed in place (ncclAllReduce on
+//              1-8 doubles), after which k_finish runs the scalar epilogue identically on every rank.
+// The reference has no distributed path at all ("Parallelism strategies: none").
+//
+// NCCL is resolved with dlopen at first use (the copy already loaded by the host process, e.g. torch's, wins), so
+// single-GPU users of liblcgb200.so do not need it.
+#include "engine.cuh"
+#include "../../include/lcgb200.h"
+#include <dlfcn.h>
+#include <cstring>
+#include <vector>
+#include <string>
+
+namespace lcgb200 {
+
+namespace {
+
+struct NcclId { char internal[128]; };
+typedef void* NcclCommT;
+
+struct NcclApi {
+	void* lib = nullptr;
+	int (*GetUniqueId)(NcclId*) = nullptr;
+	int (*CommInitRank)(NcclCommT*, int, NcclId, int) = nullptr;
+	int (*CommDestroy)(NcclCommT) = nullptr;
+	int (*AllReduce)(const void*, void*, size_t, int, int, NcclCommT, cudaStream_t) = nullptr;
+	int (*Send)(const void*, size_t, int, int, NcclCommT, cudaStream_t) = nullptr;
+	int (*Recv)(void*, size_t, int, int, NcclCommT, cudaStream_t) = nullptr;
+	int (*GroupStart)() = nullptr;
+	int (*GroupEnd)() = nullptr;
+	const char* (*GetErrorString)(int) = nullptr;
+
+	bool load()
+	{
+		if (AllReduce) return true;
+		const char* names[] = {"libnccl.so.2", "libnccl.so"};
+		for (const char* nm : names) { lib = dlopen(nm, RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL); if (lib) break; }
+		if (!lib) for (const char* nm : names) { lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+		// torch bundles NCCL under a path that is not on the loader's search list but is already mapped: look the
+		// symbols up in the global scope as a last resort
+		void* scope = lib ? lib : RTLD_DEFAULT;
+#define LCG_NCCL_SYM(field, name) field = reinterpret_cast<decltype(field)>(dlsym(scope, name))
+		LCG_NCCL_SYM(GetUniqueId, "ncclGetUniqueId");
+		LCG_NCCL_SYM(CommInitRank, "ncclCommInitRank");
+		LCG_NCCL_SYM(CommDestroy, "ncclCommDestroy");
+		LCG_NCCL_SYM(AllReduce, "ncclAllReduce");
+		LCG_NCCL_SYM(Send, "ncclSend");
+		LCG_NCCL_SYM(Recv, "ncclRecv");
+		LCG_NCCL_SYM(GroupStart, "ncclGroupStart");
+		LCG_NCCL_SYM(GroupEnd, "ncclGroupEnd");
+		LCG_NCCL_SYM(GetErrorString, "ncclGetErrorString");
+#undef LCG_NCCL_SYM
+		if (!(GetUniqueId && CommInitRank && CommDestroy && AllReduce && Send && Recv && GroupStart && GroupEnd))
+		{
+			AllReduce = nullptr;
+			set_error_msg("NCCL (libnccl.so.2) could not be loaded: multi-GPU solves need it");
+			return false;
+		}
+		return true;
+	}
+};
+NcclApi g_nccl;
+
+void nccl_check(int rc, const char* what)
+{
+	if (rc == 0) return;
+	std::string msg = std::string(what) + " failed: " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "NCCL error");
+	set_error_msg(msg.c_str());
+	throw CudaFailure();
+}
+
+// send_buf[i] = x[idx[i]] for the entries that are not sent in place
+template <class T>
+__global__ void k_halo_pack(const T* __restrict__ x, const int* __restrict__ idx, T* __restrict__ out, int count)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < count) out[i] = x[idx[i]];
+}
+
+}  // namespace
+
+class NcclComm : public Comm {
+public:
+	NcclCommT comm = nullptr;
+	int rank_ = 0, size_ = 1;
+	struct Peer { int rank; int send_count; int send_off; bool contiguous; int send_first; int recv_count; int recv_off; };
+	std::vector<Peer> peers;
+	int n_local = 0, n_ghost = 0, n_packed = 0;
+	int* d_send_idx = nullptr;     // concatenated local indices of the packed peers
+	void* d_send_buf = nullptr;    // packed values (16 bytes per entry: enough for double2)
+	int halos = 0, allreduces = 0;
+
+	~NcclComm() override
+	{
+		cudaFree(d_send_idx); cudaFree(d_send_buf);
+		if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
+	}
+	int rank() const override { return rank_; }
+	int size() const override { return size_; }
+
+	void allreduce(double* dev, int count, cudaStream_t s) override
+	{
+		nccl_check(g_nccl.AllReduce(dev, dev, (size_t)count, /*ncclDouble*/ 8, /*ncclSum*/ 0, comm, s), "ncclAllReduce");
+		allreduces++;
+	}
+
+	void halo(void* x_ext, int elem_bytes, cudaStream_t s) override
+	{
+		if (peers.empty()) return;
+		char* x = static_cast<char*>(x_ext);
+		if (n_packed > 0)
+		{
+			const int grid = (n_packed + 255) / 256;
+			if (elem_bytes == 8) k_halo_pack<double><<<grid, 256, 0, s>>>((const double*)x_ext, d_send_idx, (double*)d_send_buf, n_packed);
+			else k_halo_pack<double2><<<grid, 256, 0, s>>>((const double2*)x_ext, d_send_idx, (double2*)d_send_buf, n_packed);
+		}
+		nccl_check(g_nccl.GroupStart(), "ncclGroupStart");
+		for (const Peer& p : peers)
+		{
+			if (p.send_count > 0)
+			{
+				const void* src = p.contiguous ? (const void*)(x + (size_t)p.send_first * elem_bytes)
+				                               : (const void*)((char*)d_send_buf + (size_t)p.send_off * elem_bytes);
+				nccl_check(g_nccl.Send(src, (size_t)p.send_count * elem_bytes, /*ncclChar*/ 0, p.rank, comm, s), "ncclSend");
+			}
+			if (p.recv_count > 0)
+				nccl_check(g_nccl.Recv(x + ((size_t)n_local + p.recv_off) * elem_bytes, (size_t)p.recv_count * elem_bytes, 0, p.rank, comm, s), "ncclRecv");
+		}
+		nccl_check(g_nccl.GroupEnd(), "ncclGroupEnd");
+		halos++;
+	}
+};
+
+}  // namespace lcgb200
+
+using namespace lcgb200;
+
+namespace {
+template <class F> int guarded_comm(F&& f)
+{
+	try { return f(); }
+	catch (const CudaFailure&) { return LCGB200_UNKNOWN_ERROR; }
+	catch (const std::exception& e) { set_error_msg(e.what()); return LCGB200_UNKNOWN_ERROR; }
+}
+}  // namespace
+
+extern "C" {
+
+int lcgb200_comm_unique_id(void* id_out, int capacity)
+{
+	if (!id_out || capacity < LCGB200_COMM_ID_BYTES) return LCGB200_INVALID_POINTER;
+	if (!g_nccl.load()) return LCGB200_UNKNOWN_ERROR;
+	NcclId id;
+	int rc = g_nccl.GetUniqueId(&id);
+	if (rc != 0) { set_error_msg("ncclGetUniqueId failed"); return LCGB200_UNKNOWN_ERROR; }
+	std::memcpy(id_out, &id, sizeof(id));
+	return 0;
+}
+
+int lcgb200_comm_create(lcgb200_comm_t* out, int rank, int size, const void* unique_id)
+{
+	if (!out || !unique_id) return LCGB200_INVALID_POINTER;
+	*out = nullptr;
+	if (size < 1 || rank < 0 || rank >= size) return LCGB200_INVILAD_VARIABLE_SIZE;
+	if (!g_nccl.load()) return LCGB200_UNKNOWN_ERROR;
+	NcclComm* c = new NcclComm();
+	int rc = guarded_comm([&]() {
+		NcclId id; std::memcpy(&id, unique_id, sizeof(id));
+		c->rank_ = rank; c->size_ = size;
+		nccl_check(g_nccl.CommInitRank(&c->comm, size, id, rank), "ncclCommInitRank");
+		return 0;
+	});
+	if (rc != 0) { delete c; return rc; }
+	*out = reinterpret_cast<lcgb200_comm_t>(c);
+	return 0;
+}
+
+int lcgb200_comm_destroy(lcgb200_comm_t comm)
+{
+	delete reinterpret_cast<NcclComm*>(comm);
+	return 0;
+}
+
+int lcgb200_comm_stats(lcgb200_comm_t comm, int* halos, int* allreduces)
+{
+	NcclComm* c = reinterpret_cast<NcclComm*>(comm);
+	if (!c) return LCGB200_INVALID_POINTER;
+	if (halos) *halos = c->halos;
+	if (allreduces) *allreduces = c->allreduces;
+	return 0;
+}
+
+int lcgb200_csr_set_partition(lcgb200_csr_t A, lcgb200_comm_t comm, long long n_global, int n_peers, const int* peer_ranks,
+	const int* send_counts, const int* send_idx, const int* recv_counts)
+{
+	CsrHandle* h = reinterpret_cast<CsrHandle*>(A);
+	NcclComm* c = reinterpret_cast<NcclComm*>(comm);
+	if (!h || !c) return LCGB200_INVALID_POINTER;
+	if (n_peers < 0 || n_global < h->n_rows) return LCGB200_INVILAD_VARIABLE_SIZE;
+	if (n_peers > 0 && (!peer_ranks || !send_counts || !recv_counts)) return LCGB200_INVALID_POINTER;
+	if (h->t_row_ptr) { set_error_msg("a partitioned operator cannot carry a transpose (complex BiCG is single-GPU)"); return LCGB200_SIZE_NOT_MATCH; }
+	return guarded_comm([&]() {
+		c->peers.clear();
+		c->n_local = h->n_rows;
+		std::vector<int> packed;
+		int recv_off = 0, send_pos = 0;
+		for (int p = 0; p < n_peers; p++)
+		{
+			NcclComm::Peer pe;
+			pe.rank = peer_ranks[p]; pe.send_count = send_counts[p]; pe.recv_count = recv_counts[p];
+			pe.recv_off = recv_off; recv_off += recv_counts[p];
+			pe.contiguous = true; pe.send_first = pe.send_count > 0 ? send_idx[send_pos] : 0; pe.send_off = 0;
+			for (int i = 0; i < pe.send_count; i++)
+			{
+				const int v = send_idx[send_pos + i];
+				if (v < 0 || v >= h->n_rows) { set_error_msg("send index outside the local rows"); throw CudaFailure(); }
+				if (v != pe.send_first + i) pe.contiguous = false;
+			}
+			if (!pe.contiguous)
+			{
+				pe.send_off = (int)packed.size();
+				packed.insert(packed.end(), send_idx + send_pos, send_idx + send_pos + pe.send_count);
+			}
+			send_pos += pe.send_count;
+			if (pe.rank < 0 || pe.rank >= c->size_ || pe.rank == c->rank_) { set_error_msg("bad peer rank"); throw CudaFailure(); }
+			c->peers.push_back(pe);
+		}
+		if (h->n_rows + recv_off != h->n_cols) { set_error_msg("n_rows + ghost entries must equal n_cols of the rectangular block"); throw CudaFailure(); }
+		c->n_ghost = recv_off;
+		c->n_packed = (int)packed.size();
+		cudaFree(c->d_send_idx); cudaFree(c->d_send_buf); c->d_send_idx = nullptr; c->d_send_buf = nullptr;
+		if (c->n_packed > 0)
+		{
+			LCG_CUDA_CHECK(cudaMalloc((void**)&c->d_send_idx, packed.size() * sizeof(int)));
+			LCG_CUDA_CHECK(cudaMalloc(&c->d_send_buf, packed.size() * 16));
+			LCG_CUDA_CHECK(cudaMemcpy(c->d_send_idx, packed.data(), packed.size() * sizeof(int), cudaMemcpyHostToDevice));
+		}
+		h->comm = c;
+		h->n_global = n_global;
+		return 0;
+	});
+}
+
+}  // extern "C"

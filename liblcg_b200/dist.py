@@ -1,0 +1,198 @@
+"""Row-partitioned systems over several GPUs: one process per GPU, `torch.distributed` for the
+plumbing (rendezvous, exchanging the halo plan and the NCCL id), the C ABI (lcgb200_comm_*, lcgb200_csr_set_partition)
+for everything on the iteration path.
+
+The reference is single-device; this module is the out-of-band selection of the multi-GPU path the survey
+describes: callers still drive the solvers through `api.solve` with their row slices of m and B.
+
+Partition: contiguous row blocks [bounds[r], bounds[r+1]).  Each rank keeps its CSR rows with columns remapped to the
+extended vector  [ local entries | ghost entries grouped by owning rank, ascending global index within an owner ].
+The plan (who needs which of my rows) is derived from the column indices alone, so it works for any CSR, not only
+the stencils.  `plan_partition` is pure tensor code (CPU or CUDA) and is what the gloo tests exercise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib, api
+
+
+def row_bounds(n: int, world: int, align: int = 1) -> list[int]:
+    """Balanced contiguous row blocks; block edges rounded to a multiple of `align` (e.g. a grid plane)."""
+    b = [0]
+    for r in range(1, world):
+        e = (n * r) // world
+        if align > 1:
+            e = int(round(e / align)) * align
+        b.append(min(max(e, b[-1]), n))
+    b.append(n)
+    return b
+
+
+@dataclass
+class HaloPlan:
+    rank: int
+    world: int
+    r0: int
+    r1: int
+    n_global: int
+    ghost_global: "object"            # sorted global column ids of my ghost entries (tensor)
+    recv_from: dict = field(default_factory=dict)   # peer -> number of ghost entries it owns
+    send_to: dict = field(default_factory=dict)     # peer -> np.int32 array of MY local row indices it needs
+
+    @property
+    def n_local(self):
+        return self.r1 - self.r0
+
+    @property
+    def n_ghost(self):
+        return int(self.ghost_global.numel())
+
+    @property
+    def peers(self):
+        return sorted(set(self.recv_from) | set(self.send_to))
+
+
+def remap_columns(col_global, r0: int, r1: int, bounds):
+    """Local column indices for rows [r0,r1): (new_col int32, ghost_global sorted int64, ghost owner counts per rank)."""
+    import torch
+    col = col_global.to(torch.int64)
+    outside = (col < r0) | (col >= r1)
+    ghost = torch.unique(col[outside])                      # sorted
+    new_col = col - r0
+    if ghost.numel():
+        pos = torch.searchsorted(ghost, col[outside])
+        new_col[outside] = (r1 - r0) + pos
+    edges = torch.tensor(bounds[1:], dtype=torch.int64, device=col.device)
+    owner = torch.bucketize(ghost, edges, right=True)       # rank owning each ghost entry
+    counts = torch.bincount(owner, minlength=len(bounds) - 1).cpu().tolist() if ghost.numel() else [0] * (len(bounds) - 1)
+    return new_col.to(torch.int32), ghost, counts
+
+
+def plan_partition(col_global, bounds, rank: int, group=None):
+    """Remap the columns of this rank's rows and agree with the peers on the halo plan.
+    Returns (new_col int32 tensor, HaloPlan).  Collective over `group` (any backend: only all_gather_object)."""
+    import torch.distributed as dist
+    world = len(bounds) - 1
+    r0, r1 = bounds[rank], bounds[rank + 1]
+    new_col, ghost, counts = remap_columns(col_global, r0, r1, bounds)
+    plan = HaloPlan(rank, world, r0, r1, bounds[-1], ghost)
+    need = {}
+    off = 0
+    g_cpu = ghost.cpu().numpy()
+    for p in range(world):
+        if counts[p]:
+            need[p] = g_cpu[off:off + counts[p]]
+            plan.recv_from[p] = counts[p]
+            off += counts[p]
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, need, group=group)
+        for p, needs_of_p in enumerate(gathered):
+            if p != rank and needs_of_p and rank in needs_of_p:
+                plan.send_to[p] = (np.asarray(needs_of_p[rank], dtype=np.int64) - r0).astype(np.int32)
+    return new_col, plan
+
+
+class Communicator:
+    """lcgb200_comm_t: NCCL communicator owned by the C library; the id travels over torch.distributed."""
+
+    def __init__(self, rank: int, world: int, group=None):
+        import torch.distributed as dist
+        lib = _lib.load()
+        ident = [None]
+        if rank == 0:
+            buf = (C.c_ubyte * 128)()
+            rc = lib.lcgb200_comm_unique_id(buf, 128)
+            if rc != 0:
+                raise RuntimeError(f"lcgb200_comm_unique_id failed ({rc}): {api.last_error()}")
+            ident[0] = bytes(buf)
+        dist.broadcast_object_list(ident, src=0, group=group)
+        h = C.c_void_p()
+        idbuf = (C.c_ubyte * 128).from_buffer_copy(ident[0])
+        rc = lib.lcgb200_comm_create(C.byref(h), rank, world, idbuf)
+        if rc != 0:
+            raise RuntimeError(f"lcgb200_comm_create failed ({rc}): {api.last_error()}")
+        self.handle, self.rank, self.world = h, rank, world
+
+    def stats(self):
+        a, b = C.c_int(), C.c_int()
+        _lib.load().lcgb200_comm_stats(self.handle, C.byref(a), C.byref(b))
+        return {"halo_exchanges": a.value, "allreduces": b.value}
+
+    def close(self):
+        if getattr(self, "handle", None):
+            _lib.load().lcgb200_comm_destroy(self.handle)
+            self.handle = None
+
+
+@dataclass
+class Partition:
+    op: api.CsrOperator
+    comm: Communicator
+    plan: HaloPlan
+    n_local: int
+    b: "object" = None
+
+    def close(self):
+        self.op.close()
+        self.comm.close()
+
+
+def attach_plan(op: api.CsrOperator, comm: Communicator, plan: HaloPlan) -> None:
+    peers = plan.peers
+    ranks = np.asarray(peers, dtype=np.int32)
+    send_counts = np.asarray([len(plan.send_to.get(p, ())) for p in peers], dtype=np.int32)
+    recv_counts = np.asarray([plan.recv_from.get(p, 0) for p in peers], dtype=np.int32)
+    send_idx = np.concatenate([plan.send_to[p] for p in peers if p in plan.send_to]).astype(np.int32) if send_counts.sum() else np.zeros(1, np.int32)
+    rc = _lib.load().lcgb200_csr_set_partition(op.handle, comm.handle, plan.n_global, len(peers), ranks.ctypes.data,
+                                               send_counts.ctypes.data, send_idx.ctypes.data, recv_counts.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"lcgb200_csr_set_partition failed ({rc}): {api.last_error()}")
+
+
+def partition_csr(row_ptr_local, col_global, val, bounds, rank: int, jacobi=False, group=None) -> Partition:
+    """This rank's rows (row_ptr rebased to 0, GLOBAL column ids, values; torch CUDA tensors or numpy arrays)
+    -> rectangular operator + communicator + halo plan."""
+    import torch
+    world = len(bounds) - 1
+    on_dev = hasattr(col_global, "data_ptr")
+    colt = col_global if on_dev else torch.from_numpy(np.ascontiguousarray(col_global))
+    new_col, plan = plan_partition(colt, bounds, rank, group=group)
+    n_loc = bounds[rank + 1] - bounds[rank]
+    if on_dev:
+        op = api.CsrOperator(row_ptr_local, new_col.contiguous(), val, n_cols=n_loc + plan.n_ghost, jacobi=jacobi)
+    else:
+        op = api.CsrOperator(np.asarray(row_ptr_local), new_col.numpy(), np.asarray(val), n_cols=n_loc + plan.n_ghost, jacobi=jacobi)
+    comm = Communicator(rank, world, group=group)
+    attach_plan(op, comm, plan)
+    return Partition(op, comm, plan, n_loc)
+
+
+KIND_ID = {"7pt": 0, "27pt": 1, "7pt_cd": 2}
+
+
+def build_stencil_partition(kind: str, g: int, rank: int, world: int, device, jacobi=False, group=None) -> Partition:
+    """Rows of this rank of the g^3 stencil system (z-slab partition), generated on the device."""
+    import torch
+    lib = _lib.load()
+    n = g ** 3
+    bounds = row_bounds(n, world, align=g * g)
+    r0, r1 = bounds[rank], bounds[rank + 1]
+    nz = C.c_longlong()
+    assert lib.lcgb200_gen_stencil(KIND_ID[kind], g, r0, r1, None, None, None, 0, C.byref(nz), None) == 0
+    rp = torch.empty(r1 - r0 + 1, dtype=torch.int32, device=device)
+    ci = torch.empty(nz.value, dtype=torch.int32, device=device)
+    va = torch.empty(nz.value, dtype=torch.float64, device=device)
+    assert lib.lcgb200_gen_stencil(KIND_ID[kind], g, r0, r1, rp.data_ptr(), ci.data_ptr(), va.data_ptr(), 0, None, None) == 0
+    b = torch.empty(r1 - r0, dtype=torch.float64, device=device)
+    assert lib.lcgb200_gen_rhs(KIND_ID[kind], g, r0, r1, b.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    part = partition_csr(rp, ci, va, bounds, rank, jacobi=jacobi, group=group)
+    part.b = b
+    del rp, ci, va
+    torch.cuda.empty_cache()
+    return part

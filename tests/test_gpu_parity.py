@@ -471,3 +471,22 @@ def test_complex_residual_mode_switch(torch_cuda, fixtures):
     api.set_complex_residual_mode(0)
     # x0 = 0 -> max(|m|,1) = 1 at k = 0: CPU definition ||r||^4, CUDA definition ||r||^2
     assert res[0][0] == pytest.approx(res[1][0] ** 2, rel=1e-12)
+
+
+# ------------------------------------------------------------------------------------------------ multi-GPU
+def test_row_partitioned_solves_match_cpu(torch_cuda):
+    """halo exchange + scalar allreduce over NCCL, one process per GPU (tests/multi_gpu_check.py)."""
+    import os
+    import subprocess
+    import sys
+    torch = torch_cuda
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs >= 2 GPUs (run tests/multi_gpu_check.py under torchrun on a multi-GPU box)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    world = 2
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(root, "tests", "multi_gpu_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "multi-GPU parity ok" in r.stdout
