@@ -3,7 +3,7 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--iters I]
 
-A "step" is ONE SOLVE of a fixed number of iterations (`--iters`, default 100: epsilon = 1e-300 and
+A "step" is ONE SOLVE of a fixed number of iterations (`--iters`, default 200: epsilon = 1e-300 and
 max_iterations = I, so every step runs exactly I iterations of the reference's loop and returns
 LCG_REACHED_MAX_ITERATIONS) of the workload's system.  Workloads (BASELINE.json configs):
 
@@ -186,6 +186,8 @@ def run_ours(args, wl):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     lib = _lib.load()
+    if args.poll > 0:
+        api.set_poll_interval(args.poll)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -224,44 +226,51 @@ def run_ours(args, wl):
         torch.cuda.synchronize()
 
     def step_device():
-        m_d.zero_()
         r = api.solve(op, sid, m_d, b_d, param=para, device=True, jacobi=(solver == "PCG"), stream=stream)
         if r.ret != api.LCG_REACHED_MAX_ITERATIONS or r.iterations != iters:
             raise RuntimeError(f"solve returned {r.ret} after {r.iterations} iterations: {api.last_error()}")
         return r
 
-    def timed(fn, steps):
-        """K steps bracketed by barrier + synchronize, CUDA events on the launching stream, max over ranks."""
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        res = [fn() for _ in range(steps)]
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
+    def timed(fn, steps, prepare=None):
+        """K steps, each bracketed by barrier + synchronize and a CUDA-event pair on the launching stream; the step times
+        are summed and the MAX over ranks is taken.  `prepare` (resetting the initial guess) runs between the brackets."""
+        total, res = 0.0, []
+        for _ in range(steps):
+            if prepare is not None:
+                prepare()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            res.append(fn())
+            e1.record()
+            torch.cuda.synchronize()
+            total += e0.elapsed_time(e1)
         if dist is not None:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            t = torch.tensor([total], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            total = float(t.item())
         barrier()
-        return ms, res
+        return total, res
 
     for _ in range(max(args.warmup, 3)):
+        m_d.zero_()
         step_device()
 
     # ---- value: device-resident solve
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_dev, res = timed(step_device, args.steps)
+    ms_dev, res = timed(step_device, args.steps, prepare=lambda: m_d.zero_())
     clocks = sampler.stop() if rank == 0 else None
     launches = sum(r.info.kernel_launches for r in res)
+    dev_ms_inside = sum(r.info.device_ms for r in res)
     value = args.steps * iters / (ms_dev * 1e-3)
 
     # ---- roofline pass: same steps, every launch bracketed by events
     api.set_profile(True)
+    m_d.zero_()
     step_device()
-    _, pres = timed(step_device, args.steps)
+    _, pres = timed(step_device, args.steps, prepare=lambda: m_d.zero_())
     api.set_profile(False)
     spmv_ms = sum(r.info.spmv_ms for r in pres)
     spmv_cnt = sum(r.info.spmv_timed for r in pres)
@@ -276,8 +285,10 @@ def run_ours(args, wl):
         b_h_t = b_d.cpu().pin_memory()
         m_h, b_h = m_h_t.numpy(), b_h_t.numpy()
 
+        def zero_host():
+            m_h[:] = 0.0   # the initial guess of the step, prepared outside the timed bracket
+
         def step_host():
-            m_h[:] = 0.0
             if solver == "PCG":
                 rc = api.lcg_solver_preconditioned_cuda(api.CSR_AX, api.JACOBI_MX, None, m_h, b_h, n, nnz, para, op)
             else:
@@ -286,10 +297,11 @@ def run_ours(args, wl):
                 raise RuntimeError(f"reference-shaped solve returned {rc}: {api.last_error()}")
             return float(m_h[0])   # the step's result is read on the host
 
+        zero_host()
         step_host()
         torch.cuda.synchronize()
         with torch.cuda.stream(torch.cuda.default_stream()):   # the reference-shaped calls run on the legacy default stream
-            ms_e2e, _ = timed(step_host, args.steps)
+            ms_e2e, _ = timed(step_host, args.steps, prepare=zero_host)
         e2e = {"value": args.steps * iters / (ms_e2e * 1e-3), "unit": "iterations/s",
                "h2d_bytes_per_step": 2 * 8 * n, "d2h_bytes_per_step": 8 * n, "ms_per_step": ms_e2e / args.steps,
                "api": "lcg_solver_preconditioned_cuda" if solver == "PCG" else "lcg_solver_cuda"}
@@ -299,15 +311,18 @@ def run_ours(args, wl):
         b_h_t = b_d.cpu().pin_memory()
         m_h, b_h = m_h_t.numpy(), b_h_t.numpy()
 
-        def step_host():
+        def zero_host():
             m_h[:] = 0.0
+
+        def step_host():
             r = api.solve(op, sid, m_h, b_h, param=para, device=False, jacobi=(solver == "PCG"), stream=stream)
             if r.ret != api.LCG_REACHED_MAX_ITERATIONS:
                 raise RuntimeError(f"partitioned host solve returned {r.ret}: {api.last_error()}")
             return float(m_h[0])
 
+        zero_host()
         step_host()
-        ms_e2e, _ = timed(step_host, args.steps)
+        ms_e2e, _ = timed(step_host, args.steps, prepare=zero_host)
         e2e = {"value": args.steps * iters / (ms_e2e * 1e-3), "unit": "iterations/s",
                "h2d_bytes_per_step": 2 * 8 * n, "d2h_bytes_per_step": 8 * n, "ms_per_step": ms_e2e / args.steps,
                "api": "lcgb200_solve (host slices, row-partitioned handle)"}
@@ -367,6 +382,8 @@ def run_ours(args, wl):
                    "lanes_per_row": info["lanes_per_row"], "tiles": info["n_tiles"]},
         "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         "hbm_gbs_per_iteration": bpi * value / 1e9 / world,
+        "diagnostics": {"solve_device_ms_per_step": dev_ms_inside / args.steps, "profile_pass_device_ms_per_step": prof_dev_ms / args.steps,
+                        "kernel_ms_sum_per_step": (spmv_ms + vec_ms) / args.steps},
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
@@ -381,10 +398,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="pcg27_256", choices=sorted(WORKLOADS))
-    ap.add_argument("--iters", type=int, default=100, help="iterations per step (GPU arm)")
+    ap.add_argument("--iters", type=int, default=200, help="iterations per step (GPU arm)")
     ap.add_argument("--cpu-iters", type=int, default=10, help="iterations of the cpu_baseline sample")
     ap.add_argument("--ref-iters", type=int, default=10, help="iterations per step of the --impl reference arm")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--poll", type=int, default=0, help="iterations enqueued per host poll of the convergence flag (0 = library default)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     world = int(os.environ.get("WORLD_SIZE", "1"))

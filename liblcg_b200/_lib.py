@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "liblcgb200.so")
+SO_PATH = os.environ.get("LCGB200_LIB", os.path.join(HERE, "liblcgb200.so"))   # override: tuning variants only
 
 
 class LcgPara(C.Structure):

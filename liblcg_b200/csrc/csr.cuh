@@ -7,7 +7,8 @@
 // whose non-zeros (from the 4-aligned start) fit one shared-memory stage; the tile builder caps the row count
 // at a multiple of the row groups of a block so that the compute phase has no ragged last pass.
 //
-// Kernel (sm_100a): a persistent grid (2 CTAs x 148 SMs), warp-specialised.
+// Kernel (sm_100a): a persistent grid (4 CTAs x 148 SMs, 56 registers/thread), warp-specialised.  The constants below
+// are the best of the sweeps in profiles/sweep_r01.txt (more resident consumer warps beat deeper rings).
 //   producer  one elected thread of an extra warp streams the tile's col / val / row_ptr slices HBM -> shared
 //             memory with TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx, L2 evict-first hint: the
 //             matrix is read exactly once per SpMV and must not push the vectors out of L2) into a ring of
@@ -24,13 +25,25 @@
 
 namespace lcgb200 {
 
-constexpr int kTileNnzReal = 2048;   // staged non-zeros per tile: 16 KB val + 8 KB col
+#ifndef LCG_TILE_NNZ
+#define LCG_TILE_NNZ 1792
+#endif
+#ifndef LCG_STAGES
+#define LCG_STAGES 2
+#endif
+#ifndef LCG_CTAS
+#define LCG_CTAS 4
+#endif
+#ifndef LCG_UNROLL
+#define LCG_UNROLL 8
+#endif
+constexpr int kTileNnzReal = LCG_TILE_NNZ;   // staged non-zeros per tile (14 KB val + 7 KB col): 256 rows x 7 or 64 rows x 27-28
 constexpr int kTileNnzCplx = 1024;   // 16 KB val + 4 KB col
 constexpr int kTileRows = 512;       // max rows per tile (bounds the row_ptr slice in shared memory)
-constexpr int kStages = 3;           // shared-memory ring depth (2 CTAs x 3 stages leave ~70 KB of L1 for the gathered x)
-constexpr int kGatherUnroll = 8;     // row entries per lane whose loads are issued back to back
+constexpr int kStages = LCG_STAGES;           // shared-memory ring depth; 4 CTAs x 2 stages x 22.5 KB leave ~45 KB of L1 per SM for the gathered x
+constexpr int kGatherUnroll = LCG_UNROLL;     // row entries per lane whose loads are issued back to back
 constexpr int kSpmvThreads = kThreads + 32;   // 8 consumer warps + 1 producer warp
-constexpr int kSpmvCtasPerSm = 2;
+constexpr int kSpmvCtasPerSm = LCG_CTAS;
 
 template <class T>
 struct CsrDev {
@@ -42,8 +55,9 @@ struct CsrDev {
 };
 
 template <class T> struct TileCfg;
-template <> struct TileCfg<double> { static constexpr int NNZ = kTileNnzReal; };
-template <> struct TileCfg<double2> { static constexpr int NNZ = kTileNnzCplx; };
+template <> struct TileCfg<double> { static constexpr int NNZ = kTileNnzReal; static constexpr int CTAS = kSpmvCtasPerSm; };
+// complex rows carry twice the registers per entry: 2 CTAs per SM (112 registers) keep the gather loop spill-free
+template <> struct TileCfg<double2> { static constexpr int NNZ = kTileNnzCplx; static constexpr int CTAS = kSpmvCtasPerSm > 2 ? 2 : kSpmvCtasPerSm; };
 
 // shared-memory stage layout (bytes): val | col | row_ptr slice
 template <class T> struct StageCfg {
@@ -121,7 +135,7 @@ __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;"
 //   __device__ void row(int i, T yi, T xi, double* acc);   called once per row by one lane (may write vectors)
 //   __device__ void finish(DevState*, const double* tot);
 template <class T, int LPR, bool CONJ, class Epi>
-__global__ void __launch_bounds__(kSpmvThreads, kSpmvCtasPerSm) k_spmv(CsrDev<T> A, const T* __restrict__ x, T* __restrict__ y, Epi epi_in,
+__global__ void __launch_bounds__(kSpmvThreads, TileCfg<T>::CTAS) k_spmv(CsrDev<T> A, const T* __restrict__ x, T* __restrict__ y, Epi epi_in,
 	DevState* st, double* partials)
 {
 	if (st_done(st)) return;
@@ -292,7 +306,7 @@ struct EpiNone {
 	__device__ void finish(DevState*, const double*) {}
 };
 
-int spmv_grid_limit();   // resident CTAs of k_spmv on the current device (SMs x kSpmvCtasPerSm), engine.cu
+int spmv_grid_limit(int ctas_per_sm);   // resident CTAs of k_spmv on the current device (SMs x CTAs per SM), engine.cu
 
 template <class T, int LPR, bool CONJ, class Epi>
 inline void launch_spmv_lpr(const CsrDev<T>& A, const T* x, T* y, const Epi& epi, DevState* st, double* partials, cudaStream_t s)
@@ -305,7 +319,8 @@ inline void launch_spmv_lpr(const CsrDev<T>& A, const T* x, T* y, const Epi& epi
 		configured = true;
 	}
 	const int n_chunks = (A.n_tiles + A.chunk - 1) / A.chunk;
-	int grid = n_chunks < spmv_grid_limit() ? n_chunks : spmv_grid_limit();
+	const int limit = spmv_grid_limit(TileCfg<T>::CTAS);
+	int grid = n_chunks < limit ? n_chunks : limit;
 	if (grid < 1) grid = 1;
 	kern<<<grid, kSpmvThreads, StageCfg<T>::TOTAL, s>>>(A, x, y, epi, st, partials);
 }

@@ -19,19 +19,21 @@ const char* last_error() { return g_err.c_str(); }
 
 Settings& settings() { static Settings s; return s; }
 
-int spmv_grid_limit()
+int spmv_grid_limit(int ctas_per_sm)
 {
 	static int cached[64] = {0};
-	int dev = 0;
-	if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148 * kSpmvCtasPerSm;
-	if (!cached[dev])
+	int dev = 0, sms = 148;
+	if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64)
 	{
-		int sms = 0;
-		if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-		cached[dev] = sms * kSpmvCtasPerSm;
-		if (cached[dev] > kMaxBlocks) cached[dev] = kMaxBlocks;
+		if (!cached[dev])
+		{
+			int v = 0;
+			cached[dev] = (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) ? v : 148;
+		}
+		sms = cached[dev];
 	}
-	return cached[dev];
+	int g = sms * ctas_per_sm;
+	return g > kMaxBlocks ? kMaxBlocks : g;
 }
 
 Engine::Engine(cudaStream_t s, CsrHandle* h) : stream(s), cache(h)
@@ -79,11 +81,20 @@ cudaEvent_t Engine::prof_begin(int cls)
 
 void Engine::prof_collect(double* ms, int* count)
 {
+	// Launches enqueued after the device set `done` return at their first instruction (~3 us): they are not part of
+	// the algorithm, so only launches lasting at least a quarter of their class's longest one are counted.
 	ms[0] = ms[1] = 0.0; count[0] = count[1] = 0;
+	std::vector<float> dur(timed_used, 0.f);
+	float mx[2] = {0.f, 0.f};
 	for (size_t i = 0; i < timed_used; i++)
 	{
-		float e = 0.f;
-		if (cudaEventElapsedTime(&e, timed[i].a, timed[i].b) == cudaSuccess) { ms[timed[i].cls] += e; count[timed[i].cls]++; }
+		if (cudaEventElapsedTime(&dur[i], timed[i].a, timed[i].b) != cudaSuccess) dur[i] = 0.f;
+		if (dur[i] > mx[timed[i].cls]) mx[timed[i].cls] = dur[i];
+	}
+	for (size_t i = 0; i < timed_used; i++)
+	{
+		const int c = timed[i].cls;
+		if (dur[i] >= 0.25f * mx[c] && dur[i] > 0.f) { ms[c] += dur[i]; count[c]++; }
 	}
 }
 

@@ -105,3 +105,40 @@ def test_no_gpu_means_error_not_fallback():
     v = np.array([2.0, 2.0])
     with pytest.raises(RuntimeError):
         api.CsrOperator(rp, ci, v)
+
+
+def test_cxx_dropin_headers_compile():
+    """include/lcg_b200/{util,lcg_cuda,clcg_cuda}.h: a liblcg user's program (tests/cxx/dropin_sample.cu) compiles and links
+    against them for sm_100a; a second translation unit checks the reference's names, values and default arguments."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(["make", "-C", os.path.join(root, "tests", "cxx")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert os.path.exists(os.path.join(root, "tests", "cxx", "build", "dropin_sample"))
+    src = r"""
+#include "lcg_b200/lcg_cuda.h"
+#include "lcg_b200/clcg_cuda.h"
+#include <cstddef>
+static_assert(sizeof(lcg_para) == 64 && offsetof(lcg_para, epsilon) == 8 && offsetof(lcg_para, maxi_m) == 56, "lcg_para layout (util.h:95-148)");
+static_assert(sizeof(clcg_para) == 24, "clcg_para layout (util.h:247-273)");
+static_assert(LCG_SPG == 6 && CLCG_PBICG == 6 && LCG_REACHED_MAX_ITERATIONS == -1019 && LCG_SIZE_NOT_MATCH == -1011, "ids");
+static_assert(CLCG_REACHED_MAX_ITERATIONS == -1020 && CLCG_NAN_VALUE == -1019 && CLCG_UNKNOWN_SOLVER == -1016, "complex ids");
+int main() {
+    lcg_para p = lcg_default_parameters(); clcg_para q = clcg_default_parameters();
+    int (*f)(lcg_axfunc_cuda_ptr, lcg_progress_cuda_ptr, lcg_float*, const lcg_float*, const int, const int, const lcg_para*, void*,
+             cublasHandle_t, cusparseHandle_t, lcg_solver_enum) = lcg_solver_cuda;
+    int (*g)(clcg_axfunc_cuda_ptr, clcg_progress_cuda_ptr, cuDoubleComplex*, const cuDoubleComplex*, const int, const int, const clcg_para*,
+             void*, cublasHandle_t, cusparseHandle_t, clcg_solver_enum) = clcg_solver_cuda;
+    return (p.epsilon == 1e-6 && q.epsilon == 1e-6 && f && g && lcg_select_solver("LCG_PG") == LCG_PG && lcg_select_solver("x") == LCG_CGS) ? 0 : 1;
+}
+"""
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "names.cu")
+        open(path, "w").write(src)
+        exe = os.path.join(td, "names")
+        r = subprocess.run(["/usr/local/cuda/bin/nvcc", "-std=c++17", "-I", os.path.join(root, "include"), path, "-L", os.path.join(root, "liblcg_b200"),
+                            "-llcgb200", "-Xlinker", "-rpath=" + os.path.join(root, "liblcg_b200"), "-o", exe], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-3000:]
+        assert subprocess.run([exe]).returncode == 0
