@@ -194,6 +194,7 @@ def run_ours(args, wl):
         dist.init_process_group("nccl", device_id=dev)
 
     n, nnz = g ** 3, stencil_nnz(kind, g)
+    transport = None
     iters = args.iters
     para = api.lcg_default_parameters(epsilon=1e-300, max_iterations=iters)
 
@@ -202,6 +203,7 @@ def run_ours(args, wl):
         from liblcg_b200 import dist as ldist
         part = ldist.build_stencil_partition(kind, g, rank, world, dev, jacobi=(solver == "PCG"))
         op, b_d, n_loc = part.op, part.b, part.n_local
+        transport = "nvlink-p2p (halo + reduction totals pushed into peer memory from inside the kernels)" if part.p2p else "nccl (send/recv halo + allreduce)"
     else:
         nz = C.c_longlong()
         assert lib.lcgb200_gen_stencil(KIND_ID[kind], g, 0, n, None, None, None, 0, C.byref(nz), None) == 0
@@ -377,7 +379,7 @@ def run_ours(args, wl):
         "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "stencil": kind, "grid": g, "rows": n, "nnz": nnz, "solver": solver,
-                   "iterations_per_step": iters, "parallelism": f"row-partition x{world}" if world > 1 else "single GPU",
+                   "iterations_per_step": iters, "parallelism": f"row-partition x{world}" if world > 1 else "single GPU", "transport": transport,
                    "l2": f"inputs larger than L2: CSR {12 * nnz / world / 1e9:.2f} GB per GPU streamed every iteration (no flush needed)",
                    "lanes_per_row": info["lanes_per_row"], "tiles": info["n_tiles"]},
         "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,

@@ -144,6 +144,17 @@ int lcgb200_comm_stats(lcgb200_comm_t comm, int* halo_exchanges, int* allreduces
 int lcgb200_csr_set_partition(lcgb200_csr_t A, lcgb200_comm_t comm, long long n_global, int n_peers, const int* peer_ranks,
 	const int* send_counts, const int* send_idx, const int* recv_counts);
 
+/* NVLink peer-memory transport (optional, ranks on one NVLink/NVSwitch node): every rank exports the CUDA-IPC handle of
+ * its communication window after lcgb200_csr_set_partition, the handles are exchanged by the caller (all-gather), and
+ * lcgb200_comm_p2p_attach maps the peers' windows.  From then on real solves push halo entries and reduction totals
+ * straight into the peers' memory from inside the kernels (no NCCL call on the iteration path).
+ * handles: size x LCGB200_IPC_HANDLE_BYTES, in rank order; n_ghost_of_rank: size values (each rank's *n_ghost_out);
+ * remote_off: for each of MY n_peers neighbours, in the order given to lcgb200_csr_set_partition, the offset at which
+ * my entries start inside THAT rank's ghost region. */
+#define LCGB200_IPC_HANDLE_BYTES 64
+int lcgb200_comm_p2p_handle(lcgb200_comm_t comm, void* handle_out, long long* n_ghost_out);
+int lcgb200_comm_p2p_attach(lcgb200_comm_t comm, const void* handles, const long long* n_ghost_of_rank, const long long* remote_off);
+
 /* Sentinel callbacks: never called; their ADDRESS selects the built-in operator.  instance = lcgb200_csr_t. */
 void lcgb200_csr_ax(void* instance, lcgb200_cublas_t, lcgb200_cusparse_t, lcgb200_dnvec_t x, lcgb200_dnvec_t Ax, const int n, const int nz);
 void lcgb200_jacobi_mx(void* instance, lcgb200_cublas_t, lcgb200_cusparse_t, lcgb200_dnvec_t x, lcgb200_dnvec_t Mx, const int n, const int nz);

@@ -504,6 +504,8 @@ int lcgb200_csr_spmv(lcgb200_csr_t A, const void* x, void* y, int op, void* stre
 	cudaStream_t s = (cudaStream_t)stream;
 	return guarded([&]() {
 		ensure_state(h, s);
+		if (h->comm && h->comm->size() > 1 && op == 0)
+			h->comm->halo(const_cast<void*>(x), h->value_type == LCGB200_REAL ? 8 : 16, s, h->p2p_dev() != nullptr, h->d_state);
 		if (h->value_type == LCGB200_REAL)
 		{
 			if (op == 0) launch_spmv<double, false>(h->view<double>(), (const double*)x, (double*)y, EpiNone<double>{}, h->d_state, h->d_partials, s);
@@ -527,6 +529,8 @@ int lcgb200_csr_spmv_dot(lcgb200_csr_t A, const void* x, void* y, const void* w,
 	cudaStream_t s = (cudaStream_t)stream;
 	return guarded([&]() {
 		ensure_state(h, s);
+		if (h->comm && h->comm->size() > 1)
+			h->comm->halo(const_cast<void*>(x), h->value_type == LCGB200_REAL ? 8 : 16, s, h->p2p_dev() != nullptr, h->d_state);
 		if (h->value_type == LCGB200_REAL)
 			launch_spmv<double, false>(h->view<double>(), (const double*)x, (double*)y, EpiProbeReal{(const double*)w, dots_dev}, h->d_state, h->d_partials, s);
 		else

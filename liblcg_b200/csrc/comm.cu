@@ -16,6 +16,7 @@
 #include <cstring>
 #include <vector>
 #include <string>
+#include <algorithm>
 
 namespace lcgb200 {
 
@@ -75,6 +76,58 @@ void nccl_check(int rc, const char* what)
 	throw CudaFailure();
 }
 
+// NVLink transport, one kernel per halo exchange (grid <= SM count, so all blocks are co-resident):
+//   1. push my boundary entries straight into the peers' mailboxes (remote stores over NVLink);
+//   2. every block fences at system scope and takes a ticket; the last one bumps my sequence flag in each peer's window;
+//   3. every block waits until the peers' flags for this exchange have arrived in MY window and copies its share of my
+//      mailbox into the ghost tail of x — the SpMV that follows is the unmodified single-GPU kernel.
+// Pushing never waits on anything, so two ranks running this kernel cannot block each other.
+template <class T>
+__global__ void __launch_bounds__(256) k_halo_exchange(CommDev* c, T* __restrict__ x, DevState* st)
+{
+	if (st_done(st)) return;
+	const unsigned long long seq = c->halo_seq + 1;
+	const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+	for (int p = 0; p < c->n_peers; p++)
+	{
+		const int cnt = c->send_count[p];
+		if (cnt <= 0) continue;
+		T* dst = reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(c->win[c->peer_rank[p]]) + kMailboxOffset)
+			+ (size_t)(seq & 1) * (size_t)c->remote_ghost[p] + (size_t)c->remote_off[p];
+		const int first = c->send_first[p], off = c->send_off[p];
+		const bool contig = c->contiguous[p] != 0;
+		for (int i = gtid; i < cnt; i += gsz) dst[i] = contig ? x[first + i] : x[c->send_idx[off + i]];
+	}
+	__threadfence_system();
+	__shared__ int s_flag;
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		const bool last = atomicAdd(&c->ticket, 1u) == gridDim.x - 1;
+		if (last)
+		{
+			__threadfence_system();
+			for (int p = 0; p < c->n_peers; p++)
+				if (c->send_count[p] > 0) st_relaxed_sys(&c->win[c->peer_rank[p]]->halo_flag[c->rank], seq);
+		}
+		bool ok = true;
+		for (int p = 0; p < c->n_peers && ok; p++)
+			if (c->recv_count[p] > 0) ok = spin_until(&c->win[c->rank]->halo_flag[c->peer_rank[p]], seq);
+		if (!ok) { st->ret = RC_UNKNOWN; st->done = 1; c->abort_flag = 1; }
+		s_flag = ok ? 1 : 0;
+	}
+	__syncthreads();
+	if (s_flag)
+	{
+		const T* mail = reinterpret_cast<const T*>(reinterpret_cast<const unsigned char*>(c->win[c->rank]) + kMailboxOffset) + (size_t)(seq & 1) * (size_t)c->n_ghost;
+		T* ghost = x + c->n_local;
+		for (int i = gtid; i < c->n_ghost; i += gsz) ghost[i] = __ldcv(mail + i);
+	}
+	// the block that leaves last publishes the new sequence number for the next exchange
+	__syncthreads();
+	if (threadIdx.x == 0 && atomicAdd(&c->ticket2, 1u) == gridDim.x - 1) { c->halo_seq = seq; c->ticket = 0u; c->ticket2 = 0u; }
+}
+
 // send_buf[i] = x[idx[i]] for the entries that are not sent in place
 template <class T>
 __global__ void k_halo_pack(const T* __restrict__ x, const int* __restrict__ idx, T* __restrict__ out, int count)
@@ -95,9 +148,19 @@ public:
 	int* d_send_idx = nullptr;     // concatenated local indices of the packed peers
 	void* d_send_buf = nullptr;    // packed values (16 bytes per entry: enough for double2)
 	int halos = 0, allreduces = 0;
+	// NVLink peer-memory transport (optional; needs CUDA IPC between the ranks' devices)
+	CommWindow* window = nullptr; size_t window_bytes = 0;
+	CommDev* d_dev = nullptr; CommDev h_dev;
+	void* peer_map[kMaxRanks] = {nullptr};
+	bool p2p_ready = false;
+	int push_grid = 1;
+
+	CommDev* dev() override { return p2p_ready ? d_dev : nullptr; }
 
 	~NcclComm() override
 	{
+		for (int r = 0; r < kMaxRanks; r++) if (peer_map[r]) cudaIpcCloseMemHandle(peer_map[r]);
+		cudaFree(window); cudaFree(d_dev);
 		cudaFree(d_send_idx); cudaFree(d_send_buf);
 		if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
 	}
@@ -110,9 +173,15 @@ public:
 		allreduces++;
 	}
 
-	void halo(void* x_ext, int elem_bytes, cudaStream_t s) override
+	void halo(void* x_ext, int elem_bytes, cudaStream_t s, bool p2p, DevState* st) override
 	{
 		if (peers.empty()) return;
+		if (p2p && p2p_ready && elem_bytes == 8)
+		{
+			k_halo_exchange<double><<<push_grid, 256, 0, s>>>(d_dev, (double*)x_ext, st);
+			halos++;
+			return;
+		}
 		char* x = static_cast<char*>(x_ext);
 		if (n_packed > 0)
 		{
@@ -243,6 +312,75 @@ int lcgb200_csr_set_partition(lcgb200_csr_t A, lcgb200_comm_t comm, long long n_
 		}
 		h->comm = c;
 		h->n_global = n_global;
+		// window for the NVLink transport: header + double-buffered mailbox of 16-byte slots
+		c->p2p_ready = false;
+		for (int r = 0; r < kMaxRanks; r++) if (c->peer_map[r]) { cudaIpcCloseMemHandle(c->peer_map[r]); c->peer_map[r] = nullptr; }
+		cudaFree(c->window); c->window = nullptr; cudaFree(c->d_dev); c->d_dev = nullptr;
+		if (c->size_ <= kMaxRanks && n_peers <= kMaxRanks)
+		{
+			c->window_bytes = kMailboxOffset + 2 * (size_t)std::max(c->n_ghost, 1) * 16;
+			LCG_CUDA_CHECK(cudaMalloc((void**)&c->window, c->window_bytes));
+			LCG_CUDA_CHECK(cudaMemset(c->window, 0, c->window_bytes));
+			LCG_CUDA_CHECK(cudaMalloc((void**)&c->d_dev, sizeof(CommDev)));
+			CommDev& d = c->h_dev;
+			std::memset(&d, 0, sizeof(d));
+			d.rank = c->rank_; d.size = c->size_; d.n_local = c->n_local; d.n_ghost = c->n_ghost; d.n_peers = n_peers; d.n_packed = c->n_packed;
+			d.send_idx = c->d_send_idx;
+			int max_send = 1;
+			for (int p = 0; p < n_peers; p++)
+			{
+				const NcclComm::Peer& pe = c->peers[(size_t)p];
+				d.peer_rank[p] = pe.rank; d.send_first[p] = pe.send_first; d.send_count[p] = pe.send_count; d.send_off[p] = pe.send_off;
+				d.contiguous[p] = pe.contiguous ? 1 : 0; d.recv_count[p] = pe.recv_count;
+				max_send = std::max(max_send, pe.send_count);
+			}
+			c->push_grid = std::max(1, std::min(64, (std::max(max_send, c->n_ghost) + 1023) / 1024));
+			LCG_CUDA_CHECK(cudaDeviceSynchronize());
+		}
+		return 0;
+	});
+}
+
+int lcgb200_comm_p2p_handle(lcgb200_comm_t comm, void* handle_out, long long* n_ghost_out)
+{
+	NcclComm* c = reinterpret_cast<NcclComm*>(comm);
+	if (!c || !handle_out) return LCGB200_INVALID_POINTER;
+	if (!c->window) { set_error_msg("attach a partition (lcgb200_csr_set_partition) before asking for the window handle"); return LCGB200_SIZE_NOT_MATCH; }
+	return guarded_comm([&]() {
+		cudaIpcMemHandle_t hdl;
+		LCG_CUDA_CHECK(cudaIpcGetMemHandle(&hdl, c->window));
+		static_assert(sizeof(hdl) == LCGB200_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t is 64 bytes");
+		std::memcpy(handle_out, &hdl, sizeof(hdl));
+		if (n_ghost_out) *n_ghost_out = c->n_ghost;
+		return 0;
+	});
+}
+
+int lcgb200_comm_p2p_attach(lcgb200_comm_t comm, const void* handles, const long long* n_ghost_of_rank, const long long* remote_off)
+{
+	NcclComm* c = reinterpret_cast<NcclComm*>(comm);
+	if (!c || !handles || !n_ghost_of_rank || !remote_off) return LCGB200_INVALID_POINTER;
+	if (!c->window || !c->d_dev) return LCGB200_SIZE_NOT_MATCH;
+	return guarded_comm([&]() {
+		CommDev& d = c->h_dev;
+		for (int r = 0; r < c->size_; r++)
+		{
+			if (r == c->rank_) { d.win[r] = c->window; continue; }
+			cudaIpcMemHandle_t hdl;
+			std::memcpy(&hdl, static_cast<const char*>(handles) + (size_t)r * sizeof(hdl), sizeof(hdl));
+			void* mapped = nullptr;
+			LCG_CUDA_CHECK(cudaIpcOpenMemHandle(&mapped, hdl, cudaIpcMemLazyEnablePeerAccess));
+			c->peer_map[r] = mapped;
+			d.win[r] = static_cast<CommWindow*>(mapped);
+		}
+		for (int p = 0; p < d.n_peers; p++)
+		{
+			d.remote_off[p] = remote_off[p];
+			d.remote_ghost[p] = n_ghost_of_rank[d.peer_rank[p]];
+		}
+		LCG_CUDA_CHECK(cudaMemcpy(c->d_dev, &d, sizeof(d), cudaMemcpyHostToDevice));
+		LCG_CUDA_CHECK(cudaDeviceSynchronize());
+		c->p2p_ready = true;
 		return 0;
 	});
 }

@@ -51,6 +51,71 @@ enum : int {
 	SC_PART1, SC_PART2, SC_PART3
 };
 
+// ---- multi-GPU over NVLink peer memory (comm.cu) ------------------------------------------------------------
+// Every rank owns one CommWindow in device memory, mapped into all peers with CUDA IPC.  Peers PUSH into it:
+//   * the per-rank totals of a fused reduction (ar_val / ar_flag): the last block of the producing kernel stores its
+//     totals into every rank's window, so the "allreduce" is 8 remote stores in the kernel's tail plus a local sum;
+//   * the halo entries of the next SpMV input (mailbox behind the header, double-buffered) and a sequence flag.
+// Flags carry monotonically increasing sequence numbers (never reset), written with st.release.sys after a
+// __threadfence_system() and polled with ld.acquire.sys.
+constexpr int kMaxRanks = 8;
+constexpr int kArSlots = 4;
+struct CommWindow {
+	unsigned long long ar_flag[kArSlots][kMaxRanks];
+	double ar_val[kArSlots][kMaxRanks][kMaxRed];
+	unsigned long long halo_flag[kMaxRanks];     // [source rank]: sequence number of the last halo it pushed to me
+	unsigned long long pad[8];
+	// mailbox: 2 buffers x n_ghost x 16 bytes follow (offset kMailboxOffset)
+};
+constexpr size_t kMailboxOffset = (sizeof(CommWindow) + 255) & ~size_t(255);
+
+struct CommDev {	// device-resident, private to the rank
+	unsigned long long ar_seq, halo_seq;
+	int rank, size, n_local, n_ghost, n_peers, n_packed;
+	unsigned int ticket, ticket2, abort_flag, pad0;
+	CommWindow* win[kMaxRanks];                  // win[rank] = own window, others = IPC mappings of the peers' windows
+	int peer_rank[kMaxRanks], send_first[kMaxRanks], send_count[kMaxRanks], send_off[kMaxRanks], contiguous[kMaxRanks], recv_count[kMaxRanks];
+	long long remote_off[kMaxRanks];             // where my entries start inside the peer's ghost region
+	long long remote_ghost[kMaxRanks];           // the peer's n_ghost (size of one of its mailbox buffers)
+	const int* send_idx;                         // packed (non-contiguous) send indices
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
+{
+	asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+// flag store AFTER an explicit __threadfence_system(): no second fence (a st.release.sys per peer would pay one NVLink
+// round trip each)
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v)
+{
+	asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
+{
+	unsigned long long v;
+	asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ unsigned long long global_ns()
+{
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+constexpr unsigned long long kSpinTimeoutNs = 4000000000ull;   // a peer that never shows up ends the solve with an error, not a hang
+// spin until *flag >= want; false on timeout
+__device__ __forceinline__ bool spin_until(const unsigned long long* flag, unsigned long long want)
+{
+	if (ld_acquire_sys(flag) >= want) return true;
+	const unsigned long long t0 = global_ns();
+	while (ld_acquire_sys(flag) < want)
+	{
+		__nanosleep(64);
+		if (global_ns() - t0 > kSpinTimeoutNs) return false;
+	}
+	return true;
+}
+
 struct DevState {
 	double sc[kNumSc];
 	double red[kMaxRed];      // totals of the last reduction (multi-GPU: all-reduced in place before finish)
@@ -66,7 +131,30 @@ struct DevState {
 	int half;                 // TFQMR half-step index / BICGSTAB2 restart marker
 	unsigned int ticket;
 	unsigned int pad;
+	CommDev* comm;            // multi == 2: NVLink peer-memory transport
 };
+
+// multi-GPU: hand the totals of a fused reduction to the cross-rank sum.  Called by the whole first warp of the last
+// block (grid_reduce).  multi == 1: leave them in st->red for ncclAllReduce; multi == 2: lane p pushes them into rank
+// p's window — all peers in parallel, one system-scope fence, one flag store each: a single NVLink round trip.
+__device__ __forceinline__ void publish_totals(DevState* st, const double* tot, int nred)
+{
+	const int lane = threadIdx.x & 31;
+	if (st->multi == 2)
+	{
+		CommDev* c = st->comm;
+		const unsigned long long seq = c->ar_seq + 1;
+		const int slot = (int)(seq % kArSlots);
+		if (lane < c->size)
+			for (int r = 0; r < nred; r++) c->win[lane]->ar_val[slot][c->rank][r] = tot[r];
+		__threadfence_system();
+		if (lane < c->size) st_relaxed_sys(&c->win[lane]->ar_flag[slot][c->rank], seq);
+		__syncwarp();
+		if (lane == 0) c->ar_seq = seq;
+	}
+	else if (lane == 0)
+		for (int r = 0; r < nred; r++) st->red[r] = tot[r];
+}
 
 __device__ __forceinline__ int st_done(const DevState* st) { return *((volatile const int*)&st->done); }
 
@@ -190,8 +278,9 @@ __device__ __forceinline__ double warp_sum(double v)
 }
 
 // Block-reduce acc[0..NRED), publish per-block partials, elect the last block, and let it total the partials
-// in a fixed order (any block size that is a multiple of 32, up to kMaxWarps warps).  Returns true in exactly one thread of the whole grid (thread 0 of the last block), with
-// tot[] holding the grid totals.  partials must hold gridDim.x * NRED doubles.
+// in a fixed order (any block size that is a multiple of 32, up to kMaxWarps warps).  Returns true in the 32 threads of
+// the first warp of the last block (and nowhere else), each with tot[] holding the grid totals: lane 0 runs the scalar
+// epilogue, the whole warp takes part in the cross-GPU publish.  partials must hold gridDim.x * NRED doubles.
 template <int NRED>
 __device__ __forceinline__ bool grid_reduce(const double* acc, double* partials, unsigned int* ticket, double* tot)
 {
@@ -233,19 +322,16 @@ __device__ __forceinline__ bool grid_reduce(const double* acc, double* partials,
 		if (lane == 0) s_red[r][warp] = v;
 	}
 	__syncthreads();
-	if (threadIdx.x == 0)
-	{
+	if (warp != 0) return false;
 #pragma unroll
-		for (int r = 0; r < NRED; r++)
-		{
-			double v = 0.0;
-			for (int w = 0; w < nwarps; w++) v += s_red[r][w];
-			tot[r] = v;
-		}
-		*ticket = 0u;
-		return true;
+	for (int r = 0; r < NRED; r++)
+	{	// every lane sums the same values in the same order: identical totals without a broadcast
+		double v = 0.0;
+		for (int w = 0; w < nwarps; w++) v += s_red[r][w];
+		tot[r] = v;
 	}
-	return false;
+	if (lane == 0) *ticket = 0u;
+	return true;
 }
 
 struct OpBase {
@@ -286,8 +372,8 @@ __global__ void __launch_bounds__(kThreads) k_vec(Op op_in, size_t n, DevState* 
 		double tot[Op::NRED > 0 ? Op::NRED : 1];
 		if (grid_reduce<(Op::NRED > 0 ? Op::NRED : 1)>(acc, partials, &st->ticket, tot))
 		{
-			if (st->multi) { for (int r = 0; r < Op::NRED; r++) st->red[r] = tot[r]; }
-			else op.finish(st, tot);
+			if (st->multi) publish_totals(st, tot, Op::NRED);
+			else if ((threadIdx.x & 31) == 0) op.finish(st, tot);
 		}
 	}
 }
@@ -302,6 +388,31 @@ __global__ void k_finish(Op op_in, DevState* st)
 	op.begin(st);
 	double tot[kMaxRed];
 	for (int r = 0; r < kMaxRed; r++) tot[r] = st->red[r];
+	op.finish(st, tot);
+}
+
+// NVLink transport: wait until every rank's totals of the current reduction have landed in my window, sum them in
+// rank order (bitwise identical on all ranks) and run the scalar epilogue.  <<<1, 32>>>
+template <class Op>
+__global__ void k_finish_p2p(Op op_in, DevState* st, int nred)
+{
+	if (st_done(st)) return;
+	Op op = op_in;
+	if (!op.active(st)) return;
+	CommDev* c = st->comm;
+	const unsigned long long seq = c->ar_seq;     // set by the producing kernel, earlier in this stream
+	const int slot = (int)(seq % kArSlots);
+	CommWindow* w = c->win[c->rank];
+	bool ok = true;
+	if ((int)threadIdx.x < c->size) ok = spin_until(&w->ar_flag[slot][threadIdx.x], seq);
+	ok = __all_sync(0xffffffffu, ok);
+	if (threadIdx.x != 0) return;
+	if (!ok) { st->ret = RC_UNKNOWN; st->done = 1; c->abort_flag = 1; return; }
+	double tot[kMaxRed];
+	for (int r = 0; r < kMaxRed; r++) tot[r] = 0.0;
+	for (int src = 0; src < c->size; src++)
+		for (int r = 0; r < nred; r++) tot[r] += *((volatile double*)&w->ar_val[slot][src][r]);
+	op.begin(st);
 	op.finish(st, tot);
 }
 

@@ -278,8 +278,8 @@ __global__ void __launch_bounds__(kSpmvThreads, TileCfg<T>::CTAS) k_spmv(CsrDev<
 		double tot[Epi::NRED > 0 ? Epi::NRED : 1];
 		if (grid_reduce<(Epi::NRED > 0 ? Epi::NRED : 1)>(acc, partials, &st->ticket, tot))
 		{
-			if (st->multi) { for (int r = 0; r < Epi::NRED; r++) st->red[r] = tot[r]; }
-			else epi.finish(st, tot);
+			if (st->multi) publish_totals(st, tot, Epi::NRED);
+			else if ((threadIdx.x & 31) == 0) epi.finish(st, tot);
 		}
 	}
 }

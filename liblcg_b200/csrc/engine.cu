@@ -134,7 +134,8 @@ void Engine::reserve(size_t bytes)
 void Engine::start(const DevState& init)
 {
 	*h_st = init;
-	h_st->multi = multi() ? 1 : 0;
+	h_st->multi = multi() ? (p2p() ? 2 : 1) : 0;
+	h_st->comm = p2p() ? cache->p2p_dev() : nullptr;
 	LCG_CUDA_CHECK(cudaMemcpyAsync(d_st, h_st, sizeof(DevState), cudaMemcpyHostToDevice, stream));
 	LCG_CUDA_CHECK(cudaEventRecord(ev[2], stream));
 	seen_checks = 0;

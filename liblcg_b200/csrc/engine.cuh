@@ -18,8 +18,11 @@ struct Comm {
 	virtual int size() const = 0;
 	// sum-allreduce `count` doubles in place on the device, ordered on `s`
 	virtual void allreduce(double* dev, int count, cudaStream_t s) = 0;
-	// fill the ghost tail of an extended vector (elements [n_local, n_local + n_ghost)) from the owning ranks
-	virtual void halo(void* x_ext, int elem_bytes, cudaStream_t s) = 0;
+	// make the ghost entries of an extended vector (elements [n_local, n_local + n_ghost)) available: NCCL transport
+	// fills the vector's ghost tail; the NVLink transport (p2p) pushes my boundary entries into the peers' mailboxes
+	virtual void halo(void* x_ext, int elem_bytes, cudaStream_t s, bool p2p, DevState* st) = 0;
+	// device state of the NVLink peer-memory transport, or null when only NCCL is available
+	virtual CommDev* dev() { return nullptr; }
 };
 
 // ---- handle behind lcgb200_csr_t ------------------------------------------------------------------------
@@ -43,6 +46,7 @@ struct CsrHandle {
 	DevState* d_state = nullptr; DevState* h_state = nullptr; DevState* h_state2 = nullptr; double* d_partials = nullptr;
 	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 
+	CommDev* p2p_dev() const { return (comm && value_type == 0) ? comm->dev() : nullptr; }
 	template <class T> CsrDev<T> view() const
 	{
 		CsrDev<T> v; v.n_rows = n_rows; v.n_cols = n_cols; v.nnz = nnz; v.n_tiles = n_tiles; v.lpr = lpr; v.chunk = chunk;
@@ -117,6 +121,7 @@ public:
 	double device_ms();                 // start..now on the stream (syncs)
 
 	bool multi() const { return comm != nullptr && comm->size() > 1; }
+	bool p2p() const { return multi() && cache && cache->p2p_dev() != nullptr; }
 
 	template <class Op> void vec(const Op& op, size_t n)
 	{
@@ -129,8 +134,12 @@ public:
 
 	template <class Op> void finish_multi(const Op& op, int nred)
 	{
-		comm->allreduce(reinterpret_cast<double*>(reinterpret_cast<char*>(d_st) + offsetof(DevState, red)), nred, stream);
-		k_finish<Op><<<1, 1, 0, stream>>>(op, d_st);
+		if (p2p()) k_finish_p2p<Op><<<1, 32, 0, stream>>>(op, d_st, nred);
+		else
+		{
+			comm->allreduce(reinterpret_cast<double*>(reinterpret_cast<char*>(d_st) + offsetof(DevState, red)), nred, stream);
+			k_finish<Op><<<1, 1, 0, stream>>>(op, d_st);
+		}
 		launches++;
 	}
 
@@ -139,7 +148,7 @@ public:
 	{
 		if (A.h)
 		{
-			if (multi()) comm->halo(x, (int)sizeof(T), stream);
+			if (multi()) comm->halo(x, (int)sizeof(T), stream, p2p(), d_st);
 			cudaEvent_t pe = profiling ? prof_begin(0) : nullptr;
 			if (op == 0) launch_spmv<T, false, Epi>(A.h->template view<T>(), x, y, epi, d_st, d_partials, stream);
 			else if (op == 1) launch_spmv<T, false, Epi>(A.h->template tview<T>(), x, y, epi, d_st, d_partials, stream);

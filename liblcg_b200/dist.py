@@ -13,6 +13,7 @@ the stencils.  `plan_partition` is pure tensor code (CPU or CUDA) and is what th
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -136,6 +137,7 @@ class Partition:
     plan: HaloPlan
     n_local: int
     b: "object" = None
+    p2p: bool = False
 
     def close(self):
         self.op.close()
@@ -154,6 +156,37 @@ def attach_plan(op: api.CsrOperator, comm: Communicator, plan: HaloPlan) -> None
         raise RuntimeError(f"lcgb200_csr_set_partition failed ({rc}): {api.last_error()}")
 
 
+def enable_p2p(comm: Communicator, plan: HaloPlan, group=None) -> bool:
+    """NVLink peer-memory transport: exchange the CUDA-IPC handles of the ranks' communication windows and the offsets at
+    which each rank's entries start inside its neighbours' ghost regions, then map the peers' windows.  Returns False
+    (and leaves the NCCL transport in place) when the devices cannot map each other's memory."""
+    import torch.distributed as dist
+    lib = _lib.load()
+    buf = (C.c_ubyte * 64)()
+    ng = C.c_longlong()
+    rc = lib.lcgb200_comm_p2p_handle(comm.handle, buf, C.byref(ng))
+    # where the entries a peer sends me start inside MY ghost region (peer order = ascending rank = ghost order)
+    my_off, off = {}, 0
+    for p in plan.peers:
+        my_off[p] = off
+        off += plan.recv_from.get(p, 0)
+    info = {"ok": rc == 0, "handle": bytes(buf), "n_ghost": int(ng.value), "recv_off": my_off}
+    gathered = [None] * comm.world
+    dist.all_gather_object(gathered, info, group=group)
+    if not all(g["ok"] for g in gathered):
+        return False
+    handles = b"".join(g["handle"] for g in gathered)
+    n_ghost = np.asarray([g["n_ghost"] for g in gathered], dtype=np.int64)
+    remote_off = np.asarray([gathered[p]["recv_off"].get(comm.rank, 0) for p in plan.peers] or [0], dtype=np.int64)
+    hb = (C.c_ubyte * len(handles)).from_buffer_copy(handles)
+    rc = lib.lcgb200_comm_p2p_attach(comm.handle, hb, n_ghost.ctypes.data, remote_off.ctypes.data)
+    ok = [None] * comm.world
+    dist.all_gather_object(ok, rc == 0, group=group)
+    if not all(ok):
+        raise RuntimeError(f"lcgb200_comm_p2p_attach failed on some rank ({rc}): {api.last_error()}")
+    return True
+
+
 def partition_csr(row_ptr_local, col_global, val, bounds, rank: int, jacobi=False, group=None) -> Partition:
     """This rank's rows (row_ptr rebased to 0, GLOBAL column ids, values; torch CUDA tensors or numpy arrays)
     -> rectangular operator + communicator + halo plan."""
@@ -169,7 +202,12 @@ def partition_csr(row_ptr_local, col_global, val, bounds, rank: int, jacobi=Fals
         op = api.CsrOperator(np.asarray(row_ptr_local), new_col.numpy(), np.asarray(val), n_cols=n_loc + plan.n_ghost, jacobi=jacobi)
     comm = Communicator(rank, world, group=group)
     attach_plan(op, comm, plan)
-    return Partition(op, comm, plan, n_loc)
+    p2p = False
+    if on_dev and not op.complex and os.environ.get("LCGB200_NO_P2P", "0") != "1":   # LCGB200_NO_P2P=1: NCCL transport (comparison runs)
+        p2p = enable_p2p(comm, plan, group=group)
+    part = Partition(op, comm, plan, n_loc)
+    part.p2p = p2p
+    return part
 
 
 KIND_ID = {"7pt": 0, "27pt": 1, "7pt_cd": 2}

@@ -60,6 +60,13 @@ static int hist_push(o_hist* h, int k, double r)
 static long g_seed_time = 0;
 void lcgoracle_set_time(long t) { g_seed_time = t; }
 
+/* Summation order of the inner products.  0 (default) = left-to-right, the reference's order (algebra.cpp:154-163,
+ * lcg_complex.cpp:143-167) — the only order the golden vectors and the bit-exact pinning use.  1 = pairwise (tree), the
+ * order class of the GPU's reductions: used by the GPU parity tests to tell "same algorithm, more accurate sums" (which
+ * shortens the reference's erratic complex BiCG runs by ~5 %) from a real discrepancy. */
+static int g_sum_tree = 0;
+void lcgoracle_set_summation(int tree) { g_sum_tree = tree ? 1 : 0; }
+
 /* ---------------------------------------------------------------- real helpers */
 typedef struct { int n; const int* rp; const int* ci; const double* v; const double* diag; } o_csr;
 
@@ -83,8 +90,16 @@ static void o_mx(const o_csr* A, const double* x, double* y)
 }
 
 /* algebra.cpp:154-163 — serial left-to-right accumulation */
+static double o_dot_tree(const double* a, const double* b, int lo, int hi)
+{
+	if (hi - lo <= 8) { double s = 0.0; for (int i = lo; i < hi; i++) s += a[i] * b[i]; return s; }
+	int mid = lo + (hi - lo) / 2;
+	return o_dot_tree(a, b, lo, mid) + o_dot_tree(a, b, mid, hi);
+}
+
 static double o_dot(const double* a, const double* b, int n)
 {
+	if (g_sum_tree) return o_dot_tree(a, b, 0, n);
 	double s = 0.0;
 	for (int i = 0; i < n; i++) s += a[i] * b[i];
 	return s;
@@ -484,8 +499,25 @@ static void oc_ax(const oc_csr* A, const zc* x, zc* y, int op)
 }
 
 /* lcg_complex.cpp:156-167 — <a,b> = sum conj(a_i) b_i, serial */
+static zc oc_sum_tree(const zc* a, const zc* b, int lo, int hi, int conj_first)
+{
+	if (hi - lo <= 8)
+	{
+		double re = 0.0, im = 0.0;
+		for (int i = lo; i < hi; i++)
+		{
+			if (conj_first) { re += (creal(a[i]) * creal(b[i]) + cimag(a[i]) * cimag(b[i])); im += (creal(a[i]) * cimag(b[i]) - cimag(a[i]) * creal(b[i])); }
+			else { re += (creal(a[i]) * creal(b[i]) - cimag(a[i]) * cimag(b[i])); im += (creal(a[i]) * cimag(b[i]) + cimag(a[i]) * creal(b[i])); }
+		}
+		return CMPLX(re, im);
+	}
+	int mid = lo + (hi - lo) / 2;
+	return oc_sum_tree(a, b, lo, mid, conj_first) + oc_sum_tree(a, b, mid, hi, conj_first);
+}
+
 static zc oc_inner(const zc* a, const zc* b, int n)
 {
+	if (g_sum_tree) return oc_sum_tree(a, b, 0, n, 1);
 	double re = 0.0, im = 0.0;
 	for (int i = 0; i < n; i++)
 	{
@@ -498,6 +530,7 @@ static zc oc_inner(const zc* a, const zc* b, int n)
 /* lcg_complex.cpp:143-154 — unconjugated sum a_i b_i, serial */
 static zc oc_dot(const zc* a, const zc* b, int n)
 {
+	if (g_sum_tree) return oc_sum_tree(a, b, 0, n, 0);
 	double re = 0.0, im = 0.0;
 	for (int i = 0; i < n; i++)
 	{

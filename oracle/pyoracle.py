@@ -106,6 +106,13 @@ class Oracle:
         """Pin the seed clcg_vecrnd() derives from time(0) (reference lcg_complex.cpp:118-127)."""
         getattr(self.lib, self.pfx + "set_time")(C.c_long(t))
 
+    def set_summation(self, tree: bool) -> None:
+        """Port only: pairwise (tree) instead of the reference's left-to-right inner products — the order class of the GPU's
+        reductions.  Never used for pinning; see lcgoracle_set_summation in lcg_oracle.c."""
+        if self.kind != "port":
+            raise ValueError("the unmodified reference sums left to right")
+        self.lib.lcgoracle_set_summation(C.c_int(1 if tree else 0))
+
     def vecrnd(self, n: int) -> np.ndarray:
         out = np.empty(n, dtype=np.complex128)
         getattr(self.lib, self.pfx + "vecrnd")(_p(out, C.c_double), C.c_int(n))

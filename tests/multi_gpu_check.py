@@ -63,7 +63,7 @@ def main():
                         sens = float(np.linalg.norm(cp2.x - cpu.x) / np.linalg.norm(cpu.x))
                     ok = ok and (rel <= 1e-8 or rel <= 20 * sens)
                 print(f"{'OK  ' if ok else 'FAIL'} world={world} {kind:7s} g={g:3d} solver={sid} {name:9s} ret {r.ret}/{cpu.ret} it {r.iterations}/{cpu.iters} "
-                      f"rel {rel:.2e} launches {r.info.kernel_launches} comm {part.comm.stats()}", flush=True)
+                      f"rel {rel:.2e} launches {r.info.kernel_launches} transport {'nvlink-p2p' if part.p2p else 'nccl'} comm {part.comm.stats()}", flush=True)
                 failures += 0 if ok else 1
         part.close()
     t = torch.tensor([failures], device=dev)

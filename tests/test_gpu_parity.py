@@ -76,11 +76,23 @@ def assert_iters_parity(it_gpu, it_ref, resolve_iters, samples=8):
     resolve_iters(seed) -> iteration count of the oracle on b perturbed with that seed."""
     if iters_close(it_gpu, it_ref):
         return
-    band = np.array([it_ref] + [resolve_iters(1000 + s) for s in range(samples)], dtype=np.float64)
+    band = [it_ref] + [resolve_iters(1000 + s) for s in range(samples)]
+    # the GPU's reductions are tree-ordered, the reference's serial: on the reference's ill-conditioned complex fixtures
+    # the more accurate sums alone shift the crossing of BiCG by ~5 % (oracle run both ways), so the comparison
+    # ensemble holds the oracle with either summation order
+    _PORT.set_summation(True)
+    try:
+        band += [resolve_iters(2000 + s) for s in range(samples)]
+    finally:
+        _PORT.set_summation(False)
+    band = np.array(band, dtype=np.float64)
     slack = max(1.0, np.ceil(ITER_TOL * band.max()))
     half = slack + 4.0 * band.std(ddof=1)
     assert abs(it_gpu - band.mean()) <= half, \
         f"gpu {it_gpu} iterations, reference {it_ref}, reference under sqrt(n)-ulp noise {sorted(band.astype(int))} (mean {band.mean():.1f} +- {half:.1f})"
+
+
+_PORT = po.Oracle("port")   # every resolve_iters callback in this file solves through the port (one shared library image)
 
 
 def iters_close(a, b):
