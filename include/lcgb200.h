@@ -121,6 +121,18 @@ long long lcgb200_csr_spmv_bytes(lcgb200_csr_t A);
 int lcgb200_csr_info(lcgb200_csr_t A, int* n_rows, int* n_cols, int* nnz, int* n_tiles, int* lanes_per_row);
 
 /* =====================================================================================================
+ * Data step in front of the path (what every reference GPU sample does before solving, sample8.cu:30-64,169-173)
+ * ===================================================================================================== */
+/* replaces cusparseXcoo2csr (sample8.cu:169, sample9.cu:146): ascending row indices of nnz entries -> row_ptr[n+1], on the device */
+int lcgb200_coo2csr(const int* rows_dev, int nnz, int n, int* row_ptr_dev, void* stream);
+/* reads data/case_*_A (data/README:1-10; readers sample8.cu:30-52, sample9.cu:30-52): N, nz, the COO triplets (split, row-sorted)
+ * and the right-hand side into malloc'ed HOST arrays (free with lcgb200_free_host); value_type LCGB200_REAL or LCGB200_COMPLEX */
+int lcgb200_read_case(const char* path_A, int value_type, int* n_out, int* nz_out, int** rows_out, int** cols_out, void** vals_out, void** rhs_out);
+void lcgb200_free_host(void* p);
+/* host COO triplets (row-sorted) -> operator handle; the COO -> CSR compression runs on the device */
+int lcgb200_csr_create_from_coo(lcgb200_csr_t* out, int n, int nnz, const int* rows, const int* cols, const void* vals, int value_type, unsigned flags);
+
+/* =====================================================================================================
  * Row-partitioned systems over several GPUs (new; the reference is single-device — SURVEY.md §8(e)).
  * One process per GPU.  Every rank creates its block with lcgb200_csr_create_rect (n_rows local rows; columns
  * index the extended vector [n_rows local entries | ghost entries grouped by owning peer]) and attaches the

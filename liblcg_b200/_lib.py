@@ -48,6 +48,10 @@ SYMBOLS = {
     "lcgb200_csr_spmv_dot": (_I, [_VP, _VP, _VP, _VP, _VP, _VP]),
     "lcgb200_csr_spmv_bytes": (_LL, [_VP]),
     "lcgb200_csr_info": (_I, [_VP] + [C.POINTER(_I)] * 5),
+    "lcgb200_coo2csr": (_I, [_VP, _I, _I, _VP, _VP]),
+    "lcgb200_read_case": (_I, [C.c_char_p, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP)]),
+    "lcgb200_free_host": (None, [_VP]),
+    "lcgb200_csr_create_from_coo": (_I, [C.POINTER(_VP), _I, _I, _VP, _VP, _VP, _I, C.c_uint]),
     "lcgb200_comm_unique_id": (_I, [_VP, _I]),
     "lcgb200_comm_create": (_I, [C.POINTER(_VP), _I, _I, _VP]),
     "lcgb200_comm_destroy": (_I, [_VP]),

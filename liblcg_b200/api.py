@@ -164,6 +164,45 @@ class CsrOperator:
             raise RuntimeError(f"spmv_dot failed ({rc}): {last_error()}")
 
 
+def read_case(path_a: str, complex_valued: bool = False):
+    """lcgb200_read_case: a reference fixture (data/case_*_A) -> dict(n, nnz, rows, cols, vals, b), COO triplets row-sorted."""
+    lib = _lib.load()
+    n, nz = C.c_int(), C.c_int()
+    rows, cols, vals, rhs = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+    rc = lib.lcgb200_read_case(path_a.encode(), COMPLEX if complex_valued else REAL, C.byref(n), C.byref(nz), C.byref(rows), C.byref(cols),
+                               C.byref(vals), C.byref(rhs))
+    if rc != 0:
+        raise RuntimeError(f"lcgb200_read_case failed ({rc}): {last_error()}")
+    vt = np.complex128 if complex_valued else np.float64
+    try:
+        out = dict(n=n.value, nnz=nz.value,
+                   rows=np.ctypeslib.as_array(C.cast(rows, C.POINTER(C.c_int)), shape=(max(nz.value, 1),))[:nz.value].copy(),
+                   cols=np.ctypeslib.as_array(C.cast(cols, C.POINTER(C.c_int)), shape=(max(nz.value, 1),))[:nz.value].copy(),
+                   vals=np.frombuffer(C.string_at(vals, nz.value * np.dtype(vt).itemsize), dtype=vt).copy(),
+                   b=np.frombuffer(C.string_at(rhs, n.value * np.dtype(vt).itemsize), dtype=vt).copy())
+    finally:
+        for p in (rows, cols, vals, rhs):
+            lib.lcgb200_free_host(p)
+    return out
+
+
+def operator_from_coo(n, rows, cols, vals, transpose=False, jacobi=False) -> "CsrOperator":
+    """lcgb200_csr_create_from_coo: row-sorted host COO triplets -> built-in operator (COO -> CSR compressed on the device)."""
+    lib = _lib.load()
+    rows = np.ascontiguousarray(rows, dtype=np.int32)
+    cols = np.ascontiguousarray(cols, dtype=np.int32)
+    cx = np.iscomplexobj(vals)
+    vals = np.ascontiguousarray(vals, dtype=np.complex128 if cx else np.float64)
+    h = C.c_void_p()
+    flags = (CSR_TRANSPOSE if transpose else 0) | (CSR_JACOBI if jacobi else 0)
+    rc = lib.lcgb200_csr_create_from_coo(C.byref(h), n, len(rows), rows.ctypes.data, cols.ctypes.data, vals.ctypes.data, COMPLEX if cx else REAL, flags)
+    if rc != 0:
+        raise RuntimeError(f"lcgb200_csr_create_from_coo failed ({rc}): {last_error()}")
+    op = CsrOperator.__new__(CsrOperator)
+    op.n, op.nnz, op.complex, op.n_cols, op.handle, op._keep = n, len(rows), bool(cx), n, h, None
+    return op
+
+
 @dataclass
 class Result:
     ret: int

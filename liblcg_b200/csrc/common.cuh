@@ -134,26 +134,42 @@ struct DevState {
 	CommDev* comm;            // multi == 2: NVLink peer-memory transport
 };
 
-// multi-GPU: hand the totals of a fused reduction to the cross-rank sum.  Called by the whole first warp of the last
-// block (grid_reduce).  multi == 1: leave them in st->red for ncclAllReduce; multi == 2: lane p pushes them into rank
-// p's window — all peers in parallel, one system-scope fence, one flag store each: a single NVLink round trip.
-__device__ __forceinline__ void publish_totals(DevState* st, const double* tot, int nred)
+// multi-GPU: the cross-rank sum of a fused reduction, called by the whole first warp of the last block (grid_reduce).
+//   multi == 1 (NCCL transport): leave the local totals in st->red for ncclAllReduce + k_finish; returns false.
+//   multi == 2 (NVLink peer memory): lane p pushes the local totals into rank p's window — all peers in parallel, one
+//     system-scope fence, one flag store each, i.e. a single NVLink round trip — then the same warp waits until every
+//     rank's totals have landed in MY window and sums them in rank order (bitwise identical on all ranks).  Returns true
+//     with tot[] = global totals in lane 0: the producing kernel's tail IS the allreduce, the caller runs the scalar
+//     epilogue right there and no separate launch exists.  A peer that never arrives ends the solve with an error.
+__device__ __forceinline__ bool reduce_across_ranks(DevState* st, double* tot, int nred)
 {
 	const int lane = threadIdx.x & 31;
-	if (st->multi == 2)
+	if (st->multi != 2)
 	{
-		CommDev* c = st->comm;
-		const unsigned long long seq = c->ar_seq + 1;
-		const int slot = (int)(seq % kArSlots);
-		if (lane < c->size)
-			for (int r = 0; r < nred; r++) c->win[lane]->ar_val[slot][c->rank][r] = tot[r];
-		__threadfence_system();
-		if (lane < c->size) st_relaxed_sys(&c->win[lane]->ar_flag[slot][c->rank], seq);
-		__syncwarp();
-		if (lane == 0) c->ar_seq = seq;
+		if (lane == 0) for (int r = 0; r < nred; r++) st->red[r] = tot[r];
+		return false;
 	}
-	else if (lane == 0)
-		for (int r = 0; r < nred; r++) st->red[r] = tot[r];
+	CommDev* c = st->comm;
+	const unsigned long long seq = c->ar_seq + 1;
+	const int slot = (int)(seq % kArSlots);
+	if (lane < c->size)
+		for (int r = 0; r < nred; r++) c->win[lane]->ar_val[slot][c->rank][r] = tot[r];
+	__threadfence_system();
+	if (lane < c->size) st_relaxed_sys(&c->win[lane]->ar_flag[slot][c->rank], seq);
+	CommWindow* w = c->win[c->rank];
+	bool ok = true;
+	if (lane < c->size) ok = spin_until(&w->ar_flag[slot][lane], seq);
+	ok = __all_sync(0xffffffffu, ok);
+	if (lane != 0) return false;
+	c->ar_seq = seq;
+	if (!ok) { st->ret = RC_UNKNOWN; st->done = 1; c->abort_flag = 1; return false; }
+	for (int r = 0; r < nred; r++)
+	{
+		double v = 0.0;
+		for (int src = 0; src < c->size; src++) v += *((volatile double*)&w->ar_val[slot][src][r]);
+		tot[r] = v;
+	}
+	return true;
 }
 
 __device__ __forceinline__ int st_done(const DevState* st) { return *((volatile const int*)&st->done); }
@@ -372,7 +388,7 @@ __global__ void __launch_bounds__(kThreads) k_vec(Op op_in, size_t n, DevState* 
 		double tot[Op::NRED > 0 ? Op::NRED : 1];
 		if (grid_reduce<(Op::NRED > 0 ? Op::NRED : 1)>(acc, partials, &st->ticket, tot))
 		{
-			if (st->multi) publish_totals(st, tot, Op::NRED);
+			if (st->multi) { if (reduce_across_ranks(st, tot, Op::NRED)) op.finish(st, tot); }
 			else if ((threadIdx.x & 31) == 0) op.finish(st, tot);
 		}
 	}
@@ -388,31 +404,6 @@ __global__ void k_finish(Op op_in, DevState* st)
 	op.begin(st);
 	double tot[kMaxRed];
 	for (int r = 0; r < kMaxRed; r++) tot[r] = st->red[r];
-	op.finish(st, tot);
-}
-
-// NVLink transport: wait until every rank's totals of the current reduction have landed in my window, sum them in
-// rank order (bitwise identical on all ranks) and run the scalar epilogue.  <<<1, 32>>>
-template <class Op>
-__global__ void k_finish_p2p(Op op_in, DevState* st, int nred)
-{
-	if (st_done(st)) return;
-	Op op = op_in;
-	if (!op.active(st)) return;
-	CommDev* c = st->comm;
-	const unsigned long long seq = c->ar_seq;     // set by the producing kernel, earlier in this stream
-	const int slot = (int)(seq % kArSlots);
-	CommWindow* w = c->win[c->rank];
-	bool ok = true;
-	if ((int)threadIdx.x < c->size) ok = spin_until(&w->ar_flag[slot][threadIdx.x], seq);
-	ok = __all_sync(0xffffffffu, ok);
-	if (threadIdx.x != 0) return;
-	if (!ok) { st->ret = RC_UNKNOWN; st->done = 1; c->abort_flag = 1; return; }
-	double tot[kMaxRed];
-	for (int r = 0; r < kMaxRed; r++) tot[r] = 0.0;
-	for (int src = 0; src < c->size; src++)
-		for (int r = 0; r < nred; r++) tot[r] += *((volatile double*)&w->ar_val[slot][src][r]);
-	op.begin(st);
 	op.finish(st, tot);
 }
 

@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(kSpmvThreads, TileCfg<T>::CTAS) k_spmv(CsrDev<
 		double tot[Epi::NRED > 0 ? Epi::NRED : 1];
 		if (grid_reduce<(Epi::NRED > 0 ? Epi::NRED : 1)>(acc, partials, &st->ticket, tot))
 		{
-			if (st->multi) publish_totals(st, tot, Epi::NRED);
+			if (st->multi) { if (reduce_across_ranks(st, tot, Epi::NRED)) epi.finish(st, tot); }
 			else if ((threadIdx.x & 31) == 0) epi.finish(st, tot);
 		}
 	}

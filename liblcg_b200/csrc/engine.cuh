@@ -134,12 +134,9 @@ public:
 
 	template <class Op> void finish_multi(const Op& op, int nred)
 	{
-		if (p2p()) k_finish_p2p<Op><<<1, 32, 0, stream>>>(op, d_st, nred);
-		else
-		{
-			comm->allreduce(reinterpret_cast<double*>(reinterpret_cast<char*>(d_st) + offsetof(DevState, red)), nred, stream);
-			k_finish<Op><<<1, 1, 0, stream>>>(op, d_st);
-		}
+		if (p2p()) return;   // NVLink transport: the producing kernel's last block already summed across the ranks and ran the epilogue
+		comm->allreduce(reinterpret_cast<double*>(reinterpret_cast<char*>(d_st) + offsetof(DevState, red)), nred, stream);
+		k_finish<Op><<<1, 1, 0, stream>>>(op, d_st);
 		launches++;
 	}
 

@@ -12,7 +12,7 @@
 #include <cstdlib>
 #include <vector>
 #include <cuda_runtime.h>
-#include "lcg_b200/lcg_cuda.h"
+#include "lcg_b200/solver_cuda.h"   // pulls in lcg_cuda.h, clcg_cuda.h, util.h
 
 struct Coo { int r, c; double v; };
 
@@ -58,6 +58,23 @@ static int user_progress(void* instance, const lcg_float*, const lcg_float, cons
 	s->calls_pf++; s->last_k = k;
 	return 0;
 }
+
+// the README-advertised way to use liblcg: derive from the class wrapper (solver_cuda.h:35-207)
+class UserSolver : public LCG_CUDA_Solver
+{
+public:
+	UserSystem* sys = nullptr;
+	int monitor_calls = 0;
+	void AxProduct(cublasHandle_t cub, cusparseHandle_t cus, cusparseDnVecDescr_t x, cusparseDnVecDescr_t Ax, const int n, const int nz) override
+	{
+		user_ax(sys, cub, cus, x, Ax, n, nz);
+	}
+	void MxProduct(cublasHandle_t cub, cusparseHandle_t cus, cusparseDnVecDescr_t x, cusparseDnVecDescr_t Mx, const int n, const int nz) override
+	{
+		user_mx(sys, cub, cus, x, Mx, n, nz);
+	}
+	int Progress(const lcg_float*, const lcg_float, const lcg_para*, const int, const int, const int) override { monitor_calls++; return 0; }
+};
 
 static double avg_error(const std::vector<double>& x, const std::vector<double>& ans)
 {	// the samples' metric: sqrt(sum |x - ans|^2) / N (sample8.cu:66-74)
@@ -128,6 +145,35 @@ int main(int argc, char** argv)
 			if (path == 1 && sys.calls_ax != 0) fails++;   // the sentinel must never be called
 		}
 		if (std::abs(iters[0] - iters[1]) > 1) fails++;
+	}
+	// class wrappers: virtual AxProduct/MxProduct (with the _MxProduct fix), then the same object on the built-in operator
+	{
+		UserSolver slv; slv.sys = &sys;
+		slv.set_lcg_parameter(para);
+		slv.set_report_interval(0);
+		for (int path = 0; path < 2; path++)
+		{
+			slv.use_builtin_operator(path == 1 ? builtin : nullptr);
+			std::vector<double> m((size_t)n, 0.0);
+			sys.calls_ax = sys.calls_mx = 0; slv.monitor_calls = 0;
+			slv.MinimizePreconditioned(cub, cus, m.data(), b.data(), n, nz, LCG_PCG, false, false);
+			const double err = avg_error(m, ans);
+			std::printf("class PCG %-26s Ax-callbacks %d Mx-callbacks %d monitor-calls %d avg-error %.3e\n",
+				path == 0 ? "virtual Ax/MxProduct" : "built-in fused operator", sys.calls_ax, sys.calls_mx, slv.monitor_calls, err);
+			if (!(err < 1e-4) || slv.monitor_calls < 50) fails++;
+			if (path == 0 && (sys.calls_ax == 0 || sys.calls_mx == 0)) fails++;   // MxProduct really is the preconditioner
+			if (path == 1 && (sys.calls_ax != 0 || sys.calls_mx != 0)) fails++;
+		}
+		lcgb200_csr_set_user(builtin, &sys);
+		slv.silent();
+		std::vector<double> m((size_t)n, 0.0);
+		slv.use_builtin_operator(nullptr);
+		slv.Minimize(cub, cus, m.data(), b.data(), n, nz, LCG_CGS);
+		if (!(avg_error(m, ans) < 1e-3)) fails++;
+		bool threw = false;
+		lcg_para bad = para; bad.epsilon = -1.0; slv.set_lcg_parameter(bad);
+		try { slv.Minimize(cub, cus, m.data(), b.data(), n, nz, LCG_CG); } catch (const std::runtime_error&) { threw = true; }   // silent_ => throws on error (solver_cuda.cu:73-78)
+		if (!threw) fails++;
 	}
 	// error behaviour mirrors the reference (lcg_cuda.cu:91-98)
 	{

@@ -142,3 +142,22 @@ int main() {
                             "-llcgb200", "-Xlinker", "-rpath=" + os.path.join(root, "liblcg_b200"), "-o", exe], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr[-3000:]
         assert subprocess.run([exe]).returncode == 0
+
+
+def test_read_case_matches_python_loader():
+    """lcgb200_read_case (host only) against liblcg_b200/io.py on the reference's fixtures (data/README:1-10)."""
+    import os
+    import numpy as np
+    from liblcg_b200 import api, io as lio
+    for name, cx in (("case_10K_A", False), ("case_10K_cA", True), ("case_1K_cA", True)):
+        path = os.path.join(lio.GOLDEN_DATA, name)
+        c = api.read_case(path, cx)
+        ref = lio.read_case(path, None, cx)
+        assert c["n"] == ref["n"] and c["nnz"] == ref["nnz"]
+        rp = np.zeros(c["n"] + 1, dtype=np.int64)
+        np.add.at(rp, c["rows"].astype(np.int64) + 1, 1)
+        assert np.array_equal(np.cumsum(rp), ref["row_ptr"]) and np.all(np.diff(c["rows"]) >= 0)
+        assert np.array_equal(c["cols"], ref["col"]) and np.array_equal(c["vals"], ref["val"]) and np.array_equal(c["b"], ref["b"])
+    import pytest
+    with pytest.raises(RuntimeError):
+        api.read_case(os.path.join(lio.GOLDEN_DATA, "does_not_exist"))

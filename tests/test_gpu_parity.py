@@ -524,3 +524,32 @@ def test_cxx_dropin_sample_runs(torch_cuda):
     data = os.path.join(root, "tests", "golden", "data")
     r = subprocess.run([exe, os.path.join(data, "case_10K_A"), os.path.join(data, "case_10K_B")], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "dropin_sample: ok" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_data_step_coo_to_csr_on_device(torch_cuda, port, fixtures):
+    """Front-of-path data step: lcgb200_read_case + device COO -> CSR (replaces cusparseXcoo2csr,
+    sample8.cu:169) + solve, against the Python loader and the CPU oracle; empty rows and an unsorted input are covered."""
+    import os
+    torch = torch_cuda
+    from liblcg_b200 import _lib
+    lib = _lib.load()
+    # row compression incl. empty leading / trailing / inner rows
+    rows = np.array([2, 2, 3, 7, 7, 7, 9], dtype=np.int32)
+    d_rows = to_dev(torch, rows)
+    d_rp = torch.empty(13, dtype=torch.int32, device="cuda")
+    assert lib.lcgb200_coo2csr(d_rows.data_ptr(), len(rows), 12, d_rp.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    expect = np.searchsorted(rows, np.arange(13), side="left")
+    assert np.array_equal(d_rp.cpu().numpy(), expect)
+    bad = to_dev(torch, np.array([3, 1, 2], dtype=np.int32))
+    assert lib.lcgb200_coo2csr(bad.data_ptr(), 3, 12, d_rp.data_ptr(), None) == api.LCG_SIZE_NOT_MATCH
+    # the reference's fixture end to end
+    A = fixtures["10K"]
+    c = api.read_case(os.path.join(lio.GOLDEN_DATA, "case_10K_A"))
+    op = api.operator_from_coo(c["n"], c["rows"], c["cols"], c["vals"], jacobi=True)
+    assert op.info()["nnz"] == A["nnz"] and np.allclose(op.diagonal(), A["diag"], rtol=0, atol=0)
+    m = np.zeros(c["n"])
+    r = api.solve(op, api.LCG_PCG, m, c["b"], param=api.lcg_default_parameters(epsilon=1e-10), jacobi=True)
+    cpu = port.solve(api.LCG_PCG, A, A["b"], para=po.default_para(epsilon=1e-10), diag=A["diag"])
+    assert r.ret == cpu.ret == 0 and r.iterations == cpu.iters and rel(m, cpu.x) <= X_TOL
+    op.close()
