@@ -48,6 +48,9 @@ WORKLOADS = {
     "cg7_128": ("7pt", 128, "CG"),
     "bicgstab7cd_512": ("7pt_cd", 512, "BICGSTAB"),
     "cgs7cd_512": ("7pt_cd", 512, "CGS"),
+    # the reference's own sample systems (configs[0], configs[1]): launch-latency-bound, it/s only
+    "case10k_cg": ("fixture:10K", 0, "CG"),
+    "case10k_pcg": ("fixture:10K", 0, "PCG"),
     # small variants for quick checks (not bench lines)
     "pcg27_64": ("27pt", 64, "PCG"),
     "bicgstab7cd_96": ("7pt_cd", 96, "BICGSTAB"),
@@ -124,16 +127,26 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------ CPU arms (reference)
+def host_system(kind, g):
+    """The workload's system on the host: a SURVEY 8(d) stencil or one of the reference's fixtures (tests/golden/data)."""
+    if kind.startswith("fixture:"):
+        from liblcg_b200 import io as lio
+        return lio.load_fixture(kind.split(":")[1])
+    from oracle import pyoracle as po
+    return po.gen_system(kind, g)
+
+
 def cpu_reference_run(kind, g, solver, iters, repeats=1, warmup=0):
     """Times the reference's own CPU/OpenMP solver (oracle/_ref) — or the C port when that library is absent — on
     the workload's system for `iters` iterations per solve.  Returns (it_per_s list, kind, cores)."""
     from oracle import pyoracle as po
     which = "reference" if po.have_reference() else "port"
     orc = po.Oracle(which)
-    S = po.gen_system(kind, g)
+    S = host_system(kind, g)
     diag = None
     if solver == "PCG":
-        diag = np.full(S["n"], 26.0 if kind == "27pt" else 6.0)
+        from liblcg_b200 import io as lio
+        diag = lio.csr_diagonal(S["row_ptr"], S["col"], S["val"]) if kind.startswith("fixture:") else np.full(S["n"], 26.0 if kind == "27pt" else 6.0)
     para = po.default_para(epsilon=1e-300, max_iterations=iters)
     rates = []
     for i in range(warmup + repeats):
@@ -149,7 +162,11 @@ def run_reference_arm(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n, nnz = g ** 3, stencil_nnz(kind, g)
+    if kind.startswith("fixture:"):
+        S0 = host_system(kind, g)
+        n, nnz = S0["n"], S0["nnz"]
+    else:
+        n, nnz = g ** 3, stencil_nnz(kind, g)
     # bounded sample: a few iterations of the same system per step, so K + W steps end within minutes
     it = args.ref_iters
     t0 = time.time()
@@ -193,7 +210,14 @@ def run_ours(args, wl):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
-    n, nnz = g ** 3, stencil_nnz(kind, g)
+    fixture = kind.startswith("fixture:")
+    if fixture:
+        if world > 1:
+            raise SystemExit("the reference's 10K sample systems are single-GPU workloads")
+        S0 = host_system(kind, g)
+        n, nnz = S0["n"], S0["nnz"]
+    else:
+        n, nnz = g ** 3, stencil_nnz(kind, g)
     transport = None
     iters = args.iters
     para = api.lcg_default_parameters(epsilon=1e-300, max_iterations=iters)
@@ -204,6 +228,10 @@ def run_ours(args, wl):
         part = ldist.build_stencil_partition(kind, g, rank, world, dev, jacobi=(solver == "PCG"))
         op, b_d, n_loc = part.op, part.b, part.n_local
         transport = "nvlink-p2p (halo + reduction totals pushed into peer memory from inside the kernels)" if part.p2p else "nccl (send/recv halo + allreduce)"
+    elif fixture:
+        op = api.CsrOperator(S0["row_ptr"], S0["col"], S0["val"], jacobi=(solver == "PCG"))
+        b_d = torch.from_numpy(S0["b"]).to(dev)
+        n_loc = n
     else:
         nz = C.c_longlong()
         assert lib.lcgb200_gen_stencil(KIND_ID[kind], g, 0, n, None, None, None, 0, C.byref(nz), None) == 0
@@ -380,7 +408,8 @@ def run_ours(args, wl):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "stencil": kind, "grid": g, "rows": n, "nnz": nnz, "solver": solver,
                    "iterations_per_step": iters, "parallelism": f"row-partition x{world}" if world > 1 else "single GPU", "transport": transport,
-                   "l2": f"inputs larger than L2: CSR {12 * nnz / world / 1e9:.2f} GB per GPU streamed every iteration (no flush needed)",
+                   "l2": (f"inputs larger than L2: CSR {12 * nnz / world / 1e9:.2f} GB per GPU streamed every iteration (no flush needed)" if 12 * nnz / world > 126e6
+                          else "cache-resident system: launch-latency-bound, it/s only (no roofline claim)"),
                    "lanes_per_row": info["lanes_per_row"], "tiles": info["n_tiles"]},
         "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         "hbm_gbs_per_iteration": bpi * value / 1e9 / world,
@@ -400,13 +429,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="pcg27_256", choices=sorted(WORKLOADS))
-    ap.add_argument("--iters", type=int, default=200, help="iterations per step (GPU arm)")
+    ap.add_argument("--iters", type=int, default=0, help="iterations per step (GPU arm); default 200 (60 for the 10K sample systems)")
     ap.add_argument("--cpu-iters", type=int, default=10, help="iterations of the cpu_baseline sample")
     ap.add_argument("--ref-iters", type=int, default=10, help="iterations per step of the --impl reference arm")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--poll", type=int, default=0, help="iterations enqueued per host poll of the convergence flag (0 = library default)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
+    if args.iters <= 0:
+        args.iters = 60 if wl[0].startswith("fixture:") else 200
+    if wl[0].startswith("fixture:"):
+        args.cpu_iters = args.ref_iters = args.iters
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "ours" and args.gpus > 1 and world == 1:
         # convenience: relaunch under torchrun, one rank per GPU

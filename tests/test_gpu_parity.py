@@ -553,3 +553,67 @@ def test_data_step_coo_to_csr_on_device(torch_cuda, port, fixtures):
     cpu = port.solve(api.LCG_PCG, A, A["b"], para=po.default_para(epsilon=1e-10), diag=A["diag"])
     assert r.ret == cpu.ret == 0 and r.iterations == cpu.iters and rel(m, cpu.x) <= X_TOL
     op.close()
+
+
+# ------------------------------------------------------------------------------------------------ full sizes
+def _device_system(torch, kind_id, g, jacobi):
+    from liblcg_b200 import _lib
+    lib = _lib.load()
+    n = g ** 3
+    nz = C.c_longlong()
+    assert lib.lcgb200_gen_stencil(kind_id, g, 0, n, None, None, None, 0, C.byref(nz), None) == 0
+    rp = torch.empty(n + 1, dtype=torch.int32, device="cuda")
+    ci = torch.empty(nz.value, dtype=torch.int32, device="cuda")
+    va = torch.empty(nz.value, dtype=torch.float64, device="cuda")
+    assert lib.lcgb200_gen_stencil(kind_id, g, 0, n, rp.data_ptr(), ci.data_ptr(), va.data_ptr(), 0, None, None) == 0
+    b = torch.empty(n, dtype=torch.float64, device="cuda")
+    assert lib.lcgb200_gen_rhs(kind_id, g, 0, n, b.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    op = api.CsrOperator(rp, ci, va, jacobi=jacobi)
+    del rp, ci, va
+    torch.cuda.empty_cache()
+    return op, b, n
+
+
+@pytest.mark.parametrize("kind_id,g,sid,symmetric", [(0, 128, api.LCG_CG, True), (1, 256, api.LCG_PCG, True), (2, 320, api.LCG_BICGSTAB, False)])
+def test_full_size_properties(torch_cuda, kind_id, g, sid, symmetric):
+    """BASELINE configs[2..4] at (or near) full size, where the CPU oracle is too slow: size-independent properties.
+    (a) the fused dots of the SpMV kernel equal torch's on its own output; (b) linearity A(ax+by) = aAx + bAy;
+    (c) symmetry x.Ay = y.Ax for the Poisson stencils, and its failure for convection-diffusion; (d) after a solve, the
+    TRUE residual |b - A x|^2 / max(|x|^2, 1), recomputed from scratch, equals the residual the solver reported, and the
+    error against the known x* has dropped accordingly; (e) a second solve from the same start reproduces the first bit for bit."""
+    torch = torch_cuda
+    op, b, n = _device_system(torch, kind_id, g, jacobi=(sid == api.LCG_PCG))
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.rand(n, dtype=torch.float64, device="cuda", generator=gen) - 0.5
+    y = torch.rand(n, dtype=torch.float64, device="cuda", generator=gen) - 0.5
+    Ax, Ay, Az = (torch.empty(n, dtype=torch.float64, device="cuda") for _ in range(3))
+    dots = torch.zeros(3, dtype=torch.float64, device="cuda")
+    op.spmv_dot(x, Ax, y, dots)                       # dots = [y.Ax, Ax.Ax, x.Ax]
+    op.spmv(y, Ay)
+    torch.cuda.synchronize()
+    ref = torch.stack([torch.dot(y, Ax), torch.dot(Ax, Ax), torch.dot(x, Ax)])
+    assert torch.allclose(dots, ref, rtol=1e-12, atol=0)
+    z = 0.75 * x - 1.25 * y
+    op.spmv(z, Az)
+    torch.cuda.synchronize()
+    lin = (Az - (0.75 * Ax - 1.25 * Ay)).norm() / Az.norm()
+    assert lin.item() < 1e-14
+    sym = abs((torch.dot(x, Ay) - torch.dot(y, Ax)).item()) / abs(torch.dot(x, Ay).item())
+    assert (sym < 1e-11) if symmetric else (sym > 1e-6)
+    # (d) solve and recompute the residual from scratch
+    xs = torch.from_numpy(stencil.x_star(0, n)).cuda()
+    para = api.lcg_default_parameters(epsilon=1e-12, max_iterations=4000)
+    m = torch.zeros(n, dtype=torch.float64, device="cuda")
+    r = api.solve(op, sid, m, b, param=para, device=True, jacobi=(sid == api.LCG_PCG))
+    assert r.ret == api.LCG_CONVERGENCE, (r.ret, r.iterations, api.last_error())
+    op.spmv(m, Ax)
+    torch.cuda.synchronize()
+    true_res = ((b - Ax).square().sum() / max(m.square().sum().item(), 1.0)).item()
+    assert true_res <= 1.5e-12 and true_res == pytest.approx(r.residual, rel=2e-2)      # recurrence vs true residual drift
+    assert ((m - xs).norm() / xs.norm()).item() < (1e-5 if symmetric else 1e-4)
+    # (e) run-to-run determinism (fixed-order grid reduction)
+    m2 = torch.zeros(n, dtype=torch.float64, device="cuda")
+    r2 = api.solve(op, sid, m2, b, param=para, device=True, jacobi=(sid == api.LCG_PCG))
+    assert r2.iterations == r.iterations and torch.equal(m, m2)
+    op.close()
