@@ -241,6 +241,9 @@ void lcgb200_set_shadow_seed(long seed);
 void lcgb200_set_complex_residual_mode(int mode);
 /* iterations enqueued between two host polls of the device convergence flag when no progress callback is set */
 void lcgb200_set_poll_interval(int iterations);
+/* 1 (default): systems small enough to stay cache-resident (<= 65536 rows, <= 2M non-zeros; CG, Jacobi-PCG and the complex
+ * BICG_SYM / Jacobi-PCG) run several whole iterations per cooperative launch; 0: always the streaming kernels */
+void lcgb200_set_fused_small(int on);
 /* 1: bracket every kernel launch of a solve with CUDA events (per-kernel durations in lcgb200_info); costs a
  * little throughput, so bench.py uses it only for its roofline pass */
 void lcgb200_set_profile(int on);

@@ -74,6 +74,7 @@ SYMBOLS = {
     "lcgb200_set_complex_residual_mode": (None, [_I]),
     "lcgb200_set_poll_interval": (None, [_I]),
     "lcgb200_set_profile": (None, [_I]),
+    "lcgb200_set_fused_small": (None, [_I]),
     "lcgb200_last_error": (C.c_char_p, []),
     "lcgb200_version": (_I, []),
     "lcgb200_gen_stencil": (_I, [_I, _I, _LL, _LL, _VP, _VP, _VP, _LL, C.POINTER(_LL), _VP]),

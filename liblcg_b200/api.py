@@ -82,6 +82,10 @@ def set_poll_interval(n: int) -> None:
     _lib.load().lcgb200_set_poll_interval(n)
 
 
+def set_fused_small(on: bool) -> None:
+    _lib.load().lcgb200_set_fused_small(1 if on else 0)
+
+
 def set_profile(on: bool) -> None:
     _lib.load().lcgb200_set_profile(1 if on else 0)
 

@@ -386,6 +386,7 @@ void lcgb200_set_shadow_seed(long seed) { settings().shadow_seed = seed; }
 void lcgb200_set_complex_residual_mode(int mode) { settings().cres_mode = mode ? 1 : 0; }
 void lcgb200_set_poll_interval(int it) { settings().poll = it > 0 ? it : 1; }
 void lcgb200_set_profile(int on) { settings().profile = on ? 1 : 0; }
+void lcgb200_set_fused_small(int on) { settings().fused_small = on ? 1 : 0; }
 
 // sentinels: recognised by address, never executed on the fused path
 void lcgb200_csr_ax(void*, lcgb200_cublas_t, lcgb200_cusparse_t, lcgb200_dnvec_t, lcgb200_dnvec_t, const int, const int) {}

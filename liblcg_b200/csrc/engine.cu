@@ -64,6 +64,16 @@ Engine::Engine(cudaStream_t s, CsrHandle* h) : stream(s), cache(h)
 	}
 }
 
+int coop_grid_limit(const void* kernel, int block)
+{
+	int dev = 0, sms = 148, per_sm = 1;
+	cudaGetDevice(&dev);
+	if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+	if (per_sm > 2) per_sm = 2;   // grid barriers get slower with more blocks; two per SM are plenty for an L2-resident system
+	return sms * per_sm;
+}
+
 cudaEvent_t Engine::prof_begin(int cls)
 {
 	if (timed_used == timed.size())
@@ -187,21 +197,23 @@ bool Engine::sync_point()
 	return sync_always();
 }
 
-int Engine::run(const std::function<bool()>& iterate)
+int Engine::run(const std::function<bool()>& iterate, const std::function<void(int)>& batch)
 {
 	if (pf)
 	{	// one host round trip per loop head, exactly like the reference
 		while (true)
 		{
 			if (sync_always()) break;
-			if (iterate()) break;
+			if (batch) batch(1);
+			else if (iterate()) break;
 		}
 		LCG_CUDA_CHECK(cudaStreamSynchronize(stream));
 		return final_ret;
 	}
 	// No callback: enqueue `poll` iterations per batch, read the state back asynchronously, and look at the
 	// PREVIOUS batch's flag while the current one runs.  Kernels launched after `done` return immediately.
-	const int poll = settings().poll > 0 ? settings().poll : 1;
+	// fused launches cost ~one launch per batch: poll less often (an iteration of a cache-resident system takes microseconds)
+	const int poll = (settings().poll > 0 ? settings().poll : 1) * (batch ? 8 : 1);
 	DevState* slot[2] = {h_st, h_st2};
 	bool pending[2] = {false, false};
 	int b = 0;
@@ -213,7 +225,8 @@ int Engine::run(const std::function<bool()>& iterate)
 	while (true)
 	{
 		bool ended = false;
-		for (int i = 0; i < poll && !ended; i++) ended = iterate();
+		if (batch) batch(poll);
+		else for (int i = 0; i < poll && !ended; i++) ended = iterate();
 		if (ended) break;   // a host-driven step (SPG) saw the end itself
 		LCG_CUDA_CHECK(cudaMemcpyAsync(slot[b], d_st, sizeof(DevState), cudaMemcpyDeviceToHost, stream));
 		LCG_CUDA_CHECK(cudaEventRecord(ev[b], stream));

@@ -8,6 +8,7 @@
 #include <chrono>
 #include "common.cuh"
 #include "csr.cuh"
+#include "fused_small.cuh"
 
 namespace lcgb200 {
 
@@ -76,6 +77,7 @@ struct Settings {
 	long shadow_seed = 0;
 	int cres_mode = 0;
 	int poll = 4;
+	int fused_small = 1;           // cache-resident systems: several whole iterations per cooperative launch (fused_small.cuh)
 	int profile = 0;               // 1: bracket every kernel launch with CUDA events (bench roofline pass)
 };
 Settings& settings();
@@ -164,6 +166,20 @@ public:
 
 	size_t n_local = 0;
 
+	// cache-resident single-GPU systems on the built-in operator take the fused cooperative kernel (not while profiling:
+	// the per-kernel attribution of bench.py's roofline pass needs the separate launches)
+	template <class T> bool small_system(const Operator<T>& A) const
+	{
+		return A.h && !multi() && !profiling && settings().fused_small && A.h->n_rows <= kSmallRows && A.h->nnz <= kSmallNnz;
+	}
+	// `iters` iterations of SpMV(x -> y, epi); op1; op2 in one launch
+	template <class T, class Epi, class Op1, class Op2>
+	void fused3(const Operator<T>& A, T* x, T* y, const Epi& epi, const Op1& op1, const Op2& op2, size_t n, int iters)
+	{
+		LCG_CUDA_CHECK((launch_fused3<T, Epi, Op1, Op2>(A.h->template view<T>(), x, y, epi, op1, op2, n, d_st, d_partials, iters, stream)));
+		launches++; spmv_launches += iters;
+	}
+
 	// Pfp mode: read the state, deliver a new loop head to the callback.  Returns true when the solve is over
 	// (final_ret set).  Without a callback this is a no-op returning false (the device flags do the work).
 	bool sync_point();
@@ -171,7 +187,8 @@ public:
 	bool sync_always();
 
 	// Host loop.  `iterate` enqueues one iteration and returns true if a sync point inside it ended the solve.
-	int run(const std::function<bool()>& iterate);
+	// `batch`, when given, enqueues k iterations in one go (fused cooperative kernel) and replaces `iterate`.
+	int run(const std::function<bool()>& iterate, const std::function<void(int)>& batch = nullptr);
 };
 
 }  // namespace lcgb200

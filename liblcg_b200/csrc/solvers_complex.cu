@@ -225,6 +225,11 @@ static int run_csym(Engine& E, const Operator<Z>& A, Z* m, const Z* B, size_t n,
 		A.precond(r, z, 0);
 		E.vec(OpCsInitZ{{}, r, z, d}, n);
 	}
+	std::function<void(int)> batch;
+	if (E.small_system(A) && mode == 0)
+		batch = [&](int k) { E.fused3(A, d, Ax, EpiDotuAlpha{}, OpCsUpdate<0>{{}, m, d, r, Ax, nullptr, z, zc()}, OpCsDir{{}, r, d, zc()}, n, k); };
+	if (E.small_system(A) && mode == 1)
+		batch = [&](int k) { E.fused3(A, d, Ax, EpiDotuAlpha{}, OpCsUpdate<1>{{}, m, d, r, Ax, A.diag, z, zc()}, OpCsDir{{}, z, d, zc()}, n, k); };
 	return E.run([&]() {
 		E.spmv(A, d, Ax, EpiDotuAlpha{});
 		if (mode == 0) E.vec(OpCsUpdate<0>{{}, m, d, r, Ax, nullptr, z, zc()}, n);
@@ -237,7 +242,7 @@ static int run_csym(Engine& E, const Operator<Z>& A, Z* m, const Z* B, size_t n,
 		}
 		E.vec(OpCsDir{{}, mode == 0 ? r : z, d, zc()}, n);
 		return false;
-	});
+	}, batch);
 }
 
 // ======================================================================================== shadow residual

@@ -111,12 +111,14 @@ static int run_cg(Engine& E, const Operator<double>& A, double* m, const double*
 	double* g = E.alloc<double>(next); double* d = E.alloc<double>(next); double* Ad = E.alloc<double>(next);
 	E.spmv(A, m, Ad, EpiNone<double>{});
 	E.vec(OpCgInit{{}, m, Ad, B, g, d}, n);
+	std::function<void(int)> batch;
+	if (E.small_system(A)) batch = [&](int k) { E.fused3(A, d, Ad, EpiDotAlpha{nullptr}, OpCgUpdate{{}, m, d, g, Ad, 0.0}, OpCgDir{{}, d, g, 0.0}, n, k); };
 	return E.run([&]() {
 		E.spmv(A, d, Ad, EpiDotAlpha{nullptr});
 		E.vec(OpCgUpdate{{}, m, d, g, Ad, 0.0}, n);
 		E.vec(OpCgDir{{}, d, g, 0.0}, n);
 		return false;
-	});
+	}, batch);
 }
 
 // ======================================================================================== PCG (lcg.cpp:293-434)
@@ -241,6 +243,9 @@ static int run_pcg(Engine& E, const Operator<double>& A, double* m, const double
 		A.precond(r, z, 0);
 		E.vec(OpPcgInitZ{{}, z, r, d}, n);
 	}
+	std::function<void(int)> batch;
+	if (jac && E.small_system(A))
+		batch = [&](int k) { E.fused3(A, d, Ad, EpiDotAlpha{nullptr}, OpPcgUpdate<true>{{}, m, d, r, Ad, A.diag, z, 0.0}, OpPcgDir{{}, d, z, 0.0}, n, k); };
 	return E.run([&]() {
 		E.spmv(A, d, Ad, EpiDotAlpha{nullptr});
 		if (jac) E.vec(OpPcgUpdate<true>{{}, m, d, r, Ad, A.diag, z, 0.0}, n);
@@ -252,7 +257,7 @@ static int run_pcg(Engine& E, const Operator<double>& A, double* m, const double
 		}
 		E.vec(OpPcgDir{{}, d, z, 0.0}, n);
 		return false;
-	});
+	}, batch);
 }
 
 // ======================================================================================== CGS (lcg.cpp:437-612)
