@@ -172,12 +172,21 @@ public:
 	{
 		return A.h && !multi() && !profiling && settings().fused_small && A.h->n_rows <= kSmallRows && A.h->nnz <= kSmallNnz;
 	}
-	// `iters` iterations of SpMV(x -> y, epi); op1; op2 in one launch
-	template <class T, class Epi, class Op1, class Op2>
-	void fused3(const Operator<T>& A, T* x, T* y, const Epi& epi, const Op1& op1, const Op2& op2, size_t n, int iters)
+	// phase builders for the fused kernel (what E.spmv / E.vec would have launched)
+	template <class T, class Epi> SpmvPhase<T, false, Epi> ph_spmv(const Operator<T>& A, const T* x, T* y, const Epi& epi) const
 	{
-		LCG_CUDA_CHECK((launch_fused3<T, Epi, Op1, Op2>(A.h->template view<T>(), x, y, epi, op1, op2, n, d_st, d_partials, iters, stream)));
-		launches++; spmv_launches += iters;
+		return SpmvPhase<T, false, Epi>{A.h->template view<T>(), x, y, epi};
+	}
+	template <class T, class Epi> SpmvPhase<T, true, Epi> ph_spmv_h(const Operator<T>& A, const T* x, T* y, const Epi& epi) const   // A^H x
+	{
+		return SpmvPhase<T, true, Epi>{A.h->template tview<T>(), x, y, epi};
+	}
+	template <class Op> VecPhase<Op> ph_vec(const Op& op, size_t n) const { return VecPhase<Op>{op, n}; }
+	// `iters` iterations of the phase list in one cooperative launch; n_spmv = SpMV phases per iteration
+	template <class... Ph> void fused(int iters, int n_spmv, Ph... ph)
+	{
+		LCG_CUDA_CHECK((launch_fused<Ph...>(d_st, d_partials, iters, stream, ph...)));
+		launches++; spmv_launches += iters * n_spmv;
 	}
 
 	// Pfp mode: read the state, deliver a new loop head to the callback.  Returns true when the solve is over

@@ -121,6 +121,10 @@ static int run_cbicg(Engine& E, const Operator<Z>& A, Z* m, const Z* B, size_t n
 	Z* r1 = E.alloc<Z>(next); Z* r2 = E.alloc<Z>(next); Z* d1 = E.alloc<Z>(next); Z* d2 = E.alloc<Z>(next); Z* Ax = E.alloc<Z>(next);
 	E.spmv(A, m, Ax, EpiNone<Z>{});
 	E.vec(OpCbInit{{}, m, Ax, B, r1, r2, d1, d2}, n);
+	std::function<void(int)> batch;
+	if (E.small_system(A) && A.h->lpr == A.h->t_lpr)
+		batch = [&](int k) { E.fused(k, 2, E.ph_spmv(A, d1, Ax, EpiInnerAlpha{d2}), E.ph_vec(OpCbUpdate1{{}, m, d1, r1, Ax, zc()}, n), E.ph_spmv_h(A, d2, Ax, EpiNone<Z>{}),
+			E.ph_vec(OpCbUpdate2{{}, r2, Ax, r1, zc()}, n), E.ph_vec(OpCbDir{{}, r1, r2, d1, d2, zc()}, n)); };
 	return E.run([&]() {
 		E.spmv(A, d1, Ax, EpiInnerAlpha{d2});
 		E.vec(OpCbUpdate1{{}, m, d1, r1, Ax, zc()}, n);
@@ -128,7 +132,7 @@ static int run_cbicg(Engine& E, const Operator<Z>& A, Z* m, const Z* B, size_t n
 		E.vec(OpCbUpdate2{{}, r2, Ax, r1, zc()}, n);
 		E.vec(OpCbDir{{}, r1, r2, d1, d2, zc()}, n);
 		return false;
-	});
+	}, batch);
 }
 
 // ====================================================== BICG_SYM (clcg.cpp:228-364) and PCG (clcg_cuda.cu:403-559)
@@ -227,9 +231,9 @@ static int run_csym(Engine& E, const Operator<Z>& A, Z* m, const Z* B, size_t n,
 	}
 	std::function<void(int)> batch;
 	if (E.small_system(A) && mode == 0)
-		batch = [&](int k) { E.fused3(A, d, Ax, EpiDotuAlpha{}, OpCsUpdate<0>{{}, m, d, r, Ax, nullptr, z, zc()}, OpCsDir{{}, r, d, zc()}, n, k); };
+		batch = [&](int k) { E.fused(k, 1, E.ph_spmv(A, d, Ax, EpiDotuAlpha{}), E.ph_vec(OpCsUpdate<0>{{}, m, d, r, Ax, nullptr, z, zc()}, n), E.ph_vec(OpCsDir{{}, r, d, zc()}, n)); };
 	if (E.small_system(A) && mode == 1)
-		batch = [&](int k) { E.fused3(A, d, Ax, EpiDotuAlpha{}, OpCsUpdate<1>{{}, m, d, r, Ax, A.diag, z, zc()}, OpCsDir{{}, z, d, zc()}, n, k); };
+		batch = [&](int k) { E.fused(k, 1, E.ph_spmv(A, d, Ax, EpiDotuAlpha{}), E.ph_vec(OpCsUpdate<1>{{}, m, d, r, Ax, A.diag, z, zc()}, n), E.ph_vec(OpCsDir{{}, z, d, zc()}, n)); };
 	return E.run([&]() {
 		E.spmv(A, d, Ax, EpiDotuAlpha{});
 		if (mode == 0) E.vec(OpCsUpdate<0>{{}, m, d, r, Ax, nullptr, z, zc()}, n);
@@ -371,6 +375,10 @@ static int run_ccgs(Engine& E, const Operator<Z>& A, Z* m, const Z* B, size_t n,
 	E.spmv(A, m, Ax, EpiNone<Z>{});
 	E.vec(OpCResInit{{}, m, Ax, B, r, p, u, nullptr}, n);
 	if (!init_shadow<true>(E, rb, r, n, skip)) return RC_UNKNOWN;
+	std::function<void(int)> batch;
+	if (E.small_system(A))
+		batch = [&](int k) { E.fused(k, 2, E.ph_spmv(A, p, Ax, EpiInnerAlpha{rb}), E.ph_vec(OpCQW{{}, u, Ax, q, w, zc()}, n), E.ph_spmv(A, w, Ax, EpiNone<Z>{}),
+			E.ph_vec(OpCCgsUpdate{{}, m, w, r, Ax, rb, zc()}, n), E.ph_vec(OpCCgsDir{{}, r, q, u, p, zc()}, n)); };
 	return E.run([&]() {
 		E.spmv(A, p, Ax, EpiInnerAlpha{rb});
 		E.vec(OpCQW{{}, u, Ax, q, w, zc()}, n);
@@ -378,7 +386,7 @@ static int run_ccgs(Engine& E, const Operator<Z>& A, Z* m, const Z* B, size_t n,
 		E.vec(OpCCgsUpdate{{}, m, w, r, Ax, rb, zc()}, n);
 		E.vec(OpCCgsDir{{}, r, q, u, p, zc()}, n);
 		return false;
-	});
+	}, batch);
 }
 
 // ======================================================================================== BICGSTAB (clcg.cpp:524-679)
@@ -428,6 +436,10 @@ static int run_cbicgstab(Engine& E, const Operator<Z>& A, Z* m, const Z* B, size
 	E.spmv(A, m, Ap, EpiNone<Z>{});
 	E.vec(OpCResInit{{}, m, Ap, B, r, p, nullptr, nullptr}, n);
 	if (!init_shadow<true>(E, rb, r, n, skip)) return RC_UNKNOWN;
+	std::function<void(int)> batch;
+	if (E.small_system(A))
+		batch = [&](int k) { E.fused(k, 2, E.ph_spmv(A, p, Ap, EpiInnerAlpha{rb}), E.ph_vec(OpCBsS{{}, r, Ap, s, zc()}, n), E.ph_spmv(A, s, As, EpiCOmega{}),
+			E.ph_vec(OpCBsUpdate{{}, m, p, s, As, r, rb, zc(), zc()}, n), E.ph_vec(OpCBsDir{{}, r, p, Ap, zc(), zc()}, n)); };
 	return E.run([&]() {
 		E.spmv(A, p, Ap, EpiInnerAlpha{rb});
 		E.vec(OpCBsS{{}, r, Ap, s, zc()}, n);
@@ -435,7 +447,7 @@ static int run_cbicgstab(Engine& E, const Operator<Z>& A, Z* m, const Z* B, size
 		E.vec(OpCBsUpdate{{}, m, p, s, As, r, rb, zc(), zc()}, n);
 		E.vec(OpCBsDir{{}, r, p, Ap, zc(), zc()}, n);
 		return false;
-	});
+	}, batch);
 }
 
 // ======================================================================================== TFQMR (clcg.cpp:681-882)

@@ -112,7 +112,7 @@ static int run_cg(Engine& E, const Operator<double>& A, double* m, const double*
 	E.spmv(A, m, Ad, EpiNone<double>{});
 	E.vec(OpCgInit{{}, m, Ad, B, g, d}, n);
 	std::function<void(int)> batch;
-	if (E.small_system(A)) batch = [&](int k) { E.fused3(A, d, Ad, EpiDotAlpha{nullptr}, OpCgUpdate{{}, m, d, g, Ad, 0.0}, OpCgDir{{}, d, g, 0.0}, n, k); };
+	if (E.small_system(A)) batch = [&](int k) { E.fused(k, 1, E.ph_spmv(A, d, Ad, EpiDotAlpha{nullptr}), E.ph_vec(OpCgUpdate{{}, m, d, g, Ad, 0.0}, n), E.ph_vec(OpCgDir{{}, d, g, 0.0}, n)); };
 	return E.run([&]() {
 		E.spmv(A, d, Ad, EpiDotAlpha{nullptr});
 		E.vec(OpCgUpdate{{}, m, d, g, Ad, 0.0}, n);
@@ -245,7 +245,7 @@ static int run_pcg(Engine& E, const Operator<double>& A, double* m, const double
 	}
 	std::function<void(int)> batch;
 	if (jac && E.small_system(A))
-		batch = [&](int k) { E.fused3(A, d, Ad, EpiDotAlpha{nullptr}, OpPcgUpdate<true>{{}, m, d, r, Ad, A.diag, z, 0.0}, OpPcgDir{{}, d, z, 0.0}, n, k); };
+		batch = [&](int k) { E.fused(k, 1, E.ph_spmv(A, d, Ad, EpiDotAlpha{nullptr}), E.ph_vec(OpPcgUpdate<true>{{}, m, d, r, Ad, A.diag, z, 0.0}, n), E.ph_vec(OpPcgDir{{}, d, z, 0.0}, n)); };
 	return E.run([&]() {
 		E.spmv(A, d, Ad, EpiDotAlpha{nullptr});
 		if (jac) E.vec(OpPcgUpdate<true>{{}, m, d, r, Ad, A.diag, z, 0.0}, n);
@@ -347,6 +347,10 @@ static int run_cgs(Engine& E, const Operator<double>& A, double* m, const double
 	double* w = E.alloc<double>(next);
 	E.spmv(A, m, Ax, EpiNone<double>{});
 	E.vec(OpResInit{{}, m, Ax, B, r, r0, p, u}, n);
+	std::function<void(int)> batch;
+	if (E.small_system(A))
+		batch = [&](int k) { E.fused(k, 2, E.ph_spmv(A, p, Ax, EpiDotAlpha{r0}), E.ph_vec(OpCgsQW{{}, u, Ax, q, w, 0.0}, n), E.ph_spmv(A, w, Ax, EpiNone<double>{}),
+			E.ph_vec(OpCgsUpdate{{}, m, w, r, Ax, r0, 0.0}, n), E.ph_vec(OpCgsDir{{}, r, q, u, p, 0.0}, n)); };
 	return E.run([&]() {
 		E.spmv(A, p, Ax, EpiDotAlpha{r0});
 		E.vec(OpCgsQW{{}, u, Ax, q, w, 0.0}, n);
@@ -354,7 +358,7 @@ static int run_cgs(Engine& E, const Operator<double>& A, double* m, const double
 		E.vec(OpCgsUpdate{{}, m, w, r, Ax, r0, 0.0}, n);
 		E.vec(OpCgsDir{{}, r, q, u, p, 0.0}, n);
 		return false;
-	});
+	}, batch);
 }
 
 // ================================================================ BICGSTAB (lcg.cpp:629-794) / BICGSTAB2 (:812-1034)
@@ -459,6 +463,10 @@ static int run_bicgstab(Engine& E, const Operator<double>& A, double* m, const d
 	const bool half = RESTART && abs_diff;
 	E.spmv(A, m, Ax, EpiNone<double>{});
 	E.vec(OpResInit{{}, m, Ax, B, r, r0, p, nullptr}, n);
+	std::function<void(int)> batch;
+	if (!half && E.small_system(A))
+		batch = [&](int k) { E.fused(k, 2, E.ph_spmv(A, p, Ap, EpiDotAlpha{r0}), E.ph_vec(OpBicgS<false>{{}, r, Ap, s, 0.0}, n), E.ph_spmv(A, s, Ax, EpiOmega{}),
+			E.ph_vec(OpBicgUpdate<RESTART>{{}, m, p, s, Ax, r, r0, 0.0, 0.0}, n), E.ph_vec(OpBicgDir<RESTART>{{}, r, p, Ap, r0, 0.0, 0.0, 0}, n)); };
 	return E.run([&]() {
 		E.spmv(A, p, Ap, EpiDotAlpha{r0});
 		if (half)
@@ -472,7 +480,7 @@ static int run_bicgstab(Engine& E, const Operator<double>& A, double* m, const d
 		E.vec(OpBicgUpdate<RESTART>{{}, m, p, s, Ax, r, r0, 0.0, 0.0}, n);
 		E.vec(OpBicgDir<RESTART>{{}, r, p, Ap, r0, 0.0, 0.0, 0}, n);
 		return false;
-	});
+	}, batch);
 }
 
 // ======================================================================================== PG (lcg.cpp:1054-1204)
@@ -557,12 +565,15 @@ static int run_pg(Engine& E, const Operator<double>& A, double* m, const double*
 	E.vec(OpBox{{}, m, lo, hi}, n);
 	E.spmv(A, m, Ad, EpiNone<double>{});
 	E.vec(OpPgInit<false>{{}, m, Ad, B, g}, n);
+	std::function<void(int)> batch;
+	if (E.small_system(A))
+		batch = [&](int k) { E.fused(k, 1, E.ph_vec(OpPgStep{{}, m, g, lo, hi, mn, 0.0}, n), E.ph_spmv(A, mn, Ad, EpiNone<double>{}), E.ph_vec(OpPgUpdate{{}, m, g, mn, Ad, B}, n)); };
 	return E.run([&]() {
 		E.vec(OpPgStep{{}, m, g, lo, hi, mn, 0.0}, n);
 		E.spmv(A, mn, Ad, EpiNone<double>{});
 		E.vec(OpPgUpdate{{}, m, g, mn, Ad, B}, n);
 		return false;
-	});
+	}, batch);
 }
 
 // ======================================================================================== SPG (lcg.cpp:1224-1447)
