@@ -66,6 +66,41 @@ def main():
                       f"rel {rel:.2e} launches {r.info.kernel_launches} transport {'nvlink-p2p' if part.p2p else 'nccl'} comm {part.comm.stats()}", flush=True)
                 failures += 0 if ok else 1
         part.close()
+    # a general (non-stencil) SPD system: random long-range couplings -> scattered ghost columns, i.e. the PACKED
+    # (non-contiguous) send lists of the halo plan, and ranks that talk to every other rank
+    rng = np.random.default_rng(5)
+    n = 6000
+    import scipy.sparse as sp
+    S = sp.random(n, n, density=4.0 / n, random_state=rng, data_rvs=lambda k: -rng.random(k)).tocsr()
+    S = S + S.T
+    S.setdiag(0); S.eliminate_zeros()
+    Afull = (S + sp.diags(np.asarray(-S.sum(axis=1)).ravel() + 1.0)).tocsr()
+    Afull.sort_indices()
+    G = dict(n=n, nnz=Afull.nnz, row_ptr=Afull.indptr.astype(np.int32), col=Afull.indices.astype(np.int32), val=Afull.data.astype(np.float64))
+    xs = rng.standard_normal(n)
+    bfull = Afull @ xs
+    bounds = ldist.row_bounds(n, world)
+    r0, r1 = bounds[rank], bounds[rank + 1]
+    k0, k1 = G["row_ptr"][r0], G["row_ptr"][r1]
+    part = ldist.partition_csr(torch.from_numpy((G["row_ptr"][r0:r1 + 1] - k0).astype(np.int32)).to(dev), torch.from_numpy(G["col"][k0:k1]).to(dev),
+                               torch.from_numpy(G["val"][k0:k1]).to(dev), bounds, rank, jacobi=True)
+    packed = any(len(idx) and not np.array_equal(idx, np.arange(idx[0], idx[0] + len(idx))) for idx in part.plan.send_to.values())
+    b_loc = torch.from_numpy(bfull[r0:r1]).to(dev)
+    for sid in (api.LCG_CG, api.LCG_PCG, api.LCG_BICGSTAB):
+        for name, kw in (("pinned25", dict(epsilon=1e-300, max_iterations=25)), ("eps1e-12", dict(epsilon=1e-12, max_iterations=3000))):
+            m = torch.zeros(part.n_local, dtype=torch.float64, device=dev)
+            r = api.solve(part.op, sid, m, b_loc, param=api.lcg_default_parameters(**kw), device=True, jacobi=(sid == api.LCG_PCG))
+            parts = [torch.empty(bounds[i + 1] - bounds[i], dtype=torch.float64, device=dev) for i in range(world)]
+            dist.all_gather(parts, m)
+            if rank == 0:
+                x = torch.cat(parts).cpu().numpy()
+                cpu = port.solve(sid, G, bfull, para=po.default_para(**kw), diag=Afull.diagonal())
+                rel = float(np.linalg.norm(x - cpu.x) / np.linalg.norm(cpu.x))
+                ok = r.ret == cpu.ret and abs(r.iterations - cpu.iters) <= 1 and (r.iterations != cpu.iters or rel <= 1e-8)
+                print(f"{'OK  ' if ok else 'FAIL'} world={world} random-SPD n={n} solver={sid} {name:9s} ret {r.ret}/{cpu.ret} it {r.iterations}/{cpu.iters} rel {rel:.2e} "
+                      f"packed-sends {packed} peers {part.plan.peers} transport {'nvlink-p2p' if part.p2p else 'nccl'}", flush=True)
+                failures += 0 if ok else 1
+    part.close()
     t = torch.tensor([failures], device=dev)
     dist.broadcast(t, 0)
     dist.barrier()
