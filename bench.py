@@ -219,6 +219,7 @@ def run_ours(args, wl):
     else:
         n, nnz = g ** 3, stencil_nnz(kind, g)
     transport = None
+    dev_csr = None
     iters = args.iters
     para = api.lcg_default_parameters(epsilon=1e-300, max_iterations=iters)
 
@@ -244,8 +245,7 @@ def run_ours(args, wl):
         assert lib.lcgb200_gen_rhs(KIND_ID[kind], g, 0, n, b_d.data_ptr(), None) == 0
         torch.cuda.synchronize()
         op = api.CsrOperator(rp, ci, va, jacobi=(solver == "PCG"))
-        del rp, ci, va
-        torch.cuda.empty_cache()
+        dev_csr = (rp, ci, va)   # kept for the reference-CUDA leg (the operator owns its own copy)
         n_loc = n
     m_d = torch.zeros(n_loc, dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
@@ -393,6 +393,39 @@ def run_ours(args, wl):
                 "iteration": {"algorithmic_bytes": bpi, "achieved_GBps_per_gpu": bpi * value / 1e9 / world,
                               "frac_of_peak": bpi * value / 1e9 / world / peak, "frac_of_8TBps_nominal": bpi * value / 1e9 / world / 8000.0}}
 
+    # ---- the reference's OWN CUDA path on this GPU (cuBLAS host loop + cusparseSpMV callback, oracle/_ref/liblcg_ref_cuda.so)
+    ref_cuda = None
+    if world == 1 and not args.no_ref_cuda and dev_csr is not None and solver in ("CG", "PCG", "CGS"):
+        try:
+            from oracle import pyoracle as po
+            if po.have_reference_cuda():
+                rc_lib = po.RefCuda()
+                it_rc = min(iters, 100)
+                mh = np.zeros(n)
+                bh = b_d.cpu().numpy()
+                rc_lib.solve(solver, n, nnz, dev_csr[0].data_ptr(), dev_csr[1].data_ptr(), dev_csr[2].data_ptr(), mh, bh, 1e-300, 5)   # warm-up (library init)
+                best = None
+                for _ in range(3):
+                    mh[:] = 0.0
+                    ret_rc, secs, _k = rc_lib.solve(solver, n, nnz, dev_csr[0].data_ptr(), dev_csr[1].data_ptr(), dev_csr[2].data_ptr(), mh, bh, 1e-300, it_rc)
+                    best = secs if best is None else min(best, secs)
+                # same system, same iteration count through our entry point: the two GPU paths must land on the same iterate
+                mo = np.zeros(n)
+                para_rc = api.lcg_default_parameters(epsilon=1e-300, max_iterations=it_rc)
+                if solver == "PCG":
+                    api.lcg_solver_preconditioned_cuda(api.CSR_AX, api.JACOBI_MX, None, mo, bh, n, nnz, para_rc, op)
+                else:
+                    api.lcg_solver_cuda(api.CSR_AX, None, mo, bh, n, nnz, para_rc, op, solver_id=sid)
+                ref_cuda = {"value": it_rc / best, "unit": "iterations/s", "kind": "reference lcg_cuda.cu, unmodified: cuBLAS level-1 host loop + cusparseSpMV Ax callback"
+                            + (" + lcg_vecDvecD_element_wise Jacobi Mx callback" if solver == "PCG" else ""),
+                            "ret": ret_rc, "iterations": it_rc, "best_of": 3, "includes": "H2D of m, B and D2H of m, like e2e",
+                            "rel_l2_vs_ours_same_iterations": float(np.linalg.norm(mo - mh) / max(np.linalg.norm(mh), 1e-300)),
+                            "speedup_e2e": e2e["value"] / (it_rc / best)}
+        except Exception as exc:   # the baseline is optional evidence; never let it take the bench line down
+            ref_cuda = {"unavailable": repr(exc)[:200]}
+    dev_csr = None
+    torch.cuda.empty_cache()
+
     # ---- cpu baseline (N = 1 only): the reference CPU/OpenMP solver on the same system, bounded sample
     cpu = None
     if world == 1 and not args.no_cpu:
@@ -411,7 +444,7 @@ def run_ours(args, wl):
                    "l2": (f"inputs larger than L2: CSR {12 * nnz / world / 1e9:.2f} GB per GPU streamed every iteration (no flush needed)" if 12 * nnz / world > 126e6
                           else "cache-resident system: launch-latency-bound, it/s only (no roofline claim)"),
                    "lanes_per_row": info["lanes_per_row"], "tiles": info["n_tiles"]},
-        "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+        "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "reference_cuda": ref_cuda, "clocks": clocks,
         "hbm_gbs_per_iteration": bpi * value / 1e9 / world,
         "diagnostics": {"solve_device_ms_per_step": dev_ms_inside / args.steps, "profile_pass_device_ms_per_step": prof_dev_ms / args.steps,
                         "kernel_ms_sum_per_step": (spmv_ms + vec_ms) / args.steps},
@@ -433,6 +466,7 @@ def main():
     ap.add_argument("--cpu-iters", type=int, default=10, help="iterations of the cpu_baseline sample")
     ap.add_argument("--ref-iters", type=int, default=10, help="iterations per step of the --impl reference arm")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip the reference-CUDA (cuBLAS + cuSPARSE) leg")
     ap.add_argument("--poll", type=int, default=0, help="iterations enqueued per host poll of the convergence flag (0 = library default)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

@@ -170,6 +170,31 @@ class Oracle:
         return SolveResult(ret, out[0], out[1], dout[0], dout[1], x, hist[:min(out[1], hist_cap)].copy())
 
 
+REF_CUDA_SO = os.path.join(HERE, "_ref", "liblcg_ref_cuda.so")
+
+
+def have_reference_cuda() -> bool:
+    return os.path.exists(REF_CUDA_SO)
+
+
+class RefCuda:
+    """The UNMODIFIED reference CUDA solvers (lcg_cuda.cu: cuBLAS host loop + the caller's cusparseSpMV callback) behind
+    oracle/ref_cuda_shim.cu — a GPU baseline for bench.py.  CSR arrays: device pointers; m, b: host numpy arrays."""
+    SOLVERS = {"CG": 0, "PCG": 1, "CGS": 2}
+
+    def __init__(self):
+        self.lib = C.CDLL(REF_CUDA_SO)
+        self.lib.lcgrefcuda_solve.restype = C.c_int
+
+    def solve(self, solver: str, n: int, nnz: int, d_rp: int, d_ci: int, d_val: int, m: np.ndarray, b: np.ndarray,
+              epsilon: float, max_iterations: int, with_progress: bool = False):
+        secs, its = C.c_double(), C.c_int()
+        ret = self.lib.lcgrefcuda_solve(C.c_int(self.SOLVERS[solver]), C.c_int(n), C.c_int(nnz), C.c_void_p(d_rp), C.c_void_p(d_ci), C.c_void_p(d_val),
+                                        _p(m, C.c_double), _p(b, C.c_double), C.c_double(epsilon), C.c_int(max_iterations),
+                                        C.c_int(int(with_progress)), C.byref(secs), C.byref(its))
+        return ret, secs.value, its.value
+
+
 _KINDS = {"7pt": 0, "27pt": 1, "7pt_cd": 2}
 
 

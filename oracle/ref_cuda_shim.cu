@@ -1,0 +1,94 @@
+// TEST / BENCH INFRASTRUCTURE — NOT PART OF THE PRODUCT.
+//
+// Driver around the UNMODIFIED reference CUDA solvers (compiled by oracle/Makefile from
+// /root/reference/src/lib/{lcg_cuda.cu, algebra_cuda.cu, util.cpp, algebra.cpp} with -DLibLCG_CUDA into
+// oracle/_ref/liblcg_ref_cuda.so): the reference's own GPU path — cuBLAS level-1 calls from the host loop plus the
+// caller's cusparseSpMV in the Ax callback — run on the same B200 as a "beat that" baseline for bench.py
+// (optional third column).  The callbacks do what the reference's samples do by hand:
+// cusparseSpMV for Ax (sample8.cu:96-103, with the CUDA-12 generic API) and the element-wise divide by the CSR
+// diagonal for the Jacobi Mx (sample10.cu:100-121,193).
+#include <cstdio>
+#include <chrono>
+#include <cuda_runtime.h>
+#include <cublas_v2.h>
+#include <cusparse_v2.h>
+
+#include "lcg_cuda.h"       // resolved with -I/root/reference/src/lib at build time (never copied)
+#include "algebra_cuda.h"
+
+namespace {
+
+struct Sys
+{
+	cusparseSpMatDescr_t A = nullptr;
+	void* buf = nullptr; size_t buf_bytes = 0;
+	double* d_diag = nullptr;
+	int last_k = -1;
+};
+
+void ref_ax(void* instance, cublasHandle_t, cusparseHandle_t cus, cusparseDnVecDescr_t x, cusparseDnVecDescr_t Ax, const int, const int)
+{
+	Sys* s = static_cast<Sys*>(instance);
+	const double one = 1.0, zero = 0.0;
+	cusparseSpMV(cus, CUSPARSE_OPERATION_NON_TRANSPOSE, &one, s->A, x, &zero, Ax, CUDA_R_64F, CUSPARSE_SPMV_ALG_DEFAULT, s->buf);
+}
+
+void ref_mx(void* instance, cublasHandle_t, cusparseHandle_t, cusparseDnVecDescr_t x, cusparseDnVecDescr_t Mx, const int n, const int)
+{
+	Sys* s = static_cast<Sys*>(instance);
+	double *px = nullptr, *pz = nullptr;
+	cusparseDnVecGetValues(x, (void**)&px);
+	cusparseDnVecGetValues(Mx, (void**)&pz);
+	lcg_vecDvecD_element_wise(px, s->d_diag, pz, n);   // the reference's own kernel (algebra_cuda.cu:69-77,103-110)
+}
+
+int ref_progress(void* instance, const lcg_float*, const lcg_float, const lcg_para*, const int, const int, const int k)
+{
+	static_cast<Sys*>(instance)->last_k = k;
+	return 0;
+}
+
+}  // namespace
+
+// CSR arrays are DEVICE pointers; m (in/out) and b are HOST arrays, as the reference API wants them.
+// solver: 0 = CG (lcg_solver_cuda), 1 = Jacobi-PCG (lcg_solver_preconditioned_cuda), 2 = CGS.  with_progress: pass a
+// progress callback (the reference then records k; its loop is synchronous either way).
+// Returns the reference's return code; *seconds = wall time of the solver call, *iterations = last k seen (or -1).
+extern "C" int lcgrefcuda_solve(int solver, int n, int nnz, const int* d_rp, const int* d_ci, const double* d_val, double* m, const double* b,
+	double epsilon, int max_iterations, int with_progress, double* seconds, int* iterations)
+{
+	cublasHandle_t cub; cusparseHandle_t cus;
+	if (cublasCreate(&cub) != CUBLAS_STATUS_SUCCESS || cusparseCreate(&cus) != CUSPARSE_STATUS_SUCCESS) return -9999;
+	Sys sys;
+	cusparseCreateCsr(&sys.A, n, n, nnz, const_cast<int*>(d_rp), const_cast<int*>(d_ci), const_cast<double*>(d_val),
+		CUSPARSE_INDEX_32I, CUSPARSE_INDEX_32I, CUSPARSE_INDEX_BASE_ZERO, CUDA_R_64F);
+	{	// SpMV workspace, sized once (the samples do this before the solve, sample8.cu:179-181)
+		double *tx = nullptr, *ty = nullptr;
+		cudaMalloc((void**)&tx, sizeof(double) * n); cudaMalloc((void**)&ty, sizeof(double) * n);
+		cusparseDnVecDescr_t vx, vy;
+		cusparseCreateDnVec(&vx, n, tx, CUDA_R_64F); cusparseCreateDnVec(&vy, n, ty, CUDA_R_64F);
+		const double one = 1.0, zero = 0.0;
+		cusparseSpMV_bufferSize(cus, CUSPARSE_OPERATION_NON_TRANSPOSE, &one, sys.A, vx, &zero, vy, CUDA_R_64F, CUSPARSE_SPMV_ALG_DEFAULT, &sys.buf_bytes);
+		cudaMalloc(&sys.buf, sys.buf_bytes > 0 ? sys.buf_bytes : 16);
+		cusparseDestroyDnVec(vx); cusparseDestroyDnVec(vy); cudaFree(tx); cudaFree(ty);
+	}
+	if (solver == 1)
+	{
+		cudaMalloc((void**)&sys.d_diag, sizeof(double) * n);
+		lcg_smDcsr_get_diagonal(d_rp, d_ci, d_val, n, sys.d_diag);   // the reference's own kernel (algebra_cuda.cu:40-57)
+	}
+	lcg_para para = lcg_default_parameters();
+	para.epsilon = epsilon; para.max_iterations = max_iterations;
+	cudaDeviceSynchronize();
+	const auto t0 = std::chrono::steady_clock::now();
+	int ret;
+	lcg_progress_cuda_ptr pf = with_progress ? ref_progress : nullptr;
+	if (solver == 1) ret = lcg_solver_preconditioned_cuda(ref_ax, ref_mx, pf, m, b, n, nnz, &para, &sys, cub, cus);
+	else ret = lcg_solver_cuda(ref_ax, pf, m, b, n, nnz, &para, &sys, cub, cus, solver == 2 ? LCG_CGS : LCG_CG);
+	cudaDeviceSynchronize();
+	if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+	if (iterations) *iterations = sys.last_k;
+	cusparseDestroySpMat(sys.A); cudaFree(sys.buf); cudaFree(sys.d_diag);
+	cublasDestroy(cub); cusparseDestroy(cus);
+	return ret;
+}
