@@ -201,6 +201,28 @@ int lcgb200_csolver_preconditioned_cuda(lcgb200_caxfunc_cuda_ptr Afp, lcgb200_ca
 	void* m, const void* B, const int n_size, const int nz_size, const lcgb200_cpara* param, void* instance,
 	lcgb200_cublas_t cub_handle, lcgb200_cusparse_t cus_handle, int solver_id);
 
+/* ---- the reference's HOST-callback API (lcg.h:71-113, clcg.h:74-76) ----
+ * Same arguments, dispatch and return codes as lcg_solver (CG, CGS, BICGSTAB, BICGSTAB2; anything else -> CGS, lcg.cpp:59-82),
+ * lcg_solver_preconditioned (always PCG, lcg.cpp:87-91), lcg_solver_constrained (PG, SPG, lcg.cpp:121-140) and clcg_solver
+ * (BICG, BICG_SYM, CGS, BICGSTAB, TFQMR; anything else -> CGS, clcg.cpp:46-74).  m, B (low, hig): HOST arrays.  Pass the
+ * sentinels below with an lcgb200_csr_t as `instance` to run on the fused built-in operator; any other callback runs on
+ * the HOST as in the reference (the vector is staged over PCIe for every call: correct, slow).  The progress callback
+ * receives a HOST copy of the current solution. */
+/* clcg_axfunc_ptr (clcg.h:40-41): layout 0 = MatNormal, 1 = MatTranspose; conjugate 0 = NonConjugate, 1 = Conjugate */
+typedef void (*lcgb200_caxfunc_ptr)(void* instance, const void* x, void* prod_Ax, const int n_size, int layout, int conjugate);
+typedef int (*lcgb200_cprogress_ptr)(void* instance, const void* m, const double converge, const lcgb200_cpara* param, const int n_size, const int k);
+void lcgb200_csr_ax_host(void* instance, const double* x, double* prod_Ax, const int n_size);        /* sentinel */
+void lcgb200_jacobi_mx_host(void* instance, const double* x, double* prod_Mx, const int n_size);     /* sentinel */
+void lcgb200_csr_cax_host(void* instance, const void* x, void* prod_Ax, const int n_size, int layout, int conjugate);   /* sentinel */
+int lcgb200_solver(lcgb200_axfunc_ptr Afp, lcgb200_progress_ptr Pfp, double* m, const double* B, const int n_size,
+	const lcgb200_para* param, void* instance, int solver_id);
+int lcgb200_solver_preconditioned(lcgb200_axfunc_ptr Afp, lcgb200_axfunc_ptr Mfp, lcgb200_progress_ptr Pfp, double* m, const double* B,
+	const int n_size, const lcgb200_para* param, void* instance, int solver_id);
+int lcgb200_solver_constrained(lcgb200_axfunc_ptr Afp, lcgb200_progress_ptr Pfp, double* m, const double* B, const double* low, const double* hig,
+	const int n_size, const lcgb200_para* param, void* instance, int solver_id);
+int lcgb200_csolver(lcgb200_caxfunc_ptr Afp, lcgb200_cprogress_ptr Pfp, void* m, const void* B, const int n_size,
+	const lcgb200_cpara* param, void* instance, int solver_id);
+
 /* =====================================================================================================
  * Handle-shaped entry points (same engine; vectors may already be on the device)
  * ===================================================================================================== */

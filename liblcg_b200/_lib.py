@@ -35,6 +35,11 @@ AXFUNC = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_v
 PROGRESS = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.POINTER(LcgPara), C.c_int, C.c_int, C.c_int)
 CAXFUNC = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int)
 CPROGRESS = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.POINTER(ClcgPara), C.c_int, C.c_int, C.c_int)
+# host-callback API (lcg.h:37-38,53-54; clcg.h:40-41,56-57)
+AXFUNC_HOST = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int)
+PROGRESS_HOST = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_double, C.POINTER(LcgPara), C.c_int, C.c_int)
+CAXFUNC_HOST = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int)
+CPROGRESS_HOST = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_double, C.POINTER(ClcgPara), C.c_int, C.c_int)
 
 # every symbol include/lcgb200.h declares: name -> (restype, argtypes or None)
 _VP, _I, _D, _LL = C.c_void_p, C.c_int, C.c_double, C.c_longlong
@@ -68,6 +73,13 @@ SYMBOLS = {
     "lcgb200_solver_constrained_cuda": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, C.POINTER(LcgPara), _VP, _VP, _VP, _I]),
     "lcgb200_csolver_cuda": (_I, [_VP, _VP, _VP, _VP, _I, _I, C.POINTER(ClcgPara), _VP, _VP, _VP, _I]),
     "lcgb200_csolver_preconditioned_cuda": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, C.POINTER(ClcgPara), _VP, _VP, _VP, _I]),
+    "lcgb200_csr_ax_host": (None, None),
+    "lcgb200_jacobi_mx_host": (None, None),
+    "lcgb200_csr_cax_host": (None, None),
+    "lcgb200_solver": (_I, [_VP, _VP, _VP, _VP, _I, C.POINTER(LcgPara), _VP, _I]),
+    "lcgb200_solver_preconditioned": (_I, [_VP, _VP, _VP, _VP, _VP, _I, C.POINTER(LcgPara), _VP, _I]),
+    "lcgb200_solver_constrained": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, C.POINTER(LcgPara), _VP, _I]),
+    "lcgb200_csolver": (_I, [_VP, _VP, _VP, _VP, _I, C.POINTER(ClcgPara), _VP, _I]),
     "lcgb200_solve": (_I, [_VP, _I, _VP, _VP, _VP, _VP, C.POINTER(LcgPara), _VP, C.c_uint, _VP, C.POINTER(Info)]),
     "lcgb200_csolve": (_I, [_VP, _I, _VP, _VP, C.POINTER(ClcgPara), _VP, C.c_uint, _VP, C.POINTER(Info)]),
     "lcgb200_set_shadow_seed": (None, [C.c_long]),

@@ -286,6 +286,74 @@ def clcg_solver_preconditioned_cuda(Afp, Mfp, Pfp, m, B, n_size, nz_size, param,
                                                            cub_handle, cus_handle, solver_id)
 
 
+# ------------------------------------------------------------------ the reference's HOST-callback API (lcg.h, clcg.h)
+CSR_AX_HOST = _Sentinel("lcgb200_csr_ax_host")
+JACOBI_MX_HOST = _Sentinel("lcgb200_jacobi_mx_host")
+CSR_CAX_HOST = _Sentinel("lcgb200_csr_cax_host")
+
+
+def _host_ax(fn, n, complex_):
+    """Python callable (x: ndarray[, layout, conjugate]) -> ndarray  =>  C host callback."""
+    if fn is None or isinstance(fn, _Sentinel):
+        return fn, _afp_addr(fn)
+    k = 2 if complex_ else 1
+
+    if complex_:
+        def tramp(instance, x, y, nn, layout, conj):
+            xv = np.ctypeslib.as_array(x, shape=(nn * k,)).view(np.complex128)
+            np.ctypeslib.as_array(y, shape=(nn * k,)).view(np.complex128)[:] = fn(xv, layout, conj)
+        cb = _lib.CAXFUNC_HOST(tramp)
+    else:
+        def tramp(instance, x, y, nn):
+            np.ctypeslib.as_array(y, shape=(nn,))[:] = fn(np.ctypeslib.as_array(x, shape=(nn,)))
+        cb = _lib.AXFUNC_HOST(tramp)
+    return cb, C.cast(cb, C.c_void_p).value
+
+
+def _host_progress(fn, complex_):
+    if fn is None:
+        return None, None
+    k = 2 if complex_ else 1
+
+    def tramp(instance, m, converge, param, n, it):
+        mv = np.ctypeslib.as_array(m, shape=(n * k,))
+        return int(fn(mv.view(np.complex128) if complex_ else mv, converge, param.contents, n, it) or 0)
+
+    cb = (_lib.CPROGRESS_HOST if complex_ else _lib.PROGRESS_HOST)(tramp)
+    return cb, C.cast(cb, C.c_void_p).value
+
+
+def lcg_solver(Afp, Pfp, m, B, n_size, param, instance, solver_id=LCG_CGS) -> int:
+    """lcg_solver (reference lcg.h:71-72).  Afp: CSR_AX_HOST (instance = CsrOperator) or a Python callable x -> A x run on the host."""
+    a, ap = _host_ax(Afp, n_size, False)
+    p, pp = _host_progress(Pfp, False)
+    return _lib.load().lcgb200_solver(ap, pp, _ptr(m), _ptr(B), n_size, C.byref(param) if param is not None else None, _instance(instance), solver_id)
+
+
+def lcg_solver_preconditioned(Afp, Mfp, Pfp, m, B, n_size, param, instance, solver_id=LCG_PCG) -> int:
+    """lcg_solver_preconditioned (reference lcg.h:90-91)."""
+    a, ap = _host_ax(Afp, n_size, False)
+    mm, mp = _host_ax(Mfp, n_size, False)
+    p, pp = _host_progress(Pfp, False)
+    return _lib.load().lcgb200_solver_preconditioned(ap, mp, pp, _ptr(m), _ptr(B), n_size, C.byref(param) if param is not None else None,
+                                                     _instance(instance), solver_id)
+
+
+def lcg_solver_constrained(Afp, Pfp, m, B, low, hig, n_size, param, instance, solver_id=LCG_PG) -> int:
+    """lcg_solver_constrained (reference lcg.h:111-113)."""
+    a, ap = _host_ax(Afp, n_size, False)
+    p, pp = _host_progress(Pfp, False)
+    return _lib.load().lcgb200_solver_constrained(ap, pp, _ptr(m), _ptr(B), _ptr(low), _ptr(hig), n_size, C.byref(param) if param is not None else None,
+                                                  _instance(instance), solver_id)
+
+
+def clcg_solver(Afp, Pfp, m, B, n_size, param, instance, solver_id=CLCG_BICG) -> int:
+    """clcg_solver (reference clcg.h:74-76).  Afp: CSR_CAX_HOST or a Python callable (x, layout, conjugate) -> op(A) x."""
+    a, ap = _host_ax(Afp, n_size, True)
+    p, pp = _host_progress(Pfp, True)
+    return _lib.load().lcgb200_csolver(ap, pp, _ptr(m), _ptr(B), n_size, C.byref(param) if param is not None else None, _instance(instance), solver_id)
+
+
 # ------------------------------------------------------------------------------------- handle-shaped calls
 def solve(A: CsrOperator, solver_id, m, B, low=None, hig=None, param=None, Pfp=None, device=False, jacobi=False, stream=None) -> Result:
     """lcgb200_solve: real solvers on the built-in operator; m/B numpy (host) or CUDA tensors (device=True)."""

@@ -752,3 +752,133 @@ int lcgb200_csolver_preconditioned_cuda(lcgb200_caxfunc_cuda_ptr Afp, lcgb200_ca
 }
 
 }  // extern "C"
+
+// ================================================================================ CPU-shaped entry points
+// lcg_solver / lcg_solver_preconditioned / lcg_solver_constrained (lcg.h:71-113) and clcg_solver (clcg.h:74-76): the
+// reference's HOST-callback API.  With the sentinel callbacks (lcgb200_csr_ax_host & co.) and an lcgb200_csr_t as
+// `instance` the solve runs on the fused built-in operator; any other callback is honoured on the generic path (the
+// vector is staged to the host, the user's callback runs there, the product is staged back — correct, not fast).
+// The progress callback receives a HOST copy of the current solution, as in the reference (lcg.h:53-54).
+namespace {
+
+template <class T>
+struct HostStage {	// page-locked staging vectors for host callbacks
+	T* x = nullptr; T* y = nullptr; T* m = nullptr; int n = 0;
+	explicit HostStage(int n_) : n(n_) {}
+	T* get(T*& p) { if (!p) LCG_CUDA_CHECK(cudaMallocHost((void**)&p, sizeof(T) * (size_t)n)); return p; }
+	~HostStage() { if (x) cudaFreeHost(x); if (y) cudaFreeHost(y); if (m) cudaFreeHost(m); }
+};
+
+int host_real(lcgb200_axfunc_ptr Afp, lcgb200_axfunc_ptr Mfp, lcgb200_progress_ptr Pfp, double* m, const double* B, const double* low, const double* hig,
+	const int n, const lcgb200_para* param, void* instance, int solver_id)
+{
+	const lcgb200_para para = param ? *param : kDefPara;
+	int rc = check_real(solver_id, n, para, m, B, low, hig);
+	if (rc) return rc;
+	if (!Afp) return LCGB200_INVALID_POINTER;
+	const bool builtin = (Afp == lcgb200_csr_ax_host);
+	CsrHandle* h = builtin ? reinterpret_cast<CsrHandle*>(instance) : nullptr;
+	if (builtin)
+	{
+		if (!h) return LCGB200_INVALID_POINTER;
+		if (h->value_type != LCGB200_REAL || h->n_rows != n) return LCGB200_SIZE_NOT_MATCH;
+	}
+	if (solver_id == LCGB200_PCG)
+	{
+		if (!Mfp) return LCGB200_INVALID_POINTER;
+		if (Mfp == lcgb200_jacobi_mx_host && !(builtin && h->diag)) return LCGB200_NULL_PRECONDITION_MATRIX;
+	}
+	return guarded([&]() {
+		HostStage<double> hs(n);
+		Operator<double> A; A.h = h;
+		void* user = builtin ? h->user : instance;
+		auto host_call = [&](lcgb200_axfunc_ptr f, const double* x, double* y) {
+			LCG_CUDA_CHECK(cudaMemcpy(hs.get(hs.x), x, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+			f(user, hs.x, hs.get(hs.y), n);
+			LCG_CUDA_CHECK(cudaMemcpy(y, hs.y, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+		};
+		if (!builtin) A.apply = [&](const double* x, double* y, int) { host_call(Afp, x, y); };
+		if (solver_id == LCGB200_PCG)
+		{
+			if (Mfp == lcgb200_jacobi_mx_host) A.diag = (const double*)h->diag;
+			else A.precond = [&](const double* x, double* y, int) { host_call(Mfp, x, y); };
+		}
+		auto make_pf = [&](const double* m_dev) -> ProgressFn {
+			if (!Pfp) return ProgressFn();
+			return [&, m_dev](double res, int k) {
+				LCG_CUDA_CHECK(cudaMemcpy(hs.get(hs.m), m_dev, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+				return Pfp(user, hs.m, res, &para, n, k);
+			};
+		};
+		return do_solve_real(h, A, solver_id, m, B, low, hig, para, n, h ? h->n_cols : n, h ? h->n_global : (long long)n, make_pf, false, nullptr, nullptr);
+	});
+}
+
+}  // namespace
+
+extern "C" {
+
+void lcgb200_csr_ax_host(void*, const double*, double*, const int) {}
+void lcgb200_jacobi_mx_host(void*, const double*, double*, const int) {}
+void lcgb200_csr_cax_host(void*, const void*, void*, const int, int, int) {}
+
+int lcgb200_solver(lcgb200_axfunc_ptr Afp, lcgb200_progress_ptr Pfp, double* m, const double* B, const int n_size,
+	const lcgb200_para* param, void* instance, int solver_id)
+{	// lcg.cpp:59-82: CG, CGS, BICGSTAB, BICGSTAB2; anything else -> CGS
+	int id = LCGB200_CGS;
+	if (solver_id == LCGB200_CG || solver_id == LCGB200_BICGSTAB || solver_id == LCGB200_BICGSTAB2) id = solver_id;
+	return host_real(Afp, nullptr, Pfp, m, B, nullptr, nullptr, n_size, param, instance, id);
+}
+
+int lcgb200_solver_preconditioned(lcgb200_axfunc_ptr Afp, lcgb200_axfunc_ptr Mfp, lcgb200_progress_ptr Pfp, double* m, const double* B,
+	const int n_size, const lcgb200_para* param, void* instance, int)
+{	// lcg.cpp:87-91: always lpcg
+	return host_real(Afp, Mfp, Pfp, m, B, nullptr, nullptr, n_size, param, instance, LCGB200_PCG);
+}
+
+int lcgb200_solver_constrained(lcgb200_axfunc_ptr Afp, lcgb200_progress_ptr Pfp, double* m, const double* B, const double* low, const double* hig,
+	const int n_size, const lcgb200_para* param, void* instance, int solver_id)
+{	// lcg.cpp:121-140: PG, SPG; anything else -> PG
+	return host_real(Afp, nullptr, Pfp, m, B, low, hig, n_size, param, instance, solver_id == LCGB200_SPG ? LCGB200_SPG : LCGB200_PG);
+}
+
+int lcgb200_csolver(lcgb200_caxfunc_ptr Afp, lcgb200_cprogress_ptr Pfp, void* m, const void* B, const int n_size,
+	const lcgb200_cpara* param, void* instance, int solver_id)
+{	// clcg.cpp:46-74: BICG, BICG_SYM, CGS, BICGSTAB, TFQMR; anything else -> CGS
+	const lcgb200_cpara para = param ? *param : kDefCPara;
+	const int n = n_size;
+	int rc = check_cplx(n, para, m, B);
+	if (rc) return rc;
+	if (!Afp) return LCGB200_C_INVALID_POINTER;
+	if (solver_id < LCGB200_CBICG || solver_id > LCGB200_CTFQMR) solver_id = LCGB200_CCGS;
+	const bool builtin = (Afp == lcgb200_csr_cax_host);
+	CsrHandle* h = builtin ? reinterpret_cast<CsrHandle*>(instance) : nullptr;
+	if (builtin)
+	{
+		if (!h) return LCGB200_C_INVALID_POINTER;
+		if (h->value_type != LCGB200_COMPLEX || h->n_rows != n) return LCGB200_C_SIZE_NOT_MATCH;
+		if (solver_id == LCGB200_CBICG && !h->t_row_ptr) { set_error_msg("CLCG_BICG needs LCGB200_CSR_TRANSPOSE"); return LCGB200_C_UNKNOWN_SOLVER; }
+	}
+	return guarded([&]() {
+		HostStage<double2> hs(n);
+		Operator<double2> A; A.h = h;
+		void* user = builtin ? h->user : instance;
+		if (!builtin)
+			A.apply = [&](const double2* x, double2* y, int op) {	// op 0 = A x, 1 = A^T x, 2 = A^H x  ->  (layout, conjugate) of clcg.h:40-41
+				LCG_CUDA_CHECK(cudaMemcpy(hs.get(hs.x), x, sizeof(double2) * (size_t)n, cudaMemcpyDeviceToHost));
+				Afp(user, hs.x, hs.get(hs.y), n, op == 0 ? 0 : 1, op == 2 ? 1 : 0);
+				LCG_CUDA_CHECK(cudaMemcpy(y, hs.y, sizeof(double2) * (size_t)n, cudaMemcpyHostToDevice));
+			};
+		auto make_pf = [&](const double2* m_dev) -> ProgressFn {
+			if (!Pfp) return ProgressFn();
+			return [&, m_dev](double res, int k) {
+				LCG_CUDA_CHECK(cudaMemcpy(hs.get(hs.m), m_dev, sizeof(double2) * (size_t)n, cudaMemcpyDeviceToHost));
+				return Pfp(user, hs.m, res, &para, n, k);
+			};
+		};
+		return do_solve_cplx(h, A, solver_id, (double2*)m, (const double2*)B, para, n, h ? h->n_cols : n, h ? h->n_global : (long long)n, make_pf, false, nullptr, nullptr);
+	});
+}
+
+}  // extern "C"
+

@@ -119,6 +119,9 @@ def test_cxx_dropin_headers_compile():
     src = r"""
 #include "lcg_b200/lcg_cuda.h"
 #include "lcg_b200/clcg_cuda.h"
+#include "lcg_b200/lcg.h"
+#include "lcg_b200/clcg.h"
+#include "lcg_b200/solver_cuda.h"
 #include <cstddef>
 static_assert(sizeof(lcg_para) == 64 && offsetof(lcg_para, epsilon) == 8 && offsetof(lcg_para, maxi_m) == 56, "lcg_para layout (util.h:95-148)");
 static_assert(sizeof(clcg_para) == 24, "clcg_para layout (util.h:247-273)");
@@ -130,6 +133,9 @@ int main() {
              cublasHandle_t, cusparseHandle_t, lcg_solver_enum) = lcg_solver_cuda;
     int (*g)(clcg_axfunc_cuda_ptr, clcg_progress_cuda_ptr, cuDoubleComplex*, const cuDoubleComplex*, const int, const int, const clcg_para*,
              void*, cublasHandle_t, cusparseHandle_t, clcg_solver_enum) = clcg_solver_cuda;
+    int (*hs)(lcg_axfunc_ptr, lcg_progress_ptr, lcg_float*, const lcg_float*, const int, const lcg_para*, void*, lcg_solver_enum) = lcg_solver;
+    int (*hc)(clcg_axfunc_ptr, clcg_progress_ptr, lcg_complex*, const lcg_complex*, const int, const clcg_para*, void*, clcg_solver_enum) = clcg_solver;
+    if (!hs || !hc) return 2;
     return (p.epsilon == 1e-6 && q.epsilon == 1e-6 && f && g && lcg_select_solver("LCG_PG") == LCG_PG && lcg_select_solver("x") == LCG_CGS) ? 0 : 1;
 }
 """

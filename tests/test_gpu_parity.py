@@ -617,3 +617,59 @@ def test_full_size_properties(torch_cuda, kind_id, g, sid, symmetric):
     r2 = api.solve(op, sid, m2, b, param=para, device=True, jacobi=(sid == api.LCG_PCG))
     assert r2.iterations == r.iterations and torch.equal(m, m2)
     op.close()
+
+
+def test_host_callback_api(torch_cuda, port, fixtures):
+    """The reference's HOST-callback entry points (lcg.h:71-113, clcg.h:74-76): the built-in operator through the sentinels,
+    a genuine host Ax / Mx callback on the generic path, host-visible progress, dispatch defaults and error codes."""
+    import scipy.sparse as sp
+    A = fixtures["10K"]
+    n = A["n"]
+    S = sp.csr_matrix((A["val"], A["col"], A["row_ptr"]), shape=(n, n))
+    op = api.CsrOperator(A["row_ptr"], A["col"], A["val"], jacobi=True)
+    para = api.lcg_default_parameters(epsilon=1e-10)
+    cpu = {sid: port.solve(sid, A, A["b"], para=po.default_para(epsilon=1e-10), diag=A["diag"]) for sid in (api.LCG_CG, api.LCG_PCG, api.LCG_CGS)}
+    seen = []
+    m = np.zeros(n)
+    assert api.lcg_solver(api.CSR_AX_HOST, lambda mm, c, p, nn, k: seen.append((k, float(mm[0]))) or 0, m, A["b"], n, para, op, api.LCG_CG) == 0
+    assert seen[-1][0] == cpu[api.LCG_CG].iters and rel(m, cpu[api.LCG_CG].x) <= X_TOL and seen[-1][1] == m[0]   # Pfp saw the HOST solution
+    m = np.zeros(n)
+    assert api.lcg_solver(lambda x: S @ x, None, m, A["b"], n, para, None, api.LCG_CG) == 0          # genuine host callback
+    assert rel(m, cpu[api.LCG_CG].x) <= X_TOL
+    m = np.zeros(n)
+    assert api.lcg_solver(api.CSR_AX_HOST, None, m, A["b"], n, para, op, 99) == 0                  # unknown id -> CGS (lcg.cpp:76-78)
+    assert rel(m, cpu[api.LCG_CGS].x) <= X_TOL
+    m = np.zeros(n)
+    assert api.lcg_solver_preconditioned(api.CSR_AX_HOST, api.JACOBI_MX_HOST, None, m, A["b"], n, para, op) == 0
+    assert rel(m, cpu[api.LCG_PCG].x) <= X_TOL
+    m = np.zeros(n)
+    assert api.lcg_solver_preconditioned(lambda x: S @ x, lambda r: r / A["diag"], None, m, A["b"], n, para, None) == 0
+    assert rel(m, cpu[api.LCG_PCG].x) <= X_TOL
+    lo, hi = np.full(n, -1e3), np.full(n, 1e3)
+    m = np.zeros(n)
+    assert api.lcg_solver_constrained(api.CSR_AX_HOST, None, m, A["b"], lo, hi, n, para, op, api.LCG_PG) == 0
+    assert rel(m, port.solve(api.LCG_PG, A, A["b"], para=po.default_para(epsilon=1e-10), low=lo, hig=hi).x) <= 1e-5
+    assert api.lcg_solver(api.CSR_AX_HOST, None, m, A["b"], 0, para, op) == api.LCG_INVILAD_VARIABLE_SIZE
+    assert api.lcg_solver(None, None, m, A["b"], n, para, op) == api.LCG_INVALID_POINTER
+    op.close()
+    # complex: built-in and a host callback honouring (layout, conjugate)
+    Ac = fixtures["1Kc"]
+    nc = Ac["n"]
+    Sc = sp.csr_matrix((Ac["val"], Ac["col"], Ac["row_ptr"]), shape=(nc, nc))
+    cpara = api.clcg_default_parameters(epsilon=1e-300, max_iterations=20)
+    ref = port.csolve(po.CLCG_BICG, Ac, Ac["b"], para=po.default_cpara(epsilon=1e-300, max_iterations=20))
+    opc = api.CsrOperator(Ac["row_ptr"], Ac["col"], Ac["val"], transpose=True)
+    m = np.zeros(nc, dtype=np.complex128)
+    assert api.clcg_solver(api.CSR_CAX_HOST, None, m, Ac["b"], nc, cpara, opc, api.CLCG_BICG) == ref.ret
+    assert rel(m, ref.x) <= X_TOL
+    calls = []
+
+    def host_cax(x, layout, conj):
+        calls.append((layout, conj))
+        M = Sc.T if layout == 1 else Sc
+        return (M.conj() if conj == 1 else M) @ x
+
+    m = np.zeros(nc, dtype=np.complex128)
+    assert api.clcg_solver(host_cax, None, m, Ac["b"], nc, cpara, None, api.CLCG_BICG) == ref.ret
+    assert rel(m, ref.x) <= X_TOL and (1, 1) in calls and (0, 0) in calls          # A^H d2 requested as (MatTranspose, Conjugate)
+    opc.close()
