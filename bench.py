@@ -296,6 +296,18 @@ def run_ours(args, wl):
     dev_ms_inside = sum(r.info.device_ms for r in res)
     value = args.steps * iters / (ms_dev * 1e-3)
 
+    # ---- per-iteration host synchronisation cost: the same solve with a trivial progress callback: the host
+    # then makes one round trip per loop head, exactly like the reference's loop
+    pf_value = None
+    if world == 1:
+        m_d.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        rp_ = api.solve(op, sid, m_d, b_d, param=para, device=True, jacobi=(solver == "PCG"), stream=stream, Pfp=lambda *a: 0)
+        torch.cuda.synchronize()
+        pf_value = {"value": rp_.iterations / (time.perf_counter() - t0), "unit": "iterations/s",
+                    "note": "same step with a trivial progress callback: one host round trip per iteration"}
+
     # ---- roofline pass: same steps, every launch bracketed by events
     api.set_profile(True)
     m_d.zero_()
@@ -444,7 +456,7 @@ def run_ours(args, wl):
                    "l2": (f"inputs larger than L2: CSR {12 * nnz / world / 1e9:.2f} GB per GPU streamed every iteration (no flush needed)" if 12 * nnz / world > 126e6
                           else "cache-resident system: launch-latency-bound, it/s only (no roofline claim)"),
                    "lanes_per_row": info["lanes_per_row"], "tiles": info["n_tiles"]},
-        "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "reference_cuda": ref_cuda, "clocks": clocks,
+        "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "reference_cuda": ref_cuda, "with_progress_callback": pf_value, "clocks": clocks,
         "hbm_gbs_per_iteration": bpi * value / 1e9 / world,
         "diagnostics": {"solve_device_ms_per_step": dev_ms_inside / args.steps, "profile_pass_device_ms_per_step": prof_dev_ms / args.steps,
                         "kernel_ms_sum_per_step": (spmv_ms + vec_ms) / args.steps},

@@ -1,5 +1,5 @@
 #!/bin/bash
-export LCGB200_LIB=$PWD/scratch/variants/s2_t1792_c4.so
+export LCGB200_LIB=$PWD/tools/variants/s2_t1792_c4.so
 for poll in 4 32; do for it in 100 400; do
 timeout 300 python bench.py --workload pcg27_256 --steps 3 --iters $it --poll $poll --no-cpu 2>&1 | tail -1 | python -c "
 import sys, json

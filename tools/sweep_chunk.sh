@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: scratch/sweep.sh tag  — quick perf sweep of SpMV chunking on the two single-GPU headline workloads
+# usage: tools/sweep_chunk.sh tag  — quick perf sweep of SpMV chunking on the two single-GPU headline workloads
 for cr in 64 128 256 512 1024; do
   for wl in pcg27_256 cg7_128; do
     LCGB200_SPMV_CHUNK_ROWS=$cr timeout 300 python bench.py --workload $wl --steps 3 --no-cpu 2>&1 | tail -1 | python -c "

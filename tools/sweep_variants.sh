@@ -1,8 +1,8 @@
 #!/bin/bash
-# perf sweep over the SpMV build variants in scratch/variants (LCGB200_LIB override)
-for v in default $(ls scratch/variants/*.so | xargs -n1 basename | sed 's/\.so$//'); do
+# perf sweep over the SpMV build variants in tools/variants (LCGB200_LIB override)
+for v in default $(ls tools/variants/*.so | xargs -n1 basename | sed 's/\.so$//'); do
   for wl in pcg27_256 cg7_128; do
-    if [ "$v" = default ]; then unset LCGB200_LIB; else export LCGB200_LIB=$PWD/scratch/variants/$v.so; fi
+    if [ "$v" = default ]; then unset LCGB200_LIB; else export LCGB200_LIB=$PWD/tools/variants/$v.so; fi
     timeout 300 python bench.py --workload $wl --steps 3 --no-cpu 2>&1 | tail -1 | python -c "
 import sys, json
 try:
