@@ -49,11 +49,11 @@ int pick_tile_rows(long long nnz, long long rows, int lpr, int tile_nnz)
 	return cap;
 }
 
-// tiles per chunk: a CTA walks `chunk` consecutive tiles (~512 rows: two grid lines of a 256^3 stencil; measured best on B200, profiles/sweep_r01.txt) before jumping ahead by the grid stride
+// tiles per chunk: a CTA walks `chunk` consecutive tiles (~256 rows: one grid line of a 256^3 stencil; measured best on B200 with 4 CTAs per SM, profiles/sweep_r01.txt) before jumping ahead by the grid stride
 int pick_chunk(int tile_rows)
 {
 	static const char* env = getenv("LCGB200_SPMV_CHUNK_ROWS");
-	const int target = env ? std::max(1, atoi(env)) : 512;
+	const int target = env ? std::max(1, atoi(env)) : 256;
 	return std::max(1, target / std::max(tile_rows, 1));
 }
 

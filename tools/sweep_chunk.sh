@@ -1,8 +1,8 @@
 #!/bin/bash
 # usage: tools/sweep_chunk.sh tag  — quick perf sweep of SpMV chunking on the two single-GPU headline workloads
-for cr in 64 128 256 512 1024; do
+for cr in 256 512 1024 2048; do
   for wl in pcg27_256 cg7_128; do
-    LCGB200_SPMV_CHUNK_ROWS=$cr timeout 300 python bench.py --workload $wl --steps 3 --no-cpu 2>&1 | tail -1 | python -c "
+    LCGB200_SPMV_CHUNK_ROWS=$cr timeout 300 python bench.py --workload $wl --steps 3 --no-cpu --no-ref-cuda 2>&1 | tail -1 | python -c "
 import sys, json
 d = json.loads(sys.stdin.read())
 r = d['roofline']
