@@ -308,6 +308,7 @@ int do_solve_real(CsrHandle* h, Operator<double>& A, int solver_id, double* m, c
 	init.ret = RC_UNKNOWN;
 	E.start(init);
 	E.pf = make_pf(d_m);
+	E.sync_each = A.host_side;
 	int ret = solve_real(E, A, solver_id, d_m, d_B, d_lo, d_hi, para, (size_t)n, (size_t)n_ext);
 	const double dev_ms = E.device_ms();
 	if (!m_inplace)
@@ -349,6 +350,7 @@ int do_solve_cplx(CsrHandle* h, Operator<double2>& A, int solver_id, double2* m,
 	init.ret = RC_UNKNOWN;
 	E.start(init);
 	E.pf = make_pf(d_m);
+	E.sync_each = A.host_side;
 	int ret = solve_complex(E, A, solver_id, d_m, d_B, para, (size_t)n, (size_t)n_ext);
 	const double dev_ms = E.device_ms();
 	if (!m_inplace)
@@ -797,11 +799,11 @@ int host_real(lcgb200_axfunc_ptr Afp, lcgb200_axfunc_ptr Mfp, lcgb200_progress_p
 			f(user, hs.x, hs.get(hs.y), n);
 			LCG_CUDA_CHECK(cudaMemcpy(y, hs.y, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
 		};
-		if (!builtin) A.apply = [&](const double* x, double* y, int) { host_call(Afp, x, y); };
+		if (!builtin) { A.apply = [&](const double* x, double* y, int) { host_call(Afp, x, y); }; A.host_side = true; }
 		if (solver_id == LCGB200_PCG)
 		{
 			if (Mfp == lcgb200_jacobi_mx_host) A.diag = (const double*)h->diag;
-			else A.precond = [&](const double* x, double* y, int) { host_call(Mfp, x, y); };
+			else { A.precond = [&](const double* x, double* y, int) { host_call(Mfp, x, y); }; A.host_side = true; }
 		}
 		auto make_pf = [&](const double* m_dev) -> ProgressFn {
 			if (!Pfp) return ProgressFn();
@@ -863,6 +865,7 @@ int lcgb200_csolver(lcgb200_caxfunc_ptr Afp, lcgb200_cprogress_ptr Pfp, void* m,
 		HostStage<double2> hs(n);
 		Operator<double2> A; A.h = h;
 		void* user = builtin ? h->user : instance;
+		A.host_side = !builtin;
 		if (!builtin)
 			A.apply = [&](const double2* x, double2* y, int op) {	// op 0 = A x, 1 = A^T x, 2 = A^H x  ->  (layout, conjugate) of clcg.h:40-41
 				LCG_CUDA_CHECK(cudaMemcpy(hs.get(hs.x), x, sizeof(double2) * (size_t)n, cudaMemcpyDeviceToHost));

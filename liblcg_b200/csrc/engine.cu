@@ -199,7 +199,7 @@ bool Engine::sync_point()
 
 int Engine::run(const std::function<bool()>& iterate, const std::function<void(int)>& batch)
 {
-	if (pf)
+	if (pf || sync_each)
 	{	// one host round trip per loop head, exactly like the reference
 		while (true)
 		{

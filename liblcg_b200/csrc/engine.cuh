@@ -71,6 +71,7 @@ struct Operator {
 	ApplyFn<T> apply;               // otherwise
 	ApplyFn<T> precond;             // user M^-1 (generic path); empty when built-in Jacobi or none
 	const T* diag = nullptr;        // built-in Jacobi diagonal
+	bool host_side = false;         // the callbacks run on the HOST (lcg.h API): check convergence before every call, never run ahead
 };
 
 struct Settings {
@@ -101,6 +102,7 @@ public:
 	void prof_end(cudaEvent_t e) { if (e) cudaEventRecord(e, stream); }
 	void prof_collect(double* ms, int* count);   // sums per class (2 entries each); call after a stream sync
 	ProgressFn pf;                 // empty = no progress callback
+	bool sync_each = false;        // one host round trip per loop head even without a progress callback (host-side operator callbacks)
 	int seen_checks = 0;
 	int final_ret = RC_UNKNOWN;
 	// workspace arena

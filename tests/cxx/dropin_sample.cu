@@ -13,6 +13,7 @@
 #include <vector>
 #include <cuda_runtime.h>
 #include "lcg_b200/solver_cuda.h"   // pulls in lcg_cuda.h, clcg_cuda.h, util.h
+#include "lcg_b200/solver.h"        // host-callback API: lcg.h, clcg.h, LCG_Solver, CLCG_Solver
 
 struct Coo { int r, c; double v; };
 
@@ -74,6 +75,20 @@ public:
 		user_mx(sys, cub, cus, x, Mx, n, nz);
 	}
 	int Progress(const lcg_float*, const lcg_float, const lcg_para*, const int, const int, const int) override { monitor_calls++; return 0; }
+};
+
+// the host-callback class wrapper (solver.h:32-177): AxProduct / MxProduct work on HOST arrays, as with the reference's CPU library
+class HostUserSolver : public LCG_Solver
+{
+public:
+	const std::vector<int>* rp = nullptr; const std::vector<int>* ci = nullptr; const std::vector<double>* va = nullptr; const std::vector<double>* dg = nullptr;
+	int ax_calls = 0, mx_calls = 0;
+	void AxProduct(const lcg_float* x, lcg_float* y, const int n) override
+	{
+		for (int i = 0; i < n; i++) { double s = 0.0; for (int k = (*rp)[(size_t)i]; k < (*rp)[(size_t)i + 1]; k++) s += (*va)[(size_t)k] * x[(*ci)[(size_t)k]]; y[i] = s; }
+		ax_calls++;
+	}
+	void MxProduct(const lcg_float* r, lcg_float* z, const int n) override { for (int i = 0; i < n; i++) z[i] = r[i] / (*dg)[(size_t)i]; mx_calls++; }
 };
 
 static double avg_error(const std::vector<double>& x, const std::vector<double>& ans)
@@ -174,6 +189,26 @@ int main(int argc, char** argv)
 		lcg_para bad = para; bad.epsilon = -1.0; slv.set_lcg_parameter(bad);
 		try { slv.Minimize(cub, cus, m.data(), b.data(), n, nz, LCG_CG); } catch (const std::runtime_error&) { threw = true; }   // silent_ => throws on error (solver_cuda.cu:73-78)
 		if (!threw) fails++;
+	}
+	// host-callback API: LCG_Solver with host Ax/Mx (generic path, staged over PCIe) and on the built-in operator
+	{
+		HostUserSolver hs; hs.rp = &rp; hs.ci = &ci; hs.va = &va; hs.dg = &diag;
+		hs.set_lcg_parameter(para); hs.silent();
+		for (int path = 0; path < 2; path++)
+		{
+			hs.use_builtin_operator(path == 1 ? builtin : nullptr);
+			std::vector<double> m((size_t)n, 0.0);
+			hs.ax_calls = hs.mx_calls = 0;
+			hs.MinimizePreconditioned(m.data(), b.data(), n);
+			const double err = avg_error(m, ans);
+			std::printf("host-API class PCG %-24s host Ax calls %d Mx calls %d avg-error %.3e\n", path == 0 ? "host callbacks" : "built-in fused operator", hs.ax_calls, hs.mx_calls, err);
+			if (!(err < 1e-4)) fails++;
+			if (path == 0 && (hs.ax_calls != 100 || hs.mx_calls != 100)) fails++;   // 1 + 99 iterations: exactly the reference's call count, none past convergence
+			if (path == 1 && (hs.ax_calls != 0 || hs.mx_calls != 0)) fails++;
+		}
+		lcgb200_csr_set_user(builtin, &sys);
+		std::vector<double> m((size_t)n, 0.0);
+		if (lcg_solver(lcgb200_csr_ax_host, nullptr, m.data(), b.data(), n, &para, builtin) != LCG_CONVERGENCE || !(avg_error(m, ans) < 1e-3)) fails++;   // default id: CGS
 	}
 	// error behaviour mirrors the reference (lcg_cuda.cu:91-98)
 	{
