@@ -166,6 +166,8 @@ int lcgb200_csr_set_partition(lcgb200_csr_t A, lcgb200_comm_t comm, long long n_
 #define LCGB200_IPC_HANDLE_BYTES 64
 int lcgb200_comm_p2p_handle(lcgb200_comm_t comm, void* handle_out, long long* n_ghost_out);
 int lcgb200_comm_p2p_attach(lcgb200_comm_t comm, const void* handles, const long long* n_ghost_of_rank, const long long* remote_off);
+/* back to the NCCL transport: every rank must call it when the attach failed on ANY rank (the transports must agree) */
+int lcgb200_comm_p2p_detach(lcgb200_comm_t comm);
 
 /* Sentinel callbacks: never called; their ADDRESS selects the built-in operator.  instance = lcgb200_csr_t. */
 void lcgb200_csr_ax(void* instance, lcgb200_cublas_t, lcgb200_cusparse_t, lcgb200_dnvec_t x, lcgb200_dnvec_t Ax, const int n, const int nz);

@@ -64,6 +64,7 @@ SYMBOLS = {
     "lcgb200_csr_set_partition": (_I, [_VP, _VP, _LL, _I, _VP, _VP, _VP, _VP]),
     "lcgb200_comm_p2p_handle": (_I, [_VP, _VP, C.POINTER(_LL)]),
     "lcgb200_comm_p2p_attach": (_I, [_VP, _VP, _VP, _VP]),
+    "lcgb200_comm_p2p_detach": (_I, [_VP]),
     "lcgb200_csr_ax": (None, None),
     "lcgb200_jacobi_mx": (None, None),
     "lcgb200_csr_cax": (None, None),

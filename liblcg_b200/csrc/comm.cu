@@ -356,6 +356,14 @@ int lcgb200_comm_p2p_handle(lcgb200_comm_t comm, void* handle_out, long long* n_
 	});
 }
 
+int lcgb200_comm_p2p_detach(lcgb200_comm_t comm)
+{	// back to the NCCL transport (e.g. when some rank could not map its peers' windows)
+	NcclComm* c = reinterpret_cast<NcclComm*>(comm);
+	if (!c) return LCGB200_INVALID_POINTER;
+	c->p2p_ready = false;
+	return 0;
+}
+
 int lcgb200_comm_p2p_attach(lcgb200_comm_t comm, const void* handles, const long long* n_ghost_of_rank, const long long* remote_off)
 {
 	NcclComm* c = reinterpret_cast<NcclComm*>(comm);

@@ -182,8 +182,9 @@ def enable_p2p(comm: Communicator, plan: HaloPlan, group=None) -> bool:
     rc = lib.lcgb200_comm_p2p_attach(comm.handle, hb, n_ghost.ctypes.data, remote_off.ctypes.data)
     ok = [None] * comm.world
     dist.all_gather_object(ok, rc == 0, group=group)
-    if not all(ok):
-        raise RuntimeError(f"lcgb200_comm_p2p_attach failed on some rank ({rc}): {api.last_error()}")
+    if not all(ok):   # e.g. no CUDA-IPC between two of the devices: every rank falls back to the NCCL transport
+        lib.lcgb200_comm_p2p_detach(comm.handle)
+        return False
     return True
 
 
