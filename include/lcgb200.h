@@ -93,6 +93,12 @@ enum { LCGB200_REAL = 0, LCGB200_COMPLEX = 1 };
 enum { LCGB200_HOST = 0, LCGB200_DEVICE = 1 };
 enum {
 	LCGB200_CSR_TRANSPOSE = 1,   /* also store A^T (needed by complex BiCG's A^H d2, clcg.cpp:188) */
+	LCGB200_CSR_COMPRESS = 4,    /* real operators: if the matrix has <= 256 distinct values and <= 256 distinct (col - row) offsets
+	                                 (constant-coefficient stencils and their row blocks), keep a second copy as one 16-bit code per
+	                                 entry + two dictionaries and stream THAT in the SpMV (2 bytes per non-zero instead of 12); if in
+	                                 addition the rows fall into <= 256 distinct patterns, keep one pattern id per ROW and stream only
+	                                 that.  Same entries, row sums accumulated left to right.  Silently stays uncompressed when the
+	                                 matrix does not fit (lcgb200_csr_format). */
 	LCGB200_CSR_JACOBI = 2       /* extract diag(A) at creation (replaces lcg_smDcsr_get_diagonal, algebra_cuda.cu:40-57,
 	                                 lcg_complex_cuda.cu:46-63) so lcgb200_jacobi_mx can be used */
 };
@@ -116,6 +122,11 @@ int lcgb200_csr_spmv(lcgb200_csr_t A, const void* x_dev, void* y_dev, int op, vo
  * dots[1] = y.y, dots[2] = x.y (real: plain sums; complex: conj-first inner products, 2 doubles each).
  * dots_dev receives 3 (real) or 6 (complex) doubles.  This is exactly the kernel the solvers launch. */
 int lcgb200_csr_spmv_dot(lcgb200_csr_t A, const void* x_dev, void* y_dev, const void* w_dev, double* dots_dev, void* stream);
+/* storage format the SpMV streams (LCGB200_CSR_COMPRESS): *compressed = 0 plain CSR (S+4 bytes per entry), 1 dictionary
+ * codes (2 bytes per entry), 2 row patterns (1 byte per ROW: rows with identical (col - row, value) sequences share a
+ * pattern; at most 256 patterns of at most 64 entries); the dictionary sizes; and the bytes one SpMV launch moves in that
+ * format (matrix + row_ptr + x + y) */
+int lcgb200_csr_format(lcgb200_csr_t A, int* compressed, int* n_values, int* n_offsets, long long* stream_bytes);
 /* bytes the SpMV kernel must move per launch by SURVEY.md §8(d): nnz*(S+4) + (n+1)*4 + 2*n*S */
 long long lcgb200_csr_spmv_bytes(lcgb200_csr_t A);
 int lcgb200_csr_info(lcgb200_csr_t A, int* n_rows, int* n_cols, int* nnz, int* n_tiles, int* lanes_per_row);

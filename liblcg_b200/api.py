@@ -31,7 +31,7 @@ CLCG_REACHED_MAX_ITERATIONS, CLCG_NAN_VALUE, CLCG_INVALID_POINTER, CLCG_SIZE_NOT
 
 REAL, COMPLEX = 0, 1
 HOST, DEVICE = 0, 1
-CSR_TRANSPOSE, CSR_JACOBI = 1, 2
+CSR_TRANSPOSE, CSR_JACOBI, CSR_COMPRESS = 1, 2, 4
 VEC_DEVICE, USE_JACOBI = 1, 2
 
 
@@ -106,7 +106,7 @@ def _ptr(a):
 class CsrOperator:
     """Built-in CSR operator handle (lcgb200_csr_t).  Arrays may be numpy (host) or torch CUDA tensors (device)."""
 
-    def __init__(self, row_ptr, col, val, n_cols=None, transpose=False, jacobi=False):
+    def __init__(self, row_ptr, col, val, n_cols=None, transpose=False, jacobi=False, compress=False):
         lib = _lib.load()
         on_dev = hasattr(val, "data_ptr")
         if on_dev:
@@ -122,7 +122,7 @@ class CsrOperator:
             nnz = len(col)
         self.n, self.nnz, self.complex = n, nnz, bool(cx)
         self.n_cols = n if n_cols is None else n_cols
-        flags = (CSR_TRANSPOSE if transpose else 0) | (CSR_JACOBI if jacobi else 0)
+        flags = (CSR_TRANSPOSE if transpose else 0) | (CSR_JACOBI if jacobi else 0) | (CSR_COMPRESS if compress else 0)
         h = C.c_void_p()
         rc = lib.lcgb200_csr_create_rect(C.byref(h), n, self.n_cols, nnz, _ptr(row_ptr), _ptr(col), _ptr(val),
                                          COMPLEX if cx else REAL, DEVICE if on_dev else HOST, flags)
@@ -146,6 +146,12 @@ class CsrOperator:
         v = [C.c_int() for _ in range(5)]
         _lib.load().lcgb200_csr_info(self.handle, *[C.byref(x) for x in v])
         return dict(zip(("n_rows", "n_cols", "nnz", "n_tiles", "lanes_per_row"), (x.value for x in v)))
+
+    def format(self):
+        """dict(compressed, n_values, n_offsets, stream_bytes): what the SpMV streams (lcgb200_csr_format)."""
+        c, nv, no, sb = C.c_int(), C.c_int(), C.c_int(), C.c_longlong()
+        _lib.load().lcgb200_csr_format(self.handle, C.byref(c), C.byref(nv), C.byref(no), C.byref(sb))
+        return dict(compressed=bool(c.value), level=c.value, n_values=nv.value, n_offsets=no.value, stream_bytes=int(sb.value))
 
     def spmv_bytes(self) -> int:
         return int(_lib.load().lcgb200_csr_spmv_bytes(self.handle))

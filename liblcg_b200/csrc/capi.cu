@@ -57,14 +57,14 @@ int pick_chunk(int tile_rows)
 	return std::max(1, target / std::max(tile_rows, 1));
 }
 
-// greedy row tiles: consecutive rows (at most rows_cap) whose non-zeros, counted from the 4-aligned start, fit one stage
-void build_tiles(const int* rp, int n_rows, int tile_nnz, int rows_cap, std::vector<int4>& tiles)
+// greedy row tiles: consecutive rows (at most rows_cap) whose non-zeros, counted from the `align`-aligned start, fit one stage
+void build_tiles(const int* rp, int n_rows, int tile_nnz, int rows_cap, std::vector<int4>& tiles, int align = 4)
 {
 	tiles.clear();
 	int r = 0;
 	while (r < n_rows)
 	{
-		const int k0 = rp[r] & ~3;
+		const int k0 = rp[r] & ~(align - 1);
 		int r1 = r;
 		while (r1 < n_rows && r1 - r < rows_cap && rp[r1 + 1] - k0 <= tile_nnz) r1++;
 		if (r1 == r) r1 = r + 1;   // a single row longer than the buffer: the kernel streams it from global memory
@@ -128,6 +128,202 @@ void upload_csr(int n_rows, int nnz, const int* rp_h, const int* ci, const T* v,
 	LCG_CUDA_CHECK(cudaMemcpy(*d_tiles, tiles.data(), tiles.size() * sizeof(int4), cudaMemcpyHostToDevice));
 }
 
+// one thread per row: value -> index in vdict (bitwise match), (col - row) -> index in odict; *fail = 1 if either is missing
+__global__ void k_dict_encode(int n_rows, const int* __restrict__ rp, const int* __restrict__ ci, const double* __restrict__ v,
+	const double* __restrict__ vdict, int nv, const int* __restrict__ odict, int no, unsigned short* __restrict__ code, int* fail)
+{
+	__shared__ long long s_v[256];
+	__shared__ int s_o[256];
+	if (threadIdx.x < 256) { s_v[threadIdx.x] = __double_as_longlong(vdict[threadIdx.x]); s_o[threadIdx.x] = odict[threadIdx.x]; }
+	__syncthreads();
+	const int row = blockIdx.x * blockDim.x + threadIdx.x;
+	if (row >= n_rows) return;
+	for (int k = rp[row]; k < rp[row + 1]; k++)
+	{
+		const long long bits = __double_as_longlong(v[k]);
+		const int off = ci[k] - row;
+		int vi = -1, oi = -1;
+		for (int i = 0; i < nv; i++) if (s_v[i] == bits) { vi = i; break; }
+		for (int i = 0; i < no; i++) if (s_o[i] == off) { oi = i; break; }
+		if (vi < 0 || oi < 0) { *fail = 1; return; }
+		code[k] = (unsigned short)(vi | (oi << 8));
+	}
+}
+
+// ---- row patterns (k_spmv_pat): rows whose sequences of 16-bit codes are identical share one pattern ----------------
+constexpr int kPatTab = 2048;   // open-addressing table of row hashes (patterns are few: 27 for a 3-D stencil)
+
+__device__ __forceinline__ unsigned long long row_hash(const int* rp, const unsigned short* code, int row)
+{
+	unsigned long long h = 1469598103934665603ull;   // FNV-1a over (length, codes)
+	const int kb = rp[row], ke = rp[row + 1];
+	h = (h ^ (unsigned long long)(ke - kb)) * 1099511628211ull;
+	for (int k = kb; k < ke; k++) h = (h ^ (unsigned long long)code[k]) * 1099511628211ull;
+	return h ? h : 1ull;
+}
+
+// every row inserts its hash; slot_of_row[row] = table slot, rep[slot] = smallest row with that hash; *fail on overflow
+__global__ void k_pat_insert(int n_rows, const int* __restrict__ rp, const unsigned short* __restrict__ code, unsigned long long* key, int* rep,
+	int* slot_of_row, int* fail)
+{
+	const int row = blockIdx.x * blockDim.x + threadIdx.x;
+	if (row >= n_rows) return;
+	const unsigned long long h = row_hash(rp, code, row);
+	int slot = (int)(h % kPatTab);
+	for (int probe = 0; probe < kPatTab; probe++)
+	{
+		const unsigned long long prev = atomicCAS(&key[slot], 0ull, h);
+		if (prev == 0ull || prev == h) { atomicMin(&rep[slot], row); slot_of_row[row] = slot; return; }
+		slot = (slot + 1) % kPatTab;
+	}
+	*fail = 1;
+}
+
+// pat[row] = pattern id of its slot; a row that differs from its pattern's representative (hash collision) sets *fail
+__global__ void k_pat_assign(int n_rows, const int* __restrict__ rp, const unsigned short* __restrict__ code, const int* __restrict__ slot_of_row,
+	const int* __restrict__ id_of_slot, const int* __restrict__ rep, unsigned char* pat, int* fail)
+{
+	const int row = blockIdx.x * blockDim.x + threadIdx.x;
+	if (row >= n_rows) return;
+	const int slot = slot_of_row[row];
+	const int r = rep[slot];
+	const int kb = rp[row], len = rp[row + 1] - kb, kr = rp[r];
+	if (rp[r + 1] - kr != len) { *fail = 1; return; }
+	for (int j = 0; j < len; j++) if (code[kb + j] != code[kr + j]) { *fail = 1; return; }
+	pat[row] = (unsigned char)id_of_slot[slot];
+}
+
+// Row-pattern copy on top of the dictionary codes.  Leaves the handle without it when there are more than 256 distinct
+// rows, a row longer than 64 entries, or a table larger than shared memory.
+void try_patterns(CsrHandle* h, const std::vector<int>& rp_h, const std::vector<double>& vd, const std::vector<int>& od)
+{
+	const int n = h->n_rows;
+	unsigned long long* d_key = dev_alloc<unsigned long long>(kPatTab);
+	int* d_rep = dev_alloc<int>(kPatTab); int* d_slot = dev_alloc<int>((size_t)n); int* d_fail = dev_alloc<int>(1);
+	int* d_id = dev_alloc<int>(kPatTab); unsigned char* d_pat = dev_alloc<unsigned char>((size_t)n);
+	int* d_len = nullptr; double2* d_ent = nullptr;
+	bool ok = false;
+	try
+	{
+		std::vector<int> rep_init(kPatTab, 0x7fffffff);
+		LCG_CUDA_CHECK(cudaMemset(d_key, 0, sizeof(unsigned long long) * kPatTab));
+		LCG_CUDA_CHECK(cudaMemcpy(d_rep, rep_init.data(), sizeof(int) * kPatTab, cudaMemcpyHostToDevice));
+		LCG_CUDA_CHECK(cudaMemset(d_fail, 0, sizeof(int)));
+		k_pat_insert<<<(n + 255) / 256, 256>>>(n, h->row_ptr, h->code, d_key, d_rep, d_slot, d_fail);
+		LCG_CUDA_CHECK(cudaGetLastError());
+		int fail = 1;
+		LCG_CUDA_CHECK(cudaMemcpy(&fail, d_fail, sizeof(int), cudaMemcpyDeviceToHost));
+		std::vector<int> rep(kPatTab), id(kPatTab, -1);
+		LCG_CUDA_CHECK(cudaMemcpy(rep.data(), d_rep, sizeof(int) * kPatTab, cudaMemcpyDeviceToHost));
+		std::vector<int> reps;   // representative row of each pattern, in slot order
+		if (!fail)
+		{
+			for (int s = 0; s < kPatTab; s++) if (rep[(size_t)s] != 0x7fffffff) { id[(size_t)s] = (int)reps.size(); reps.push_back(rep[(size_t)s]); }
+			int maxlen = 0;
+			for (int r : reps) maxlen = std::max(maxlen, rp_h[(size_t)r + 1] - rp_h[(size_t)r]);
+			if (reps.size() <= 256 && maxlen >= 1 && maxlen <= 64 && (long long)reps.size() * maxlen <= kPatMaxEntries)
+			{
+				LCG_CUDA_CHECK(cudaMemcpy(d_id, id.data(), sizeof(int) * kPatTab, cudaMemcpyHostToDevice));
+				k_pat_assign<<<(n + 255) / 256, 256>>>(n, h->row_ptr, h->code, d_slot, d_id, d_rep, d_pat, d_fail);
+				LCG_CUDA_CHECK(cudaGetLastError());
+				LCG_CUDA_CHECK(cudaMemcpy(&fail, d_fail, sizeof(int), cudaMemcpyDeviceToHost));
+				if (!fail)
+				{	// the table: decode each representative row through the dictionaries
+					struct Ent { double v; int off; int pad; };
+					std::vector<Ent> ent(reps.size() * (size_t)maxlen, Ent{0.0, 0, 0});
+					std::vector<int> len(reps.size());
+					std::vector<unsigned short> cbuf((size_t)maxlen);
+					for (size_t p = 0; p < reps.size(); p++)
+					{
+						const int r = reps[p], kb = rp_h[(size_t)r];
+						len[p] = rp_h[(size_t)r + 1] - kb;
+						if (len[p] > 0) LCG_CUDA_CHECK(cudaMemcpy(cbuf.data(), h->code + kb, sizeof(unsigned short) * (size_t)len[p], cudaMemcpyDeviceToHost));
+						for (int j = 0; j < len[p]; j++) ent[p * (size_t)maxlen + (size_t)j] = Ent{vd[cbuf[(size_t)j] & 255u], od[cbuf[(size_t)j] >> 8], 0};
+					}
+					d_len = dev_alloc<int>(reps.size()); d_ent = dev_alloc<double2>(ent.size());
+					LCG_CUDA_CHECK(cudaMemcpy(d_len, len.data(), sizeof(int) * len.size(), cudaMemcpyHostToDevice));
+					LCG_CUDA_CHECK(cudaMemcpy(d_ent, ent.data(), sizeof(Ent) * ent.size(), cudaMemcpyHostToDevice));
+					h->pat = d_pat; h->pat_len = d_len; h->pat_ent = d_ent; h->n_pat = (int)reps.size(); h->pat_maxlen = maxlen;
+					ok = true;
+				}
+			}
+		}
+	}
+	catch (...) { cudaFree(d_key); cudaFree(d_rep); cudaFree(d_slot); cudaFree(d_fail); cudaFree(d_id); cudaFree(d_pat); cudaFree(d_len); cudaFree(d_ent); throw; }
+	cudaFree(d_key); cudaFree(d_rep); cudaFree(d_slot); cudaFree(d_fail); cudaFree(d_id);
+	if (!ok) cudaFree(d_pat);
+}
+
+// LCGB200_CSR_COMPRESS: if the matrix has <= 256 distinct values and <= 256 distinct (col - row) offsets, store a second
+// copy as 16-bit codes + dictionaries (csr.cuh: k_spmv_dict).  The dictionaries are guessed from three windows of the
+// matrix (start, middle, end) and then VERIFIED over every entry on the device; anything that does not fit leaves the
+// handle uncompressed.  Returns true when the compressed copy exists.
+bool try_compress(CsrHandle* h, const std::vector<int>& rp_h)
+{
+	const int n = h->n_rows, nnz = h->nnz;
+	if (nnz <= 0) return false;
+	for (int i = 0; i < n; i++) if (rp_h[(size_t)i + 1] - rp_h[(size_t)i] > kDictTileNnz - 8) return false;   // no over-long-row path in the dict kernel
+	const int W = 1 << 17;
+	std::vector<long long> vset; std::vector<int> oset;
+	std::vector<int> cbuf((size_t)std::min(W, nnz)); std::vector<double> vbuf(cbuf.size());
+	const int starts[3] = {0, std::max(0, nnz / 2 - W / 2), std::max(0, nnz - W)};
+	for (int w = 0; w < 3; w++)
+	{
+		const int k0 = starts[w], cnt = std::min(W, nnz - k0);
+		LCG_CUDA_CHECK(cudaMemcpy(cbuf.data(), h->col + k0, sizeof(int) * (size_t)cnt, cudaMemcpyDeviceToHost));
+		LCG_CUDA_CHECK(cudaMemcpy(vbuf.data(), (const double*)h->val + k0, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost));
+		int row = (int)(std::upper_bound(rp_h.begin(), rp_h.end(), k0) - rp_h.begin()) - 1;
+		for (int k = 0; k < cnt; k++)
+		{
+			while (rp_h[(size_t)row + 1] <= k0 + k) row++;
+			long long bits; std::memcpy(&bits, &vbuf[(size_t)k], 8);
+			if (std::find(vset.begin(), vset.end(), bits) == vset.end()) { vset.push_back(bits); if (vset.size() > 256) return false; }
+			const int off = cbuf[(size_t)k] - row;
+			if (std::find(oset.begin(), oset.end(), off) == oset.end()) { oset.push_back(off); if (oset.size() > 256) return false; }
+		}
+	}
+	std::sort(oset.begin(), oset.end());
+	std::vector<double> vd(256, 0.0); std::vector<int> od(256, 0);
+	for (size_t i = 0; i < vset.size(); i++) std::memcpy(&vd[i], &vset[i], 8);
+	for (size_t i = 0; i < oset.size(); i++) od[i] = oset[i];
+	double* d_vd = dev_alloc<double>(256); int* d_od = dev_alloc<int>(256);
+	unsigned short* d_code = dev_alloc<unsigned short>((size_t)nnz + kPad);
+	int* d_fail = dev_alloc<int>(1);
+	bool ok = false;
+	try
+	{
+		LCG_CUDA_CHECK(cudaMemcpy(d_vd, vd.data(), 256 * sizeof(double), cudaMemcpyHostToDevice));
+		LCG_CUDA_CHECK(cudaMemcpy(d_od, od.data(), 256 * sizeof(int), cudaMemcpyHostToDevice));
+		LCG_CUDA_CHECK(cudaMemset(d_code + nnz, 0, kPad * sizeof(unsigned short)));
+		LCG_CUDA_CHECK(cudaMemset(d_fail, 0, sizeof(int)));
+		k_dict_encode<<<(n + 255) / 256, 256>>>(n, h->row_ptr, h->col, (const double*)h->val, d_vd, (int)vset.size(), d_od, (int)oset.size(), d_code, d_fail);
+		LCG_CUDA_CHECK(cudaGetLastError());
+		int fail = 1;
+		LCG_CUDA_CHECK(cudaMemcpy(&fail, d_fail, sizeof(int), cudaMemcpyDeviceToHost));
+		ok = (fail == 0);
+	}
+	catch (...) { cudaFree(d_vd); cudaFree(d_od); cudaFree(d_code); cudaFree(d_fail); throw; }
+	cudaFree(d_fail);
+	if (!ok) { cudaFree(d_vd); cudaFree(d_od); cudaFree(d_code); return false; }
+	// 2-byte entries make a whole pass of 256 rows fit one stage for rows of up to 28 entries: one THREAD per row (no
+	// cross-lane butterfly, no per-lane predication, gathers of 32 consecutive rows coalesce into 2 lines); longer
+	// rows get the fewest lanes per row whose pass still fits
+	const double avg = (double)nnz / (double)n;
+	int dlpr = 1;
+	while (dlpr < 32 && avg * (kThreads / dlpr) > (double)kDictTileNnz) dlpr *= 2;
+	h->dlpr = dlpr;
+	std::vector<int4> tiles;
+	const int rows_cap = pick_tile_rows(nnz, n, dlpr, kDictTileNnz);
+	build_tiles(rp_h.data(), n, kDictTileNnz, rows_cap, tiles, 8);
+	h->dtiles = dev_alloc<int4>(tiles.size());
+	LCG_CUDA_CHECK(cudaMemcpy(h->dtiles, tiles.data(), tiles.size() * sizeof(int4), cudaMemcpyHostToDevice));
+	h->n_dtiles = (int)tiles.size(); h->dchunk = pick_chunk(rows_cap);
+	h->code = d_code; h->vdict = d_vd; h->odict = d_od; h->n_vdict = (int)vset.size(); h->n_odict = (int)oset.size();
+	static const bool no_pat = getenv("LCGB200_NO_PATTERNS") != nullptr;   // comparison runs: dictionary level only
+	if (!no_pat) try_patterns(h, rp_h, vd, od);
+	return true;
+}
+
 template <class T>
 void create_typed(CsrHandle* h, const int* row_ptr, const int* col, const T* val, int location, int tile_nnz)
 {
@@ -153,6 +349,7 @@ void create_typed(CsrHandle* h, const int* row_ptr, const int* col, const T* val
 		host_transpose<T>(h->n_rows, h->n_cols, rp_h.data(), cip, vp, trp, tci, tv);
 		upload_csr<T>(h->n_cols, h->nnz, trp.data(), tci.data(), tv.data(), false, &h->t_row_ptr, &h->t_col, &h->t_val, &h->t_tiles, &h->t_n_tiles, tile_nnz, &h->t_lpr, &h->t_chunk);
 	}
+	if ((h->flags & LCGB200_CSR_COMPRESS) && sizeof(T) == sizeof(double)) try_compress(h, rp_h);
 	if (h->flags & LCGB200_CSR_JACOBI)
 	{
 		T* d = dev_alloc<T>((size_t)h->n_rows);
@@ -170,6 +367,8 @@ void destroy_handle(CsrHandle* h)
 	if (!h) return;
 	cudaFree(h->row_ptr); cudaFree(h->col); cudaFree(h->val); cudaFree(h->tiles);
 	cudaFree(h->t_row_ptr); cudaFree(h->t_col); cudaFree(h->t_val); cudaFree(h->t_tiles);
+	cudaFree(h->code); cudaFree(h->vdict); cudaFree(h->odict); cudaFree(h->dtiles);
+	cudaFree(h->pat); cudaFree(h->pat_len); cudaFree(h->pat_ent);
 	cudaFree(h->diag); cudaFree(h->ws);
 	cudaFree(h->d_state); cudaFree(h->d_partials);
 	if (h->h_state) cudaFreeHost(h->h_state);
@@ -445,6 +644,22 @@ int lcgb200_csr_info(lcgb200_csr_t A, int* n_rows, int* n_cols, int* nnz, int* n
 	if (!h) return LCGB200_INVALID_POINTER;
 	if (n_rows) *n_rows = h->n_rows; if (n_cols) *n_cols = h->n_cols; if (nnz) *nnz = h->nnz;
 	if (n_tiles) *n_tiles = h->n_tiles; if (lanes_per_row) *lanes_per_row = h->lpr;
+	return 0;
+}
+
+int lcgb200_csr_format(lcgb200_csr_t A, int* compressed, int* n_values, int* n_offsets, long long* stream_bytes)
+{
+	CsrHandle* h = reinterpret_cast<CsrHandle*>(A);
+	if (!h) return LCGB200_INVALID_POINTER;
+	const long long S = h->value_type == LCGB200_REAL ? 8 : 16;
+	if (compressed) *compressed = h->pat ? 2 : (h->code ? 1 : 0);
+	if (n_values) *n_values = h->n_vdict;
+	if (n_offsets) *n_offsets = h->n_odict;
+	if (stream_bytes)
+	{
+		if (h->pat) *stream_bytes = (long long)h->n_rows + 2LL * h->n_rows * S;   // one id per row + x + y
+		else *stream_bytes = (long long)h->nnz * (h->code ? 2 : (S + 4)) + ((long long)h->n_rows + 1) * 4 + 2LL * h->n_rows * S;
+	}
 	return 0;
 }
 

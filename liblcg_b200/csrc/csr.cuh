@@ -52,6 +52,13 @@ struct CsrDev {
 	const int* col = nullptr;
 	const T* val = nullptr;
 	const int4* tiles = nullptr;
+	// dictionary-compressed copy (real operators, optional): code = value index | offset index << 8
+	const unsigned short* code = nullptr;
+	const double* vdict = nullptr; const int* odict = nullptr;
+	const int4* dtiles = nullptr; int n_dtiles = 0, dchunk = 1, dlpr = 1;
+	// row-pattern copy (real operators, optional): one pattern id per ROW + a table of the distinct rows
+	const unsigned char* pat = nullptr; const int* pat_len = nullptr; const double2* pat_ent = nullptr;   // entry = {value, (double)offset bits}
+	int n_pat = 0, pat_maxlen = 0;
 };
 
 template <class T> struct TileCfg;
@@ -128,6 +135,8 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 }
 // consumer-only barrier (the producer warp never joins it)
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" :: "n"(kThreads) : "memory"); }
+
+int spmv_grid_limit(int ctas_per_sm);   // resident CTAs of k_spmv on the current device (SMs x CTAs per SM), engine.cu
 
 // Epi interface:
 //   static constexpr int NRED;
@@ -284,6 +293,223 @@ __global__ void __launch_bounds__(kSpmvThreads, TileCfg<T>::CTAS) k_spmv(CsrDev<
 	}
 }
 
+// ---- dictionary-compressed operator ------------------------------------------------------------------------------
+// Matrices with few distinct values and few distinct (col - row) offsets — constant-coefficient stencils, and their
+// row blocks after the ghost remap — are stored a second time as ONE 16-bit code per entry (value index | offset index
+// << 8) plus two dictionaries of <= 256 entries: 2 bytes per non-zero instead of 12 stream from HBM.  The kernel is
+// the same producer/consumer pipeline; consumers decode through the dictionaries held in shared memory.  Entries,
+// per-lane accumulation order and butterfly are those of k_spmv, so y and the fused dots are bitwise identical.
+constexpr int kDictTileNnz = 7168;    // 14 KB of codes per stage: 256 rows x 27-28 or 512 rows x 7
+struct DictStage {
+	static constexpr int CODE_OFF = 0;
+	static constexpr int ROW_OFF = kDictTileNnz * 2;
+	static constexpr int BYTES = (ROW_OFF + (kTileRows + 8) * 4 + 127) & ~127;
+	static constexpr int TOTAL = BYTES * kStages;
+};
+
+template <int LPR, class Epi>
+__global__ void __launch_bounds__(kSpmvThreads, kSpmvCtasPerSm) k_spmv_dict(CsrDev<double> A, const double* __restrict__ x, double* __restrict__ y, Epi epi_in,
+	DevState* st, double* partials)
+{
+	if (st_done(st)) return;
+	typedef DictStage SC;
+	extern __shared__ __align__(128) unsigned char smem[];
+	__shared__ __align__(8) unsigned long long s_bar[2 * kStages];
+	__shared__ double s_vdict[256];
+	__shared__ int s_odict[256];
+
+	const int tid = threadIdx.x;
+	const bool producer = tid >= kThreads;
+	if (tid < 256) { s_vdict[tid] = A.vdict[tid]; s_odict[tid] = A.odict[tid]; }
+	if (tid == 0)
+	{
+		for (int s = 0; s < kStages; s++) { mbar_init(smem_u32(&s_bar[s]), 1); mbar_init(smem_u32(&s_bar[kStages + s]), kThreads / 32); }
+		mbar_fence_init();
+	}
+	__syncthreads();
+
+	Epi epi = epi_in;
+	double acc[Epi::NRED > 0 ? Epi::NRED : 1];
+#pragma unroll
+	for (int r = 0; r < (Epi::NRED > 0 ? Epi::NRED : 1); r++) acc[r] = 0.0;
+	const int n_chunks = (A.n_dtiles + A.dchunk - 1) / A.dchunk;
+
+	if (producer)
+	{
+		if (tid == kThreads)
+		{
+			const uint64_t pol = l2_evict_first_policy();
+			int idx = 0;
+			for (int c = blockIdx.x; c < n_chunks; c += gridDim.x)
+			{
+				const int t1 = min((c + 1) * A.dchunk, A.n_dtiles);
+				for (int tile = c * A.dchunk; tile < t1; tile++)
+				{
+					const int4 td = __ldg(A.dtiles + tile);
+					const int s = idx % kStages, j = idx / kStages;
+					if (j > 0) mbar_wait(smem_u32(&s_bar[kStages + s]), (uint32_t)((j - 1) & 1));
+					const uint32_t cnt = (uint32_t)((td.w - td.z + 7) & ~7);
+					const int ra = td.x & ~3;
+					const uint32_t rcnt = (uint32_t)((td.y - ra + 1 + 3) & ~3);
+					const uint32_t full = smem_u32(&s_bar[s]);
+					const uint32_t base = smem_u32(smem + (size_t)s * SC::BYTES);
+					mbar_expect_tx(full, cnt * 2u + rcnt * 4u);
+					bulk_g2s(base + SC::CODE_OFF, A.code + td.z, cnt * 2u, full, pol);
+					bulk_g2s(base + SC::ROW_OFF, A.row_ptr + ra, rcnt * 4u, full, pol);
+					idx++;
+				}
+			}
+		}
+	}
+	else
+	{
+		epi.begin(st);
+		constexpr int NG = kThreads / LPR;
+		const int group = tid / LPR, lane = tid % LPR;
+		int idx = 0;
+		for (int c = blockIdx.x; c < n_chunks; c += gridDim.x)
+		{
+			const int t1 = min((c + 1) * A.dchunk, A.n_dtiles);
+			for (int tile = c * A.dchunk; tile < t1; tile++)
+			{
+				const int4 td = __ldg(A.dtiles + tile);
+				const int r0 = td.x, nrows = td.y - td.x, k0 = td.z;
+				const int s = idx % kStages;
+				mbar_wait(smem_u32(&s_bar[s]), (uint32_t)((idx / kStages) & 1));
+				const unsigned char* base = smem + (size_t)s * SC::BYTES;
+				const unsigned short* scode = reinterpret_cast<const unsigned short*>(base + SC::CODE_OFF);
+				const int* srow = reinterpret_cast<const int*>(base + SC::ROW_OFF) + (r0 & 3);
+				for (int rb = 0; rb < nrows; rb += NG)
+				{
+					const int r = rb + group;
+					const int row = r0 + r;
+					int kb = 0, ke = 0;
+					if (r < nrows) { kb = srow[r] - k0; ke = srow[r + 1] - k0; }
+					double sum = 0.0;
+					for (int j0 = kb + lane; j0 < ke; j0 += LPR * kGatherUnroll)
+					{
+						int cidx[kGatherUnroll]; double a[kGatherUnroll], xv[kGatherUnroll];
+#pragma unroll
+						for (int u = 0; u < kGatherUnroll; u++)
+						{
+							const int j = j0 + u * LPR;
+							const bool ok = j < ke;
+							const unsigned int cd = ok ? (unsigned int)scode[j] : 0u;
+							cidx[u] = ok ? row + s_odict[cd >> 8] : -1;
+							a[u] = ok ? s_vdict[cd & 255u] : 0.0;
+						}
+#pragma unroll
+						for (int u = 0; u < kGatherUnroll; u++) xv[u] = cidx[u] >= 0 ? tldg(x + cidx[u]) : 0.0;
+#pragma unroll
+						for (int u = 0; u < kGatherUnroll; u++) sum = mulacc(sum, a[u], xv[u]);
+					}
+#pragma unroll
+					for (int o = LPR / 2; o > 0; o >>= 1) sum = tadd(sum, tshfl_xor(sum, o));
+					if (lane == 0 && r < nrows)
+					{
+						y[row] = sum;
+						epi.row(row, sum, tldg(x + row), acc);
+					}
+				}
+				__syncwarp();
+				if ((tid & 31) == 0) mbar_arrive(smem_u32(&s_bar[kStages + s]));
+				idx++;
+			}
+		}
+	}
+	if (Epi::NRED > 0)
+	{
+		double tot[Epi::NRED > 0 ? Epi::NRED : 1];
+		if (grid_reduce<(Epi::NRED > 0 ? Epi::NRED : 1)>(acc, partials, &st->ticket, tot))
+		{
+			if (st->multi) { if (reduce_across_ranks(st, tot, Epi::NRED)) epi.finish(st, tot); }
+			else if ((threadIdx.x & 31) == 0) epi.finish(st, tot);
+		}
+	}
+}
+
+// ---- row-pattern operator ----------------------------------------------------------------------------------------
+// Constant-coefficient discretisations have only a handful of DISTINCT ROWS once a row is written as its sequence of
+// (col - row, value) pairs: interior, faces, edges, corners (27 for a 3-D stencil; a few more after the ghost remap of a
+// row block).  Such a matrix is stored a third time as ONE BYTE PER ROW (its pattern id) plus the table of patterns:
+// the SpMV streams x, y and n bytes of ids — the 12 bytes per non-zero of CSR disappear.  One thread per row walks its
+// pattern out of shared memory (lanes of a warp mostly share the pattern: broadcast reads) and gathers x of 32
+// consecutive rows per instruction (2 lines).  Entries are accumulated left to right with fma: the reference's own
+// order (algebra.cpp-style serial row sums).  Rows are dealt to blocks in chunks of kPatChunk consecutive rows so that
+// neighbouring grid lines are re-used out of L1.
+constexpr int kPatChunk = 2048;
+constexpr int kPatMaxEntries = 3072;   // pattern table entries held in shared memory (48 KB)
+struct PatEntry { double v; int off; int pad; };
+
+template <class Epi>
+__global__ void __launch_bounds__(kThreads) k_spmv_pat(CsrDev<double> A, const double* __restrict__ x, double* __restrict__ y, Epi epi_in,
+	DevState* st, double* partials)
+{
+	if (st_done(st)) return;
+	extern __shared__ __align__(16) unsigned char smem[];
+	PatEntry* s_ent = reinterpret_cast<PatEntry*>(smem);
+	int* s_len = reinterpret_cast<int*>(smem + (size_t)A.n_pat * A.pat_maxlen * sizeof(PatEntry));
+	const int n_ent = A.n_pat * A.pat_maxlen;
+	const PatEntry* g_ent = reinterpret_cast<const PatEntry*>(A.pat_ent);
+	for (int i = threadIdx.x; i < n_ent; i += blockDim.x) s_ent[i] = g_ent[i];
+	for (int i = threadIdx.x; i < A.n_pat; i += blockDim.x) s_len[i] = A.pat_len[i];
+	__syncthreads();
+
+	Epi epi = epi_in;
+	epi.begin(st);
+	double acc[Epi::NRED > 0 ? Epi::NRED : 1];
+#pragma unroll
+	for (int r = 0; r < (Epi::NRED > 0 ? Epi::NRED : 1); r++) acc[r] = 0.0;
+	const int n_chunks = (A.n_rows + kPatChunk - 1) / kPatChunk;
+	for (int c = blockIdx.x; c < n_chunks; c += gridDim.x)
+	{
+		const int end = min((c + 1) * kPatChunk, A.n_rows);
+		for (int row = c * kPatChunk + threadIdx.x; row < end; row += kThreads)
+		{
+			const int p = A.pat[row];
+			const int len = s_len[p];
+			const PatEntry* e = s_ent + p * A.pat_maxlen;
+			const double* xr = x + row;
+			double sum = 0.0;
+			int j = 0;
+			for (; j + 9 <= len; j += 9)
+			{	// 9 independent gathers in flight (a 27-entry row = 3 rounds)
+				double xv[9];
+#pragma unroll
+				for (int u = 0; u < 9; u++) xv[u] = __ldg(xr + e[j + u].off);
+#pragma unroll
+				for (int u = 0; u < 9; u++) sum = fma(e[j + u].v, xv[u], sum);
+			}
+			for (; j < len; j++) sum = fma(e[j].v, __ldg(xr + e[j].off), sum);
+			y[row] = sum;
+			epi.row(row, sum, __ldg(xr), acc);
+		}
+	}
+	if (Epi::NRED > 0)
+	{
+		double tot[Epi::NRED > 0 ? Epi::NRED : 1];
+		if (grid_reduce<(Epi::NRED > 0 ? Epi::NRED : 1)>(acc, partials, &st->ticket, tot))
+		{
+			if (st->multi) { if (reduce_across_ranks(st, tot, Epi::NRED)) epi.finish(st, tot); }
+			else if ((threadIdx.x & 31) == 0) epi.finish(st, tot);
+		}
+	}
+}
+
+template <class Epi>
+inline void launch_spmv_pat(const CsrDev<double>& A, const double* x, double* y, const Epi& epi, DevState* st, double* partials, cudaStream_t s)
+{
+	const size_t smem = (size_t)A.n_pat * A.pat_maxlen * sizeof(PatEntry) + (size_t)A.n_pat * sizeof(int);
+	auto kern = k_spmv_pat<Epi>;
+	static bool configured = false;
+	if (!configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kPatMaxEntries * sizeof(PatEntry) + 1024)); configured = true; }
+	const int n_chunks = (A.n_rows + kPatChunk - 1) / kPatChunk;
+	const int limit = spmv_grid_limit(4);
+	int grid = n_chunks < limit ? n_chunks : limit;
+	if (grid < 1) grid = 1;
+	kern<<<grid, kThreads, smem, s>>>(A, x, y, epi, st, partials);
+}
+
 // Adaptor: run an SpMV epilogue as a plain vector kernel over an already computed y (user-callback operators).
 template <class T, class Epi>
 struct RowEpilogueOp {
@@ -306,7 +532,6 @@ struct EpiNone {
 	__device__ void finish(DevState*, const double*) {}
 };
 
-int spmv_grid_limit(int ctas_per_sm);   // resident CTAs of k_spmv on the current device (SMs x CTAs per SM), engine.cu
 
 template <class T, int LPR, bool CONJ, class Epi>
 inline void launch_spmv_lpr(const CsrDev<T>& A, const T* x, T* y, const Epi& epi, DevState* st, double* partials, cudaStream_t s)
@@ -325,10 +550,42 @@ inline void launch_spmv_lpr(const CsrDev<T>& A, const T* x, T* y, const Epi& epi
 	kern<<<grid, kSpmvThreads, StageCfg<T>::TOTAL, s>>>(A, x, y, epi, st, partials);
 }
 
+template <int LPR, class Epi>
+inline void launch_spmv_dict_lpr(const CsrDev<double>& A, const double* x, double* y, const Epi& epi, DevState* st, double* partials, cudaStream_t s)
+{
+	static bool configured = false;
+	auto kern = k_spmv_dict<LPR, Epi>;
+	if (!configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DictStage::TOTAL); configured = true; }
+	const int n_chunks = (A.n_dtiles + A.dchunk - 1) / A.dchunk;
+	const int limit = spmv_grid_limit(kSpmvCtasPerSm);
+	int grid = n_chunks < limit ? n_chunks : limit;
+	if (grid < 1) grid = 1;
+	kern<<<grid, kSpmvThreads, DictStage::TOTAL, s>>>(A, x, y, epi, st, partials);
+}
+
+template <class Epi>
+inline void launch_spmv_dict(const CsrDev<double>& A, const double* x, double* y, const Epi& epi, DevState* st, double* partials, cudaStream_t s)
+{
+	switch (A.dlpr)
+	{
+		case 1: launch_spmv_dict_lpr<1, Epi>(A, x, y, epi, st, partials, s); break;
+		case 2: launch_spmv_dict_lpr<2, Epi>(A, x, y, epi, st, partials, s); break;
+		case 4: launch_spmv_dict_lpr<4, Epi>(A, x, y, epi, st, partials, s); break;
+		case 8: launch_spmv_dict_lpr<8, Epi>(A, x, y, epi, st, partials, s); break;
+		case 16: launch_spmv_dict_lpr<16, Epi>(A, x, y, epi, st, partials, s); break;
+		default: launch_spmv_dict_lpr<32, Epi>(A, x, y, epi, st, partials, s); break;
+	}
+}
+
 // launch with the lanes-per-row variant recorded in the handle
 template <class T, bool CONJ, class Epi>
 inline void launch_spmv(const CsrDev<T>& A, const T* x, T* y, const Epi& epi, DevState* st, double* partials, cudaStream_t s)
 {
+	if constexpr (sizeof(T) == sizeof(double) && !CONJ)
+	{
+		if (A.pat) { launch_spmv_pat<Epi>(A, x, y, epi, st, partials, s); return; }      // row-pattern copy: 1 B per ROW
+		if (A.code) { launch_spmv_dict<Epi>(A, x, y, epi, st, partials, s); return; }   // dictionary copy: 2 B per entry
+	}
 	switch (A.lpr)
 	{
 		case 1: launch_spmv_lpr<T, 1, CONJ, Epi>(A, x, y, epi, st, partials, s); break;

@@ -40,6 +40,11 @@ struct CsrHandle {
 	int* t_row_ptr = nullptr; int* t_col = nullptr; void* t_val = nullptr; int4* t_tiles = nullptr;
 	int t_n_tiles = 0, t_lpr = 1, t_chunk = 1;
 	void* diag = nullptr;          // Jacobi diagonal (optional), n_rows values
+	// dictionary-compressed copy (LCGB200_CSR_COMPRESS, real): 16-bit codes + dictionaries + its own (larger) tiles
+	unsigned short* code = nullptr; double* vdict = nullptr; int* odict = nullptr; int4* dtiles = nullptr;
+	int n_dtiles = 0, dchunk = 1, dlpr = 1, n_vdict = 0, n_odict = 0;
+	// row-pattern copy: one id per row + the table of distinct rows
+	unsigned char* pat = nullptr; int* pat_len = nullptr; double2* pat_ent = nullptr; int n_pat = 0, pat_maxlen = 0;
 	void* user = nullptr;          // instance handed to progress callbacks
 	Comm* comm = nullptr;          // set for a row block of a partitioned system
 	// cached workspace
@@ -51,7 +56,10 @@ struct CsrHandle {
 	template <class T> CsrDev<T> view() const
 	{
 		CsrDev<T> v; v.n_rows = n_rows; v.n_cols = n_cols; v.nnz = nnz; v.n_tiles = n_tiles; v.lpr = lpr; v.chunk = chunk;
-		v.row_ptr = row_ptr; v.col = col; v.val = (const T*)val; v.tiles = tiles; return v;
+		v.row_ptr = row_ptr; v.col = col; v.val = (const T*)val; v.tiles = tiles;
+		v.code = code; v.vdict = vdict; v.odict = odict; v.dtiles = dtiles; v.n_dtiles = n_dtiles; v.dchunk = dchunk; v.dlpr = dlpr;
+		v.pat = pat; v.pat_len = pat_len; v.pat_ent = pat_ent; v.n_pat = n_pat; v.pat_maxlen = pat_maxlen;
+		return v;
 	}
 	template <class T> CsrDev<T> tview() const
 	{

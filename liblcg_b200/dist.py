@@ -188,7 +188,7 @@ def enable_p2p(comm: Communicator, plan: HaloPlan, group=None) -> bool:
     return True
 
 
-def partition_csr(row_ptr_local, col_global, val, bounds, rank: int, jacobi=False, group=None) -> Partition:
+def partition_csr(row_ptr_local, col_global, val, bounds, rank: int, jacobi=False, group=None, compress=False) -> Partition:
     """This rank's rows (row_ptr rebased to 0, GLOBAL column ids, values; torch CUDA tensors or numpy arrays)
     -> rectangular operator + communicator + halo plan."""
     import torch
@@ -198,9 +198,9 @@ def partition_csr(row_ptr_local, col_global, val, bounds, rank: int, jacobi=Fals
     new_col, plan = plan_partition(colt, bounds, rank, group=group)
     n_loc = bounds[rank + 1] - bounds[rank]
     if on_dev:
-        op = api.CsrOperator(row_ptr_local, new_col.contiguous(), val, n_cols=n_loc + plan.n_ghost, jacobi=jacobi)
+        op = api.CsrOperator(row_ptr_local, new_col.contiguous(), val, n_cols=n_loc + plan.n_ghost, jacobi=jacobi, compress=compress)
     else:
-        op = api.CsrOperator(np.asarray(row_ptr_local), new_col.numpy(), np.asarray(val), n_cols=n_loc + plan.n_ghost, jacobi=jacobi)
+        op = api.CsrOperator(np.asarray(row_ptr_local), new_col.numpy(), np.asarray(val), n_cols=n_loc + plan.n_ghost, jacobi=jacobi, compress=compress)
     comm = Communicator(rank, world, group=group)
     attach_plan(op, comm, plan)
     p2p = False
@@ -214,7 +214,7 @@ def partition_csr(row_ptr_local, col_global, val, bounds, rank: int, jacobi=Fals
 KIND_ID = {"7pt": 0, "27pt": 1, "7pt_cd": 2}
 
 
-def build_stencil_partition(kind: str, g: int, rank: int, world: int, device, jacobi=False, group=None) -> Partition:
+def build_stencil_partition(kind: str, g: int, rank: int, world: int, device, jacobi=False, group=None, compress=False) -> Partition:
     """Rows of this rank of the g^3 stencil system (z-slab partition), generated on the device."""
     import torch
     lib = _lib.load()
@@ -230,7 +230,7 @@ def build_stencil_partition(kind: str, g: int, rank: int, world: int, device, ja
     b = torch.empty(r1 - r0, dtype=torch.float64, device=device)
     assert lib.lcgb200_gen_rhs(KIND_ID[kind], g, r0, r1, b.data_ptr(), None) == 0
     torch.cuda.synchronize()
-    part = partition_csr(rp, ci, va, bounds, rank, jacobi=jacobi, group=group)
+    part = partition_csr(rp, ci, va, bounds, rank, jacobi=jacobi, group=group, compress=compress)
     part.b = b
     del rp, ci, va
     torch.cuda.empty_cache()

@@ -673,3 +673,62 @@ def test_host_callback_api(torch_cuda, port, fixtures):
     assert api.clcg_solver(host_cax, None, m, Ac["b"], nc, cpara, None, api.CLCG_BICG) == ref.ret
     assert rel(m, ref.x) <= X_TOL and (1, 1) in calls and (0, 0) in calls          # A^H d2 requested as (MatTranspose, Conjugate)
     opc.close()
+
+
+@pytest.mark.parametrize("kind,g", [("7pt", 50), ("27pt", 44), ("7pt_cd", 52), ("7pt_varcoef", 40)])
+def test_compressed_operator_formats(torch_cuda, port, kind, g):
+    """LCGB200_CSR_COMPRESS.  Level 2 (row patterns, 1 byte per ROW) for the constant-coefficient stencils, level 1
+    (16-bit codes, 2 bytes per entry) for a 7-point matrix whose coefficients vary from row to row over a small set (too
+    many distinct rows for patterns).  Same entries as the plain CSR copy; row sums left to right with fma, so y agrees
+    to rounding of a different summation order (bitwise for one lane per row), and the solvers land on the same iterates."""
+    torch = torch_cuda
+    if kind == "7pt_varcoef":
+        S = stencil.make_system("7pt", g)
+        rng = np.random.default_rng(12)
+        rows = np.repeat(np.arange(S["n"]), np.diff(S["row_ptr"]))
+        offd = S["col"] != rows
+        S["val"] = S["val"].copy()
+        S["val"][offd] = rng.choice([-1.0, -0.5, -0.25], size=int(offd.sum()))
+        S["val"][~offd] = 7.0                                       # strictly diagonally dominant, nonsymmetric
+        S["b"] = port.spmv(S, S["x_star"])
+        sids, level = (api.LCG_BICGSTAB, api.LCG_CGS), 1
+    else:
+        S = stencil.make_system(kind, g)
+        sids = (api.LCG_CG, api.LCG_PCG) if kind != "7pt_cd" else (api.LCG_BICGSTAB, api.LCG_CGS)
+        level = 2
+    n = S["n"]
+    plain = api.CsrOperator(S["row_ptr"], S["col"], S["val"], jacobi=True)
+    comp = api.CsrOperator(S["row_ptr"], S["col"], S["val"], jacobi=True, compress=True)
+    f = comp.format()
+    assert f["level"] == level and plain.format()["level"] == 0
+    assert f["n_offsets"] == (27 if kind == "27pt" else 7)
+    assert f["stream_bytes"] == (n + 16 * n if level == 2 else 2 * S["nnz"] + 4 * (n + 1) + 16 * n)
+    x = to_dev(torch, np.random.default_rng(3).standard_normal(n))
+    w = to_dev(torch, np.random.default_rng(4).standard_normal(n))
+    y1, y2 = torch.empty_like(x), torch.empty_like(x)
+    d1, d2 = torch.zeros(3, dtype=torch.float64, device="cuda"), torch.zeros(3, dtype=torch.float64, device="cuda")
+    plain.spmv_dot(x, y1, w, d1)
+    comp.spmv_dot(x, y2, w, d2)
+    torch.cuda.synchronize()
+    if plain.info()["lanes_per_row"] == 1:
+        assert torch.equal(y1, y2)                                  # one lane per row on both sides: identical order
+    y_ref = port.spmv(S, x.cpu().numpy())
+    scale = np.linalg.norm(y_ref) / np.sqrt(n)
+    assert np.max(np.abs(y2.cpu().numpy() - y_ref)) / scale < 1e-13
+    assert torch.allclose(d1, d2, rtol=1e-12, atol=1e-9)
+    for sid in sids:
+        para = api.lcg_default_parameters(epsilon=1e-10)
+        m1, m2 = np.zeros(n), np.zeros(n)
+        r1 = api.solve(plain, sid, m1, S["b"], param=para, jacobi=(sid == api.LCG_PCG))
+        r2 = api.solve(comp, sid, m2, S["b"], param=para, jacobi=(sid == api.LCG_PCG))
+        assert r1.ret == r2.ret == 0 and abs(r1.iterations - r2.iterations) <= 1
+        if r1.iterations == r2.iterations:
+            assert rel(m2, m1) <= 1e-8
+        assert rel(m2, S["x_star"]) < 1e-3
+    plain.close()
+    comp.close()
+    # a matrix that does not fit the dictionaries silently stays uncompressed and still works
+    R = random_csr(np.random.default_rng(8), 3000)
+    op = api.CsrOperator(R["row_ptr"], R["col"], R["val"], compress=True)
+    assert op.format()["level"] == 0
+    op.close()
