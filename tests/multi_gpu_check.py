@@ -15,6 +15,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+COMPRESS = os.environ.get("LCGB200_CHECK_COMPRESS", "0") == "1"   # run the stencil cases on the compressed operator copies
+
+
 def main():
     import torch
     import torch.distributed as dist
@@ -31,7 +34,9 @@ def main():
              ("7pt_cd", 5 * world + 14, api.LCG_CGS), ("7pt_cd", 4 * world + 9, api.LCG_BICGSTAB2), ("7pt", 3 * world + 7, api.LCG_PG),
              ("7pt", 3 * world + 7, api.LCG_SPG)]
     for kind, g, sid in cases:
-        part = ldist.build_stencil_partition(kind, g, rank, world, dev, jacobi=(sid == api.LCG_PCG))
+        part = ldist.build_stencil_partition(kind, g, rank, world, dev, jacobi=(sid == api.LCG_PCG), compress=COMPRESS)
+        if COMPRESS and part.op.format()["level"] == 0:
+            raise SystemExit(f"rank {rank}: the row block of the {kind} stencil did not compress")
         n = g ** 3
         S = stencil.make_system(kind, g) if rank == 0 else None
         constrained = sid in (api.LCG_PG, api.LCG_SPG)
@@ -63,7 +68,7 @@ def main():
                         sens = float(np.linalg.norm(cp2.x - cpu.x) / np.linalg.norm(cpu.x))
                     ok = ok and (rel <= 1e-8 or rel <= 20 * sens)
                 print(f"{'OK  ' if ok else 'FAIL'} world={world} {kind:7s} g={g:3d} solver={sid} {name:9s} ret {r.ret}/{cpu.ret} it {r.iterations}/{cpu.iters} "
-                      f"rel {rel:.2e} launches {r.info.kernel_launches} transport {'nvlink-p2p' if part.p2p else 'nccl'} comm {part.comm.stats()}", flush=True)
+                      f"rel {rel:.2e} launches {r.info.kernel_launches} format-level {part.op.format()['level']} transport {'nvlink-p2p' if part.p2p else 'nccl'} comm {part.comm.stats()}", flush=True)
                 failures += 0 if ok else 1
         part.close()
     # a general (non-stencil) SPD system: random long-range couplings -> scattered ghost columns, i.e. the PACKED
