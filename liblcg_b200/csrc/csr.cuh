@@ -191,8 +191,11 @@ __global__ void __launch_bounds__(kSpmvThreads, TileCfg<T>::CTAS) k_spmv(CsrDev<
 					const uint32_t full = smem_u32(&s_bar[s]);
 					const uint32_t base = smem_u32(smem + (size_t)s * SC::BYTES);
 					mbar_expect_tx(full, cnt * (uint32_t)(sizeof(T) + 4) + rcnt * 4u);
-					bulk_g2s(base + SC::VAL_OFF, A.val + td.z, cnt * (uint32_t)sizeof(T), full, pol);
-					bulk_g2s(base + SC::COL_OFF, A.col + td.z, cnt * 4u, full, pol);
+					if (cnt > 0)
+					{	// a tile made only of empty rows has nothing to stream but its row_ptr slice
+						bulk_g2s(base + SC::VAL_OFF, A.val + td.z, cnt * (uint32_t)sizeof(T), full, pol);
+						bulk_g2s(base + SC::COL_OFF, A.col + td.z, cnt * 4u, full, pol);
+					}
 					bulk_g2s(base + SC::ROW_OFF, A.row_ptr + ra, rcnt * 4u, full, pol);
 					idx++;
 				}
@@ -354,7 +357,7 @@ __global__ void __launch_bounds__(kSpmvThreads, kSpmvCtasPerSm) k_spmv_dict(CsrD
 					const uint32_t full = smem_u32(&s_bar[s]);
 					const uint32_t base = smem_u32(smem + (size_t)s * SC::BYTES);
 					mbar_expect_tx(full, cnt * 2u + rcnt * 4u);
-					bulk_g2s(base + SC::CODE_OFF, A.code + td.z, cnt * 2u, full, pol);
+					if (cnt > 0) bulk_g2s(base + SC::CODE_OFF, A.code + td.z, cnt * 2u, full, pol);
 					bulk_g2s(base + SC::ROW_OFF, A.row_ptr + ra, rcnt * 4u, full, pol);
 					idx++;
 				}

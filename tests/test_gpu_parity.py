@@ -120,7 +120,7 @@ def random_csr(rng, n, long_row=None, empty_every=0, cx=False):
 
 
 # ------------------------------------------------------------------------------------------------ SpMV
-@pytest.mark.parametrize("case", ["10K", "7pt", "27pt", "7pt_cd", "ragged", "ragged_long", "tiny"])
+@pytest.mark.parametrize("case", ["10K", "7pt", "27pt", "7pt_cd", "ragged", "ragged_long", "empty_runs", "all_empty", "tiny"])
 def test_spmv_real_matches_oracle(torch_cuda, port, fixtures, case):
     torch = torch_cuda
     rng = np.random.default_rng(3)
@@ -132,6 +132,18 @@ def test_spmv_real_matches_oracle(torch_cuda, port, fixtures, case):
         A = random_csr(rng, 5000, empty_every=7)
     elif case == "ragged_long":
         A = random_csr(rng, 6000, long_row=(1234, 5000), empty_every=11)   # 5000 > 2048 staged non-zeros
+    elif case in ("empty_runs", "all_empty"):
+        # whole tiles made of empty rows (nothing to stream but the row_ptr slice), a matrix with no entries at all
+        A = random_csr(rng, 9000, empty_every=3)
+        lens = np.diff(A["row_ptr"]).copy()
+        lens[1500:5200] = 0
+        lens[8000:] = 0
+        if case == "all_empty":
+            lens[:] = 0
+        keep = np.repeat(lens > 0, np.diff(A["row_ptr"]))
+        rp = np.zeros(A["n"] + 1, dtype=np.int32)
+        np.cumsum(lens, out=rp[1:])
+        A = dict(n=A["n"], nnz=int(rp[-1]), row_ptr=rp, col=A["col"][keep], val=A["val"][keep])
     else:
         A = random_csr(rng, 3)
     op = api.CsrOperator(A["row_ptr"], A["col"], A["val"])
