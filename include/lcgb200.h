@@ -238,6 +238,8 @@ int lcgb200_csolver(lcgb200_caxfunc_ptr Afp, lcgb200_cprogress_ptr Pfp, void* m,
 
 /* =====================================================================================================
  * Handle-shaped entry points (same engine; vectors may already be on the device)
+ * A handle caches the workspace, the device state block and the pinned read-back buffers of its solves: ONE solve at a
+ * time per handle (use one handle per concurrent solve; the matrix arrays can be shared by creating it from device arrays).
  * ===================================================================================================== */
 typedef struct lcgb200_info {
 	int iterations;        /* k handed to the last convergence check (what the reference reports through Pfp) */
@@ -279,6 +281,16 @@ void lcgb200_set_poll_interval(int iterations);
 /* 1 (default): systems small enough to stay cache-resident (<= 65536 rows, <= 2M non-zeros; CG, Jacobi-PCG and the complex
  * BICG_SYM / Jacobi-PCG) run several whole iterations per cooperative launch; 0: always the streaming kernels */
 void lcgb200_set_fused_small(int on);
+/* Cross-GPU waits of the NVLink peer-memory transport (a rank waiting for a neighbour's halo or reduction totals) give up
+ * after this many milliseconds (default: environment LCGB200_SPIN_TIMEOUT_MS, else 30000; 0 = wait for ever); the limit is
+ * 20x longer while a progress callback or a host-side operator keeps the host inside every iteration.  A timeout ends the
+ * solve with LCGB200_UNKNOWN_ERROR and a message (lcgb200_last_error), and POISONS the communicator: its sequence counters
+ * may no longer agree with the peers', so later solves on it are refused — destroy it and create a new one. */
+void lcgb200_set_spin_timeout_ms(long long ms);
+/* CUDA graphs for batches of iterations when no host-visible sync point lies inside an iteration: -1 (default) =
+ * environment LCGB200_GRAPHS or automatic (on for systems whose iteration is short enough for launch gaps to matter),
+ * 0 = off, 1 = on */
+void lcgb200_set_graphs(int mode);
 /* 1: bracket every kernel launch of a solve with CUDA events (per-kernel durations in lcgb200_info); costs a
  * little throughput, so bench.py uses it only for its roofline pass */
 void lcgb200_set_profile(int on);

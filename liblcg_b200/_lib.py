@@ -89,6 +89,8 @@ SYMBOLS = {
     "lcgb200_set_poll_interval": (None, [_I]),
     "lcgb200_set_profile": (None, [_I]),
     "lcgb200_set_fused_small": (None, [_I]),
+    "lcgb200_set_spin_timeout_ms": (None, [_LL]),
+    "lcgb200_set_graphs": (None, [_I]),
     "lcgb200_last_error": (C.c_char_p, []),
     "lcgb200_version": (_I, []),
     "lcgb200_gen_stencil": (_I, [_I, _I, _LL, _LL, _VP, _VP, _VP, _LL, C.POINTER(_LL), _VP]),

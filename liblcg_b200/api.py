@@ -113,6 +113,11 @@ class CsrOperator:
             cx = val.is_complex() or (val.dim() == 2 and val.shape[-1] == 2)
             n = row_ptr.numel() - 1
             nnz = col.numel()
+            # the C ABI takes raw pointers: anything but contiguous CUDA int32 / float64 / complex128 would be reinterpreted silently
+            for name, t, ok in (("row_ptr", row_ptr, ("torch.int32",)), ("col", col, ("torch.int32",)),
+                                ("val", val, ("torch.complex128",) if val.is_complex() else ("torch.float64",))):
+                if not (t.is_cuda and t.is_contiguous() and str(t.dtype) in ok):
+                    raise TypeError(f"CsrOperator: {name} must be a contiguous CUDA tensor of dtype {ok[0]} (got {t.dtype}, cuda={t.is_cuda}, contiguous={t.is_contiguous()})")
         else:
             row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int32)
             col = np.ascontiguousarray(col, dtype=np.int32)

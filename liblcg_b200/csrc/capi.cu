@@ -90,6 +90,16 @@ __global__ void k_diag_cplx(int n, const int* rp, const int* ci, const double2* 
 	d[i] = out;
 }
 
+// *fail = 1 if any column index lies outside [0, n_cols): a bad index would send the gathers of k_spmv (and the host
+// transpose) out of bounds
+__global__ void k_check_cols(long long nnz, const int* __restrict__ ci, int n_cols, int* fail)
+{
+	const long long stride = (long long)gridDim.x * blockDim.x;
+	bool bad = false;
+	for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += stride) bad |= ((unsigned)ci[k] >= (unsigned)n_cols);
+	if (bad) *fail = 1;
+}
+
 template <class T>
 void host_transpose(int n_rows, int n_cols, const int* rp, const int* ci, const T* v, std::vector<int>& trp, std::vector<int>& tci, std::vector<T>& tv)
 {
@@ -334,6 +344,21 @@ void create_typed(CsrHandle* h, const int* row_ptr, const int* col, const T* val
 	if (rp_h[0] != 0 || rp_h[(size_t)h->n_rows] != h->nnz) { set_error_msg("row_ptr[0] must be 0 and row_ptr[n] must equal nnz"); throw ApiFailure{LCGB200_SIZE_NOT_MATCH}; }
 	for (int i = 0; i < h->n_rows; i++) if (rp_h[(size_t)i + 1] < rp_h[(size_t)i]) { set_error_msg("row_ptr must be non-decreasing"); throw ApiFailure{LCGB200_SIZE_NOT_MATCH}; }
 	upload_csr<T>(h->n_rows, h->nnz, rp_h.data(), col, val, dev, &h->row_ptr, &h->col, &h->val, &h->tiles, &h->n_tiles, tile_nnz, &h->lpr, &h->chunk);
+	if (h->nnz > 0)
+	{	// 0 <= col < n_cols, checked over every entry on the device copy before anything gathers through it
+		int* d_fail = dev_alloc<int>(1);
+		int fail = 1;
+		cudaError_t e = cudaMemset(d_fail, 0, sizeof(int));
+		if (e == cudaSuccess)
+		{
+			const int grid = (int)std::min<long long>(((long long)h->nnz + 255) / 256, 148 * 16);
+			k_check_cols<<<grid, 256>>>(h->nnz, h->col, h->n_cols, d_fail);
+			e = cudaMemcpy(&fail, d_fail, sizeof(int), cudaMemcpyDeviceToHost);
+		}
+		cudaFree(d_fail);
+		LCG_CUDA_CHECK(e);
+		if (fail) { set_error_msg("column index outside [0, n_cols)"); throw ApiFailure{LCGB200_SIZE_NOT_MATCH}; }
+	}
 	if (h->flags & LCGB200_CSR_TRANSPOSE)
 	{
 		std::vector<int> ci_h; std::vector<T> v_h;
@@ -505,11 +530,15 @@ int do_solve_real(CsrHandle* h, Operator<double>& A, int solver_id, double* m, c
 	init.n_global = n_global; init.abs_diff = para.abs_diff; init.max_it = para.max_iterations;
 	init.sc[SC_STEP] = para.step;
 	init.ret = RC_UNKNOWN;
-	E.start(init);
 	E.pf = make_pf(d_m);
-	E.sync_each = A.host_side;
+	// user operator callbacks (cuSPARSE-descriptor Ax / Mx or host callbacks): one loop head per host round trip, so that
+	// Afp / Mfp are never invoked after the convergence test has fired (the reference's call pattern)
+	E.sync_each = A.host_side || (bool)A.apply || (bool)A.precond;
+	if (E.comm && E.comm->poisoned()) { set_error_msg("this communicator timed out in an earlier solve: its sequence counters may disagree with the peers'; create a new one"); throw ApiFailure{LCGB200_UNKNOWN_ERROR}; }
+	E.start(init);
 	int ret = solve_real(E, A, solver_id, d_m, d_B, d_lo, d_hi, para, (size_t)n, (size_t)n_ext);
 	const double dev_ms = E.device_ms();
+	if (E.multi() && E.comm->check_abort()) set_error_msg("a cross-GPU wait timed out (a peer rank never arrived): the solve was ended and the communicator is poisoned");
 	if (!m_inplace)
 	{
 		const cudaMemcpyKind out_kind = dev_vecs ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
@@ -547,11 +576,13 @@ int do_solve_cplx(CsrHandle* h, Operator<double2>& A, int solver_id, double2* m,
 	init.eps = para.epsilon; init.n_global = n_global; init.abs_diff = para.abs_diff; init.max_it = para.max_iterations;
 	init.cres_mode = settings().cres_mode;
 	init.ret = RC_UNKNOWN;
-	E.start(init);
 	E.pf = make_pf(d_m);
-	E.sync_each = A.host_side;
+	E.sync_each = A.host_side || (bool)A.apply || (bool)A.precond;
+	if (E.comm && E.comm->poisoned()) { set_error_msg("this communicator timed out in an earlier solve: its sequence counters may disagree with the peers'; create a new one"); throw ApiFailure{LCGB200_UNKNOWN_ERROR}; }
+	E.start(init);
 	int ret = solve_complex(E, A, solver_id, d_m, d_B, para, (size_t)n, (size_t)n_ext);
 	const double dev_ms = E.device_ms();
+	if (E.multi() && E.comm->check_abort()) set_error_msg("a cross-GPU wait timed out (a peer rank never arrived): the solve was ended and the communicator is poisoned");
 	if (!m_inplace)
 	{
 		const cudaMemcpyKind out_kind = dev_vecs ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
@@ -588,6 +619,8 @@ void lcgb200_set_complex_residual_mode(int mode) { settings().cres_mode = mode ?
 void lcgb200_set_poll_interval(int it) { settings().poll = it > 0 ? it : 1; }
 void lcgb200_set_profile(int on) { settings().profile = on ? 1 : 0; }
 void lcgb200_set_fused_small(int on) { settings().fused_small = on ? 1 : 0; }
+void lcgb200_set_spin_timeout_ms(long long ms) { settings().spin_timeout_ms = ms; }
+void lcgb200_set_graphs(int mode) { settings().graphs = mode; }
 
 // sentinels: recognised by address, never executed on the fused path
 void lcgb200_csr_ax(void*, lcgb200_cublas_t, lcgb200_cusparse_t, lcgb200_dnvec_t, lcgb200_dnvec_t, const int, const int) {}
@@ -703,6 +736,14 @@ struct EpiProbeCplx {
 	__device__ void finish(DevState*, const double* tot) const { for (int i = 0; i < 6; i++) out[i] = tot[i]; }
 };
 
+// halo exchange in front of a stand-alone SpMV on a partitioned handle: push half only when k_spmv holds the receive half
+void exchange_for_spmv(CsrHandle* h, const void* x, cudaStream_t s)
+{
+	const int eb = h->value_type == LCGB200_REAL ? 8 : 16;
+	if (h->halo_in_spmv()) h->comm->push(x, eb, s, h->d_state);
+	else h->comm->halo(const_cast<void*>(x), eb, s, h->p2p_dev() != nullptr, h->d_state);
+}
+
 void ensure_state(CsrHandle* h, cudaStream_t s)
 {
 	Engine E(s, h);   // allocates the cached state block on first use
@@ -722,8 +763,7 @@ int lcgb200_csr_spmv(lcgb200_csr_t A, const void* x, void* y, int op, void* stre
 	cudaStream_t s = (cudaStream_t)stream;
 	return guarded([&]() {
 		ensure_state(h, s);
-		if (h->comm && h->comm->size() > 1 && op == 0)
-			h->comm->halo(const_cast<void*>(x), h->value_type == LCGB200_REAL ? 8 : 16, s, h->p2p_dev() != nullptr, h->d_state);
+		if (h->comm && h->comm->size() > 1 && op == 0) exchange_for_spmv(h, x, s);
 		if (h->value_type == LCGB200_REAL)
 		{
 			if (op == 0) launch_spmv<double, false>(h->view<double>(), (const double*)x, (double*)y, EpiNone<double>{}, h->d_state, h->d_partials, s);
@@ -747,8 +787,7 @@ int lcgb200_csr_spmv_dot(lcgb200_csr_t A, const void* x, void* y, const void* w,
 	cudaStream_t s = (cudaStream_t)stream;
 	return guarded([&]() {
 		ensure_state(h, s);
-		if (h->comm && h->comm->size() > 1)
-			h->comm->halo(const_cast<void*>(x), h->value_type == LCGB200_REAL ? 8 : 16, s, h->p2p_dev() != nullptr, h->d_state);
+		if (h->comm && h->comm->size() > 1) exchange_for_spmv(h, x, s);
 		if (h->value_type == LCGB200_REAL)
 			launch_spmv<double, false>(h->view<double>(), (const double*)x, (double*)y, EpiProbeReal{(const double*)w, dots_dev}, h->d_state, h->d_partials, s);
 		else

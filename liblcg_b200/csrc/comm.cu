@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) k_halo_exchange(CommDev* c, T* __restrict
 		}
 		bool ok = true;
 		for (int p = 0; p < c->n_peers && ok; p++)
-			if (c->recv_count[p] > 0) ok = spin_until(&c->win[c->rank]->halo_flag[c->peer_rank[p]], seq);
+			if (c->recv_count[p] > 0) ok = spin_until(&c->win[c->rank]->halo_flag[c->peer_rank[p]], seq, st->spin_timeout_ns);
 		if (!ok) { st->ret = RC_UNKNOWN; st->done = 1; c->abort_flag = 1; }
 		s_flag = ok ? 1 : 0;
 	}
@@ -126,6 +126,56 @@ __global__ void __launch_bounds__(256) k_halo_exchange(CommDev* c, T* __restrict
 	// the block that leaves last publishes the new sequence number for the next exchange
 	__syncthreads();
 	if (threadIdx.x == 0 && atomicAdd(&c->ticket2, 1u) == gridDim.x - 1) { c->halo_seq = seq; c->ticket = 0u; c->ticket2 = 0u; }
+}
+
+// NVLink transport, push half only (the receive half lives in k_spmv: boundary tiles wait for the flags and read the
+// mailbox in place).  Used when the SpMV input was not produced by one of our pushing kernels: the first SpMV of a solve
+// (the caller's m), stand-alone lcgb200_csr_spmv, send lists that are not runs of consecutive rows.  Before overwriting
+// mailbox buffer (seq & 1) the sender waits until every receiver has acknowledged exchange seq - 2 — inside the solvers
+// that is already implied by the reductions between two exchanges; back-to-back stand-alone SpMVs need it.
+template <class T>
+__global__ void __launch_bounds__(256) k_halo_push(CommDev* c, const T* __restrict__ x, DevState* st)
+{
+	if (st_done(st)) return;
+	const unsigned long long seq = c->halo_seq + 1;
+	__shared__ int s_ok;
+	if (threadIdx.x == 0)
+	{
+		bool ok = true;
+		if (seq > 2)
+			for (int p = 0; p < c->n_peers && ok; p++)
+				if (c->send_count[p] > 0) ok = spin_until(&c->win[c->rank]->halo_ack[c->peer_rank[p]], seq - 2, st->spin_timeout_ns);
+		if (!ok) { st->ret = RC_UNKNOWN; st->done = 1; c->abort_flag = 1; }
+		s_ok = ok ? 1 : 0;
+	}
+	__syncthreads();
+	bool pushed = false;
+	if (s_ok)
+	{
+		const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+		for (int p = 0; p < c->n_peers; p++)
+		{
+			const int cnt = c->send_count[p];
+			if (cnt <= 0) continue;
+			T* dst = mailbox_of<T>(c->win[c->peer_rank[p]], seq, c->remote_ghost[p]) + c->remote_off[p];
+			const int first = c->send_first[p], off = c->send_off[p];
+			const bool contig = c->contiguous[p] != 0;
+			for (int i = gtid; i < cnt; i += gsz) { dst[i] = contig ? x[first + i] : x[c->send_idx[off + i]]; pushed = true; }
+		}
+	}
+	push_signal(c, seq, pushed);
+}
+
+// flag[tile] = 1 if any entry of the tile's rows references a ghost column (>= n_local); one warp per tile
+__global__ void k_tile_boundary(int n_tiles, const int4* __restrict__ tiles, const int* __restrict__ row_ptr, const int* __restrict__ col, int n_local, int* flag)
+{
+	const int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	if (tile >= n_tiles) return;
+	const int4 td = tiles[tile];
+	bool hit = false;
+	for (int k = row_ptr[td.x] + lane; k < td.w && !hit; k += 32) hit = col[k] >= n_local;
+	hit = __any_sync(0xffffffffu, hit);
+	if (lane == 0) flag[tile] = hit ? 1 : 0;
 }
 
 // send_buf[i] = x[idx[i]] for the entries that are not sent in place
@@ -156,6 +206,26 @@ public:
 	int push_grid = 1;
 
 	CommDev* dev() override { return p2p_ready ? d_dev : nullptr; }
+	bool fused_push_ok() const override { return p2p_ready && h_dev.all_contiguous != 0; }
+	void push(const void* x, int elem_bytes, cudaStream_t s, DevState* st) override
+	{
+		if (peers.empty()) return;
+		if (elem_bytes == 8) k_halo_push<double><<<push_grid, 256, 0, s>>>(d_dev, (const double*)x, st);
+		else k_halo_push<double2><<<push_grid, 256, 0, s>>>(d_dev, (const double2*)x, st);
+		halos++;
+	}
+	// after a solve on the NVLink transport: did a cross-GPU wait time out?  A timed-out communicator is poisoned — its
+	// sequence counters and mailboxes can no longer be trusted to agree with the peers'.
+	bool poisoned_ = false;
+	bool poisoned() const override { return poisoned_; }
+	bool check_abort() override
+	{
+		if (!p2p_ready || !d_dev) return false;
+		unsigned int flag = 0;
+		if (cudaMemcpy(&flag, reinterpret_cast<const char*>(d_dev) + offsetof(CommDev, abort_flag), sizeof(flag), cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+		if (flag) poisoned_ = true;
+		return flag != 0;
+	}
 
 	~NcclComm() override
 	{
@@ -176,9 +246,10 @@ public:
 	void halo(void* x_ext, int elem_bytes, cudaStream_t s, bool p2p, DevState* st) override
 	{
 		if (peers.empty()) return;
-		if (p2p && p2p_ready && elem_bytes == 8)
+		if (p2p && p2p_ready)
 		{
-			k_halo_exchange<double><<<push_grid, 256, 0, s>>>(d_dev, (double*)x_ext, st);
+			if (elem_bytes == 8) k_halo_exchange<double><<<push_grid, 256, 0, s>>>(d_dev, (double*)x_ext, st);
+			else k_halo_exchange<double2><<<push_grid, 256, 0, s>>>(d_dev, (double2*)x_ext, st);
 			halos++;
 			return;
 		}
@@ -335,8 +406,44 @@ int lcgb200_csr_set_partition(lcgb200_csr_t A, lcgb200_comm_t comm, long long n_
 				max_send = std::max(max_send, pe.send_count);
 			}
 			c->push_grid = std::max(1, std::min(64, (std::max(max_send, c->n_ghost) + 1023) / 1024));
+			// fused push: every send list one run of consecutive rows; [gap_lo, gap_hi) = the largest run of local indices
+			// that nobody needs (interior of a z-slab), so that the pushing kernels test two bounds per access
+			d.all_contiguous = 1;
+			std::vector<std::pair<int, int>> runs;
+			for (const NcclComm::Peer& pe : c->peers)
+			{
+				if (pe.send_count > 0 && !pe.contiguous) d.all_contiguous = 0;
+				if (pe.send_count > 0) runs.emplace_back(pe.send_first, pe.send_first + pe.send_count);
+			}
+			std::sort(runs.begin(), runs.end());
+			int best_lo = 0, best_hi = 0, cur = 0;
+			for (const auto& r : runs) { if (r.first - cur > best_hi - best_lo) { best_lo = cur; best_hi = r.first; } cur = std::max(cur, r.second); }
+			if (h->n_rows - cur > best_hi - best_lo) { best_lo = cur; best_hi = h->n_rows; }
+			d.gap_lo = best_lo; d.gap_hi = best_hi;
 			LCG_CUDA_CHECK(cudaDeviceSynchronize());
 		}
+		// interior / boundary split of the SpMV tiles: boundary tiles (rows that reference ghost columns) go to the end of the
+		// tile list, so that k_spmv starts on interior rows while the neighbours' halo entries are still in flight
+		h->n_interior = -1;
+		if (h->n_tiles > 0 && c->n_ghost > 0)
+		{
+			int* d_flag = nullptr;
+			LCG_CUDA_CHECK(cudaMalloc((void**)&d_flag, sizeof(int) * (size_t)h->n_tiles));
+			k_tile_boundary<<<(h->n_tiles * 32 + 255) / 256, 256>>>(h->n_tiles, h->tiles, h->row_ptr, h->col, h->n_rows, d_flag);
+			std::vector<int> flag((size_t)h->n_tiles);
+			std::vector<int4> tiles((size_t)h->n_tiles), sorted;
+			cudaError_t e1 = cudaMemcpy(flag.data(), d_flag, sizeof(int) * flag.size(), cudaMemcpyDeviceToHost);
+			cudaError_t e2 = cudaMemcpy(tiles.data(), h->tiles, sizeof(int4) * tiles.size(), cudaMemcpyDeviceToHost);
+			cudaFree(d_flag);
+			LCG_CUDA_CHECK(e1); LCG_CUDA_CHECK(e2);
+			sorted.reserve(tiles.size());
+			for (size_t t = 0; t < tiles.size(); t++) if (!flag[t]) sorted.push_back(tiles[t]);
+			const int n_int = (int)sorted.size();
+			for (size_t t = 0; t < tiles.size(); t++) if (flag[t]) sorted.push_back(tiles[t]);
+			LCG_CUDA_CHECK(cudaMemcpy(h->tiles, sorted.data(), sizeof(int4) * sorted.size(), cudaMemcpyHostToDevice));
+			h->n_interior = n_int;
+		}
+		else if (h->n_tiles > 0) h->n_interior = h->n_tiles;
 		return 0;
 	});
 }

@@ -64,7 +64,7 @@ struct CommWindow {
 	unsigned long long ar_flag[kArSlots][kMaxRanks];
 	double ar_val[kArSlots][kMaxRanks][kMaxRed];
 	unsigned long long halo_flag[kMaxRanks];     // [source rank]: sequence number of the last halo it pushed to me
-	unsigned long long pad[8];
+	unsigned long long halo_ack[kMaxRanks];      // [receiving rank]: sequence number of the last halo of MINE it has consumed
 	// mailbox: 2 buffers x n_ghost x 16 bytes follow (offset kMailboxOffset)
 };
 constexpr size_t kMailboxOffset = (sizeof(CommWindow) + 255) & ~size_t(255);
@@ -78,7 +78,17 @@ struct CommDev {	// device-resident, private to the rank
 	long long remote_off[kMaxRanks];             // where my entries start inside the peer's ghost region
 	long long remote_ghost[kMaxRanks];           // the peer's n_ghost (size of one of its mailbox buffers)
 	const int* send_idx;                         // packed (non-contiguous) send indices
+	// fused push (the kernel that WRITES an SpMV input stores the entries its neighbours need straight into their
+	// mailboxes): possible when every send list is one run of consecutive rows (z-slabs of a stencil, banded matrices);
+	// local indices in [gap_lo, gap_hi) are sent to nobody
+	int all_contiguous, gap_lo, gap_hi, pad1;
 };
+
+// mailbox buffer `buf` of window w, as elements of type T
+template <class T> __device__ __forceinline__ T* mailbox_of(CommWindow* w, unsigned long long buf, long long n_ghost)
+{
+	return reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(w) + kMailboxOffset) + (size_t)(buf & 1ull) * (size_t)n_ghost;
+}
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
 {
@@ -102,16 +112,17 @@ __device__ __forceinline__ unsigned long long global_ns()
 	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
 	return t;
 }
-constexpr unsigned long long kSpinTimeoutNs = 4000000000ull;   // a peer that never shows up ends the solve with an error, not a hang
-// spin until *flag >= want; false on timeout
-__device__ __forceinline__ bool spin_until(const unsigned long long* flag, unsigned long long want)
+// spin until *flag >= want; false after timeout_ns (0 = wait for ever).  The timeout is a per-solve setting carried in
+// DevState::spin_timeout_ns (lcgb200_set_spin_timeout_ms / LCGB200_SPIN_TIMEOUT_MS; longer when the host is in the loop):
+// a peer that never shows up ends the solve with an error instead of a hang, and the communicator is then poisoned.
+__device__ __forceinline__ bool spin_until(const unsigned long long* flag, unsigned long long want, unsigned long long timeout_ns)
 {
 	if (ld_acquire_sys(flag) >= want) return true;
 	const unsigned long long t0 = global_ns();
 	while (ld_acquire_sys(flag) < want)
 	{
 		__nanosleep(64);
-		if (global_ns() - t0 > kSpinTimeoutNs) return false;
+		if (timeout_ns && global_ns() - t0 > timeout_ns) return false;
 	}
 	return true;
 }
@@ -132,6 +143,7 @@ struct DevState {
 	unsigned int ticket;
 	unsigned int pad;
 	CommDev* comm;            // multi == 2: NVLink peer-memory transport
+	unsigned long long spin_timeout_ns;   // cross-GPU waits give up after this long (0 = never)
 };
 
 // multi-GPU: the cross-rank sum of a fused reduction, called by the whole first warp of the last block (grid_reduce).
@@ -158,7 +170,7 @@ __device__ __forceinline__ bool reduce_across_ranks(DevState* st, double* tot, i
 	if (lane < c->size) st_relaxed_sys(&c->win[lane]->ar_flag[slot][c->rank], seq);
 	CommWindow* w = c->win[c->rank];
 	bool ok = true;
-	if (lane < c->size) ok = spin_until(&w->ar_flag[slot][lane], seq);
+	if (lane < c->size) ok = spin_until(&w->ar_flag[slot][lane], seq, st->spin_timeout_ns);
 	ok = __all_sync(0xffffffffu, ok);
 	if (lane != 0) return false;
 	c->ar_seq = seq;
@@ -350,6 +362,52 @@ __device__ __forceinline__ bool grid_reduce(const double* acc, double* partials,
 	return true;
 }
 
+// ---- fused halo push (multi-GPU, NVLink transport) -----------------------------------------------------------
+// Called by the thread that has just written src[i .. i+V): the entries that fall into a neighbour's send range go
+// straight into that neighbour's mailbox (remote stores over NVLink).  Returns true if anything was pushed.
+template <class T, int V>
+__device__ __forceinline__ bool push_elems(const CommDev* c, const T* src, size_t i, unsigned long long seq)
+{
+	if ((long long)i >= c->gap_lo && (long long)(i + V) <= c->gap_hi) return false;
+	bool pushed = false;
+	for (int p = 0; p < c->n_peers; p++)
+	{
+		const long long first = c->send_first[p], cnt = c->send_count[p];
+#pragma unroll
+		for (int k = 0; k < V; k++)
+		{
+			const long long e = (long long)i + k - first;
+			if (e >= 0 && e < cnt)
+			{
+				T* dst = mailbox_of<T>(c->win[c->peer_rank[p]], seq, c->remote_ghost[p]) + c->remote_off[p];
+				dst[e] = src[i + k];
+				pushed = true;
+			}
+		}
+	}
+	return pushed;
+}
+
+// End of a pushing kernel: every block fences and takes a ticket; the last one bumps my sequence flag in the
+// neighbours' windows and publishes the new halo_seq for the consumer (the next SpMV on this stream).
+__device__ __forceinline__ void push_signal(CommDev* c, unsigned long long seq, bool pushed)
+{
+	if (pushed) __threadfence_system();
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		__threadfence();
+		if (atomicAdd(&c->ticket, 1u) == gridDim.x - 1)
+		{
+			__threadfence_system();
+			for (int p = 0; p < c->n_peers; p++)
+				if (c->send_count[p] > 0) st_relaxed_sys(&c->win[c->peer_rank[p]]->halo_flag[c->rank], seq);
+			c->halo_seq = seq;
+			c->ticket = 0u;
+		}
+	}
+}
+
 struct OpBase {
 	__device__ __forceinline__ bool active(const DevState*) const { return true; }
 	__device__ __forceinline__ void begin(const DevState*) {}
@@ -364,8 +422,10 @@ struct OpBase {
 //   __device__ bool active(const DevState*);                      false -> the whole kernel is a no-op (OpBase: true)
 //   template<int V> __device__ void elem(size_t i, double* acc);  process V elements starting at i
 //   __device__ void finish(DevState*, const double* tot);         scalar epilogue (one thread of the grid)
-template <class Op>
-__global__ void __launch_bounds__(kThreads) k_vec(Op op_in, size_t n, DevState* st, double* partials)
+// PUSH (multi-GPU, NVLink transport): `push_src` is the vector this kernel produces and the next SpMV consumes; its
+// boundary entries are pushed to the neighbours as they are written (T = element type of that vector).
+template <class Op, bool PUSH = false, class T = double>
+__global__ void __launch_bounds__(kThreads) k_vec(Op op_in, size_t n, DevState* st, double* partials, CommDev* comm = nullptr, const T* push_src = nullptr)
 {
 	if (st_done(st)) return;
 	Op op = op_in;
@@ -377,12 +437,23 @@ __global__ void __launch_bounds__(kThreads) k_vec(Op op_in, size_t n, DevState* 
 	constexpr int W = Op::W;
 	const size_t npack = n / W;
 	const size_t stride = (size_t)gridDim.x * kThreads;
-	for (size_t p = (size_t)blockIdx.x * kThreads + threadIdx.x; p < npack; p += stride) op.template elem<W>(p * W, acc);
+	unsigned long long hseq = 0; bool pushed = false;
+	if (PUSH) hseq = comm->halo_seq + 1;
+	for (size_t p = (size_t)blockIdx.x * kThreads + threadIdx.x; p < npack; p += stride)
+	{
+		op.template elem<W>(p * W, acc);
+		if (PUSH) pushed |= push_elems<T, W>(comm, push_src, p * W, hseq);
+	}
 	if (W > 1)
 	{
 		const size_t tail = npack * W + (size_t)blockIdx.x * kThreads + threadIdx.x;
-		if (tail < n) op.template elem<1>(tail, acc);
+		if (tail < n)
+		{
+			op.template elem<1>(tail, acc);
+			if (PUSH) pushed |= push_elems<T, 1>(comm, push_src, tail, hseq);
+		}
 	}
+	if (PUSH) push_signal(comm, hseq, pushed);
 	if (Op::NRED > 0)
 	{
 		double tot[Op::NRED > 0 ? Op::NRED : 1];

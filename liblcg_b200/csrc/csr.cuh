@@ -48,6 +48,9 @@ constexpr int kSpmvCtasPerSm = LCG_CTAS;
 template <class T>
 struct CsrDev {
 	int n_rows = 0, n_cols = 0, nnz = 0, n_tiles = 0, lpr = 1, chunk = 1;
+	// row block of a partitioned system on the NVLink transport: tiles [n_interior, n_tiles) reference ghost columns
+	// (>= n_rows) and are read from the halo mailbox once the neighbours' pushes have landed; -1 = not in use
+	int n_interior = -1;
 	const int* row_ptr = nullptr;
 	const int* col = nullptr;
 	const T* val = nullptr;
@@ -138,12 +141,77 @@ __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;"
 
 int spmv_grid_limit(int ctas_per_sm);   // resident CTAs of k_spmv on the current device (SMs x CTAs per SM), engine.cu
 
+// cudaFuncSetAttribute applies to ONE device: remember per (kernel instantiation, device) whether the dynamic shared-memory
+// limit has been raised (a process may drive several GPUs)
+struct PerDeviceOnce {
+	bool done[64] = {false};
+	bool first()
+	{
+		int dev = 0;
+		if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+		if (done[dev]) return false;
+		done[dev] = true;
+		return true;
+	}
+};
+
+// One staged tile: LPR lanes per row walk the rows out of shared memory and gather x.  GHOST: columns >= n_local are
+// ghost entries and are read in place from the halo mailbox (`ghost` is biased by -n_local, so it is indexed by the column).
+template <class T, int LPR, bool CONJ, bool GHOST, class Epi>
+__device__ __forceinline__ void spmv_tile_rows(const T* __restrict__ sval, const int* __restrict__ scol, const int* __restrict__ srow,
+	int r0, int nrows, int k0, const T* __restrict__ x, const T* ghost, int n_local, T* __restrict__ y, Epi& epi, double* acc, int group, int lane)
+{
+	constexpr int NG = kThreads / LPR;          // row groups per block
+	for (int rb = 0; rb < nrows; rb += NG)
+	{
+		const int r = rb + group;
+		int kb = 0, ke = 0;
+		if (r < nrows) { kb = srow[r] - k0; ke = srow[r + 1] - k0; }
+		T sum = tzero(T());
+		// kGatherUnroll entries per lane at a time, all their loads issued before the first use: the row walk
+		// is bound by the latency of the gathered x (L2 for most stencil neighbours), not by issue slots
+		for (int j0 = kb + lane; j0 < ke; j0 += LPR * kGatherUnroll)
+		{
+			int cidx[kGatherUnroll]; T a[kGatherUnroll], xv[kGatherUnroll];
+#pragma unroll
+			for (int u = 0; u < kGatherUnroll; u++)
+			{
+				const int j = j0 + u * LPR;
+				const bool ok = j < ke;
+				cidx[u] = ok ? scol[j] : -1;
+				a[u] = ok ? sval[j] : tzero(T());
+			}
+#pragma unroll
+			for (int u = 0; u < kGatherUnroll; u++)
+			{
+				if (GHOST) xv[u] = cidx[u] >= 0 ? tldg((cidx[u] >= n_local ? ghost : x) + cidx[u]) : tzero(T());
+				else xv[u] = cidx[u] >= 0 ? tldg(x + cidx[u]) : tzero(T());
+			}
+#pragma unroll
+			for (int u = 0; u < kGatherUnroll; u++)
+			{
+				if (CONJ) a[u] = tconj(a[u]);
+				sum = mulacc(sum, a[u], xv[u]);
+			}
+		}
+#pragma unroll
+		for (int o = LPR / 2; o > 0; o >>= 1) sum = tadd(sum, tshfl_xor(sum, o));
+		if (lane == 0 && r < nrows)
+		{
+			y[r0 + r] = sum;
+			epi.row(r0 + r, sum, tldg(x + r0 + r), acc);
+		}
+	}
+}
+
 // Epi interface:
 //   static constexpr int NRED;
 //   __device__ void begin(const DevState*);
 //   __device__ void row(int i, T yi, T xi, double* acc);   called once per row by one lane (may write vectors)
 //   __device__ void finish(DevState*, const double* tot);
-template <class T, int LPR, bool CONJ, class Epi>
+// PART: row block of a partitioned system on the NVLink transport (receive half of the halo exchange in the boundary
+// tiles); a separate instantiation, so that the single-GPU kernel carries none of it.
+template <class T, int LPR, bool CONJ, class Epi, bool PART = false>
 __global__ void __launch_bounds__(kSpmvThreads, TileCfg<T>::CTAS) k_spmv(CsrDev<T> A, const T* __restrict__ x, T* __restrict__ y, Epi epi_in,
 	DevState* st, double* partials)
 {
@@ -205,8 +273,11 @@ __global__ void __launch_bounds__(kSpmvThreads, TileCfg<T>::CTAS) k_spmv(CsrDev<
 	else
 	{
 		epi.begin(st);
-		constexpr int NG = kThreads / LPR;          // row groups per block
 		const int group = tid / LPR, lane = tid % LPR;
+		// partitioned row block (NVLink transport): interior tiles start at once, the first boundary tile of this warp waits
+		// until every neighbour's push for this exchange has landed in my mailbox
+		const bool partitioned = PART && A.n_interior >= 0;
+		const T* ghost = nullptr; bool ghost_ready = false;
 		int idx = 0;
 		for (int c = blockIdx.x; c < n_chunks; c += gridDim.x)
 		{
@@ -215,13 +286,27 @@ __global__ void __launch_bounds__(kSpmvThreads, TileCfg<T>::CTAS) k_spmv(CsrDev<
 			{
 				const int4 td = __ldg(A.tiles + tile);
 				const int r0 = td.x, nrows = td.y - td.x, k0 = td.z, k1 = td.w;
+				const bool boundary = partitioned && tile >= A.n_interior;
+				if (boundary && !ghost_ready)
+				{
+					CommDev* cd = st->comm;
+					const unsigned long long hseq = cd->halo_seq;
+					bool ok = true;
+					if ((tid & 31) < cd->n_peers && cd->recv_count[tid & 31] > 0)
+						ok = spin_until(&cd->win[cd->rank]->halo_flag[cd->peer_rank[tid & 31]], hseq, st->spin_timeout_ns);
+					ok = __all_sync(0xffffffffu, ok);
+					if (!ok && (tid & 31) == 0) { st->ret = RC_UNKNOWN; st->done = 1; cd->abort_flag = 1; }
+					ghost = mailbox_of<T>(cd->win[cd->rank], hseq, cd->n_ghost) - cd->n_local;
+					ghost_ready = true;
+				}
 				if (k1 - k0 > TN)
 				{	// one row longer than a stage: stream it straight from global memory
 					T part = tzero(T());
 					for (int k = A.row_ptr[r0] + tid; k < k1; k += kThreads)
 					{
 						T a = A.val[k]; if (CONJ) a = tconj(a);
-						part = mulacc(part, a, tldg(x + A.col[k]));
+						const int cc = A.col[k];
+						part = mulacc(part, a, tldg((boundary && cc >= A.n_rows ? ghost : x) + cc));
 					}
 #pragma unroll
 					for (int o = 16; o > 0; o >>= 1) part = tadd(part, tshfl_xor(part, o));
@@ -243,45 +328,26 @@ __global__ void __launch_bounds__(kSpmvThreads, TileCfg<T>::CTAS) k_spmv(CsrDev<
 				const T* sval = reinterpret_cast<const T*>(base + SC::VAL_OFF);
 				const int* scol = reinterpret_cast<const int*>(base + SC::COL_OFF);
 				const int* srow = reinterpret_cast<const int*>(base + SC::ROW_OFF) + (r0 & 3);
-				for (int rb = 0; rb < nrows; rb += NG)
-				{
-					const int r = rb + group;
-					int kb = 0, ke = 0;
-					if (r < nrows) { kb = srow[r] - k0; ke = srow[r + 1] - k0; }
-					T sum = tzero(T());
-					// kGatherUnroll entries per lane at a time, all their loads issued before the first use: the row walk
-					// is bound by the latency of the gathered x (L2 for most stencil neighbours), not by issue slots
-					for (int j0 = kb + lane; j0 < ke; j0 += LPR * kGatherUnroll)
-					{
-						int cidx[kGatherUnroll]; T a[kGatherUnroll], xv[kGatherUnroll];
-#pragma unroll
-						for (int u = 0; u < kGatherUnroll; u++)
-						{
-							const int j = j0 + u * LPR;
-							const bool ok = j < ke;
-							cidx[u] = ok ? scol[j] : -1;
-							a[u] = ok ? sval[j] : tzero(T());
-						}
-#pragma unroll
-						for (int u = 0; u < kGatherUnroll; u++) xv[u] = cidx[u] >= 0 ? tldg(x + cidx[u]) : tzero(T());
-#pragma unroll
-						for (int u = 0; u < kGatherUnroll; u++)
-						{
-							if (CONJ) a[u] = tconj(a[u]);
-							sum = mulacc(sum, a[u], xv[u]);
-						}
-					}
-#pragma unroll
-					for (int o = LPR / 2; o > 0; o >>= 1) sum = tadd(sum, tshfl_xor(sum, o));
-					if (lane == 0 && r < nrows)
-					{
-						y[r0 + r] = sum;
-						epi.row(r0 + r, sum, tldg(x + r0 + r), acc);
-					}
-				}
+				if (boundary) spmv_tile_rows<T, LPR, CONJ, true, Epi>(sval, scol, srow, r0, nrows, k0, x, ghost, A.n_rows, y, epi, acc, group, lane);
+				else spmv_tile_rows<T, LPR, CONJ, false, Epi>(sval, scol, srow, r0, nrows, k0, x, nullptr, 0, y, epi, acc, group, lane);
 				__syncwarp();
 				if ((tid & 31) == 0) mbar_arrive(smem_u32(&s_bar[kStages + s]));
 				idx++;
+			}
+		}
+	}
+	if (PART && A.n_interior >= 0)
+	{	// the block that leaves last tells every sender that this exchange's mailbox buffer has been consumed
+		__syncthreads();
+		if (tid == 0)
+		{
+			CommDev* cd = st->comm;
+			if (atomicAdd(&cd->ticket2, 1u) == gridDim.x - 1)
+			{
+				const unsigned long long hseq = cd->halo_seq;
+				for (int p = 0; p < cd->n_peers; p++)
+					if (cd->recv_count[p] > 0) st_relaxed_sys(&cd->win[cd->peer_rank[p]]->halo_ack[cd->rank], hseq);
+				cd->ticket2 = 0u;
 			}
 		}
 	}
@@ -558,8 +624,8 @@ inline void launch_spmv_pat(const CsrDev<double>& A, const double* x, double* y,
 {
 	const size_t smem = (size_t)A.n_pat * A.pat_maxlen * sizeof(PatEntry) + (size_t)A.n_pat * sizeof(int);
 	auto kern = k_spmv_pat<Epi>;
-	static bool configured = false;
-	if (!configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kPatMaxEntries * sizeof(PatEntry) + 1024)); configured = true; }
+	static PerDeviceOnce once;
+	if (once.first()) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kPatMaxEntries * sizeof(PatEntry) + 1024));
 	const int n_chunks = (A.n_rows + kPatChunk - 1) / kPatChunk;
 	const int limit = spmv_grid_limit(4);
 	int grid = n_chunks < limit ? n_chunks : limit;
@@ -593,26 +659,32 @@ struct EpiNone {
 template <class T, int LPR, bool CONJ, class Epi>
 inline void launch_spmv_lpr(const CsrDev<T>& A, const T* x, T* y, const Epi& epi, DevState* st, double* partials, cudaStream_t s)
 {
-	static bool configured = false;   // per instantiation
-	auto kern = k_spmv<T, LPR, CONJ, Epi>;
-	if (!configured)
-	{
-		cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, StageCfg<T>::TOTAL);
-		configured = true;
-	}
 	const int n_chunks = (A.n_tiles + A.chunk - 1) / A.chunk;
 	const int limit = spmv_grid_limit(TileCfg<T>::CTAS);
 	int grid = n_chunks < limit ? n_chunks : limit;
 	if (grid < 1) grid = 1;
-	kern<<<grid, kSpmvThreads, StageCfg<T>::TOTAL, s>>>(A, x, y, epi, st, partials);
+	if (A.n_interior >= 0)
+	{
+		static PerDeviceOnce once;   // per instantiation
+		auto kern = k_spmv<T, LPR, CONJ, Epi, true>;
+		if (once.first()) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, StageCfg<T>::TOTAL);
+		kern<<<grid, kSpmvThreads, StageCfg<T>::TOTAL, s>>>(A, x, y, epi, st, partials);
+	}
+	else
+	{
+		static PerDeviceOnce once;
+		auto kern = k_spmv<T, LPR, CONJ, Epi, false>;
+		if (once.first()) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, StageCfg<T>::TOTAL);
+		kern<<<grid, kSpmvThreads, StageCfg<T>::TOTAL, s>>>(A, x, y, epi, st, partials);
+	}
 }
 
 template <int LPR, class Epi>
 inline void launch_spmv_dict_lpr(const CsrDev<double>& A, const double* x, double* y, const Epi& epi, DevState* st, double* partials, cudaStream_t s)
 {
-	static bool configured = false;
+	static PerDeviceOnce once;
 	auto kern = k_spmv_dict<LPR, Epi>;
-	if (!configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DictStage::TOTAL); configured = true; }
+	if (once.first()) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DictStage::TOTAL);
 	const int n_chunks = (A.n_dtiles + A.dchunk - 1) / A.dchunk;
 	const int limit = spmv_grid_limit(kSpmvCtasPerSm);
 	int grid = n_chunks < limit ? n_chunks : limit;

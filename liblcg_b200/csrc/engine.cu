@@ -19,6 +19,13 @@ const char* last_error() { return g_err.c_str(); }
 
 Settings& settings() { static Settings s; return s; }
 
+long long spin_timeout_ms()
+{
+	if (settings().spin_timeout_ms >= 0) return settings().spin_timeout_ms;
+	static const long long env = [] { const char* e = getenv("LCGB200_SPIN_TIMEOUT_MS"); return e ? atoll(e) : 30000ll; }();
+	return env < 0 ? 30000ll : env;
+}
+
 int spmv_grid_limit(int ctas_per_sm)
 {
 	static int cached[64] = {0};
@@ -146,6 +153,10 @@ void Engine::start(const DevState& init)
 	*h_st = init;
 	h_st->multi = multi() ? (p2p() ? 2 : 1) : 0;
 	h_st->comm = p2p() ? cache->p2p_dev() : nullptr;
+	// a progress callback or a host-side operator puts the host into every iteration: a rank may then legitimately be
+	// seconds late (slow callback, debugger), so the peers wait 20x longer before they give up
+	h_st->spin_timeout_ns = (unsigned long long)spin_timeout_ms() * 1000000ull * ((pf || sync_each) ? 20ull : 1ull);
+	pushed_vec = nullptr;
 	LCG_CUDA_CHECK(cudaMemcpyAsync(d_st, h_st, sizeof(DevState), cudaMemcpyHostToDevice, stream));
 	LCG_CUDA_CHECK(cudaEventRecord(ev[2], stream));
 	seen_checks = 0;
@@ -197,6 +208,24 @@ bool Engine::sync_point()
 	return sync_always();
 }
 
+namespace {
+struct GraphGuard {
+	cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+	void reset() { if (exec) cudaGraphExecDestroy(exec); if (graph) cudaGraphDestroy(graph); exec = nullptr; graph = nullptr; }
+	~GraphGuard() { reset(); }
+};
+// graphs pay when launch gaps are a visible share of an iteration: up to ~8 M local rows (an iteration of a few hundred
+// microseconds); lcgb200_set_graphs / LCGB200_GRAPHS = 0 | 1 overrides
+bool use_graphs(size_t n_local)
+{
+	int mode = settings().graphs;
+	if (mode < 0) { static const int env = [] { const char* e = getenv("LCGB200_GRAPHS"); return e ? atoi(e) : -1; }(); mode = env; }
+	if (mode == 0) return false;
+	if (mode > 0) return true;
+	return n_local <= (size_t)8 << 20;
+}
+}  // namespace
+
 int Engine::run(const std::function<bool()>& iterate, const std::function<void(int)>& batch)
 {
 	if (pf || sync_each)
@@ -206,6 +235,7 @@ int Engine::run(const std::function<bool()>& iterate, const std::function<void(i
 			if (sync_always()) break;
 			if (batch) batch(1);
 			else if (iterate()) break;
+			LCG_CUDA_CHECK(cudaPeekAtLastError());
 		}
 		LCG_CUDA_CHECK(cudaStreamSynchronize(stream));
 		return final_ret;
@@ -222,12 +252,47 @@ int Engine::run(const std::function<bool()>& iterate, const std::function<void(i
 	LCG_CUDA_CHECK(cudaEventRecord(ev[b], stream));
 	pending[b] = true;
 	b ^= 1;
+	// CUDA graph of one batch: every kernel argument of an iteration is a constant of the solve (the scalars live in
+	// DevState), so the second batch is captured once and replayed — kernel-to-kernel gaps shrink to the graph's
+	// pre-resolved dependencies, which matters when an iteration lasts tens of microseconds (mid-size systems, the
+	// per-GPU slabs of a partitioned solve).  The first batch runs uncaptured so that one-time launch set-up is done.
+	GraphGuard gg;
+	const bool want_graph = !batch && capturable && !profiling && (!multi() || p2p()) && use_graphs(n_local);
+	int batches = 0, per_batch_launches = 0, per_batch_spmv = 0;
 	while (true)
 	{
 		bool ended = false;
 		if (batch) batch(poll);
+		else if (gg.exec)
+		{
+			LCG_CUDA_CHECK(cudaGraphLaunch(gg.exec, stream));
+			launches += per_batch_launches; spmv_launches += per_batch_spmv;
+		}
+		else if (want_graph && batches == 1)
+		{
+			const int l0 = launches, s0 = spmv_launches;
+			LCG_CUDA_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+			for (int i = 0; i < poll; i++) iterate();
+			cudaError_t ce = cudaStreamEndCapture(stream, &gg.graph);
+			if (ce == cudaSuccess && gg.graph) ce = cudaGraphInstantiate(&gg.exec, gg.graph, 0);
+			if (ce != cudaSuccess || !gg.exec)
+			{	// capture refused (e.g. a user stream in a state that forbids it): forget it and carry on with plain launches
+				(void)cudaGetLastError();
+				gg.reset();
+				launches = l0; spmv_launches = s0;
+				for (int i = 0; i < poll && !ended; i++) ended = iterate();
+				batches = 2;   // do not try again
+			}
+			else
+			{
+				per_batch_launches = launches - l0; per_batch_spmv = spmv_launches - s0;
+				LCG_CUDA_CHECK(cudaGraphLaunch(gg.exec, stream));
+			}
+		}
 		else for (int i = 0; i < poll && !ended; i++) ended = iterate();
+		batches++;
 		if (ended) break;   // a host-driven step (SPG) saw the end itself
+		LCG_CUDA_CHECK(cudaPeekAtLastError());   // a launch that failed would never set `done`
 		LCG_CUDA_CHECK(cudaMemcpyAsync(slot[b], d_st, sizeof(DevState), cudaMemcpyDeviceToHost, stream));
 		LCG_CUDA_CHECK(cudaEventRecord(ev[b], stream));
 		pending[b] = true;

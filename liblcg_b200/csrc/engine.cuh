@@ -6,6 +6,7 @@
 #include <vector>
 #include <map>
 #include <chrono>
+#include <cstdlib>
 #include "common.cuh"
 #include "csr.cuh"
 #include "fused_small.cuh"
@@ -24,6 +25,14 @@ struct Comm {
 	virtual void halo(void* x_ext, int elem_bytes, cudaStream_t s, bool p2p, DevState* st) = 0;
 	// device state of the NVLink peer-memory transport, or null when only NCCL is available
 	virtual CommDev* dev() { return nullptr; }
+	// NVLink transport, push half only: my boundary entries of x go into the neighbours' mailboxes (the receive half is in
+	// k_spmv's boundary tiles)
+	virtual void push(const void* x, int elem_bytes, cudaStream_t s, DevState* st) = 0;
+	// every send list is a run of consecutive rows: the kernels that write SpMV inputs can push while they write
+	virtual bool fused_push_ok() const { return false; }
+	// a cross-GPU wait of an earlier solve timed out: the transport state is out of step with the peers
+	virtual bool poisoned() const { return false; }
+	virtual bool check_abort() { return false; }
 };
 
 // ---- handle behind lcgb200_csr_t ------------------------------------------------------------------------
@@ -36,6 +45,7 @@ struct CsrHandle {
 	// device arrays (owned)
 	int* row_ptr = nullptr; int* col = nullptr; void* val = nullptr; int4* tiles = nullptr;
 	int n_tiles = 0, lpr = 1, chunk = 1;
+	int n_interior = -1;           // partitioned row block: tiles [n_interior, n_tiles) reference ghost columns (set by lcgb200_csr_set_partition)
 	// transpose (optional)
 	int* t_row_ptr = nullptr; int* t_col = nullptr; void* t_val = nullptr; int4* t_tiles = nullptr;
 	int t_n_tiles = 0, t_lpr = 1, t_chunk = 1;
@@ -52,10 +62,15 @@ struct CsrHandle {
 	DevState* d_state = nullptr; DevState* h_state = nullptr; DevState* h_state2 = nullptr; double* d_partials = nullptr;
 	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 
-	CommDev* p2p_dev() const { return (comm && value_type == 0) ? comm->dev() : nullptr; }
+	CommDev* p2p_dev() const { return comm ? comm->dev() : nullptr; }
+	// NVLink transport with the receive half of the halo exchange inside k_spmv (boundary tiles wait for the neighbours'
+	// pushes and read the mailbox in place); the compressed operator copies keep the stand-alone exchange kernel
+	bool halo_in_spmv() const { return comm && comm->size() > 1 && comm->dev() && n_interior >= 0 && !code && !pat && !legacy_halo(); }
+	static bool legacy_halo() { static const bool v = getenv("LCGB200_HALO_LEGACY") != nullptr; return v; }
 	template <class T> CsrDev<T> view() const
 	{
 		CsrDev<T> v; v.n_rows = n_rows; v.n_cols = n_cols; v.nnz = nnz; v.n_tiles = n_tiles; v.lpr = lpr; v.chunk = chunk;
+		v.n_interior = halo_in_spmv() ? n_interior : -1;
 		v.row_ptr = row_ptr; v.col = col; v.val = (const T*)val; v.tiles = tiles;
 		v.code = code; v.vdict = vdict; v.odict = odict; v.dtiles = dtiles; v.n_dtiles = n_dtiles; v.dchunk = dchunk; v.dlpr = dlpr;
 		v.pat = pat; v.pat_len = pat_len; v.pat_ent = pat_ent; v.n_pat = n_pat; v.pat_maxlen = pat_maxlen;
@@ -88,7 +103,10 @@ struct Settings {
 	int poll = 4;
 	int fused_small = 1;           // cache-resident systems: several whole iterations per cooperative launch (fused_small.cuh)
 	int profile = 0;               // 1: bracket every kernel launch with CUDA events (bench roofline pass)
+	long long spin_timeout_ms = -1; // cross-GPU waits (NVLink transport); -1 = LCGB200_SPIN_TIMEOUT_MS or 30 s; 0 = wait for ever
+	int graphs = -1;               // CUDA graph per batch of iterations; -1 = LCGB200_GRAPHS or automatic
 };
+long long spin_timeout_ms();
 Settings& settings();
 
 class Engine {
@@ -110,7 +128,9 @@ public:
 	void prof_end(cudaEvent_t e) { if (e) cudaEventRecord(e, stream); }
 	void prof_collect(double* ms, int* count);   // sums per class (2 entries each); call after a stream sync
 	ProgressFn pf;                 // empty = no progress callback
-	bool sync_each = false;        // one host round trip per loop head even without a progress callback (host-side operator callbacks)
+	bool sync_each = false;        // one host round trip per loop head even without a progress callback (user operator callbacks:
+	                               // the reference never calls Afp / Mfp after convergence, so the host must not run ahead of the test)
+	bool capturable = true;        // the iteration is a fixed list of kernel launches (no host-visible sync point inside): a batch may be a CUDA graph
 	int seen_checks = 0;
 	int final_ret = RC_UNKNOWN;
 	// workspace arena
@@ -144,6 +164,23 @@ public:
 		if (Op::NRED > 0 && multi()) finish_multi(op, Op::NRED);
 	}
 
+	// Same, for a kernel that WRITES `out`, the input of the next SpMV.  On the NVLink transport (row partition whose send
+	// lists are runs of consecutive rows) the kernel pushes the entries the neighbours need into their mailboxes while it
+	// writes them, and the SpMV that follows needs no exchange launch: its interior tiles start at once, its boundary tiles
+	// wait for the neighbours' flags (halo overlapped with the interior rows).
+	const void* pushed_vec = nullptr;   // the vector whose halo the last pushing kernel has already sent
+	bool halo_in_spmv() const { return multi() && cache && cache->halo_in_spmv(); }
+	template <class T, class Op> void vec_push(const Op& op, size_t n, const T* out)
+	{
+		if (!(halo_in_spmv() && comm->fused_push_ok())) { vec(op, n); return; }
+		cudaEvent_t pe = profiling ? prof_begin(1) : nullptr;
+		k_vec<Op, true, T><<<vec_grid(n, Op::W), kThreads, 0, stream>>>(op, n, d_st, d_partials, cache->p2p_dev(), out);
+		prof_end(pe);
+		launches++;
+		pushed_vec = out;
+		if (Op::NRED > 0 && multi()) finish_multi(op, Op::NRED);
+	}
+
 	template <class Op> void finish_multi(const Op& op, int nred)
 	{
 		if (p2p()) return;   // NVLink transport: the producing kernel's last block already summed across the ranks and ran the epilogue
@@ -157,7 +194,15 @@ public:
 	{
 		if (A.h)
 		{
-			if (multi()) comm->halo(x, (int)sizeof(T), stream, p2p(), d_st);
+			if (multi())
+			{
+				if (halo_in_spmv() && op == 0)
+				{	// receive half inside k_spmv; push half only if the producing kernel has not done it already
+					if (pushed_vec != (const void*)x) { comm->push(x, (int)sizeof(T), stream, d_st); launches++; }
+					pushed_vec = nullptr;
+				}
+				else { comm->halo(x, (int)sizeof(T), stream, p2p(), d_st); if (p2p()) launches++; }
+			}
 			cudaEvent_t pe = profiling ? prof_begin(0) : nullptr;
 			if (op == 0) launch_spmv<T, false, Epi>(A.h->template view<T>(), x, y, epi, d_st, d_partials, stream);
 			else if (op == 1) launch_spmv<T, false, Epi>(A.h->template tview<T>(), x, y, epi, d_st, d_partials, stream);

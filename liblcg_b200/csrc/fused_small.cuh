@@ -138,8 +138,11 @@ template <class... Ph>
 inline cudaError_t launch_fused(DevState* st, double* partials, int iters, cudaStream_t s, Ph... ph)
 {
 	auto kern = k_fused<Ph...>;
-	static int limit = 0;   // per instantiation
-	if (!limit) limit = coop_grid_limit((const void*)kern, kThreads);
+	static int limits[64] = {0};   // per instantiation and device
+	int dev = 0;
+	if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+	if (!limits[dev]) limits[dev] = coop_grid_limit((const void*)kern, kThreads);
+	const int limit = limits[dev];
 	int work = 1;
 	int each[] = {ph.rows()...};
 	for (int w : each) work = w > work ? w : work;

@@ -110,13 +110,13 @@ static int run_cg(Engine& E, const Operator<double>& A, double* m, const double*
 {
 	double* g = E.alloc<double>(next); double* d = E.alloc<double>(next); double* Ad = E.alloc<double>(next);
 	E.spmv(A, m, Ad, EpiNone<double>{});
-	E.vec(OpCgInit{{}, m, Ad, B, g, d}, n);
+	E.vec_push(OpCgInit{{}, m, Ad, B, g, d}, n, d);
 	std::function<void(int)> batch;
 	if (E.small_system(A)) batch = [&](int k) { E.fused(k, 1, E.ph_spmv(A, d, Ad, EpiDotAlpha{nullptr}), E.ph_vec(OpCgUpdate{{}, m, d, g, Ad, 0.0}, n), E.ph_vec(OpCgDir{{}, d, g, 0.0}, n)); };
 	return E.run([&]() {
 		E.spmv(A, d, Ad, EpiDotAlpha{nullptr});
 		E.vec(OpCgUpdate{{}, m, d, g, Ad, 0.0}, n);
-		E.vec(OpCgDir{{}, d, g, 0.0}, n);
+		E.vec_push(OpCgDir{{}, d, g, 0.0}, n, d);
 		return false;
 	}, batch);
 }
@@ -236,12 +236,12 @@ static int run_pcg(Engine& E, const Operator<double>& A, double* m, const double
 	double* d = E.alloc<double>(next); double* Ad = E.alloc<double>(next);
 	const bool jac = (A.diag != nullptr);
 	E.spmv(A, m, Ad, EpiNone<double>{});
-	if (jac) E.vec(OpPcgInit<true>{{}, m, Ad, B, A.diag, r, z, d}, n);
+	if (jac) E.vec_push(OpPcgInit<true>{{}, m, Ad, B, A.diag, r, z, d}, n, d);
 	else
 	{
 		E.vec(OpPcgInit<false>{{}, m, Ad, B, nullptr, r, z, d}, n);
 		A.precond(r, z, 0);
-		E.vec(OpPcgInitZ{{}, z, r, d}, n);
+		E.vec_push(OpPcgInitZ{{}, z, r, d}, n, d);
 	}
 	std::function<void(int)> batch;
 	if (jac && E.small_system(A))
@@ -255,7 +255,7 @@ static int run_pcg(Engine& E, const Operator<double>& A, double* m, const double
 			A.precond(r, z, 0);
 			E.vec(OpPcgZr{{}, z, r}, n);
 		}
-		E.vec(OpPcgDir{{}, d, z, 0.0}, n);
+		E.vec_push(OpPcgDir{{}, d, z, 0.0}, n, d);
 		return false;
 	}, batch);
 }
@@ -346,17 +346,17 @@ static int run_cgs(Engine& E, const Operator<double>& A, double* m, const double
 	double* Ax = E.alloc<double>(next); double* u = E.alloc<double>(next); double* q = E.alloc<double>(next);
 	double* w = E.alloc<double>(next);
 	E.spmv(A, m, Ax, EpiNone<double>{});
-	E.vec(OpResInit{{}, m, Ax, B, r, r0, p, u}, n);
+	E.vec_push(OpResInit{{}, m, Ax, B, r, r0, p, u}, n, p);
 	std::function<void(int)> batch;
 	if (E.small_system(A))
 		batch = [&](int k) { E.fused(k, 2, E.ph_spmv(A, p, Ax, EpiDotAlpha{r0}), E.ph_vec(OpCgsQW{{}, u, Ax, q, w, 0.0}, n), E.ph_spmv(A, w, Ax, EpiNone<double>{}),
 			E.ph_vec(OpCgsUpdate{{}, m, w, r, Ax, r0, 0.0}, n), E.ph_vec(OpCgsDir{{}, r, q, u, p, 0.0}, n)); };
 	return E.run([&]() {
 		E.spmv(A, p, Ax, EpiDotAlpha{r0});
-		E.vec(OpCgsQW{{}, u, Ax, q, w, 0.0}, n);
+		E.vec_push(OpCgsQW{{}, u, Ax, q, w, 0.0}, n, w);
 		E.spmv(A, w, Ax, EpiNone<double>{});
 		E.vec(OpCgsUpdate{{}, m, w, r, Ax, r0, 0.0}, n);
-		E.vec(OpCgsDir{{}, r, q, u, p, 0.0}, n);
+		E.vec_push(OpCgsDir{{}, r, q, u, p, 0.0}, n, p);
 		return false;
 	}, batch);
 }
@@ -461,8 +461,9 @@ static int run_bicgstab(Engine& E, const Operator<double>& A, double* m, const d
 	double* r = E.alloc<double>(next); double* r0 = E.alloc<double>(next); double* p = E.alloc<double>(next);
 	double* Ax = E.alloc<double>(next); double* s = E.alloc<double>(next); double* Ap = E.alloc<double>(next);
 	const bool half = RESTART && abs_diff;
+	if (half) E.capturable = false;	// Pfp may be consulted in the middle of the iteration
 	E.spmv(A, m, Ax, EpiNone<double>{});
-	E.vec(OpResInit{{}, m, Ax, B, r, r0, p, nullptr}, n);
+	E.vec_push(OpResInit{{}, m, Ax, B, r, r0, p, nullptr}, n, p);
 	std::function<void(int)> batch;
 	if (!half && E.small_system(A))
 		batch = [&](int k) { E.fused(k, 2, E.ph_spmv(A, p, Ap, EpiDotAlpha{r0}), E.ph_vec(OpBicgS<false>{{}, r, Ap, s, 0.0}, n), E.ph_spmv(A, s, Ax, EpiOmega{}),
@@ -471,14 +472,14 @@ static int run_bicgstab(Engine& E, const Operator<double>& A, double* m, const d
 		E.spmv(A, p, Ap, EpiDotAlpha{r0});
 		if (half)
 		{
-			E.vec(OpBicgS<true>{{}, r, Ap, s, 0.0}, n);
+			E.vec_push(OpBicgS<true>{{}, r, Ap, s, 0.0}, n, s);
 			if (E.sync_point()) return true;	// Pfp sees m before the half update, as in the reference
 			E.vec(OpBicgHalf{{}, m, p, 0.0}, n);
 		}
-		else E.vec(OpBicgS<false>{{}, r, Ap, s, 0.0}, n);
+		else E.vec_push(OpBicgS<false>{{}, r, Ap, s, 0.0}, n, s);
 		E.spmv(A, s, Ax, EpiOmega{});
 		E.vec(OpBicgUpdate<RESTART>{{}, m, p, s, Ax, r, r0, 0.0, 0.0}, n);
-		E.vec(OpBicgDir<RESTART>{{}, r, p, Ap, r0, 0.0, 0.0, 0}, n);
+		E.vec_push(OpBicgDir<RESTART>{{}, r, p, Ap, r0, 0.0, 0.0, 0}, n, p);
 		return false;
 	}, batch);
 }
@@ -562,14 +563,14 @@ struct OpPgUpdate : OpBase {	// g_new = Ad - B, s = m_new - m, y = g_new - g; s.
 static int run_pg(Engine& E, const Operator<double>& A, double* m, const double* B, const double* lo, const double* hi, size_t n, size_t next)
 {
 	double* g = E.alloc<double>(next); double* Ad = E.alloc<double>(next); double* mn = E.alloc<double>(next);
-	E.vec(OpBox{{}, m, lo, hi}, n);
+	E.vec_push(OpBox{{}, m, lo, hi}, n, m);
 	E.spmv(A, m, Ad, EpiNone<double>{});
 	E.vec(OpPgInit<false>{{}, m, Ad, B, g}, n);
 	std::function<void(int)> batch;
 	if (E.small_system(A))
 		batch = [&](int k) { E.fused(k, 1, E.ph_vec(OpPgStep{{}, m, g, lo, hi, mn, 0.0}, n), E.ph_spmv(A, mn, Ad, EpiNone<double>{}), E.ph_vec(OpPgUpdate{{}, m, g, mn, Ad, B}, n)); };
 	return E.run([&]() {
-		E.vec(OpPgStep{{}, m, g, lo, hi, mn, 0.0}, n);
+		E.vec_push(OpPgStep{{}, m, g, lo, hi, mn, 0.0}, n, mn);
 		E.spmv(A, mn, Ad, EpiNone<double>{});
 		E.vec(OpPgUpdate{{}, m, g, mn, Ad, B}, n);
 		return false;
@@ -608,7 +609,8 @@ static int run_spg(Engine& E, const Operator<double>& A, double* m, const double
 {
 	double* g = E.alloc<double>(next); double* Ad = E.alloc<double>(next); double* mn = E.alloc<double>(next);
 	double* d = E.alloc<double>(next);
-	E.vec(OpBox{{}, m, lo, hi}, n);
+	E.capturable = false;	// host-side line search
+	E.vec_push(OpBox{{}, m, lo, hi}, n, m);
 	E.spmv(A, m, Ad, EpiNone<double>{});
 	E.vec(OpPgInit<true>{{}, m, Ad, B, g}, n);
 	// the non-monotone history lives on the host: the line search is data dependent (lcg.cpp:1377-1399)
@@ -625,7 +627,7 @@ static int run_spg(Engine& E, const Operator<double>& A, double* m, const double
 		int t_now = 0;
 		while (true)
 		{
-			E.vec(OpSpgTrial{{}, m, d, mn, alpha}, n);
+			E.vec_push(OpSpgTrial{{}, m, d, mn, alpha}, n, mn);
 			E.spmv(A, mn, Ad, EpiSpgQ{B});
 			E.read_state();
 			const double qk = E.h_st->sc[SC_QK], gd = E.h_st->sc[SC_GD];

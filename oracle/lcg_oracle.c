@@ -841,6 +841,16 @@ int lcgoracle_num_threads(void)
 #endif
 }
 
+/* bench.py's CPU arms set their own thread count: a launcher (torchrun) may have exported OMP_NUM_THREADS=1 */
+void lcgoracle_set_num_threads(int n)
+{
+#ifdef _OPENMP
+	if (n > 0) omp_set_num_threads(n);
+#else
+	(void)n;
+#endif
+}
+
 /* ================================================================ synthetic systems
  * Host generator of the bench workloads for the CPU arms of bench.py (cpu_baseline, --impl reference): rows
  * [row0,row1) of the g^3 7-point / 27-point Poisson or 7-point convection-diffusion matrix, columns ascending,

@@ -102,6 +102,10 @@ class Oracle:
     def num_threads(self) -> int:
         return int(getattr(self.lib, self.pfx + "num_threads")())
 
+    def set_num_threads(self, n: int) -> None:
+        """OpenMP threads of the CPU arm, independent of an inherited OMP_NUM_THREADS (torchrun exports 1)."""
+        getattr(self.lib, self.pfx + "set_num_threads")(C.c_int(int(n)))
+
     def set_time(self, t: int) -> None:
         """Pin the seed clcg_vecrnd() derives from time(0) (reference lcg_complex.cpp:118-127)."""
         getattr(self.lib, self.pfx + "set_time")(C.c_long(t))
@@ -193,6 +197,20 @@ class RefCuda:
                                         _p(m, C.c_double), _p(b, C.c_double), C.c_double(epsilon), C.c_int(max_iterations),
                                         C.c_int(int(with_progress)), C.byref(secs), C.byref(its))
         return ret, secs.value, its.value
+
+    CSOLVERS = {"BICG": 0, "BICG_SYM": 1, "PCG": 5}
+
+    def csolve(self, solver: str, n: int, nnz: int, d_rp: int, d_ci: int, d_val: int, m: np.ndarray, b: np.ndarray,
+               epsilon: float, max_iterations: int, abs_diff: int = 0, hist_cap: int = 0):
+        """clcg_solver_cuda / clcg_solver_preconditioned_cuda (clcg_cuda.cu:86-559), unmodified.  d_val: device pointer to nnz
+        cuDoubleComplex; m (in/out), b: host complex128.  Returns (ret, seconds, last k, residual history)."""
+        self.lib.lcgrefcuda_csolve.restype = C.c_int
+        secs, its, calls = C.c_double(), C.c_int(), C.c_int()
+        hist = np.zeros(max(hist_cap, 1), dtype=np.float64)
+        ret = self.lib.lcgrefcuda_csolve(C.c_int(self.CSOLVERS[solver]), C.c_int(n), C.c_int(nnz), C.c_void_p(d_rp), C.c_void_p(d_ci), C.c_void_p(d_val),
+                                         _p(m, C.c_double), _p(b, C.c_double), C.c_double(epsilon), C.c_int(max_iterations), C.c_int(abs_diff),
+                                         _p(hist, C.c_double), C.c_int(hist_cap), C.byref(secs), C.byref(its), C.byref(calls))
+        return ret, secs.value, its.value, hist[:min(calls.value, hist_cap)].copy()
 
 
 _KINDS = {"7pt": 0, "27pt": 1, "7pt_cd": 2}

@@ -91,6 +91,26 @@ def main():
                                torch.from_numpy(G["val"][k0:k1]).to(dev), bounds, rank, jacobi=True)
     packed = any(len(idx) and not np.array_equal(idx, np.arange(idx[0], idx[0] + len(idx))) for idx in part.plan.send_to.values())
     b_loc = torch.from_numpy(bfull[r0:r1]).to(dev)
+    # stand-alone SpMVs back to back on the partitioned handle (no reduction in between: the mailbox buffers are recycled
+    # under the acknowledgement flags alone), each against the global product
+    n_ext = part.n_local + part.plan.n_ghost
+    bad_spmv = 0
+    for t in range(6):
+        xg = np.random.default_rng(100 + t).standard_normal(n)
+        x_ext = torch.zeros(n_ext, dtype=torch.float64, device=dev)
+        x_ext[:part.n_local] = torch.from_numpy(xg[r0:r1]).to(dev)
+        y_loc = torch.empty(part.n_local, dtype=torch.float64, device=dev)
+        part.op.spmv(x_ext, y_loc)
+        torch.cuda.synchronize()
+        ref = (Afull @ xg)[r0:r1]
+        err = float(np.max(np.abs(y_loc.cpu().numpy() - ref)) / (np.max(np.abs(ref)) + 1e-300))
+        bad_spmv += int(not err < 1e-13)
+    tb = torch.tensor([bad_spmv], device=dev)
+    dist.all_reduce(tb)
+    if rank == 0:
+        print(f"{'OK  ' if int(tb.item()) == 0 else 'FAIL'} world={world} random-SPD n={n} 6 stand-alone SpMVs back to back on the partitioned handle "
+              f"transport {'nvlink-p2p' if part.p2p else 'nccl'}", flush=True)
+        failures += int(tb.item() != 0)
     for sid in (api.LCG_CG, api.LCG_PCG, api.LCG_BICGSTAB):
         for name, kw in (("pinned25", dict(epsilon=1e-300, max_iterations=25)), ("eps1e-12", dict(epsilon=1e-12, max_iterations=3000))):
             m = torch.zeros(part.n_local, dtype=torch.float64, device=dev)

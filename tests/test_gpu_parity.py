@@ -426,10 +426,6 @@ def gpu_cplx(A, sid, b, para, Pfp=None, diag=False):
 def test_complex_solvers_match_reference_counts(torch_cuda, golden, port, fixtures, fx, mode, sid):
     """config[1]: data/case_10K_cA + case_10K_cB (sample6.cpp:162-196 setting) and case_1K_cA (sample4.cpp:145-157)."""
     g = golden["complex"][f"{fx}/{mode}/{CPLX[sid]}"]
-    if fx == "1Kc" and CPLX[sid] == "BICGSTAB":
-        pytest.xfail("case_1K_cA BiCGSTAB is a breakdown case: <r0~,r> sinks to rounding level (1e-14 vs |r||r0~| ~ 1e3) and the "
-                     "reference itself wanders for 10825 iterations (10 n) before a lucky crossing; any change of summation order "
-                     "ends elsewhere (profiles/parity_r01_first_run.txt)")
     Ac = fixtures[fx]
     api.set_shadow_seed(golden["seed"])
     para = dict(abs_diff=1 if mode == "abs" else 0)
@@ -437,13 +433,45 @@ def test_complex_solvers_match_reference_counts(torch_cuda, golden, port, fixtur
     assert r.ret == g["ret"], api.last_error()
     port.set_time(golden["seed"])
     cpu_solve = lambda b: port.csolve(sid, Ac, b, para=po.default_cpara(**para))
-    if CPLX[sid] == "BICGSTAB":
-        # thousands of iterations of an erratic recurrence: rounding differences move the crossing; only sanity here
-        assert 0.5 * g["iters"] <= r.iterations <= 1.5 * g["iters"]
+    if fx == "1Kc" and CPLX[sid] == "BICGSTAB":
+        # breakdown case: <r0~,r> sinks to rounding level and the reference itself wanders 10 n iterations before a lucky
+        # crossing — its count is not a property of the algorithm; the iterates are compared by test_complex_bicgstab_history
+        assert r.iterations > 0
     else:
-        assert_iters_parity(r.iterations, g["iters"], lambda seed: cpu_solve(noisy(Ac["b"], seed)).iters)
+        assert_iters_parity(r.iterations, g["iters"], lambda seed: cpu_solve(noisy(Ac["b"], seed)).iters, samples=4 if CPLX[sid] == "BICGSTAB" else 8)
     # both stopped on the same threshold: as close to the reference's known answer as the reference's own run is
     assert rel(x, Ac["answer"]) < max(5e-3, 3.0 * rel(cpu_solve(Ac["b"]).x, Ac["answer"]))
+
+
+@pytest.mark.parametrize("fx", ["10Kc", "1Kc"])
+def test_complex_bicgstab_history(torch_cuda, golden, port, fixtures, fx):
+    """Complex BiCGSTAB (clcg.cpp:524-679) iteration by iteration: the residual history the progress callback sees must be the
+    CPU solver's for as long as the CPU solver's OWN history is reproducible (its sensitivity to a 1-ulp change of b stays
+    below 1e-8); past that point the recurrence amplifies rounding and no two summation orders agree."""
+    Ac = fixtures[fx]
+    K = 60
+    api.set_shadow_seed(golden["seed"])
+    port.set_time(golden["seed"])
+    para = dict(epsilon=1e-300, max_iterations=K)
+    hist = []
+    r, x = gpu_cplx(Ac, api.CLCG_BICGSTAB, Ac["b"], api.clcg_default_parameters(**para), Pfp=lambda i, m, c, p, n, nz, k: hist.append(c) or 0)
+    cpu = port.csolve(po.CLCG_BICGSTAB, Ac, Ac["b"], para=po.default_cpara(**para), hist_cap=K + 2)
+    pert = port.csolve(po.CLCG_BICGSTAB, Ac, perturbed(Ac["b"]), para=po.default_cpara(**para), hist_cap=K + 2)
+    assert r.ret == cpu.ret == api.LCG_REACHED_MAX_ITERATIONS and r.iterations == cpu.iters == K and len(hist) == cpu.calls
+    h_gpu, h_cpu, h_pert = np.array(hist), cpu.history, pert.history
+    sens = np.abs(h_pert - h_cpu) / h_cpu
+    unstable = np.nonzero(sens >= 1e-8)[0]
+    prefix = int(unstable[0]) if len(unstable) else len(h_cpu)
+    assert prefix >= 5, f"the oracle's own history is unstable after {prefix} iterations"   # measured: 7 (10Kc), 10 (1Kc); x10 per iteration after that
+    d = np.abs(h_gpu[:prefix] - h_cpu[:prefix]) / h_cpu[:prefix]
+    assert d.max() <= 1e-6, f"history differs by {d.max():.2e} at k={int(d.argmax())} (oracle-stable prefix {prefix})"
+    # and the iterate itself at the end of the stable prefix
+    kp = max(1, prefix - 1)
+    para = dict(epsilon=1e-300, max_iterations=kp)
+    r2, x2 = gpu_cplx(Ac, api.CLCG_BICGSTAB, Ac["b"], api.clcg_default_parameters(**para))
+    cpu2 = port.csolve(po.CLCG_BICGSTAB, Ac, Ac["b"], para=po.default_cpara(**para))
+    assert r2.iterations == cpu2.iters == kp
+    assert_x_parity(x2, cpu2.x, lambda: port.csolve(po.CLCG_BICGSTAB, Ac, perturbed(Ac["b"]), para=po.default_cpara(**para)).x)
 
 
 @pytest.mark.parametrize("k", [1, 10, 50])
@@ -473,6 +501,45 @@ def test_complex_pcg_jacobi(torch_cuda, port, fixtures):
                                                                            para=po.default_cpara(**para)).iters)
         if r.iterations == cpu.iters:
             assert_x_parity(x, cpu.x, lambda: port.csolve(po.CLCG_PCG, Ac, perturbed(Ac["b"]), diag=Ac["diag"], para=po.default_cpara(**para)).x)
+
+
+@pytest.mark.parametrize("k", [1, 10, 40])
+@pytest.mark.parametrize("name", ["PCG", "BICG", "BICG_SYM"])
+def test_complex_pinned_to_reference_cuda(torch_cuda, port, fixtures, name, k):
+    """The reference's OWN complex CUDA solvers (clcg_cuda.cu: clpcg :403-559, clbicg :86-252, clbicg_symmetric :254-401;
+    cuBLAS + cusparseSpMV, built unmodified into oracle/_ref/liblcg_ref_cuda.so) after exactly k iterations on
+    data/case_10K_cA: our iterate, and the CPU port's (the restatement of complex Jacobi-PCG has no CPU reference to be
+    pinned to — this is its pin), must be the reference's to 1e-8, and with lcgb200_set_complex_residual_mode(1) the residual
+    the progress callback sees is the reference-CUDA definition (clcg_cuda.cu:145-176)."""
+    torch = torch_cuda
+    if not po.have_reference_cuda():
+        pytest.skip("oracle/_ref/liblcg_ref_cuda.so not present")
+    Ac = fixtures["10Kc"]
+    n, nnz = Ac["n"], Ac["nnz"]
+    rc = po.RefCuda()
+    d_rp, d_ci = to_dev(torch, Ac["row_ptr"]), to_dev(torch, Ac["col"])
+    d_val = to_dev(torch, np.ascontiguousarray(Ac["val"], dtype=np.complex128))
+    m_ref = np.zeros(n, dtype=np.complex128)
+    ret_ref, _, k_ref, h_ref = rc.csolve(name, n, nnz, d_rp.data_ptr(), d_ci.data_ptr(), d_val.data_ptr(), m_ref, np.ascontiguousarray(Ac["b"]),
+                                         1e-300, k, abs_diff=0, hist_cap=k + 2)
+    assert ret_ref == api.LCG_REACHED_MAX_ITERATIONS and k_ref == k
+    sid = {"PCG": api.CLCG_PCG, "BICG": api.CLCG_BICG, "BICG_SYM": api.CLCG_BICG_SYM}[name]
+    hist = []
+    api.set_complex_residual_mode(1)
+    try:
+        r, x = gpu_cplx(Ac, sid, Ac["b"], api.clcg_default_parameters(epsilon=1e-300, max_iterations=k), diag=(name == "PCG"),
+                        Pfp=lambda i, m, c, p, nn, nz, kk: hist.append(c) or 0)
+    finally:
+        api.set_complex_residual_mode(0)
+    assert r.ret == ret_ref and r.iterations == k
+    cpu = port.csolve(sid, Ac, Ac["b"], para=po.default_cpara(epsilon=1e-300, max_iterations=k), diag=Ac["diag"] if name == "PCG" else None)
+    assert cpu.iters == k
+    resolve = lambda: port.csolve(sid, Ac, perturbed(Ac["b"]), para=po.default_cpara(epsilon=1e-300, max_iterations=k),
+                                  diag=Ac["diag"] if name == "PCG" else None).x
+    assert_x_parity(x, m_ref, resolve)            # ours vs the reference's CUDA solver
+    assert_x_parity(cpu.x, m_ref, resolve)        # the CPU port vs the reference's CUDA solver
+    if rel(x, m_ref) <= X_TOL:
+        np.testing.assert_allclose(hist, h_ref, rtol=1e-6)
 
 
 def test_complex_history_and_stop(torch_cuda, port, fixtures):
@@ -629,6 +696,29 @@ def test_full_size_properties(torch_cuda, kind_id, g, sid, symmetric):
     r2 = api.solve(op, sid, m2, b, param=para, device=True, jacobi=(sid == api.LCG_PCG))
     assert r2.iterations == r.iterations and torch.equal(m, m2)
     op.close()
+
+
+@pytest.mark.parametrize("kind,g,sid,k", [("7pt", 128, api.LCG_CG, 25), ("27pt", 256, api.LCG_PCG, 10), ("7pt_cd", 320, api.LCG_BICGSTAB, 5)])
+def test_full_size_pinned_iterations_match_cpu(torch_cuda, port, kind, g, sid, k):
+    """BASELINE configs[2..4] at (or near) FULL size against the CPU oracle: both sides run exactly k iterations of the same
+    system (generated bit-identically on the host and on the device, test_device_stencil_generator_is_bit_exact) and must
+    hold the same iterate to 1e-8 and report the same residual.  128^3 CG k=25, 256^3 Jacobi-PCG k=10 (16.8 M rows, 449 M
+    non-zeros: the bench's system), 320^3 convection-diffusion BiCGSTAB k=5 — a few seconds of CPU work each."""
+    torch = torch_cuda
+    S = po.gen_system(kind, g)
+    n = S["n"]
+    diag = np.full(n, 26.0 if kind == "27pt" else 6.0) if sid == api.LCG_PCG else None
+    cpu = port.solve(sid, S, S["b"], para=po.default_para(epsilon=1e-300, max_iterations=k), diag=diag, progress=True)
+    del S
+    op, b, n_dev = _device_system(torch, stencil.KINDS.index(kind), g, jacobi=(sid == api.LCG_PCG))
+    assert n_dev == n
+    m = torch.zeros(n, dtype=torch.float64, device="cuda")
+    r = api.solve(op, sid, m, b, param=api.lcg_default_parameters(epsilon=1e-300, max_iterations=k), device=True, jacobi=(sid == api.LCG_PCG))
+    x = m.cpu().numpy()
+    op.close()
+    assert r.ret == cpu.ret == api.LCG_REACHED_MAX_ITERATIONS and r.iterations == cpu.iters == k
+    assert rel(x, cpu.x) <= X_TOL, rel(x, cpu.x)
+    assert r.residual == pytest.approx(cpu.residual, rel=1e-7)
 
 
 def test_host_callback_api(torch_cuda, port, fixtures):
