@@ -231,6 +231,13 @@ int lcgb200_solver(lcgb200_axfunc_ptr Afp, lcgb200_progress_ptr Pfp, double* m, 
 	const lcgb200_para* param, void* instance, int solver_id);
 int lcgb200_solver_preconditioned(lcgb200_axfunc_ptr Afp, lcgb200_axfunc_ptr Mfp, lcgb200_progress_ptr Pfp, double* m, const double* B,
 	const int n_size, const lcgb200_para* param, void* instance, int solver_id);
+/* replace the stand-alone lcg() (lcg.h:135-137) and lcgs() (lcg.h:166-169): CG / CGS with optional caller-owned HOST work
+ * vectors (any of them may be NULL).  The solve's work vectors live on the device; the caller's arrays receive their
+ * final contents (lcg: Gk = gradient A m - B, Dk = direction, ADk = A Dk; lcgs: RK, R0T, PK, AX, UK, QK, WK). */
+int lcgb200_lcg(lcgb200_axfunc_ptr Afp, lcgb200_progress_ptr Pfp, double* m, const double* B, const int n_size,
+	const lcgb200_para* param, void* instance, double* Gk, double* Dk, double* ADk);
+int lcgb200_lcgs(lcgb200_axfunc_ptr Afp, lcgb200_progress_ptr Pfp, double* m, const double* B, const int n_size,
+	const lcgb200_para* param, void* instance, double* RK, double* R0T, double* PK, double* AX, double* UK, double* QK, double* WK);
 int lcgb200_solver_constrained(lcgb200_axfunc_ptr Afp, lcgb200_progress_ptr Pfp, double* m, const double* B, const double* low, const double* hig,
 	const int n_size, const lcgb200_para* param, void* instance, int solver_id);
 int lcgb200_csolver(lcgb200_caxfunc_ptr Afp, lcgb200_cprogress_ptr Pfp, void* m, const void* B, const int n_size,

@@ -79,6 +79,8 @@ SYMBOLS = {
     "lcgb200_jacobi_mx_host": (None, None),
     "lcgb200_csr_cax_host": (None, None),
     "lcgb200_solver": (_I, [_VP, _VP, _VP, _VP, _I, C.POINTER(LcgPara), _VP, _I]),
+    "lcgb200_lcg": (_I, [_VP, _VP, _VP, _VP, _I, C.POINTER(LcgPara), _VP, _VP, _VP, _VP]),
+    "lcgb200_lcgs": (_I, [_VP, _VP, _VP, _VP, _I, C.POINTER(LcgPara), _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "lcgb200_solver_preconditioned": (_I, [_VP, _VP, _VP, _VP, _VP, _I, C.POINTER(LcgPara), _VP, _I]),
     "lcgb200_solver_constrained": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, C.POINTER(LcgPara), _VP, _I]),
     "lcgb200_csolver": (_I, [_VP, _VP, _VP, _VP, _I, C.POINTER(ClcgPara), _VP, _I]),

@@ -399,6 +399,8 @@ void destroy_handle(CsrHandle* h)
 	if (h->h_state) cudaFreeHost(h->h_state);
 	if (h->h_state2) cudaFreeHost(h->h_state2);
 	for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+	if (h->own_stream) cudaStreamDestroy(h->own_stream);
+	if (h->own_event) cudaEventDestroy(h->own_event);
 	delete h;
 }
 
@@ -482,6 +484,22 @@ int check_cplx(int n, const lcgb200_cpara& p, const void* m, const void* B)
 const lcgb200_para kDefPara = {0, 1e-6, 0, 1e-6, 1.0, 0.95, 0.9, 10};	// defparam, util.h:153
 const lcgb200_cpara kDefCPara = {0, 1e-6, 0};				// defparam2, util.h:278
 
+// The legacy default stream cannot be captured into a CUDA graph.  A solve on the built-in operator (no user callback that
+// might enqueue work on a stream of its own) that was handed that stream is moved to a private non-blocking stream of the
+// handle, ordered after everything the caller has enqueued so far; the entry points return only when the solve is complete.
+cudaStream_t solve_stream(CsrHandle* h, bool builtin_only, cudaStream_t stream)
+{
+	if (!h || !builtin_only || !(stream == nullptr || stream == cudaStreamLegacy)) return stream;
+	if (!h->own_stream)
+	{
+		LCG_CUDA_CHECK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+		LCG_CUDA_CHECK(cudaEventCreateWithFlags(&h->own_event, cudaEventDisableTiming));
+	}
+	LCG_CUDA_CHECK(cudaEventRecord(h->own_event, stream));
+	LCG_CUDA_CHECK(cudaStreamWaitEvent(h->own_stream, h->own_event, 0));
+	return h->own_stream;
+}
+
 inline double now_ms()
 {
 	using namespace std::chrono;
@@ -491,9 +509,11 @@ inline double now_ms()
 // One solve, real.  `h` may be null (callback operator).  m/B/lo/hi live on the host unless dev_vecs.
 int do_solve_real(CsrHandle* h, Operator<double>& A, int solver_id, double* m, const double* B, const double* lo, const double* hi,
 	const lcgb200_para& para, int n, int n_ext, long long n_global,
-	const std::function<ProgressFn(const double* m_dev)>& make_pf, bool dev_vecs, cudaStream_t stream, lcgb200_info* info)
+	const std::function<ProgressFn(const double* m_dev)>& make_pf, bool dev_vecs, cudaStream_t stream, lcgb200_info* info,
+	double* const* ws_out = nullptr, int n_ws_out = 0)
 {
 	const double t0 = now_ms();
+	stream = solve_stream(h, A.h && !A.apply && !A.precond && !(bool)make_pf(nullptr), stream);   // a progress callback may use the caller's stream
 	Engine E(stream, h);
 	E.n_local = (size_t)n;
 	const bool constrained = (solver_id == LCGB200_PG || solver_id == LCGB200_SPG);
@@ -536,15 +556,19 @@ int do_solve_real(CsrHandle* h, Operator<double>& A, int solver_id, double* m, c
 	E.sync_each = A.host_side || (bool)A.apply || (bool)A.precond;
 	if (E.comm && E.comm->poisoned()) { set_error_msg("this communicator timed out in an earlier solve: its sequence counters may disagree with the peers'; create a new one"); throw ApiFailure{LCGB200_UNKNOWN_ERROR}; }
 	E.start(init);
+	const size_t first_work = E.allocs.size();
 	int ret = solve_real(E, A, solver_id, d_m, d_B, d_lo, d_hi, para, (size_t)n, (size_t)n_ext);
 	const double dev_ms = E.device_ms();
+	// lcg() / lcgs(): the caller's work vectors receive the solver's (host arrays, in the solver's allocation order)
+	for (int i = 0; i < n_ws_out && first_work + (size_t)i < E.allocs.size(); i++)
+		if (ws_out[i]) LCG_CUDA_CHECK(cudaMemcpy(ws_out[i], E.allocs[first_work + (size_t)i], (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
 	if (E.multi() && E.comm->check_abort()) set_error_msg("a cross-GPU wait timed out (a peer rank never arrived): the solve was ended and the communicator is poisoned");
 	if (!m_inplace)
 	{
 		const cudaMemcpyKind out_kind = dev_vecs ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
 		LCG_CUDA_CHECK(cudaMemcpyAsync(m, d_m, (size_t)n * sizeof(double), out_kind, stream));
-		LCG_CUDA_CHECK(cudaStreamSynchronize(stream));
 	}
+	LCG_CUDA_CHECK(cudaStreamSynchronize(stream));
 	if (info)
 	{
 		info->iterations = E.h_st->k_report; info->checks = E.h_st->checks; info->spmv_launches = E.spmv_launches;
@@ -560,6 +584,7 @@ int do_solve_cplx(CsrHandle* h, Operator<double2>& A, int solver_id, double2* m,
 	cudaStream_t stream, lcgb200_info* info)
 {
 	const double t0 = now_ms();
+	stream = solve_stream(h, A.h && !A.apply && !A.precond && !(bool)make_pf(nullptr), stream);   // a progress callback may use the caller's stream
 	Engine E(stream, h);
 	E.n_local = (size_t)n;
 	const bool m_inplace = dev_vecs && n_ext == n && ((reinterpret_cast<uintptr_t>(m) & 15) == 0);
@@ -587,8 +612,8 @@ int do_solve_cplx(CsrHandle* h, Operator<double2>& A, int solver_id, double2* m,
 	{
 		const cudaMemcpyKind out_kind = dev_vecs ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
 		LCG_CUDA_CHECK(cudaMemcpyAsync(m, d_m, (size_t)n * sizeof(double2), out_kind, stream));
-		LCG_CUDA_CHECK(cudaStreamSynchronize(stream));
 	}
+	LCG_CUDA_CHECK(cudaStreamSynchronize(stream));
 	if (info)
 	{
 		info->iterations = E.h_st->k_report; info->checks = E.h_st->checks; info->spmv_launches = E.spmv_launches;
@@ -1026,7 +1051,7 @@ struct HostStage {	// page-locked staging vectors for host callbacks
 };
 
 int host_real(lcgb200_axfunc_ptr Afp, lcgb200_axfunc_ptr Mfp, lcgb200_progress_ptr Pfp, double* m, const double* B, const double* low, const double* hig,
-	const int n, const lcgb200_para* param, void* instance, int solver_id)
+	const int n, const lcgb200_para* param, void* instance, int solver_id, double* const* ws_out = nullptr, int n_ws_out = 0)
 {
 	const lcgb200_para para = param ? *param : kDefPara;
 	int rc = check_real(solver_id, n, para, m, B, low, hig);
@@ -1066,7 +1091,8 @@ int host_real(lcgb200_axfunc_ptr Afp, lcgb200_axfunc_ptr Mfp, lcgb200_progress_p
 				return Pfp(user, hs.m, res, &para, n, k);
 			};
 		};
-		return do_solve_real(h, A, solver_id, m, B, low, hig, para, n, h ? h->n_cols : n, h ? h->n_global : (long long)n, make_pf, false, nullptr, nullptr);
+		return do_solve_real(h, A, solver_id, m, B, low, hig, para, n, h ? h->n_cols : n, h ? h->n_global : (long long)n, make_pf, false, nullptr, nullptr,
+			ws_out, n_ws_out);
 	});
 }
 
@@ -1084,6 +1110,23 @@ int lcgb200_solver(lcgb200_axfunc_ptr Afp, lcgb200_progress_ptr Pfp, double* m, 
 	int id = LCGB200_CGS;
 	if (solver_id == LCGB200_CG || solver_id == LCGB200_BICGSTAB || solver_id == LCGB200_BICGSTAB2) id = solver_id;
 	return host_real(Afp, nullptr, Pfp, m, B, nullptr, nullptr, n_size, param, instance, id);
+}
+
+// lcg() (lcg.h:135-137, lcg.cpp:143-274): the stand-alone CG with optional caller-owned work vectors Gk, Dk, ADk.  The work
+// vectors of the solve live on the device; the caller's arrays (where given) receive their final contents.
+int lcgb200_lcg(lcgb200_axfunc_ptr Afp, lcgb200_progress_ptr Pfp, double* m, const double* B, const int n_size,
+	const lcgb200_para* param, void* instance, double* Gk, double* Dk, double* ADk)
+{
+	double* ws[3] = {Gk, Dk, ADk};
+	return host_real(Afp, nullptr, Pfp, m, B, nullptr, nullptr, n_size, param, instance, LCGB200_CG, ws, 3);
+}
+
+// lcgs() (lcg.h:166-169, lcg.cpp:437-612): the stand-alone CGS with optional work vectors RK, R0T, PK, AX, UK, QK, WK
+int lcgb200_lcgs(lcgb200_axfunc_ptr Afp, lcgb200_progress_ptr Pfp, double* m, const double* B, const int n_size,
+	const lcgb200_para* param, void* instance, double* RK, double* R0T, double* PK, double* AX, double* UK, double* QK, double* WK)
+{
+	double* ws[7] = {RK, R0T, PK, AX, UK, QK, WK};
+	return host_real(Afp, nullptr, Pfp, m, B, nullptr, nullptr, n_size, param, instance, LCGB200_CGS, ws, 7);
 }
 
 int lcgb200_solver_preconditioned(lcgb200_axfunc_ptr Afp, lcgb200_axfunc_ptr Mfp, lcgb200_progress_ptr Pfp, double* m, const double* B,

@@ -204,6 +204,59 @@ __device__ __forceinline__ void spmv_tile_rows(const T* __restrict__ sval, const
 	}
 }
 
+// Consumer side of k_spmv: chunks c, c + gridDim.x, ... below c_end.  `idx` counts the staged tiles this CTA has consumed
+// (the ring position shared with the producer), so that two calls can split the chunk range between them.
+template <class T, int LPR, bool CONJ, bool GHOST, class Epi>
+__device__ __forceinline__ void spmv_consume(const CsrDev<T>& A, const T* __restrict__ x, const T* ghost, T* __restrict__ y, Epi& epi, double* acc,
+	unsigned char* smem, unsigned long long* s_bar, T* s_long, int& idx, int& c, const int c_end, const int tid)
+{
+	typedef StageCfg<T> SC;
+	constexpr int TN = SC::NNZ;
+	const int group = tid / LPR, lane = tid % LPR;
+	for (; c < c_end; c += gridDim.x)
+	{
+		const int t1 = min((c + 1) * A.chunk, A.n_tiles);
+		for (int tile = c * A.chunk; tile < t1; tile++)
+		{
+			const int4 td = __ldg(A.tiles + tile);
+			const int r0 = td.x, nrows = td.y - td.x, k0 = td.z, k1 = td.w;
+			if (k1 - k0 > TN)
+			{	// one row longer than a stage: stream it straight from global memory
+				T part = tzero(T());
+				for (int k = A.row_ptr[r0] + tid; k < k1; k += kThreads)
+				{
+					T a = A.val[k]; if (CONJ) a = tconj(a);
+					const int cc = A.col[k];
+					part = mulacc(part, a, tldg((GHOST && cc >= A.n_rows ? ghost : x) + cc));
+				}
+#pragma unroll
+				for (int o = 16; o > 0; o >>= 1) part = tadd(part, tshfl_xor(part, o));
+				if ((tid & 31) == 0) s_long[tid >> 5] = part;
+				consumer_sync();
+				if (tid == 0)
+				{
+					T tot = s_long[0];
+					for (int w = 1; w < kThreads / 32; w++) tot = tadd(tot, s_long[w]);
+					y[r0] = tot;
+					epi.row(r0, tot, tldg(x + r0), acc);
+				}
+				consumer_sync();
+				continue;
+			}
+			const int s = idx % kStages;
+			mbar_wait(smem_u32(&s_bar[s]), (uint32_t)((idx / kStages) & 1));
+			const unsigned char* base = smem + (size_t)s * SC::BYTES;
+			const T* sval = reinterpret_cast<const T*>(base + SC::VAL_OFF);
+			const int* scol = reinterpret_cast<const int*>(base + SC::COL_OFF);
+			const int* srow = reinterpret_cast<const int*>(base + SC::ROW_OFF) + (r0 & 3);
+			spmv_tile_rows<T, LPR, CONJ, GHOST, Epi>(sval, scol, srow, r0, nrows, k0, x, ghost, A.n_rows, y, epi, acc, group, lane);
+			__syncwarp();
+			if ((tid & 31) == 0) mbar_arrive(smem_u32(&s_bar[kStages + s]));
+			idx++;
+		}
+	}
+}
+
 // Epi interface:
 //   static constexpr int NRED;
 //   __device__ void begin(const DevState*);
@@ -273,68 +326,23 @@ __global__ void __launch_bounds__(kSpmvThreads, TileCfg<T>::CTAS) k_spmv(CsrDev<
 	else
 	{
 		epi.begin(st);
-		const int group = tid / LPR, lane = tid % LPR;
-		// partitioned row block (NVLink transport): interior tiles start at once, the first boundary tile of this warp waits
-		// until every neighbour's push for this exchange has landed in my mailbox
-		const bool partitioned = PART && A.n_interior >= 0;
-		const T* ghost = nullptr; bool ghost_ready = false;
-		int idx = 0;
-		for (int c = blockIdx.x; c < n_chunks; c += gridDim.x)
-		{
-			const int t1 = min((c + 1) * A.chunk, A.n_tiles);
-			for (int tile = c * A.chunk; tile < t1; tile++)
-			{
-				const int4 td = __ldg(A.tiles + tile);
-				const int r0 = td.x, nrows = td.y - td.x, k0 = td.z, k1 = td.w;
-				const bool boundary = partitioned && tile >= A.n_interior;
-				if (boundary && !ghost_ready)
-				{
-					CommDev* cd = st->comm;
-					const unsigned long long hseq = cd->halo_seq;
-					bool ok = true;
-					if ((tid & 31) < cd->n_peers && cd->recv_count[tid & 31] > 0)
-						ok = spin_until(&cd->win[cd->rank]->halo_flag[cd->peer_rank[tid & 31]], hseq, st->spin_timeout_ns);
-					ok = __all_sync(0xffffffffu, ok);
-					if (!ok && (tid & 31) == 0) { st->ret = RC_UNKNOWN; st->done = 1; cd->abort_flag = 1; }
-					ghost = mailbox_of<T>(cd->win[cd->rank], hseq, cd->n_ghost) - cd->n_local;
-					ghost_ready = true;
-				}
-				if (k1 - k0 > TN)
-				{	// one row longer than a stage: stream it straight from global memory
-					T part = tzero(T());
-					for (int k = A.row_ptr[r0] + tid; k < k1; k += kThreads)
-					{
-						T a = A.val[k]; if (CONJ) a = tconj(a);
-						const int cc = A.col[k];
-						part = mulacc(part, a, tldg((boundary && cc >= A.n_rows ? ghost : x) + cc));
-					}
-#pragma unroll
-					for (int o = 16; o > 0; o >>= 1) part = tadd(part, tshfl_xor(part, o));
-					if ((tid & 31) == 0) s_long[tid >> 5] = part;
-					consumer_sync();
-					if (tid == 0)
-					{
-						T tot = s_long[0];
-						for (int w = 1; w < kThreads / 32; w++) tot = tadd(tot, s_long[w]);
-						y[r0] = tot;
-						epi.row(r0, tot, tldg(x + r0), acc);
-					}
-					consumer_sync();
-					continue;
-				}
-				const int s = idx % kStages;
-				mbar_wait(smem_u32(&s_bar[s]), (uint32_t)((idx / kStages) & 1));
-				const unsigned char* base = smem + (size_t)s * SC::BYTES;
-				const T* sval = reinterpret_cast<const T*>(base + SC::VAL_OFF);
-				const int* scol = reinterpret_cast<const int*>(base + SC::COL_OFF);
-				const int* srow = reinterpret_cast<const int*>(base + SC::ROW_OFF) + (r0 & 3);
-				if (boundary) spmv_tile_rows<T, LPR, CONJ, true, Epi>(sval, scol, srow, r0, nrows, k0, x, ghost, A.n_rows, y, epi, acc, group, lane);
-				else spmv_tile_rows<T, LPR, CONJ, false, Epi>(sval, scol, srow, r0, nrows, k0, x, nullptr, 0, y, epi, acc, group, lane);
-				__syncwarp();
-				if ((tid & 31) == 0) mbar_arrive(smem_u32(&s_bar[kStages + s]));
-				idx++;
-			}
+		int idx = 0, c = blockIdx.x;
+		if (PART && A.n_interior >= 0)
+		{	// partitioned row block (NVLink transport): the chunks made of interior tiles only run the very loop of the single-GPU
+			// kernel; then this warp waits until every neighbour's push for this exchange has landed in my mailbox and walks the
+			// remaining chunks with ghost columns read in place from the mailbox
+			spmv_consume<T, LPR, CONJ, false, Epi>(A, x, nullptr, y, epi, acc, smem, s_bar, s_long, idx, c, A.n_interior / A.chunk, tid);
+			CommDev* cd = st->comm;
+			const unsigned long long hseq = cd->halo_seq;
+			bool ok = true;
+			if ((tid & 31) < cd->n_peers && cd->recv_count[tid & 31] > 0)
+				ok = spin_until(&cd->win[cd->rank]->halo_flag[cd->peer_rank[tid & 31]], hseq, st->spin_timeout_ns);
+			ok = __all_sync(0xffffffffu, ok);
+			if (!ok && (tid & 31) == 0) { st->ret = RC_UNKNOWN; st->done = 1; cd->abort_flag = 1; }
+			const T* ghost = mailbox_of<T>(cd->win[cd->rank], hseq, cd->n_ghost) - cd->n_local;
+			spmv_consume<T, LPR, CONJ, true, Epi>(A, x, ghost, y, epi, acc, smem, s_bar, s_long, idx, c, n_chunks, tid);
 		}
+		else spmv_consume<T, LPR, CONJ, false, Epi>(A, x, nullptr, y, epi, acc, smem, s_bar, s_long, idx, c, n_chunks, tid);
 	}
 	if (PART && A.n_interior >= 0)
 	{	// the block that leaves last tells every sender that this exchange's mailbox buffer has been consumed

@@ -1,0 +1,428 @@
+// liblcg_dropin.cpp — liblcg_dropin.so: liblcg's C++ symbols (liblcg_abi.h), defined out of line and forwarding to the C ABI
+// of liblcgb200.so.  A program compiled against the REFERENCE's own headers (lcg.h, clcg.h, lcg_cuda.h, clcg_cuda.h,
+// solver.h, solver_cuda.h, util.h, algebra.h, lcg_complex.h) links against this library instead of liblcg.so — or is
+// re-pointed at it at load time — and runs on the B200-native engine: its Ax/Mx/progress callbacks are honoured on the
+// generic path, and passing the exported sentinels (lcgb200_csr_ax & co.) selects the fused built-in CSR operator.
+//
+// The small host helpers of algebra.h / lcg_complex.h are provided because every caller of the solvers uses them around
+// the call (vector allocation, fill, dot); they are host-side conveniences, not part of the hot path.
+#include "liblcg_abi.h"
+#include "../../../include/lcgb200.h"
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <ctime>
+#include <iostream>
+#include <stdexcept>
+
+static_assert(sizeof(lcg_para) == sizeof(lcgb200_para) && sizeof(clcg_para) == sizeof(lcgb200_cpara), "parameter blocks pass through the C ABI as they are");
+
+namespace {
+inline const lcgb200_para* P(const lcg_para* p) { return reinterpret_cast<const lcgb200_para*>(p); }
+inline const lcgb200_cpara* P(const clcg_para* p) { return reinterpret_cast<const lcgb200_cpara*>(p); }
+const lcg_para kDef = {0, 1e-6, 0, 1e-6, 1.0, 0.95, 0.9, 10};   // util.h:153
+const clcg_para kDefC = {0, 1e-6, 0};                           // util.h:278
+}
+
+// ------------------------------------------------------------------------------------------------ util.h
+lcg_para lcg_default_parameters() { return kDef; }
+clcg_para clcg_default_parameters() { return kDefC; }
+
+lcg_solver_enum lcg_select_solver(std::string name)
+{	// util.cpp:39-51: unknown names fall back to CGS
+	static const char* names[] = {"LCG_CG", "LCG_PCG", "LCG_CGS", "LCG_BICGSTAB", "LCG_BICGSTAB2", "LCG_PG", "LCG_SPG"};
+	for (int i = 0; i < 7; i++) if (name == names[i]) return static_cast<lcg_solver_enum>(i);
+	return LCG_CGS;
+}
+clcg_solver_enum clcg_select_solver(std::string name)
+{	// util.cpp:157-166 knows four names
+	if (name == "CLCG_BICG") return CLCG_BICG;
+	if (name == "CLCG_BICG_SYM") return CLCG_BICG_SYM;
+	if (name == "CLCG_TFQMR") return CLCG_TFQMR;
+	return CLCG_CGS;
+}
+
+namespace {
+const char* code_text(int code, bool cplx)
+{
+	if (code == 0) return "The iteration reached convergence.";
+	if (code == 1) return "The iteration was stopped by the progress callback.";
+	if (code == 2) return "The initial solution is already optimized.";
+	if (cplx)
+		switch (code)
+		{
+			case CLCG_INVILAD_VARIABLE_SIZE: return "The variable size is not positive.";
+			case CLCG_INVILAD_MAX_ITERATIONS: return "The maximal iteration count is negative.";
+			case CLCG_INVILAD_EPSILON: return "The epsilon is not in (0,1).";
+			case CLCG_REACHED_MAX_ITERATIONS: return "The iteration reached the maximal limit.";
+			case CLCG_NAN_VALUE: return "The model values are NaN.";
+			case CLCG_INVALID_POINTER: return "Invalid pointer.";
+			case CLCG_SIZE_NOT_MATCH: return "The sizes of the operator and the vectors do not match.";
+			case CLCG_UNKNOWN_SOLVER: return "Unknown solver.";
+			default: return "Unknown error.";
+		}
+	switch (code)
+	{
+		case LCG_INVILAD_VARIABLE_SIZE: return "The variable size is not positive.";
+		case LCG_INVILAD_MAX_ITERATIONS: return "The maximal iteration count is negative.";
+		case LCG_INVILAD_EPSILON: return "The epsilon is not in (0,1).";
+		case LCG_INVILAD_RESTART_EPSILON: return "The restart epsilon is not positive.";
+		case LCG_REACHED_MAX_ITERATIONS: return "The iteration reached the maximal limit.";
+		case LCG_NULL_PRECONDITION_MATRIX: return "The preconditioner is missing.";
+		case LCG_NAN_VALUE: return "The model values are NaN.";
+		case LCG_INVALID_POINTER: return "Invalid pointer.";
+		case LCG_INVALID_LAMBDA: return "Invalid range for lambda (step).";
+		case LCG_INVALID_SIGMA: return "Invalid range for sigma.";
+		case LCG_INVALID_BETA: return "Invalid range for beta.";
+		case LCG_INVALID_MAXIM: return "Invalid range for maxi_m.";
+		case LCG_SIZE_NOT_MATCH: return "The sizes of the operator and the vectors do not match.";
+		default: return "Unknown error.";
+	}
+}
+}  // namespace
+
+void lcg_error_str(int er_index, bool er_throw)
+{	// util.cpp:53-148: one line on stderr; with er_throw a negative code raises (the only thrower of the library, util.cpp:120)
+	const char* text = code_text(er_index, false);
+	if (er_throw && er_index < 0) throw std::runtime_error(std::string("[LibLCG] ") + text);
+	std::fprintf(stderr, "%s %s\n", er_index >= 0 ? "Success!" : (er_index == LCG_REACHED_MAX_ITERATIONS ? "Warning!" : "Fail!"), text);
+}
+void clcg_error_str(int er_index, bool er_throw)
+{
+	const char* text = code_text(er_index, true);
+	if (er_throw && er_index < 0) throw std::runtime_error(std::string("[LibLCG] ") + text);
+	std::fprintf(stderr, "%s %s\n", er_index >= 0 ? "Success!" : "Fail!", text);
+}
+
+// ------------------------------------------------------------------------------------ algebra.h host helpers
+lcg_float lcg_abs(lcg_float a) { return a >= 0.0 ? a : -a; }
+lcg_float lcg_max(lcg_float a, lcg_float b) { return a >= b ? a : b; }
+lcg_float lcg_min(lcg_float a, lcg_float b) { return a <= b ? a : b; }
+lcg_float lcg_set2box(lcg_float low, lcg_float hig, lcg_float a, bool low_bound, bool hig_bound)
+{	// algebra.cpp:50-58: closed bounds clamp onto the bound, open bounds stop a hair inside
+	if (hig_bound && a >= hig) return hig;
+	if (!hig_bound && a >= hig) return hig - 1e-16;
+	if (low_bound && a <= low) return low;
+	if (!low_bound && a <= low) return low + 1e-16;
+	return a;
+}
+lcg_float* lcg_malloc(int n) { return new lcg_float[n]; }
+lcg_float** lcg_malloc(int m, int n)
+{
+	lcg_float** x = new lcg_float*[m];
+	for (int i = 0; i < m; i++) x[i] = new lcg_float[n];
+	return x;
+}
+void lcg_free(lcg_float* x) { delete[] x; }
+void lcg_free(lcg_float** x, int m)
+{
+	if (!x) return;
+	for (int i = 0; i < m; i++) delete[] x[i];
+	delete[] x;
+}
+void lcg_vecset(lcg_float* a, lcg_float b, int size) { for (int i = 0; i < size; i++) a[i] = b; }
+void lcg_vecset(lcg_float** a, lcg_float b, int m, int n) { for (int i = 0; i < m; i++) lcg_vecset(a[i], b, n); }
+void lcg_vecrnd(lcg_float* a, lcg_float l, lcg_float h, int size)
+{	// algebra.cpp: seeded from the clock on every call, uniform in [l, h]
+	srand((unsigned)time(nullptr));
+	for (int i = 0; i < size; i++) a[i] = (h - l) * rand() / RAND_MAX + l;
+}
+void lcg_vecrnd(lcg_float** a, lcg_float l, lcg_float h, int m, int n)
+{
+	srand((unsigned)time(nullptr));
+	for (int i = 0; i < m; i++) for (int j = 0; j < n; j++) a[i][j] = (h - l) * rand() / RAND_MAX + l;
+}
+double lcg_squaredl2norm(lcg_float* a, int n) { double s = 0.0; for (int i = 0; i < n; i++) s += a[i] * a[i]; return s; }
+void lcg_dot(lcg_float& ret, const lcg_float* a, const lcg_float* b, int size)
+{	// algebra.cpp:154-163: left-to-right serial sum
+	ret = 0.0;
+	for (int i = 0; i < size; i++) ret += a[i] * b[i];
+}
+void lcg_matvec(lcg_float** A, const lcg_float* x, lcg_float* Ax, int m_size, int n_size, lcg_matrix_e layout)
+{
+	if (layout == MatNormal)
+		for (int i = 0; i < m_size; i++) { lcg_float s = 0.0; for (int j = 0; j < n_size; j++) s += A[i][j] * x[j]; Ax[i] = s; }
+	else
+		for (int j = 0; j < n_size; j++) { lcg_float s = 0.0; for (int i = 0; i < m_size; i++) s += A[i][j] * x[i]; Ax[j] = s; }
+}
+void lcg_matvec_coo(const int* row, const int* col, const lcg_float* Mat, const lcg_float* V, lcg_float* p, int M, int N, int nz_size, bool pre_position)
+{	// p = A V, or p = A^T V when pre_position
+	const int out = pre_position ? N : M;
+	for (int i = 0; i < out; i++) p[i] = 0.0;
+	if (pre_position) for (int k = 0; k < nz_size; k++) p[col[k]] += Mat[k] * V[row[k]];
+	else for (int k = 0; k < nz_size; k++) p[row[k]] += Mat[k] * V[col[k]];
+}
+
+// -------------------------------------------------------------------------------- lcg_complex.h host helpers
+lcg_complex* clcg_malloc(int n) { return new lcg_complex[n]; }
+lcg_complex** clcg_malloc(int m, int n)
+{
+	lcg_complex** x = new lcg_complex*[m];
+	for (int i = 0; i < m; i++) x[i] = new lcg_complex[n];
+	return x;
+}
+void clcg_free(lcg_complex* x) { delete[] x; }
+void clcg_free(lcg_complex** x, int m)
+{
+	if (!x) return;
+	for (int i = 0; i < m; i++) delete[] x[i];
+	delete[] x;
+}
+void clcg_vecset(lcg_complex* a, lcg_complex b, int size) { for (int i = 0; i < size; i++) a[i] = b; }
+void clcg_vecset(lcg_complex** a, lcg_complex b, int m, int n) { for (int i = 0; i < m; i++) clcg_vecset(a[i], b, n); }
+void clcg_set(lcg_complex* a, lcg_float r, lcg_float i) { *a = lcg_complex(r, i); }
+lcg_float clcg_square(const lcg_complex* a) { return std::norm(*a); }
+lcg_float clcg_module(const lcg_complex* a) { return std::sqrt(std::norm(*a)); }
+lcg_complex clcg_conjugate(const lcg_complex* a) { return std::conj(*a); }
+void clcg_vecrnd(lcg_complex* a, lcg_complex l, lcg_complex h, int size)
+{	// lcg_complex.cpp:118-127: one rand() per component, real first
+	srand((unsigned)time(nullptr));
+	for (int i = 0; i < size; i++)
+	{
+		const lcg_float re = (h.real() - l.real()) * rand() / RAND_MAX + l.real();
+		const lcg_float im = (h.imag() - l.imag()) * rand() / RAND_MAX + l.imag();
+		a[i] = lcg_complex(re, im);
+	}
+}
+void clcg_vecrnd(lcg_complex** a, lcg_complex l, lcg_complex h, int m, int n)
+{
+	srand((unsigned)time(nullptr));
+	for (int i = 0; i < m; i++)
+		for (int j = 0; j < n; j++)
+		{
+			const lcg_float re = (h.real() - l.real()) * rand() / RAND_MAX + l.real();
+			const lcg_float im = (h.imag() - l.imag()) * rand() / RAND_MAX + l.imag();
+			a[i][j] = lcg_complex(re, im);
+		}
+}
+void clcg_dot(lcg_complex& ret, const lcg_complex* a, const lcg_complex* b, int size)
+{	// unconjugated (lcg_complex.cpp:143-153)
+	ret = lcg_complex(0.0, 0.0);
+	for (int i = 0; i < size; i++) ret += a[i] * b[i];
+}
+void clcg_inner(lcg_complex& ret, const lcg_complex* a, const lcg_complex* b, int size)
+{	// conjugate of the FIRST argument (lcg_complex.cpp:155-167)
+	ret = lcg_complex(0.0, 0.0);
+	for (int i = 0; i < size; i++) ret += std::conj(a[i]) * b[i];
+}
+void clcg_matvec(lcg_complex** A, const lcg_complex* x, lcg_complex* Ax, int m_size, int n_size, lcg_matrix_e layout, clcg_complex_e conjugate)
+{
+	const bool cj = conjugate == Conjugate;
+	if (layout == MatNormal)
+		for (int i = 0; i < m_size; i++) { lcg_complex s(0.0, 0.0); for (int j = 0; j < n_size; j++) s += (cj ? std::conj(A[i][j]) : A[i][j]) * x[j]; Ax[i] = s; }
+	else
+		for (int j = 0; j < n_size; j++) { lcg_complex s(0.0, 0.0); for (int i = 0; i < m_size; i++) s += (cj ? std::conj(A[i][j]) : A[i][j]) * x[i]; Ax[j] = s; }
+}
+
+// --------------------------------------------------------------------------------------- host-callback solvers
+int lcg_solver(lcg_axfunc_ptr Afp, lcg_progress_ptr Pfp, lcg_float* m, const lcg_float* B, const int n_size, const lcg_para* param, void* instance,
+	lcg_solver_enum solver_id)
+{
+	return lcgb200_solver(Afp, reinterpret_cast<lcgb200_progress_ptr>(Pfp), m, B, n_size, P(param), instance, static_cast<int>(solver_id));
+}
+int lcg_solver_preconditioned(lcg_axfunc_ptr Afp, lcg_axfunc_ptr Mfp, lcg_progress_ptr Pfp, lcg_float* m, const lcg_float* B, const int n_size,
+	const lcg_para* param, void* instance, lcg_solver_enum solver_id)
+{
+	return lcgb200_solver_preconditioned(Afp, Mfp, reinterpret_cast<lcgb200_progress_ptr>(Pfp), m, B, n_size, P(param), instance, static_cast<int>(solver_id));
+}
+int lcg_solver_constrained(lcg_axfunc_ptr Afp, lcg_progress_ptr Pfp, lcg_float* m, const lcg_float* B, const lcg_float* low, const lcg_float* hig,
+	const int n_size, const lcg_para* param, void* instance, lcg_solver_enum solver_id)
+{
+	return lcgb200_solver_constrained(Afp, reinterpret_cast<lcgb200_progress_ptr>(Pfp), m, B, low, hig, n_size, P(param), instance, static_cast<int>(solver_id));
+}
+int lcg(lcg_axfunc_ptr Afp, lcg_progress_ptr Pfp, lcg_float* m, const lcg_float* B, const int n_size, const lcg_para* param, void* instance,
+	lcg_float* Gk, lcg_float* Dk, lcg_float* ADk)
+{
+	return lcgb200_lcg(Afp, reinterpret_cast<lcgb200_progress_ptr>(Pfp), m, B, n_size, P(param), instance, Gk, Dk, ADk);
+}
+int lcgs(lcg_axfunc_ptr Afp, lcg_progress_ptr Pfp, lcg_float* m, const lcg_float* B, const int n_size, const lcg_para* param, void* instance,
+	lcg_float* RK, lcg_float* R0T, lcg_float* PK, lcg_float* AX, lcg_float* UK, lcg_float* QK, lcg_float* WK)
+{
+	return lcgb200_lcgs(Afp, reinterpret_cast<lcgb200_progress_ptr>(Pfp), m, B, n_size, P(param), instance, RK, R0T, PK, AX, UK, QK, WK);
+}
+int clcg_solver(clcg_axfunc_ptr Afp, clcg_progress_ptr Pfp, lcg_complex* m, const lcg_complex* B, const int n_size, const clcg_para* param,
+	void* instance, clcg_solver_enum solver_id)
+{	// std::complex<double> is layout-compatible with interleaved (re, im); the enums travel as ints
+	return lcgb200_csolver(reinterpret_cast<lcgb200_caxfunc_ptr>(Afp), reinterpret_cast<lcgb200_cprogress_ptr>(Pfp), m, B, n_size, P(param), instance,
+		static_cast<int>(solver_id));
+}
+
+// ------------------------------------------------------------------------------------------- CUDA entry points
+int lcg_solver_cuda(lcg_axfunc_cuda_ptr Afp, lcg_progress_cuda_ptr Pfp, lcg_float* m, const lcg_float* B, const int n_size, const int nz_size,
+	const lcg_para* param, void* instance, cublasHandle_t cub_handle, cusparseHandle_t cus_handle, lcg_solver_enum solver_id)
+{
+	return lcgb200_solver_cuda(reinterpret_cast<lcgb200_axfunc_cuda_ptr>(Afp), reinterpret_cast<lcgb200_progress_cuda_ptr>(Pfp), m, B, n_size, nz_size,
+		P(param), instance, reinterpret_cast<lcgb200_cublas_t>(cub_handle), reinterpret_cast<lcgb200_cusparse_t>(cus_handle), static_cast<int>(solver_id));
+}
+int lcg_solver_preconditioned_cuda(lcg_axfunc_cuda_ptr Afp, lcg_axfunc_cuda_ptr Mfp, lcg_progress_cuda_ptr Pfp, lcg_float* m, const lcg_float* B,
+	const int n_size, const int nz_size, const lcg_para* param, void* instance, cublasHandle_t cub_handle, cusparseHandle_t cus_handle,
+	lcg_solver_enum solver_id)
+{
+	return lcgb200_solver_preconditioned_cuda(reinterpret_cast<lcgb200_axfunc_cuda_ptr>(Afp), reinterpret_cast<lcgb200_axfunc_cuda_ptr>(Mfp),
+		reinterpret_cast<lcgb200_progress_cuda_ptr>(Pfp), m, B, n_size, nz_size, P(param), instance, reinterpret_cast<lcgb200_cublas_t>(cub_handle),
+		reinterpret_cast<lcgb200_cusparse_t>(cus_handle), static_cast<int>(solver_id));
+}
+int lcg_solver_constrained_cuda(lcg_axfunc_cuda_ptr Afp, lcg_progress_cuda_ptr Pfp, lcg_float* m, const lcg_float* B, const lcg_float* low,
+	const lcg_float* hig, const int n_size, const int nz_size, const lcg_para* param, void* instance, cublasHandle_t cub_handle,
+	cusparseHandle_t cus_handle, lcg_solver_enum solver_id)
+{
+	return lcgb200_solver_constrained_cuda(reinterpret_cast<lcgb200_axfunc_cuda_ptr>(Afp), reinterpret_cast<lcgb200_progress_cuda_ptr>(Pfp), m, B, low, hig,
+		n_size, nz_size, P(param), instance, reinterpret_cast<lcgb200_cublas_t>(cub_handle), reinterpret_cast<lcgb200_cusparse_t>(cus_handle),
+		static_cast<int>(solver_id));
+}
+int clcg_solver_cuda(clcg_axfunc_cuda_ptr Afp, clcg_progress_cuda_ptr Pfp, cuDoubleComplex* m, const cuDoubleComplex* B, const int n_size,
+	const int nz_size, const clcg_para* param, void* instance, cublasHandle_t cub_handle, cusparseHandle_t cus_handle, clcg_solver_enum solver_id)
+{
+	return lcgb200_csolver_cuda(reinterpret_cast<lcgb200_caxfunc_cuda_ptr>(Afp), reinterpret_cast<lcgb200_cprogress_cuda_ptr>(Pfp), m, B, n_size, nz_size,
+		P(param), instance, reinterpret_cast<lcgb200_cublas_t>(cub_handle), reinterpret_cast<lcgb200_cusparse_t>(cus_handle), static_cast<int>(solver_id));
+}
+int clcg_solver_preconditioned_cuda(clcg_axfunc_cuda_ptr Afp, clcg_axfunc_cuda_ptr Mfp, clcg_progress_cuda_ptr Pfp, cuDoubleComplex* m,
+	const cuDoubleComplex* B, const int n_size, const int nz_size, const clcg_para* param, void* instance, cublasHandle_t cub_handle,
+	cusparseHandle_t cus_handle, clcg_solver_enum solver_id)
+{
+	return lcgb200_csolver_preconditioned_cuda(reinterpret_cast<lcgb200_caxfunc_cuda_ptr>(Afp), reinterpret_cast<lcgb200_caxfunc_cuda_ptr>(Mfp),
+		reinterpret_cast<lcgb200_cprogress_cuda_ptr>(Pfp), m, B, n_size, nz_size, P(param), instance, reinterpret_cast<lcgb200_cublas_t>(cub_handle),
+		reinterpret_cast<lcgb200_cusparse_t>(cus_handle), static_cast<int>(solver_id));
+}
+
+// ------------------------------------------------------------------------------------------- class wrappers
+// solver.cpp:29-283 / solver_cuda.cu:29-414.  Minimize* print the solver's name, run, print the elapsed time and report the
+// return code through lcg_error_str / clcg_error_str (which throws for a negative code when er_throw is set).
+namespace {
+const char* real_name(int id) { static const char* n[] = {"CG", "PCG", "CGS", "BICGSTAB", "BICGSTAB2", "PG", "SPG"}; return (id >= 0 && id < 7) ? n[id] : "Unknown"; }
+const char* cplx_name(int id) { static const char* n[] = {"BICG", "BICG_SYM", "CGS", "BICGSTAB", "TFQMR", "PCG", "PBICG"}; return (id >= 0 && id < 7) ? n[id] : "Unknown"; }
+
+int monitor(unsigned int inter, double converge, double epsilon, int k)
+{	// the default Progress of every wrapper class (solver.cpp:36-51)
+	if ((inter > 0 && k % inter == 0) || converge <= epsilon) std::clog << "\rIteration-times: " << k << "\tconvergence: " << converge;
+	return 0;
+}
+
+template <class Call>
+void minimize(bool silent, bool verbose, bool er_throw, bool cplx, const char* name, Call&& call)
+{
+	auto report = [&](int ret) { if (cplx) clcg_error_str(ret, er_throw); else lcg_error_str(ret, er_throw); };
+	if (silent)
+	{
+		const int ret = call(false);
+		if (ret < 0) report(ret);
+		return;
+	}
+	const auto t0 = std::chrono::steady_clock::now();
+	const int ret = call(true);
+	const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+	std::clog << std::endl << "Solver: " << name << ". Time cost: " << ms << " ms" << std::endl;
+	if (verbose || ret < 0) report(ret);
+}
+}  // namespace
+
+LCG_Solver::LCG_Solver() : param_(kDef), inter_(1), silent_(false) {}
+int LCG_Solver::Progress(const lcg_float*, const lcg_float converge, const lcg_para* param, const int, const int k) { return monitor(inter_, converge, param->epsilon, k); }
+void LCG_Solver::silent() { silent_ = true; }
+void LCG_Solver::set_report_interval(unsigned int inter) { inter_ = inter; }
+void LCG_Solver::set_lcg_parameter(const lcg_para& in_param) { param_ = in_param; }
+
+namespace {
+// the trampolines the reference keeps inline in its header (solver.h:52-75): the library needs its own to pass as callbacks
+struct LcgTramp {
+	static void ax(void* inst, const lcg_float* a, lcg_float* b, const int n) { static_cast<LCG_Solver*>(inst)->AxProduct(a, b, n); }
+	static void mx(void* inst, const lcg_float* a, lcg_float* b, const int n) { static_cast<LCG_Solver*>(inst)->MxProduct(a, b, n); }
+	static int pg(void* inst, const lcg_float* m, const lcg_float c, const lcg_para* p, const int n, const int k) { return static_cast<LCG_Solver*>(inst)->Progress(m, c, p, n, k); }
+};
+struct ClcgTramp {
+	static void ax(void* inst, const lcg_complex* x, lcg_complex* y, const int n, lcg_matrix_e l, clcg_complex_e c) { static_cast<CLCG_Solver*>(inst)->AxProduct(x, y, n, l, c); }
+	static int pg(void* inst, const lcg_complex* m, const lcg_float c, const clcg_para* p, const int n, const int k) { return static_cast<CLCG_Solver*>(inst)->Progress(m, c, p, n, k); }
+};
+struct LcgCudaTramp {
+	static void ax(void* inst, cublasHandle_t cb, cusparseHandle_t cs, cusparseDnVecDescr_t x, cusparseDnVecDescr_t y, const int n, const int nz)
+	{ static_cast<LCG_CUDA_Solver*>(inst)->AxProduct(cb, cs, x, y, n, nz); }
+	static void mx(void* inst, cublasHandle_t cb, cusparseHandle_t cs, cusparseDnVecDescr_t x, cusparseDnVecDescr_t y, const int n, const int nz)
+	{ static_cast<LCG_CUDA_Solver*>(inst)->MxProduct(cb, cs, x, y, n, nz); }   // the reference's own trampoline calls AxProduct here (solver_cuda.h:87-91)
+	static int pg(void* inst, const lcg_float* m, const lcg_float c, const lcg_para* p, const int n, const int nz, const int k)
+	{ return static_cast<LCG_CUDA_Solver*>(inst)->Progress(m, c, p, n, nz, k); }
+};
+struct ClcgCudaTramp {
+	static void ax(void* inst, cublasHandle_t cb, cusparseHandle_t cs, cusparseDnVecDescr_t x, cusparseDnVecDescr_t y, const int n, const int nz, cusparseOperation_t op)
+	{ static_cast<CLCG_CUDA_Solver*>(inst)->AxProduct(cb, cs, x, y, n, nz, op); }
+	static void mx(void* inst, cublasHandle_t cb, cusparseHandle_t cs, cusparseDnVecDescr_t x, cusparseDnVecDescr_t y, const int n, const int nz, cusparseOperation_t op)
+	{ static_cast<CLCG_CUDA_Solver*>(inst)->MxProduct(cb, cs, x, y, n, nz, op); }
+	static int pg(void* inst, const cuDoubleComplex* m, const lcg_float c, const clcg_para* p, const int n, const int nz, const int k)
+	{ return static_cast<CLCG_CUDA_Solver*>(inst)->Progress(m, c, p, n, nz, k); }
+};
+}  // namespace
+
+void LCG_Solver::Minimize(lcg_float* m, const lcg_float* b, int x_size, lcg_solver_enum solver_id, bool verbose, bool er_throw)
+{
+	minimize(silent_, verbose, er_throw, false, real_name(solver_id), [&](bool mon) {
+		return lcg_solver(LcgTramp::ax, mon ? LcgTramp::pg : nullptr, m, b, x_size, &param_, this, solver_id); });
+}
+void LCG_Solver::MinimizePreconditioned(lcg_float* m, const lcg_float* b, int x_size, lcg_solver_enum solver_id, bool verbose, bool er_throw)
+{
+	minimize(silent_, verbose, er_throw, false, real_name(LCG_PCG), [&](bool mon) {
+		return lcg_solver_preconditioned(LcgTramp::ax, LcgTramp::mx, mon ? LcgTramp::pg : nullptr, m, b, x_size, &param_, this, solver_id); });
+}
+void LCG_Solver::MinimizeConstrained(lcg_float* m, const lcg_float* b, const lcg_float* low, const lcg_float* hig, int x_size, lcg_solver_enum solver_id,
+	bool verbose, bool er_throw)
+{
+	minimize(silent_, verbose, er_throw, false, real_name(solver_id), [&](bool mon) {
+		return lcg_solver_constrained(LcgTramp::ax, mon ? LcgTramp::pg : nullptr, m, b, low, hig, x_size, &param_, this, solver_id); });
+}
+
+CLCG_Solver::CLCG_Solver() : param_(kDefC), inter_(1), silent_(false) {}
+int CLCG_Solver::Progress(const lcg_complex*, const lcg_float converge, const clcg_para* param, const int, const int k) { return monitor(inter_, converge, param->epsilon, k); }
+void CLCG_Solver::silent() { silent_ = true; }
+void CLCG_Solver::set_report_interval(unsigned int inter) { inter_ = inter; }
+void CLCG_Solver::set_clcg_parameter(const clcg_para& in_param) { param_ = in_param; }
+void CLCG_Solver::Minimize(lcg_complex* m, const lcg_complex* b, int x_size, clcg_solver_enum solver_id, bool verbose, bool er_throw)
+{
+	minimize(silent_, verbose, er_throw, true, cplx_name(solver_id), [&](bool mon) {
+		return clcg_solver(ClcgTramp::ax, mon ? ClcgTramp::pg : nullptr, m, b, x_size, &param_, this, solver_id); });
+}
+
+LCG_CUDA_Solver::LCG_CUDA_Solver() : param_(kDef), inter_(1), silent_(false) {}
+int LCG_CUDA_Solver::Progress(const lcg_float*, const lcg_float converge, const lcg_para* param, const int, const int, const int k)
+{ return monitor(inter_, converge, param->epsilon, k); }
+void LCG_CUDA_Solver::silent() { silent_ = true; }
+void LCG_CUDA_Solver::set_report_interval(unsigned int inter) { inter_ = inter; }
+void LCG_CUDA_Solver::set_lcg_parameter(const lcg_para& in_param) { param_ = in_param; }
+void LCG_CUDA_Solver::Minimize(cublasHandle_t cub_handle, cusparseHandle_t cus_handle, lcg_float* x, lcg_float* b, const int n_size, const int nz_size,
+	lcg_solver_enum solver_id, bool verbose, bool er_throw)
+{
+	minimize(silent_, verbose, er_throw, false, real_name(solver_id), [&](bool mon) {
+		return lcg_solver_cuda(LcgCudaTramp::ax, mon ? LcgCudaTramp::pg : nullptr, x, b, n_size, nz_size, &param_, this, cub_handle, cus_handle, solver_id); });
+}
+void LCG_CUDA_Solver::MinimizePreconditioned(cublasHandle_t cub_handle, cusparseHandle_t cus_handle, lcg_float* x, lcg_float* b, const int n_size,
+	const int nz_size, lcg_solver_enum solver_id, bool verbose, bool er_throw)
+{
+	minimize(silent_, verbose, er_throw, false, real_name(LCG_PCG), [&](bool mon) {
+		return lcg_solver_preconditioned_cuda(LcgCudaTramp::ax, LcgCudaTramp::mx, mon ? LcgCudaTramp::pg : nullptr, x, b, n_size, nz_size, &param_, this,
+			cub_handle, cus_handle, solver_id); });
+}
+void LCG_CUDA_Solver::MinimizeConstrained(cublasHandle_t cub_handle, cusparseHandle_t cus_handle, lcg_float* x, const lcg_float* b, const lcg_float* low,
+	const lcg_float* hig, const int n_size, const int nz_size, lcg_solver_enum solver_id, bool verbose, bool er_throw)
+{
+	minimize(silent_, verbose, er_throw, false, real_name(solver_id), [&](bool mon) {
+		return lcg_solver_constrained_cuda(LcgCudaTramp::ax, mon ? LcgCudaTramp::pg : nullptr, x, b, low, hig, n_size, nz_size, &param_, this, cub_handle,
+			cus_handle, solver_id); });
+}
+
+CLCG_CUDA_Solver::CLCG_CUDA_Solver() : param_(kDefC), inter_(1), silent_(false) {}
+int CLCG_CUDA_Solver::Progress(const cuDoubleComplex*, const lcg_float converge, const clcg_para* param, const int, const int, const int k)
+{ return monitor(inter_, converge, param->epsilon, k); }
+void CLCG_CUDA_Solver::silent() { silent_ = true; }
+void CLCG_CUDA_Solver::set_report_interval(unsigned int inter) { inter_ = inter; }
+void CLCG_CUDA_Solver::set_clcg_parameter(const clcg_para& in_param) { param_ = in_param; }
+void CLCG_CUDA_Solver::Minimize(cublasHandle_t cub_handle, cusparseHandle_t cus_handle, cuDoubleComplex* x, cuDoubleComplex* b, const int n_size,
+	const int nz_size, clcg_solver_enum solver_id, bool verbose, bool er_throw)
+{
+	minimize(silent_, verbose, er_throw, true, cplx_name(solver_id), [&](bool mon) {
+		return clcg_solver_cuda(ClcgCudaTramp::ax, mon ? ClcgCudaTramp::pg : nullptr, x, b, n_size, nz_size, &param_, this, cub_handle, cus_handle, solver_id); });
+}
+void CLCG_CUDA_Solver::MinimizePreconditioned(cublasHandle_t cub_handle, cusparseHandle_t cus_handle, cuDoubleComplex* x, cuDoubleComplex* b,
+	const int n_size, const int nz_size, clcg_solver_enum solver_id, bool verbose, bool er_throw)
+{
+	minimize(silent_, verbose, er_throw, true, cplx_name(CLCG_PCG), [&](bool mon) {
+		return clcg_solver_preconditioned_cuda(ClcgCudaTramp::ax, ClcgCudaTramp::mx, mon ? ClcgCudaTramp::pg : nullptr, x, b, n_size, nz_size, &param_, this,
+			cub_handle, cus_handle, solver_id); });
+}

@@ -257,7 +257,8 @@ int Engine::run(const std::function<bool()>& iterate, const std::function<void(i
 	// pre-resolved dependencies, which matters when an iteration lasts tens of microseconds (mid-size systems, the
 	// per-GPU slabs of a partitioned solve).  The first batch runs uncaptured so that one-time launch set-up is done.
 	GraphGuard gg;
-	const bool want_graph = !batch && capturable && !profiling && (!multi() || p2p()) && use_graphs(n_local);
+	// (the legacy default stream cannot be captured: the API layer moves built-in-operator solves to a stream of the handle)
+	const bool want_graph = !batch && capturable && !profiling && (!multi() || p2p()) && stream != nullptr && stream != cudaStreamLegacy && use_graphs(n_local);
 	int batches = 0, per_batch_launches = 0, per_batch_spmv = 0;
 	while (true)
 	{
@@ -271,9 +272,12 @@ int Engine::run(const std::function<bool()>& iterate, const std::function<void(i
 		else if (want_graph && batches == 1)
 		{
 			const int l0 = launches, s0 = spmv_launches;
-			LCG_CUDA_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-			for (int i = 0; i < poll; i++) iterate();
-			cudaError_t ce = cudaStreamEndCapture(stream, &gg.graph);
+			cudaError_t ce = cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal);
+			if (ce == cudaSuccess)
+			{
+				for (int i = 0; i < poll; i++) iterate();
+				ce = cudaStreamEndCapture(stream, &gg.graph);
+			}
 			if (ce == cudaSuccess && gg.graph) ce = cudaGraphInstantiate(&gg.exec, gg.graph, 0);
 			if (ce != cudaSuccess || !gg.exec)
 			{	// capture refused (e.g. a user stream in a state that forbids it): forget it and carry on with plain launches

@@ -61,6 +61,9 @@ struct CsrHandle {
 	void* ws = nullptr; size_t ws_bytes = 0;
 	DevState* d_state = nullptr; DevState* h_state = nullptr; DevState* h_state2 = nullptr; double* d_partials = nullptr;
 	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+	// solves on the built-in operator that were handed the legacy default stream run on this stream instead (ordered after
+	// the caller's stream by an event; the entry points are host-synchronous): a private stream can be captured into CUDA graphs
+	cudaStream_t own_stream = nullptr; cudaEvent_t own_event = nullptr;
 
 	CommDev* p2p_dev() const { return comm ? comm->dev() : nullptr; }
 	// NVLink transport with the receive half of the halo exchange inside k_spmv (boundary tiles wait for the neighbours'
@@ -141,11 +144,12 @@ public:
 	~Engine();
 
 	void reserve(size_t bytes);
+	std::vector<void*> allocs;     // every vector handed out, in order (lcg()/lcgs() copy their work vectors back to the caller)
 	template <class T> T* alloc(size_t count)
 	{
 		size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
 		if (ws_off + bytes > ws_cap) { set_error_msg("workspace overflow"); throw CudaFailure(); }
-		T* p = reinterpret_cast<T*>(ws + ws_off); ws_off += bytes; return p;
+		T* p = reinterpret_cast<T*>(ws + ws_off); ws_off += bytes; allocs.push_back(p); return p;
 	}
 
 	void start(const DevState& init);   // upload the initial state, record the start event

@@ -8,6 +8,7 @@
 //        -L liblcg_b200 -llcgb200 -lcusparse -lcublas -Xlinker -rpath=$PWD/liblcg_b200 -o dropin_sample
 //   ./dropin_sample tests/golden/data/case_10K_A tests/golden/data/case_10K_B
 #include <cmath>
+#include <complex>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -90,6 +91,109 @@ public:
 	}
 	void MxProduct(const lcg_float* r, lcg_float* z, const int n) override { for (int i = 0; i < n; i++) z[i] = r[i] / (*dg)[(size_t)i]; mx_calls++; }
 };
+
+// ---- complex (clcg) class wrappers: solver_cuda.h:380-541 and solver.h:182-283 ------------------------------------------------
+struct CUserSystem { int n = 0, nnz = 0; cusparseSpMatDescr_t A = nullptr; void* buf = nullptr; size_t cap = 0; int calls[3] = {0, 0, 0}; };
+
+class CUserSolver : public CLCG_CUDA_Solver
+{
+public:
+	CUserSystem* sys = nullptr;
+	void AxProduct(cublasHandle_t, cusparseHandle_t cus, cusparseDnVecDescr_t x, cusparseDnVecDescr_t Ax, const int, const int, cusparseOperation_t op) override
+	{
+		const cuDoubleComplex one = make_cuDoubleComplex(1.0, 0.0), zero = make_cuDoubleComplex(0.0, 0.0);
+		size_t need = 0;
+		cusparseSpMV_bufferSize(cus, op, &one, sys->A, x, &zero, Ax, CUDA_C_64F, CUSPARSE_SPMV_ALG_DEFAULT, &need);
+		if (need > sys->cap) { cudaFree(sys->buf); cudaMalloc(&sys->buf, need); sys->cap = need; }
+		cusparseSpMV(cus, op, &one, sys->A, x, &zero, Ax, CUDA_C_64F, CUSPARSE_SPMV_ALG_DEFAULT, sys->buf);
+		sys->calls[(int)op]++;
+	}
+	void MxProduct(cublasHandle_t, cusparseHandle_t, cusparseDnVecDescr_t, cusparseDnVecDescr_t, const int, const int, cusparseOperation_t) override {}
+};
+
+class CHostSolver : public CLCG_Solver
+{
+public:
+	const std::vector<int>* rp = nullptr; const std::vector<int>* ci = nullptr; const std::vector<lcg_complex>* va = nullptr;
+	int calls = 0;
+	void AxProduct(const lcg_complex* x, lcg_complex* y, const int n, lcg_matrix_e layout, clcg_complex_e conj) override
+	{
+		for (int i = 0; i < n; i++) y[i] = lcg_complex(0.0, 0.0);
+		for (int i = 0; i < n; i++)
+			for (int k = (*rp)[(size_t)i]; k < (*rp)[(size_t)i + 1]; k++)
+			{
+				const lcg_complex a = conj == Conjugate ? std::conj((*va)[(size_t)k]) : (*va)[(size_t)k];
+				if (layout == MatNormal) y[i] += a * x[(*ci)[(size_t)k]]; else y[(*ci)[(size_t)k]] += a * x[i];
+			}
+		calls++;
+	}
+};
+
+static int complex_wrappers(const char* path_a, const char* path_b, cublasHandle_t cub, cusparseHandle_t cus)
+{
+	FILE* fa = std::fopen(path_a, "rb"); FILE* fb = std::fopen(path_b, "rb");
+	if (!fa || !fb) { std::fprintf(stderr, "cannot open the complex fixture\n"); return 1; }
+	int n = 0, nz = 0, nb = 0;
+	if (std::fread(&n, 4, 1, fa) != 1 || std::fread(&nz, 4, 1, fa) != 1) return 1;
+	std::vector<int> r((size_t)nz), c((size_t)nz); std::vector<lcg_complex> v((size_t)nz), b((size_t)n), ans((size_t)n);
+	for (int k = 0; k < nz; k++) if (std::fread(&r[(size_t)k], 4, 1, fa) != 1 || std::fread(&c[(size_t)k], 4, 1, fa) != 1 || std::fread(&v[(size_t)k], 16, 1, fa) != 1) return 1;
+	if (std::fread(b.data(), 16, (size_t)n, fa) != (size_t)n) return 1;
+	if (std::fread(&nb, 4, 1, fb) != 1 || nb != n || std::fread(ans.data(), 16, (size_t)n, fb) != (size_t)n) return 1;
+	std::fclose(fa); std::fclose(fb);
+	std::vector<int> rp((size_t)n + 1, 0), ci((size_t)nz); std::vector<lcg_complex> va((size_t)nz);
+	for (int k = 0; k < nz; k++) rp[(size_t)r[(size_t)k] + 1]++;
+	for (int i = 0; i < n; i++) rp[(size_t)i + 1] += rp[(size_t)i];
+	{ std::vector<int> fill(rp.begin(), rp.end() - 1); for (int k = 0; k < nz; k++) { int d = fill[(size_t)r[(size_t)k]]++; ci[(size_t)d] = c[(size_t)k]; va[(size_t)d] = v[(size_t)k]; } }
+	auto cerr = [&](const lcg_complex* x) { double s = 0.0; for (int i = 0; i < n; i++) s += std::norm(x[i] - ans[(size_t)i]); return std::sqrt(s) / (double)n; };
+
+	int fails = 0;
+	CUserSystem sys; sys.n = n; sys.nnz = nz;
+	int *d_rp, *d_ci; cuDoubleComplex* d_v;
+	cudaMalloc((void**)&d_rp, sizeof(int) * (n + 1)); cudaMalloc((void**)&d_ci, sizeof(int) * nz); cudaMalloc((void**)&d_v, sizeof(cuDoubleComplex) * nz);
+	cudaMemcpy(d_rp, rp.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice); cudaMemcpy(d_ci, ci.data(), sizeof(int) * nz, cudaMemcpyHostToDevice);
+	cudaMemcpy(d_v, va.data(), sizeof(cuDoubleComplex) * nz, cudaMemcpyHostToDevice);
+	cusparseCreateCsr(&sys.A, n, n, nz, d_rp, d_ci, d_v, CUSPARSE_INDEX_32I, CUSPARSE_INDEX_32I, CUSPARSE_INDEX_BASE_ZERO, CUDA_C_64F);
+	lcgb200_csr_t builtin = nullptr;
+	if (lcgb200_csr_create(&builtin, n, nz, rp.data(), ci.data(), va.data(), LCGB200_COMPLEX, LCGB200_HOST, LCGB200_CSR_TRANSPOSE | LCGB200_CSR_JACOBI) != 0) return 1;
+	clcg_para cp = clcg_default_parameters();
+	cp.abs_diff = 1;   // sample6.cpp:162-196 setting
+	CUserSolver slv; slv.sys = &sys; slv.set_clcg_parameter(cp); slv.silent();
+	std::vector<cuDoubleComplex> m((size_t)n);
+	for (int path = 0; path < 2; path++)
+	{
+		slv.use_builtin_operator(path == 1 ? builtin : nullptr);
+		for (auto& z : m) z = make_cuDoubleComplex(0.0, 0.0);
+		sys.calls[0] = sys.calls[1] = sys.calls[2] = 0;
+		slv.Minimize(cub, cus, m.data(), reinterpret_cast<cuDoubleComplex*>(b.data()), n, nz, CLCG_BICG);
+		const double e = cerr(reinterpret_cast<const lcg_complex*>(m.data()));
+		std::printf("class CLCG_CUDA_Solver BICG %-26s A-calls %d A^H-calls %d avg-error %.3e\n", path == 0 ? "virtual AxProduct" : "built-in fused operator",
+			sys.calls[0], sys.calls[2], e);
+		if (!(e < 1e-4)) fails++;
+		if (path == 0 && (sys.calls[0] < 100 || sys.calls[2] < 100)) fails++;   // A d1 and A^H d2 every iteration (clcg.cpp:170,188)
+		if (path == 1 && (sys.calls[0] || sys.calls[2])) fails++;
+	}
+	slv.use_builtin_operator(builtin);
+	for (auto& z : m) z = make_cuDoubleComplex(0.0, 0.0);
+	slv.MinimizePreconditioned(cub, cus, m.data(), reinterpret_cast<cuDoubleComplex*>(b.data()), n, nz, CLCG_PCG);
+	if (!(cerr(reinterpret_cast<const lcg_complex*>(m.data())) < 1e-4)) fails++;
+	// host-callback CLCG_Solver: (layout, conjugate) callback on the generic path, then the built-in operator
+	CHostSolver hs; hs.rp = &rp; hs.ci = &ci; hs.va = &va; hs.set_clcg_parameter(cp); hs.silent();
+	std::vector<lcg_complex> mh((size_t)n);
+	for (int path = 0; path < 2; path++)
+	{
+		hs.use_builtin_operator(path == 1 ? builtin : nullptr);
+		for (auto& z : mh) z = lcg_complex(0.0, 0.0);
+		hs.calls = 0;
+		hs.Minimize(mh.data(), b.data(), n, CLCG_BICG_SYM);
+		const double e = cerr(mh.data());
+		std::printf("class CLCG_Solver BICG_SYM %-27s host Ax calls %d avg-error %.3e\n", path == 0 ? "host callback" : "built-in fused operator", hs.calls, e);
+		if (!(e < 1e-4)) fails++;
+		if (path == 1 && hs.calls != 0) fails++;
+	}
+	lcgb200_csr_destroy(builtin);
+	cusparseDestroySpMat(sys.A); cudaFree(sys.buf); cudaFree(d_rp); cudaFree(d_ci); cudaFree(d_v);
+	return fails;
+}
 
 static double avg_error(const std::vector<double>& x, const std::vector<double>& ans)
 {	// the samples' metric: sqrt(sum |x - ans|^2) / N (sample8.cu:66-74)
@@ -218,6 +322,9 @@ int main(int argc, char** argv)
 		if (lcg_solver_cuda(user_ax, nullptr, m.data(), b.data(), n, nz, &para, &sys, nullptr, cus) != LCG_INVALID_POINTER) fails++;
 		if (lcg_solver_cuda(user_ax, nullptr, m.data(), b.data(), 0, nz, &para, &sys, cub, cus) != LCG_INVILAD_VARIABLE_SIZE) fails++;
 	}
+	// complex class wrappers on data/case_10K_cA (configs[1]): CLCG_CUDA_Solver with the caller's cusparseSpMV honouring oper_t
+	// (generic path) and on the built-in operator (BiCG needs the stored transpose), then the host-callback CLCG_Solver
+	if (argc >= 5) fails += complex_wrappers(argv[3], argv[4], cub, cus);
 	lcgb200_csr_destroy(builtin);
 	cusparseDestroySpMat(sys.A); cudaFree(sys.d_rp); cudaFree(sys.d_ci); cudaFree(sys.d_v); cudaFree(sys.d_diag); cudaFree(sys.buf);
 	cublasDestroy(cub); cusparseDestroy(cus);

@@ -192,3 +192,46 @@ def test_bench_reference_arm_contract():
     r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "pcg27_64", "--steps", "1", "--warmup", "0"],
                        capture_output=True, text=True, timeout=600, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_dropin_library_exports_liblcg_cxx_symbols():
+    """liblcg_dropin.so defines liblcg's OWN C++ symbols out of line (the mangled names a program built against the reference's
+    headers references: entry points, lcg()/lcgs(), util / algebra helpers, the out-of-line members and vtables of the four
+    wrapper classes), so an existing binary can be re-linked against it.  Checked through the dynamic symbol table (no GPU)."""
+    import subprocess
+    so = os.path.join(ROOT, "liblcg_b200", "liblcg_dropin.so")
+    assert os.path.exists(so), "liblcg_dropin.so is missing: run __graft_entry__.build()"
+    out = subprocess.run(["nm", "-DC", "--defined-only", so], capture_output=True, text=True, check=True).stdout
+    defined = {l.split(" ", 2)[2] for l in out.splitlines() if len(l.split(" ", 2)) == 3}
+    para, cpara = "lcg_para const*", "clcg_para const*"
+    ax = "void (*)(void*, double const*, double*, int)"
+    pf = f"int (*)(void*, double const*, double, {para}, int, int)"
+    cax = "void (*)(void*, cublasContext*, cusparseContext*, cusparseDnVecDescr*, cusparseDnVecDescr*, int, int)"
+    cpf = f"int (*)(void*, double const*, double, {para}, int, int, int)"
+    zax = "void (*)(void*, cublasContext*, cusparseContext*, cusparseDnVecDescr*, cusparseDnVecDescr*, int, int, cusparseOperation_t)"
+    zpf = f"int (*)(void*, double2 const*, double, {cpara}, int, int, int)"
+    hz = "std::complex<double>"
+    must = [
+        f"lcg_solver({ax}, {pf}, double*, double const*, int, {para}, void*, lcg_solver_enum)",
+        f"lcg_solver_preconditioned({ax}, {ax}, {pf}, double*, double const*, int, {para}, void*, lcg_solver_enum)",
+        f"lcg_solver_constrained({ax}, {pf}, double*, double const*, double const*, double const*, int, {para}, void*, lcg_solver_enum)",
+        f"lcg({ax}, {pf}, double*, double const*, int, {para}, void*, double*, double*, double*)",
+        f"lcgs({ax}, {pf}, double*, double const*, int, {para}, void*, double*, double*, double*, double*, double*, double*, double*)",
+        f"clcg_solver(void (*)(void*, {hz} const*, {hz}*, int, lcg_matrix_e, clcg_complex_e), int (*)(void*, {hz} const*, double, {cpara}, int, int), "
+        f"{hz}*, {hz} const*, int, {cpara}, void*, clcg_solver_enum)",
+        f"lcg_solver_cuda({cax}, {cpf}, double*, double const*, int, int, {para}, void*, cublasContext*, cusparseContext*, lcg_solver_enum)",
+        f"lcg_solver_preconditioned_cuda({cax}, {cax}, {cpf}, double*, double const*, int, int, {para}, void*, cublasContext*, cusparseContext*, lcg_solver_enum)",
+        f"lcg_solver_constrained_cuda({cax}, {cpf}, double*, double const*, double const*, double const*, int, int, {para}, void*, cublasContext*, "
+        "cusparseContext*, lcg_solver_enum)",
+        f"clcg_solver_cuda({zax}, {zpf}, double2*, double2 const*, int, int, {cpara}, void*, cublasContext*, cusparseContext*, clcg_solver_enum)",
+        f"clcg_solver_preconditioned_cuda({zax}, {zax}, {zpf}, double2*, double2 const*, int, int, {cpara}, void*, cublasContext*, cusparseContext*, clcg_solver_enum)",
+        "lcg_default_parameters()", "clcg_default_parameters()", "lcg_error_str(int, bool)", "clcg_error_str(int, bool)",
+        "lcg_malloc(int)", "lcg_free(double*)", "lcg_vecset(double*, double, int)", "lcg_dot(double&, double const*, double const*, int)",
+        "clcg_malloc(int)", "clcg_inner(std::complex<double>&, std::complex<double> const*, std::complex<double> const*, int)",
+        "LCG_Solver::LCG_Solver()", "LCG_Solver::Minimize(double*, double const*, int, lcg_solver_enum, bool, bool)",
+        "CLCG_Solver::Minimize(std::complex<double>*, std::complex<double> const*, int, clcg_solver_enum, bool, bool)",
+        "LCG_CUDA_Solver::MinimizePreconditioned(cublasContext*, cusparseContext*, double*, double*, int, int, lcg_solver_enum, bool, bool)",
+        "CLCG_CUDA_Solver::Minimize(cublasContext*, cusparseContext*, double2*, double2*, int, int, clcg_solver_enum, bool, bool)",
+    ]
+    missing = [m for m in must if m not in defined]
+    assert not missing, missing

@@ -601,8 +601,27 @@ def test_cxx_dropin_sample_runs(torch_cuda):
     if not os.path.exists(exe):
         assert subprocess.run(["make", "-C", os.path.join(root, "tests", "cxx")]).returncode == 0
     data = os.path.join(root, "tests", "golden", "data")
-    r = subprocess.run([exe, os.path.join(data, "case_10K_A"), os.path.join(data, "case_10K_B")], capture_output=True, text=True, timeout=300)
+    r = subprocess.run([exe, os.path.join(data, "case_10K_A"), os.path.join(data, "case_10K_B"), os.path.join(data, "case_10K_cA"),
+                        os.path.join(data, "case_10K_cB")], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "dropin_sample: ok" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "class CLCG_CUDA_Solver BICG" in r.stdout and "class CLCG_Solver BICG_SYM" in r.stdout
+
+
+def test_program_built_against_reference_headers_runs_on_dropin_library(torch_cuda):
+    """tests/cxx/ref_header_sample.cu is compiled against the REFERENCE'S OWN headers (lcg.h, clcg.h, lcg_cuda.h, clcg_cuda.h,
+    solver.h, solver_cuda.h; built where the reference tree exists, the binary travels) and linked against liblcg_dropin.so: every
+    reference symbol it uses — entry points, lcg()/lcgs() with caller-owned work vectors, the four wrapper classes, the algebra
+    helpers — resolves in our library and behaves as documented."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cxx", "build", "ref_header_sample")
+    if not os.path.exists(exe):
+        pytest.skip("tests/cxx/build/ref_header_sample is built only where the reference headers exist")
+    data = os.path.join(root, "tests", "golden", "data")
+    r = subprocess.run([exe] + [os.path.join(data, f) for f in ("case_10K_A", "case_10K_B", "case_1K_cA", "case_1K_cB")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ref_header_sample: ok" in r.stdout, r.stdout[-4000:] + r.stderr[-2000:]
 
 
 def test_data_step_coo_to_csr_on_device(torch_cuda, port, fixtures):
