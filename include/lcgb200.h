@@ -167,6 +167,13 @@ int lcgb200_comm_stats(lcgb200_comm_t comm, int* halo_exchanges, int* allreduces
 int lcgb200_csr_set_partition(lcgb200_csr_t A, lcgb200_comm_t comm, long long n_global, int n_peers, const int* peer_ranks,
 	const int* send_counts, const int* send_idx, const int* recv_counts);
 
+/* Partitioned complex systems.  (1) clcg BiCG multiplies by A^H (clcg.cpp:188): build the rows [r0, r1) of A^T (values NOT
+ * conjugated) as a second rectangular handle with its own communicator and partition, and attach it; A does not own At.
+ * (2) The random shadow residual of complex CGS/BICGSTAB/TFQMR is ONE rand() sequence over the whole vector
+ * (lcg_complex.cpp:118-127): tell the block where it starts so that every rank draws its slice of that sequence. */
+int lcgb200_csr_attach_transpose(lcgb200_csr_t A, lcgb200_csr_t At);
+int lcgb200_csr_set_row_offset(lcgb200_csr_t A, long long first_global_row);
+
 /* NVLink peer-memory transport (optional, ranks on one NVLink/NVSwitch node): every rank exports the CUDA-IPC handle of
  * its communication window after lcgb200_csr_set_partition, the handles are exchanged by the caller (all-gather), and
  * lcgb200_comm_p2p_attach maps the peers' windows.  From then on real solves push halo entries and reduction totals

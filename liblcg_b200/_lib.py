@@ -63,6 +63,8 @@ SYMBOLS = {
     "lcgb200_comm_destroy": (_I, [_VP]),
     "lcgb200_comm_stats": (_I, [_VP, C.POINTER(_I), C.POINTER(_I)]),
     "lcgb200_csr_set_partition": (_I, [_VP, _VP, _LL, _I, _VP, _VP, _VP, _VP]),
+    "lcgb200_csr_attach_transpose": (_I, [_VP, _VP]),
+    "lcgb200_csr_set_row_offset": (_I, [_VP, _LL]),
     "lcgb200_comm_p2p_handle": (_I, [_VP, _VP, C.POINTER(_LL)]),
     "lcgb200_comm_p2p_attach": (_I, [_VP, _VP, _VP, _VP]),
     "lcgb200_comm_p2p_detach": (_I, [_VP]),

@@ -687,6 +687,24 @@ int lcgb200_csr_set_user(lcgb200_csr_t A, void* user)
 	reinterpret_cast<CsrHandle*>(A)->user = user; return 0;
 }
 
+int lcgb200_csr_attach_transpose(lcgb200_csr_t A, lcgb200_csr_t At)
+{
+	CsrHandle* h = reinterpret_cast<CsrHandle*>(A);
+	CsrHandle* t = reinterpret_cast<CsrHandle*>(At);
+	if (!h) return LCGB200_INVALID_POINTER;
+	if (t && (t->value_type != h->value_type || t->n_rows != h->n_rows)) { set_error_msg("the transposed block must hold the same rows [r0, r1) and value type"); return LCGB200_SIZE_NOT_MATCH; }
+	h->t_handle = t;
+	return 0;
+}
+
+int lcgb200_csr_set_row_offset(lcgb200_csr_t A, long long first_global_row)
+{
+	CsrHandle* h = reinterpret_cast<CsrHandle*>(A);
+	if (!h || first_global_row < 0) return LCGB200_INVALID_POINTER;
+	h->row_offset = first_global_row;
+	return 0;
+}
+
 int lcgb200_csr_get_diagonal(lcgb200_csr_t A, void* diag_host)
 {
 	CsrHandle* h = reinterpret_cast<CsrHandle*>(A);
@@ -856,13 +874,12 @@ int lcgb200_csolve(lcgb200_csr_t Ah, int solver_id, void* m, const void* B, cons
 	if (solver_id < LCGB200_CBICG || solver_id > LCGB200_CPCG) solver_id = LCGB200_CCGS;	// clcg.cpp:68-70
 	int rc = check_cplx(h->n_rows, para, m, B);
 	if (rc) return rc;
-	if (solver_id == LCGB200_CBICG && !h->t_row_ptr) { set_error_msg("CLCG_BICG needs the transposed operator: create the handle with LCGB200_CSR_TRANSPOSE"); return LCGB200_C_UNKNOWN_SOLVER; }
-	if (solver_id == LCGB200_CPCG && !((flags & LCGB200_USE_JACOBI) && h->diag)) return LCGB200_NULL_PRECONDITION_MATRIX;
-	if (h->comm && h->comm->size() > 1 && (solver_id == LCGB200_CCGS || solver_id == LCGB200_CBICGSTAB || solver_id == LCGB200_CTFQMR))
-	{	// their shadow residual is ONE rand() sequence over the whole vector (lcg_complex.cpp:118-127)
-		set_error_msg("complex CGS/BICGSTAB/TFQMR are single-GPU: the reference's random shadow residual is one host rand() sequence");
+	if (solver_id == LCGB200_CBICG && !h->t_row_ptr && !h->t_handle)
+	{
+		set_error_msg("CLCG_BICG needs the transposed operator: create the handle with LCGB200_CSR_TRANSPOSE (a partitioned block: lcgb200_csr_attach_transpose)");
 		return LCGB200_C_UNKNOWN_SOLVER;
 	}
+	if (solver_id == LCGB200_CPCG && !((flags & LCGB200_USE_JACOBI) && h->diag)) return LCGB200_NULL_PRECONDITION_MATRIX;
 	return guarded([&]() {
 		Operator<double2> A; A.h = h;
 		if (solver_id == LCGB200_CPCG) A.diag = (const double2*)h->diag;
@@ -870,7 +887,8 @@ int lcgb200_csolve(lcgb200_csr_t Ah, int solver_id, void* m, const void* B, cons
 			if (!Pfp) return ProgressFn();
 			return [=](double res, int k) { return Pfp(h->user, m_dev, res, &para, h->n_rows, h->nnz, k); };
 		};
-		return do_solve_cplx(h, A, solver_id, (double2*)m, (const double2*)B, para, h->n_rows, h->n_cols, h->n_global, make_pf,
+		const int n_ext = std::max(h->n_cols, h->t_handle ? h->t_handle->n_cols : 0);
+		return do_solve_cplx(h, A, solver_id, (double2*)m, (const double2*)B, para, h->n_rows, n_ext, h->n_global, make_pf,
 			(flags & LCGB200_VEC_DEVICE) != 0, (cudaStream_t)stream, info);
 	});
 }
@@ -970,7 +988,7 @@ static int ref_cplx(lcgb200_caxfunc_cuda_ptr Afp, lcgb200_caxfunc_cuda_ptr Mfp, 
 		CsrHandle* h = reinterpret_cast<CsrHandle*>(instance);
 		if (!h) return LCGB200_INVALID_POINTER;
 		if (h->value_type != LCGB200_COMPLEX || h->n_rows != n) return LCGB200_C_SIZE_NOT_MATCH;
-		if (solver_id == LCGB200_CBICG && !h->t_row_ptr) { set_error_msg("CLCG_BICG needs LCGB200_CSR_TRANSPOSE"); return LCGB200_C_UNKNOWN_SOLVER; }
+		if (solver_id == LCGB200_CBICG && !h->t_row_ptr && !h->t_handle) { set_error_msg("CLCG_BICG needs LCGB200_CSR_TRANSPOSE"); return LCGB200_C_UNKNOWN_SOLVER; }
 		if (solver_id == LCGB200_CPCG)
 		{
 			if (Mfp == lcgb200_jacobi_cmx) { if (!h->diag) return LCGB200_NULL_PRECONDITION_MATRIX; }
@@ -992,7 +1010,7 @@ static int ref_cplx(lcgb200_caxfunc_cuda_ptr Afp, lcgb200_caxfunc_cuda_ptr Mfp, 
 				if (!Pfp) return ProgressFn();
 				return [=](double res, int k) { return Pfp(h->user, m_dev, res, &para, n, nz, k); };
 			};
-			return do_solve_cplx(h, A, solver_id, (double2*)m, (const double2*)B, para, n, h->n_cols, h->n_global, make_pf, false, nullptr, nullptr);
+			return do_solve_cplx(h, A, solver_id, (double2*)m, (const double2*)B, para, n, std::max(h->n_cols, h->t_handle ? h->t_handle->n_cols : 0), h->n_global, make_pf, false, nullptr, nullptr);
 		});
 	}
 	if (solver_id == LCGB200_CPCG && (!Mfp || Mfp == lcgb200_jacobi_cmx)) return LCGB200_INVALID_POINTER;
@@ -1156,7 +1174,7 @@ int lcgb200_csolver(lcgb200_caxfunc_ptr Afp, lcgb200_cprogress_ptr Pfp, void* m,
 	{
 		if (!h) return LCGB200_C_INVALID_POINTER;
 		if (h->value_type != LCGB200_COMPLEX || h->n_rows != n) return LCGB200_C_SIZE_NOT_MATCH;
-		if (solver_id == LCGB200_CBICG && !h->t_row_ptr) { set_error_msg("CLCG_BICG needs LCGB200_CSR_TRANSPOSE"); return LCGB200_C_UNKNOWN_SOLVER; }
+		if (solver_id == LCGB200_CBICG && !h->t_row_ptr && !h->t_handle) { set_error_msg("CLCG_BICG needs LCGB200_CSR_TRANSPOSE"); return LCGB200_C_UNKNOWN_SOLVER; }
 	}
 	return guarded([&]() {
 		HostStage<double2> hs(n);
@@ -1176,7 +1194,7 @@ int lcgb200_csolver(lcgb200_caxfunc_ptr Afp, lcgb200_cprogress_ptr Pfp, void* m,
 				return Pfp(user, hs.m, res, &para, n, k);
 			};
 		};
-		return do_solve_cplx(h, A, solver_id, (double2*)m, (const double2*)B, para, n, h ? h->n_cols : n, h ? h->n_global : (long long)n, make_pf, false, nullptr, nullptr);
+		return do_solve_cplx(h, A, solver_id, (double2*)m, (const double2*)B, para, n, h ? std::max(h->n_cols, h->t_handle ? h->t_handle->n_cols : 0) : n, h ? h->n_global : (long long)n, make_pf, false, nullptr, nullptr);
 	});
 }
 

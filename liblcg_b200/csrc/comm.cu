@@ -344,7 +344,7 @@ int lcgb200_csr_set_partition(lcgb200_csr_t A, lcgb200_comm_t comm, long long n_
 	if (!h || !c) return LCGB200_INVALID_POINTER;
 	if (n_peers < 0 || n_global < h->n_rows) return LCGB200_INVILAD_VARIABLE_SIZE;
 	if (n_peers > 0 && (!peer_ranks || !send_counts || !recv_counts)) return LCGB200_INVALID_POINTER;
-	if (h->t_row_ptr) { set_error_msg("a partitioned operator cannot carry a transpose (complex BiCG is single-GPU)"); return LCGB200_SIZE_NOT_MATCH; }
+	if (h->t_row_ptr) { set_error_msg("the local transpose of a rectangular row block is not A^T: build the rows of A^T as a second partitioned handle and attach it (lcgb200_csr_attach_transpose)"); return LCGB200_SIZE_NOT_MATCH; }
 	return guarded_comm([&]() {
 		c->peers.clear();
 		c->n_local = h->n_rows;

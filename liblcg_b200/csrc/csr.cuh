@@ -51,6 +51,7 @@ struct CsrDev {
 	// row block of a partitioned system on the NVLink transport: tiles [n_interior, n_tiles) reference ghost columns
 	// (>= n_rows) and are read from the halo mailbox once the neighbours' pushes have landed; -1 = not in use
 	int n_interior = -1;
+	CommDev* comm = nullptr;   // the transport state of THIS block's halo plan (a partitioned transpose has its own)
 	const int* row_ptr = nullptr;
 	const int* col = nullptr;
 	const T* val = nullptr;
@@ -332,7 +333,7 @@ __global__ void __launch_bounds__(kSpmvThreads, TileCfg<T>::CTAS) k_spmv(CsrDev<
 			// kernel; then this warp waits until every neighbour's push for this exchange has landed in my mailbox and walks the
 			// remaining chunks with ghost columns read in place from the mailbox
 			spmv_consume<T, LPR, CONJ, false, Epi>(A, x, nullptr, y, epi, acc, smem, s_bar, s_long, idx, c, A.n_interior / A.chunk, tid);
-			CommDev* cd = st->comm;
+			CommDev* cd = A.comm;
 			const unsigned long long hseq = cd->halo_seq;
 			bool ok = true;
 			if ((tid & 31) < cd->n_peers && cd->recv_count[tid & 31] > 0)
@@ -349,7 +350,7 @@ __global__ void __launch_bounds__(kSpmvThreads, TileCfg<T>::CTAS) k_spmv(CsrDev<
 		__syncthreads();
 		if (tid == 0)
 		{
-			CommDev* cd = st->comm;
+			CommDev* cd = A.comm;
 			if (atomicAdd(&cd->ticket2, 1u) == gridDim.x - 1)
 			{
 				const unsigned long long hseq = cd->halo_seq;

@@ -302,18 +302,18 @@ int monitor(unsigned int inter, double converge, double epsilon, int k)
 template <class Call>
 void minimize(bool silent, bool verbose, bool er_throw, bool cplx, const char* name, Call&& call)
 {
-	auto report = [&](int ret) { if (cplx) clcg_error_str(ret, er_throw); else lcg_error_str(ret, er_throw); };
+	auto report = [&](int ret, bool thr) { if (cplx) clcg_error_str(ret, thr); else lcg_error_str(ret, thr); };
 	if (silent)
-	{
+	{	// solver.cpp:77-82: no monitor, and an error always raises
 		const int ret = call(false);
-		if (ret < 0) report(ret);
+		if (ret < 0) report(ret, true);
 		return;
 	}
 	const auto t0 = std::chrono::steady_clock::now();
 	const int ret = call(true);
 	const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-	std::clog << std::endl << "Solver: " << name << ". Time cost: " << ms << " ms" << std::endl;
-	if (verbose || ret < 0) report(ret);
+	if (!er_throw) std::clog << std::endl << "Solver: " << name << ". Time cost: " << ms << " ms" << std::endl;
+	if (verbose || ret < 0) report(ret, er_throw);
 }
 }  // namespace
 

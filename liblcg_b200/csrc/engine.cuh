@@ -57,6 +57,11 @@ struct CsrHandle {
 	unsigned char* pat = nullptr; int* pat_len = nullptr; double2* pat_ent = nullptr; int n_pat = 0, pat_maxlen = 0;
 	void* user = nullptr;          // instance handed to progress callbacks
 	Comm* comm = nullptr;          // set for a row block of a partitioned system
+	// partitioned systems: the rows [r0, r1) of A^T live in a second partitioned handle with its own halo plan and windows
+	// (complex BiCG's A^H d2, clcg.cpp:188); not owned.  row_offset = global index of the first local row (the shadow
+	// residual of complex CGS/BICGSTAB/TFQMR is one rand() sequence over the WHOLE vector, lcg_complex.cpp:118-127)
+	const CsrHandle* t_handle = nullptr;
+	long long row_offset = 0;
 	// cached workspace
 	void* ws = nullptr; size_t ws_bytes = 0;
 	DevState* d_state = nullptr; DevState* h_state = nullptr; DevState* h_state2 = nullptr; double* d_partials = nullptr;
@@ -74,6 +79,7 @@ struct CsrHandle {
 	{
 		CsrDev<T> v; v.n_rows = n_rows; v.n_cols = n_cols; v.nnz = nnz; v.n_tiles = n_tiles; v.lpr = lpr; v.chunk = chunk;
 		v.n_interior = halo_in_spmv() ? n_interior : -1;
+		v.comm = halo_in_spmv() ? comm->dev() : nullptr;
 		v.row_ptr = row_ptr; v.col = col; v.val = (const T*)val; v.tiles = tiles;
 		v.code = code; v.vdict = vdict; v.odict = odict; v.dtiles = dtiles; v.n_dtiles = n_dtiles; v.dchunk = dchunk; v.dlpr = dlpr;
 		v.pat = pat; v.pat_len = pat_len; v.pat_ent = pat_ent; v.n_pat = n_pat; v.pat_maxlen = pat_maxlen;
@@ -198,19 +204,21 @@ public:
 	{
 		if (A.h)
 		{
-			if (multi())
+			// op(A) of a partitioned system: A^T / A^H come from the second partitioned handle (its own plan, windows, sequence)
+			const CsrHandle* hh = (op != 0 && A.h->t_handle) ? A.h->t_handle : A.h;
+			if (hh->comm && hh->comm->size() > 1)
 			{
-				if (halo_in_spmv() && op == 0)
+				if (hh->halo_in_spmv())
 				{	// receive half inside k_spmv; push half only if the producing kernel has not done it already
-					if (pushed_vec != (const void*)x) { comm->push(x, (int)sizeof(T), stream, d_st); launches++; }
-					pushed_vec = nullptr;
+					if (hh != A.h || pushed_vec != (const void*)x) { hh->comm->push(x, (int)sizeof(T), stream, d_st); launches++; }
+					if (hh == A.h) pushed_vec = nullptr;
 				}
-				else { comm->halo(x, (int)sizeof(T), stream, p2p(), d_st); if (p2p()) launches++; }
+				else { hh->comm->halo(x, (int)sizeof(T), stream, hh->p2p_dev() != nullptr, d_st); if (hh->p2p_dev()) launches++; }
 			}
+			const CsrDev<T> V = (hh != A.h || op == 0) ? hh->template view<T>() : hh->template tview<T>();
 			cudaEvent_t pe = profiling ? prof_begin(0) : nullptr;
-			if (op == 0) launch_spmv<T, false, Epi>(A.h->template view<T>(), x, y, epi, d_st, d_partials, stream);
-			else if (op == 1) launch_spmv<T, false, Epi>(A.h->template tview<T>(), x, y, epi, d_st, d_partials, stream);
-			else launch_spmv<T, true, Epi>(A.h->template tview<T>(), x, y, epi, d_st, d_partials, stream);
+			if (op == 2) launch_spmv<T, true, Epi>(V, x, y, epi, d_st, d_partials, stream);
+			else launch_spmv<T, false, Epi>(V, x, y, epi, d_st, d_partials, stream);
 			prof_end(pe);
 			launches++; spmv_launches++;
 			if (Epi::NRED > 0 && multi()) finish_multi(RowEpilogueOp<T, Epi>{epi, x, y}, Epi::NRED);

@@ -120,7 +120,7 @@ static int run_cbicg(Engine& E, const Operator<Z>& A, Z* m, const Z* B, size_t n
 {
 	Z* r1 = E.alloc<Z>(next); Z* r2 = E.alloc<Z>(next); Z* d1 = E.alloc<Z>(next); Z* d2 = E.alloc<Z>(next); Z* Ax = E.alloc<Z>(next);
 	E.spmv(A, m, Ax, EpiNone<Z>{});
-	E.vec(OpCbInit{{}, m, Ax, B, r1, r2, d1, d2}, n);
+	E.vec_push(OpCbInit{{}, m, Ax, B, r1, r2, d1, d2}, n, d1);
 	std::function<void(int)> batch;
 	if (E.small_system(A) && A.h->lpr == A.h->t_lpr)
 		batch = [&](int k) { E.fused(k, 2, E.ph_spmv(A, d1, Ax, EpiInnerAlpha{d2}), E.ph_vec(OpCbUpdate1{{}, m, d1, r1, Ax, zc()}, n), E.ph_spmv_h(A, d2, Ax, EpiNone<Z>{}),
@@ -130,7 +130,7 @@ static int run_cbicg(Engine& E, const Operator<Z>& A, Z* m, const Z* B, size_t n
 		E.vec(OpCbUpdate1{{}, m, d1, r1, Ax, zc()}, n);
 		E.spmv(A, d2, Ax, EpiNone<Z>{}, 2);	// A^H d2 (MatTranspose, Conjugate — clcg.cpp:188)
 		E.vec(OpCbUpdate2{{}, r2, Ax, r1, zc()}, n);
-		E.vec(OpCbDir{{}, r1, r2, d1, d2, zc()}, n);
+		E.vec_push(OpCbDir{{}, r1, r2, d1, d2, zc()}, n, d1);
 		return false;
 	}, batch);
 }
@@ -221,13 +221,13 @@ static int run_csym(Engine& E, const Operator<Z>& A, Z* m, const Z* B, size_t n,
 	Z* z = pcg ? E.alloc<Z>(next) : nullptr;
 	const int mode = !pcg ? 0 : (A.diag ? 1 : 2);
 	E.spmv(A, m, Ax, EpiNone<Z>{});
-	if (mode == 0) E.vec(OpCsInit<0>{{}, m, Ax, B, nullptr, r, z, d}, n);
-	else if (mode == 1) E.vec(OpCsInit<1>{{}, m, Ax, B, A.diag, r, z, d}, n);
+	if (mode == 0) E.vec_push(OpCsInit<0>{{}, m, Ax, B, nullptr, r, z, d}, n, d);
+	else if (mode == 1) E.vec_push(OpCsInit<1>{{}, m, Ax, B, A.diag, r, z, d}, n, d);
 	else
 	{
 		E.vec(OpCsInit<2>{{}, m, Ax, B, nullptr, r, z, d}, n);
 		A.precond(r, z, 0);
-		E.vec(OpCsInitZ{{}, r, z, d}, n);
+		E.vec_push(OpCsInitZ{{}, r, z, d}, n, d);
 	}
 	std::function<void(int)> batch;
 	if (E.small_system(A) && mode == 0)
@@ -244,7 +244,7 @@ static int run_csym(Engine& E, const Operator<Z>& A, Z* m, const Z* B, size_t n,
 			A.precond(r, z, 0);
 			E.vec(OpCsRho{{}, r, z}, n);
 		}
-		E.vec(OpCsDir{{}, mode == 0 ? r : z, d, zc()}, n);
+		E.vec_push(OpCsDir{{}, mode == 0 ? r : z, d, zc()}, n, d);
 		return false;
 	}, batch);
 }
@@ -304,11 +304,27 @@ struct OpCRho : OpBase {
 	}
 };
 
+// Partitioned solves with the reference's clock seed (shadow_seed = 0): every rank must seed rand() identically, so the ranks
+// agree on the mean of their clocks through the same cross-rank sum the dot products use (bitwise identical on all ranks).
+struct OpSeedAgree : OpBase {
+	static constexpr int NRED = 1, W = 1;
+	double t;
+	template <int V> __device__ void elem(size_t i, double* acc) const { if (i == 0) acc[0] += t; }
+	__device__ void finish(DevState* st, const double* tot) const { st->sc[SC_TMP5] = tot[0]; }
+};
+
 template <bool HEAD>
 static bool init_shadow(Engine& E, Z* rb, const Z* r, size_t n, size_t skip)
 {
 	std::vector<Z> host;
 	long seed = settings().shadow_seed;
+	if (seed == 0 && E.multi())
+	{
+		E.vec(OpSeedAgree{{}, (double)time(nullptr)}, 1);
+		E.read_state();
+		seed = (long)(E.h_st->sc[SC_TMP5] / (double)E.comm->size());
+		if (seed == 0) seed = 1;
+	}
 	for (int attempt = 0; attempt < 64; attempt++)
 	{
 		draw_shadow(host, n, seed, skip);
@@ -373,7 +389,7 @@ static int run_ccgs(Engine& E, const Operator<Z>& A, Z* m, const Z* B, size_t n,
 	Z* r = E.alloc<Z>(next); Z* rb = E.alloc<Z>(next); Z* p = E.alloc<Z>(next); Z* Ax = E.alloc<Z>(next);
 	Z* u = E.alloc<Z>(next); Z* q = E.alloc<Z>(next); Z* w = E.alloc<Z>(next);
 	E.spmv(A, m, Ax, EpiNone<Z>{});
-	E.vec(OpCResInit{{}, m, Ax, B, r, p, u, nullptr}, n);
+	E.vec_push(OpCResInit{{}, m, Ax, B, r, p, u, nullptr}, n, p);
 	if (!init_shadow<true>(E, rb, r, n, skip)) return RC_UNKNOWN;
 	std::function<void(int)> batch;
 	if (E.small_system(A))
@@ -381,10 +397,10 @@ static int run_ccgs(Engine& E, const Operator<Z>& A, Z* m, const Z* B, size_t n,
 			E.ph_vec(OpCCgsUpdate{{}, m, w, r, Ax, rb, zc()}, n), E.ph_vec(OpCCgsDir{{}, r, q, u, p, zc()}, n)); };
 	return E.run([&]() {
 		E.spmv(A, p, Ax, EpiInnerAlpha{rb});
-		E.vec(OpCQW{{}, u, Ax, q, w, zc()}, n);
+		E.vec_push(OpCQW{{}, u, Ax, q, w, zc()}, n, w);
 		E.spmv(A, w, Ax, EpiNone<Z>{});
 		E.vec(OpCCgsUpdate{{}, m, w, r, Ax, rb, zc()}, n);
-		E.vec(OpCCgsDir{{}, r, q, u, p, zc()}, n);
+		E.vec_push(OpCCgsDir{{}, r, q, u, p, zc()}, n, p);
 		return false;
 	}, batch);
 }
@@ -434,7 +450,7 @@ static int run_cbicgstab(Engine& E, const Operator<Z>& A, Z* m, const Z* B, size
 	Z* r = E.alloc<Z>(next); Z* rb = E.alloc<Z>(next); Z* p = E.alloc<Z>(next); Z* s = E.alloc<Z>(next);
 	Z* Ap = E.alloc<Z>(next); Z* As = E.alloc<Z>(next);
 	E.spmv(A, m, Ap, EpiNone<Z>{});
-	E.vec(OpCResInit{{}, m, Ap, B, r, p, nullptr, nullptr}, n);
+	E.vec_push(OpCResInit{{}, m, Ap, B, r, p, nullptr, nullptr}, n, p);
 	if (!init_shadow<true>(E, rb, r, n, skip)) return RC_UNKNOWN;
 	std::function<void(int)> batch;
 	if (E.small_system(A))
@@ -442,10 +458,10 @@ static int run_cbicgstab(Engine& E, const Operator<Z>& A, Z* m, const Z* B, size
 			E.ph_vec(OpCBsUpdate{{}, m, p, s, As, r, rb, zc(), zc()}, n), E.ph_vec(OpCBsDir{{}, r, p, Ap, zc(), zc()}, n)); };
 	return E.run([&]() {
 		E.spmv(A, p, Ap, EpiInnerAlpha{rb});
-		E.vec(OpCBsS{{}, r, Ap, s, zc()}, n);
+		E.vec_push(OpCBsS{{}, r, Ap, s, zc()}, n, s);
 		E.spmv(A, s, As, EpiCOmega{});
 		E.vec(OpCBsUpdate{{}, m, p, s, As, r, rb, zc(), zc()}, n);
-		E.vec(OpCBsDir{{}, r, p, Ap, zc(), zc()}, n);
+		E.vec_push(OpCBsDir{{}, r, p, Ap, zc(), zc()}, n, p);
 		return false;
 	}, batch);
 }
@@ -524,7 +540,7 @@ static int run_ctfqmr(Engine& E, const Operator<Z>& A, Z* m, const Z* B, size_t 
 	Z* p = E.alloc<Z>(next); Z* u = E.alloc<Z>(next); Z* v = E.alloc<Z>(next); Z* d = E.alloc<Z>(next);
 	Z* rb = E.alloc<Z>(next); Z* r = E.alloc<Z>(next); Z* Ax = E.alloc<Z>(next); Z* q = E.alloc<Z>(next); Z* uq = E.alloc<Z>(next);
 	E.spmv(A, m, Ax, EpiNone<Z>{});
-	E.vec(OpCResInit{{}, m, Ax, B, r, p, u, d}, n);
+	E.vec_push(OpCResInit{{}, m, Ax, B, r, p, u, d}, n, p);
 	if (!init_shadow<false>(E, rb, r, n, skip)) return RC_UNKNOWN;
 	// theta = 0, omega = tao = |<r,r>| = r.r, eta = 0 — written straight into the state block
 	{
@@ -538,14 +554,14 @@ static int run_ctfqmr(Engine& E, const Operator<Z>& A, Z* m, const Z* B, size_t 
 	}
 	return E.run([&]() {
 		E.spmv(A, p, v, EpiInnerAlpha{rb});
-		E.vec(OpCQW{{}, u, v, q, uq, zc()}, n);
+		E.vec_push(OpCQW{{}, u, v, q, uq, zc()}, n, uq);
 		E.spmv(A, uq, Ax, EpiNone<Z>{});
 		E.vec(OpCTfR{{}, r, Ax, rb, zc()}, n);
 		if (E.sync_point()) return true;
 		E.vec(OpCTfHalf<1>{{}, u, d, m, zc(), zc()}, n);
 		if (E.sync_point()) return true;
 		E.vec(OpCTfHalf<2>{{}, q, d, m, zc(), zc()}, n);
-		E.vec(OpCCgsDir{{}, r, q, u, p, zc()}, n);
+		E.vec_push(OpCCgsDir{{}, r, q, u, p, zc()}, n, p);
 		return false;
 	});
 }
@@ -553,7 +569,7 @@ static int run_ctfqmr(Engine& E, const Operator<Z>& A, Z* m, const Z* B, size_t 
 // ======================================================================================== dispatch
 int solve_complex(Engine& E, const Operator<Z>& A, int solver_id, Z* m, const Z* B, const lcgb200_cpara& para, size_t n, size_t next)
 {
-	size_t skip = 0;	// multi-GPU: global index of the first local row (set by the partitioned path)
+	const size_t skip = A.h ? (size_t)A.h->row_offset : 0;	// partitioned: global index of the first local row (lcgb200_csr_set_row_offset)
 	switch (solver_id)
 	{
 		case LCGB200_CBICG: return run_cbicg(E, A, m, B, n, next);

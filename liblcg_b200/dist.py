@@ -138,10 +138,14 @@ class Partition:
     n_local: int
     b: "object" = None
     p2p: bool = False
+    t_part: "object" = None     # the rows of A^T as a second partition (complex BiCG's A^H d2), attached to `op`
 
     def close(self):
         self.op.close()
         self.comm.close()
+        if self.t_part is not None:
+            self.t_part.close()
+            self.t_part = None
 
 
 def attach_plan(op: api.CsrOperator, comm: Communicator, plan: HaloPlan) -> None:
@@ -188,9 +192,38 @@ def enable_p2p(comm: Communicator, plan: HaloPlan, group=None) -> bool:
     return True
 
 
-def partition_csr(row_ptr_local, col_global, val, bounds, rank: int, jacobi=False, group=None, compress=False) -> Partition:
+def transposed_rows(row_ptr_local, col_global, val, bounds, rank: int, group=None):
+    """Rows [r0, r1) of A^T from the row blocks of A: every rank buckets its entries (i, j, v) by the owner of column j and
+    ships them there (set-up time, over all_gather_object: any backend).  Returns numpy (row_ptr rebased to 0, GLOBAL column
+    ids ascending within a row, values NOT conjugated)."""
+    import torch
+    import torch.distributed as dist
+    world = len(bounds) - 1
+    r0, r1 = bounds[rank], bounds[rank + 1]
+    to_np = lambda a: a.detach().cpu().numpy() if hasattr(a, "data_ptr") else np.asarray(a)
+    rp, cj, v = to_np(row_ptr_local).astype(np.int64), to_np(col_global).astype(np.int64), to_np(val)
+    ri = np.repeat(np.arange(r0, r1, dtype=np.int64), np.diff(rp))
+    owner = np.searchsorted(np.asarray(bounds[1:], dtype=np.int64), cj, side="right")
+    out = {p: (cj[owner == p], ri[owner == p], v[owner == p]) for p in range(world) if np.any(owner == p)}
+    gathered = [out]
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, out, group=group)
+    mine = [g[rank] for g in gathered if g and rank in g]
+    trow = np.concatenate([m[0] for m in mine]) if mine else np.zeros(0, np.int64)
+    tcol = np.concatenate([m[1] for m in mine]) if mine else np.zeros(0, np.int64)
+    tval = np.concatenate([m[2] for m in mine]) if mine else np.zeros(0, v.dtype)
+    order = np.lexsort((tcol, trow))
+    trow, tcol, tval = trow[order], tcol[order], tval[order]
+    t_rp = np.zeros(r1 - r0 + 1, dtype=np.int32)
+    np.cumsum(np.bincount(trow - r0, minlength=r1 - r0), out=t_rp[1:])
+    return t_rp, tcol.astype(np.int32), tval
+
+
+def partition_csr(row_ptr_local, col_global, val, bounds, rank: int, jacobi=False, group=None, compress=False, transpose=False) -> Partition:
     """This rank's rows (row_ptr rebased to 0, GLOBAL column ids, values; torch CUDA tensors or numpy arrays)
-    -> rectangular operator + communicator + halo plan."""
+    -> rectangular operator + communicator + halo plan.  transpose=True also builds the rows of A^T as a second partition
+    (its own plan and windows) and attaches it, so that complex BiCG's A^H d2 (clcg.cpp:188) works on the partitioned system."""
     import torch
     world = len(bounds) - 1
     on_dev = hasattr(col_global, "data_ptr")
@@ -203,11 +236,22 @@ def partition_csr(row_ptr_local, col_global, val, bounds, rank: int, jacobi=Fals
         op = api.CsrOperator(np.asarray(row_ptr_local), new_col.numpy(), np.asarray(val), n_cols=n_loc + plan.n_ghost, jacobi=jacobi, compress=compress)
     comm = Communicator(rank, world, group=group)
     attach_plan(op, comm, plan)
+    # the shadow residual of complex CGS/BICGSTAB/TFQMR is one rand() sequence over the whole vector: tell the block where it starts
+    _lib.load().lcgb200_csr_set_row_offset(op.handle, bounds[rank])
     p2p = False
-    if on_dev and not op.complex and os.environ.get("LCGB200_NO_P2P", "0") != "1":   # LCGB200_NO_P2P=1: NCCL transport (comparison runs)
+    if on_dev and os.environ.get("LCGB200_NO_P2P", "0") != "1":   # LCGB200_NO_P2P=1: NCCL transport (comparison runs)
         p2p = enable_p2p(comm, plan, group=group)
     part = Partition(op, comm, plan, n_loc)
     part.p2p = p2p
+    if transpose:
+        t_rp, t_col, t_val = transposed_rows(row_ptr_local, col_global, val, bounds, rank, group=group)
+        if on_dev:
+            dev = col_global.device
+            t_rp, t_col, t_val = torch.from_numpy(t_rp).to(dev), torch.from_numpy(t_col).to(dev), torch.from_numpy(np.ascontiguousarray(t_val)).to(dev)
+        part.t_part = partition_csr(t_rp, t_col, t_val, bounds, rank, group=group)
+        rc = _lib.load().lcgb200_csr_attach_transpose(op.handle, part.t_part.op.handle)
+        if rc != 0:
+            raise RuntimeError(f"lcgb200_csr_attach_transpose failed ({rc}): {api.last_error()}")
     return part
 
 

@@ -152,8 +152,11 @@ int main(int argc, char** argv)
 		lcg_float *ws[7]; for (auto& w : ws) w = lcg_malloc(n);
 		lcg_vecset(m, 0.0, n);
 		ret = lcgs(host_ax, nullptr, m, g_A.b.data(), n, &para, nullptr, ws[0], ws[1], ws[2], ws[3], ws[4], ws[5], ws[6]);
-		lcg_float rr = 0.0; lcg_dot(rr, ws[0], ws[0], n);
-		check(ret == LCG_CONVERGENCE && avg_err(m, g_A.ans) < 1e-3 && rr > 0.0 && rr < 1e-6, "lcgs() stand-alone CGS with 7 caller-owned work vectors (lcg.h:166-169); RK holds the final residual");
+		host_ax(nullptr, m, Am, n);
+		lcg_float dr = 0.0, nb = 0.0;   // RK must come back as the residual B - A m of the returned solution
+		for (int i = 0; i < n; i++) { const double t = g_A.b[(size_t)i] - Am[i] - ws[0][i]; dr += t * t; }
+		lcg_dot(nb, g_A.b.data(), g_A.b.data(), n);
+		check(ret == LCG_CONVERGENCE && avg_err(m, g_A.ans) < 1e-3 && std::sqrt(dr) <= 1e-8 * std::sqrt(nb), "lcgs() stand-alone CGS with 7 caller-owned work vectors (lcg.h:166-169); RK holds the final residual");
 		for (auto& w : ws) lcg_free(w);
 		lcg_free(Gk); lcg_free(Dk); lcg_free(ADk); lcg_free(Am);
 	}

@@ -126,6 +126,41 @@ def main():
                       f"packed-sends {packed} peers {part.plan.peers} transport {'nvlink-p2p' if part.p2p else 'nccl'}", flush=True)
                 failures += 0 if ok else 1
     part.close()
+    # ---- complex solvers on the partitioned data/case_10K_cA (configs[1]): BiCG through the attached A^T partition (A^H d2),
+    # CGS / BICGSTAB / TFQMR with every rank drawing its slice of the ONE rand() sequence of the shadow residual, Jacobi-PCG
+    Ac = lio.load_fixture("10Kc")
+    n = Ac["n"]
+    bounds = ldist.row_bounds(n, world)
+    r0, r1 = bounds[rank], bounds[rank + 1]
+    k0, k1 = Ac["row_ptr"][r0], Ac["row_ptr"][r1]
+    cpart = ldist.partition_csr(torch.from_numpy((Ac["row_ptr"][r0:r1 + 1] - k0).astype(np.int32)).to(dev), torch.from_numpy(Ac["col"][k0:k1].astype(np.int32)).to(dev),
+                                torch.from_numpy(np.ascontiguousarray(Ac["val"][k0:k1], dtype=np.complex128)).to(dev), bounds, rank, jacobi=True, transpose=True)
+    bc_loc = torch.from_numpy(np.ascontiguousarray(Ac["b"][r0:r1])).to(dev)
+    api.set_shadow_seed(4242)
+    if rank == 0:
+        port.set_time(4242)
+        cdiag = lio.csr_diagonal(Ac["row_ptr"], Ac["col"], Ac["val"])
+    for name, sid, k in (("BICG", api.CLCG_BICG, 20), ("BICG_SYM", api.CLCG_BICG_SYM, 20), ("CGS", api.CLCG_CGS, 10), ("BICGSTAB", api.CLCG_BICGSTAB, 5),
+                         ("TFQMR", api.CLCG_TFQMR, 10), ("PCG", api.CLCG_PCG, 20)):
+        mc = torch.zeros(cpart.n_local, dtype=torch.complex128, device=dev)
+        kw = dict(epsilon=1e-300, max_iterations=k)
+        r = api.csolve(cpart.op, sid, mc, bc_loc, param=api.clcg_default_parameters(**kw), device=True, jacobi=(sid == api.CLCG_PCG))
+        parts = [torch.empty(bounds[i + 1] - bounds[i], dtype=torch.complex128, device=dev) for i in range(world)]
+        dist.all_gather(parts, mc)
+        if rank == 0:
+            x = torch.cat(parts).cpu().numpy()
+            cpu = port.csolve(sid, Ac, Ac["b"], para=po.default_cpara(**kw), diag=cdiag if sid == api.CLCG_PCG else None)
+            rel = float(np.linalg.norm(x - cpu.x) / np.linalg.norm(cpu.x))
+            sens = 0.0
+            if rel > 1e-8:
+                bp = Ac["b"] * (1 + 2.2e-16 * np.random.default_rng(2024).standard_normal(n))
+                cp2 = port.csolve(sid, Ac, bp, para=po.default_cpara(**kw), diag=cdiag if sid == api.CLCG_PCG else None)
+                sens = float(np.linalg.norm(cp2.x - cpu.x) / np.linalg.norm(cpu.x))
+            ok = r.ret == cpu.ret and r.iterations == cpu.iters and (rel <= 1e-8 or rel <= 20 * sens)
+            print(f"{'OK  ' if ok else 'FAIL'} world={world} case_10K_cA complex {name:8s} pinned{k:<3d} ret {r.ret}/{cpu.ret} it {r.iterations}/{cpu.iters} rel {rel:.2e} "
+                  f"(oracle 1-ulp sensitivity {sens:.1e}) transport {'nvlink-p2p' if cpart.p2p else 'nccl'} err '{api.last_error() if r.ret != cpu.ret else ''}'", flush=True)
+            failures += 0 if ok else 1
+    cpart.close()
     t = torch.tensor([failures], device=dev)
     dist.broadcast(t, 0)
     dist.barrier()

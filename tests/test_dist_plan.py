@@ -87,6 +87,15 @@ def _worker(rank, world, port, case, out):
         t = torch.tensor([float(np.dot(x[r0:r1], y_loc))], dtype=torch.float64)
         dist.all_reduce(t)
         assert abs(t.item() - float(np.dot(x, y_glob))) < 1e-10
+        # rows [r0, r1) of A^T assembled from the row blocks of A (complex BiCG's A^H d2 on a partitioned system)
+        import scipy.sparse as sp
+        cval = val * (1.0 + 0.25j)
+        t_rp, t_col, t_val = ldist.transposed_rows(rpl.astype(np.int32), col[k0:k1], cval[k0:k1], bounds, rank)
+        At = sp.csr_matrix((cval, col, rp), shape=(n, n)).T.tocsr()
+        At.sort_indices()
+        assert np.array_equal(t_rp, At.indptr[r0:r1 + 1] - At.indptr[r0])
+        assert np.array_equal(t_col, At.indices[At.indptr[r0]:At.indptr[r1]])
+        np.testing.assert_array_equal(t_val, At.data[At.indptr[r0]:At.indptr[r1]])
         out[rank] = "ok"
     finally:
         dist.destroy_process_group()
