@@ -89,7 +89,8 @@ typedef int (*lcgb200_progress_ptr)(void* instance, const double* m, const doubl
  * ===================================================================================================== */
 typedef struct lcgb200_csr_s* lcgb200_csr_t;
 
-enum { LCGB200_REAL = 0, LCGB200_COMPLEX = 1 };
+enum { LCGB200_REAL = 0, LCGB200_COMPLEX = 1,   /* double / cuDoubleComplex (interleaved re, im doubles) */
+       LCGB200_COMPLEX_FLOAT = 2 };              /* cuComplex (interleaved floats): the clcg_cudaf.h entry points */
 enum { LCGB200_HOST = 0, LCGB200_DEVICE = 1 };
 enum {
 	LCGB200_CSR_TRANSPOSE = 1,   /* also store A^T (needed by complex BiCG's A^H d2, clcg.cpp:188) */
@@ -221,6 +222,20 @@ int lcgb200_csolver_preconditioned_cuda(lcgb200_caxfunc_cuda_ptr Afp, lcgb200_ca
 	void* m, const void* B, const int n_size, const int nz_size, const lcgb200_cpara* param, void* instance,
 	lcgb200_cublas_t cub_handle, lcgb200_cusparse_t cus_handle, int solver_id);
 
+/* replace the cuComplex overloads of clcg_solver_cuda / clcg_solver_preconditioned_cuda (clcg_cudaf.h:81-83, 103-105): BICG and
+ * BICG_SYM / PCG in single-precision complex storage.  m, B: HOST arrays of n_size cuComplex.  Vectors and matrix values are
+ * stored as floats (half the bytes per iteration); dot products, norms and the iteration scalars are carried in double.
+ * The residual handed to the callback follows the reference's CUDA definition (clcg_cudaf.cu:142-176).  Built-in operator:
+ * lcgb200_csr_cax / lcgb200_jacobi_cmx with an lcgb200_csr_t of value type LCGB200_COMPLEX_FLOAT as `instance`. */
+typedef int (*lcgb200_cprogress_cudaf_ptr)(void* instance, const void* m_dev, const float converge,
+	const lcgb200_cpara* param, const int n_size, const int nz_size, const int k);
+int lcgb200_csolver_cudaf(lcgb200_caxfunc_cuda_ptr Afp, lcgb200_cprogress_cudaf_ptr Pfp, void* m, const void* B,
+	const int n_size, const int nz_size, const lcgb200_cpara* param, void* instance,
+	lcgb200_cublas_t cub_handle, lcgb200_cusparse_t cus_handle, int solver_id);
+int lcgb200_csolver_preconditioned_cudaf(lcgb200_caxfunc_cuda_ptr Afp, lcgb200_caxfunc_cuda_ptr Mfp, lcgb200_cprogress_cudaf_ptr Pfp,
+	void* m, const void* B, const int n_size, const int nz_size, const lcgb200_cpara* param, void* instance,
+	lcgb200_cublas_t cub_handle, lcgb200_cusparse_t cus_handle, int solver_id);
+
 /* ---- the reference's HOST-callback API (lcg.h:71-113, clcg.h:74-76) ----
  * Same arguments, dispatch and return codes as lcg_solver (CG, CGS, BICGSTAB, BICGSTAB2; anything else -> CGS, lcg.cpp:59-82),
  * lcg_solver_preconditioned (always PCG, lcg.cpp:87-91), lcg_solver_constrained (PG, SPG, lcg.cpp:121-140) and clcg_solver
@@ -277,7 +292,8 @@ enum {
 /* real solvers on the built-in operator: solver_id in LCGB200_CG..LCGB200_SPG (low/hig only for PG, SPG) */
 int lcgb200_solve(lcgb200_csr_t A, int solver_id, double* m, const double* B, const double* low, const double* hig,
 	const lcgb200_para* param, lcgb200_progress_cuda_ptr Pfp, unsigned flags, void* stream, lcgb200_info* info);
-/* complex solvers on the built-in operator: solver_id in LCGB200_CBICG..LCGB200_CPCG */
+/* complex solvers on the built-in operator: solver_id in LCGB200_CBICG..LCGB200_CPCG; m, B in the handle's precision
+ * (cuDoubleComplex for LCGB200_COMPLEX, cuComplex for LCGB200_COMPLEX_FLOAT) */
 int lcgb200_csolve(lcgb200_csr_t A, int solver_id, void* m, const void* B, const lcgb200_cpara* param,
 	lcgb200_cprogress_cuda_ptr Pfp, unsigned flags, void* stream, lcgb200_info* info);
 
@@ -305,6 +321,9 @@ void lcgb200_set_spin_timeout_ms(long long ms);
  * environment LCGB200_GRAPHS or automatic (on for systems whose iteration is short enough for launch gaps to matter),
  * 0 = off, 1 = on */
 void lcgb200_set_graphs(int mode);
+/* programmatic dependent launch between the kernels of an iteration (the next kernel is scheduled while the current one
+ * finishes its reduction and parks in griddepcontrol.wait): -1 (default) = environment LCGB200_PDL or on, 0 = off, 1 = on */
+void lcgb200_set_pdl(int mode);
 /* 1: bracket every kernel launch of a solve with CUDA events (per-kernel durations in lcgb200_info); costs a
  * little throughput, so bench.py uses it only for its roofline pass */
 void lcgb200_set_profile(int on);

@@ -35,6 +35,7 @@ AXFUNC = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_v
 PROGRESS = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.POINTER(LcgPara), C.c_int, C.c_int, C.c_int)
 CAXFUNC = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int)
 CPROGRESS = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.POINTER(ClcgPara), C.c_int, C.c_int, C.c_int)
+CPROGRESSF = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.POINTER(ClcgPara), C.c_int, C.c_int, C.c_int)   # clcg_cudaf.h:61-62
 # host-callback API (lcg.h:37-38,53-54; clcg.h:40-41,56-57)
 AXFUNC_HOST = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int)
 PROGRESS_HOST = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_double, C.POINTER(LcgPara), C.c_int, C.c_int)
@@ -77,6 +78,8 @@ SYMBOLS = {
     "lcgb200_solver_constrained_cuda": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, C.POINTER(LcgPara), _VP, _VP, _VP, _I]),
     "lcgb200_csolver_cuda": (_I, [_VP, _VP, _VP, _VP, _I, _I, C.POINTER(ClcgPara), _VP, _VP, _VP, _I]),
     "lcgb200_csolver_preconditioned_cuda": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, C.POINTER(ClcgPara), _VP, _VP, _VP, _I]),
+    "lcgb200_csolver_cudaf": (_I, [_VP, _VP, _VP, _VP, _I, _I, C.POINTER(ClcgPara), _VP, _VP, _VP, _I]),
+    "lcgb200_csolver_preconditioned_cudaf": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, C.POINTER(ClcgPara), _VP, _VP, _VP, _I]),
     "lcgb200_csr_ax_host": (None, None),
     "lcgb200_jacobi_mx_host": (None, None),
     "lcgb200_csr_cax_host": (None, None),
@@ -95,6 +98,7 @@ SYMBOLS = {
     "lcgb200_set_fused_small": (None, [_I]),
     "lcgb200_set_spin_timeout_ms": (None, [_LL]),
     "lcgb200_set_graphs": (None, [_I]),
+    "lcgb200_set_pdl": (None, [_I]),
     "lcgb200_last_error": (C.c_char_p, []),
     "lcgb200_version": (_I, []),
     "lcgb200_gen_stencil": (_I, [_I, _I, _LL, _LL, _VP, _VP, _VP, _LL, C.POINTER(_LL), _VP]),

@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <type_traits>
 
 using namespace lcgb200;
 
@@ -98,6 +99,15 @@ __global__ void k_check_cols(long long nnz, const int* __restrict__ ci, int n_co
 	bool bad = false;
 	for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += stride) bad |= ((unsigned)ci[k] >= (unsigned)n_cols);
 	if (bad) *fail = 1;
+}
+
+__global__ void k_diag_cplxf(int n, const int* rp, const int* ci, const ZF* v, ZF* d)
+{	// clcg_smCcsr_get_diagonal (lcg_complex_cuda.cu), single precision
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	ZF out(0.f, 0.f);
+	for (int k = rp[i]; k < rp[i + 1]; k++) if (ci[k] == i) { out = v[k]; break; }
+	d[i] = out;
 }
 
 template <class T>
@@ -374,13 +384,14 @@ void create_typed(CsrHandle* h, const int* row_ptr, const int* col, const T* val
 		host_transpose<T>(h->n_rows, h->n_cols, rp_h.data(), cip, vp, trp, tci, tv);
 		upload_csr<T>(h->n_cols, h->nnz, trp.data(), tci.data(), tv.data(), false, &h->t_row_ptr, &h->t_col, &h->t_val, &h->t_tiles, &h->t_n_tiles, tile_nnz, &h->t_lpr, &h->t_chunk);
 	}
-	if ((h->flags & LCGB200_CSR_COMPRESS) && sizeof(T) == sizeof(double)) try_compress(h, rp_h);
+	if ((h->flags & LCGB200_CSR_COMPRESS) && std::is_same<T, double>::value) try_compress(h, rp_h);
 	if (h->flags & LCGB200_CSR_JACOBI)
 	{
 		T* d = dev_alloc<T>((size_t)h->n_rows);
 		h->diag = d;
 		const int grid = (h->n_rows + 255) / 256;
-		if (sizeof(T) == sizeof(double)) k_diag_real<<<grid, 256>>>(h->n_rows, h->row_ptr, h->col, (const double*)h->val, (double*)d);
+		if (std::is_same<T, double>::value) k_diag_real<<<grid, 256>>>(h->n_rows, h->row_ptr, h->col, (const double*)h->val, (double*)d);
+		else if (std::is_same<T, ZF>::value) k_diag_cplxf<<<grid, 256>>>(h->n_rows, h->row_ptr, h->col, (const ZF*)h->val, (ZF*)d);
 		else k_diag_cplx<<<grid, 256>>>(h->n_rows, h->row_ptr, h->col, (const double2*)h->val, (double2*)d);
 		LCG_CUDA_CHECK(cudaGetLastError());
 		LCG_CUDA_CHECK(cudaDeviceSynchronize());
@@ -579,8 +590,14 @@ int do_solve_real(CsrHandle* h, Operator<double>& A, int solver_id, double* m, c
 	return ret;
 }
 
-int do_solve_cplx(CsrHandle* h, Operator<double2>& A, int solver_id, double2* m, const double2* B, const lcgb200_cpara& para,
-	int n, int n_ext, long long n_global, const std::function<ProgressFn(const double2* m_dev)>& make_pf, bool dev_vecs,
+inline int run_complex(Engine& E, const Operator<double2>& A, int id, double2* m, const double2* B, const lcgb200_cpara& p, size_t n, size_t ne) { return solve_complex(E, A, id, m, B, p, n, ne); }
+inline int run_complex(Engine& E, const Operator<ZF>& A, int id, ZF* m, const ZF* B, const lcgb200_cpara& p, size_t n, size_t ne) { return solve_complexf(E, A, id, m, B, p, n, ne); }
+
+// ZV = double2 (cuDoubleComplex vectors) or ZF (cuComplex vectors, clcg_cudaf.h)
+template <class T> struct Ident { typedef T type; };   // keeps make_pf out of template argument deduction
+template <class ZV>
+int do_solve_cplx(CsrHandle* h, Operator<ZV>& A, int solver_id, ZV* m, const ZV* B, const lcgb200_cpara& para,
+	int n, int n_ext, long long n_global, const std::function<ProgressFn(const typename Ident<ZV>::type* m_dev)>& make_pf, bool dev_vecs,
 	cudaStream_t stream, lcgb200_info* info)
 {
 	const double t0 = now_ms();
@@ -589,29 +606,30 @@ int do_solve_cplx(CsrHandle* h, Operator<double2>& A, int solver_id, double2* m,
 	E.n_local = (size_t)n;
 	const bool m_inplace = dev_vecs && n_ext == n && ((reinterpret_cast<uintptr_t>(m) & 15) == 0);
 	const bool b_inplace = dev_vecs && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
-	const size_t vec_bytes = (((size_t)n_ext * sizeof(double2)) + 255) & ~size_t(255);
+	const size_t vec_bytes = (((size_t)n_ext * sizeof(ZV)) + 255) & ~size_t(255);
 	int nvec = complex_vector_count(solver_id) + (m_inplace ? 0 : 1) + (b_inplace ? 0 : 1);
 	E.reserve(vec_bytes * (size_t)nvec);
-	double2* d_m = m; const double2* d_B = B;
+	ZV* d_m = m; const ZV* d_B = B;
 	const cudaMemcpyKind in_kind = dev_vecs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-	if (!m_inplace) { d_m = E.alloc<double2>((size_t)n_ext); LCG_CUDA_CHECK(cudaMemcpyAsync(d_m, m, (size_t)n * sizeof(double2), in_kind, stream)); }
-	if (!b_inplace) { double2* t = E.alloc<double2>((size_t)n_ext); LCG_CUDA_CHECK(cudaMemcpyAsync(t, B, (size_t)n * sizeof(double2), in_kind, stream)); d_B = t; }
+	if (!m_inplace) { d_m = E.alloc<ZV>((size_t)n_ext); LCG_CUDA_CHECK(cudaMemcpyAsync(d_m, m, (size_t)n * sizeof(ZV), in_kind, stream)); }
+	if (!b_inplace) { ZV* t = E.alloc<ZV>((size_t)n_ext); LCG_CUDA_CHECK(cudaMemcpyAsync(t, B, (size_t)n * sizeof(ZV), in_kind, stream)); d_B = t; }
 	DevState init;
 	std::memset(&init, 0, sizeof(init));
 	init.eps = para.epsilon; init.n_global = n_global; init.abs_diff = para.abs_diff; init.max_it = para.max_iterations;
-	init.cres_mode = settings().cres_mode;
+	// the single-precision entry points exist only in the reference's CUDA library: its residual definition (clcg_cudaf.cu:142-176)
+	init.cres_mode = std::is_same<ZV, ZF>::value ? 1 : settings().cres_mode;
 	init.ret = RC_UNKNOWN;
 	E.pf = make_pf(d_m);
 	E.sync_each = A.host_side || (bool)A.apply || (bool)A.precond;
 	if (E.comm && E.comm->poisoned()) { set_error_msg("this communicator timed out in an earlier solve: its sequence counters may disagree with the peers'; create a new one"); throw ApiFailure{LCGB200_UNKNOWN_ERROR}; }
 	E.start(init);
-	int ret = solve_complex(E, A, solver_id, d_m, d_B, para, (size_t)n, (size_t)n_ext);
+	int ret = run_complex(E, A, solver_id, d_m, d_B, para, (size_t)n, (size_t)n_ext);
 	const double dev_ms = E.device_ms();
 	if (E.multi() && E.comm->check_abort()) set_error_msg("a cross-GPU wait timed out (a peer rank never arrived): the solve was ended and the communicator is poisoned");
 	if (!m_inplace)
 	{
 		const cudaMemcpyKind out_kind = dev_vecs ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-		LCG_CUDA_CHECK(cudaMemcpyAsync(m, d_m, (size_t)n * sizeof(double2), out_kind, stream));
+		LCG_CUDA_CHECK(cudaMemcpyAsync(m, d_m, (size_t)n * sizeof(ZV), out_kind, stream));
 	}
 	LCG_CUDA_CHECK(cudaStreamSynchronize(stream));
 	if (info)
@@ -646,6 +664,7 @@ void lcgb200_set_profile(int on) { settings().profile = on ? 1 : 0; }
 void lcgb200_set_fused_small(int on) { settings().fused_small = on ? 1 : 0; }
 void lcgb200_set_spin_timeout_ms(long long ms) { settings().spin_timeout_ms = ms; }
 void lcgb200_set_graphs(int mode) { settings().graphs = mode; }
+void lcgb200_set_pdl(int mode) { settings().pdl = mode; }
 
 // sentinels: recognised by address, never executed on the fused path
 void lcgb200_csr_ax(void*, lcgb200_cublas_t, lcgb200_cusparse_t, lcgb200_dnvec_t, lcgb200_dnvec_t, const int, const int) {}
@@ -665,7 +684,9 @@ int lcgb200_csr_create_rect(lcgb200_csr_t* out, int n_rows, int n_cols, int nnz,
 		h->value_type = value_type; h->n_rows = n_rows; h->n_cols = n_cols; h->nnz = nnz; h->n_global = n_rows; h->flags = flags;
 		LCG_CUDA_CHECK(cudaGetDevice(&h->device));
 		if (value_type == LCGB200_REAL) create_typed<double>(h, row_ptr, col, (const double*)val, location, kTileNnzReal);
-		else create_typed<double2>(h, row_ptr, col, (const double2*)val, location, kTileNnzCplx);
+		else if (value_type == LCGB200_COMPLEX_FLOAT) create_typed<ZF>(h, row_ptr, col, (const ZF*)val, location, kTileNnzReal);
+		else if (value_type == LCGB200_COMPLEX) create_typed<double2>(h, row_ptr, col, (const double2*)val, location, kTileNnzCplx);
+		else throw ApiFailure{LCGB200_INVILAD_VARIABLE_SIZE};
 		return 0;
 	});
 	if (rc != 0) { destroy_handle(h); return rc; }
@@ -710,7 +731,7 @@ int lcgb200_csr_get_diagonal(lcgb200_csr_t A, void* diag_host)
 	CsrHandle* h = reinterpret_cast<CsrHandle*>(A);
 	if (!h || !diag_host) return LCGB200_INVALID_POINTER;
 	if (!h->diag) return LCGB200_NULL_PRECONDITION_MATRIX;
-	const size_t es = h->value_type == LCGB200_REAL ? sizeof(double) : sizeof(double2);
+	const size_t es = h->value_type == LCGB200_COMPLEX ? sizeof(double2) : 8;   // double, or a pair of floats
 	return guarded([&]() { LCG_CUDA_CHECK(cudaMemcpy(diag_host, h->diag, es * (size_t)h->n_rows, cudaMemcpyDeviceToHost)); return 0; });
 }
 
@@ -727,7 +748,7 @@ int lcgb200_csr_format(lcgb200_csr_t A, int* compressed, int* n_values, int* n_o
 {
 	CsrHandle* h = reinterpret_cast<CsrHandle*>(A);
 	if (!h) return LCGB200_INVALID_POINTER;
-	const long long S = h->value_type == LCGB200_REAL ? 8 : 16;
+	const long long S = h->value_type == LCGB200_COMPLEX ? 16 : 8;
 	if (compressed) *compressed = h->pat ? 2 : (h->code ? 1 : 0);
 	if (n_values) *n_values = h->n_vdict;
 	if (n_offsets) *n_offsets = h->n_odict;
@@ -743,7 +764,7 @@ long long lcgb200_csr_spmv_bytes(lcgb200_csr_t A)
 {
 	CsrHandle* h = reinterpret_cast<CsrHandle*>(A);
 	if (!h) return 0;
-	const long long S = h->value_type == LCGB200_REAL ? 8 : 16;
+	const long long S = h->value_type == LCGB200_COMPLEX ? 16 : 8;
 	return (long long)h->nnz * (S + 4) + ((long long)h->n_rows + 1) * 4 + 2LL * h->n_rows * S;
 }
 
@@ -782,7 +803,7 @@ struct EpiProbeCplx {
 // halo exchange in front of a stand-alone SpMV on a partitioned handle: push half only when k_spmv holds the receive half
 void exchange_for_spmv(CsrHandle* h, const void* x, cudaStream_t s)
 {
-	const int eb = h->value_type == LCGB200_REAL ? 8 : 16;
+	const int eb = h->value_type == LCGB200_COMPLEX ? 16 : 8;
 	if (h->halo_in_spmv()) h->comm->push(x, eb, s, h->d_state);
 	else h->comm->halo(const_cast<void*>(x), eb, s, h->p2p_dev() != nullptr, h->d_state);
 }
@@ -812,6 +833,12 @@ int lcgb200_csr_spmv(lcgb200_csr_t A, const void* x, void* y, int op, void* stre
 			if (op == 0) launch_spmv<double, false>(h->view<double>(), (const double*)x, (double*)y, EpiNone<double>{}, h->d_state, h->d_partials, s);
 			else launch_spmv<double, false>(h->tview<double>(), (const double*)x, (double*)y, EpiNone<double>{}, h->d_state, h->d_partials, s);
 		}
+		else if (h->value_type == LCGB200_COMPLEX_FLOAT)
+		{
+			if (op == 0) launch_spmv<ZF, false>(h->view<ZF>(), (const ZF*)x, (ZF*)y, EpiNone<ZF>{}, h->d_state, h->d_partials, s);
+			else if (op == 1) launch_spmv<ZF, false>(h->tview<ZF>(), (const ZF*)x, (ZF*)y, EpiNone<ZF>{}, h->d_state, h->d_partials, s);
+			else launch_spmv<ZF, true>(h->tview<ZF>(), (const ZF*)x, (ZF*)y, EpiNone<ZF>{}, h->d_state, h->d_partials, s);
+		}
 		else
 		{
 			if (op == 0) launch_spmv<double2, false>(h->view<double2>(), (const double2*)x, (double2*)y, EpiNone<double2>{}, h->d_state, h->d_partials, s);
@@ -833,6 +860,7 @@ int lcgb200_csr_spmv_dot(lcgb200_csr_t A, const void* x, void* y, const void* w,
 		if (h->comm && h->comm->size() > 1) exchange_for_spmv(h, x, s);
 		if (h->value_type == LCGB200_REAL)
 			launch_spmv<double, false>(h->view<double>(), (const double*)x, (double*)y, EpiProbeReal{(const double*)w, dots_dev}, h->d_state, h->d_partials, s);
+		else if (h->value_type == LCGB200_COMPLEX_FLOAT) { set_error_msg("lcgb200_csr_spmv_dot: double and double-complex operators only"); throw ApiFailure{LCGB200_SIZE_NOT_MATCH}; }
 		else
 			launch_spmv<double2, false>(h->view<double2>(), (const double2*)x, (double2*)y, EpiProbeCplx{(const double2*)w, dots_dev}, h->d_state, h->d_partials, s);
 		LCG_CUDA_CHECK(cudaGetLastError());
@@ -869,7 +897,7 @@ int lcgb200_csolve(lcgb200_csr_t Ah, int solver_id, void* m, const void* B, cons
 {
 	CsrHandle* h = reinterpret_cast<CsrHandle*>(Ah);
 	if (!h) return LCGB200_C_INVALID_POINTER;
-	if (h->value_type != LCGB200_COMPLEX) return LCGB200_C_SIZE_NOT_MATCH;
+	if (h->value_type != LCGB200_COMPLEX && h->value_type != LCGB200_COMPLEX_FLOAT) return LCGB200_C_SIZE_NOT_MATCH;
 	const lcgb200_cpara para = param ? *param : kDefCPara;
 	if (solver_id < LCGB200_CBICG || solver_id > LCGB200_CPCG) solver_id = LCGB200_CCGS;	// clcg.cpp:68-70
 	int rc = check_cplx(h->n_rows, para, m, B);
@@ -881,14 +909,25 @@ int lcgb200_csolve(lcgb200_csr_t Ah, int solver_id, void* m, const void* B, cons
 	}
 	if (solver_id == LCGB200_CPCG && !((flags & LCGB200_USE_JACOBI) && h->diag)) return LCGB200_NULL_PRECONDITION_MATRIX;
 	return guarded([&]() {
+		const int n_ext = std::max(h->n_cols, h->t_handle ? h->t_handle->n_cols : 0);
+		if (h->value_type == LCGB200_COMPLEX_FLOAT)
+		{	// cuComplex vectors (m, B: interleaved float pairs)
+			Operator<ZF> A; A.h = h;
+			if (solver_id == LCGB200_CPCG) A.diag = (const ZF*)h->diag;
+			auto make_pf = [&](const ZF* m_dev) -> ProgressFn {
+				if (!Pfp) return ProgressFn();
+				return [=](double res, int k) { return Pfp(h->user, m_dev, res, &para, h->n_rows, h->nnz, k); };
+			};
+			return do_solve_cplx<ZF>(h, A, solver_id, (ZF*)m, (const ZF*)B, para, h->n_rows, n_ext, h->n_global, make_pf,
+				(flags & LCGB200_VEC_DEVICE) != 0, (cudaStream_t)stream, info);
+		}
 		Operator<double2> A; A.h = h;
 		if (solver_id == LCGB200_CPCG) A.diag = (const double2*)h->diag;
 		auto make_pf = [&](const double2* m_dev) -> ProgressFn {
 			if (!Pfp) return ProgressFn();
 			return [=](double res, int k) { return Pfp(h->user, m_dev, res, &para, h->n_rows, h->nnz, k); };
 		};
-		const int n_ext = std::max(h->n_cols, h->t_handle ? h->t_handle->n_cols : 0);
-		return do_solve_cplx(h, A, solver_id, (double2*)m, (const double2*)B, para, h->n_rows, n_ext, h->n_global, make_pf,
+		return do_solve_cplx<double2>(h, A, solver_id, (double2*)m, (const double2*)B, para, h->n_rows, n_ext, h->n_global, make_pf,
 			(flags & LCGB200_VEC_DEVICE) != 0, (cudaStream_t)stream, info);
 	});
 }
@@ -974,9 +1013,15 @@ int lcgb200_solver_constrained_cuda(lcgb200_axfunc_cuda_ptr Afp, lcgb200_progres
 	return ref_real(Afp, nullptr, Pfp, m, B, low, hig, n_size, nz_size, param, instance, cub, cus, id);
 }
 
-static int ref_cplx(lcgb200_caxfunc_cuda_ptr Afp, lcgb200_caxfunc_cuda_ptr Mfp, lcgb200_cprogress_cuda_ptr Pfp, void* m, const void* B,
+}  // extern "C"
+
+// ZV = double2: clcg_cuda.h entry points; ZV = ZF: the cuComplex overloads of clcg_cudaf.h (progress callback with a float `converge`)
+template <class ZV, class PfT>
+static int ref_cplx(lcgb200_caxfunc_cuda_ptr Afp, lcgb200_caxfunc_cuda_ptr Mfp, PfT Pfp, void* m, const void* B,
 	const int n, const int nz, const lcgb200_cpara* param, void* instance, lcgb200_cublas_t cub, lcgb200_cusparse_t cus, int solver_id)
 {
+	constexpr bool kF32 = std::is_same<ZV, ZF>::value;
+	constexpr int kValueType = kF32 ? LCGB200_COMPLEX_FLOAT : LCGB200_COMPLEX, kCudaType = kF32 ? 4 : 5;   // CUDA_C_32F / CUDA_C_64F
 	const lcgb200_cpara para = param ? *param : kDefCPara;
 	int rc = check_cplx(n, para, m, B);
 	if (rc) return rc;
@@ -987,7 +1032,7 @@ static int ref_cplx(lcgb200_caxfunc_cuda_ptr Afp, lcgb200_caxfunc_cuda_ptr Mfp, 
 	{
 		CsrHandle* h = reinterpret_cast<CsrHandle*>(instance);
 		if (!h) return LCGB200_INVALID_POINTER;
-		if (h->value_type != LCGB200_COMPLEX || h->n_rows != n) return LCGB200_C_SIZE_NOT_MATCH;
+		if (h->value_type != kValueType || h->n_rows != n) return LCGB200_C_SIZE_NOT_MATCH;
 		if (solver_id == LCGB200_CBICG && !h->t_row_ptr && !h->t_handle) { set_error_msg("CLCG_BICG needs LCGB200_CSR_TRANSPOSE"); return LCGB200_C_UNKNOWN_SOLVER; }
 		if (solver_id == LCGB200_CPCG)
 		{
@@ -995,38 +1040,40 @@ static int ref_cplx(lcgb200_caxfunc_cuda_ptr Afp, lcgb200_caxfunc_cuda_ptr Mfp, 
 			else if (!Mfp) return LCGB200_INVALID_POINTER;
 		}
 		return guarded([&]() {
-			Operator<double2> A; A.h = h;
-			DescrCache dc{n, 5, {}};
+			Operator<ZV> A; A.h = h;
+			DescrCache dc{n, kCudaType, {}};
 			if (solver_id == LCGB200_CPCG)
 			{
-				if (Mfp == lcgb200_jacobi_cmx) A.diag = (const double2*)h->diag;
+				if (Mfp == lcgb200_jacobi_cmx) A.diag = (const ZV*)h->diag;
 				else
 				{
 					if (!g_cusparse.load()) throw ApiFailure{LCGB200_UNKNOWN_ERROR};
-					A.precond = [&](const double2* x, double2* y, int) { Mfp(h->user, cub, cus, dc.get(x), dc.get(y), n, nz, 0); };
+					A.precond = [&](const ZV* x, ZV* y, int) { Mfp(h->user, cub, cus, dc.get(x), dc.get(y), n, nz, 0); };
 				}
 			}
-			auto make_pf = [&](const double2* m_dev) -> ProgressFn {
+			auto make_pf = [&](const ZV* m_dev) -> ProgressFn {
 				if (!Pfp) return ProgressFn();
 				return [=](double res, int k) { return Pfp(h->user, m_dev, res, &para, n, nz, k); };
 			};
-			return do_solve_cplx(h, A, solver_id, (double2*)m, (const double2*)B, para, n, std::max(h->n_cols, h->t_handle ? h->t_handle->n_cols : 0), h->n_global, make_pf, false, nullptr, nullptr);
+			return do_solve_cplx<ZV>(h, A, solver_id, (ZV*)m, (const ZV*)B, para, n, std::max(h->n_cols, h->t_handle ? h->t_handle->n_cols : 0), h->n_global, make_pf, false, nullptr, nullptr);
 		});
 	}
 	if (solver_id == LCGB200_CPCG && (!Mfp || Mfp == lcgb200_jacobi_cmx)) return LCGB200_INVALID_POINTER;
 	return guarded([&]() {
 		if (!g_cusparse.load()) throw ApiFailure{LCGB200_UNKNOWN_ERROR};
-		DescrCache dc{n, 5, {}};
-		Operator<double2> A;
-		A.apply = [&](const double2* x, double2* y, int op) { Afp(instance, cub, cus, dc.get(x), dc.get(y), n, nz, op); };
-		if (solver_id == LCGB200_CPCG) A.precond = [&](const double2* x, double2* y, int) { Mfp(instance, cub, cus, dc.get(x), dc.get(y), n, nz, 0); };
-		auto make_pf = [&](const double2* m_dev) -> ProgressFn {
+		DescrCache dc{n, kCudaType, {}};
+		Operator<ZV> A;
+		A.apply = [&](const ZV* x, ZV* y, int op) { Afp(instance, cub, cus, dc.get(x), dc.get(y), n, nz, op); };
+		if (solver_id == LCGB200_CPCG) A.precond = [&](const ZV* x, ZV* y, int) { Mfp(instance, cub, cus, dc.get(x), dc.get(y), n, nz, 0); };
+		auto make_pf = [&](const ZV* m_dev) -> ProgressFn {
 			if (!Pfp) return ProgressFn();
 			return [=](double res, int k) { return Pfp(instance, m_dev, res, &para, n, nz, k); };
 		};
-		return do_solve_cplx(nullptr, A, solver_id, (double2*)m, (const double2*)B, para, n, n, n, make_pf, false, nullptr, nullptr);
+		return do_solve_cplx<ZV>(nullptr, A, solver_id, (ZV*)m, (const ZV*)B, para, n, n, n, make_pf, false, nullptr, nullptr);
 	});
 }
+
+extern "C" {
 
 int lcgb200_csolver_cuda(lcgb200_caxfunc_cuda_ptr Afp, lcgb200_cprogress_cuda_ptr Pfp, void* m, const void* B,
 	const int n_size, const int nz_size, const lcgb200_cpara* param, void* instance,
@@ -1039,7 +1086,7 @@ int lcgb200_csolver_cuda(lcgb200_caxfunc_cuda_ptr Afp, lcgb200_cprogress_cuda_pt
 		case LCGB200_CBICG: case LCGB200_CBICG_SYM: case LCGB200_CCGS: case LCGB200_CBICGSTAB: case LCGB200_CTFQMR: break;
 		default: return LCGB200_C_UNKNOWN_SOLVER;
 	}
-	return ref_cplx(Afp, nullptr, Pfp, m, B, n_size, nz_size, param, instance, cub, cus, solver_id);
+	return ref_cplx<double2>(Afp, nullptr, Pfp, m, B, n_size, nz_size, param, instance, cub, cus, solver_id);
 }
 
 int lcgb200_csolver_preconditioned_cuda(lcgb200_caxfunc_cuda_ptr Afp, lcgb200_caxfunc_cuda_ptr Mfp, lcgb200_cprogress_cuda_ptr Pfp,
@@ -1047,7 +1094,25 @@ int lcgb200_csolver_preconditioned_cuda(lcgb200_caxfunc_cuda_ptr Afp, lcgb200_ca
 	lcgb200_cublas_t cub, lcgb200_cusparse_t cus, int solver_id)
 {
 	if (solver_id != LCGB200_CPCG) return LCGB200_C_UNKNOWN_SOLVER;	// clcg_cuda.cu:75-83
-	return ref_cplx(Afp, Mfp, Pfp, m, B, n_size, nz_size, param, instance, cub, cus, LCGB200_CPCG);
+	return ref_cplx<double2>(Afp, Mfp, Pfp, m, B, n_size, nz_size, param, instance, cub, cus, LCGB200_CPCG);
+}
+
+// replace the cuComplex overloads of clcg_solver_cuda / clcg_solver_preconditioned_cuda (clcg_cudaf.h:81-83,103-105;
+// clcg_cudaf.cu: BICG :86-252, BICG_SYM :254-401, PCG :403-558).  m, B: HOST arrays of n_size float pairs.
+int lcgb200_csolver_cudaf(lcgb200_caxfunc_cuda_ptr Afp, lcgb200_cprogress_cudaf_ptr Pfp, void* m, const void* B,
+	const int n_size, const int nz_size, const lcgb200_cpara* param, void* instance,
+	lcgb200_cublas_t cub, lcgb200_cusparse_t cus, int solver_id)
+{
+	if (solver_id != LCGB200_CBICG && solver_id != LCGB200_CBICG_SYM) return LCGB200_C_UNKNOWN_SOLVER;	// clcg_cudaf.cu:42-60
+	return ref_cplx<ZF>(Afp, nullptr, Pfp, m, B, n_size, nz_size, param, instance, cub, cus, solver_id);
+}
+
+int lcgb200_csolver_preconditioned_cudaf(lcgb200_caxfunc_cuda_ptr Afp, lcgb200_caxfunc_cuda_ptr Mfp, lcgb200_cprogress_cudaf_ptr Pfp,
+	void* m, const void* B, const int n_size, const int nz_size, const lcgb200_cpara* param, void* instance,
+	lcgb200_cublas_t cub, lcgb200_cusparse_t cus, int solver_id)
+{
+	if (solver_id != LCGB200_CPCG) return LCGB200_C_UNKNOWN_SOLVER;	// clcg_cudaf.cu:70-84
+	return ref_cplx<ZF>(Afp, Mfp, Pfp, m, B, n_size, nz_size, param, instance, cub, cus, LCGB200_CPCG);
 }
 
 }  // extern "C"
@@ -1194,7 +1259,7 @@ int lcgb200_csolver(lcgb200_caxfunc_ptr Afp, lcgb200_cprogress_ptr Pfp, void* m,
 				return Pfp(user, hs.m, res, &para, n, k);
 			};
 		};
-		return do_solve_cplx(h, A, solver_id, (double2*)m, (const double2*)B, para, n, h ? std::max(h->n_cols, h->t_handle ? h->t_handle->n_cols : 0) : n, h ? h->n_global : (long long)n, make_pf, false, nullptr, nullptr);
+		return do_solve_cplx<double2>(h, A, solver_id, (double2*)m, (const double2*)B, para, n, h ? std::max(h->n_cols, h->t_handle ? h->t_handle->n_cols : 0) : n, h ? h->n_global : (long long)n, make_pf, false, nullptr, nullptr);
 	});
 }
 

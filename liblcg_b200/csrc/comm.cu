@@ -85,6 +85,7 @@ void nccl_check(int rc, const char* what)
 template <class T>
 __global__ void __launch_bounds__(256) k_halo_exchange(CommDev* c, T* __restrict__ x, DevState* st)
 {
+	pdl_enter();
 	if (st_done(st)) return;
 	const unsigned long long seq = c->halo_seq + 1;
 	const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
@@ -136,6 +137,7 @@ __global__ void __launch_bounds__(256) k_halo_exchange(CommDev* c, T* __restrict
 template <class T>
 __global__ void __launch_bounds__(256) k_halo_push(CommDev* c, const T* __restrict__ x, DevState* st)
 {
+	pdl_enter();
 	if (st_done(st)) return;
 	const unsigned long long seq = c->halo_seq + 1;
 	__shared__ int s_ok;
@@ -210,8 +212,8 @@ public:
 	void push(const void* x, int elem_bytes, cudaStream_t s, DevState* st) override
 	{
 		if (peers.empty()) return;
-		if (elem_bytes == 8) k_halo_push<double><<<push_grid, 256, 0, s>>>(d_dev, (const double*)x, st);
-		else k_halo_push<double2><<<push_grid, 256, 0, s>>>(d_dev, (const double2*)x, st);
+		if (elem_bytes == 8) launch_k(k_halo_push<double>, push_grid, 256, 0, s, d_dev, (const double*)x, st);
+		else launch_k(k_halo_push<double2>, push_grid, 256, 0, s, d_dev, (const double2*)x, st);
 		halos++;
 	}
 	// after a solve on the NVLink transport: did a cross-GPU wait time out?  A timed-out communicator is poisoned — its
@@ -248,8 +250,8 @@ public:
 		if (peers.empty()) return;
 		if (p2p && p2p_ready)
 		{
-			if (elem_bytes == 8) k_halo_exchange<double><<<push_grid, 256, 0, s>>>(d_dev, (double*)x_ext, st);
-			else k_halo_exchange<double2><<<push_grid, 256, 0, s>>>(d_dev, (double2*)x_ext, st);
+			if (elem_bytes == 8) launch_k(k_halo_exchange<double>, push_grid, 256, 0, s, d_dev, (double*)x_ext, st);
+			else launch_k(k_halo_exchange<double2>, push_grid, 256, 0, s, d_dev, (double2*)x_ext, st);
 			halos++;
 			return;
 		}

@@ -61,8 +61,10 @@ enum : int {
 constexpr int kMaxRanks = 8;
 constexpr int kArSlots = 4;
 struct CommWindow {
-	unsigned long long ar_flag[kArSlots][kMaxRanks];
-	double ar_val[kArSlots][kMaxRanks][kMaxRed];
+	// reduction totals, one 64-bit word per HALF double: low 32 bits = data, high 32 bits = sequence tag.  An aligned 8-byte
+	// store lands atomically, so a word whose tag matches carries valid data: no fence and no separate flag between the
+	// payload and its arrival signal (the "LL" idea of NCCL's low-latency protocol) — one NVLink one-way trip per reduction.
+	unsigned long long ar_ll[kArSlots][kMaxRanks][2 * kMaxRed];
 	unsigned long long halo_flag[kMaxRanks];     // [source rank]: sequence number of the last halo it pushed to me
 	unsigned long long halo_ack[kMaxRanks];      // [receiving rank]: sequence number of the last halo of MINE it has consumed
 	// mailbox: 2 buffers x n_ghost x 16 bytes follow (offset kMailboxOffset)
@@ -153,6 +155,13 @@ struct DevState {
 //     rank's totals have landed in MY window and sums them in rank order (bitwise identical on all ranks).  Returns true
 //     with tot[] = global totals in lane 0: the producing kernel's tail IS the allreduce, the caller runs the scalar
 //     epilogue right there and no separate launch exists.  A peer that never arrives ends the solve with an error.
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p)
+{
+	unsigned long long v;
+	asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+
 __device__ __forceinline__ bool reduce_across_ranks(DevState* st, double* tot, int nred)
 {
 	const int lane = threadIdx.x & 31;
@@ -163,24 +172,48 @@ __device__ __forceinline__ bool reduce_across_ranks(DevState* st, double* tot, i
 	}
 	CommDev* c = st->comm;
 	const unsigned long long seq = c->ar_seq + 1;
+	const unsigned long long tag = (seq & 0xffffffffull) << 32;
 	const int slot = (int)(seq % kArSlots);
 	if (lane < c->size)
-		for (int r = 0; r < nred; r++) c->win[lane]->ar_val[slot][c->rank][r] = tot[r];
-	__threadfence_system();
-	if (lane < c->size) st_relaxed_sys(&c->win[lane]->ar_flag[slot][c->rank], seq);
-	CommWindow* w = c->win[c->rank];
+	{	// lane p -> rank p's window, all peers in parallel; tagged words need no fence
+		unsigned long long* dst = c->win[lane]->ar_ll[slot][c->rank];
+		for (int r = 0; r < nred; r++)
+		{
+			const unsigned long long bits = (unsigned long long)__double_as_longlong(tot[r]);
+			st_relaxed_sys(dst + 2 * r, (bits & 0xffffffffull) | tag);
+			st_relaxed_sys(dst + 2 * r + 1, (bits >> 32) | tag);
+		}
+	}
+	// lane s collects rank s's totals out of MY window
+	double mine[kMaxRed];
 	bool ok = true;
-	if (lane < c->size) ok = spin_until(&w->ar_flag[slot][lane], seq, st->spin_timeout_ns);
+	if (lane < c->size)
+	{
+		const unsigned long long* src = c->win[c->rank]->ar_ll[slot][lane];
+		const unsigned long long t0 = global_ns();
+		for (int r = 0; r < nred && ok; r++)
+		{
+			unsigned long long lo, hi;
+			while (true)
+			{
+				lo = ld_relaxed_sys(src + 2 * r); hi = ld_relaxed_sys(src + 2 * r + 1);
+				if ((lo & 0xffffffff00000000ull) == tag && (hi & 0xffffffff00000000ull) == tag) break;
+				if (st->spin_timeout_ns && global_ns() - t0 > st->spin_timeout_ns) { ok = false; break; }
+			}
+			mine[r] = __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
+		}
+	}
 	ok = __all_sync(0xffffffffu, ok);
-	if (lane != 0) return false;
-	c->ar_seq = seq;
-	if (!ok) { st->ret = RC_UNKNOWN; st->done = 1; c->abort_flag = 1; return false; }
+	// every lane sums the ranks' values in rank order: bitwise identical totals on all ranks
 	for (int r = 0; r < nred; r++)
 	{
 		double v = 0.0;
-		for (int src = 0; src < c->size; src++) v += *((volatile double*)&w->ar_val[slot][src][r]);
+		for (int srk = 0; srk < c->size; srk++) v += __shfl_sync(0xffffffffu, (lane < c->size && ok) ? mine[r] : 0.0, srk);
 		tot[r] = v;
 	}
+	if (lane != 0) return false;
+	c->ar_seq = seq;
+	if (!ok) { st->ret = RC_UNKNOWN; st->done = 1; c->abort_flag = 1; return false; }
 	return true;
 }
 
@@ -263,6 +296,17 @@ __device__ __forceinline__ zc zdiv(zc a, zc b)
 	else { ratio = b.y / b.x; denom = b.y * ratio + b.x; re = (a.y * ratio + a.x) / denom; im = (a.y - a.x * ratio) / denom; }
 	return make_double2(re, im);
 }
+// Single-precision complex STORAGE (cuComplex vectors and matrix values of clcg_cudaf.h:81-105): 8 bytes in memory, converts
+// to and from the double2 the solver arithmetic uses, so the same step functors serve both precisions — they read with
+// `Z v = x[i]` and write with `x[i] = v`.  Scalars, dot products and norms stay in double.
+struct __align__(8) ZF {
+	float x, y;
+	ZF() = default;
+	__host__ __device__ ZF(float re, float im) : x(re), y(im) {}
+	__host__ __device__ ZF(const double2& v) : x((float)v.x), y((float)v.y) {}
+	__host__ __device__ operator double2() const { return make_double2((double)x, (double)y); }
+};
+
 __device__ __forceinline__ zc sc_ldz(const DevState* st, int i) { return make_double2(st->sc[i], st->sc[i + 1]); }
 __device__ __forceinline__ void sc_stz(DevState* st, int i, zc v) { st->sc[i] = v.x; st->sc[i + 1] = v.y; }
 
@@ -408,6 +452,33 @@ __device__ __forceinline__ void push_signal(CommDev* c, unsigned long long seq, 
 	}
 }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------
+// The kernels of an iteration form a chain in which each one needs everything its predecessor wrote.  Launched with the
+// programmatic-stream-serialization attribute, a kernel may be SCHEDULED while its predecessor is still running: its blocks
+// become resident as the predecessor's blocks retire and park in griddepcontrol.wait until the predecessor has completed
+// and its writes are visible — the launch latency and block scheduling of kernel k+1 overlap the tail of kernel k (the
+// last block's grid reduction and its cross-GPU round trip).  Every kernel launched through launch_k() therefore starts
+// with pdl_enter(): wait for the predecessor, then allow the successor to be scheduled behind us.
+__device__ __forceinline__ void pdl_enter()
+{
+	asm volatile("griddepcontrol.wait;" ::: "memory");
+	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+bool pdl_enabled();   // engine.cu: lcgb200_set_pdl / LCGB200_PDL (default on)
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t s, Args&&... args)
+{
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1u : 0u;
+	return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 struct OpBase {
 	__device__ __forceinline__ bool active(const DevState*) const { return true; }
 	__device__ __forceinline__ void begin(const DevState*) {}
@@ -427,6 +498,7 @@ struct OpBase {
 template <class Op, bool PUSH = false, class T = double>
 __global__ void __launch_bounds__(kThreads) k_vec(Op op_in, size_t n, DevState* st, double* partials, CommDev* comm = nullptr, const T* push_src = nullptr)
 {
+	pdl_enter();
 	if (st_done(st)) return;
 	Op op = op_in;
 	if (!op.active(st)) return;
@@ -469,6 +541,7 @@ __global__ void __launch_bounds__(kThreads) k_vec(Op op_in, size_t n, DevState* 
 template <class Op>
 __global__ void k_finish(Op op_in, DevState* st)
 {
+	pdl_enter();
 	if (st_done(st)) return;
 	Op op = op_in;
 	if (!op.active(st)) return;

@@ -22,6 +22,7 @@
 // re-used out of L1, and at any moment all CTAs work inside one band of rows, so the band's x stays L2-resident.
 #pragma once
 #include "common.cuh"
+#include <type_traits>
 
 namespace lcgb200 {
 
@@ -68,6 +69,7 @@ struct CsrDev {
 template <class T> struct TileCfg;
 template <> struct TileCfg<double> { static constexpr int NNZ = kTileNnzReal; static constexpr int CTAS = kSpmvCtasPerSm; };
 // complex rows carry twice the registers per entry: 2 CTAs per SM (112 registers) keep the gather loop spill-free
+template <> struct TileCfg<ZF> { static constexpr int NNZ = kTileNnzReal; static constexpr int CTAS = kSpmvCtasPerSm > 2 ? 2 : kSpmvCtasPerSm; };   // 8-byte entries like double, complex arithmetic
 template <> struct TileCfg<double2> { static constexpr int NNZ = kTileNnzCplx; static constexpr int CTAS = kSpmvCtasPerSm > 2 ? 2 : kSpmvCtasPerSm; };
 
 // shared-memory stage layout (bytes): val | col | row_ptr slice
@@ -87,6 +89,18 @@ __device__ __forceinline__ double2 mulacc(double2 acc, double2 a, double2 x)
 	acc.y = fma(a.x, x.y, acc.y); acc.y = fma(a.y, x.x, acc.y);
 	return acc;
 }
+// single-precision complex entries: products and row sums in float (as cusparseSpMV does for CUDA_C_32F)
+__device__ __forceinline__ ZF mulacc(ZF acc, ZF a, ZF x)
+{
+	acc.x = fmaf(a.x, x.x, acc.x); acc.x = fmaf(-a.y, x.y, acc.x);
+	acc.y = fmaf(a.x, x.y, acc.y); acc.y = fmaf(a.y, x.x, acc.y);
+	return acc;
+}
+__device__ __forceinline__ ZF tzero(ZF) { return ZF(0.f, 0.f); }
+__device__ __forceinline__ ZF tconj(ZF a) { return ZF(a.x, -a.y); }
+__device__ __forceinline__ ZF tadd(ZF a, ZF b) { return ZF(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ ZF tshfl_xor(ZF v, int o) { return ZF(__shfl_xor_sync(0xffffffffu, v.x, o), __shfl_xor_sync(0xffffffffu, v.y, o)); }
+__device__ __forceinline__ ZF tldg(const ZF* p) { const float2 t = __ldg(reinterpret_cast<const float2*>(p)); return ZF(t.x, t.y); }
 __device__ __forceinline__ double tzero(double) { return 0.0; }
 __device__ __forceinline__ double2 tzero(double2) { return make_double2(0.0, 0.0); }
 __device__ __forceinline__ double tconj(double a) { return a; }
@@ -269,6 +283,7 @@ template <class T, int LPR, bool CONJ, class Epi, bool PART = false>
 __global__ void __launch_bounds__(kSpmvThreads, TileCfg<T>::CTAS) k_spmv(CsrDev<T> A, const T* __restrict__ x, T* __restrict__ y, Epi epi_in,
 	DevState* st, double* partials)
 {
+	pdl_enter();
 	if (st_done(st)) return;
 	typedef StageCfg<T> SC;
 	constexpr int TN = SC::NNZ;
@@ -389,6 +404,7 @@ template <int LPR, class Epi>
 __global__ void __launch_bounds__(kSpmvThreads, kSpmvCtasPerSm) k_spmv_dict(CsrDev<double> A, const double* __restrict__ x, double* __restrict__ y, Epi epi_in,
 	DevState* st, double* partials)
 {
+	pdl_enter();
 	if (st_done(st)) return;
 	typedef DictStage SC;
 	extern __shared__ __align__(128) unsigned char smem[];
@@ -524,6 +540,7 @@ template <class Epi>
 __global__ void __launch_bounds__(kThreads) k_spmv_pat(CsrDev<double> A, const double* __restrict__ x, double* __restrict__ y, Epi epi_in,
 	DevState* st, double* partials)
 {
+	pdl_enter();
 	if (st_done(st)) return;
 	extern __shared__ __align__(16) unsigned char smem[];
 	PatEntry* s_ent = reinterpret_cast<PatEntry*>(smem);
@@ -639,7 +656,7 @@ inline void launch_spmv_pat(const CsrDev<double>& A, const double* x, double* y,
 	const int limit = spmv_grid_limit(4);
 	int grid = n_chunks < limit ? n_chunks : limit;
 	if (grid < 1) grid = 1;
-	kern<<<grid, kThreads, smem, s>>>(A, x, y, epi, st, partials);
+	launch_k(kern, grid, kThreads, smem, s, A, x, y, epi, st, partials);
 }
 
 // Adaptor: run an SpMV epilogue as a plain vector kernel over an already computed y (user-callback operators).
@@ -677,14 +694,14 @@ inline void launch_spmv_lpr(const CsrDev<T>& A, const T* x, T* y, const Epi& epi
 		static PerDeviceOnce once;   // per instantiation
 		auto kern = k_spmv<T, LPR, CONJ, Epi, true>;
 		if (once.first()) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, StageCfg<T>::TOTAL);
-		kern<<<grid, kSpmvThreads, StageCfg<T>::TOTAL, s>>>(A, x, y, epi, st, partials);
+		launch_k(kern, grid, kSpmvThreads, StageCfg<T>::TOTAL, s, A, x, y, epi, st, partials);
 	}
 	else
 	{
 		static PerDeviceOnce once;
 		auto kern = k_spmv<T, LPR, CONJ, Epi, false>;
 		if (once.first()) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, StageCfg<T>::TOTAL);
-		kern<<<grid, kSpmvThreads, StageCfg<T>::TOTAL, s>>>(A, x, y, epi, st, partials);
+		launch_k(kern, grid, kSpmvThreads, StageCfg<T>::TOTAL, s, A, x, y, epi, st, partials);
 	}
 }
 
@@ -698,7 +715,7 @@ inline void launch_spmv_dict_lpr(const CsrDev<double>& A, const double* x, doubl
 	const int limit = spmv_grid_limit(kSpmvCtasPerSm);
 	int grid = n_chunks < limit ? n_chunks : limit;
 	if (grid < 1) grid = 1;
-	kern<<<grid, kSpmvThreads, DictStage::TOTAL, s>>>(A, x, y, epi, st, partials);
+	launch_k(kern, grid, kSpmvThreads, DictStage::TOTAL, s, A, x, y, epi, st, partials);
 }
 
 template <class Epi>
@@ -719,7 +736,7 @@ inline void launch_spmv_dict(const CsrDev<double>& A, const double* x, double* y
 template <class T, bool CONJ, class Epi>
 inline void launch_spmv(const CsrDev<T>& A, const T* x, T* y, const Epi& epi, DevState* st, double* partials, cudaStream_t s)
 {
-	if constexpr (sizeof(T) == sizeof(double) && !CONJ)
+	if constexpr (std::is_same<T, double>::value && !CONJ)
 	{
 		if (A.pat) { launch_spmv_pat<Epi>(A, x, y, epi, st, partials, s); return; }      // row-pattern copy: 1 B per ROW
 		if (A.code) { launch_spmv_dict<Epi>(A, x, y, epi, st, partials, s); return; }   // dictionary copy: 2 B per entry

@@ -19,6 +19,14 @@ const char* last_error() { return g_err.c_str(); }
 
 Settings& settings() { static Settings s; return s; }
 
+bool pdl_enabled()
+{
+	const int mode = settings().pdl;
+	if (mode >= 0) return mode != 0;
+	static const int env = [] { const char* e = getenv("LCGB200_PDL"); return e ? atoi(e) : 1; }();
+	return env != 0;
+}
+
 long long spin_timeout_ms()
 {
 	if (settings().spin_timeout_ms >= 0) return settings().spin_timeout_ms;

@@ -114,6 +114,7 @@ struct Settings {
 	int profile = 0;               // 1: bracket every kernel launch with CUDA events (bench roofline pass)
 	long long spin_timeout_ms = -1; // cross-GPU waits (NVLink transport); -1 = LCGB200_SPIN_TIMEOUT_MS or 30 s; 0 = wait for ever
 	int graphs = -1;               // CUDA graph per batch of iterations; -1 = LCGB200_GRAPHS or automatic
+	int pdl = -1;                  // programmatic dependent launch between the kernels of an iteration; -1 = LCGB200_PDL or on
 };
 long long spin_timeout_ms();
 Settings& settings();
@@ -168,7 +169,7 @@ public:
 	template <class Op> void vec(const Op& op, size_t n)
 	{
 		cudaEvent_t pe = profiling ? prof_begin(1) : nullptr;
-		k_vec<Op><<<vec_grid(n, Op::W), kThreads, 0, stream>>>(op, n, d_st, d_partials);
+		launch_k(k_vec<Op, false, double>, vec_grid(n, Op::W), kThreads, 0, stream, op, n, d_st, d_partials, (CommDev*)nullptr, (const double*)nullptr);
 		prof_end(pe);
 		launches++;
 		if (Op::NRED > 0 && multi()) finish_multi(op, Op::NRED);
@@ -184,7 +185,7 @@ public:
 	{
 		if (!(halo_in_spmv() && comm->fused_push_ok())) { vec(op, n); return; }
 		cudaEvent_t pe = profiling ? prof_begin(1) : nullptr;
-		k_vec<Op, true, T><<<vec_grid(n, Op::W), kThreads, 0, stream>>>(op, n, d_st, d_partials, cache->p2p_dev(), out);
+		launch_k(k_vec<Op, true, T>, vec_grid(n, Op::W), kThreads, 0, stream, op, n, d_st, d_partials, cache->p2p_dev(), out);
 		prof_end(pe);
 		launches++;
 		pushed_vec = out;
@@ -195,7 +196,7 @@ public:
 	{
 		if (p2p()) return;   // NVLink transport: the producing kernel's last block already summed across the ranks and ran the epilogue
 		comm->allreduce(reinterpret_cast<double*>(reinterpret_cast<char*>(d_st) + offsetof(DevState, red)), nred, stream);
-		k_finish<Op><<<1, 1, 0, stream>>>(op, d_st);
+		launch_k(k_finish<Op>, 1, 1, 0, stream, op, d_st);
 		launches++;
 	}
 

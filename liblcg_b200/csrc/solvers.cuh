@@ -13,6 +13,9 @@ int real_vector_count(int solver_id);
 int solve_complex(Engine& E, const Operator<double2>& A, int solver_id, double2* m, const double2* B,
 	const lcgb200_cpara& para, size_t n, size_t next);
 int complex_vector_count(int solver_id);
+// the same loops on cuComplex vectors (clcg_cudaf.h:81-105): storage float2, arithmetic and scalars in double
+int solve_complexf(Engine& E, const Operator<ZF>& A, int solver_id, ZF* m, const ZF* B,
+	const lcgb200_cpara& para, size_t n, size_t next);
 
 const char* last_error();
 

@@ -8,9 +8,24 @@
 #include <cstdlib>
 #include <ctime>
 
+// The file is compiled twice: as it is for cuDoubleComplex vectors (solve_complex), and with -DLCG_CPLX_FLOAT for cuComplex
+// vectors (solve_complexf: the entry points of clcg_cudaf.h:81-105, reference implementation clcg_cudaf.cu).  ZV is the type
+// of a vector / matrix element in memory; the arithmetic of every step runs on Z = double2 either way.
+#ifdef LCG_CPLX_FLOAT
+#define LCG_CPLX_NS cf32
+#else
+#define LCG_CPLX_NS cf64
+#endif
+
 namespace lcgb200 {
+namespace LCG_CPLX_NS {
 
 typedef double2 Z;
+#ifdef LCG_CPLX_FLOAT
+typedef ZF ZV;
+#else
+typedef double2 ZV;
+#endif
 
 __device__ __forceinline__ void acc_inner(double* acc, Z a, Z b)	// acc += conj(a) b
 {
@@ -29,7 +44,7 @@ __device__ __forceinline__ bool bad(double v) { return v != v; }
 struct EpiInnerAlpha {
 	static constexpr int NRED = 2;
 	static constexpr bool ACTIVE = true;
-	const Z* w;
+	const ZV* w;
 	__device__ void begin(const DevState*) {}
 	__device__ void row(int i, Z yi, Z, double* acc) const { acc_inner(acc, w[i], yi); }
 	__device__ void finish(DevState* st, const double* tot) const { sc_stz(st, SC_ALPHA, zdiv(sc_ldz(st, SC_RHO), zmk(tot[0], tot[1]))); }
@@ -56,7 +71,7 @@ struct EpiCOmega {
 // ======================================================================================== BiCG (clcg.cpp:77-226)
 struct OpCbInit : OpBase {	// d1 = r1 = B - Ax, d2 = r2 = conj(r1); <r2,r1>, m.m, r.r (clcg.cpp:102-121) + first head
 	static constexpr int NRED = 4, W = 1;
-	const Z* m; const Z* Ax; const Z* B; Z* r1; Z* r2; Z* d1; Z* d2;
+	const ZV* m; const ZV* Ax; const ZV* B; ZV* r1; ZV* r2; ZV* d1; ZV* d2;
 	template <int V> __device__ void elem(size_t i, double* acc) const
 	{
 		Z r = zsub(B[i], Ax[i]), rc = zconj(r), mi = m[i];
@@ -74,7 +89,7 @@ struct OpCbInit : OpBase {	// d1 = r1 = B - Ax, d2 = r2 = conj(r1); <r2,r1>, m.m
 
 struct OpCbUpdate1 : OpBase {	// m += a d1, r1 -= a A d1; m.m, r.r (clcg.cpp:174-186)
 	static constexpr int NRED = 2, W = 1;
-	Z* m; const Z* d1; Z* r1; const Z* Ax; Z ak;
+	ZV* m; const ZV* d1; ZV* r1; const ZV* Ax; Z ak;
 	__device__ void begin(const DevState* st) { ak = sc_ldz(st, SC_ALPHA); }
 	template <int V> __device__ void elem(size_t i, double* acc) const
 	{
@@ -87,7 +102,7 @@ struct OpCbUpdate1 : OpBase {	// m += a d1, r1 -= a A d1; m.m, r.r (clcg.cpp:174
 
 struct OpCbUpdate2 : OpBase {	// r2 -= conj(a) A^H d2; NaN; <r2,r1>; beta (clcg.cpp:190-206) + head
 	static constexpr int NRED = 2, W = 1;
-	Z* r2; const Z* Ax; const Z* r1; Z akc;
+	ZV* r2; const ZV* Ax; const ZV* r1; Z akc;
 	__device__ void begin(const DevState* st) { akc = zconj(sc_ldz(st, SC_ALPHA)); }
 	template <int V> __device__ void elem(size_t i, double* acc) const
 	{
@@ -107,7 +122,7 @@ struct OpCbUpdate2 : OpBase {	// r2 -= conj(a) A^H d2; NaN; <r2,r1>; beta (clcg.
 
 struct OpCbDir : OpBase {	// d1 = r1 + b d1, d2 = r2 + conj(b) d2 (clcg.cpp:208-213)
 	static constexpr int NRED = 0, W = 1;
-	const Z* r1; const Z* r2; Z* d1; Z* d2; Z bk;
+	const ZV* r1; const ZV* r2; ZV* d1; ZV* d2; Z bk;
 	__device__ void begin(const DevState* st) { bk = sc_ldz(st, SC_BETA); }
 	template <int V> __device__ void elem(size_t i, double*) const
 	{
@@ -116,19 +131,19 @@ struct OpCbDir : OpBase {	// d1 = r1 + b d1, d2 = r2 + conj(b) d2 (clcg.cpp:208-
 	}
 };
 
-static int run_cbicg(Engine& E, const Operator<Z>& A, Z* m, const Z* B, size_t n, size_t next)
+static int run_cbicg(Engine& E, const Operator<ZV>& A, ZV* m, const ZV* B, size_t n, size_t next)
 {
-	Z* r1 = E.alloc<Z>(next); Z* r2 = E.alloc<Z>(next); Z* d1 = E.alloc<Z>(next); Z* d2 = E.alloc<Z>(next); Z* Ax = E.alloc<Z>(next);
-	E.spmv(A, m, Ax, EpiNone<Z>{});
+	ZV* r1 = E.alloc<ZV>(next); ZV* r2 = E.alloc<ZV>(next); ZV* d1 = E.alloc<ZV>(next); ZV* d2 = E.alloc<ZV>(next); ZV* Ax = E.alloc<ZV>(next);
+	E.spmv(A, m, Ax, EpiNone<ZV>{});
 	E.vec_push(OpCbInit{{}, m, Ax, B, r1, r2, d1, d2}, n, d1);
 	std::function<void(int)> batch;
 	if (E.small_system(A) && A.h->lpr == A.h->t_lpr)
-		batch = [&](int k) { E.fused(k, 2, E.ph_spmv(A, d1, Ax, EpiInnerAlpha{d2}), E.ph_vec(OpCbUpdate1{{}, m, d1, r1, Ax, zc()}, n), E.ph_spmv_h(A, d2, Ax, EpiNone<Z>{}),
+		batch = [&](int k) { E.fused(k, 2, E.ph_spmv(A, d1, Ax, EpiInnerAlpha{d2}), E.ph_vec(OpCbUpdate1{{}, m, d1, r1, Ax, zc()}, n), E.ph_spmv_h(A, d2, Ax, EpiNone<ZV>{}),
 			E.ph_vec(OpCbUpdate2{{}, r2, Ax, r1, zc()}, n), E.ph_vec(OpCbDir{{}, r1, r2, d1, d2, zc()}, n)); };
 	return E.run([&]() {
 		E.spmv(A, d1, Ax, EpiInnerAlpha{d2});
 		E.vec(OpCbUpdate1{{}, m, d1, r1, Ax, zc()}, n);
-		E.spmv(A, d2, Ax, EpiNone<Z>{}, 2);	// A^H d2 (MatTranspose, Conjugate — clcg.cpp:188)
+		E.spmv(A, d2, Ax, EpiNone<ZV>{}, 2);	// A^H d2 (MatTranspose, Conjugate — clcg.cpp:188)
 		E.vec(OpCbUpdate2{{}, r2, Ax, r1, zc()}, n);
 		E.vec_push(OpCbDir{{}, r1, r2, d1, d2, zc()}, n, d1);
 		return false;
@@ -141,7 +156,7 @@ static int run_cbicg(Engine& E, const Operator<Z>& A, Z* m, const Z* B, size_t n
 template <int MODE>
 struct OpCsInit : OpBase {
 	static constexpr int NRED = 4, W = 1;
-	const Z* m; const Z* Ax; const Z* B; const Z* diag; Z* r; Z* z; Z* d;
+	const ZV* m; const ZV* Ax; const ZV* B; const ZV* diag; ZV* r; ZV* z; ZV* d;
 	template <int V> __device__ void elem(size_t i, double* acc) const
 	{
 		Z ri = zsub(B[i], Ax[i]), mi = m[i];
@@ -161,7 +176,7 @@ struct OpCsInit : OpBase {
 
 struct OpCsInitZ : OpBase {	// MODE 2: d = z, rho = r.z, then the first head
 	static constexpr int NRED = 2, W = 1;
-	const Z* r; const Z* z; Z* d;
+	const ZV* r; const ZV* z; ZV* d;
 	template <int V> __device__ void elem(size_t i, double* acc) const { Z zi = z[i]; d[i] = zi; acc_dotu(acc, r[i], zi); }
 	__device__ void finish(DevState* st, const double* tot) const
 	{
@@ -183,7 +198,7 @@ __device__ __forceinline__ void cs_tail(DevState* st, Z rho2)
 template <int MODE>
 struct OpCsUpdate : OpBase {	// m += a d, r -= a Ad [, z = r/diag]; m.m, r.r, rho' (clcg.cpp:323-347 / clcg_cuda.cu:518-539)
 	static constexpr int NRED = 4, W = 1;
-	Z* m; const Z* d; Z* r; const Z* Ax; const Z* diag; Z* z; Z ak;
+	ZV* m; const ZV* d; ZV* r; const ZV* Ax; const ZV* diag; ZV* z; Z ak;
 	__device__ void begin(const DevState* st) { ak = sc_ldz(st, SC_ALPHA); }
 	template <int V> __device__ void elem(size_t i, double* acc) const
 	{
@@ -203,24 +218,24 @@ struct OpCsUpdate : OpBase {	// m += a d, r -= a Ad [, z = r/diag]; m.m, r.r, rh
 
 struct OpCsRho : OpBase {	// MODE 2: rho' = r.z after the user's preconditioner
 	static constexpr int NRED = 2, W = 1;
-	const Z* r; const Z* z;
+	const ZV* r; const ZV* z;
 	template <int V> __device__ void elem(size_t i, double* acc) const { acc_dotu(acc, r[i], z[i]); }
 	__device__ void finish(DevState* st, const double* tot) const { cs_tail(st, zmk(tot[0], tot[1])); }
 };
 
 struct OpCsDir : OpBase {	// d = s + b d with s = r (BICG_SYM, clcg.cpp:349-353) or s = z (PCG, clcg_cuda.cu:536-537)
 	static constexpr int NRED = 0, W = 1;
-	const Z* s; Z* d; Z bk;
+	const ZV* s; ZV* d; Z bk;
 	__device__ void begin(const DevState* st) { bk = sc_ldz(st, SC_BETA); }
 	template <int V> __device__ void elem(size_t i, double*) const { d[i] = zadd(s[i], zmul(bk, d[i])); }
 };
 
-static int run_csym(Engine& E, const Operator<Z>& A, Z* m, const Z* B, size_t n, size_t next, bool pcg)
+static int run_csym(Engine& E, const Operator<ZV>& A, ZV* m, const ZV* B, size_t n, size_t next, bool pcg)
 {
-	Z* r = E.alloc<Z>(next); Z* d = E.alloc<Z>(next); Z* Ax = E.alloc<Z>(next);
-	Z* z = pcg ? E.alloc<Z>(next) : nullptr;
+	ZV* r = E.alloc<ZV>(next); ZV* d = E.alloc<ZV>(next); ZV* Ax = E.alloc<ZV>(next);
+	ZV* z = pcg ? E.alloc<ZV>(next) : nullptr;
 	const int mode = !pcg ? 0 : (A.diag ? 1 : 2);
-	E.spmv(A, m, Ax, EpiNone<Z>{});
+	E.spmv(A, m, Ax, EpiNone<ZV>{});
 	if (mode == 0) E.vec_push(OpCsInit<0>{{}, m, Ax, B, nullptr, r, z, d}, n, d);
 	else if (mode == 1) E.vec_push(OpCsInit<1>{{}, m, Ax, B, A.diag, r, z, d}, n, d);
 	else
@@ -252,7 +267,7 @@ static int run_csym(Engine& E, const Operator<Z>& A, Z* m, const Z* B, size_t n,
 // ======================================================================================== shadow residual
 // r0bar exactly as the reference draws it (lcg_complex.cpp:118-127 with l = 1+0i, h = 2+0i): libc srand/rand on
 // the host, the imaginary draw consumes a rand() too.  `skip` = global index of the first local element.
-static void draw_shadow(std::vector<Z>& host, size_t n, long seed, size_t skip)
+static void draw_shadow(std::vector<ZV>& host, size_t n, long seed, size_t skip)
 {
 	srand((unsigned)(seed ? seed : (long)time(nullptr)));
 	for (size_t i = 0; i < skip; i++) { (void)rand(); (void)rand(); }
@@ -267,7 +282,7 @@ static void draw_shadow(std::vector<Z>& host, size_t n, long seed, size_t skip)
 
 struct OpCResInit : OpBase {	// p = [u =] r = B - Ax [, d = 0]; m.m, r.r (clcg.cpp:392-396, 549-553, 709-719)
 	static constexpr int NRED = 2, W = 1;
-	const Z* m; const Z* Ax; const Z* B; Z* r; Z* p; Z* u; Z* dz;
+	const ZV* m; const ZV* Ax; const ZV* B; ZV* r; ZV* p; ZV* u; ZV* dz;
 	template <int V> __device__ void elem(size_t i, double* acc) const
 	{
 		Z ri = zsub(B[i], Ax[i]);
@@ -284,7 +299,7 @@ struct OpCResInit : OpBase {	// p = [u =] r = B - Ax [, d = 0]; m.m, r.r (clcg.c
 template <bool HEAD>
 struct OpCRho : OpBase {
 	static constexpr int NRED = 2, W = 1;
-	const Z* rb; const Z* r;
+	const ZV* rb; const ZV* r;
 	template <int V> __device__ void elem(size_t i, double* acc) const { acc_inner(acc, rb[i], r[i]); }
 	__device__ void finish(DevState* st, const double* tot) const
 	{
@@ -314,9 +329,9 @@ struct OpSeedAgree : OpBase {
 };
 
 template <bool HEAD>
-static bool init_shadow(Engine& E, Z* rb, const Z* r, size_t n, size_t skip)
+static bool init_shadow(Engine& E, ZV* rb, const ZV* r, size_t n, size_t skip)
 {
-	std::vector<Z> host;
+	std::vector<ZV> host;
 	long seed = settings().shadow_seed;
 	if (seed == 0 && E.multi())
 	{
@@ -328,7 +343,7 @@ static bool init_shadow(Engine& E, Z* rb, const Z* r, size_t n, size_t skip)
 	for (int attempt = 0; attempt < 64; attempt++)
 	{
 		draw_shadow(host, n, seed, skip);
-		LCG_CUDA_CHECK(cudaMemcpyAsync(rb, host.data(), n * sizeof(Z), cudaMemcpyHostToDevice, E.stream));
+		LCG_CUDA_CHECK(cudaMemcpyAsync(rb, host.data(), n * sizeof(ZV), cudaMemcpyHostToDevice, E.stream));
 		E.vec(OpCRho<HEAD>{{}, rb, r}, n);
 		E.read_state();	// also makes the pageable `host` buffer safe to reuse
 		if (!E.h_st->flag) return true;
@@ -341,7 +356,7 @@ static bool init_shadow(Engine& E, Z* rb, const Z* r, size_t n, size_t skip)
 // ======================================================================================== CGS (clcg.cpp:366-522)
 struct OpCQW : OpBase {	// q = u - a Ap, w = u + q (clcg.cpp:467-472, 764-769)
 	static constexpr int NRED = 0, W = 1;
-	const Z* u; const Z* Ax; Z* q; Z* w; Z ak;
+	const ZV* u; const ZV* Ax; ZV* q; ZV* w; Z ak;
 	__device__ void begin(const DevState* st) { ak = sc_ldz(st, SC_ALPHA); }
 	template <int V> __device__ void elem(size_t i, double*) const
 	{
@@ -352,7 +367,7 @@ struct OpCQW : OpBase {	// q = u - a Ap, w = u + q (clcg.cpp:467-472, 764-769)
 
 struct OpCCgsUpdate : OpBase {	// m += a w, r -= a Aw; m.m, r.r, <r0bar,r>; beta (clcg.cpp:476-500) + head
 	static constexpr int NRED = 4, W = 1;
-	Z* m; const Z* w; Z* r; const Z* Ax; const Z* rb; Z ak;
+	ZV* m; const ZV* w; ZV* r; const ZV* Ax; const ZV* rb; Z ak;
 	__device__ void begin(const DevState* st) { ak = sc_ldz(st, SC_ALPHA); }
 	template <int V> __device__ void elem(size_t i, double* acc) const
 	{
@@ -374,7 +389,7 @@ struct OpCCgsUpdate : OpBase {	// m += a w, r -= a Aw; m.m, r.r, <r0bar,r>; beta
 
 struct OpCCgsDir : OpBase {	// u = r + b q, p = u + b (q + b p) (clcg.cpp:502-507, 860-865)
 	static constexpr int NRED = 0, W = 1;
-	const Z* r; const Z* q; Z* u; Z* p; Z bk;
+	const ZV* r; const ZV* q; ZV* u; ZV* p; Z bk;
 	__device__ void begin(const DevState* st) { bk = sc_ldz(st, SC_BETA); }
 	template <int V> __device__ void elem(size_t i, double*) const
 	{
@@ -384,21 +399,21 @@ struct OpCCgsDir : OpBase {	// u = r + b q, p = u + b (q + b p) (clcg.cpp:502-50
 	}
 };
 
-static int run_ccgs(Engine& E, const Operator<Z>& A, Z* m, const Z* B, size_t n, size_t next, size_t skip)
+static int run_ccgs(Engine& E, const Operator<ZV>& A, ZV* m, const ZV* B, size_t n, size_t next, size_t skip)
 {
-	Z* r = E.alloc<Z>(next); Z* rb = E.alloc<Z>(next); Z* p = E.alloc<Z>(next); Z* Ax = E.alloc<Z>(next);
-	Z* u = E.alloc<Z>(next); Z* q = E.alloc<Z>(next); Z* w = E.alloc<Z>(next);
-	E.spmv(A, m, Ax, EpiNone<Z>{});
+	ZV* r = E.alloc<ZV>(next); ZV* rb = E.alloc<ZV>(next); ZV* p = E.alloc<ZV>(next); ZV* Ax = E.alloc<ZV>(next);
+	ZV* u = E.alloc<ZV>(next); ZV* q = E.alloc<ZV>(next); ZV* w = E.alloc<ZV>(next);
+	E.spmv(A, m, Ax, EpiNone<ZV>{});
 	E.vec_push(OpCResInit{{}, m, Ax, B, r, p, u, nullptr}, n, p);
 	if (!init_shadow<true>(E, rb, r, n, skip)) return RC_UNKNOWN;
 	std::function<void(int)> batch;
 	if (E.small_system(A))
-		batch = [&](int k) { E.fused(k, 2, E.ph_spmv(A, p, Ax, EpiInnerAlpha{rb}), E.ph_vec(OpCQW{{}, u, Ax, q, w, zc()}, n), E.ph_spmv(A, w, Ax, EpiNone<Z>{}),
+		batch = [&](int k) { E.fused(k, 2, E.ph_spmv(A, p, Ax, EpiInnerAlpha{rb}), E.ph_vec(OpCQW{{}, u, Ax, q, w, zc()}, n), E.ph_spmv(A, w, Ax, EpiNone<ZV>{}),
 			E.ph_vec(OpCCgsUpdate{{}, m, w, r, Ax, rb, zc()}, n), E.ph_vec(OpCCgsDir{{}, r, q, u, p, zc()}, n)); };
 	return E.run([&]() {
 		E.spmv(A, p, Ax, EpiInnerAlpha{rb});
 		E.vec_push(OpCQW{{}, u, Ax, q, w, zc()}, n, w);
-		E.spmv(A, w, Ax, EpiNone<Z>{});
+		E.spmv(A, w, Ax, EpiNone<ZV>{});
 		E.vec(OpCCgsUpdate{{}, m, w, r, Ax, rb, zc()}, n);
 		E.vec_push(OpCCgsDir{{}, r, q, u, p, zc()}, n, p);
 		return false;
@@ -408,14 +423,14 @@ static int run_ccgs(Engine& E, const Operator<Z>& A, Z* m, const Z* B, size_t n,
 // ======================================================================================== BICGSTAB (clcg.cpp:524-679)
 struct OpCBsS : OpBase {	// s = r - a Ap (clcg.cpp:624-628)
 	static constexpr int NRED = 0, W = 1;
-	const Z* r; const Z* Ap; Z* s; Z ak;
+	const ZV* r; const ZV* Ap; ZV* s; Z ak;
 	__device__ void begin(const DevState* st) { ak = sc_ldz(st, SC_ALPHA); }
 	template <int V> __device__ void elem(size_t i, double*) const { s[i] = zsub(r[i], zmul(ak, Ap[i])); }
 };
 
 struct OpCBsUpdate : OpBase {	// m += a p + w s, r = s - w As; m.m, r.r, <r0bar,r>; beta (clcg.cpp:635-659) + head
 	static constexpr int NRED = 4, W = 1;
-	Z* m; const Z* p; const Z* s; const Z* As; Z* r; const Z* rb; Z ak, wk;
+	ZV* m; const ZV* p; const ZV* s; const ZV* As; ZV* r; const ZV* rb; Z ak, wk;
 	__device__ void begin(const DevState* st) { ak = sc_ldz(st, SC_ALPHA); wk = sc_ldz(st, SC_OMEGA); }
 	template <int V> __device__ void elem(size_t i, double* acc) const
 	{
@@ -440,16 +455,16 @@ struct OpCBsUpdate : OpBase {	// m += a p + w s, r = s - w As; m.m, r.r, <r0bar,
 
 struct OpCBsDir : OpBase {	// p = r + b (p - w Ap) (clcg.cpp:661-665)
 	static constexpr int NRED = 0, W = 1;
-	const Z* r; Z* p; const Z* Ap; Z bk, wk;
+	const ZV* r; ZV* p; const ZV* Ap; Z bk, wk;
 	__device__ void begin(const DevState* st) { bk = sc_ldz(st, SC_BETA); wk = sc_ldz(st, SC_OMEGA); }
 	template <int V> __device__ void elem(size_t i, double*) const { p[i] = zadd(r[i], zmul(bk, zsub(p[i], zmul(wk, Ap[i])))); }
 };
 
-static int run_cbicgstab(Engine& E, const Operator<Z>& A, Z* m, const Z* B, size_t n, size_t next, size_t skip)
+static int run_cbicgstab(Engine& E, const Operator<ZV>& A, ZV* m, const ZV* B, size_t n, size_t next, size_t skip)
 {
-	Z* r = E.alloc<Z>(next); Z* rb = E.alloc<Z>(next); Z* p = E.alloc<Z>(next); Z* s = E.alloc<Z>(next);
-	Z* Ap = E.alloc<Z>(next); Z* As = E.alloc<Z>(next);
-	E.spmv(A, m, Ap, EpiNone<Z>{});
+	ZV* r = E.alloc<ZV>(next); ZV* rb = E.alloc<ZV>(next); ZV* p = E.alloc<ZV>(next); ZV* s = E.alloc<ZV>(next);
+	ZV* Ap = E.alloc<ZV>(next); ZV* As = E.alloc<ZV>(next);
+	E.spmv(A, m, Ap, EpiNone<ZV>{});
 	E.vec_push(OpCResInit{{}, m, Ap, B, r, p, nullptr, nullptr}, n, p);
 	if (!init_shadow<true>(E, rb, r, n, skip)) return RC_UNKNOWN;
 	std::function<void(int)> batch;
@@ -485,7 +500,7 @@ __device__ __forceinline__ void tfqmr_half_scalars(DevState* st, int j)
 
 struct OpCTfR : OpBase {	// r -= a A(u+q); <r,r>, <r0bar,r> (clcg.cpp:773-779, 856) + head of half step 1
 	static constexpr int NRED = 3, W = 1;
-	Z* r; const Z* Ax; const Z* rb; Z ak;
+	ZV* r; const ZV* Ax; const ZV* rb; Z ak;
 	__device__ void begin(const DevState* st) { ak = sc_ldz(st, SC_ALPHA); }
 	template <int V> __device__ void elem(size_t i, double* acc) const
 	{
@@ -506,7 +521,7 @@ struct OpCTfR : OpBase {	// r -= a A(u+q); <r,r>, <r0bar,r> (clcg.cpp:773-779, 8
 template <int J>
 struct OpCTfHalf : OpBase {	// d = (u|q) + sign d, m += eta d; m.m, NaN (clcg.cpp:810-851) [+ head of half step 2]
 	static constexpr int NRED = 1, W = 1;
-	const Z* uq; Z* d; Z* m; Z sign, eta;
+	const ZV* uq; ZV* d; ZV* m; Z sign, eta;
 	__device__ void begin(const DevState* st) { sign = sc_ldz(st, SC_TMP0); eta = sc_ldz(st, SC_ETA); }
 	template <int V> __device__ void elem(size_t i, double* acc) const
 	{
@@ -535,11 +550,11 @@ struct OpCTfHalf : OpBase {	// d = (u|q) + sign d, m += eta d; m.m, NaN (clcg.cp
 	}
 };
 
-static int run_ctfqmr(Engine& E, const Operator<Z>& A, Z* m, const Z* B, size_t n, size_t next, size_t skip)
+static int run_ctfqmr(Engine& E, const Operator<ZV>& A, ZV* m, const ZV* B, size_t n, size_t next, size_t skip)
 {
-	Z* p = E.alloc<Z>(next); Z* u = E.alloc<Z>(next); Z* v = E.alloc<Z>(next); Z* d = E.alloc<Z>(next);
-	Z* rb = E.alloc<Z>(next); Z* r = E.alloc<Z>(next); Z* Ax = E.alloc<Z>(next); Z* q = E.alloc<Z>(next); Z* uq = E.alloc<Z>(next);
-	E.spmv(A, m, Ax, EpiNone<Z>{});
+	ZV* p = E.alloc<ZV>(next); ZV* u = E.alloc<ZV>(next); ZV* v = E.alloc<ZV>(next); ZV* d = E.alloc<ZV>(next);
+	ZV* rb = E.alloc<ZV>(next); ZV* r = E.alloc<ZV>(next); ZV* Ax = E.alloc<ZV>(next); ZV* q = E.alloc<ZV>(next); ZV* uq = E.alloc<ZV>(next);
+	E.spmv(A, m, Ax, EpiNone<ZV>{});
 	E.vec_push(OpCResInit{{}, m, Ax, B, r, p, u, d}, n, p);
 	if (!init_shadow<false>(E, rb, r, n, skip)) return RC_UNKNOWN;
 	// theta = 0, omega = tao = |<r,r>| = r.r, eta = 0 — written straight into the state block
@@ -555,7 +570,7 @@ static int run_ctfqmr(Engine& E, const Operator<Z>& A, Z* m, const Z* B, size_t 
 	return E.run([&]() {
 		E.spmv(A, p, v, EpiInnerAlpha{rb});
 		E.vec_push(OpCQW{{}, u, v, q, uq, zc()}, n, uq);
-		E.spmv(A, uq, Ax, EpiNone<Z>{});
+		E.spmv(A, uq, Ax, EpiNone<ZV>{});
 		E.vec(OpCTfR{{}, r, Ax, rb, zc()}, n);
 		if (E.sync_point()) return true;
 		E.vec(OpCTfHalf<1>{{}, u, d, m, zc(), zc()}, n);
@@ -567,7 +582,7 @@ static int run_ctfqmr(Engine& E, const Operator<Z>& A, Z* m, const Z* B, size_t 
 }
 
 // ======================================================================================== dispatch
-int solve_complex(Engine& E, const Operator<Z>& A, int solver_id, Z* m, const Z* B, const lcgb200_cpara& para, size_t n, size_t next)
+static int dispatch(Engine& E, const Operator<ZV>& A, int solver_id, ZV* m, const ZV* B, const lcgb200_cpara& para, size_t n, size_t next)
 {
 	const size_t skip = A.h ? (size_t)A.h->row_offset : 0;	// partitioned: global index of the first local row (lcgb200_csr_set_row_offset)
 	switch (solver_id)
@@ -579,6 +594,19 @@ int solve_complex(Engine& E, const Operator<Z>& A, int solver_id, Z* m, const Z*
 		case LCGB200_CTFQMR: return run_ctfqmr(E, A, m, B, n, next, skip);
 		case LCGB200_CCGS: default: return run_ccgs(E, A, m, B, n, next, skip);
 	}
+}
+
+}  // namespace LCG_CPLX_NS
+
+#ifdef LCG_CPLX_FLOAT
+int solve_complexf(Engine& E, const Operator<ZF>& A, int solver_id, ZF* m, const ZF* B, const lcgb200_cpara& para, size_t n, size_t next)
+{
+	return cf32::dispatch(E, A, solver_id, m, B, para, n, next);
+}
+#else
+int solve_complex(Engine& E, const Operator<double2>& A, int solver_id, double2* m, const double2* B, const lcgb200_cpara& para, size_t n, size_t next)
+{
+	return cf64::dispatch(E, A, solver_id, m, B, para, n, next);
 }
 
 int complex_vector_count(int solver_id)
@@ -593,5 +621,7 @@ int complex_vector_count(int solver_id)
 		default: return 7;
 	}
 }
+
+#endif
 
 }  // namespace lcgb200

@@ -59,6 +59,20 @@ def main():
                                  low=np.full(n, blo) if constrained else None, hig=np.full(n, bhi) if constrained else None)
                 rel = float(np.linalg.norm(x - cpu.x) / np.linalg.norm(cpu.x))
                 ok = (r.ret == cpu.ret) and abs(r.iterations - cpu.iters) <= max(1, int(np.ceil(0.02 * cpu.iters)))
+                if not ok and r.ret == cpu.ret and sid == api.LCG_SPG and name != "pinned25":
+                    # SPG's non-monotone line search turns summation-order-level noise into different accept/reject decisions: the
+                    # crossing of the reference ITSELF scatters by tens of iterations under sqrt(n)-ulp noise on b (the yardstick of
+                    # tests/test_gpu_parity.py: mean +- (2 % + 4 sigma) over both summation orders); same converged solution required
+                    band = [cpu.iters]
+                    for tree in (False, True):
+                        port.set_summation(tree)
+                        for sd in range(6):
+                            bn = S["b"] * (1 + np.sqrt(n) * 2.2e-16 * np.random.default_rng(1000 + sd).standard_normal(n))
+                            band.append(port.solve(sid, S, bn, para=po.default_para(**kw), diag=d, low=np.full(n, blo), hig=np.full(n, bhi)).iters)
+                    port.set_summation(False)
+                    band = np.array(band, dtype=np.float64)
+                    ok = abs(r.iterations - band.mean()) <= max(1.0, np.ceil(0.02 * band.max())) + 4.0 * band.std(ddof=1) and rel <= 1e-3
+                    print(f"     SPG iteration band of the CPU solver under summation-order noise: {sorted(band.astype(int))}", flush=True)
                 if r.iterations == cpu.iters:
                     bp = S["b"] * (1 + 2.2e-16 * np.random.default_rng(2024).standard_normal(n))
                     sens = 0.0
