@@ -15,6 +15,7 @@
 #include <iostream>
 #include "lcg_cuda.h"
 #include "clcg_cuda.h"
+#include "clcg_cudaf.h"
 
 namespace lcg_b200_detail {
 
@@ -179,6 +180,55 @@ public:
 		run(lcg_b200_detail::ComplexTraits::name(solver_id), verbose, er_throw, [&](bool monitor) {
 			return clcg_solver_preconditioned_cuda(builtin_ ? reinterpret_cast<clcg_axfunc_cuda_ptr>(&lcgb200_csr_cax) : &_AxProduct,
 				builtin_ ? reinterpret_cast<clcg_axfunc_cuda_ptr>(&lcgb200_jacobi_cmx) : &_MxProduct, monitor ? &_Progress : nullptr,
+				x, b, n_size, nz_size, &param_, builtin_ ? (void*)builtin_ : (void*)this, cub, cus, solver_id);
+		});
+	}
+};
+
+// CLCG_CUDAF_Solver (solver_cuda.h:213-374, solver_cuda.cu:182-298): the same wrapper on cuComplex vectors
+class CLCG_CUDAF_Solver : public lcg_b200_detail::SolverBase<lcg_b200_detail::ComplexTraits> {
+public:
+	virtual void AxProduct(cublasHandle_t cub_handle, cusparseHandle_t cus_handle, cusparseDnVecDescr_t x, cusparseDnVecDescr_t prod_Ax,
+		const int n_size, const int nz_size, cusparseOperation_t oper_t) = 0;
+	virtual void MxProduct(cublasHandle_t cub_handle, cusparseHandle_t cus_handle, cusparseDnVecDescr_t x, cusparseDnVecDescr_t prod_Mx,
+		const int n_size, const int nz_size, cusparseOperation_t oper_t) = 0;
+	virtual int Progress(const cuComplex* m, const float converge, const clcg_para* param, const int n_size, const int nz_size, const int k)
+	{
+		(void)m; (void)n_size; (void)nz_size;
+		return default_progress(converge, param->epsilon, k);
+	}
+
+	static void _AxProduct(void* instance, cublasHandle_t cub, cusparseHandle_t cus, cusparseDnVecDescr_t x, cusparseDnVecDescr_t Ax, const int n, const int nz,
+		cusparseOperation_t oper_t)
+	{
+		static_cast<CLCG_CUDAF_Solver*>(instance)->AxProduct(cub, cus, x, Ax, n, nz, oper_t);
+	}
+	static void _MxProduct(void* instance, cublasHandle_t cub, cusparseHandle_t cus, cusparseDnVecDescr_t x, cusparseDnVecDescr_t Mx, const int n, const int nz,
+		cusparseOperation_t oper_t)
+	{
+		static_cast<CLCG_CUDAF_Solver*>(instance)->MxProduct(cub, cus, x, Mx, n, nz, oper_t);
+	}
+	static int _Progress(void* instance, const cuComplex* m, const float converge, const clcg_para* param, const int n, const int nz, const int k)
+	{
+		return static_cast<CLCG_CUDAF_Solver*>(instance)->Progress(m, converge, param, n, nz, k);
+	}
+
+	void set_clcg_parameter(const clcg_para& in_param) { param_ = in_param; }
+
+	void Minimize(cublasHandle_t cub, cusparseHandle_t cus, cuComplex* x, cuComplex* b, const int n_size, const int nz_size,
+		clcg_solver_enum solver_id = CLCG_BICG, bool verbose = true, bool er_throw = false)
+	{
+		run(lcg_b200_detail::ComplexTraits::name(solver_id), verbose, er_throw, [&](bool monitor) {
+			return clcg_solver_cuda(builtin_ ? reinterpret_cast<clcg_axfunc_cudaf_ptr>(&lcgb200_csr_cax) : &_AxProduct, monitor ? &_Progress : nullptr,
+				x, b, n_size, nz_size, &param_, builtin_ ? (void*)builtin_ : (void*)this, cub, cus, solver_id);
+		});
+	}
+	void MinimizePreconditioned(cublasHandle_t cub, cusparseHandle_t cus, cuComplex* x, cuComplex* b, const int n_size, const int nz_size,
+		clcg_solver_enum solver_id = CLCG_PCG, bool verbose = true, bool er_throw = false)
+	{
+		run(lcg_b200_detail::ComplexTraits::name(solver_id), verbose, er_throw, [&](bool monitor) {
+			return clcg_solver_preconditioned_cuda(builtin_ ? reinterpret_cast<clcg_axfunc_cudaf_ptr>(&lcgb200_csr_cax) : &_AxProduct,
+				builtin_ ? reinterpret_cast<clcg_axfunc_cudaf_ptr>(&lcgb200_jacobi_cmx) : &_MxProduct, monitor ? &_Progress : nullptr,
 				x, b, n_size, nz_size, &param_, builtin_ ? (void*)builtin_ : (void*)this, cub, cus, solver_id);
 		});
 	}

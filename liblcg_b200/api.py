@@ -29,7 +29,7 @@ LCG_INVILAD_RESTART_EPSILON, LCG_REACHED_MAX_ITERATIONS, LCG_NULL_PRECONDITION_M
 LCG_INVALID_POINTER, LCG_INVALID_LAMBDA, LCG_INVALID_SIGMA, LCG_INVALID_BETA, LCG_INVALID_MAXIM, LCG_SIZE_NOT_MATCH = -1016, -1015, -1014, -1013, -1012, -1011
 CLCG_REACHED_MAX_ITERATIONS, CLCG_NAN_VALUE, CLCG_INVALID_POINTER, CLCG_SIZE_NOT_MATCH, CLCG_UNKNOWN_SOLVER = -1020, -1019, -1018, -1017, -1016
 
-REAL, COMPLEX = 0, 1
+REAL, COMPLEX, COMPLEX_FLOAT = 0, 1, 2
 HOST, DEVICE = 0, 1
 CSR_TRANSPOSE, CSR_JACOBI, CSR_COMPRESS = 1, 2, 4
 VEC_DEVICE, USE_JACOBI = 1, 2
@@ -113,24 +113,26 @@ class CsrOperator:
             cx = val.is_complex() or (val.dim() == 2 and val.shape[-1] == 2)
             n = row_ptr.numel() - 1
             nnz = col.numel()
+            single = str(val.dtype) == "torch.complex64"
             # the C ABI takes raw pointers: anything but contiguous CUDA int32 / float64 / complex128 would be reinterpreted silently
             for name, t, ok in (("row_ptr", row_ptr, ("torch.int32",)), ("col", col, ("torch.int32",)),
-                                ("val", val, ("torch.complex128",) if val.is_complex() else ("torch.float64",))):
+                                ("val", val, ("torch.complex128", "torch.complex64") if val.is_complex() else ("torch.float64",))):
                 if not (t.is_cuda and t.is_contiguous() and str(t.dtype) in ok):
                     raise TypeError(f"CsrOperator: {name} must be a contiguous CUDA tensor of dtype {ok[0]} (got {t.dtype}, cuda={t.is_cuda}, contiguous={t.is_contiguous()})")
         else:
             row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int32)
             col = np.ascontiguousarray(col, dtype=np.int32)
             cx = np.iscomplexobj(val)
-            val = np.ascontiguousarray(val, dtype=np.complex128 if cx else np.float64)
+            single = cx and np.asarray(val).dtype == np.complex64   # cuComplex storage: the clcg_cudaf.h entry points
+            val = np.ascontiguousarray(val, dtype=(np.complex64 if single else np.complex128) if cx else np.float64)
             n = len(row_ptr) - 1
             nnz = len(col)
-        self.n, self.nnz, self.complex = n, nnz, bool(cx)
+        self.n, self.nnz, self.complex, self.single = n, nnz, bool(cx), bool(cx and single)
         self.n_cols = n if n_cols is None else n_cols
         flags = (CSR_TRANSPOSE if transpose else 0) | (CSR_JACOBI if jacobi else 0) | (CSR_COMPRESS if compress else 0)
         h = C.c_void_p()
         rc = lib.lcgb200_csr_create_rect(C.byref(h), n, self.n_cols, nnz, _ptr(row_ptr), _ptr(col), _ptr(val),
-                                         COMPLEX if cx else REAL, DEVICE if on_dev else HOST, flags)
+                                         (COMPLEX_FLOAT if self.single else COMPLEX) if cx else REAL, DEVICE if on_dev else HOST, flags)
         if rc != 0:
             raise RuntimeError(f"lcgb200_csr_create failed ({rc}): {last_error()}")
         self.handle = h
@@ -162,7 +164,7 @@ class CsrOperator:
         return int(_lib.load().lcgb200_csr_spmv_bytes(self.handle))
 
     def diagonal(self) -> np.ndarray:
-        out = np.empty(self.n, dtype=np.complex128 if self.complex else np.float64)
+        out = np.empty(self.n, dtype=(np.complex64 if getattr(self, "single", False) else np.complex128) if self.complex else np.float64)
         rc = _lib.load().lcgb200_csr_get_diagonal(self.handle, out.ctypes.data)
         if rc != 0:
             raise RuntimeError(f"get_diagonal failed ({rc})")
@@ -214,7 +216,7 @@ def operator_from_coo(n, rows, cols, vals, transpose=False, jacobi=False) -> "Cs
     if rc != 0:
         raise RuntimeError(f"lcgb200_csr_create_from_coo failed ({rc}): {last_error()}")
     op = CsrOperator.__new__(CsrOperator)
-    op.n, op.nnz, op.complex, op.n_cols, op.handle, op._keep = n, len(rows), bool(cx), n, h, None
+    op.n, op.nnz, op.complex, op.n_cols, op.handle, op._keep, op.single = n, len(rows), bool(cx), n, h, None, False
     return op
 
 
@@ -295,6 +297,34 @@ def clcg_solver_preconditioned_cuda(Afp, Mfp, Pfp, m, B, n_size, nz_size, param,
     return _lib.load().lcgb200_csolver_preconditioned_cuda(_afp_addr(Afp), _afp_addr(Mfp), cbp, _ptr(m), _ptr(B), n_size, nz_size,
                                                            C.byref(param) if param is not None else None, _instance(instance),
                                                            cub_handle, cus_handle, solver_id)
+
+
+def _wrap_progress_f(Pfp):
+    if Pfp is None:
+        return None, None
+
+    def tramp(instance, m_dev, converge, param, n, nz, k):
+        return int(Pfp(instance, m_dev, converge, param.contents, n, nz, k) or 0)
+
+    cb = _lib.CPROGRESSF(tramp)
+    return cb, C.cast(cb, C.c_void_p)
+
+
+def clcg_solver_cudaf(Afp, Pfp, m, B, n_size, nz_size, param, instance, cub_handle=None, cus_handle=None, solver_id=CLCG_BICG) -> int:
+    """The cuComplex overload of clcg_solver_cuda (reference clcg_cudaf.h:81-83).  m, B: host complex64 arrays."""
+    cb, cbp = _wrap_progress_f(Pfp)
+    return _lib.load().lcgb200_csolver_cudaf(_afp_addr(Afp), cbp, _ptr(m), _ptr(B), n_size, nz_size,
+                                             C.byref(param) if param is not None else None, _instance(instance),
+                                             cub_handle, cus_handle, solver_id)
+
+
+def clcg_solver_preconditioned_cudaf(Afp, Mfp, Pfp, m, B, n_size, nz_size, param, instance, cub_handle=None, cus_handle=None,
+                                     solver_id=CLCG_PCG) -> int:
+    """The cuComplex overload of clcg_solver_preconditioned_cuda (reference clcg_cudaf.h:103-105)."""
+    cb, cbp = _wrap_progress_f(Pfp)
+    return _lib.load().lcgb200_csolver_preconditioned_cudaf(_afp_addr(Afp), _afp_addr(Mfp), cbp, _ptr(m), _ptr(B), n_size, nz_size,
+                                                            C.byref(param) if param is not None else None, _instance(instance),
+                                                            cub_handle, cus_handle, solver_id)
 
 
 # ------------------------------------------------------------------ the reference's HOST-callback API (lcg.h, clcg.h)

@@ -811,6 +811,7 @@ void exchange_for_spmv(CsrHandle* h, const void* x, cudaStream_t s)
 void ensure_state(CsrHandle* h, cudaStream_t s)
 {
 	Engine E(s, h);   // allocates the cached state block on first use
+	E.n_local = (size_t)h->n_rows;
 	DevState init; std::memset(&init, 0, sizeof(init));
 	E.start(init);
 }

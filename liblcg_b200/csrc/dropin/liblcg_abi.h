@@ -116,6 +116,17 @@ int clcg_solver_preconditioned_cuda(clcg_axfunc_cuda_ptr Afp, clcg_axfunc_cuda_p
 	const cuDoubleComplex* B, const int n_size, const int nz_size, const clcg_para* param, void* instance, cublasHandle_t cub_handle,
 	cusparseHandle_t cus_handle, clcg_solver_enum solver_id);
 
+// ---- clcg_cudaf.h: the cuComplex overloads
+typedef void (*clcg_axfunc_cudaf_ptr)(void* instance, cublasHandle_t cub_handle, cusparseHandle_t cus_handle, cusparseDnVecDescr_t x,
+	cusparseDnVecDescr_t prod_Ax, const int n_size, const int nz_size, cusparseOperation_t oper_t);
+typedef int (*clcg_progress_cudaf_ptr)(void* instance, const cuComplex* m, const float converge, const clcg_para* param, const int n_size,
+	const int nz_size, const int k);
+int clcg_solver_cuda(clcg_axfunc_cudaf_ptr Afp, clcg_progress_cudaf_ptr Pfp, cuComplex* m, const cuComplex* B, const int n_size, const int nz_size,
+	const clcg_para* param, void* instance, cublasHandle_t cub_handle, cusparseHandle_t cus_handle, clcg_solver_enum solver_id);
+int clcg_solver_preconditioned_cuda(clcg_axfunc_cudaf_ptr Afp, clcg_axfunc_cudaf_ptr Mfp, clcg_progress_cudaf_ptr Pfp, cuComplex* m, const cuComplex* B,
+	const int n_size, const int nz_size, const clcg_para* param, void* instance, cublasHandle_t cub_handle, cusparseHandle_t cus_handle,
+	clcg_solver_enum solver_id);
+
 // ---- solver.h / solver_cuda.h: the class wrappers.  Data members and virtual functions in the reference's order (the
 // object layout and the vtable are part of the ABI); the static trampolines are inline in the reference's header and are
 // therefore compiled into the caller, not into the library.
@@ -187,5 +198,24 @@ public:
 	void Minimize(cublasHandle_t cub_handle, cusparseHandle_t cus_handle, cuDoubleComplex* x, cuDoubleComplex* b, const int n_size,
 		const int nz_size, clcg_solver_enum solver_id, bool verbose, bool er_throw);
 	void MinimizePreconditioned(cublasHandle_t cub_handle, cusparseHandle_t cus_handle, cuDoubleComplex* x, cuDoubleComplex* b, const int n_size,
+		const int nz_size, clcg_solver_enum solver_id, bool verbose, bool er_throw);
+};
+class CLCG_CUDAF_Solver {
+protected:
+	clcg_para param_; unsigned int inter_; bool silent_;
+public:
+	CLCG_CUDAF_Solver();
+	virtual ~CLCG_CUDAF_Solver() {}
+	virtual void AxProduct(cublasHandle_t cub_handle, cusparseHandle_t cus_handle, cusparseDnVecDescr_t x, cusparseDnVecDescr_t prod_Ax,
+		const int n_size, const int nz_size, cusparseOperation_t oper_t) = 0;
+	virtual void MxProduct(cublasHandle_t cub_handle, cusparseHandle_t cus_handle, cusparseDnVecDescr_t x, cusparseDnVecDescr_t prod_Mx,
+		const int n_size, const int nz_size, cusparseOperation_t oper_t) = 0;
+	virtual int Progress(const cuComplex* m, const float converge, const clcg_para* param, const int n_size, const int nz_size, const int k);
+	void silent();
+	void set_report_interval(unsigned int inter);
+	void set_clcg_parameter(const clcg_para& in_param);
+	void Minimize(cublasHandle_t cub_handle, cusparseHandle_t cus_handle, cuComplex* x, cuComplex* b, const int n_size, const int nz_size,
+		clcg_solver_enum solver_id, bool verbose, bool er_throw);
+	void MinimizePreconditioned(cublasHandle_t cub_handle, cusparseHandle_t cus_handle, cuComplex* x, cuComplex* b, const int n_size,
 		const int nz_size, clcg_solver_enum solver_id, bool verbose, bool er_throw);
 };

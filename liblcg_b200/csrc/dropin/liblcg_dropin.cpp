@@ -286,6 +286,22 @@ int clcg_solver_preconditioned_cuda(clcg_axfunc_cuda_ptr Afp, clcg_axfunc_cuda_p
 		reinterpret_cast<lcgb200_cusparse_t>(cus_handle), static_cast<int>(solver_id));
 }
 
+// the cuComplex overloads (clcg_cudaf.h:81-83, 103-105)
+int clcg_solver_cuda(clcg_axfunc_cudaf_ptr Afp, clcg_progress_cudaf_ptr Pfp, cuComplex* m, const cuComplex* B, const int n_size, const int nz_size,
+	const clcg_para* param, void* instance, cublasHandle_t cub_handle, cusparseHandle_t cus_handle, clcg_solver_enum solver_id)
+{
+	return lcgb200_csolver_cudaf(reinterpret_cast<lcgb200_caxfunc_cuda_ptr>(Afp), reinterpret_cast<lcgb200_cprogress_cudaf_ptr>(Pfp), m, B, n_size, nz_size,
+		P(param), instance, reinterpret_cast<lcgb200_cublas_t>(cub_handle), reinterpret_cast<lcgb200_cusparse_t>(cus_handle), static_cast<int>(solver_id));
+}
+int clcg_solver_preconditioned_cuda(clcg_axfunc_cudaf_ptr Afp, clcg_axfunc_cudaf_ptr Mfp, clcg_progress_cudaf_ptr Pfp, cuComplex* m, const cuComplex* B,
+	const int n_size, const int nz_size, const clcg_para* param, void* instance, cublasHandle_t cub_handle, cusparseHandle_t cus_handle,
+	clcg_solver_enum solver_id)
+{
+	return lcgb200_csolver_preconditioned_cudaf(reinterpret_cast<lcgb200_caxfunc_cuda_ptr>(Afp), reinterpret_cast<lcgb200_caxfunc_cuda_ptr>(Mfp),
+		reinterpret_cast<lcgb200_cprogress_cudaf_ptr>(Pfp), m, B, n_size, nz_size, P(param), instance, reinterpret_cast<lcgb200_cublas_t>(cub_handle),
+		reinterpret_cast<lcgb200_cusparse_t>(cus_handle), static_cast<int>(solver_id));
+}
+
 // ------------------------------------------------------------------------------------------- class wrappers
 // solver.cpp:29-283 / solver_cuda.cu:29-414.  Minimize* print the solver's name, run, print the elapsed time and report the
 // return code through lcg_error_str / clcg_error_str (which throws for a negative code when er_throw is set).
@@ -424,5 +440,36 @@ void CLCG_CUDA_Solver::MinimizePreconditioned(cublasHandle_t cub_handle, cuspars
 {
 	minimize(silent_, verbose, er_throw, true, cplx_name(CLCG_PCG), [&](bool mon) {
 		return clcg_solver_preconditioned_cuda(ClcgCudaTramp::ax, ClcgCudaTramp::mx, mon ? ClcgCudaTramp::pg : nullptr, x, b, n_size, nz_size, &param_, this,
+			cub_handle, cus_handle, solver_id); });
+}
+
+// solver_cuda.h:213-374 / solver_cuda.cu:182-298
+namespace {
+struct ClcgCudafTramp {
+	static void ax(void* inst, cublasHandle_t cb, cusparseHandle_t cs, cusparseDnVecDescr_t x, cusparseDnVecDescr_t y, const int n, const int nz, cusparseOperation_t op)
+	{ static_cast<CLCG_CUDAF_Solver*>(inst)->AxProduct(cb, cs, x, y, n, nz, op); }
+	static void mx(void* inst, cublasHandle_t cb, cusparseHandle_t cs, cusparseDnVecDescr_t x, cusparseDnVecDescr_t y, const int n, const int nz, cusparseOperation_t op)
+	{ static_cast<CLCG_CUDAF_Solver*>(inst)->MxProduct(cb, cs, x, y, n, nz, op); }
+	static int pg(void* inst, const cuComplex* m, const float c, const clcg_para* p, const int n, const int nz, const int k)
+	{ return static_cast<CLCG_CUDAF_Solver*>(inst)->Progress(m, c, p, n, nz, k); }
+};
+}  // namespace
+CLCG_CUDAF_Solver::CLCG_CUDAF_Solver() : param_(kDefC), inter_(1), silent_(false) {}
+int CLCG_CUDAF_Solver::Progress(const cuComplex*, const float converge, const clcg_para* param, const int, const int, const int k)
+{ return monitor(inter_, converge, param->epsilon, k); }
+void CLCG_CUDAF_Solver::silent() { silent_ = true; }
+void CLCG_CUDAF_Solver::set_report_interval(unsigned int inter) { inter_ = inter; }
+void CLCG_CUDAF_Solver::set_clcg_parameter(const clcg_para& in_param) { param_ = in_param; }
+void CLCG_CUDAF_Solver::Minimize(cublasHandle_t cub_handle, cusparseHandle_t cus_handle, cuComplex* x, cuComplex* b, const int n_size,
+	const int nz_size, clcg_solver_enum solver_id, bool verbose, bool er_throw)
+{
+	minimize(silent_, verbose, er_throw, true, cplx_name(solver_id), [&](bool mon) {
+		return clcg_solver_cuda(ClcgCudafTramp::ax, mon ? ClcgCudafTramp::pg : nullptr, x, b, n_size, nz_size, &param_, this, cub_handle, cus_handle, solver_id); });
+}
+void CLCG_CUDAF_Solver::MinimizePreconditioned(cublasHandle_t cub_handle, cusparseHandle_t cus_handle, cuComplex* x, cuComplex* b,
+	const int n_size, const int nz_size, clcg_solver_enum solver_id, bool verbose, bool er_throw)
+{
+	minimize(silent_, verbose, er_throw, true, cplx_name(CLCG_PCG), [&](bool mon) {
+		return clcg_solver_preconditioned_cuda(ClcgCudafTramp::ax, ClcgCudafTramp::mx, mon ? ClcgCudafTramp::pg : nullptr, x, b, n_size, nz_size, &param_, this,
 			cub_handle, cus_handle, solver_id); });
 }

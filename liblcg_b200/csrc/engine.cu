@@ -19,12 +19,16 @@ const char* last_error() { return g_err.c_str(); }
 
 Settings& settings() { static Settings s; return s; }
 
-bool pdl_enabled()
+// PDL pays where launch gaps are a visible share of an iteration (the same regime as the CUDA graphs: up to ~8 M local
+// rows); on the largest systems (7-point 512^3 on one GPU) letting the next grid become resident early costs more than the
+// gap it hides (measured: BiCGSTAB 151 -> 131 it/s), so the automatic setting is decided per solve from the local size.
+static thread_local bool t_pdl_active = false;
+bool pdl_enabled() { return t_pdl_active; }
+static void pdl_decide(size_t n_local)
 {
-	const int mode = settings().pdl;
-	if (mode >= 0) return mode != 0;
-	static const int env = [] { const char* e = getenv("LCGB200_PDL"); return e ? atoi(e) : 1; }();
-	return env != 0;
+	int mode = settings().pdl;
+	if (mode < 0) { static const int env = [] { const char* e = getenv("LCGB200_PDL"); return e ? atoi(e) : -1; }(); mode = env; }
+	t_pdl_active = mode > 0 || (mode < 0 && n_local <= ((size_t)8 << 20));
 }
 
 long long spin_timeout_ms()
@@ -165,6 +169,7 @@ void Engine::start(const DevState& init)
 	// seconds late (slow callback, debugger), so the peers wait 20x longer before they give up
 	h_st->spin_timeout_ns = (unsigned long long)spin_timeout_ms() * 1000000ull * ((pf || sync_each) ? 20ull : 1ull);
 	pushed_vec = nullptr;
+	pdl_decide(n_local);
 	LCG_CUDA_CHECK(cudaMemcpyAsync(d_st, h_st, sizeof(DevState), cudaMemcpyHostToDevice, stream));
 	LCG_CUDA_CHECK(cudaEventRecord(ev[2], stream));
 	seen_checks = 0;

@@ -212,6 +212,19 @@ class RefCuda:
                                          _p(hist, C.c_double), C.c_int(hist_cap), C.byref(secs), C.byref(its), C.byref(calls))
         return ret, secs.value, its.value, hist[:min(calls.value, hist_cap)].copy()
 
+    def csolvef(self, solver: str, n: int, nnz: int, d_rp: int, d_ci: int, d_val: int, m: np.ndarray, b: np.ndarray,
+                epsilon: float, max_iterations: int, abs_diff: int = 0, hist_cap: int = 0):
+        """The cuComplex overloads (clcg_cudaf.cu:86-558), unmodified.  d_val: device pointer to nnz cuComplex; m (in/out), b: host
+        complex64.  Returns (ret, seconds, last k, residual history)."""
+        assert m.dtype == np.complex64 and b.dtype == np.complex64
+        self.lib.lcgrefcuda_csolvef.restype = C.c_int
+        secs, its, calls = C.c_double(), C.c_int(), C.c_int()
+        hist = np.zeros(max(hist_cap, 1), dtype=np.float64)
+        ret = self.lib.lcgrefcuda_csolvef(C.c_int(self.CSOLVERS[solver]), C.c_int(n), C.c_int(nnz), C.c_void_p(d_rp), C.c_void_p(d_ci), C.c_void_p(d_val),
+                                          m.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), C.c_double(epsilon), C.c_int(max_iterations),
+                                          C.c_int(abs_diff), _p(hist, C.c_double), C.c_int(hist_cap), C.byref(secs), C.byref(its), C.byref(calls))
+        return ret, secs.value, its.value, hist[:min(calls.value, hist_cap)].copy()
+
 
 _KINDS = {"7pt": 0, "27pt": 1, "7pt_cd": 2}
 

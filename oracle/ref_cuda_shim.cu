@@ -189,3 +189,96 @@ extern "C" int lcgrefcuda_csolve(int solver, int n, int nnz, const int* d_rp, co
 	cublasDestroy(cub); cusparseDestroy(cus);
 	return ret;
 }
+
+// ------------------------------------------------------------------------------------------ complex, single precision
+// The cuComplex overloads (clcg_cudaf.cu: BICG :86-252, BICG_SYM :254-401, PCG :403-558), unmodified, same driver shape.
+#include "clcg_cudaf.h"
+
+namespace {
+
+struct FSys
+{
+	cusparseSpMatDescr_t A = nullptr;
+	void* buf = nullptr; size_t buf_bytes = 0;
+	cuComplex* d_diag = nullptr;
+	int last_k = -1, calls = 0;
+	double* hist = nullptr; int hist_cap = 0;
+};
+
+void fref_ax(void* instance, cublasHandle_t, cusparseHandle_t cus, cusparseDnVecDescr_t x, cusparseDnVecDescr_t Ax, const int, const int,
+	cusparseOperation_t oper_t)
+{
+	FSys* s = static_cast<FSys*>(instance);
+	const cuComplex one = make_cuComplex(1.f, 0.f), zero = make_cuComplex(0.f, 0.f);
+	cusparseSpMV(cus, oper_t, &one, s->A, x, &zero, Ax, CUDA_C_32F, CUSPARSE_SPMV_ALG_DEFAULT, s->buf);
+}
+
+void fref_mx(void* instance, cublasHandle_t, cusparseHandle_t, cusparseDnVecDescr_t x, cusparseDnVecDescr_t Mx, const int n, const int,
+	cusparseOperation_t)
+{
+	FSys* s = static_cast<FSys*>(instance);
+	cuComplex *px = nullptr, *pz = nullptr;
+	cusparseDnVecGetValues(x, (void**)&px);
+	cusparseDnVecGetValues(Mx, (void**)&pz);
+	clcg_vecDvecC_element_wise(px, s->d_diag, pz, n);   // the reference's own kernel (lcg_complex_cuda.cu)
+}
+
+int fref_progress(void* instance, const cuComplex*, const float converge, const clcg_para*, const int, const int, const int k)
+{
+	FSys* s = static_cast<FSys*>(instance);
+	s->last_k = k;
+	if (s->hist && s->calls < s->hist_cap) s->hist[s->calls] = (double)converge;
+	s->calls++;
+	return 0;
+}
+
+}  // namespace
+
+// solver: 0 = CLCG_BICG, 1 = CLCG_BICG_SYM, 5 = CLCG_PCG (Jacobi).  d_val: DEVICE pointer to nnz cuComplex; m (in/out), b: HOST cuComplex.
+extern "C" int lcgrefcuda_csolvef(int solver, int n, int nnz, const int* d_rp, const int* d_ci, const void* d_val, void* m, const void* b,
+	double epsilon, int max_iterations, int abs_diff, double* hist, int hist_cap, double* seconds, int* iterations, int* calls)
+{
+	cublasHandle_t cub; cusparseHandle_t cus;
+	if (cublasCreate(&cub) != CUBLAS_STATUS_SUCCESS || cusparseCreate(&cus) != CUSPARSE_STATUS_SUCCESS) return -9999;
+	FSys sys;
+	sys.hist = hist; sys.hist_cap = hist_cap;
+	cusparseCreateCsr(&sys.A, n, n, nnz, const_cast<int*>(d_rp), const_cast<int*>(d_ci), const_cast<void*>(d_val),
+		CUSPARSE_INDEX_32I, CUSPARSE_INDEX_32I, CUSPARSE_INDEX_BASE_ZERO, CUDA_C_32F);
+	{
+		cuComplex *tx = nullptr, *ty = nullptr;
+		cudaMalloc((void**)&tx, sizeof(cuComplex) * n); cudaMalloc((void**)&ty, sizeof(cuComplex) * n);
+		cusparseDnVecDescr_t vx, vy;
+		cusparseCreateDnVec(&vx, n, tx, CUDA_C_32F); cusparseCreateDnVec(&vy, n, ty, CUDA_C_32F);
+		const cuComplex one = make_cuComplex(1.f, 0.f), zero = make_cuComplex(0.f, 0.f);
+		const cusparseOperation_t ops[3] = {CUSPARSE_OPERATION_NON_TRANSPOSE, CUSPARSE_OPERATION_TRANSPOSE, CUSPARSE_OPERATION_CONJUGATE_TRANSPOSE};
+		for (int i = 0; i < 3; i++)
+		{
+			size_t need = 0;
+			cusparseSpMV_bufferSize(cus, ops[i], &one, sys.A, vx, &zero, vy, CUDA_C_32F, CUSPARSE_SPMV_ALG_DEFAULT, &need);
+			if (need > sys.buf_bytes) sys.buf_bytes = need;
+		}
+		cudaMalloc(&sys.buf, sys.buf_bytes > 0 ? sys.buf_bytes : 16);
+		cusparseDestroyDnVec(vx); cusparseDestroyDnVec(vy); cudaFree(tx); cudaFree(ty);
+	}
+	if (solver == 5)
+	{
+		cudaMalloc((void**)&sys.d_diag, sizeof(cuComplex) * n);
+		clcg_smCcsr_get_diagonal(d_rp, d_ci, static_cast<const cuComplex*>(d_val), n, sys.d_diag);
+	}
+	clcg_para para = clcg_default_parameters();
+	para.epsilon = epsilon; para.max_iterations = max_iterations; para.abs_diff = abs_diff;
+	cudaDeviceSynchronize();
+	const auto t0 = std::chrono::steady_clock::now();
+	int ret;
+	if (solver == 5) ret = clcg_solver_preconditioned_cuda(fref_ax, fref_mx, fref_progress, static_cast<cuComplex*>(m),
+		static_cast<const cuComplex*>(b), n, nnz, &para, &sys, cub, cus, CLCG_PCG);
+	else ret = clcg_solver_cuda(fref_ax, fref_progress, static_cast<cuComplex*>(m), static_cast<const cuComplex*>(b), n, nnz, &para, &sys,
+		cub, cus, solver == 1 ? CLCG_BICG_SYM : CLCG_BICG);
+	cudaDeviceSynchronize();
+	if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+	if (iterations) *iterations = sys.last_k;
+	if (calls) *calls = sys.calls;
+	cusparseDestroySpMat(sys.A); cudaFree(sys.buf); cudaFree(sys.d_diag);
+	cublasDestroy(cub); cusparseDestroy(cus);
+	return ret;
+}

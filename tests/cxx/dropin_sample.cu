@@ -190,6 +190,52 @@ static int complex_wrappers(const char* path_a, const char* path_b, cublasHandle
 		if (!(e < 1e-4)) fails++;
 		if (path == 1 && hs.calls != 0) fails++;
 	}
+	// CLCG_CUDAF_Solver (solver_cuda.h:213-374): the same system in single-precision complex, caller's cusparseSpMV (CUDA_C_32F)
+	// callback on the generic path, then the built-in operator; float storage reaches the answer to float accuracy
+	{
+		std::vector<cuComplex> vf((size_t)nz), bf((size_t)n), mf((size_t)n);
+		for (int k = 0; k < nz; k++) vf[(size_t)k] = make_cuComplex((float)va[(size_t)k].real(), (float)va[(size_t)k].imag());
+		for (int i = 0; i < n; i++) bf[(size_t)i] = make_cuComplex((float)b[(size_t)i].real(), (float)b[(size_t)i].imag());
+		cuComplex* d_vf; cudaMalloc((void**)&d_vf, sizeof(cuComplex) * nz);
+		cudaMemcpy(d_vf, vf.data(), sizeof(cuComplex) * nz, cudaMemcpyHostToDevice);
+		struct FSys { cusparseSpMatDescr_t A = nullptr; void* buf = nullptr; size_t cap = 0; int calls = 0; } fs;
+		cusparseCreateCsr(&fs.A, n, n, nz, d_rp, d_ci, d_vf, CUSPARSE_INDEX_32I, CUSPARSE_INDEX_32I, CUSPARSE_INDEX_BASE_ZERO, CUDA_C_32F);
+		struct FSolver : CLCG_CUDAF_Solver {
+			FSys* s = nullptr;
+			void AxProduct(cublasHandle_t, cusparseHandle_t cus, cusparseDnVecDescr_t x, cusparseDnVecDescr_t y, const int, const int, cusparseOperation_t op) override
+			{
+				const cuComplex one = make_cuComplex(1.f, 0.f), zero = make_cuComplex(0.f, 0.f);
+				size_t need = 0;
+				cusparseSpMV_bufferSize(cus, op, &one, s->A, x, &zero, y, CUDA_C_32F, CUSPARSE_SPMV_ALG_DEFAULT, &need);
+				if (need > s->cap) { cudaFree(s->buf); cudaMalloc(&s->buf, need); s->cap = need; }
+				cusparseSpMV(cus, op, &one, s->A, x, &zero, y, CUDA_C_32F, CUSPARSE_SPMV_ALG_DEFAULT, s->buf);
+				s->calls++;
+			}
+			void MxProduct(cublasHandle_t, cusparseHandle_t, cusparseDnVecDescr_t, cusparseDnVecDescr_t, const int, const int, cusparseOperation_t) override {}
+		} fslv;
+		fslv.s = &fs;
+		clcg_para fp = clcg_default_parameters();
+		fp.max_iterations = 300;   // float storage stalls near 1e-7 relative: bound the run, judge by the error
+		fslv.set_clcg_parameter(fp); fslv.silent();
+		lcgb200_csr_t fb = nullptr;
+		if (lcgb200_csr_create(&fb, n, nz, rp.data(), ci.data(), vf.data(), LCGB200_COMPLEX_FLOAT, LCGB200_HOST, LCGB200_CSR_TRANSPOSE | LCGB200_CSR_JACOBI) != 0) return fails + 1;
+		for (int path = 0; path < 2; path++)
+		{
+			fslv.use_builtin_operator(path == 1 ? fb : nullptr);
+			for (auto& z : mf) z = make_cuComplex(0.f, 0.f);
+			fs.calls = 0;
+			try { fslv.Minimize(cub, cus, mf.data(), bf.data(), n, nz, CLCG_BICG_SYM); } catch (const std::runtime_error&) {}   // -1019 (max iterations) raises in silent mode
+			double s2 = 0.0;
+			for (int i = 0; i < n; i++) s2 += std::norm(lcg_complex(mf[(size_t)i].x, mf[(size_t)i].y) - ans[(size_t)i]);
+			const double e = std::sqrt(s2) / (double)n;
+			std::printf("class CLCG_CUDAF_Solver BICG_SYM %-24s A-calls %d avg-error %.3e\n", path == 0 ? "virtual AxProduct" : "built-in fused operator", fs.calls, e);
+			if (!(e < 1e-3)) fails++;
+			if (path == 0 && fs.calls < 50) fails++;
+			if (path == 1 && fs.calls != 0) fails++;
+		}
+		lcgb200_csr_destroy(fb);
+		cusparseDestroySpMat(fs.A); cudaFree(fs.buf); cudaFree(d_vf);
+	}
 	lcgb200_csr_destroy(builtin);
 	cusparseDestroySpMat(sys.A); cudaFree(sys.buf); cudaFree(d_rp); cudaFree(d_ci); cudaFree(d_v);
 	return fails;

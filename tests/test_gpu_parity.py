@@ -542,6 +542,49 @@ def test_complex_pinned_to_reference_cuda(torch_cuda, port, fixtures, name, k):
         np.testing.assert_allclose(hist, h_ref, rtol=1e-6)
 
 
+@pytest.mark.parametrize("k", [1, 10, 30])
+@pytest.mark.parametrize("name", ["BICG", "BICG_SYM", "PCG"])
+def test_float_complex_entry_points_match_reference_cuda(torch_cuda, fixtures, name, k):
+    """The cuComplex overloads (clcg_cudaf.h:81-105): BICG, BICG_SYM and Jacobi-PCG in single-precision complex storage on
+    data/case_10K_cA, after exactly k iterations, against the reference's own clcg_cudaf.cu (cuBLAS Cdotc/Caxpy/Scnrm2 +
+    cusparseSpMV in float, built unmodified into oracle/_ref/liblcg_ref_cuda.so) and against our double-precision solve.
+    Tolerance (written here): float arithmetic — our error against the double iterate must not exceed twice the reference's own
+    (plus 1e-5), and the two float iterates agree to three times the reference's error; the residual history agrees to 1e-3."""
+    torch = torch_cuda
+    if not po.have_reference_cuda():
+        pytest.skip("oracle/_ref/liblcg_ref_cuda.so not present")
+    Ac = fixtures["10Kc"]
+    n, nnz = Ac["n"], Ac["nnz"]
+    val32, b32 = np.ascontiguousarray(Ac["val"], dtype=np.complex64), np.ascontiguousarray(Ac["b"], dtype=np.complex64)
+    rc = po.RefCuda()
+    d_rp, d_ci, d_val = to_dev(torch, Ac["row_ptr"]), to_dev(torch, Ac["col"]), to_dev(torch, val32)
+    m_ref = np.zeros(n, dtype=np.complex64)
+    ret_ref, _, k_ref, h_ref = rc.csolvef(name, n, nnz, d_rp.data_ptr(), d_ci.data_ptr(), d_val.data_ptr(), m_ref, b32, 1e-30, k, hist_cap=k + 2)
+    assert ret_ref == api.LCG_REACHED_MAX_ITERATIONS and k_ref == k
+    sid = {"PCG": api.CLCG_PCG, "BICG": api.CLCG_BICG, "BICG_SYM": api.CLCG_BICG_SYM}[name]
+    para = api.clcg_default_parameters(epsilon=1e-30, max_iterations=k)
+    op = api.CsrOperator(Ac["row_ptr"], Ac["col"], val32, transpose=(name == "BICG"), jacobi=(name == "PCG"))
+    assert op.single
+    hist = []
+    m = np.zeros(n, dtype=np.complex64)
+    pf = lambda i, md, c, p, nn, nz, kk: hist.append(c) or 0
+    if name == "PCG":
+        ret = api.clcg_solver_preconditioned_cudaf(api.CSR_CAX, api.JACOBI_CMX, pf, m, b32, n, nnz, para, op)
+    else:
+        ret = api.clcg_solver_cudaf(api.CSR_CAX, pf, m, b32, n, nnz, para, op, solver_id=sid)
+    assert ret == ret_ref, api.last_error()
+    op.close()
+    # the same system (rounded to float) solved in double: the yardstick for both float paths
+    A64 = dict(Ac, val=val32.astype(np.complex128))
+    r64, x64 = gpu_cplx(A64, sid, b32.astype(np.complex128), api.clcg_default_parameters(epsilon=1e-300, max_iterations=k), diag=(name == "PCG"))
+    assert r64.iterations == k
+    e_ref, e_our, d = rel(m_ref.astype(np.complex128), x64), rel(m.astype(np.complex128), x64), rel(m.astype(np.complex128), m_ref.astype(np.complex128))
+    assert e_our <= 2.0 * e_ref + 1e-5, (e_our, e_ref)
+    assert d <= 3.0 * e_ref + 1e-5, (d, e_ref)
+    assert len(hist) == len(h_ref)
+    np.testing.assert_allclose(hist, h_ref, rtol=1e-3 + 20 * e_ref)
+
+
 def test_complex_history_and_stop(torch_cuda, port, fixtures):
     Ac = fixtures["1Kc"]
     api.set_shadow_seed(99)
