@@ -459,11 +459,9 @@ __device__ __forceinline__ void push_signal(CommDev* c, unsigned long long seq, 
 // and its writes are visible — the launch latency and block scheduling of kernel k+1 overlap the tail of kernel k (the
 // last block's grid reduction and its cross-GPU round trip).  Every kernel launched through launch_k() therefore starts
 // with pdl_enter(): wait for the predecessor, then allow the successor to be scheduled behind us.
-__device__ __forceinline__ void pdl_enter()
-{
-	asm volatile("griddepcontrol.wait;" ::: "memory");
-	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_wait(); pdl_trigger(); }
 
 bool pdl_enabled();   // engine.cu: lcgb200_set_pdl / LCGB200_PDL (default on)
 

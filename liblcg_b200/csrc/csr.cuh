@@ -283,8 +283,11 @@ template <class T, int LPR, bool CONJ, class Epi, bool PART = false>
 __global__ void __launch_bounds__(kSpmvThreads, TileCfg<T>::CTAS) k_spmv(CsrDev<T> A, const T* __restrict__ x, T* __restrict__ y, Epi epi_in,
 	DevState* st, double* partials)
 {
-	pdl_enter();
-	if (st_done(st)) return;
+	// Programmatic dependent launch: this grid may be scheduled while its predecessor (the kernel that wrote x and the
+	// iteration scalars) is still in its reduction tail.  Nothing the predecessor writes is touched before pdl_wait(): the
+	// barriers are set up and the producer already streams the first stages of the MATRIX (which no kernel of the solve
+	// writes) into shared memory, so the consumers find their first tiles waiting when the predecessor completes.
+	pdl_trigger();
 	typedef StageCfg<T> SC;
 	constexpr int TN = SC::NNZ;
 	extern __shared__ __align__(128) unsigned char smem[];
@@ -309,11 +312,13 @@ __global__ void __launch_bounds__(kSpmvThreads, TileCfg<T>::CTAS) k_spmv(CsrDev<
 
 	if (producer)
 	{
-		if (tid == kThreads)
+		if (tid != kThreads) { pdl_wait(); if (st_done(st)) return; }
+		else
 		{
 			const uint64_t pol = l2_evict_first_policy();
 			int idx = 0;
-			for (int c = blockIdx.x; c < n_chunks; c += gridDim.x)
+			bool waited = false, stop = false;
+			for (int c = blockIdx.x; c < n_chunks && !stop; c += gridDim.x)
 			{
 				const int t1 = min((c + 1) * A.chunk, A.n_tiles);
 				for (int tile = c * A.chunk; tile < t1; tile++)
@@ -321,6 +326,11 @@ __global__ void __launch_bounds__(kSpmvThreads, TileCfg<T>::CTAS) k_spmv(CsrDev<
 					const int4 td = __ldg(A.tiles + tile);
 					if (td.w - td.z > TN) continue;   // over-long row: the consumers stream it from global memory
 					const int s = idx % kStages, j = idx / kStages;
+					if (j > 0 && !waited)
+					{	// the first kStages tiles went out ahead of the predecessor's completion; from here on the consumers are needed
+						pdl_wait(); waited = true;
+						if (st_done(st)) { stop = true; break; }
+					}
 					if (j > 0) mbar_wait(smem_u32(&s_bar[kStages + s]), (uint32_t)((j - 1) & 1));
 					const uint32_t cnt = (uint32_t)((td.w - td.z + 3) & ~3);
 					const int ra = td.x & ~3;
@@ -337,10 +347,18 @@ __global__ void __launch_bounds__(kSpmvThreads, TileCfg<T>::CTAS) k_spmv(CsrDev<
 					idx++;
 				}
 			}
+			if (!waited) { pdl_wait(); if (st_done(st)) stop = true; }
+			if (stop)
+			{	// the solve is over and the consumers have left: let the copies already in flight land before this CTA's shared memory is released
+				for (int s = 0; s < kStages && s < idx; s++) mbar_wait(smem_u32(&s_bar[s]), 0u);
+				return;
+			}
 		}
 	}
 	else
 	{
+		pdl_wait();
+		if (st_done(st)) return;
 		epi.begin(st);
 		int idx = 0, c = blockIdx.x;
 		if (PART && A.n_interior >= 0)
