@@ -100,6 +100,12 @@ enum {
 	                                 addition the rows fall into <= 256 distinct patterns, keep one pattern id per ROW and stream only
 	                                 that.  Same entries, row sums accumulated left to right.  Silently stays uncompressed when the
 	                                 matrix does not fit (lcgb200_csr_format). */
+	LCGB200_CSR_IC0 = 8,         /* zero-fill incomplete Cholesky of the (symmetric, square, unpartitioned) matrix at creation: the
+	                                 reference's sequential algorithm on the host (lcg_incomplete_Cholesky_half_coo, preconditioner.cpp:33-160;
+	                                 clcg_incomplete_Cholesky_cuda_half, preconditioner_cuda.cu:40-270; complex: L L^T, unconjugated),
+	                                 bit-identical factor; L, L^T and their level orders are kept on the device so that lcgb200_ic0_mx /
+	                                 lcgb200_ic0_cmx apply z = L^-T L^-1 r by two level-ordered triangular solves (what the reference's
+	                                 samples do with cusparseSpSV in their Mx callback, sample12.cu:95-105) */
 	LCGB200_CSR_JACOBI = 2       /* extract diag(A) at creation (replaces lcg_smDcsr_get_diagonal, algebra_cuda.cu:40-57,
 	                                 lcg_complex_cuda.cu:46-63) so lcgb200_jacobi_mx can be used */
 };
@@ -117,6 +123,15 @@ int lcgb200_csr_destroy(lcgb200_csr_t A);
 int lcgb200_csr_set_user(lcgb200_csr_t A, void* user_instance);
 /* diag(A) to a HOST array of n values (double or interleaved complex) */
 int lcgb200_csr_get_diagonal(lcgb200_csr_t A, void* diag_host);
+/* the IC(0) factor of a handle created with LCGB200_CSR_IC0: number of entries of L, its CSR arrays on the HOST (any pointer
+ * may be NULL; values double / interleaved complex in the handle's precision) and the number of dependency levels of the
+ * forward (L) and backward (L^T) solves */
+int lcgb200_csr_get_ic0(lcgb200_csr_t A, int* lnz, int* row_ptr_host, int* col_host, void* val_host, int* n_levels_lower, int* n_levels_upper);
+/* z = (L L^T)^-1 r on device vectors: one application of the IC(0) preconditioner (two sparse triangular solves) */
+int lcgb200_csr_ic0_apply(lcgb200_csr_t A, const void* r_dev, void* z_dev, void* stream);
+/* the factorisation alone, on the host, in place on the lower triangle given as CSR (row_ptr[n+1], ascending columns, the
+ * diagonal last in every row): the arithmetic of preconditioner.cpp:33-160 / preconditioner_cuda.cu:40-270 */
+int lcgb200_ic0_factor_host(int n, const int* row_ptr, const int* col, void* val, int value_type);
 /* y = op(A) x on device vectors; op: 0 = N, 1 = T, 2 = H (T/H need LCGB200_CSR_TRANSPOSE).  stream = cudaStream_t */
 int lcgb200_csr_spmv(lcgb200_csr_t A, const void* x_dev, void* y_dev, int op, void* stream);
 /* y = A x fused with the dot products the solvers take from it: dots[0] = w.y (w = x if w_dev is NULL),
@@ -191,6 +206,8 @@ int lcgb200_comm_p2p_detach(lcgb200_comm_t comm);
 /* Sentinel callbacks: never called; their ADDRESS selects the built-in operator.  instance = lcgb200_csr_t. */
 void lcgb200_csr_ax(void* instance, lcgb200_cublas_t, lcgb200_cusparse_t, lcgb200_dnvec_t x, lcgb200_dnvec_t Ax, const int n, const int nz);
 void lcgb200_jacobi_mx(void* instance, lcgb200_cublas_t, lcgb200_cusparse_t, lcgb200_dnvec_t x, lcgb200_dnvec_t Mx, const int n, const int nz);
+void lcgb200_ic0_mx(void* instance, lcgb200_cublas_t, lcgb200_cusparse_t, lcgb200_dnvec_t x, lcgb200_dnvec_t Mx, const int n, const int nz);   /* needs LCGB200_CSR_IC0 */
+void lcgb200_ic0_cmx(void* instance, lcgb200_cublas_t, lcgb200_cusparse_t, lcgb200_dnvec_t x, lcgb200_dnvec_t Mx, const int n, const int nz, int oper_t);
 void lcgb200_csr_cax(void* instance, lcgb200_cublas_t, lcgb200_cusparse_t, lcgb200_dnvec_t x, lcgb200_dnvec_t Ax, const int n, const int nz, int oper_t);
 void lcgb200_jacobi_cmx(void* instance, lcgb200_cublas_t, lcgb200_cusparse_t, lcgb200_dnvec_t x, lcgb200_dnvec_t Mx, const int n, const int nz, int oper_t);
 
@@ -248,6 +265,7 @@ typedef void (*lcgb200_caxfunc_ptr)(void* instance, const void* x, void* prod_Ax
 typedef int (*lcgb200_cprogress_ptr)(void* instance, const void* m, const double converge, const lcgb200_cpara* param, const int n_size, const int k);
 void lcgb200_csr_ax_host(void* instance, const double* x, double* prod_Ax, const int n_size);        /* sentinel */
 void lcgb200_jacobi_mx_host(void* instance, const double* x, double* prod_Mx, const int n_size);     /* sentinel */
+void lcgb200_ic0_mx_host(void* instance, const double* x, double* prod_Mx, const int n_size);        /* sentinel: built-in IC(0) */
 void lcgb200_csr_cax_host(void* instance, const void* x, void* prod_Ax, const int n_size, int layout, int conjugate);   /* sentinel */
 int lcgb200_solver(lcgb200_axfunc_ptr Afp, lcgb200_progress_ptr Pfp, double* m, const double* B, const int n_size,
 	const lcgb200_para* param, void* instance, int solver_id);
@@ -286,7 +304,8 @@ typedef struct lcgb200_info {
 
 enum {
 	LCGB200_VEC_DEVICE = 1,   /* m, B (low, hig) are device pointers */
-	LCGB200_USE_JACOBI = 2    /* PCG: built-in Jacobi z = r/diag (needs LCGB200_CSR_JACOBI) */
+	LCGB200_USE_JACOBI = 2,   /* PCG: built-in Jacobi z = r/diag (needs LCGB200_CSR_JACOBI) */
+	LCGB200_USE_IC0 = 4       /* PCG: built-in IC(0) z = L^-T L^-1 r (needs LCGB200_CSR_IC0) */
 };
 
 /* real solvers on the built-in operator: solver_id in LCGB200_CG..LCGB200_SPG (low/hig only for PG, SPG) */

@@ -50,6 +50,12 @@ SYMBOLS = {
     "lcgb200_csr_destroy": (_I, [_VP]),
     "lcgb200_csr_set_user": (_I, [_VP, _VP]),
     "lcgb200_csr_get_diagonal": (_I, [_VP, _VP]),
+    "lcgb200_csr_get_ic0": (_I, [_VP, C.POINTER(_I), _VP, _VP, _VP, C.POINTER(_I), C.POINTER(_I)]),
+    "lcgb200_csr_ic0_apply": (_I, [_VP, _VP, _VP, _VP]),
+    "lcgb200_ic0_factor_host": (_I, [_I, _VP, _VP, _VP, _I]),
+    "lcgb200_ic0_mx": (None, None),
+    "lcgb200_ic0_cmx": (None, None),
+    "lcgb200_ic0_mx_host": (None, None),
     "lcgb200_csr_spmv": (_I, [_VP, _VP, _VP, _I, _VP]),
     "lcgb200_csr_spmv_dot": (_I, [_VP, _VP, _VP, _VP, _VP, _VP]),
     "lcgb200_csr_spmv_bytes": (_LL, [_VP]),

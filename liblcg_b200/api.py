@@ -31,8 +31,8 @@ CLCG_REACHED_MAX_ITERATIONS, CLCG_NAN_VALUE, CLCG_INVALID_POINTER, CLCG_SIZE_NOT
 
 REAL, COMPLEX, COMPLEX_FLOAT = 0, 1, 2
 HOST, DEVICE = 0, 1
-CSR_TRANSPOSE, CSR_JACOBI, CSR_COMPRESS = 1, 2, 4
-VEC_DEVICE, USE_JACOBI = 1, 2
+CSR_TRANSPOSE, CSR_JACOBI, CSR_COMPRESS, CSR_IC0 = 1, 2, 4, 8
+VEC_DEVICE, USE_JACOBI, USE_IC0 = 1, 2, 4
 
 
 class _Sentinel:
@@ -48,6 +48,8 @@ CSR_AX = _Sentinel("lcgb200_csr_ax")
 JACOBI_MX = _Sentinel("lcgb200_jacobi_mx")
 CSR_CAX = _Sentinel("lcgb200_csr_cax")
 JACOBI_CMX = _Sentinel("lcgb200_jacobi_cmx")
+IC0_MX = _Sentinel("lcgb200_ic0_mx")      # built-in IC(0) preconditioner (operator created with ic0=True)
+IC0_CMX = _Sentinel("lcgb200_ic0_cmx")
 
 
 def lcg_default_parameters(**kw) -> LcgPara:
@@ -106,7 +108,7 @@ def _ptr(a):
 class CsrOperator:
     """Built-in CSR operator handle (lcgb200_csr_t).  Arrays may be numpy (host) or torch CUDA tensors (device)."""
 
-    def __init__(self, row_ptr, col, val, n_cols=None, transpose=False, jacobi=False, compress=False):
+    def __init__(self, row_ptr, col, val, n_cols=None, transpose=False, jacobi=False, compress=False, ic0=False):
         lib = _lib.load()
         on_dev = hasattr(val, "data_ptr")
         if on_dev:
@@ -129,7 +131,7 @@ class CsrOperator:
             nnz = len(col)
         self.n, self.nnz, self.complex, self.single = n, nnz, bool(cx), bool(cx and single)
         self.n_cols = n if n_cols is None else n_cols
-        flags = (CSR_TRANSPOSE if transpose else 0) | (CSR_JACOBI if jacobi else 0) | (CSR_COMPRESS if compress else 0)
+        flags = (CSR_TRANSPOSE if transpose else 0) | (CSR_JACOBI if jacobi else 0) | (CSR_COMPRESS if compress else 0) | (CSR_IC0 if ic0 else 0)
         h = C.c_void_p()
         rc = lib.lcgb200_csr_create_rect(C.byref(h), n, self.n_cols, nnz, _ptr(row_ptr), _ptr(col), _ptr(val),
                                          (COMPLEX_FLOAT if self.single else COMPLEX) if cx else REAL, DEVICE if on_dev else HOST, flags)
@@ -169,6 +171,27 @@ class CsrOperator:
         if rc != 0:
             raise RuntimeError(f"get_diagonal failed ({rc})")
         return out
+
+    def ic0_factor(self):
+        """The IC(0) factor L of an operator created with ic0=True: dict(row_ptr, col, val, levels_lower, levels_upper)."""
+        lib = _lib.load()
+        lnz, ll, lu = C.c_int(), C.c_int(), C.c_int()
+        rc = lib.lcgb200_csr_get_ic0(self.handle, C.byref(lnz), None, None, None, C.byref(ll), C.byref(lu))
+        if rc != 0:
+            raise RuntimeError(f"lcgb200_csr_get_ic0 failed ({rc}): {last_error()}")
+        rp = np.empty(self.n + 1, dtype=np.int32)
+        ci = np.empty(lnz.value, dtype=np.int32)
+        val = np.empty(lnz.value, dtype=(np.complex64 if getattr(self, "single", False) else np.complex128) if self.complex else np.float64)
+        rc = lib.lcgb200_csr_get_ic0(self.handle, None, rp.ctypes.data, ci.ctypes.data, val.ctypes.data, None, None)
+        if rc != 0:
+            raise RuntimeError(f"lcgb200_csr_get_ic0 failed ({rc}): {last_error()}")
+        return dict(row_ptr=rp, col=ci, val=val, levels_lower=ll.value, levels_upper=lu.value)
+
+    def ic0_apply(self, r_dev, z_dev, stream=None):
+        """z = (L L^T)^-1 r on device vectors (two sparse triangular solves)."""
+        rc = _lib.load().lcgb200_csr_ic0_apply(self.handle, _ptr(r_dev), _ptr(z_dev), stream)
+        if rc != 0:
+            raise RuntimeError(f"ic0_apply failed ({rc}): {last_error()}")
 
     def spmv(self, x_dev, y_dev, op=0, stream=None):
         rc = _lib.load().lcgb200_csr_spmv(self.handle, _ptr(x_dev), _ptr(y_dev), op, stream)
@@ -396,21 +419,34 @@ def clcg_solver(Afp, Pfp, m, B, n_size, param, instance, solver_id=CLCG_BICG) ->
 
 
 # ------------------------------------------------------------------------------------- handle-shaped calls
-def solve(A: CsrOperator, solver_id, m, B, low=None, hig=None, param=None, Pfp=None, device=False, jacobi=False, stream=None) -> Result:
+def ic0_factor_host(row_ptr, col, val):
+    """lcgb200_ic0_factor_host: IC(0) of the lower triangle given as CSR (diagonal last in every row), on the host, in place."""
+    val = np.ascontiguousarray(val)
+    vt = {np.dtype(np.float64): REAL, np.dtype(np.complex128): COMPLEX, np.dtype(np.complex64): COMPLEX_FLOAT}[val.dtype]
+    rp = np.ascontiguousarray(row_ptr, dtype=np.int32)
+    ci = np.ascontiguousarray(col, dtype=np.int32)
+    out = val.copy()
+    rc = _lib.load().lcgb200_ic0_factor_host(len(rp) - 1, rp.ctypes.data, ci.ctypes.data, out.ctypes.data, vt)
+    if rc != 0:
+        raise RuntimeError(f"lcgb200_ic0_factor_host failed ({rc})")
+    return out
+
+
+def solve(A: CsrOperator, solver_id, m, B, low=None, hig=None, param=None, Pfp=None, device=False, jacobi=False, stream=None, ic0=False) -> Result:
     """lcgb200_solve: real solvers on the built-in operator; m/B numpy (host) or CUDA tensors (device=True)."""
     cb, cbp = _wrap_progress(Pfp, False)
     info = Info()
-    flags = (VEC_DEVICE if device else 0) | (USE_JACOBI if jacobi else 0)
+    flags = (VEC_DEVICE if device else 0) | (USE_JACOBI if jacobi else 0) | (USE_IC0 if ic0 else 0)
     rc = _lib.load().lcgb200_solve(A.handle, solver_id, _ptr(m), _ptr(B), _ptr(low), _ptr(hig),
                                    C.byref(param) if param is not None else None, cbp, flags, stream, C.byref(info))
     return Result(rc, info.iterations, info.residual, info)
 
 
-def csolve(A: CsrOperator, solver_id, m, B, param=None, Pfp=None, device=False, jacobi=False, stream=None) -> Result:
+def csolve(A: CsrOperator, solver_id, m, B, param=None, Pfp=None, device=False, jacobi=False, stream=None, ic0=False) -> Result:
     """lcgb200_csolve: complex solvers on the built-in operator."""
     cb, cbp = _wrap_progress(Pfp, True)
     info = Info()
-    flags = (VEC_DEVICE if device else 0) | (USE_JACOBI if jacobi else 0)
+    flags = (VEC_DEVICE if device else 0) | (USE_JACOBI if jacobi else 0) | (USE_IC0 if ic0 else 0)
     rc = _lib.load().lcgb200_csolve(A.handle, solver_id, _ptr(m), _ptr(B), C.byref(param) if param is not None else None,
                                     cbp, flags, stream, C.byref(info))
     return Result(rc, info.iterations, info.residual, info)

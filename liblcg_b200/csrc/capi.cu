@@ -2,6 +2,7 @@
 // reference's order, host<->device staging of m/B as the reference does it (lcg_cuda.cu:110-111,210), and the
 // adaptors that let user Ax/Mx callbacks (cuSPARSE descriptors) drive the same engine.
 #include "solvers.cuh"
+#include "ic0_host.h"
 #include <dlfcn.h>
 #include <cstring>
 #include <string>
@@ -344,6 +345,74 @@ bool try_compress(CsrHandle* h, const std::vector<int>& rp_h)
 	return true;
 }
 
+// ---- IC(0) preconditioner (LCGB200_CSR_IC0) ---------------------------------------------------------------------------
+template <class T> struct IcTraits;
+template <> struct IcTraits<double> { typedef IcReal M; };
+template <> struct IcTraits<double2> { typedef IcCplx M; };
+template <> struct IcTraits<ZF> { typedef IcCplxF M; };
+
+template <class V>
+void upload_factor(IcDev& F, int n, const std::vector<int>& rp, const std::vector<int>& ci, const std::vector<V>& val, bool upper)
+{
+	std::vector<int> order;
+	F.n = n;
+	F.n_levels = level_order(n, rp.data(), ci.data(), upper, 32, order);
+	F.n_pos = (int)order.size();
+	F.rp = dev_alloc<int>(rp.size()); F.ci = dev_alloc<int>(ci.size()); F.val = dev_alloc<V>(val.size());
+	F.order = dev_alloc<int>(order.size()); F.ready = dev_alloc<int>((size_t)n); F.ctl = dev_alloc<IcCtl>(1);
+	LCG_CUDA_CHECK(cudaMemcpy(F.rp, rp.data(), rp.size() * sizeof(int), cudaMemcpyHostToDevice));
+	LCG_CUDA_CHECK(cudaMemcpy(F.ci, ci.data(), ci.size() * sizeof(int), cudaMemcpyHostToDevice));
+	LCG_CUDA_CHECK(cudaMemcpy(F.val, val.data(), val.size() * sizeof(V), cudaMemcpyHostToDevice));
+	LCG_CUDA_CHECK(cudaMemcpy(F.order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice));
+	LCG_CUDA_CHECK(cudaMemset(F.ready, 0, (size_t)n * sizeof(int)));
+	LCG_CUDA_CHECK(cudaMemset(F.ctl, 0, sizeof(IcCtl)));
+}
+
+// factorise the lower triangle of the (symmetric) matrix on the host — the reference's sequential algorithm, ic0_host.h —
+// and put L, U = L^T and their level orders on the device
+template <class T>
+void setup_ic0(CsrHandle* h, const std::vector<int>& rp_h, const int* col, const T* val, bool on_device)
+{
+	typedef typename IcTraits<T>::M M;
+	typedef typename M::T V;
+	static_assert(sizeof(V) == sizeof(T), "storage types are layout-compatible with the reference's");
+	const int n = h->n_rows, nnz = h->nnz;
+	if (h->n_cols != n) { set_error_msg("IC(0) needs a square (unpartitioned) operator"); throw ApiFailure{LCGB200_SIZE_NOT_MATCH}; }
+	std::vector<int> ci_h((size_t)nnz); std::vector<V> v_h((size_t)nnz);
+	const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost;
+	if (nnz > 0)
+	{
+		LCG_CUDA_CHECK(cudaMemcpy(ci_h.data(), col, (size_t)nnz * sizeof(int), kind));
+		LCG_CUDA_CHECK(cudaMemcpy(v_h.data(), val, (size_t)nnz * sizeof(V), kind));
+	}
+	std::vector<int> lrp((size_t)n + 1, 0), lci; std::vector<V> lv;
+	for (int i = 0; i < n; i++)
+	{
+		for (int k = rp_h[(size_t)i]; k < rp_h[(size_t)i + 1]; k++) if (ci_h[(size_t)k] <= i) { lci.push_back(ci_h[(size_t)k]); lv.push_back(v_h[(size_t)k]); }
+		lrp[(size_t)i + 1] = (int)lci.size();
+	}
+	if (!ic0_lower<M>(n, lrp.data(), lci.data(), lv.data()))
+	{
+		set_error_msg("IC(0): every row needs a diagonal entry and ascending column indices");
+		throw ApiFailure{LCGB200_NULL_PRECONDITION_MATRIX};
+	}
+	// U = L^T by counting (rows of U: ascending columns, the diagonal first)
+	std::vector<int> urp((size_t)n + 1, 0), uci(lci.size()); std::vector<V> uv(lv.size());
+	for (size_t k = 0; k < lci.size(); k++) urp[(size_t)lci[k] + 1]++;
+	for (int i = 0; i < n; i++) urp[(size_t)i + 1] += urp[(size_t)i];
+	{
+		std::vector<int> fill(urp.begin(), urp.end() - 1);
+		for (int i = 0; i < n; i++)
+			for (int k = lrp[(size_t)i]; k < lrp[(size_t)i + 1]; k++) { const int d = fill[(size_t)lci[(size_t)k]]++; uci[(size_t)d] = i; uv[(size_t)d] = lv[(size_t)k]; }
+	}
+	upload_factor<V>(h->icL, n, lrp, lci, lv, false);
+	upload_factor<V>(h->icU, n, urp, uci, uv, true);
+	h->ic_tmp = dev_alloc<V>((size_t)n);
+	h->has_ic0 = true;
+}
+
+void free_factor(IcDev& F) { cudaFree(F.rp); cudaFree(F.ci); cudaFree(F.val); cudaFree(F.order); cudaFree(F.ready); cudaFree(F.ctl); F = IcDev(); }
+
 template <class T>
 void create_typed(CsrHandle* h, const int* row_ptr, const int* col, const T* val, int location, int tile_nnz)
 {
@@ -385,6 +454,7 @@ void create_typed(CsrHandle* h, const int* row_ptr, const int* col, const T* val
 		upload_csr<T>(h->n_cols, h->nnz, trp.data(), tci.data(), tv.data(), false, &h->t_row_ptr, &h->t_col, &h->t_val, &h->t_tiles, &h->t_n_tiles, tile_nnz, &h->t_lpr, &h->t_chunk);
 	}
 	if ((h->flags & LCGB200_CSR_COMPRESS) && std::is_same<T, double>::value) try_compress(h, rp_h);
+	if (h->flags & LCGB200_CSR_IC0) setup_ic0<T>(h, rp_h, col, val, dev);
 	if (h->flags & LCGB200_CSR_JACOBI)
 	{
 		T* d = dev_alloc<T>((size_t)h->n_rows);
@@ -405,6 +475,7 @@ void destroy_handle(CsrHandle* h)
 	cudaFree(h->t_row_ptr); cudaFree(h->t_col); cudaFree(h->t_val); cudaFree(h->t_tiles);
 	cudaFree(h->code); cudaFree(h->vdict); cudaFree(h->odict); cudaFree(h->dtiles);
 	cudaFree(h->pat); cudaFree(h->pat_len); cudaFree(h->pat_ent);
+	free_factor(h->icL); free_factor(h->icU); cudaFree(h->ic_tmp);
 	cudaFree(h->diag); cudaFree(h->ws);
 	cudaFree(h->d_state); cudaFree(h->d_partials);
 	if (h->h_state) cudaFreeHost(h->h_state);
@@ -669,6 +740,8 @@ void lcgb200_set_pdl(int mode) { settings().pdl = mode; }
 // sentinels: recognised by address, never executed on the fused path
 void lcgb200_csr_ax(void*, lcgb200_cublas_t, lcgb200_cusparse_t, lcgb200_dnvec_t, lcgb200_dnvec_t, const int, const int) {}
 void lcgb200_jacobi_mx(void*, lcgb200_cublas_t, lcgb200_cusparse_t, lcgb200_dnvec_t, lcgb200_dnvec_t, const int, const int) {}
+void lcgb200_ic0_mx(void*, lcgb200_cublas_t, lcgb200_cusparse_t, lcgb200_dnvec_t, lcgb200_dnvec_t, const int, const int) {}
+void lcgb200_ic0_cmx(void*, lcgb200_cublas_t, lcgb200_cusparse_t, lcgb200_dnvec_t, lcgb200_dnvec_t, const int, const int, int) {}
 void lcgb200_csr_cax(void*, lcgb200_cublas_t, lcgb200_cusparse_t, lcgb200_dnvec_t, lcgb200_dnvec_t, const int, const int, int) {}
 void lcgb200_jacobi_cmx(void*, lcgb200_cublas_t, lcgb200_cusparse_t, lcgb200_dnvec_t, lcgb200_dnvec_t, const int, const int, int) {}
 
@@ -724,6 +797,59 @@ int lcgb200_csr_set_row_offset(lcgb200_csr_t A, long long first_global_row)
 	if (!h || first_global_row < 0) return LCGB200_INVALID_POINTER;
 	h->row_offset = first_global_row;
 	return 0;
+}
+
+int lcgb200_csr_get_ic0(lcgb200_csr_t A, int* lnz, int* row_ptr_host, int* col_host, void* val_host, int* n_levels_lower, int* n_levels_upper)
+{
+	CsrHandle* h = reinterpret_cast<CsrHandle*>(A);
+	if (!h) return LCGB200_INVALID_POINTER;
+	if (!h->has_ic0) return LCGB200_NULL_PRECONDITION_MATRIX;
+	return guarded([&]() {
+		int total = 0;
+		LCG_CUDA_CHECK(cudaMemcpy(&total, h->icL.rp + h->n_rows, sizeof(int), cudaMemcpyDeviceToHost));
+		if (lnz) *lnz = total;
+		if (n_levels_lower) *n_levels_lower = h->icL.n_levels;
+		if (n_levels_upper) *n_levels_upper = h->icU.n_levels;
+		const size_t es = h->value_type == LCGB200_COMPLEX ? 16 : 8;
+		if (row_ptr_host) LCG_CUDA_CHECK(cudaMemcpy(row_ptr_host, h->icL.rp, ((size_t)h->n_rows + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+		if (col_host) LCG_CUDA_CHECK(cudaMemcpy(col_host, h->icL.ci, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost));
+		if (val_host) LCG_CUDA_CHECK(cudaMemcpy(val_host, h->icL.val, (size_t)total * es, cudaMemcpyDeviceToHost));
+		return 0;
+	});
+}
+
+// z = (L L^T)^-1 r on device vectors with the handle's IC(0) factor (the two triangular solves of one preconditioner application)
+int lcgb200_csr_ic0_apply(lcgb200_csr_t A, const void* r_dev, void* z_dev, void* stream)
+{
+	CsrHandle* h = reinterpret_cast<CsrHandle*>(A);
+	if (!h || !r_dev || !z_dev) return LCGB200_INVALID_POINTER;
+	if (!h->has_ic0) return LCGB200_NULL_PRECONDITION_MATRIX;
+	cudaStream_t s = (cudaStream_t)stream;
+	return guarded([&]() {
+		Engine E(s, h);
+		E.n_local = (size_t)h->n_rows;
+		DevState init; std::memset(&init, 0, sizeof(init));
+		E.start(init);
+		if (h->value_type == LCGB200_REAL) E.ic0_solve<double>(h, (const double*)r_dev, (double*)z_dev);
+		else if (h->value_type == LCGB200_COMPLEX) E.ic0_solve<double2>(h, (const double2*)r_dev, (double2*)z_dev);
+		else E.ic0_solve<ZF>(h, (const ZF*)r_dev, (ZF*)z_dev);
+		LCG_CUDA_CHECK(cudaGetLastError());
+		return 0;
+	});
+}
+
+// The factorisation alone, on the host (no GPU needed): lower triangle as CSR (row_ptr[n+1], ascending columns, diagonal last
+// in every row), values factorised in place.  value_type LCGB200_REAL / LCGB200_COMPLEX / LCGB200_COMPLEX_FLOAT.
+int lcgb200_ic0_factor_host(int n, const int* row_ptr, const int* col, void* val, int value_type)
+{
+	if (n <= 0) return LCGB200_INVILAD_VARIABLE_SIZE;
+	if (!row_ptr || !col || !val) return LCGB200_INVALID_POINTER;
+	bool ok = false;
+	if (value_type == LCGB200_REAL) ok = ic0_lower<IcReal>(n, row_ptr, col, static_cast<double*>(val));
+	else if (value_type == LCGB200_COMPLEX) ok = ic0_lower<IcCplx>(n, row_ptr, col, static_cast<cuDoubleComplex*>(val));
+	else if (value_type == LCGB200_COMPLEX_FLOAT) ok = ic0_lower<IcCplxF>(n, row_ptr, col, static_cast<cuComplex*>(val));
+	else return LCGB200_INVILAD_VARIABLE_SIZE;
+	return ok ? 0 : LCGB200_NULL_PRECONDITION_MATRIX;
 }
 
 int lcgb200_csr_get_diagonal(lcgb200_csr_t A, void* diag_host)
@@ -880,10 +1006,10 @@ int lcgb200_solve(lcgb200_csr_t Ah, int solver_id, double* m, const double* B, c
 	if (solver_id < LCGB200_CG || solver_id > LCGB200_SPG) solver_id = LCGB200_CGS;	// lcg.cpp:76-78
 	int rc = check_real(solver_id, h->n_rows, para, m, B, low, hig);
 	if (rc) return rc;
-	if (solver_id == LCGB200_PCG && !((flags & LCGB200_USE_JACOBI) && h->diag)) return LCGB200_NULL_PRECONDITION_MATRIX;
+	if (solver_id == LCGB200_PCG && !(((flags & LCGB200_USE_JACOBI) && h->diag) || ((flags & LCGB200_USE_IC0) && h->has_ic0))) return LCGB200_NULL_PRECONDITION_MATRIX;
 	return guarded([&]() {
 		Operator<double> A; A.h = h;
-		if (solver_id == LCGB200_PCG) A.diag = (const double*)h->diag;
+		if (solver_id == LCGB200_PCG) { if (flags & LCGB200_USE_IC0) A.ic0 = h; else A.diag = (const double*)h->diag; }
 		auto make_pf = [&](const double* m_dev) -> ProgressFn {
 			if (!Pfp) return ProgressFn();
 			return [=](double res, int k) { return Pfp(h->user, m_dev, res, &para, h->n_rows, h->nnz, k); };
@@ -908,13 +1034,14 @@ int lcgb200_csolve(lcgb200_csr_t Ah, int solver_id, void* m, const void* B, cons
 		set_error_msg("CLCG_BICG needs the transposed operator: create the handle with LCGB200_CSR_TRANSPOSE (a partitioned block: lcgb200_csr_attach_transpose)");
 		return LCGB200_C_UNKNOWN_SOLVER;
 	}
-	if (solver_id == LCGB200_CPCG && !((flags & LCGB200_USE_JACOBI) && h->diag)) return LCGB200_NULL_PRECONDITION_MATRIX;
+	if (solver_id == LCGB200_CPCG && !(((flags & LCGB200_USE_JACOBI) && h->diag) || ((flags & LCGB200_USE_IC0) && h->has_ic0))) return LCGB200_NULL_PRECONDITION_MATRIX;
+	const bool use_ic0 = (flags & LCGB200_USE_IC0) != 0;
 	return guarded([&]() {
 		const int n_ext = std::max(h->n_cols, h->t_handle ? h->t_handle->n_cols : 0);
 		if (h->value_type == LCGB200_COMPLEX_FLOAT)
 		{	// cuComplex vectors (m, B: interleaved float pairs)
 			Operator<ZF> A; A.h = h;
-			if (solver_id == LCGB200_CPCG) A.diag = (const ZF*)h->diag;
+			if (solver_id == LCGB200_CPCG) { if (use_ic0) A.ic0 = h; else A.diag = (const ZF*)h->diag; }
 			auto make_pf = [&](const ZF* m_dev) -> ProgressFn {
 				if (!Pfp) return ProgressFn();
 				return [=](double res, int k) { return Pfp(h->user, m_dev, res, &para, h->n_rows, h->nnz, k); };
@@ -923,7 +1050,7 @@ int lcgb200_csolve(lcgb200_csr_t Ah, int solver_id, void* m, const void* B, cons
 				(flags & LCGB200_VEC_DEVICE) != 0, (cudaStream_t)stream, info);
 		}
 		Operator<double2> A; A.h = h;
-		if (solver_id == LCGB200_CPCG) A.diag = (const double2*)h->diag;
+		if (solver_id == LCGB200_CPCG) { if (use_ic0) A.ic0 = h; else A.diag = (const double2*)h->diag; }
 		auto make_pf = [&](const double2* m_dev) -> ProgressFn {
 			if (!Pfp) return ProgressFn();
 			return [=](double res, int k) { return Pfp(h->user, m_dev, res, &para, h->n_rows, h->nnz, k); };
@@ -952,6 +1079,7 @@ static int ref_real(lcgb200_axfunc_cuda_ptr Afp, lcgb200_axfunc_cuda_ptr Mfp, lc
 		if (solver_id == LCGB200_PCG)
 		{
 			if (Mfp == lcgb200_jacobi_mx) { if (!h->diag) return LCGB200_NULL_PRECONDITION_MATRIX; }
+			else if (Mfp == lcgb200_ic0_mx) { if (!h->has_ic0) return LCGB200_NULL_PRECONDITION_MATRIX; }
 			else if (!Mfp) return LCGB200_INVALID_POINTER;
 		}
 		return guarded([&]() {
@@ -960,6 +1088,7 @@ static int ref_real(lcgb200_axfunc_cuda_ptr Afp, lcgb200_axfunc_cuda_ptr Mfp, lc
 			if (solver_id == LCGB200_PCG)
 			{
 				if (Mfp == lcgb200_jacobi_mx) A.diag = (const double*)h->diag;
+				else if (Mfp == lcgb200_ic0_mx) A.ic0 = h;
 				else
 				{
 					if (!g_cusparse.load()) throw ApiFailure{LCGB200_UNKNOWN_ERROR};
@@ -1038,6 +1167,7 @@ static int ref_cplx(lcgb200_caxfunc_cuda_ptr Afp, lcgb200_caxfunc_cuda_ptr Mfp, 
 		if (solver_id == LCGB200_CPCG)
 		{
 			if (Mfp == lcgb200_jacobi_cmx) { if (!h->diag) return LCGB200_NULL_PRECONDITION_MATRIX; }
+			else if (Mfp == lcgb200_ic0_cmx) { if (!h->has_ic0) return LCGB200_NULL_PRECONDITION_MATRIX; }
 			else if (!Mfp) return LCGB200_INVALID_POINTER;
 		}
 		return guarded([&]() {
@@ -1046,6 +1176,7 @@ static int ref_cplx(lcgb200_caxfunc_cuda_ptr Afp, lcgb200_caxfunc_cuda_ptr Mfp, 
 			if (solver_id == LCGB200_CPCG)
 			{
 				if (Mfp == lcgb200_jacobi_cmx) A.diag = (const ZV*)h->diag;
+				else if (Mfp == lcgb200_ic0_cmx) A.ic0 = h;
 				else
 				{
 					if (!g_cusparse.load()) throw ApiFailure{LCGB200_UNKNOWN_ERROR};
@@ -1152,6 +1283,7 @@ int host_real(lcgb200_axfunc_ptr Afp, lcgb200_axfunc_ptr Mfp, lcgb200_progress_p
 	{
 		if (!Mfp) return LCGB200_INVALID_POINTER;
 		if (Mfp == lcgb200_jacobi_mx_host && !(builtin && h->diag)) return LCGB200_NULL_PRECONDITION_MATRIX;
+		if (Mfp == lcgb200_ic0_mx_host && !(builtin && h->has_ic0)) return LCGB200_NULL_PRECONDITION_MATRIX;
 	}
 	return guarded([&]() {
 		HostStage<double> hs(n);
@@ -1166,6 +1298,7 @@ int host_real(lcgb200_axfunc_ptr Afp, lcgb200_axfunc_ptr Mfp, lcgb200_progress_p
 		if (solver_id == LCGB200_PCG)
 		{
 			if (Mfp == lcgb200_jacobi_mx_host) A.diag = (const double*)h->diag;
+			else if (Mfp == lcgb200_ic0_mx_host) A.ic0 = h;
 			else { A.precond = [&](const double* x, double* y, int) { host_call(Mfp, x, y); }; A.host_side = true; }
 		}
 		auto make_pf = [&](const double* m_dev) -> ProgressFn {
@@ -1186,6 +1319,7 @@ extern "C" {
 
 void lcgb200_csr_ax_host(void*, const double*, double*, const int) {}
 void lcgb200_jacobi_mx_host(void*, const double*, double*, const int) {}
+void lcgb200_ic0_mx_host(void*, const double*, double*, const int) {}
 void lcgb200_csr_cax_host(void*, const void*, void*, const int, int, int) {}
 
 int lcgb200_solver(lcgb200_axfunc_ptr Afp, lcgb200_progress_ptr Pfp, double* m, const double* B, const int n_size,

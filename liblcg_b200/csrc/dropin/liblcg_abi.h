@@ -75,6 +75,22 @@ void clcg_dot(lcg_complex& ret, const lcg_complex* a, const lcg_complex* b, int 
 void clcg_inner(lcg_complex& ret, const lcg_complex* a, const lcg_complex* b, int size);
 void clcg_matvec(lcg_complex** A, const lcg_complex* x, lcg_complex* Ax, int m_size, int n_size, lcg_matrix_e layout, clcg_complex_e conjugate);
 
+// ---- preconditioner.h / preconditioner_cuda.h: IC(0) of a row-sorted COO matrix and the COO triangular solves (host code)
+void lcg_incomplete_Cholesky_half_buffsize_coo(const int* row, const int* col, int nz_size, int* lnz_size);
+void lcg_incomplete_Cholesky_half_coo(const int* row, const int* col, const lcg_float* val, int N, int nz_size, int lnz_size, int* IC_row, int* IC_col,
+	lcg_float* IC_val);
+void lcg_incomplete_Cholesky_full_coo(const int* row, const int* col, const lcg_float* val, int N, int nz_size, int* IC_row, int* IC_col, lcg_float* IC_val);
+void lcg_solve_upper_triangle_coo(const int* row, const int* col, const lcg_float* U, const lcg_float* B, lcg_float* x, int N, int nz_size);
+void lcg_solve_lower_triangle_coo(const int* row, const int* col, const lcg_float* L, const lcg_float* B, lcg_float* x, int N, int nz_size);
+bool lcg_full_rank_coo(const int* row, const int* col, const lcg_float* M, int N, int nz_size);
+void clcg_incomplete_Cholesky_cuda_half_buffsize(const int* row, const int* col, int nz_size, int* lnz_size);
+void clcg_incomplete_Cholesky_cuda_half(const int* row, const int* col, const cuComplex* val, int N, int nz_size, int lnz_size, int* IC_row, int* IC_col,
+	cuComplex* IC_val);
+void clcg_incomplete_Cholesky_cuda_half(const int* row, const int* col, const cuDoubleComplex* val, int N, int nz_size, int lnz_size, int* IC_row,
+	int* IC_col, cuDoubleComplex* IC_val);
+void clcg_incomplete_Cholesky_cuda_full(const int* row, const int* col, const cuDoubleComplex* val, int N, int nz_size, int* IC_row, int* IC_col,
+	cuDoubleComplex* IC_val);
+
 // ---- lcg.h / clcg.h: host-callback solvers
 typedef void (*lcg_axfunc_ptr)(void* instance, const lcg_float* x, lcg_float* prod_Ax, const int n_size);
 typedef int (*lcg_progress_ptr)(void* instance, const lcg_float* m, const lcg_float converge, const lcg_para* param, const int n_size, const int k);

@@ -8,6 +8,8 @@
 // the call (vector allocation, fill, dot); they are host-side conveniences, not part of the hot path.
 #include "liblcg_abi.h"
 #include "../../../include/lcgb200.h"
+#include "../ic0_host.h"
+#include <vector>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -213,6 +215,113 @@ void clcg_matvec(lcg_complex** A, const lcg_complex* x, lcg_complex* Ax, int m_s
 		for (int i = 0; i < m_size; i++) { lcg_complex s(0.0, 0.0); for (int j = 0; j < n_size; j++) s += (cj ? std::conj(A[i][j]) : A[i][j]) * x[j]; Ax[i] = s; }
 	else
 		for (int j = 0; j < n_size; j++) { lcg_complex s(0.0, 0.0); for (int i = 0; i < m_size; i++) s += (cj ? std::conj(A[i][j]) : A[i][j]) * x[i]; Ax[j] = s; }
+}
+
+// ------------------------------------------------------------------- preconditioner.h / preconditioner_cuda.h
+// IC(0) on row-sorted COO input: the lower triangle is copied out, factorised by the shared host routine (ic0_host.h: the
+// reference's operations in the reference's order, bit-identical factor) and, for the *_full variants, mirrored into the
+// upper positions of the output (which keeps the pattern of A).
+namespace {
+template <class M>
+void ic0_half_coo(const int* row, const int* col, const typename M::T* val, int N, int nz, int* ic_row, int* ic_col, typename M::T* ic_val)
+{
+	std::vector<int> rp((size_t)N + 1, 0);
+	int j = 0;
+	for (int i = 0; i < nz; i++)
+		if (row[i] >= col[i]) { ic_row[j] = row[i]; ic_col[j] = col[i]; ic_val[j] = val[i]; rp[(size_t)row[i] + 1]++; j++; }
+	for (int i = 0; i < N; i++) rp[(size_t)i + 1] += rp[(size_t)i];
+	lcgb200::ic0_lower<M>(N, rp.data(), ic_col, ic_val);
+}
+template <class M>
+void ic0_full_coo(const int* row, const int* col, const typename M::T* val, int N, int nz, int* ic_row, int* ic_col, typename M::T* ic_val)
+{
+	int lnz = 0;
+	for (int i = 0; i < nz; i++) lnz += row[i] >= col[i];
+	std::vector<int> lr((size_t)lnz), lc((size_t)lnz); std::vector<typename M::T> lv((size_t)lnz);
+	ic0_half_coo<M>(row, col, val, N, nz, lr.data(), lc.data(), lv.data());
+	// position of every lower entry, to mirror L(i,c) into (c,i)
+	std::vector<int> rp((size_t)N + 1, 0);
+	for (int k = 0; k < lnz; k++) rp[(size_t)lr[(size_t)k] + 1]++;
+	for (int i = 0; i < N; i++) rp[(size_t)i + 1] += rp[(size_t)i];
+	int l = 0;
+	for (int i = 0; i < nz; i++)
+	{
+		ic_row[i] = row[i]; ic_col[i] = col[i];
+		if (row[i] >= col[i]) ic_val[i] = lv[(size_t)l++];
+		else
+		{	// upper entry (r, c), r < c: the value of L(c, r) if the lower triangle holds it
+			ic_val[i] = val[i];
+			for (int k = rp[(size_t)col[i]]; k < rp[(size_t)col[i] + 1]; k++) if (lc[(size_t)k] == row[i]) { ic_val[i] = lv[(size_t)k]; break; }
+		}
+	}
+}
+}  // namespace
+
+void lcg_incomplete_Cholesky_half_buffsize_coo(const int* row, const int* col, int nz_size, int* lnz_size)
+{
+	int c = 0;
+	for (int i = 0; i < nz_size; i++) c += row[i] >= col[i];
+	*lnz_size = c;
+}
+void lcg_incomplete_Cholesky_half_coo(const int* row, const int* col, const lcg_float* val, int N, int nz_size, int, int* IC_row, int* IC_col, lcg_float* IC_val)
+{
+	ic0_half_coo<lcgb200::IcReal>(row, col, val, N, nz_size, IC_row, IC_col, IC_val);
+}
+void lcg_incomplete_Cholesky_full_coo(const int* row, const int* col, const lcg_float* val, int N, int nz_size, int* IC_row, int* IC_col, lcg_float* IC_val)
+{
+	ic0_full_coo<lcgb200::IcReal>(row, col, val, N, nz_size, IC_row, IC_col, IC_val);
+}
+void clcg_incomplete_Cholesky_cuda_half_buffsize(const int* row, const int* col, int nz_size, int* lnz_size)
+{
+	lcg_incomplete_Cholesky_half_buffsize_coo(row, col, nz_size, lnz_size);
+}
+void clcg_incomplete_Cholesky_cuda_half(const int* row, const int* col, const cuComplex* val, int N, int nz_size, int, int* IC_row, int* IC_col, cuComplex* IC_val)
+{
+	ic0_half_coo<lcgb200::IcCplxF>(row, col, val, N, nz_size, IC_row, IC_col, IC_val);
+}
+void clcg_incomplete_Cholesky_cuda_half(const int* row, const int* col, const cuDoubleComplex* val, int N, int nz_size, int, int* IC_row, int* IC_col,
+	cuDoubleComplex* IC_val)
+{
+	ic0_half_coo<lcgb200::IcCplx>(row, col, val, N, nz_size, IC_row, IC_col, IC_val);
+}
+void clcg_incomplete_Cholesky_cuda_full(const int* row, const int* col, const cuDoubleComplex* val, int N, int nz_size, int* IC_row, int* IC_col,
+	cuDoubleComplex* IC_val)
+{
+	ic0_full_coo<lcgb200::IcCplx>(row, col, val, N, nz_size, IC_row, IC_col, IC_val);
+}
+void lcg_solve_lower_triangle_coo(const int* row, const int* col, const lcg_float* L, const lcg_float* B, lcg_float* x, int N, int nz_size)
+{	// forward substitution over row-sorted COO, the row's sum accumulated left to right (preconditioner.cpp:340-366)
+	for (int i = 0; i < N; i++) x[i] = 0.0;
+	int k = 0;
+	for (int i = 0; i < N; i++)
+	{
+		double sum = 0.0;
+		for (; k < nz_size && row[k] == i; k++)
+		{
+			if (col[k] < i) sum += L[k] * x[col[k]];
+			else if (col[k] == i) { x[i] = (B[i] - sum) / L[k]; }
+		}
+	}
+}
+void lcg_solve_upper_triangle_coo(const int* row, const int* col, const lcg_float* U, const lcg_float* B, lcg_float* x, int N, int nz_size)
+{	// backward substitution, the row's sum accumulated right to left (preconditioner.cpp:300-338)
+	for (int i = 0; i < N; i++) x[i] = 0.0;
+	int k = nz_size - 1;
+	for (int i = N - 1; i >= 0; i--)
+	{
+		double sum = 0.0;
+		for (; k >= 0 && row[k] == i; k--)
+		{
+			if (col[k] > i) sum += U[k] * x[col[k]];
+			else if (col[k] == i) { x[i] = (B[i] - sum) / U[k]; }
+		}
+	}
+}
+bool lcg_full_rank_coo(const int* row, const int* col, const lcg_float* M, int N, int nz_size)
+{
+	int s = 0;
+	for (int i = 0; i < nz_size; i++) s += (row[i] == col[i] && M[i] != 0.0);
+	return s == N;
 }
 
 // --------------------------------------------------------------------------------------- host-callback solvers

@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "csr.cuh"
 #include "fused_small.cuh"
+#include "ic0.cuh"
 
 namespace lcgb200 {
 
@@ -55,6 +56,9 @@ struct CsrHandle {
 	int n_dtiles = 0, dchunk = 1, dlpr = 1, n_vdict = 0, n_odict = 0;
 	// row-pattern copy: one id per row + the table of distinct rows
 	unsigned char* pat = nullptr; int* pat_len = nullptr; double2* pat_ent = nullptr; int n_pat = 0, pat_maxlen = 0;
+	// IC(0) preconditioner (LCGB200_CSR_IC0): L (rows, diagonal last) and U = L^T (rows, diagonal first) with their level
+	// orders, plus the vector between the two triangular solves
+	IcDev icL, icU; void* ic_tmp = nullptr; bool has_ic0 = false;
 	void* user = nullptr;          // instance handed to progress callbacks
 	Comm* comm = nullptr;          // set for a row block of a partitioned system
 	// partitioned systems: the rows [r0, r1) of A^T live in a second partitioned handle with its own halo plan and windows
@@ -103,6 +107,7 @@ struct Operator {
 	ApplyFn<T> apply;               // otherwise
 	ApplyFn<T> precond;             // user M^-1 (generic path); empty when built-in Jacobi or none
 	const T* diag = nullptr;        // built-in Jacobi diagonal
+	const CsrHandle* ic0 = nullptr; // built-in IC(0): z = L^-T L^-1 r by two level-ordered triangular solves (ic0.cuh)
 	bool host_side = false;         // the callbacks run on the HOST (lcg.h API): check convergence before every call, never run ahead
 };
 
@@ -233,6 +238,22 @@ public:
 	}
 
 	size_t n_local = 0;
+
+	// z = (L L^T)^-1 r with the handle's IC(0) factor: forward solve into the handle's scratch vector, backward solve into z
+	template <class T> void ic0_solve(const CsrHandle* h, const T* r, T* z)
+	{
+		cudaEvent_t pe = profiling ? prof_begin(1) : nullptr;
+		launch_sptrsv<T, false>(h->icL, r, static_cast<T*>(h->ic_tmp), d_st, stream);
+		launch_sptrsv<T, true>(h->icU, static_cast<const T*>(h->ic_tmp), z, d_st, stream);
+		prof_end(pe);
+		launches += 2;
+	}
+	// M^-1 of the preconditioned solvers' generic path: the built-in IC(0) or the user's callback
+	template <class T> void precondition(const Operator<T>& A, const T* r, T* z)
+	{
+		if (A.ic0) ic0_solve<T>(A.ic0, r, z);
+		else A.precond(r, z, 0);
+	}
 
 	// cache-resident single-GPU systems on the built-in operator take the fused cooperative kernel (not while profiling:
 	// the per-kernel attribution of bench.py's roofline pass needs the separate launches)

@@ -241,7 +241,7 @@ static int run_csym(Engine& E, const Operator<ZV>& A, ZV* m, const ZV* B, size_t
 	else
 	{
 		E.vec(OpCsInit<2>{{}, m, Ax, B, nullptr, r, z, d}, n);
-		A.precond(r, z, 0);
+		E.precondition(A, r, z);
 		E.vec_push(OpCsInitZ{{}, r, z, d}, n, d);
 	}
 	std::function<void(int)> batch;
@@ -256,7 +256,7 @@ static int run_csym(Engine& E, const Operator<ZV>& A, ZV* m, const ZV* B, size_t
 		else
 		{
 			E.vec(OpCsUpdate<2>{{}, m, d, r, Ax, nullptr, z, zc()}, n);
-			A.precond(r, z, 0);
+			E.precondition(A, r, z);
 			E.vec(OpCsRho{{}, r, z}, n);
 		}
 		E.vec_push(OpCsDir{{}, mode == 0 ? r : z, d, zc()}, n, d);

@@ -240,7 +240,7 @@ static int run_pcg(Engine& E, const Operator<double>& A, double* m, const double
 	else
 	{
 		E.vec(OpPcgInit<false>{{}, m, Ad, B, nullptr, r, z, d}, n);
-		A.precond(r, z, 0);
+		E.precondition(A, r, z);
 		E.vec_push(OpPcgInitZ{{}, z, r, d}, n, d);
 	}
 	std::function<void(int)> batch;
@@ -252,7 +252,7 @@ static int run_pcg(Engine& E, const Operator<double>& A, double* m, const double
 		else
 		{
 			E.vec(OpPcgUpdate<false>{{}, m, d, r, Ad, nullptr, z, 0.0}, n);
-			A.precond(r, z, 0);
+			E.precondition(A, r, z);
 			E.vec(OpPcgZr{{}, z, r}, n);
 		}
 		E.vec_push(OpPcgDir{{}, d, z, 0.0}, n, d);

@@ -174,6 +174,55 @@ class Oracle:
         return SolveResult(ret, out[0], out[1], dout[0], dout[1], x, hist[:min(out[1], hist_cap)].copy())
 
 
+def _lower_coo(A):
+    """Row-sorted COO of the full matrix A = dict(n, row_ptr, col, val)."""
+    rows = np.repeat(np.arange(A["n"], dtype=np.int32), np.diff(A["row_ptr"])).astype(np.int32)
+    return rows, np.ascontiguousarray(A["col"], dtype=np.int32)
+
+
+def ref_ic0_half(A):
+    """lcg_incomplete_Cholesky_half_coo (reference preconditioner.cpp:33-160) on a real CSR system -> (row, col, val) of L (COO)."""
+    lib = C.CDLL(REF_SO)
+    lib.lcgref_ic0_half.restype = C.c_int
+    rows, cols = _lower_coo(A)
+    val = np.ascontiguousarray(A["val"], dtype=np.float64)
+    lnz = lib.lcgref_ic0_half(_p(rows, C.c_int), _p(cols, C.c_int), _p(val, C.c_double), C.c_int(A["n"]), C.c_int(len(cols)), None, None, None)
+    ir, ic, iv = np.empty(lnz, np.int32), np.empty(lnz, np.int32), np.empty(lnz, np.float64)
+    lib.lcgref_ic0_half(_p(rows, C.c_int), _p(cols, C.c_int), _p(val, C.c_double), C.c_int(A["n"]), C.c_int(len(cols)), _p(ir, C.c_int), _p(ic, C.c_int), _p(iv, C.c_double))
+    return ir, ic, iv
+
+
+def ref_cic0_half(A, single=False):
+    """clcg_incomplete_Cholesky_cuda_half (reference preconditioner_cuda.cu:40-270; host code) on a complex CSR system."""
+    lib = C.CDLL(REF_CUDA_SO)
+    lib.lcgrefcuda_cic0_half.restype = C.c_int
+    rows, cols = _lower_coo(A)
+    dt = np.complex64 if single else np.complex128
+    val = np.ascontiguousarray(A["val"], dtype=dt)
+    args = [C.c_int(1 if single else 0), _p(rows, C.c_int), _p(cols, C.c_int), val.ctypes.data_as(C.c_void_p), C.c_int(A["n"]), C.c_int(len(cols))]
+    lnz = lib.lcgrefcuda_cic0_half(*args, None, None, None)
+    ir, ic, iv = np.empty(lnz, np.int32), np.empty(lnz, np.int32), np.empty(lnz, dt)
+    lib.lcgrefcuda_cic0_half(*args, _p(ir, C.c_int), _p(ic, C.c_int), iv.ctypes.data_as(C.c_void_p))
+    return ir, ic, iv
+
+
+def ref_pcg_ic0(A, b, para=None, hist_cap=0):
+    """The reference's PCG (lcg_solver_preconditioned) with M = L L^T from its own IC(0) and its own COO triangular solves as the Mx
+    callback.  Returns (SolveResult, z_probe) with z_probe = M^-1 b."""
+    lib = C.CDLL(REF_SO)
+    lib.lcgref_pcg_ic0.restype = C.c_int
+    n = A["n"]
+    x = np.zeros(n)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    hist = np.zeros(max(hist_cap, 1))
+    out, dout = (C.c_int * 2)(), (C.c_double * 2)()
+    zp = np.empty(n)
+    para = para if para is not None else default_para()
+    ret = lib.lcgref_pcg_ic0(C.c_int(n), _p(A["row_ptr"], C.c_int), _p(A["col"], C.c_int), _p(A["val"], C.c_double), _p(x, C.c_double), _p(b, C.c_double),
+                             C.byref(para), _p(hist, C.c_double), C.c_int(hist_cap), out, dout, _p(zp, C.c_double))
+    return SolveResult(ret, out[0], out[1], dout[0], dout[1], x, hist[:min(out[1], hist_cap)].copy()), zp
+
+
 REF_CUDA_SO = os.path.join(HERE, "_ref", "liblcg_ref_cuda.so")
 
 

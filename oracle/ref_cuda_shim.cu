@@ -282,3 +282,19 @@ extern "C" int lcgrefcuda_csolvef(int solver, int n, int nnz, const int* d_rp, c
 	cublasDestroy(cub); cusparseDestroy(cus);
 	return ret;
 }
+
+// ------------------------------------------------------------------------------------------ complex IC(0), host functions
+// clcg_incomplete_Cholesky_cuda_half (preconditioner_cuda.cu:40-270): sequential host code despite its name; used to pin our
+// restatement of the complex factorisation bit for bit.  prec: 0 = cuDoubleComplex, 1 = cuComplex.  Returns the size of L.
+#include "preconditioner_cuda.h"
+extern "C" int lcgrefcuda_cic0_half(int prec, const int* row, const int* col, const void* val, int n, int nz, int* ic_row, int* ic_col, void* ic_val)
+{
+	int lnz = 0;
+	clcg_incomplete_Cholesky_cuda_half_buffsize(row, col, nz, &lnz);
+	if (ic_row && ic_col && ic_val)
+	{
+		if (prec == 0) clcg_incomplete_Cholesky_cuda_half(row, col, static_cast<const cuDoubleComplex*>(val), n, nz, lnz, ic_row, ic_col, static_cast<cuDoubleComplex*>(ic_val));
+		else clcg_incomplete_Cholesky_cuda_half(row, col, static_cast<const cuComplex*>(val), n, nz, lnz, ic_row, ic_col, static_cast<cuComplex*>(ic_val));
+	}
+	return lnz;
+}

@@ -206,3 +206,73 @@ extern "C" void lcgref_vecrnd(double* a, int n)
 
 extern "C" int lcgref_sizeof_para() { return (int)sizeof(lcg_para); }
 extern "C" int lcgref_sizeof_cpara() { return (int)sizeof(clcg_para); }
+
+// ---------------------------------------------------------------------------------------------
+// IC(0) preconditioning with the reference's own functions (preconditioner.cpp): the factorisation
+// lcg_incomplete_Cholesky_half_coo and PCG whose Mx callback is the pair of COO triangular solves
+// lcg_solve_lower_triangle_coo / lcg_solve_upper_triangle_coo (sample7.cpp does the complex twin of this by hand).
+#include "preconditioner.h"
+
+// COO (row-sorted, base 0) of the full matrix -> lower factor in COO; returns the number of entries of L
+extern "C" int lcgref_ic0_half(const int* row, const int* col, const double* val, int n, int nz, int* ic_row, int* ic_col, double* ic_val)
+{
+	int lnz = 0;
+	lcg_incomplete_Cholesky_half_buffsize_coo(row, col, nz, &lnz);
+	if (ic_row && ic_col && ic_val) lcg_incomplete_Cholesky_half_coo(row, col, val, n, nz, lnz, ic_row, ic_col, ic_val);
+	return lnz;
+}
+
+struct IcSys
+{
+	RealSys base;
+	int lnz;
+	std::vector<int> l_row, l_col, u_row, u_col;
+	std::vector<double> l_val, u_val, tmp;
+};
+
+static void ic_ax(void* inst, const lcg_float* x, lcg_float* y, const int n) { real_ax(&((IcSys*)inst)->base, x, y, n); }
+static void ic_mx(void* inst, const lcg_float* r, lcg_float* z, const int n)
+{	// z = L^-T L^-1 r
+	IcSys* s = (IcSys*)inst;
+	lcg_solve_lower_triangle_coo(s->l_row.data(), s->l_col.data(), s->l_val.data(), r, s->tmp.data(), n, s->lnz);
+	lcg_solve_upper_triangle_coo(s->u_row.data(), s->u_col.data(), s->u_val.data(), s->tmp.data(), z, n, s->lnz);
+}
+static int ic_pf(void* inst, const lcg_float* m, const lcg_float conv, const lcg_para* p, const int n, const int k)
+{
+	IcSys* s = (IcSys*)inst;
+	s->base.h.push(k, conv);
+	return 0;
+}
+
+// PCG with M = L L^T from the reference's IC(0).  z_probe (nullable, n values): receives M^-1 B (one application of the
+// preconditioner to the right-hand side), for checking the GPU triangular solves against the reference's.
+extern "C" int lcgref_pcg_ic0(int n, const int* rp, const int* ci, const double* val, double* m, const double* B, const void* para,
+	double* hist, int hist_cap, int* out, double* dout, double* z_probe)
+{
+	IcSys s;
+	s.base.n = n; s.base.rp = rp; s.base.ci = ci; s.base.v = val; s.base.diag = nullptr;
+	s.base.h.buf = hist; s.base.h.cap = hist_cap;
+	const int nz = rp[n];
+	std::vector<int> row((size_t)nz);
+	for (int i = 0; i < n; i++) for (int k = rp[i]; k < rp[i + 1]; k++) row[(size_t)k] = i;
+	s.lnz = lcgref_ic0_half(row.data(), ci, val, n, nz, nullptr, nullptr, nullptr);
+	s.l_row.resize((size_t)s.lnz); s.l_col.resize((size_t)s.lnz); s.l_val.resize((size_t)s.lnz); s.tmp.resize((size_t)n);
+	lcgref_ic0_half(row.data(), ci, val, n, nz, s.l_row.data(), s.l_col.data(), s.l_val.data());
+	// U = L^T, row-sorted
+	std::vector<int> cnt((size_t)n + 1, 0);
+	for (int k = 0; k < s.lnz; k++) cnt[(size_t)s.l_col[(size_t)k] + 1]++;
+	for (int i = 0; i < n; i++) cnt[(size_t)i + 1] += cnt[(size_t)i];
+	s.u_row.resize((size_t)s.lnz); s.u_col.resize((size_t)s.lnz); s.u_val.resize((size_t)s.lnz);
+	for (int k = 0; k < s.lnz; k++)
+	{
+		const int d = cnt[(size_t)s.l_col[(size_t)k]]++;
+		s.u_row[(size_t)d] = s.l_col[(size_t)k]; s.u_col[(size_t)d] = s.l_row[(size_t)k]; s.u_val[(size_t)d] = s.l_val[(size_t)k];
+	}
+	if (z_probe) ic_mx(&s, B, z_probe, n);
+	double t0 = omp_get_wtime();
+	int ret = lcg_solver_preconditioned(ic_ax, ic_mx, ic_pf, m, B, n, (const lcg_para*)para, &s, LCG_PCG);
+	double t1 = omp_get_wtime();
+	if (out) { out[0] = s.base.h.last_k; out[1] = s.base.h.calls; }
+	if (dout) { dout[0] = s.base.h.last_res; dout[1] = t1 - t0; }
+	return ret;
+}

@@ -20,6 +20,7 @@
 #include "clcg_cuda.h"
 #include "solver.h"
 #include "solver_cuda.h"
+#include "preconditioner.h"
 #include "lcgb200.h"
 
 struct Csr { int n = 0, nnz = 0; std::vector<int> rp, ci; std::vector<double> va, diag, b, ans; };
@@ -62,6 +63,16 @@ static void host_ax(void*, const lcg_float* x, lcg_float* y, const int n)
 }
 static void host_mx(void*, const lcg_float* r, lcg_float* z, const int n) { for (int i = 0; i < n; i++) z[i] = r[i] / g_A.diag[(size_t)i]; }
 static int host_pf(void*, const lcg_float*, const lcg_float, const lcg_para*, const int, const int k) { g_last_k = k; return 0; }
+
+// IC(0) preconditioner from the reference's preconditioner.h functions: factor once, two COO triangular solves per application
+static std::vector<int> g_lrow, g_lcol, g_urow, g_ucol;
+static std::vector<double> g_lval, g_uval, g_tmp;
+static int g_lnz = 0;
+static void host_ic_mx(void*, const lcg_float* r, lcg_float* z, const int n)
+{
+	lcg_solve_lower_triangle_coo(g_lrow.data(), g_lcol.data(), g_lval.data(), r, g_tmp.data(), n, g_lnz);
+	lcg_solve_upper_triangle_coo(g_urow.data(), g_ucol.data(), g_uval.data(), g_tmp.data(), z, n, g_lnz);
+}
 
 static void host_cax(void*, const lcg_complex* x, lcg_complex* y, const int n, lcg_matrix_e layout, clcg_complex_e conj)
 {	// op(A) x, honouring (layout, conjugate) as clcg.h:40-41 asks
@@ -159,6 +170,29 @@ int main(int argc, char** argv)
 		check(ret == LCG_CONVERGENCE && avg_err(m, g_A.ans) < 1e-3 && std::sqrt(dr) <= 1e-8 * std::sqrt(nb), "lcgs() stand-alone CGS with 7 caller-owned work vectors (lcg.h:166-169); RK holds the final residual");
 		for (auto& w : ws) lcg_free(w);
 		lcg_free(Gk); lcg_free(Dk); lcg_free(ADk); lcg_free(Am);
+	}
+	{	// preconditioner.h: IC(0) on the row-sorted COO of case_10K_A, applied through the COO triangular solves inside the reference's PCG
+		std::vector<int> row((size_t)nz);
+		for (int i = 0; i < n; i++) for (int k = g_A.rp[(size_t)i]; k < g_A.rp[(size_t)i + 1]; k++) row[(size_t)k] = i;
+		lcg_incomplete_Cholesky_half_buffsize_coo(row.data(), g_A.ci.data(), nz, &g_lnz);
+		g_lrow.resize((size_t)g_lnz); g_lcol.resize((size_t)g_lnz); g_lval.resize((size_t)g_lnz); g_tmp.resize((size_t)n);
+		lcg_incomplete_Cholesky_half_coo(row.data(), g_A.ci.data(), g_A.va.data(), n, nz, g_lnz, g_lrow.data(), g_lcol.data(), g_lval.data());
+		std::vector<int> cnt((size_t)n + 1, 0);
+		for (int k = 0; k < g_lnz; k++) cnt[(size_t)g_lcol[(size_t)k] + 1]++;
+		for (int i = 0; i < n; i++) cnt[(size_t)i + 1] += cnt[(size_t)i];
+		g_urow.resize((size_t)g_lnz); g_ucol.resize((size_t)g_lnz); g_uval.resize((size_t)g_lnz);
+		for (int k = 0; k < g_lnz; k++) { const int d = cnt[(size_t)g_lcol[(size_t)k]]++; g_urow[(size_t)d] = g_lcol[(size_t)k]; g_ucol[(size_t)d] = g_lrow[(size_t)k]; g_uval[(size_t)d] = g_lval[(size_t)k]; }
+		lcg_vecset(m, 0.0, n);
+		ret = lcg_solver_preconditioned(host_ax, host_ic_mx, host_pf, m, g_A.b.data(), n, &para, nullptr);
+		check(ret == LCG_CONVERGENCE && g_last_k == 30 && avg_err(m, g_A.ans) < 1e-4 && lcg_full_rank_coo(g_lrow.data(), g_lcol.data(), g_lval.data(), n, g_lnz),
+			"preconditioner.h: lcg_incomplete_Cholesky_half_coo + COO triangular solves as Mx: PCG converges in 30 iterations (Jacobi: 99)");
+		// the same preconditioner built into the operator: factor on the host at creation, two level-ordered triangular solves on the GPU
+		lcgb200_csr_t opi = nullptr;
+		lcgb200_csr_create(&opi, n, nz, g_A.rp.data(), g_A.ci.data(), g_A.va.data(), LCGB200_REAL, LCGB200_HOST, LCGB200_CSR_IC0);
+		lcg_vecset(m, 0.0, n);
+		ret = lcg_solver_preconditioned(lcgb200_csr_ax_host, lcgb200_ic0_mx_host, host_pf, m, g_A.b.data(), n, &para, opi);
+		check(ret == LCG_CONVERGENCE && g_last_k == 30 && avg_err(m, g_A.ans) < 1e-4, "built-in IC(0) (lcgb200_ic0_mx_host): same 30 iterations on the GPU");
+		lcgb200_csr_destroy(opi);
 	}
 	{
 		HostSolver hs; hs.set_lcg_parameter(para); hs.silent();

@@ -698,6 +698,95 @@ def test_data_step_coo_to_csr_on_device(torch_cuda, port, fixtures):
     op.close()
 
 
+# ------------------------------------------------------------------------------------------------ IC(0)
+def test_ic0_preconditioned_cg_matches_reference(torch_cuda, fixtures):
+    """IC(0)-preconditioned CG on data/case_10K_A (what samples 8, 10-14 demonstrate): the factor kept by the handle is the
+    reference's bit for bit; one application z = L^-T L^-1 b by the two level-ordered GPU triangular solves equals the
+    reference's COO triangular solves (preconditioner.cpp:286-366); and lcg_solver_preconditioned_cuda with lcgb200_ic0_mx
+    follows the reference's lcg_solver_preconditioned driven by its own IC(0) + triangular solves: same iterate after a pinned
+    number of iterations, same iteration count at convergence, far fewer iterations than Jacobi."""
+    torch = torch_cuda
+    if not po.have_reference():
+        pytest.skip("oracle/_ref not present")
+    A = fixtures["10K"]
+    n, nnz = A["n"], A["nnz"]
+    op = api.CsrOperator(A["row_ptr"], A["col"], A["val"], ic0=True, jacobi=True)
+    f = op.ic0_factor()
+    ir, ic, iv = po.ref_ic0_half(A)
+    assert np.array_equal(f["col"], ic) and np.array_equal(f["val"].view(np.int64), iv.view(np.int64))
+    assert f["levels_lower"] >= 2 and f["levels_upper"] >= 2
+    ref, zp = po.ref_pcg_ic0(A, A["b"], para=po.default_para(epsilon=1e-10))
+    z = torch.empty(n, dtype=torch.float64, device="cuda")
+    for _ in range(3):                                        # repeated applications: the epoch flags are never cleared
+        op.ic0_apply(to_dev(torch, A["b"]), z)
+    torch.cuda.synchronize()
+    assert rel(z.cpu().numpy(), zp) <= 1e-12
+    # pinned iterations
+    for k in (1, 10, 30):
+        refk, _ = po.ref_pcg_ic0(A, A["b"], para=po.default_para(epsilon=1e-300, max_iterations=k))
+        m = np.zeros(n)
+        ret = api.lcg_solver_preconditioned_cuda(api.CSR_AX, api.IC0_MX, None, m, A["b"], n, nnz, api.lcg_default_parameters(epsilon=1e-300, max_iterations=k), op)
+        assert ret == refk.ret == api.LCG_REACHED_MAX_ITERATIONS and refk.iters == k
+        assert rel(m, refk.x) <= X_TOL, (k, rel(m, refk.x))
+    # convergence: same count as the reference's, the known answer, and fewer iterations than Jacobi
+    ks = []
+    m = np.zeros(n)
+    ret = api.lcg_solver_preconditioned_cuda(api.CSR_AX, api.IC0_MX, lambda i, md, c, p, nn, z_, k: ks.append(k) or 0, m, A["b"], n, nnz,
+                                             api.lcg_default_parameters(epsilon=1e-10), op)
+    assert ret == ref.ret == 0 and iters_close(ks[-1], ref.iters), (ks[-1], ref.iters)
+    assert rel(m, A["answer"]) < 1e-4
+    r_jac = api.solve(op, api.LCG_PCG, np.zeros(n), A["b"], param=api.lcg_default_parameters(epsilon=1e-10), jacobi=True)
+    r_ic = api.solve(op, api.LCG_PCG, np.zeros(n), A["b"], param=api.lcg_default_parameters(epsilon=1e-10), ic0=True)
+    assert r_ic.ret == 0 and r_ic.iterations == ks[-1] and r_ic.iterations < 0.7 * r_jac.iterations
+    op.close()
+    # a handle without the factor refuses the sentinel like the reference refuses a null Mfp
+    op2 = api.CsrOperator(A["row_ptr"], A["col"], A["val"])
+    assert api.lcg_solver_preconditioned_cuda(api.CSR_AX, api.IC0_MX, None, m, A["b"], n, nnz, api.lcg_default_parameters(), op2) == api.LCG_NULL_PRECONDITION_MATRIX
+    op2.close()
+
+
+@pytest.mark.parametrize("kind,g", [("7pt", 24), ("27pt", 16)])
+def test_ic0_on_stencils_and_complex(torch_cuda, fixtures, kind, g):
+    """Deep dependency chains (a g^3 stencil has O(g) levels) through the synchronisation-free triangular solves against scipy's
+    sparse triangular solver on the same factor; IC(0)-PCG converges to x* in fewer iterations than Jacobi-PCG; and the complex
+    factor (L L^T, unconjugated) applied on data/case_10K_cA in double and single precision."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    torch = torch_cuda
+    S = stencil.make_system(kind, g)
+    n = S["n"]
+    op = api.CsrOperator(S["row_ptr"], S["col"], S["val"], ic0=True, jacobi=True)
+    f = op.ic0_factor()
+    L = sp.csr_matrix((f["val"], f["col"], f["row_ptr"]), shape=(n, n))
+    assert f["levels_lower"] >= g and f["levels_upper"] >= g
+    r = np.random.default_rng(9).standard_normal(n)
+    z = torch.empty(n, dtype=torch.float64, device="cuda")
+    op.ic0_apply(to_dev(torch, r), z)
+    torch.cuda.synchronize()
+    z_ref = spla.spsolve_triangular(L.T.tocsr(), spla.spsolve_triangular(L, r, lower=True), lower=False)
+    assert rel(z.cpu().numpy(), z_ref) <= 1e-12
+    para = api.lcg_default_parameters(epsilon=1e-12)
+    m_ic, m_j = np.zeros(n), np.zeros(n)
+    r_ic = api.solve(op, api.LCG_PCG, m_ic, S["b"], param=para, ic0=True)
+    r_j = api.solve(op, api.LCG_PCG, m_j, S["b"], param=para, jacobi=True)
+    assert r_ic.ret == r_j.ret == 0 and r_ic.iterations < r_j.iterations
+    assert rel(m_ic, S["x_star"]) < 1e-4
+    op.close()
+    if kind == "7pt":
+        Ac = fixtures["10Kc"]
+        for dt, tol in ((np.complex128, 1e-11), (np.complex64, 2e-4)):
+            opc = api.CsrOperator(Ac["row_ptr"], Ac["col"], Ac["val"].astype(dt), ic0=True)
+            fc = opc.ic0_factor()
+            Lc = sp.csr_matrix((fc["val"].astype(np.complex128), fc["col"], fc["row_ptr"]), shape=(Ac["n"], Ac["n"]))
+            rc_ = (np.random.default_rng(3).standard_normal(Ac["n"]) + 1j * np.random.default_rng(4).standard_normal(Ac["n"])).astype(dt)
+            zc = torch.empty(Ac["n"], dtype=torch.complex64 if dt == np.complex64 else torch.complex128, device="cuda")
+            opc.ic0_apply(to_dev(torch, rc_), zc)
+            torch.cuda.synchronize()
+            zc_ref = spla.spsolve_triangular(Lc.T.tocsr(), spla.spsolve_triangular(Lc, rc_.astype(np.complex128), lower=True), lower=False)
+            assert rel(zc.cpu().numpy().astype(np.complex128), zc_ref) <= tol
+            opc.close()
+
+
 # ------------------------------------------------------------------------------------------------ full sizes
 def _device_system(torch, kind_id, g, jacobi):
     from liblcg_b200 import _lib

@@ -181,3 +181,38 @@ def test_complex_port_equals_reference_bitwise(port, reflib, fixtures, sid):
     a, b = port.csolve(sid, Ac, Ac["b"], **kw), reflib.csolve(sid, Ac, Ac["b"], **kw)
     assert (a.ret, a.iters, a.calls) == (b.ret, b.iters, b.calls)
     assert np.array_equal(a.x, b.x) and np.array_equal(a.history, b.history)
+
+
+# ------------------------------------------------------------------------------------------------ IC(0)
+def _lower_csr(A):
+    rows = np.repeat(np.arange(A["n"]), np.diff(A["row_ptr"]))
+    keep = A["col"] <= rows
+    rp = np.zeros(A["n"] + 1, dtype=np.int32)
+    np.cumsum(np.bincount(rows[keep], minlength=A["n"]), out=rp[1:])
+    return rp, A["col"][keep].astype(np.int32), A["val"][keep]
+
+
+def test_ic0_factor_is_bit_identical_to_the_reference():
+    """lcgb200_ic0_factor_host (liblcg_b200/csrc/ic0_host.h; host code, no GPU) against the reference's own factorisations compiled
+    into oracle/_ref: lcg_incomplete_Cholesky_half_coo (preconditioner.cpp:33-160) on data/case_10K_A and
+    clcg_incomplete_Cholesky_cuda_half (preconditioner_cuda.cu:40-270) in double and single complex on data/case_10K_cA — the same
+    entries, bit for bit (the restatement performs the reference's operations in the reference's order)."""
+    from liblcg_b200 import api, io as lio
+    if not po.have_reference():
+        pytest.skip("oracle/_ref not present")
+    A = lio.load_fixture("10K")
+    rp, ci, v = _lower_csr(A)
+    ours = api.ic0_factor_host(rp, ci, v)
+    ir, ic, iv = po.ref_ic0_half(A)
+    assert np.array_equal(ic, ci) and np.array_equal(ir, np.repeat(np.arange(A["n"]), np.diff(rp)))
+    assert np.array_equal(ours.view(np.int64), iv.view(np.int64))
+    assert np.all(np.isfinite(ours))
+    if po.have_reference_cuda():
+        Ac = lio.load_fixture("10Kc")
+        rpc, cic, vc = _lower_csr(Ac)
+        for single in (False, True):
+            dt = np.complex64 if single else np.complex128
+            ours_c = api.ic0_factor_host(rpc, cic, vc.astype(dt))
+            _, icc, ivc = po.ref_cic0_half(Ac, single=single)
+            assert np.array_equal(icc, cic)
+            assert ours_c.tobytes() == ivc.tobytes()
