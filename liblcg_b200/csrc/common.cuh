@@ -146,6 +146,8 @@ struct DevState {
 	unsigned int pad;
 	CommDev* comm;            // multi == 2: NVLink peer-memory transport
 	unsigned long long spin_timeout_ns;   // cross-GPU waits give up after this long (0 = never)
+	int gate;                 // k_vec2: bumped by the block that finished the first step's reduction, releases the second step
+	int pad2;
 };
 
 // multi-GPU: the cross-rank sum of a fused reduction, called by the whole first warp of the last block (grid_reduce).
@@ -532,6 +534,74 @@ __global__ void __launch_bounds__(kThreads) k_vec(Op op_in, size_t n, DevState* 
 			if (st->multi) { if (reduce_across_ranks(st, tot, Op::NRED)) op.finish(st, tot); }
 			else if ((threadIdx.x & 31) == 0) op.finish(st, tot);
 		}
+	}
+}
+
+// ---- two dependent vector steps in one kernel ---------------------------------------------------------------------
+// Every iteration ends with the pair "update (m, r, [z], reductions -> beta, loop head)" -> "direction (d = z + beta d)".  The
+// second step needs ONE scalar of the first one's reduction, nothing else crosses threads: both steps walk the vectors
+// with the same index mapping, so a thread re-reads in step 2 only what it wrote itself in step 1 (L2 hits at the sizes
+// where this matters).  One cooperative launch (all blocks co-resident) runs both: step 1, single-pass grid reduction, the
+// last block finishes the reduction (across GPUs too), runs the scalar epilogue and opens the gate the other blocks spin
+// on; then step 2 (and the halo push).  Saves a kernel boundary per iteration — launch, ramp-up, tail — which is a fifth of
+// the iteration on a 2 M-row system or an 8-GPU slab.
+__device__ __forceinline__ int ld_acquire_gpu_s32(const int* p)
+{
+	int v;
+	asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_release_gpu_s32(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+
+template <class Op1, class Op2, bool PUSH, class T>
+__global__ void __launch_bounds__(kThreads) k_vec2(Op1 op1_in, Op2 op2_in, size_t n, DevState* st, double* partials, CommDev* comm, const T* push_src)
+{
+	static_assert(Op1::W == Op2::W && Op1::NRED > 0, "same index mapping in both steps; the first one ends in a reduction");
+	pdl_enter();
+	if (st_done(st)) return;
+	__shared__ int s_gate;
+	if (threadIdx.x == 0) s_gate = ld_acquire_gpu_s32(&st->gate);
+	constexpr int W = Op1::W;
+	const size_t npack = n / W;
+	const size_t stride = (size_t)gridDim.x * kThreads;
+	const size_t first = (size_t)blockIdx.x * kThreads + threadIdx.x;
+	{
+		Op1 op = op1_in;
+		op.begin(st);
+		double acc[Op1::NRED];
+#pragma unroll
+		for (int r = 0; r < Op1::NRED; r++) acc[r] = 0.0;
+		for (size_t p = first; p < npack; p += stride) op.template elem<W>(p * W, acc);
+		if (W > 1) { const size_t tail = npack * W + first; if (tail < n) op.template elem<1>(tail, acc); }
+		double tot[Op1::NRED];
+		if (grid_reduce<Op1::NRED>(acc, partials, &st->ticket, tot))
+		{	// first warp of the block that finished last
+			if (st->multi) { if (reduce_across_ranks(st, tot, Op1::NRED)) op.finish(st, tot); }
+			else if ((threadIdx.x & 31) == 0) op.finish(st, tot);
+			__syncwarp();
+			if ((threadIdx.x & 31) == 0) { __threadfence(); st_release_gpu_s32(&st->gate, s_gate + 1); }
+		}
+	}
+	if (threadIdx.x == 0) { const int g0 = s_gate; while (ld_acquire_gpu_s32(&st->gate) == g0) __nanosleep(20); }
+	__syncthreads();
+	if (st_done(st)) return;   // the loop head of step 1 ended the solve: the direction step is skipped, as a separate launch would be
+	{
+		Op2 op = op2_in;
+		op.begin(st);
+		double none[1];
+		unsigned long long hseq = 0; bool pushed = false;
+		if (PUSH) hseq = comm->halo_seq + 1;
+		for (size_t p = first; p < npack; p += stride)
+		{
+			op.template elem<W>(p * W, none);
+			if (PUSH) pushed |= push_elems<T, W>(comm, push_src, p * W, hseq);
+		}
+		if (W > 1)
+		{
+			const size_t tail = npack * W + first;
+			if (tail < n) { op.template elem<1>(tail, none); if (PUSH) pushed |= push_elems<T, 1>(comm, push_src, tail, hseq); }
+		}
+		if (PUSH) push_signal(comm, hseq, pushed);
 	}
 }
 

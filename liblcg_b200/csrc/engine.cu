@@ -4,6 +4,8 @@
 #include <string>
 #include <mutex>
 #include <cstdlib>
+#include <vector>
+#include <utility>
 
 namespace lcgb200 {
 
@@ -91,6 +93,28 @@ int coop_grid_limit(const void* kernel, int block)
 	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
 	if (per_sm > 2) per_sm = 2;   // grid barriers get slower with more blocks; two per SM are plenty for an L2-resident system
 	return sms * per_sm;
+}
+
+int coop_grid_full(const void* kernel, int block)
+{
+	struct Key { const void* k; int dev; };
+	static thread_local std::vector<std::pair<Key, int>> cache;
+	int dev = 0, sms = 148, per_sm = 1;
+	cudaGetDevice(&dev);
+	for (const auto& e : cache) if (e.first.k == kernel && e.first.dev == dev) return e.second;
+	if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+	cache.push_back({Key{kernel, dev}, sms * per_sm});
+	return sms * per_sm;
+}
+
+bool fuse_vec2(size_t n_local)
+{
+	int mode = settings().fuse_vec2;
+	if (mode < 0) { static const int env = [] { const char* e = getenv("LCGB200_FUSE_VEC2"); return e ? atoi(e) : -1; }(); mode = env; }
+	if (mode == 0) return false;
+	if (mode > 0) return true;
+	return n_local <= ((size_t)8 << 20);
 }
 
 cudaEvent_t Engine::prof_begin(int cls)

@@ -120,8 +120,11 @@ struct Settings {
 	long long spin_timeout_ms = -1; // cross-GPU waits (NVLink transport); -1 = LCGB200_SPIN_TIMEOUT_MS or 30 s; 0 = wait for ever
 	int graphs = -1;               // CUDA graph per batch of iterations; -1 = LCGB200_GRAPHS or automatic
 	int pdl = -1;                  // programmatic dependent launch between the kernels of an iteration; -1 = LCGB200_PDL or on
+	int fuse_vec2 = -1;            // update + direction in one cooperative kernel; -1 = LCGB200_FUSE_VEC2 or automatic (by size)
 };
 long long spin_timeout_ms();
+bool fuse_vec2(size_t n_local);
+int coop_grid_full(const void* kernel, int block);   // all co-resident blocks of a kernel on the current device (engine.cu)
 Settings& settings();
 
 class Engine {
@@ -195,6 +198,28 @@ public:
 		launches++;
 		pushed_vec = out;
 		if (Op::NRED > 0 && multi()) finish_multi(op, Op::NRED);
+	}
+
+	// update + direction in one cooperative launch (k_vec2) where that is possible: our own reductions (single GPU or the
+	// NVLink transport: the NCCL transport needs a collective between the two steps), a grid that is wholly co-resident, and
+	// systems small enough for a kernel boundary to matter (the regime of the CUDA graphs); otherwise two launches.
+	template <class T, class Op1, class Op2> void vec2_push(const Op1& a, const Op2& b, size_t n, const T* out)
+	{
+		if (!fuse_vec2(n) || (multi() && !p2p())) { vec(a, n); vec_push(b, n, out); return; }
+		const bool push = halo_in_spmv() && comm->fused_push_ok();
+		CommDev* cd = push ? cache->p2p_dev() : nullptr;
+		DevState* st = d_st; double* parts = d_partials; size_t nn = n;
+		Op1 a1 = a; Op2 b1 = b;
+		void* args[] = {&a1, &b1, &nn, &st, &parts, &cd, (void*)&out};
+		const void* kern = push ? (const void*)k_vec2<Op1, Op2, true, T> : (const void*)k_vec2<Op1, Op2, false, T>;
+		int grid = vec_grid(n, Op1::W);
+		const int limit = coop_grid_full(kern, kThreads);
+		if (grid > limit) grid = limit;
+		cudaEvent_t pe = profiling ? prof_begin(1) : nullptr;
+		LCG_CUDA_CHECK(cudaLaunchCooperativeKernel(kern, dim3((unsigned)grid), dim3(kThreads), args, 0, stream));
+		prof_end(pe);
+		launches++;
+		if (push) pushed_vec = out;
 	}
 
 	template <class Op> void finish_multi(const Op& op, int nred)

@@ -144,8 +144,7 @@ static int run_cbicg(Engine& E, const Operator<ZV>& A, ZV* m, const ZV* B, size_
 		E.spmv(A, d1, Ax, EpiInnerAlpha{d2});
 		E.vec(OpCbUpdate1{{}, m, d1, r1, Ax, zc()}, n);
 		E.spmv(A, d2, Ax, EpiNone<ZV>{}, 2);	// A^H d2 (MatTranspose, Conjugate — clcg.cpp:188)
-		E.vec(OpCbUpdate2{{}, r2, Ax, r1, zc()}, n);
-		E.vec_push(OpCbDir{{}, r1, r2, d1, d2, zc()}, n, d1);
+		E.vec2_push(OpCbUpdate2{{}, r2, Ax, r1, zc()}, OpCbDir{{}, r1, r2, d1, d2, zc()}, n, d1);
 		return false;
 	}, batch);
 }
@@ -251,15 +250,14 @@ static int run_csym(Engine& E, const Operator<ZV>& A, ZV* m, const ZV* B, size_t
 		batch = [&](int k) { E.fused(k, 1, E.ph_spmv(A, d, Ax, EpiDotuAlpha{}), E.ph_vec(OpCsUpdate<1>{{}, m, d, r, Ax, A.diag, z, zc()}, n), E.ph_vec(OpCsDir{{}, z, d, zc()}, n)); };
 	return E.run([&]() {
 		E.spmv(A, d, Ax, EpiDotuAlpha{});
-		if (mode == 0) E.vec(OpCsUpdate<0>{{}, m, d, r, Ax, nullptr, z, zc()}, n);
-		else if (mode == 1) E.vec(OpCsUpdate<1>{{}, m, d, r, Ax, A.diag, z, zc()}, n);
+		if (mode == 0) E.vec2_push(OpCsUpdate<0>{{}, m, d, r, Ax, nullptr, z, zc()}, OpCsDir{{}, r, d, zc()}, n, d);
+		else if (mode == 1) E.vec2_push(OpCsUpdate<1>{{}, m, d, r, Ax, A.diag, z, zc()}, OpCsDir{{}, z, d, zc()}, n, d);
 		else
 		{
 			E.vec(OpCsUpdate<2>{{}, m, d, r, Ax, nullptr, z, zc()}, n);
 			E.precondition(A, r, z);
-			E.vec(OpCsRho{{}, r, z}, n);
+			E.vec2_push(OpCsRho{{}, r, z}, OpCsDir{{}, z, d, zc()}, n, d);
 		}
-		E.vec_push(OpCsDir{{}, mode == 0 ? r : z, d, zc()}, n, d);
 		return false;
 	}, batch);
 }
@@ -414,8 +412,7 @@ static int run_ccgs(Engine& E, const Operator<ZV>& A, ZV* m, const ZV* B, size_t
 		E.spmv(A, p, Ax, EpiInnerAlpha{rb});
 		E.vec_push(OpCQW{{}, u, Ax, q, w, zc()}, n, w);
 		E.spmv(A, w, Ax, EpiNone<ZV>{});
-		E.vec(OpCCgsUpdate{{}, m, w, r, Ax, rb, zc()}, n);
-		E.vec_push(OpCCgsDir{{}, r, q, u, p, zc()}, n, p);
+		E.vec2_push(OpCCgsUpdate{{}, m, w, r, Ax, rb, zc()}, OpCCgsDir{{}, r, q, u, p, zc()}, n, p);
 		return false;
 	}, batch);
 }
@@ -475,8 +472,7 @@ static int run_cbicgstab(Engine& E, const Operator<ZV>& A, ZV* m, const ZV* B, s
 		E.spmv(A, p, Ap, EpiInnerAlpha{rb});
 		E.vec_push(OpCBsS{{}, r, Ap, s, zc()}, n, s);
 		E.spmv(A, s, As, EpiCOmega{});
-		E.vec(OpCBsUpdate{{}, m, p, s, As, r, rb, zc(), zc()}, n);
-		E.vec_push(OpCBsDir{{}, r, p, Ap, zc(), zc()}, n, p);
+		E.vec2_push(OpCBsUpdate{{}, m, p, s, As, r, rb, zc(), zc()}, OpCBsDir{{}, r, p, Ap, zc(), zc()}, n, p);
 		return false;
 	}, batch);
 }

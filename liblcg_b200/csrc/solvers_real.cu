@@ -115,8 +115,7 @@ static int run_cg(Engine& E, const Operator<double>& A, double* m, const double*
 	if (E.small_system(A)) batch = [&](int k) { E.fused(k, 1, E.ph_spmv(A, d, Ad, EpiDotAlpha{nullptr}), E.ph_vec(OpCgUpdate{{}, m, d, g, Ad, 0.0}, n), E.ph_vec(OpCgDir{{}, d, g, 0.0}, n)); };
 	return E.run([&]() {
 		E.spmv(A, d, Ad, EpiDotAlpha{nullptr});
-		E.vec(OpCgUpdate{{}, m, d, g, Ad, 0.0}, n);
-		E.vec_push(OpCgDir{{}, d, g, 0.0}, n, d);
+		E.vec2_push(OpCgUpdate{{}, m, d, g, Ad, 0.0}, OpCgDir{{}, d, g, 0.0}, n, d);
 		return false;
 	}, batch);
 }
@@ -248,14 +247,13 @@ static int run_pcg(Engine& E, const Operator<double>& A, double* m, const double
 		batch = [&](int k) { E.fused(k, 1, E.ph_spmv(A, d, Ad, EpiDotAlpha{nullptr}), E.ph_vec(OpPcgUpdate<true>{{}, m, d, r, Ad, A.diag, z, 0.0}, n), E.ph_vec(OpPcgDir{{}, d, z, 0.0}, n)); };
 	return E.run([&]() {
 		E.spmv(A, d, Ad, EpiDotAlpha{nullptr});
-		if (jac) E.vec(OpPcgUpdate<true>{{}, m, d, r, Ad, A.diag, z, 0.0}, n);
+		if (jac) E.vec2_push(OpPcgUpdate<true>{{}, m, d, r, Ad, A.diag, z, 0.0}, OpPcgDir{{}, d, z, 0.0}, n, d);
 		else
 		{
 			E.vec(OpPcgUpdate<false>{{}, m, d, r, Ad, nullptr, z, 0.0}, n);
 			E.precondition(A, r, z);
-			E.vec(OpPcgZr{{}, z, r}, n);
+			E.vec2_push(OpPcgZr{{}, z, r}, OpPcgDir{{}, d, z, 0.0}, n, d);
 		}
-		E.vec_push(OpPcgDir{{}, d, z, 0.0}, n, d);
 		return false;
 	}, batch);
 }
@@ -355,8 +353,7 @@ static int run_cgs(Engine& E, const Operator<double>& A, double* m, const double
 		E.spmv(A, p, Ax, EpiDotAlpha{r0});
 		E.vec_push(OpCgsQW{{}, u, Ax, q, w, 0.0}, n, w);
 		E.spmv(A, w, Ax, EpiNone<double>{});
-		E.vec(OpCgsUpdate{{}, m, w, r, Ax, r0, 0.0}, n);
-		E.vec_push(OpCgsDir{{}, r, q, u, p, 0.0}, n, p);
+		E.vec2_push(OpCgsUpdate{{}, m, w, r, Ax, r0, 0.0}, OpCgsDir{{}, r, q, u, p, 0.0}, n, p);
 		return false;
 	}, batch);
 }
@@ -478,8 +475,7 @@ static int run_bicgstab(Engine& E, const Operator<double>& A, double* m, const d
 		}
 		else E.vec_push(OpBicgS<false>{{}, r, Ap, s, 0.0}, n, s);
 		E.spmv(A, s, Ax, EpiOmega{});
-		E.vec(OpBicgUpdate<RESTART>{{}, m, p, s, Ax, r, r0, 0.0, 0.0}, n);
-		E.vec_push(OpBicgDir<RESTART>{{}, r, p, Ap, r0, 0.0, 0.0, 0}, n, p);
+		E.vec2_push(OpBicgUpdate<RESTART>{{}, m, p, s, Ax, r, r0, 0.0, 0.0}, OpBicgDir<RESTART>{{}, r, p, Ap, r0, 0.0, 0.0, 0}, n, p);
 		return false;
 	}, batch);
 }
