@@ -280,7 +280,10 @@ int Engine::run(const std::function<bool()>& iterate, const std::function<void(i
 	// No callback: enqueue `poll` iterations per batch, read the state back asynchronously, and look at the
 	// PREVIOUS batch's flag while the current one runs.  Kernels launched after `done` return immediately.
 	// fused launches cost ~one launch per batch: poll less often (an iteration of a cache-resident system takes microseconds)
-	const int poll = (settings().poll > 0 ? settings().poll : 1) * (batch ? 8 : 1);
+	// (graph-sized systems: an iteration lasts tens of microseconds, so four times as many per batch — the gap between two graph
+	// launches is then a percent of the batch, and iterations enqueued past convergence are no-ops)
+	const bool want_graph_pre = !batch && capturable && !profiling && (!multi() || p2p()) && stream != nullptr && stream != cudaStreamLegacy && use_graphs(n_local);
+	const int poll = (settings().poll > 0 ? settings().poll : 1) * (batch ? 8 : (want_graph_pre ? 4 : 1));
 	DevState* slot[2] = {h_st, h_st2};
 	bool pending[2] = {false, false};
 	int b = 0;
@@ -295,7 +298,7 @@ int Engine::run(const std::function<bool()>& iterate, const std::function<void(i
 	// per-GPU slabs of a partitioned solve).  The first batch runs uncaptured so that one-time launch set-up is done.
 	GraphGuard gg;
 	// (the legacy default stream cannot be captured: the API layer moves built-in-operator solves to a stream of the handle)
-	const bool want_graph = !batch && capturable && !profiling && (!multi() || p2p()) && stream != nullptr && stream != cudaStreamLegacy && use_graphs(n_local);
+	const bool want_graph = want_graph_pre;
 	int batches = 0, per_batch_launches = 0, per_batch_spmv = 0;
 	while (true)
 	{
