@@ -53,6 +53,7 @@ WORKLOADS = {
     "case10k_pcg": ("fixture:10K", 0, "PCG"),
     # small variants for quick checks (not bench lines)
     "pcg27_64": ("27pt", 64, "PCG"),
+    "pcg27_128": ("27pt", 128, "PCG"),   # the per-GPU share of pcg27_256 on 8 GPUs (2.1 M rows), without the exchanges
     "bicgstab7cd_96": ("7pt_cd", 96, "BICGSTAB"),
 }
 KIND_ID = {"7pt": 0, "27pt": 1, "7pt_cd": 2}
@@ -312,6 +313,18 @@ def parity_block(ctx, kind, solver, g=48, k=25):
         ctx.dist.all_gather_object(gathered, (S["r0"], x_loc))
         parts = gathered
     err = api.last_error() if r.ret != api.LCG_REACHED_MAX_ITERATIONS else ""
+    # one GPU: the same solve once more in reference-order mode (lcgb200_set_reference_order: no FMA contraction, serial row
+    # sums and dot products) — iterate and final residual must equal the CPU port's bit for bit
+    x_exact = r_exact = None
+    if ctx.world == 1:
+        m_d.zero_()
+        api.set_reference_order(True)
+        try:
+            r_exact = api.solve(S["op"], sid, m_d, S["b"], param=para, device=True, jacobi=(solver == "PCG"), stream=ctx.stream)
+        finally:
+            api.set_reference_order(False)
+        torch.cuda.synchronize()
+        x_exact = m_d.cpu().numpy()
     close_system(ctx, S)
     if ctx.rank != 0:
         return None
@@ -321,7 +334,12 @@ def parity_block(ctx, kind, solver, g=48, k=25):
     diag = np.full(H["n"], 26.0 if kind == "27pt" else 6.0) if solver == "PCG" else None
     cpu = po.Oracle("port").solve(sid, H, H["b"], para=po.default_para(epsilon=1e-300, max_iterations=k), diag=diag)
     rel = float(np.linalg.norm(x - cpu.x) / max(np.linalg.norm(cpu.x), 1e-300))
-    return {"system": f"{kind} {g}^3", "solver": solver, "pinned_iterations": k, "n_gpus": ctx.world, "rel_l2": rel,
+    exact = None
+    if x_exact is not None:
+        exact = {"bit_identical_solution": bool(x_exact.tobytes() == cpu.x.tobytes()), "bit_identical_residual": bool(r_exact.residual == cpu.residual),
+                 "ret": r_exact.ret, "iterations": r_exact.iterations,
+                 "note": "lcgb200_set_reference_order(1): second build of the loops without FMA contraction and with serial sums"}
+    return {"system": f"{kind} {g}^3", "solver": solver, "pinned_iterations": k, "n_gpus": ctx.world, "rel_l2": rel, "reference_order": exact,
             "ret_gpu": r.ret, "ret_cpu": cpu.ret, "iterations_gpu": r.iterations, "iterations_cpu": cpu.iters,
             "residual_gpu": r.residual, "residual_cpu": cpu.residual, "ok": bool(rel <= 1e-8 and r.ret == cpu.ret and r.iterations == cpu.iters),
             "checker": "oracle/lcg_oracle.c (CPU port, pinned bit-for-bit to the reference)", "error": err}

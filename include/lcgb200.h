@@ -343,6 +343,14 @@ void lcgb200_set_graphs(int mode);
 /* programmatic dependent launch between the kernels of an iteration (the next kernel is scheduled while the current one
  * finishes its reduction and parks in griddepcontrol.wait): -1 (default) = environment LCGB200_PDL or on, 0 = off, 1 = on */
 void lcgb200_set_pdl(int mode);
+/* Reference-order arithmetic (verification mode; single GPU, double precision): 1 = every later solve runs the second
+ * build of the iteration loops, which reproduces the reference's x86-64 CPU arithmetic operation for operation — no fused
+ * multiply-adds, SpMV row sums and dot products added left to right in index order (algebra.cpp:154-163,
+ * lcg_complex.cpp:143-167) — so that iterates, residual histories and iteration counts are BIT-IDENTICAL to
+ * lcg_solver / clcg_solver driven by a plain CSR callback.  O(n) dependent additions per dot product: meant for the
+ * reference's sample systems (10^3-10^4 rows), where it turns "statistically indistinguishable" convergence counts of the
+ * erratic recurrences (BiCG, BiCGSTAB, CGS) into equalities.  -1 (default) = environment LCGB200_REFERENCE_ORDER or off. */
+void lcgb200_set_reference_order(int mode);
 /* 1: bracket every kernel launch of a solve with CUDA events (per-kernel durations in lcgb200_info); costs a
  * little throughput, so bench.py uses it only for its roofline pass */
 void lcgb200_set_profile(int on);

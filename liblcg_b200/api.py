@@ -88,6 +88,11 @@ def set_fused_small(on: bool) -> None:
     _lib.load().lcgb200_set_fused_small(1 if on else 0)
 
 
+def set_reference_order(on: bool) -> None:
+    """Reference-order arithmetic (lcgb200_set_reference_order): later solves are bit-identical to the reference's CPU solvers."""
+    _lib.load().lcgb200_set_reference_order(1 if on else 0)
+
+
 def set_profile(on: bool) -> None:
     _lib.load().lcgb200_set_profile(1 if on else 0)
 

@@ -605,7 +605,11 @@ int do_solve_real(CsrHandle* h, Operator<double>& A, int solver_id, double* m, c
 	const bool box_inplace = dev_vecs && constrained && ((reinterpret_cast<uintptr_t>(lo) & 15) == 0) && ((reinterpret_cast<uintptr_t>(hi) & 15) == 0);
 	const size_t vec_bytes = (((size_t)n_ext * sizeof(double)) + 255) & ~size_t(255);
 	int nvec = real_vector_count(solver_id) + (m_inplace ? 0 : 1) + (b_inplace ? 0 : 1) + ((constrained && !box_inplace) ? 2 : 0);
+	const bool exact = reference_order();
+	if (exact && E.multi()) { set_error_msg("reference-order mode runs on one GPU (a serial sum has no partition)"); throw ApiFailure{LCGB200_UNKNOWN_ERROR}; }
+	if (exact) nvec += kMaxRed;   // one term per element and reduction slot
 	E.reserve(vec_bytes * (size_t)nvec);
+	if (exact) { E.terms_stride = vec_bytes / sizeof(double); E.d_terms = E.alloc<double>(E.terms_stride * kMaxRed); E.allocs.clear(); }
 	double* d_m = m; const double* d_B = B; const double* d_lo = lo; const double* d_hi = hi;
 	const cudaMemcpyKind in_kind = dev_vecs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
 	if (!m_inplace)
@@ -639,7 +643,8 @@ int do_solve_real(CsrHandle* h, Operator<double>& A, int solver_id, double* m, c
 	if (E.comm && E.comm->poisoned()) { set_error_msg("this communicator timed out in an earlier solve: its sequence counters may disagree with the peers'; create a new one"); throw ApiFailure{LCGB200_UNKNOWN_ERROR}; }
 	E.start(init);
 	const size_t first_work = E.allocs.size();
-	int ret = solve_real(E, A, solver_id, d_m, d_B, d_lo, d_hi, para, (size_t)n, (size_t)n_ext);
+	int ret = exact ? solve_real_x(E, A, solver_id, d_m, d_B, d_lo, d_hi, para, (size_t)n, (size_t)n_ext)
+	                : solve_real(E, A, solver_id, d_m, d_B, d_lo, d_hi, para, (size_t)n, (size_t)n_ext);
 	const double dev_ms = E.device_ms();
 	// lcg() / lcgs(): the caller's work vectors receive the solver's (host arrays, in the solver's allocation order)
 	for (int i = 0; i < n_ws_out && first_work + (size_t)i < E.allocs.size(); i++)
@@ -661,7 +666,10 @@ int do_solve_real(CsrHandle* h, Operator<double>& A, int solver_id, double* m, c
 	return ret;
 }
 
-inline int run_complex(Engine& E, const Operator<double2>& A, int id, double2* m, const double2* B, const lcgb200_cpara& p, size_t n, size_t ne) { return solve_complex(E, A, id, m, B, p, n, ne); }
+inline int run_complex(Engine& E, const Operator<double2>& A, int id, double2* m, const double2* B, const lcgb200_cpara& p, size_t n, size_t ne)
+{
+	return E.d_terms ? solve_complex_x(E, A, id, m, B, p, n, ne) : solve_complex(E, A, id, m, B, p, n, ne);
+}
 inline int run_complex(Engine& E, const Operator<ZF>& A, int id, ZF* m, const ZF* B, const lcgb200_cpara& p, size_t n, size_t ne) { return solve_complexf(E, A, id, m, B, p, n, ne); }
 
 // ZV = double2 (cuDoubleComplex vectors) or ZF (cuComplex vectors, clcg_cudaf.h)
@@ -679,7 +687,12 @@ int do_solve_cplx(CsrHandle* h, Operator<ZV>& A, int solver_id, ZV* m, const ZV*
 	const bool b_inplace = dev_vecs && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
 	const size_t vec_bytes = (((size_t)n_ext * sizeof(ZV)) + 255) & ~size_t(255);
 	int nvec = complex_vector_count(solver_id) + (m_inplace ? 0 : 1) + (b_inplace ? 0 : 1);
-	E.reserve(vec_bytes * (size_t)nvec);
+	// reference-order mode: the double-precision loops only (the cuComplex entry points have no CPU reference to be identical to)
+	const bool exact = reference_order() && std::is_same<ZV, double2>::value;
+	if (exact && E.multi()) { set_error_msg("reference-order mode runs on one GPU (a serial sum has no partition)"); throw ApiFailure{LCGB200_UNKNOWN_ERROR}; }
+	const size_t term_bytes = (((size_t)n_ext * sizeof(double)) + 255) & ~size_t(255);
+	E.reserve(vec_bytes * (size_t)nvec + (exact ? term_bytes * kMaxRed : 0));
+	if (exact) { E.terms_stride = term_bytes / sizeof(double); E.d_terms = E.alloc<double>(E.terms_stride * kMaxRed); E.allocs.clear(); }
 	ZV* d_m = m; const ZV* d_B = B;
 	const cudaMemcpyKind in_kind = dev_vecs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
 	if (!m_inplace) { d_m = E.alloc<ZV>((size_t)n_ext); LCG_CUDA_CHECK(cudaMemcpyAsync(d_m, m, (size_t)n * sizeof(ZV), in_kind, stream)); }
@@ -736,6 +749,7 @@ void lcgb200_set_fused_small(int on) { settings().fused_small = on ? 1 : 0; }
 void lcgb200_set_spin_timeout_ms(long long ms) { settings().spin_timeout_ms = ms; }
 void lcgb200_set_graphs(int mode) { settings().graphs = mode; }
 void lcgb200_set_pdl(int mode) { settings().pdl = mode; }
+void lcgb200_set_reference_order(int mode) { settings().reference_order = mode; }
 
 // sentinels: recognised by address, never executed on the fused path
 void lcgb200_csr_ax(void*, lcgb200_cublas_t, lcgb200_cusparse_t, lcgb200_dnvec_t, lcgb200_dnvec_t, const int, const int) {}

@@ -15,6 +15,26 @@
 
 namespace lcgb200 {
 
+// ---- arithmetic variants ------------------------------------------------------------------------------------
+// The solver translation units are compiled twice.  The default build (VariantStd) is the fast path: fused
+// multiply-adds and tree-ordered reductions.  The second build (-DLCG_REFORDER -fmad=false, VariantExact) reproduces the
+// arithmetic of the reference's x86-64 CPU build operation for operation — every a*b+c rounds twice (gcc emits no FMA
+// for the reference's flags, src/CMakeLists.txt:39-40), every row sum and every dot product adds its terms left to right
+// in index order (algebra.cpp:154-163, lcg_complex.cpp:143-167) — so that iterates, residual histories and iteration
+// counts are bit-identical to the reference's (lcgb200_set_reference_order; exact.cuh).  The variant is a (defaulted)
+// template argument of every Engine launch helper: the two builds instantiate differently named functions and kernels.
+struct VariantStd { static constexpr bool exact = false; };
+struct VariantExact { static constexpr bool exact = true; };
+#ifdef LCG_REFORDER
+typedef VariantExact Variant;
+__device__ __forceinline__ double lcg_mul_add(double a, double b, double c) { return __dadd_rn(__dmul_rn(a, b), c); }
+__device__ __forceinline__ float lcg_mul_addf(float a, float b, float c) { return __fadd_rn(__fmul_rn(a, b), c); }
+#define fma(a, b, c) lcg_mul_add((a), (b), (c))
+#define fmaf(a, b, c) lcg_mul_addf((a), (b), (c))
+#else
+typedef VariantStd Variant;
+#endif
+
 constexpr int kThreads = 256;        // threads per block, all kernels
 constexpr int kMaxBlocks = 148 * 8;  // persistent grids: multiples of the 148 SMs of a B200
 constexpr int kMaxRed = 8;           // max reduction slots per kernel

@@ -83,12 +83,17 @@ template <class T> struct StageCfg {
 };
 
 __device__ __forceinline__ double mulacc(double acc, double a, double x) { return fma(a, x, acc); }
+#ifdef LCG_REFORDER
+// reference order: the complex product is formed first (re = ac - bd, im = ad + bc), then added to the running sum
+__device__ __forceinline__ double2 mulacc(double2 acc, double2 a, double2 x) { return zadd(acc, zmul(a, x)); }
+#else
 __device__ __forceinline__ double2 mulacc(double2 acc, double2 a, double2 x)
 {
 	acc.x = fma(a.x, x.x, acc.x); acc.x = fma(-a.y, x.y, acc.x);
 	acc.y = fma(a.x, x.y, acc.y); acc.y = fma(a.y, x.x, acc.y);
 	return acc;
 }
+#endif
 // single-precision complex entries: products and row sums in float (as cusparseSpMV does for CUDA_C_32F)
 __device__ __forceinline__ ZF mulacc(ZF acc, ZF a, ZF x)
 {

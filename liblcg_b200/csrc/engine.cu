@@ -33,6 +33,13 @@ static void pdl_decide(size_t n_local)
 	t_pdl_active = mode > 0 || (mode < 0 && n_local <= ((size_t)8 << 20));
 }
 
+bool reference_order()
+{
+	int mode = settings().reference_order;
+	if (mode < 0) { static const int env = [] { const char* e = getenv("LCGB200_REFERENCE_ORDER"); return e ? atoi(e) : 0; }(); mode = env; }
+	return mode > 0;
+}
+
 long long spin_timeout_ms()
 {
 	if (settings().spin_timeout_ms >= 0) return settings().spin_timeout_ms;
@@ -153,6 +160,7 @@ void Engine::prof_collect(double* ms, int* count)
 
 Engine::~Engine()
 {
+	l2_window_end();
 	for (auto& t : timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
 	if (own_state)
 	{
@@ -162,10 +170,46 @@ Engine::~Engine()
 	if (own_ws && ws) cudaFree(ws);
 }
 
+void Engine::l2_window_begin()
+{
+	int mode = settings().l2_persist;
+	if (mode < 0) { static const int env = [] { const char* e = getenv("LCGB200_L2_PERSIST"); return e ? atoi(e) : 0; }(); mode = env; }
+	if (mode <= 0 || !ws || !ws_need || stream == nullptr || stream == cudaStreamLegacy) return;
+	int dev = 0, max_persist = 0, max_window = 0;
+	if (cudaGetDevice(&dev) != cudaSuccess) return;
+	cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+	cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+	if (max_persist <= 0 || max_window <= 0) return;
+	size_t carve = ws_need < (size_t)max_persist ? ws_need : (size_t)max_persist;
+	if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) != cudaSuccess) { (void)cudaGetLastError(); return; }
+	cudaStreamAttrValue v = {};
+	v.accessPolicyWindow.base_ptr = ws;
+	v.accessPolicyWindow.num_bytes = ws_need < (size_t)max_window ? ws_need : (size_t)max_window;
+	v.accessPolicyWindow.hitRatio = (float)((double)carve / (double)v.accessPolicyWindow.num_bytes);
+	if (v.accessPolicyWindow.hitRatio > 1.f) v.accessPolicyWindow.hitRatio = 1.f;
+	v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+	v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+	if (cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) { (void)cudaGetLastError(); return; }
+	l2_window_set = true;
+	static const bool dbg = getenv("LCGB200_DEBUG_L2") != nullptr;
+	if (dbg) fprintf(stderr, "[lcgb200] L2 window: need %zu B, max persisting %d B, max window %d B, hit ratio %.3f\n", ws_need, max_persist, max_window, v.accessPolicyWindow.hitRatio);
+}
+
+void Engine::l2_window_end()
+{
+	if (!l2_window_set) return;
+	cudaStreamAttrValue v = {};
+	v.accessPolicyWindow.num_bytes = 0;
+	cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &v);
+	cudaCtxResetPersistingL2Cache();
+	l2_window_set = false;
+}
+
 void Engine::reserve(size_t bytes)
 {
 	bytes = (bytes + 255) & ~size_t(255);
 	ws_off = 0;
+	ws_need = bytes;
 	if (cache)
 	{
 		if (cache->ws_bytes < bytes)
@@ -194,6 +238,7 @@ void Engine::start(const DevState& init)
 	h_st->spin_timeout_ns = (unsigned long long)spin_timeout_ms() * 1000000ull * ((pf || sync_each) ? 20ull : 1ull);
 	pushed_vec = nullptr;
 	pdl_decide(n_local);
+	l2_window_begin();
 	LCG_CUDA_CHECK(cudaMemcpyAsync(d_st, h_st, sizeof(DevState), cudaMemcpyHostToDevice, stream));
 	LCG_CUDA_CHECK(cudaEventRecord(ev[2], stream));
 	seen_checks = 0;

@@ -11,6 +11,7 @@
 #include "csr.cuh"
 #include "fused_small.cuh"
 #include "ic0.cuh"
+#include "exact.cuh"
 
 namespace lcgb200 {
 
@@ -121,7 +122,10 @@ struct Settings {
 	int graphs = -1;               // CUDA graph per batch of iterations; -1 = LCGB200_GRAPHS or automatic
 	int pdl = -1;                  // programmatic dependent launch between the kernels of an iteration; -1 = LCGB200_PDL or on
 	int fuse_vec2 = -1;            // update + direction in one cooperative kernel; -1 = LCGB200_FUSE_VEC2 or automatic (by size)
+	int l2_persist = -1;           // persisting-L2 window over the work vectors; -1 = LCGB200_L2_PERSIST or off
+	int reference_order = -1;      // reference-order arithmetic (exact.cuh): bit-identical to the reference's CPU build; -1 = LCGB200_REFERENCE_ORDER or off
 };
+bool reference_order();
 long long spin_timeout_ms();
 bool fuse_vec2(size_t n_local);
 int coop_grid_full(const void* kernel, int block);   // all co-resident blocks of a kernel on the current device (engine.cu)
@@ -159,6 +163,12 @@ public:
 	~Engine();
 
 	void reserve(size_t bytes);
+	size_t ws_need = 0;            // bytes of the arena this solve uses
+	// L2 residency of the work vectors (mid-size systems whose vectors fit the 126 MB L2 while the matrix does not): the
+	// arena becomes a persisting access-policy window of the solve's stream for the duration of the solve
+	bool l2_window_set = false;
+	void l2_window_begin();
+	void l2_window_end();
 	std::vector<void*> allocs;     // every vector handed out, in order (lcg()/lcgs() copy their work vectors back to the caller)
 	template <class T> T* alloc(size_t count)
 	{
@@ -174,13 +184,21 @@ public:
 	bool multi() const { return comm != nullptr && comm->size() > 1; }
 	bool p2p() const { return multi() && cache && cache->p2p_dev() != nullptr; }
 
-	template <class Op> void vec(const Op& op, size_t n)
+	template <class Op, class V = Variant> void vec(const Op& op, size_t n)
 	{
-		cudaEvent_t pe = profiling ? prof_begin(1) : nullptr;
-		launch_k(k_vec<Op, false, double>, vec_grid(n, Op::W), kThreads, 0, stream, op, n, d_st, d_partials, (CommDev*)nullptr, (const double*)nullptr);
-		prof_end(pe);
-		launches++;
-		if (Op::NRED > 0 && multi()) finish_multi(op, Op::NRED);
+		if constexpr (V::exact)
+		{	// reference-order build: terms in parallel, serial totals + scalar epilogue in a second launch
+			launch_exact_vec(op, n, d_st, d_terms, terms_stride, stream);
+			launches += Op::NRED > 0 ? 2 : 1;
+		}
+		else
+		{
+			cudaEvent_t pe = profiling ? prof_begin(1) : nullptr;
+			launch_k(k_vec<Op, false, double>, vec_grid(n, Op::W), kThreads, 0, stream, op, n, d_st, d_partials, (CommDev*)nullptr, (const double*)nullptr);
+			prof_end(pe);
+			launches++;
+			if (Op::NRED > 0 && multi()) finish_multi(op, Op::NRED);
+		}
 	}
 
 	// Same, for a kernel that WRITES `out`, the input of the next SpMV.  On the NVLink transport (row partition whose send
@@ -189,37 +207,45 @@ public:
 	// wait for the neighbours' flags (halo overlapped with the interior rows).
 	const void* pushed_vec = nullptr;   // the vector whose halo the last pushing kernel has already sent
 	bool halo_in_spmv() const { return multi() && cache && cache->halo_in_spmv(); }
-	template <class T, class Op> void vec_push(const Op& op, size_t n, const T* out)
+	template <class T, class Op, class V = Variant> void vec_push(const Op& op, size_t n, const T* out)
 	{
-		if (!(halo_in_spmv() && comm->fused_push_ok())) { vec(op, n); return; }
-		cudaEvent_t pe = profiling ? prof_begin(1) : nullptr;
-		launch_k(k_vec<Op, true, T>, vec_grid(n, Op::W), kThreads, 0, stream, op, n, d_st, d_partials, cache->p2p_dev(), out);
-		prof_end(pe);
-		launches++;
-		pushed_vec = out;
-		if (Op::NRED > 0 && multi()) finish_multi(op, Op::NRED);
+		if constexpr (V::exact) vec(op, n);
+		else
+		{
+			if (!(halo_in_spmv() && comm->fused_push_ok())) { vec(op, n); return; }
+			cudaEvent_t pe = profiling ? prof_begin(1) : nullptr;
+			launch_k(k_vec<Op, true, T>, vec_grid(n, Op::W), kThreads, 0, stream, op, n, d_st, d_partials, cache->p2p_dev(), out);
+			prof_end(pe);
+			launches++;
+			pushed_vec = out;
+			if (Op::NRED > 0 && multi()) finish_multi(op, Op::NRED);
+		}
 	}
 
 	// update + direction in one cooperative launch (k_vec2) where that is possible: our own reductions (single GPU or the
 	// NVLink transport: the NCCL transport needs a collective between the two steps), a grid that is wholly co-resident, and
 	// systems small enough for a kernel boundary to matter (the regime of the CUDA graphs); otherwise two launches.
-	template <class T, class Op1, class Op2> void vec2_push(const Op1& a, const Op2& b, size_t n, const T* out)
+	template <class T, class Op1, class Op2, class V = Variant> void vec2_push(const Op1& a, const Op2& b, size_t n, const T* out)
 	{
-		if (!fuse_vec2(n) || (multi() && !p2p())) { vec(a, n); vec_push(b, n, out); return; }
-		const bool push = halo_in_spmv() && comm->fused_push_ok();
-		CommDev* cd = push ? cache->p2p_dev() : nullptr;
-		DevState* st = d_st; double* parts = d_partials; size_t nn = n;
-		Op1 a1 = a; Op2 b1 = b;
-		void* args[] = {&a1, &b1, &nn, &st, &parts, &cd, (void*)&out};
-		const void* kern = push ? (const void*)k_vec2<Op1, Op2, true, T> : (const void*)k_vec2<Op1, Op2, false, T>;
-		int grid = vec_grid(n, Op1::W);
-		const int limit = coop_grid_full(kern, kThreads);
-		if (grid > limit) grid = limit;
-		cudaEvent_t pe = profiling ? prof_begin(1) : nullptr;
-		LCG_CUDA_CHECK(cudaLaunchCooperativeKernel(kern, dim3((unsigned)grid), dim3(kThreads), args, 0, stream));
-		prof_end(pe);
-		launches++;
-		if (push) pushed_vec = out;
+		if constexpr (V::exact) { vec(a, n); vec(b, n); }
+		else
+		{
+			if (!fuse_vec2(n) || (multi() && !p2p())) { vec(a, n); vec_push(b, n, out); return; }
+			const bool push = halo_in_spmv() && comm->fused_push_ok();
+			CommDev* cd = push ? cache->p2p_dev() : nullptr;
+			DevState* st = d_st; double* parts = d_partials; size_t nn = n;
+			Op1 a1 = a; Op2 b1 = b;
+			void* args[] = {&a1, &b1, &nn, &st, &parts, &cd, (void*)&out};
+			const void* kern = push ? (const void*)k_vec2<Op1, Op2, true, T> : (const void*)k_vec2<Op1, Op2, false, T>;
+			int grid = vec_grid(n, Op1::W);
+			const int limit = coop_grid_full(kern, kThreads);
+			if (grid > limit) grid = limit;
+			cudaEvent_t pe = profiling ? prof_begin(1) : nullptr;
+			LCG_CUDA_CHECK(cudaLaunchCooperativeKernel(kern, dim3((unsigned)grid), dim3(kThreads), args, 0, stream));
+			prof_end(pe);
+			launches++;
+			if (push) pushed_vec = out;
+		}
 	}
 
 	template <class Op> void finish_multi(const Op& op, int nred)
@@ -231,9 +257,25 @@ public:
 	}
 
 	// y = op(A) x with a fused per-row epilogue.  op: 0 = N, 1 = T, 2 = H.
-	template <class T, class Epi> void spmv(const Operator<T>& A, T* x, T* y, const Epi& epi, int op = 0)
+	template <class T, class Epi, class V = Variant> void spmv(const Operator<T>& A, T* x, T* y, const Epi& epi, int op = 0)
 	{
-		if (A.h)
+		if constexpr (V::exact)
+		{
+			if (A.h)
+			{	// built-in operator, reference order: one thread per row over the plain CSR arrays (A^T / A^H: the stored transpose)
+				const CsrDev<T> Vw = op == 0 ? A.h->template view<T>() : A.h->template tview<T>();
+				if (op == 2) launch_exact_spmv<T, true, Epi>(Vw, x, y, epi, d_st, d_terms, terms_stride, stream);
+				else launch_exact_spmv<T, false, Epi>(Vw, x, y, epi, d_st, d_terms, terms_stride, stream);
+				launches += Epi::NRED > 0 ? 2 : 1; spmv_launches++;
+			}
+			else
+			{
+				A.apply(x, y, op);
+				spmv_launches++;
+				if (Epi::ACTIVE) vec(RowEpilogueOp<T, Epi>{epi, x, y}, (size_t)n_local);
+			}
+		}
+		else if (A.h)
 		{
 			// op(A) of a partitioned system: A^T / A^H come from the second partitioned handle (its own plan, windows, sequence)
 			const CsrHandle* hh = (op != 0 && A.h->t_handle) ? A.h->t_handle : A.h;
@@ -246,10 +288,10 @@ public:
 				}
 				else { hh->comm->halo(x, (int)sizeof(T), stream, hh->p2p_dev() != nullptr, d_st); if (hh->p2p_dev()) launches++; }
 			}
-			const CsrDev<T> V = (hh != A.h || op == 0) ? hh->template view<T>() : hh->template tview<T>();
+			const CsrDev<T> Vw = (hh != A.h || op == 0) ? hh->template view<T>() : hh->template tview<T>();
 			cudaEvent_t pe = profiling ? prof_begin(0) : nullptr;
-			if (op == 2) launch_spmv<T, true, Epi>(V, x, y, epi, d_st, d_partials, stream);
-			else launch_spmv<T, false, Epi>(V, x, y, epi, d_st, d_partials, stream);
+			if (op == 2) launch_spmv<T, true, Epi>(Vw, x, y, epi, d_st, d_partials, stream);
+			else launch_spmv<T, false, Epi>(Vw, x, y, epi, d_st, d_partials, stream);
 			prof_end(pe);
 			launches++; spmv_launches++;
 			if (Epi::NRED > 0 && multi()) finish_multi(RowEpilogueOp<T, Epi>{epi, x, y}, Epi::NRED);
@@ -263,27 +305,34 @@ public:
 	}
 
 	size_t n_local = 0;
+	// reference-order build: one term per element and reduction slot (kMaxRed x terms_stride doubles, from the workspace arena)
+	double* d_terms = nullptr; size_t terms_stride = 0;
 
 	// z = (L L^T)^-1 r with the handle's IC(0) factor: forward solve into the handle's scratch vector, backward solve into z
-	template <class T> void ic0_solve(const CsrHandle* h, const T* r, T* z)
+	template <class T, class V = Variant> void ic0_solve(const CsrHandle* h, const T* r, T* z)
 	{
-		cudaEvent_t pe = profiling ? prof_begin(1) : nullptr;
-		launch_sptrsv<T, false>(h->icL, r, static_cast<T*>(h->ic_tmp), d_st, stream);
-		launch_sptrsv<T, true>(h->icU, static_cast<const T*>(h->ic_tmp), z, d_st, stream);
-		prof_end(pe);
-		launches += 2;
+		if constexpr (V::exact) { set_error_msg("the IC(0) preconditioner is not available in reference-order mode"); throw CudaFailure(); }
+		else
+		{
+			cudaEvent_t pe = profiling ? prof_begin(1) : nullptr;
+			launch_sptrsv<T, false>(h->icL, r, static_cast<T*>(h->ic_tmp), d_st, stream);
+			launch_sptrsv<T, true>(h->icU, static_cast<const T*>(h->ic_tmp), z, d_st, stream);
+			prof_end(pe);
+			launches += 2;
+		}
 	}
 	// M^-1 of the preconditioned solvers' generic path: the built-in IC(0) or the user's callback
-	template <class T> void precondition(const Operator<T>& A, const T* r, T* z)
+	template <class T, class V = Variant> void precondition(const Operator<T>& A, const T* r, T* z)
 	{
-		if (A.ic0) ic0_solve<T>(A.ic0, r, z);
+		if (A.ic0) ic0_solve<T, V>(A.ic0, r, z);
 		else A.precond(r, z, 0);
 	}
 
 	// cache-resident single-GPU systems on the built-in operator take the fused cooperative kernel (not while profiling:
 	// the per-kernel attribution of bench.py's roofline pass needs the separate launches)
-	template <class T> bool small_system(const Operator<T>& A) const
+	template <class T, class V = Variant> bool small_system(const Operator<T>& A) const
 	{
+		if (V::exact) return false;
 		return A.h && !multi() && !profiling && settings().fused_small && A.h->n_rows <= kSmallRows && A.h->nnz <= kSmallNnz;
 	}
 	// phase builders for the fused kernel (what E.spmv / E.vec would have launched)
@@ -299,8 +348,12 @@ public:
 	// `iters` iterations of the phase list in one cooperative launch; n_spmv = SpMV phases per iteration
 	template <class... Ph> void fused(int iters, int n_spmv, Ph... ph)
 	{
-		LCG_CUDA_CHECK((launch_fused<Ph...>(d_st, d_partials, iters, stream, ph...)));
-		launches++; spmv_launches += iters * n_spmv;
+		if constexpr (Variant::exact) { set_error_msg("no fused path in the reference-order build"); throw CudaFailure(); }
+		else
+		{
+			LCG_CUDA_CHECK((launch_fused<Ph...>(d_st, d_partials, iters, stream, ph...)));
+			launches++; spmv_launches += iters * n_spmv;
+		}
 	}
 
 	// Pfp mode: read the state, deliver a new loop head to the callback.  Returns true when the solve is over

@@ -11,8 +11,12 @@
 // The file is compiled twice: as it is for cuDoubleComplex vectors (solve_complex), and with -DLCG_CPLX_FLOAT for cuComplex
 // vectors (solve_complexf: the entry points of clcg_cudaf.h:81-105, reference implementation clcg_cudaf.cu).  ZV is the type
 // of a vector / matrix element in memory; the arithmetic of every step runs on Z = double2 either way.
-#ifdef LCG_CPLX_FLOAT
+// A third build (-DLCG_REFORDER -fmad=false: solve_complex_x) is the reference-order variant of the double-precision loops
+// (common.cuh "arithmetic variants" / exact.cuh).
+#if defined(LCG_CPLX_FLOAT)
 #define LCG_CPLX_NS cf32
+#elif defined(LCG_REFORDER)
+#define LCG_CPLX_NS cx64
 #else
 #define LCG_CPLX_NS cf64
 #endif
@@ -598,6 +602,11 @@ static int dispatch(Engine& E, const Operator<ZV>& A, int solver_id, ZV* m, cons
 int solve_complexf(Engine& E, const Operator<ZF>& A, int solver_id, ZF* m, const ZF* B, const lcgb200_cpara& para, size_t n, size_t next)
 {
 	return cf32::dispatch(E, A, solver_id, m, B, para, n, next);
+}
+#elif defined(LCG_REFORDER)
+int solve_complex_x(Engine& E, const Operator<double2>& A, int solver_id, double2* m, const double2* B, const lcgb200_cpara& para, size_t n, size_t next)
+{
+	return cx64::dispatch(E, A, solver_id, m, B, para, n, next);
 }
 #else
 int solve_complex(Engine& E, const Operator<double2>& A, int solver_id, double2* m, const double2* B, const lcgb200_cpara& para, size_t n, size_t next)

@@ -5,7 +5,18 @@
 //   CG  6 + 3 | PCG 8 + 3 | CGS 1 + 4 + 7 + 5 | BICGSTAB 1 + 3 + 1 + 7 + 4 | PG 3 + 7
 #include "solvers.cuh"
 
+// The file is compiled twice: as it is (solve_real, the fast path), and with -DLCG_REFORDER -fmad=false (solve_real_x: the
+// reference-order build, common.cuh "arithmetic variants" / exact.cuh).  The step functors below are written so that each
+// expression has the reference's shape — fma(a, b, c) stands where the reference computes a*b + c — which makes the second
+// build bit-identical to the reference's CPU loops.
+#ifdef LCG_REFORDER
+#define LCG_REAL_NS rx64
+#else
+#define LCG_REAL_NS r64
+#endif
+
 namespace lcgb200 {
+namespace LCG_REAL_NS {
 
 __device__ __forceinline__ double box(double lo, double hi, double a)
 {	// lcg_set2box with closed bounds (algebra.cpp:50-58 as called at lcg.cpp:1089)
@@ -641,7 +652,7 @@ static int run_spg(Engine& E, const Operator<double>& A, double* m, const double
 }
 
 // ======================================================================================== dispatch
-int solve_real(Engine& E, const Operator<double>& A, int solver_id, double* m, const double* B, const double* lo, const double* hi,
+static int dispatch(Engine& E, const Operator<double>& A, int solver_id, double* m, const double* B, const double* lo, const double* hi,
 	const lcgb200_para& para, size_t n, size_t next)
 {
 	switch (solver_id)
@@ -656,6 +667,21 @@ int solve_real(Engine& E, const Operator<double>& A, int solver_id, double* m, c
 	}
 }
 
+}  // namespace LCG_REAL_NS
+
+#ifdef LCG_REFORDER
+int solve_real_x(Engine& E, const Operator<double>& A, int solver_id, double* m, const double* B, const double* lo, const double* hi,
+	const lcgb200_para& para, size_t n, size_t next)
+{
+	return rx64::dispatch(E, A, solver_id, m, B, lo, hi, para, n, next);
+}
+#else
+int solve_real(Engine& E, const Operator<double>& A, int solver_id, double* m, const double* B, const double* lo, const double* hi,
+	const lcgb200_para& para, size_t n, size_t next)
+{
+	return r64::dispatch(E, A, solver_id, m, B, lo, hi, para, n, next);
+}
+
 int real_vector_count(int solver_id)
 {
 	switch (solver_id)
@@ -668,5 +694,7 @@ int real_vector_count(int solver_id)
 		default: return 7;
 	}
 }
+
+#endif
 
 }  // namespace lcgb200
