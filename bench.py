@@ -54,6 +54,8 @@ WORKLOADS = {
     # small variants for quick checks (not bench lines)
     "pcg27_64": ("27pt", 64, "PCG"),
     "pcg27_128": ("27pt", 128, "PCG"),   # the per-GPU share of pcg27_256 on 8 GPUs (2.1 M rows), without the exchanges
+    "pcg27_160": ("27pt", 160, "PCG"),   # ~ the share on 4 GPUs
+    "pcg27_200": ("27pt", 200, "PCG"),   # ~ the share on 2 GPUs
     "bicgstab7cd_96": ("7pt_cd", 96, "BICGSTAB"),
 }
 KIND_ID = {"7pt": 0, "27pt": 1, "7pt_cd": 2}

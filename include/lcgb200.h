@@ -343,6 +343,11 @@ void lcgb200_set_graphs(int mode);
 /* programmatic dependent launch between the kernels of an iteration (the next kernel is scheduled while the current one
  * finishes its reduction and parks in griddepcontrol.wait): -1 (default) = environment LCGB200_PDL or on, 0 = off, 1 = on */
 void lcgb200_set_pdl(int mode);
+/* Persisting-L2 window over the iteration's work vectors for the duration of a solve (systems whose vectors fit the 126 MB
+ * L2 while the matrix does not: 10^6-10^7 rows per GPU): -1 (default) = environment LCGB200_L2_PERSIST or automatic,
+ * 0 = off, 1 = always.  Uses the device-wide persisting carve-out (cudaLimitPersistingL2CacheSize), released at the end
+ * of the solve. */
+void lcgb200_set_l2_persist(int mode);
 /* Reference-order arithmetic (verification mode; single GPU, double precision): 1 = every later solve runs the second
  * build of the iteration loops, which reproduces the reference's x86-64 CPU arithmetic operation for operation — no fused
  * multiply-adds, SpMV row sums and dot products added left to right in index order (algebra.cpp:154-163,

@@ -106,6 +106,7 @@ SYMBOLS = {
     "lcgb200_set_graphs": (None, [_I]),
     "lcgb200_set_pdl": (None, [_I]),
     "lcgb200_set_reference_order": (None, [_I]),
+    "lcgb200_set_l2_persist": (None, [_I]),
     "lcgb200_last_error": (C.c_char_p, []),
     "lcgb200_version": (_I, []),
     "lcgb200_gen_stencil": (_I, [_I, _I, _LL, _LL, _VP, _VP, _VP, _LL, C.POINTER(_LL), _VP]),

@@ -612,16 +612,20 @@ int do_solve_real(CsrHandle* h, Operator<double>& A, int solver_id, double* m, c
 	if (exact) { E.terms_stride = vec_bytes / sizeof(double); E.d_terms = E.alloc<double>(E.terms_stride * kMaxRed); E.allocs.clear(); }
 	double* d_m = m; const double* d_B = B; const double* d_lo = lo; const double* d_hi = hi;
 	const cudaMemcpyKind in_kind = dev_vecs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-	if (!m_inplace)
-	{
-		d_m = E.alloc<double>((size_t)n_ext);
-		LCG_CUDA_CHECK(cudaMemcpyAsync(d_m, m, (size_t)n * sizeof(double), in_kind, stream));
-	}
+	// copies of B (read by the init step only) come first; everything behind them is touched every iteration and forms the
+	// persisting-L2 window (Engine::l2_window_begin)
 	if (!b_inplace)
 	{
 		double* t = E.alloc<double>((size_t)n_ext);
 		LCG_CUDA_CHECK(cudaMemcpyAsync(t, B, (size_t)n * sizeof(double), in_kind, stream));
 		d_B = t;
+	}
+	if (!constrained) E.l2_from = E.ws_off;
+	E.l2_unit = vec_bytes;
+	if (!m_inplace)
+	{
+		d_m = E.alloc<double>((size_t)n_ext);
+		LCG_CUDA_CHECK(cudaMemcpyAsync(d_m, m, (size_t)n * sizeof(double), in_kind, stream));
 	}
 	if (constrained && !box_inplace)
 	{
@@ -695,8 +699,9 @@ int do_solve_cplx(CsrHandle* h, Operator<ZV>& A, int solver_id, ZV* m, const ZV*
 	if (exact) { E.terms_stride = term_bytes / sizeof(double); E.d_terms = E.alloc<double>(E.terms_stride * kMaxRed); E.allocs.clear(); }
 	ZV* d_m = m; const ZV* d_B = B;
 	const cudaMemcpyKind in_kind = dev_vecs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-	if (!m_inplace) { d_m = E.alloc<ZV>((size_t)n_ext); LCG_CUDA_CHECK(cudaMemcpyAsync(d_m, m, (size_t)n * sizeof(ZV), in_kind, stream)); }
 	if (!b_inplace) { ZV* t = E.alloc<ZV>((size_t)n_ext); LCG_CUDA_CHECK(cudaMemcpyAsync(t, B, (size_t)n * sizeof(ZV), in_kind, stream)); d_B = t; }
+	E.l2_from = E.ws_off; E.l2_unit = vec_bytes;   // behind the copy of B: what every iteration touches (persisting-L2 window)
+	if (!m_inplace) { d_m = E.alloc<ZV>((size_t)n_ext); LCG_CUDA_CHECK(cudaMemcpyAsync(d_m, m, (size_t)n * sizeof(ZV), in_kind, stream)); }
 	DevState init;
 	std::memset(&init, 0, sizeof(init));
 	init.eps = para.epsilon; init.n_global = n_global; init.abs_diff = para.abs_diff; init.max_it = para.max_iterations;
@@ -750,6 +755,7 @@ void lcgb200_set_spin_timeout_ms(long long ms) { settings().spin_timeout_ms = ms
 void lcgb200_set_graphs(int mode) { settings().graphs = mode; }
 void lcgb200_set_pdl(int mode) { settings().pdl = mode; }
 void lcgb200_set_reference_order(int mode) { settings().reference_order = mode; }
+void lcgb200_set_l2_persist(int mode) { settings().l2_persist = mode; }
 
 // sentinels: recognised by address, never executed on the fused path
 void lcgb200_csr_ax(void*, lcgb200_cublas_t, lcgb200_cusparse_t, lcgb200_dnvec_t, lcgb200_dnvec_t, const int, const int) {}

@@ -122,7 +122,7 @@ struct Settings {
 	int graphs = -1;               // CUDA graph per batch of iterations; -1 = LCGB200_GRAPHS or automatic
 	int pdl = -1;                  // programmatic dependent launch between the kernels of an iteration; -1 = LCGB200_PDL or on
 	int fuse_vec2 = -1;            // update + direction in one cooperative kernel; -1 = LCGB200_FUSE_VEC2 or automatic (by size)
-	int l2_persist = -1;           // persisting-L2 window over the work vectors; -1 = LCGB200_L2_PERSIST or off
+	int l2_persist = -1;           // persisting-L2 window over the work vectors; -1 = LCGB200_L2_PERSIST or automatic
 	int reference_order = -1;      // reference-order arithmetic (exact.cuh): bit-identical to the reference's CPU build; -1 = LCGB200_REFERENCE_ORDER or off
 };
 bool reference_order();
@@ -164,6 +164,8 @@ public:
 
 	void reserve(size_t bytes);
 	size_t ws_need = 0;            // bytes of the arena this solve uses
+	size_t l2_from = 0;            // arena offset where the iteration's vectors start (copies of B / the box come first)
+	size_t l2_unit = 0;            // bytes of one work vector in the arena
 	// L2 residency of the work vectors (mid-size systems whose vectors fit the 126 MB L2 while the matrix does not): the
 	// arena becomes a persisting access-policy window of the solve's stream for the duration of the solve
 	bool l2_window_set = false;

@@ -33,6 +33,58 @@ def row_bounds(n: int, world: int, align: int = 1) -> list[int]:
     return b
 
 
+# bytes one row costs per iteration besides its non-zeros: row_ptr, x, y of the SpMV (20 B) + ~11 vector passes of 8 B
+ROW_OVERHEAD_BYTES = 108
+NNZ_BYTES = 12
+
+
+def row_bounds_nnz(row_ptr, world: int, align: int = 1) -> list[int]:
+    """Contiguous row blocks balanced by the BYTES an iteration streams ("balanced by nnz"): a row weighs
+    12 B per non-zero plus ROW_OVERHEAD_BYTES.  `row_ptr` is the global row pointer (numpy or tensor, n + 1 entries);
+    block edges are rounded to a multiple of `align` rows (e.g. a grid plane, so that send lists stay contiguous)."""
+    rp = np.asarray(row_ptr.cpu() if hasattr(row_ptr, "cpu") else row_ptr, dtype=np.int64)
+    n = len(rp) - 1
+    weight = NNZ_BYTES * (rp - rp[0]) + ROW_OVERHEAD_BYTES * np.arange(n + 1, dtype=np.int64)   # prefix sums of the row weights
+    b = [0]
+    for r in range(1, world):
+        e = int(np.searchsorted(weight, weight[-1] * r / world, side="left"))
+        if align > 1:
+            e = int(round(e / align)) * align
+        b.append(min(max(e, b[-1]), n))
+    b.append(n)
+    return b
+
+
+def stencil_row_ptr_planes(kind: str, g: int) -> np.ndarray:
+    """Prefix sums of the non-zeros per z-plane of the g^3 stencils (plane z holds rows [z g^2, (z+1) g^2)), as a row pointer
+    over PLANES — what row_bounds_nnz needs to balance a z-slab partition without building the matrix."""
+    def line(reach):   # neighbours within `reach` along one axis, summed over a line of g points
+        return g + 2 * (g - 1) * reach
+    if kind == "27pt":
+        per_axis = np.array([3 if 0 < z < g - 1 else (2 if g > 1 else 1) for z in range(g)], dtype=np.int64)
+        plane = per_axis * (line(1) ** 2)
+    else:   # 7-point stars: centre + 2 in-plane axes + the z neighbours
+        in_plane = g * g + 2 * 2 * g * (g - 1)
+        plane = np.array([in_plane + g * g * ((z > 0) + (z < g - 1)) for z in range(g)], dtype=np.int64)
+    out = np.zeros(g + 1, dtype=np.int64)
+    np.cumsum(plane, out=out[1:])
+    return out
+
+
+def stencil_bounds(kind: str, g: int, world: int) -> list[int]:
+    """z-slab partition of a g^3 stencil system balanced by streamed bytes (whole planes per rank)."""
+    planes = stencil_row_ptr_planes(kind, g)
+    weight = NNZ_BYTES * planes + ROW_OVERHEAD_BYTES * g * g * np.arange(g + 1, dtype=np.int64)
+    b = [0]
+    for r in range(1, world):
+        z = int(np.searchsorted(weight, weight[-1] * r / world, side="left"))
+        if z > 0 and abs(weight[z - 1] - weight[-1] * r / world) <= abs(weight[z] - weight[-1] * r / world):
+            z -= 1
+        b.append(min(max(z * g * g, b[-1]), g ** 3))
+    b.append(g ** 3)
+    return b
+
+
 @dataclass
 class HaloPlan:
     rank: int
@@ -263,7 +315,7 @@ def build_stencil_partition(kind: str, g: int, rank: int, world: int, device, ja
     import torch
     lib = _lib.load()
     n = g ** 3
-    bounds = row_bounds(n, world, align=g * g)
+    bounds = stencil_bounds(kind, g, world)
     r0, r1 = bounds[rank], bounds[rank + 1]
     nz = C.c_longlong()
     assert lib.lcgb200_gen_stencil(KIND_ID[kind], g, r0, r1, None, None, None, 0, C.byref(nz), None) == 0

@@ -99,7 +99,7 @@ def main():
     G = dict(n=n, nnz=Afull.nnz, row_ptr=Afull.indptr.astype(np.int32), col=Afull.indices.astype(np.int32), val=Afull.data.astype(np.float64))
     xs = rng.standard_normal(n)
     bfull = Afull @ xs
-    bounds = ldist.row_bounds(n, world)
+    bounds = ldist.row_bounds_nnz(G["row_ptr"], world)   # balanced by streamed bytes
     r0, r1 = bounds[rank], bounds[rank + 1]
     k0, k1 = G["row_ptr"][r0], G["row_ptr"][r1]
     part = ldist.partition_csr(torch.from_numpy((G["row_ptr"][r0:r1 + 1] - k0).astype(np.int32)).to(dev), torch.from_numpy(G["col"][k0:k1]).to(dev),
@@ -145,7 +145,7 @@ def main():
     # CGS / BICGSTAB / TFQMR with every rank drawing its slice of the ONE rand() sequence of the shadow residual, Jacobi-PCG
     Ac = lio.load_fixture("10Kc")
     n = Ac["n"]
-    bounds = ldist.row_bounds(n, world)
+    bounds = ldist.row_bounds_nnz(Ac["row_ptr"], world)
     r0, r1 = bounds[rank], bounds[rank + 1]
     k0, k1 = Ac["row_ptr"][r0], Ac["row_ptr"][r1]
     cpart = ldist.partition_csr(torch.from_numpy((Ac["row_ptr"][r0:r1 + 1] - k0).astype(np.int32)).to(dev), torch.from_numpy(Ac["col"][k0:k1].astype(np.int32)).to(dev),

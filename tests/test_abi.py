@@ -4,6 +4,7 @@ integers in the reference's order; the product package never touches the oracle.
 import ctypes as C
 import os
 import re
+import subprocess
 
 import numpy as np
 import pytest
@@ -235,3 +236,27 @@ def test_dropin_library_exports_liblcg_cxx_symbols():
     ]
     missing = [m for m in must if m not in defined]
     assert not missing, missing
+
+
+def test_reference_order_build_shares_no_kernel_with_the_fast_build():
+    """The solver sources are compiled twice (fast build / reference-order build with -fmad=false).  A kernel instantiated
+    under the same name in both would be an ODR collision: the linker keeps one host stub and one of the two device images
+    would silently serve both builds.  The variant tag of the Engine launch helpers must keep the kernel sets disjoint, and the
+    reference-order objects must contain only the exact.cuh kernels."""
+    import shutil
+    build = os.path.join(ROOT, "liblcg_b200", "csrc", "build")
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not (os.path.isdir(build) and os.path.exists(cuobjdump)):
+        pytest.skip("object files / cuobjdump not available")
+
+    def kernels(obj):
+        out = subprocess.run([cuobjdump, "-elf", os.path.join(build, obj)], capture_output=True, text=True).stdout
+        return set(re.findall(r"\.text\.(_Z\w+)", out))
+
+    exact = kernels("solvers_real_x.o") | kernels("solvers_complex_x.o")
+    fast = set()
+    for o in ("solvers_real.o", "solvers_complex.o", "solvers_complexf.o", "capi.o", "comm.o", "engine.o", "datastep.o", "stencil_gen.o"):
+        fast |= kernels(o)
+    assert exact and fast
+    assert not (exact & fast), sorted(exact & fast)[:5]
+    assert all(re.match(r"_ZN7lcgb200(6kx_vec|7kx_spmv|8kx_total)I", k) for k in exact), [k for k in exact if "kx_" not in k][:5]

@@ -118,3 +118,27 @@ def test_row_bounds():
     assert ldist.row_bounds(8 ** 3, 8, align=64) == [64 * i for i in range(9)]
     b = ldist.row_bounds(256 ** 3, 3, align=256 * 256)
     assert b[0] == 0 and b[-1] == 256 ** 3 and all(x % 65536 == 0 for x in b) and all(b[i] < b[i + 1] for i in range(3))
+
+
+def test_row_bounds_balanced_by_streamed_bytes():
+    """contiguous row blocks balanced by nnz (bytes streamed per iteration), not by row count."""
+    from liblcg_b200 import dist as ldist, stencil
+    # a matrix whose second half is eight times denser: the cut moves towards the dense half's start
+    lens = np.concatenate([np.full(500, 2), np.full(500, 16)])
+    rp = np.zeros(1001, dtype=np.int64)
+    np.cumsum(lens, out=rp[1:])
+    b = ldist.row_bounds_nnz(rp, 2)
+    w = ldist.NNZ_BYTES * rp + ldist.ROW_OVERHEAD_BYTES * np.arange(1001)
+    assert 500 < b[1] < 1000 and abs(2 * w[b[1]] - w[-1]) <= 2 * (ldist.NNZ_BYTES * 16 + ldist.ROW_OVERHEAD_BYTES)
+    assert ldist.row_bounds_nnz(rp, 1) == [0, 1000]
+    b4 = ldist.row_bounds_nnz(rp, 4, align=10)
+    assert b4[0] == 0 and b4[-1] == 1000 and all(x % 10 == 0 for x in b4) and all(b4[i] <= b4[i + 1] for i in range(4))
+    # the analytic plane counts of the stencils are the generated matrices' row pointers at the plane edges
+    for kind in ("7pt", "27pt", "7pt_cd"):
+        for g in (5, 8):
+            S = stencil.make_system(kind, g)
+            assert np.array_equal(ldist.stencil_row_ptr_planes(kind, g), S["row_ptr"].astype(np.int64)[::g * g])
+    # whole planes per rank, every rank non-empty, within one plane of the byte-balanced cut
+    for world in (2, 3, 5, 8):
+        bs = ldist.stencil_bounds("27pt", 32, world)
+        assert bs[0] == 0 and bs[-1] == 32 ** 3 and all(x % 1024 == 0 for x in bs) and all(bs[i] < bs[i + 1] for i in range(world))
