@@ -115,6 +115,27 @@ int coop_grid_full(const void* kernel, int block)
 	return sms * per_sm;
 }
 
+cudaError_t launch_coop_pdl(const void* kern, int grid, int block, void** args, cudaStream_t s)
+{
+	static int combo = [] { const char* e = getenv("LCGB200_VEC2_PDL"); return e ? atoi(e) : 1; }();   // 0 once refused
+	if (combo && pdl_enabled())
+	{
+		cudaLaunchConfig_t cfg = {};
+		cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+		cudaLaunchAttribute attr[2];
+		attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;
+		attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[1].val.programmaticStreamSerializationAllowed = 1;
+		cfg.attrs = attr; cfg.numAttrs = 2;
+		const cudaError_t e = cudaLaunchKernelExC(&cfg, kern, args);
+		if (e == cudaSuccess) return e;
+		(void)cudaGetLastError();
+		combo = 0;
+		static const bool dbg = getenv("LCGB200_DEBUG_L2") != nullptr;
+		if (dbg) fprintf(stderr, "[lcgb200] cooperative + programmatic launch refused (%s): plain cooperative launches from here on\n", cudaGetErrorString(e));
+	}
+	return cudaLaunchCooperativeKernel(kern, dim3((unsigned)grid), dim3((unsigned)block), args, 0, s);
+}
+
 bool fuse_vec2(size_t n_local)
 {
 	int mode = settings().fuse_vec2;

@@ -127,6 +127,9 @@ struct Settings {
 };
 bool reference_order();
 long long spin_timeout_ms();
+// cooperative launch that also carries the programmatic-stream-serialisation attribute when PDL is active for this solve
+// (the kernel starts with pdl_enter()); falls back to the plain cooperative launch if the driver refuses the combination
+cudaError_t launch_coop_pdl(const void* kern, int grid, int block, void** args, cudaStream_t s);
 bool fuse_vec2(size_t n_local);
 int coop_grid_full(const void* kernel, int block);   // all co-resident blocks of a kernel on the current device (engine.cu)
 Settings& settings();
@@ -243,7 +246,7 @@ public:
 			const int limit = coop_grid_full(kern, kThreads);
 			if (grid > limit) grid = limit;
 			cudaEvent_t pe = profiling ? prof_begin(1) : nullptr;
-			LCG_CUDA_CHECK(cudaLaunchCooperativeKernel(kern, dim3((unsigned)grid), dim3(kThreads), args, 0, stream));
+			LCG_CUDA_CHECK(launch_coop_pdl(kern, grid, kThreads, args, stream));
 			prof_end(pe);
 			launches++;
 			if (push) pushed_vec = out;
