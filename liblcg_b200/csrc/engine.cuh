@@ -172,6 +172,7 @@ public:
 	// L2 residency of the work vectors (mid-size systems whose vectors fit the 126 MB L2 while the matrix does not): the
 	// arena becomes a persisting access-policy window of the solve's stream for the duration of the solve
 	bool l2_window_set = false;
+	size_t l2_prev_limit = 0;      // the device's persisting carve-out before this solve changed it
 	void l2_window_begin();
 	void l2_window_end();
 	std::vector<void*> allocs;     // every vector handed out, in order (lcg()/lcgs() copy their work vectors back to the caller)

@@ -19,8 +19,22 @@ namespace cg = cooperative_groups;
 constexpr int kSmallRows = 65536;      // systems up to this many rows ...
 constexpr int kSmallNnz = 1 << 21;     // ... and non-zeros take the fused path (matrix + vectors stay L2-resident)
 
+// A phase that ends in a reduction needs TWO things from the grid: the totals (every block's partial) and a barrier (the
+// next phase reads what other blocks wrote and the scalars the epilogue produced).  Both are one round: a block's arrival
+// at the reduction ticket IS its arrival at the barrier; the block that arrives last totals the partials, runs the scalar
+// epilogue and opens the gate (DevState::gate, a monotonic counter) the others spin on — instead of a reduction round
+// followed by a separate grid.sync() round (each ~2 us on 148-296 blocks, which is what an iteration of a 10^4-row system is
+// made of).  Returns after the gate has opened; `gate` is the block's private copy of the counter.
+__device__ __forceinline__ void gate_open(DevState* st, int next) { __threadfence(); st_release_gpu_s32(&st->gate, next); }
+__device__ __forceinline__ void gate_wait(DevState* st, int& gate)
+{
+	if (threadIdx.x == 0) { const int g0 = gate; while (ld_acquire_gpu_s32(&st->gate) == g0) { } }
+	gate++;
+	__syncthreads();
+}
+
 template <class Op>
-__device__ __forceinline__ void phase_vec(Op& op, size_t n, DevState* st, double* partials)
+__device__ __forceinline__ void phase_vec(Op& op, size_t n, DevState* st, double* partials, int& gate)
 {
 	if (!op.active(st)) return;   // uniform across the grid: st only changes right before a barrier everyone passed
 	op.begin(st);
@@ -40,14 +54,17 @@ __device__ __forceinline__ void phase_vec(Op& op, size_t n, DevState* st, double
 	{
 		double tot[Op::NRED > 0 ? Op::NRED : 1];
 		if (grid_reduce<(Op::NRED > 0 ? Op::NRED : 1)>(acc, partials, &st->ticket, tot))
-			if ((threadIdx.x & 31) == 0) op.finish(st, tot);
+		{
+			if ((threadIdx.x & 31) == 0) { op.finish(st, tot); gate_open(st, gate + 1); }
+		}
+		gate_wait(st, gate);
 	}
 }
 
 // y = op(A) x straight out of L2: `lpr` lanes per row (run-time here), the same per-lane accumulation order and
 // butterfly as k_spmv, so a row sum is bitwise what the streaming kernel produces
 template <class T, bool CONJ, class Epi>
-__device__ __forceinline__ void phase_spmv(const CsrDev<T>& A, const T* x, T* y, Epi& epi, DevState* st, double* partials)
+__device__ __forceinline__ void phase_spmv(const CsrDev<T>& A, const T* x, T* y, Epi& epi, DevState* st, double* partials, int& gate)
 {
 	epi.begin(st);
 	double acc[Epi::NRED > 0 ? Epi::NRED : 1];
@@ -95,7 +112,10 @@ __device__ __forceinline__ void phase_spmv(const CsrDev<T>& A, const T* x, T* y,
 	{
 		double tot[Epi::NRED > 0 ? Epi::NRED : 1];
 		if (grid_reduce<(Epi::NRED > 0 ? Epi::NRED : 1)>(acc, partials, &st->ticket, tot))
-			if ((threadIdx.x & 31) == 0) epi.finish(st, tot);
+		{
+			if ((threadIdx.x & 31) == 0) { epi.finish(st, tot); gate_open(st, gate + 1); }
+		}
+		gate_wait(st, gate);
 	}
 }
 
@@ -103,21 +123,26 @@ __device__ __forceinline__ void phase_spmv(const CsrDev<T>& A, const T* x, T* y,
 template <class T, bool CONJ, class Epi>
 struct SpmvPhase {
 	CsrDev<T> A; const T* x; T* y; Epi epi;
-	__device__ void run(DevState* st, double* partials) { Epi e = epi; phase_spmv<T, CONJ, Epi>(A, x, y, e, st, partials); }
+	static constexpr bool GATED = Epi::NRED > 0;   // the phase ends in a reduction whose gate is its barrier
+	__device__ void run(DevState* st, double* partials, int& gate) { Epi e = epi; phase_spmv<T, CONJ, Epi>(A, x, y, e, st, partials, gate); }
 	int rows() const { return A.n_rows * A.lpr; }
 };
 template <class Op>
 struct VecPhase {
 	Op op; size_t n;
-	__device__ void run(DevState* st, double* partials) { Op o = op; phase_vec(o, n, st, partials); }
+	static constexpr bool GATED = Op::NRED > 0;
+	__device__ void run(DevState* st, double* partials, int& gate) { Op o = op; phase_vec(o, n, st, partials, gate); }
 	int rows() const { return (int)(n / Op::W); }
 };
 
 template <class P>
-__device__ __forceinline__ void run_phase(P& p, DevState* st, double* partials, cg::grid_group& grid)
+__device__ __forceinline__ void run_phase(P& p, DevState* st, double* partials, cg::grid_group& grid, int& gate)
 {
-	if (!st_done(st)) p.run(st, partials);   // like the streaming kernels: nothing happens once the solve is over
-	grid.sync();
+	// like the streaming kernels, nothing happens once the solve is over (`done` only changes right before a barrier every
+	// block has passed, so the decision is uniform across the grid)
+	if (st_done(st)) return;
+	p.run(st, partials, gate);
+	if (!P::GATED) grid.sync();
 }
 
 // `iters` iterations of the phase list per launch (cooperative: the whole grid is co-resident)
@@ -125,10 +150,11 @@ template <class... Ph>
 __global__ void __launch_bounds__(kThreads) k_fused(DevState* st, double* partials, int iters, Ph... ph)
 {
 	cg::grid_group grid = cg::this_grid();
+	int gate = ld_acquire_gpu_s32(&st->gate);   // no block can open a gate before every block has arrived at the first reduction
 	for (int it = 0; it < iters; it++)
 	{
 		if (st_done(st)) return;   // `done` only changes right before a barrier every block has passed: a uniform decision
-		(run_phase(ph, st, partials, grid), ...);
+		(run_phase(ph, st, partials, grid, gate), ...);
 	}
 }
 

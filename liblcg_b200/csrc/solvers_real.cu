@@ -637,6 +637,9 @@ static int run_spg(Engine& E, const Operator<double>& A, double* m, const double
 			E.vec_push(OpSpgTrial{{}, m, d, mn, alpha}, n, mn);
 			E.spmv(A, mn, Ad, EpiSpgQ{B});
 			E.read_state();
+			// the loop head of the previous iteration (read here for the first time when no progress callback forces a round
+			// trip of its own) may have ended the solve: everything enqueued since then was a no-op
+			if (E.h_st->done) return E.sync_always();
 			const double qk = E.h_st->sc[SC_QK], gd = E.h_st->sc[SC_GD];
 			t_now = E.h_st->t;
 			const double amod = para.sigma * alpha * gd;
@@ -647,7 +650,9 @@ static int run_spg(Engine& E, const Operator<double>& A, double* m, const double
 			if (!(alpha > 0.0) || alpha < 1e-300) { qm[(size_t)((t_now + 1) % para.maxi_m)] = qk; break; }	// guard: the reference would spin forever
 		}
 		E.vec(OpPgUpdate{{}, m, g, mn, Ad, B}, n);
-		return E.sync_always();
+		// one host round trip per line-search trial is inherent (the search is data dependent); the loop head needs a second
+		// one only when a progress callback must see it — otherwise the next iteration's first trial reads it
+		return E.pf ? E.sync_always() : false;
 	});
 }
 
