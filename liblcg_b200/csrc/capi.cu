@@ -3,6 +3,7 @@
 // adaptors that let user Ax/Mx callbacks (cuSPARSE descriptors) drive the same engine.
 #include "solvers.cuh"
 #include "ic0_host.h"
+#include "pat_host.h"
 #include <dlfcn.h>
 #include <cstring>
 #include <string>
@@ -214,15 +215,38 @@ __global__ void k_pat_assign(int n_rows, const int* __restrict__ rp, const unsig
 	pat[row] = (unsigned char)id_of_slot[slot];
 }
 
-// Row-pattern copy on top of the dictionary codes.  Leaves the handle without it when there are more than 256 distinct
-// rows, a row longer than 64 entries, or a table larger than shared memory.
+// pat_item[it] = the pattern id shared by ALL rows of warp work item `it` of k_spmv_pat (rows (a R + q) S + 32 ib + lane,
+// q < R, lanes with 32 ib + lane < S), 255 when a row is missing (beyond n_rows) or the ids differ
+__global__ void k_pat_items(long long n_rows, int S, int nib, int n_items, const unsigned char* __restrict__ pat, unsigned char* __restrict__ item)
+{
+	const int it = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+	if (it >= n_items) return;
+	const int a = it / nib, ib = it - a * nib;
+	const int i = ib * 32 + lane;
+	int p0 = -1; bool bad = false;
+	if (i < S)
+		for (int q = 0; q < kPatRows; q++)
+		{
+			const long long row = ((long long)a * kPatRows + q) * S + i;
+			const int pq = row < n_rows ? (int)pat[row] : -1;
+			if (q == 0) p0 = pq;
+			bad = bad || pq < 0 || pq != p0;
+		}
+	const int first = __shfl_sync(0xffffffffu, p0, 0);   // lane 0 always has 32 ib < S
+	bad = bad || (i < S && p0 != first);
+	const bool any_bad = __any_sync(0xffffffffu, bad);
+	if (lane == 0) item[it] = (unsigned char)(any_bad ? 255 : first);
+}
+
+// Row-pattern copy on top of the dictionary codes.  Leaves the handle without it when there are more than 255 distinct
+// rows, a row longer than 64 entries, or a chain table larger than shared memory.
 void try_patterns(CsrHandle* h, const std::vector<int>& rp_h, const std::vector<double>& vd, const std::vector<int>& od)
 {
 	const int n = h->n_rows;
 	unsigned long long* d_key = dev_alloc<unsigned long long>(kPatTab);
 	int* d_rep = dev_alloc<int>(kPatTab); int* d_slot = dev_alloc<int>((size_t)n); int* d_fail = dev_alloc<int>(1);
 	int* d_id = dev_alloc<int>(kPatTab); unsigned char* d_pat = dev_alloc<unsigned char>((size_t)n);
-	int* d_len = nullptr; double2* d_ent = nullptr;
+	PatInfo* d_info = nullptr; PatChain* d_chain = nullptr; unsigned char* d_item = nullptr;
 	bool ok = false;
 	try
 	{
@@ -242,37 +266,66 @@ void try_patterns(CsrHandle* h, const std::vector<int>& rp_h, const std::vector<
 			for (int s = 0; s < kPatTab; s++) if (rep[(size_t)s] != 0x7fffffff) { id[(size_t)s] = (int)reps.size(); reps.push_back(rep[(size_t)s]); }
 			int maxlen = 0;
 			for (int r : reps) maxlen = std::max(maxlen, rp_h[(size_t)r + 1] - rp_h[(size_t)r]);
-			if (reps.size() <= 256 && maxlen >= 1 && maxlen <= 64 && (long long)reps.size() * maxlen <= kPatMaxEntries)
+			if (reps.size() <= 255 && maxlen >= 1 && maxlen <= 64)
 			{
 				LCG_CUDA_CHECK(cudaMemcpy(d_id, id.data(), sizeof(int) * kPatTab, cudaMemcpyHostToDevice));
 				k_pat_assign<<<(n + 255) / 256, 256>>>(n, h->row_ptr, h->code, d_slot, d_id, d_rep, d_pat, d_fail);
 				LCG_CUDA_CHECK(cudaGetLastError());
 				LCG_CUDA_CHECK(cudaMemcpy(&fail, d_fail, sizeof(int), cudaMemcpyDeviceToHost));
 				if (!fail)
-				{	// the table: decode each representative row through the dictionaries
-					struct Ent { double v; int off; int pad; };
-					std::vector<Ent> ent(reps.size() * (size_t)maxlen, Ent{0.0, 0, 0});
-					std::vector<int> len(reps.size());
+				{	// decode each representative row through the dictionaries, pick the stride on the longest one, build the chains
+					std::vector<std::vector<std::pair<int, double>>> rows(reps.size());
 					std::vector<unsigned short> cbuf((size_t)maxlen);
+					size_t longest = 0;
 					for (size_t p = 0; p < reps.size(); p++)
 					{
-						const int r = reps[p], kb = rp_h[(size_t)r];
-						len[p] = rp_h[(size_t)r + 1] - kb;
-						if (len[p] > 0) LCG_CUDA_CHECK(cudaMemcpy(cbuf.data(), h->code + kb, sizeof(unsigned short) * (size_t)len[p], cudaMemcpyDeviceToHost));
-						for (int j = 0; j < len[p]; j++) ent[p * (size_t)maxlen + (size_t)j] = Ent{vd[cbuf[(size_t)j] & 255u], od[cbuf[(size_t)j] >> 8], 0};
+						const int r = reps[p], kb = rp_h[(size_t)r], len = rp_h[(size_t)r + 1] - kb;
+						if (len > 0) LCG_CUDA_CHECK(cudaMemcpy(cbuf.data(), h->code + kb, sizeof(unsigned short) * (size_t)len, cudaMemcpyDeviceToHost));
+						for (int j = 0; j < len; j++) rows[p].push_back({od[cbuf[(size_t)j] >> 8], vd[cbuf[(size_t)j] & 255u]});
+						if (rows[p].size() > rows[longest].size()) longest = p;
 					}
-					d_len = dev_alloc<int>(reps.size()); d_ent = dev_alloc<double2>(ent.size());
-					LCG_CUDA_CHECK(cudaMemcpy(d_len, len.data(), sizeof(int) * len.size(), cudaMemcpyHostToDevice));
-					LCG_CUDA_CHECK(cudaMemcpy(d_ent, ent.data(), sizeof(Ent) * ent.size(), cudaMemcpyHostToDevice));
-					h->pat = d_pat; h->pat_len = d_len; h->pat_ent = d_ent; h->n_pat = (int)reps.size(); h->pat_maxlen = maxlen;
-					ok = true;
+					static const char* s_env = getenv("LCGB200_PAT_STRIDE");   // experiments: force the stride (>= 32)
+					int S = pat_pick_stride(rows[longest], n, kPatRows, kPatDefaultStride);
+					if (s_env && atoi(s_env) >= 32) S = atoi(s_env);
+					std::vector<std::vector<PatChainH>> chains(reps.size());
+					std::vector<PatInfo> info(reps.size());
+					size_t maxch = 1;
+					for (size_t p = 0; p < reps.size(); p++)
+					{
+						int t0 = -1;
+						pat_build_chains(rows[p], S, chains[p], &t0);
+						info[p].info = (int)chains[p].size() | ((t0 + 1) << 8);
+						maxch = std::max(maxch, chains[p].size());
+					}
+					{
+						std::vector<int> sup; std::vector<unsigned long long> mask;
+						pat_build_masks(rows, chains, S, sup, mask);
+						for (size_t p = 0; p < reps.size(); p++) { info[p].sup = sup[p]; info[p].mask = mask[p]; }
+					}
+					const long long n_super = ((long long)n + S - 1) / S;
+					const long long n_a = (n_super + kPatRows - 1) / kPatRows, nib = (S + 31) / 32;
+					if (reps.size() * maxch <= (size_t)kPatMaxChains && n_a * nib < 0x7fffffffLL / 32)
+					{
+						std::vector<PatChainH> tab(reps.size() * maxch, PatChainH{{0.0, 0.0, 0.0}, 0, 0});
+						for (size_t p = 0; p < reps.size(); p++) std::copy(chains[p].begin(), chains[p].end(), tab.begin() + (ptrdiff_t)(p * maxch));
+						const int n_items = (int)(n_a * nib);
+						d_info = dev_alloc<PatInfo>(reps.size()); d_chain = dev_alloc<PatChain>(tab.size()); d_item = dev_alloc<unsigned char>((size_t)n_items);
+						LCG_CUDA_CHECK(cudaMemcpy(d_info, info.data(), sizeof(PatInfo) * info.size(), cudaMemcpyHostToDevice));
+						LCG_CUDA_CHECK(cudaMemcpy(d_chain, tab.data(), sizeof(PatChainH) * tab.size(), cudaMemcpyHostToDevice));
+						k_pat_items<<<(unsigned)(((long long)n_items * 32 + 255) / 256), 256>>>(n, S, (int)nib, n_items, d_pat, d_item);
+						LCG_CUDA_CHECK(cudaGetLastError());
+						LCG_CUDA_CHECK(cudaDeviceSynchronize());
+						h->pat = d_pat; h->pat_item = d_item; h->pat_info = d_info; h->pat_chain = d_chain; h->n_pat = (int)reps.size();
+						h->pat_maxch = (int)maxch; h->pat_stride = S; h->pat_nib = (int)nib; h->pat_items = n_items;
+						ok = true;
+					}
 				}
 			}
 		}
 	}
-	catch (...) { cudaFree(d_key); cudaFree(d_rep); cudaFree(d_slot); cudaFree(d_fail); cudaFree(d_id); cudaFree(d_pat); cudaFree(d_len); cudaFree(d_ent); throw; }
+	catch (...) { cudaFree(d_key); cudaFree(d_rep); cudaFree(d_slot); cudaFree(d_fail); cudaFree(d_id); cudaFree(d_pat); cudaFree(d_info); cudaFree(d_chain); cudaFree(d_item); throw; }
 	cudaFree(d_key); cudaFree(d_rep); cudaFree(d_slot); cudaFree(d_fail); cudaFree(d_id);
-	if (!ok) cudaFree(d_pat);
+	if (!ok) { cudaFree(d_pat); cudaFree(d_info); cudaFree(d_chain); cudaFree(d_item); }
 }
 
 // LCGB200_CSR_COMPRESS: if the matrix has <= 256 distinct values and <= 256 distinct (col - row) offsets, store a second
@@ -474,7 +527,7 @@ void destroy_handle(CsrHandle* h)
 	cudaFree(h->row_ptr); cudaFree(h->col); cudaFree(h->val); cudaFree(h->tiles);
 	cudaFree(h->t_row_ptr); cudaFree(h->t_col); cudaFree(h->t_val); cudaFree(h->t_tiles);
 	cudaFree(h->code); cudaFree(h->vdict); cudaFree(h->odict); cudaFree(h->dtiles);
-	cudaFree(h->pat); cudaFree(h->pat_len); cudaFree(h->pat_ent);
+	cudaFree(h->pat); cudaFree(h->pat_item); cudaFree(h->pat_info); cudaFree(h->pat_chain);
 	free_factor(h->icL); free_factor(h->icU); cudaFree(h->ic_tmp);
 	cudaFree(h->diag); cudaFree(h->ws);
 	cudaFree(h->d_state); cudaFree(h->d_partials);

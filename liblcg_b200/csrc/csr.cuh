@@ -62,8 +62,9 @@ struct CsrDev {
 	const double* vdict = nullptr; const int* odict = nullptr;
 	const int4* dtiles = nullptr; int n_dtiles = 0, dchunk = 1, dlpr = 1;
 	// row-pattern copy (real operators, optional): one pattern id per ROW + a table of the distinct rows
-	const unsigned char* pat = nullptr; const int* pat_len = nullptr; const double2* pat_ent = nullptr;   // entry = {value, (double)offset bits}
-	int n_pat = 0, pat_maxlen = 0;
+	// (csr.cuh "row-pattern operator": chains of offsets S apart, one byte per warp work item)
+	const unsigned char* pat = nullptr; const unsigned char* pat_item = nullptr; const void* pat_info = nullptr; const void* pat_chain = nullptr;
+	int n_pat = 0, pat_maxch = 0, pat_stride = 0, pat_nib = 0, pat_items = 0;
 };
 
 template <class T> struct TileCfg;
@@ -549,29 +550,62 @@ __global__ void __launch_bounds__(kSpmvThreads, kSpmvCtasPerSm) k_spmv_dict(CsrD
 // Constant-coefficient discretisations have only a handful of DISTINCT ROWS once a row is written as its sequence of
 // (col - row, value) pairs: interior, faces, edges, corners (27 for a 3-D stencil; a few more after the ghost remap of a
 // row block).  Such a matrix is stored a third time as ONE BYTE PER ROW (its pattern id) plus the table of patterns:
-// the SpMV streams x, y and n bytes of ids — the 12 bytes per non-zero of CSR disappear.  One thread per row walks its
-// pattern out of shared memory (lanes of a warp mostly share the pattern: broadcast reads) and gathers x of 32
-// consecutive rows per instruction (2 lines).  Entries are accumulated left to right with fma: the reference's own
-// order (algebra.cpp-style serial row sums).  Rows are dealt to blocks in chunks of kPatChunk consecutive rows so that
-// neighbouring grid lines are re-used out of L1.
-constexpr int kPatChunk = 2048;
-constexpr int kPatRowsPerThread = 4;   // rows a thread handles together (kPatChunk = 2 x 256 x 4)
-constexpr int kPatMaxEntries = 3072;   // pattern table entries held in shared memory (48 KB)
-struct PatEntry { double v; int off; int pad; };
+// the SpMV streams x, y and n bytes of ids — the 12 bytes per non-zero of CSR disappear, and what bounds the kernel is
+// the number of gathers the load/store pipe has to serve (round 1: 27 per row, LSU data pipe 84 % busy, 0.2 of HBM).
+//
+// Round 2: gathers shared in REGISTERS.  The entries of a pattern are grouped into CHAINS: up to kPatChainLen offsets in
+// arithmetic progression with the matrix-wide stride S (for a 3-D stencil S = nx: the entries (dx, dz) fixed, dy = -1, 0,
+// +1).  A thread owns R rows that are S apart (row, row + S, ..., row + (R-1) S: a column of R grid points in y), so the
+// x values one chain needs for all R rows are R + m - 1 loads instead of R * m — x[row + off + u S] serves row q = u - t
+// through chain entry t.  27-point stencil, R = 8: 9 chains x 10 loads for 8 rows = 11.25 gathers per row instead of 27,
+// and one 32-byte table read per chain instead of one per entry.  Lanes of a warp sit on 32 consecutive rows, so every
+// gather is 32 consecutive doubles (2-3 lines), every store a full 256-byte line.
+//
+// Work item of a warp = R x 32 rows: rows (A R + q) S + 32 ib + lane.  A byte per ITEM (pat_item) says whether all its
+// rows exist and share one pattern (the rule inside a stencil): then the warp does not even read the per-row ids and all
+// table reads are broadcasts.  Otherwise each thread looks at its own R rows: same pattern -> the chain path with a
+// per-lane pattern; patterns that are SUBSETS of one longer pattern (a column of grid points that starts on a face: the
+// face row is the interior row minus the entries that leave the grid; pat_host.h: pat_build_masks) -> the longer pattern's
+// chains with a 64-bit presence mask per row, loads still shared; anything else row by row through the same chain table.
+// Entries are accumulated chain by chain with fma (a different order from the CSR row order: y agrees with the plain
+// copy to rounding, not bitwise).
+constexpr int kPatRows = 8;            // R: rows (S apart) a thread computes together
+constexpr int kPatChainLen = 3;        // entries per chain (v[3])
+constexpr int kPatMaxChains = 3072;    // chain table entries held in shared memory (96 KB)
+constexpr int kPatDefaultStride = 256; // S when no pair of offsets repeats (all chains have one entry)
+struct __align__(16) PatChain { double v[kPatChainLen]; int off; int m; };   // 32 bytes: two 128-bit shared-memory reads
+static_assert(sizeof(PatChain) == 32, "PatChain is read as two 16-byte words");
+// per pattern: presence mask over the chains of pattern `sup` (bit 3 c + t), chains | (index of offset 0 in chain 0, +1) << 8
+struct __align__(16) PatInfo { unsigned long long mask; int info; int sup; };
+
+__device__ __forceinline__ void pat_chain_load(const PatChain* c, double& v0, double& v1, double& v2, int& off, int& m)
+{
+	const double2 a = reinterpret_cast<const double2*>(c)[0];
+	const double2 b = reinterpret_cast<const double2*>(c)[1];
+	v0 = a.x; v1 = a.y; v2 = b.x;
+	const long long om = __double_as_longlong(b.y);
+	off = (int)(om & 0xffffffffll); m = (int)(om >> 32);
+}
 
 template <class Epi>
-__global__ void __launch_bounds__(kThreads) k_spmv_pat(CsrDev<double> A, const double* __restrict__ x, double* __restrict__ y, Epi epi_in,
+__global__ void __launch_bounds__(kThreads, 3) k_spmv_pat(CsrDev<double> A, const double* __restrict__ x, double* __restrict__ y, Epi epi_in,
 	DevState* st, double* partials)
 {
 	pdl_enter();
 	if (st_done(st)) return;
-	extern __shared__ __align__(16) unsigned char smem[];
-	PatEntry* s_ent = reinterpret_cast<PatEntry*>(smem);
-	int* s_len = reinterpret_cast<int*>(smem + (size_t)A.n_pat * A.pat_maxlen * sizeof(PatEntry));
-	const int n_ent = A.n_pat * A.pat_maxlen;
-	const PatEntry* g_ent = reinterpret_cast<const PatEntry*>(A.pat_ent);
-	for (int i = threadIdx.x; i < n_ent; i += blockDim.x) s_ent[i] = g_ent[i];
-	for (int i = threadIdx.x; i < A.n_pat; i += blockDim.x) s_len[i] = A.pat_len[i];
+	constexpr int R = kPatRows;
+	extern __shared__ __align__(128) unsigned char smem[];
+	PatChain* s_ch = reinterpret_cast<PatChain*>(smem);
+	const int n_ch = A.n_pat * A.pat_maxch;
+	PatInfo* s_info = reinterpret_cast<PatInfo*>(smem + (size_t)n_ch * sizeof(PatChain));
+	{
+		const double2* g = reinterpret_cast<const double2*>(A.pat_chain);
+		double2* s = reinterpret_cast<double2*>(smem);
+		for (int i = threadIdx.x; i < 2 * n_ch; i += blockDim.x) s[i] = g[i];
+		const double2* gi = reinterpret_cast<const double2*>(A.pat_info);
+		double2* si = reinterpret_cast<double2*>(s_info);
+		for (int i = threadIdx.x; i < A.n_pat; i += blockDim.x) si[i] = gi[i];
+	}
 	__syncthreads();
 
 	Epi epi = epi_in;
@@ -579,81 +613,155 @@ __global__ void __launch_bounds__(kThreads) k_spmv_pat(CsrDev<double> A, const d
 	double acc[Epi::NRED > 0 ? Epi::NRED : 1];
 #pragma unroll
 	for (int r = 0; r < (Epi::NRED > 0 ? Epi::NRED : 1); r++) acc[r] = 0.0;
-	const int n_chunks = (A.n_rows + kPatChunk - 1) / kPatChunk;
-	constexpr int R = kPatRowsPerThread;
-	for (int c = blockIdx.x; c < n_chunks; c += gridDim.x)
+
+	const int S = A.pat_stride, nib = A.pat_nib, n_items = A.pat_items, maxch = A.pat_maxch;
+	const long long n_rows = A.n_rows;
+	const size_t Ss = (size_t)S;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	constexpr int WPB = kThreads / 32;
+	for (int it = blockIdx.x * WPB + warp; it < n_items; it += gridDim.x * WPB)
 	{
-		const int end = min((c + 1) * kPatChunk, A.n_rows);
-		for (int row0 = c * kPatChunk + threadIdx.x; row0 < end; row0 += kThreads * R)
+		const int a = it / nib, ib = it - a * nib;
+		const int i = ib * 32 + lane;
+		if (i >= S) continue;
+		const long long row0 = (long long)a * R * S + i;
+		const int uni = (int)A.pat_item[it];   // warp-uniform: pattern id shared by the whole item, 255 = mixed
+		int p = uni;
+		bool chained = true, masked = false;
+		unsigned long long mk[R];
+		if (uni == 255)
 		{
-			// R rows per thread (row0, row0 + 256, ...): when they share the pattern — the rule inside a stencil — every table
-			// entry is read once and used for R gathers, which takes a third of the load off the LSU data pipe
-			int p[R]; bool same = true, all_in = true;
+			int p0 = -1, sup = -1;
+			masked = true;
 #pragma unroll
 			for (int q = 0; q < R; q++)
 			{
-				const int row = row0 + q * kThreads;
-				const bool in = row < end;
-				p[q] = in ? (int)A.pat[row] : -1;
-				all_in = all_in && in;
-				same = same && (p[q] == p[0]);
-			}
-			if (all_in && same)
-			{
-				const int len = s_len[p[0]];
-				const PatEntry* e = s_ent + p[0] * A.pat_maxlen;
-				const double* xr = x + row0;
-				double sum[R];
-#pragma unroll
-				for (int q = 0; q < R; q++) sum[q] = 0.0;
-				int j = 0;
-				for (; j + 3 <= len; j += 3)
-				{	// 3 entries x R rows = 3R independent gathers in flight
-					double xv[3][R];
-#pragma unroll
-					for (int u = 0; u < 3; u++)
-					{
-						const int off = e[j + u].off;
-#pragma unroll
-						for (int q = 0; q < R; q++) xv[u][q] = __ldg(xr + q * kThreads + off);
-					}
-#pragma unroll
-					for (int u = 0; u < 3; u++)
-					{
-						const double v = e[j + u].v;
-#pragma unroll
-						for (int q = 0; q < R; q++) sum[q] = fma(v, xv[u][q], sum[q]);
-					}
+				const long long row = row0 + (long long)q * S;
+				const int pq = row < n_rows ? (int)A.pat[row] : -1;
+				if (q == 0) p0 = pq;
+				chained = chained && pq >= 0 && pq == p0;
+				mk[q] = 0ull;
+				if (pq >= 0)
+				{	// rows beyond the matrix keep an empty mask: no loads, no store
+					const PatInfo pi = s_info[pq];
+					if (sup < 0) sup = pi.sup;
+					masked = masked && pi.sup == sup && pi.mask != 0ull;
+					mk[q] = pi.mask;
 				}
-				for (; j < len; j++)
-				{
-					const double v = e[j].v; const int off = e[j].off;
+			}
+			p = chained ? p0 : sup;
+		}
+		if (chained)
+		{
+			const int info = s_info[p].info;
+			const int nch = info & 255, t0 = (info >> 8) - 1;
+			const PatChain* ch = s_ch + p * maxch;
+			const double* xr = x + row0;
+			double sum[R], xc[R];
 #pragma unroll
-					for (int q = 0; q < R; q++) sum[q] = fma(v, __ldg(xr + q * kThreads + off), sum[q]);
+			for (int q = 0; q < R; q++) { sum[q] = 0.0; xc[q] = 0.0; }
+			for (int c = 0; c < nch; c++)
+			{
+				double v0, v1, v2; int off, m;
+				pat_chain_load(ch + c, v0, v1, v2, off, m);
+				const double* xb = xr + off;
+				double xl[R + 2];
+#pragma unroll
+				for (int u = 0; u < R; u++) xl[u] = __ldg(xb + u * Ss);
+				xl[R] = m > 1 ? __ldg(xb + R * Ss) : 0.0;
+				xl[R + 1] = m > 2 ? __ldg(xb + (R + 1) * Ss) : 0.0;
+				if (c == 0)
+				{	// chain 0 holds the diagonal when the row has one: keep x[row] for the epilogue
+#pragma unroll
+					for (int q = 0; q < R; q++) xc[q] = t0 == 0 ? xl[q] : (t0 == 1 ? xl[q + 1] : xl[q + 2]);
+				}
+#pragma unroll
+				for (int q = 0; q < R; q++) sum[q] = fma(v0, xl[q], sum[q]);
+				if (m > 1)
+				{
+#pragma unroll
+					for (int q = 0; q < R; q++) sum[q] = fma(v1, xl[q + 1], sum[q]);
+				}
+				if (m > 2)
+				{
+#pragma unroll
+					for (int q = 0; q < R; q++) sum[q] = fma(v2, xl[q + 2], sum[q]);
+				}
+			}
+			if (t0 < 0)
+			{
+#pragma unroll
+				for (int q = 0; q < R; q++) xc[q] = __ldg(xr + q * Ss);
+			}
+#pragma unroll
+			for (int q = 0; q < R; q++)
+			{
+				const long long row = row0 + (long long)q * S;
+				y[row] = sum[q];
+				epi.row((int)row, sum[q], xc[q], acc);
+			}
+		}
+		else if (masked && p >= 0)
+		{	// the chains of pattern p = sup, every row with its own presence mask
+			const int nch = s_info[p].info & 255;
+			const PatChain* ch = s_ch + p * maxch;
+			const double* xr = x + row0;
+			double sum[R];
+#pragma unroll
+			for (int q = 0; q < R; q++) sum[q] = 0.0;
+			for (int c = 0; c < nch; c++)
+			{
+				double v0, v1, v2; int off, m;
+				pat_chain_load(ch + c, v0, v1, v2, off, m);
+				const double* xb = xr + off;
+				unsigned int b[R + 2];
+#pragma unroll
+				for (int q = 0; q < R; q++) b[q] = (unsigned int)(mk[q] >> (kPatChainLen * c)) & 7u;
+				b[R] = 0u; b[R + 1] = 0u;
+				double xl[R + 2];
+#pragma unroll
+				for (int u = 0; u < R + 2; u++)
+				{
+					const unsigned int need = (b[u] & 1u) | (u >= 1 ? (b[u - 1] & 2u) : 0u) | (u >= 2 ? (b[u - 2] & 4u) : 0u);
+					xl[u] = need ? __ldg(xb + u * Ss) : 0.0;
 				}
 #pragma unroll
 				for (int q = 0; q < R; q++)
 				{
-					const int row = row0 + q * kThreads;
+					if (b[q] & 1u) sum[q] = fma(v0, xl[q], sum[q]);
+					if (b[q] & 2u) sum[q] = fma(v1, xl[q + 1], sum[q]);
+					if (b[q] & 4u) sum[q] = fma(v2, xl[q + 2], sum[q]);
+				}
+			}
+#pragma unroll
+			for (int q = 0; q < R; q++)
+			{
+				const long long row = row0 + (long long)q * S;
+				if (row < n_rows)
+				{
 					y[row] = sum[q];
-					epi.row(row, sum[q], __ldg(x + row), acc);
+					epi.row((int)row, sum[q], __ldg(x + row), acc);
 				}
 			}
-			else
+		}
+		else
+		{
+			for (int q = 0; q < R; q++)
 			{
-#pragma unroll
-				for (int q = 0; q < R; q++)
+				const long long row = row0 + (long long)q * S;
+				if (row >= n_rows) break;
+				const int pq = (int)A.pat[row];
+				const int nch = s_info[pq].info & 255;
+				const PatChain* ch = s_ch + pq * maxch;
+				const double* xr = x + row;
+				double sum = 0.0;
+				for (int c = 0; c < nch; c++)
 				{
-					if (p[q] < 0) continue;
-					const int row = row0 + q * kThreads;
-					const int len = s_len[p[q]];
-					const PatEntry* e = s_ent + p[q] * A.pat_maxlen;
-					const double* xr = x + row;
-					double sum = 0.0;
-					for (int j = 0; j < len; j++) sum = fma(e[j].v, __ldg(xr + e[j].off), sum);
-					y[row] = sum;
-					epi.row(row, sum, __ldg(xr), acc);
+					const int off = ch[c].off, m = ch[c].m;
+					for (int t = 0; t < m; t++) sum = fma(ch[c].v[t], __ldg(xr + off + t * Ss), sum);
 				}
+				y[row] = sum;
+				epi.row((int)row, sum, __ldg(xr), acc);
 			}
 		}
 	}
@@ -671,13 +779,13 @@ __global__ void __launch_bounds__(kThreads) k_spmv_pat(CsrDev<double> A, const d
 template <class Epi>
 inline void launch_spmv_pat(const CsrDev<double>& A, const double* x, double* y, const Epi& epi, DevState* st, double* partials, cudaStream_t s)
 {
-	const size_t smem = (size_t)A.n_pat * A.pat_maxlen * sizeof(PatEntry) + (size_t)A.n_pat * sizeof(int);
+	const size_t smem = (size_t)A.n_pat * A.pat_maxch * sizeof(PatChain) + (size_t)A.n_pat * sizeof(PatInfo);
 	auto kern = k_spmv_pat<Epi>;
 	static PerDeviceOnce once;
-	if (once.first()) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kPatMaxEntries * sizeof(PatEntry) + 1024));
-	const int n_chunks = (A.n_rows + kPatChunk - 1) / kPatChunk;
-	const int limit = spmv_grid_limit(4);
-	int grid = n_chunks < limit ? n_chunks : limit;
+	if (once.first()) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kPatMaxChains * sizeof(PatChain) + 256 * sizeof(PatInfo)));
+	const int n_blocks = (A.pat_items + kThreads / 32 - 1) / (kThreads / 32);
+	const int limit = spmv_grid_limit(3);
+	int grid = n_blocks < limit ? n_blocks : limit;
 	if (grid < 1) grid = 1;
 	launch_k(kern, grid, kThreads, smem, s, A, x, y, epi, st, partials);
 }

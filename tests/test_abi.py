@@ -108,6 +108,21 @@ def test_no_gpu_means_error_not_fallback():
         api.CsrOperator(rp, ci, v)
 
 
+def test_row_pattern_chains_and_tiling_on_cpu():
+    """liblcg_b200/csrc/pat_host.h (stride choice, chains, subset masks of the row-pattern operator copy) and the work-item
+    tiling of k_spmv_pat, emulated on the CPU by tests/cxx/pat_chain_check.cpp: every row written exactly once, no load out
+    of range, y equal to the CSR product, for cubes / bricks / a row block with ghost columns / matrices that take the
+    masked and the row-by-row paths."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cxx", "build", "pat_chain_check")
+    r = subprocess.run(["make", "-C", os.path.join(root, "tests", "cxx"), exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout[-3000:]
+
+
 def test_cxx_dropin_headers_compile():
     """include/lcg_b200/{util,lcg_cuda,clcg_cuda}.h: a liblcg user's program (tests/cxx/dropin_sample.cu) compiles and links
     against them for sm_100a; a second translation unit checks the reference's names, values and default arguments."""
