@@ -216,8 +216,10 @@ __global__ void k_pat_assign(int n_rows, const int* __restrict__ rp, const unsig
 }
 
 // pat_item[it] = the pattern id shared by ALL rows of warp work item `it` of k_spmv_pat (rows (a R + q) S + 32 ib + lane,
-// q < R, lanes with 32 ib + lane < S), 255 when a row is missing (beyond n_rows) or the ids differ
-__global__ void k_pat_items(long long n_rows, int S, int nib, int n_items, const unsigned char* __restrict__ pat, unsigned char* __restrict__ item)
+// q < R, lanes with 32 ib + lane < S), 255 when a row is missing (beyond n_rows) or the ids differ;
+// pat_thread[32 it + lane] = the same for the R rows of one thread
+__global__ void k_pat_items(long long n_rows, int S, int nib, int n_items, const unsigned char* __restrict__ pat, unsigned char* __restrict__ item,
+	unsigned char* __restrict__ thread_code)
 {
 	const int it = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
 	if (it >= n_items) return;
@@ -232,10 +234,50 @@ __global__ void k_pat_items(long long n_rows, int S, int nib, int n_items, const
 			if (q == 0) p0 = pq;
 			bad = bad || pq < 0 || pq != p0;
 		}
+	thread_code[(size_t)it * 32 + lane] = (unsigned char)((bad || p0 < 0) ? 255 : p0);
 	const int first = __shfl_sync(0xffffffffu, p0, 0);   // lane 0 always has 32 ib < S
 	bad = bad || (i < S && p0 != first);
 	const bool any_bad = __any_sync(0xffffffffu, bad);
 	if (lane == 0) item[it] = (unsigned char)(any_bad ? 255 : first);
+}
+
+// rows per pattern
+__global__ void k_pat_count(int n_rows, const unsigned char* __restrict__ pat, unsigned int* count)
+{
+	__shared__ unsigned int s_cnt[256];
+	s_cnt[threadIdx.x] = 0u;
+	__syncthreads();
+	for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (long long)gridDim.x * blockDim.x) atomicAdd(&s_cnt[pat[r]], 1u);
+	__syncthreads();
+	if (s_cnt[threadIdx.x]) atomicAdd(&count[threadIdx.x], s_cnt[threadIdx.x]);
+}
+
+// block items of k_spmv_pat_march, one block of 8 warps per item: bitem[16 bi + w] = the pattern all rows of warp w's item
+// share (255 = mixed, 254 = the item has no rows), bitem[16 bi + 8] = 1 when every existing row of the block item is a
+// subset of the geometry pattern gpat (sup == gpat with a non-empty mask)
+__global__ void k_pat_bitems(long long n_rows, int S, int wx, int wy, int nibb, int gpat, const unsigned char* __restrict__ pat,
+	const PatInfo* __restrict__ info, unsigned char* __restrict__ bitem)
+{
+	const long long bi = blockIdx.x;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const long long ab = bi / nibb; const int ibb = (int)(bi - ab * nibb);
+	const int wq = warp / wx, wi = warp % wx;
+	const long long row0 = ((ab * wy + wq) * kPatRows) * S + (long long)(ibb * wx + wi) * 32 + lane;
+	int p0 = -2; bool mixed = false, geo_bad = false, any_row = false;
+	for (int q = 0; q < kPatRows; q++)
+	{
+		const long long row = row0 + (long long)q * S;
+		const int pq = row < n_rows ? (int)pat[row] : -1;
+		if (q == 0) p0 = pq;
+		mixed = mixed || pq != p0 || pq < 0;
+		if (pq >= 0) { any_row = true; geo_bad = geo_bad || info[pq].sup != gpat || info[pq].mask == 0ull; }
+	}
+	const int first = __shfl_sync(0xffffffffu, p0, 0);
+	mixed = mixed || p0 != first;
+	const bool w_mixed = __any_sync(0xffffffffu, mixed), w_rows = __any_sync(0xffffffffu, any_row);
+	const int bad_block = __syncthreads_or(geo_bad ? 1 : 0);
+	if (lane == 0) bitem[16 * bi + warp] = (unsigned char)(!w_rows ? 254 : (w_mixed ? 255 : first));
+	if (threadIdx.x == 0) bitem[16 * bi + 8] = (unsigned char)(bad_block ? 0 : 1);
 }
 
 // Row-pattern copy on top of the dictionary codes.  Leaves the handle without it when there are more than 255 distinct
@@ -246,7 +288,8 @@ void try_patterns(CsrHandle* h, const std::vector<int>& rp_h, const std::vector<
 	unsigned long long* d_key = dev_alloc<unsigned long long>(kPatTab);
 	int* d_rep = dev_alloc<int>(kPatTab); int* d_slot = dev_alloc<int>((size_t)n); int* d_fail = dev_alloc<int>(1);
 	int* d_id = dev_alloc<int>(kPatTab); unsigned char* d_pat = dev_alloc<unsigned char>((size_t)n);
-	PatInfo* d_info = nullptr; PatChain* d_chain = nullptr; unsigned char* d_item = nullptr;
+	unsigned char* d_tab = nullptr; unsigned char* d_item = nullptr; unsigned char* d_thread = nullptr; unsigned char* d_bitem = nullptr; int4* d_segs = nullptr;
+	PatMarch* march = nullptr;
 	bool ok = false;
 	try
 	{
@@ -266,66 +309,129 @@ void try_patterns(CsrHandle* h, const std::vector<int>& rp_h, const std::vector<
 			for (int s = 0; s < kPatTab; s++) if (rep[(size_t)s] != 0x7fffffff) { id[(size_t)s] = (int)reps.size(); reps.push_back(rep[(size_t)s]); }
 			int maxlen = 0;
 			for (int r : reps) maxlen = std::max(maxlen, rp_h[(size_t)r + 1] - rp_h[(size_t)r]);
-			if (reps.size() <= 255 && maxlen >= 1 && maxlen <= 64)
+			if (reps.size() <= 253 && maxlen >= 1 && maxlen <= 64)
 			{
 				LCG_CUDA_CHECK(cudaMemcpy(d_id, id.data(), sizeof(int) * kPatTab, cudaMemcpyHostToDevice));
 				k_pat_assign<<<(n + 255) / 256, 256>>>(n, h->row_ptr, h->code, d_slot, d_id, d_rep, d_pat, d_fail);
 				LCG_CUDA_CHECK(cudaGetLastError());
 				LCG_CUDA_CHECK(cudaMemcpy(&fail, d_fail, sizeof(int), cudaMemcpyDeviceToHost));
 				if (!fail)
-				{	// decode each representative row through the dictionaries, pick the stride on the longest one, build the chains
-					std::vector<std::vector<std::pair<int, double>>> rows(reps.size());
+				{	// decode each representative row through the dictionaries, pick the stride on the longest one, build chains, plan, masks
+					const size_t np = reps.size();
+					std::vector<std::vector<std::pair<int, double>>> rows(np);
 					std::vector<unsigned short> cbuf((size_t)maxlen);
+					// the geometry pattern: the longest row, the most frequent one among equally long rows (the interior row of a
+					// stencil; on a row block the ghost-coupled rows of the first and last plane are as long but fewer)
+					std::vector<unsigned int> count(256, 0u);
+					{
+						unsigned int* d_count = reinterpret_cast<unsigned int*>(d_key);   // the hash table is not needed any more
+						LCG_CUDA_CHECK(cudaMemset(d_count, 0, 256 * sizeof(unsigned int)));
+						k_pat_count<<<592, 256>>>(n, d_pat, d_count);
+						LCG_CUDA_CHECK(cudaGetLastError());
+						LCG_CUDA_CHECK(cudaMemcpy(count.data(), d_count, 256 * sizeof(unsigned int), cudaMemcpyDeviceToHost));
+					}
 					size_t longest = 0;
-					for (size_t p = 0; p < reps.size(); p++)
+					for (size_t p = 0; p < np; p++)
 					{
 						const int r = reps[p], kb = rp_h[(size_t)r], len = rp_h[(size_t)r + 1] - kb;
 						if (len > 0) LCG_CUDA_CHECK(cudaMemcpy(cbuf.data(), h->code + kb, sizeof(unsigned short) * (size_t)len, cudaMemcpyDeviceToHost));
 						for (int j = 0; j < len; j++) rows[p].push_back({od[cbuf[(size_t)j] >> 8], vd[cbuf[(size_t)j] & 255u]});
-						if (rows[p].size() > rows[longest].size()) longest = p;
+						if (rows[p].size() > rows[longest].size() || (rows[p].size() == rows[longest].size() && count[p] > count[longest])) longest = p;
 					}
 					static const char* s_env = getenv("LCGB200_PAT_STRIDE");   // experiments: force the stride (>= 32)
 					int S = pat_pick_stride(rows[longest], n, kPatRows, kPatDefaultStride);
 					if (s_env && atoi(s_env) >= 32) S = atoi(s_env);
-					std::vector<std::vector<PatChainH>> chains(reps.size());
-					std::vector<PatInfo> info(reps.size());
+					std::vector<std::vector<PatChainH>> chains(np);
+					std::vector<PatInfo> info(np);
+					std::vector<int> t0s(np, -1);
 					size_t maxch = 1;
-					for (size_t p = 0; p < reps.size(); p++)
+					for (size_t p = 0; p < np; p++)
 					{
-						int t0 = -1;
-						pat_build_chains(rows[p], S, chains[p], &t0);
-						info[p].info = (int)chains[p].size() | ((t0 + 1) << 8);
+						pat_build_chains(rows[p], S, chains[p], &t0s[p]);
+						info[p].info = (int)chains[p].size() | ((t0s[p] + 1) << 8);
 						maxch = std::max(maxch, chains[p].size());
 					}
+					// 32-bit row and column arithmetic in the kernels: the last (partly empty) item and its reads stay below 2^31
+					const long long n_super = ((long long)n + S - 1) / S;
+					const long long n_a = (n_super + kPatRows - 1) / kPatRows, nib = (S + 31) / 32;
+					const bool fits32 = (long long)n + (long long)h->n_cols + (long long)(4 * kPatRows + 4) * S < 0x7fffffffLL - 64 && n_a * nib < 0x7fffffffLL / 32;
+					// the plane-marching kernel is opt-in (LCGB200_PAT_MARCH=1, read per handle): measured slower than the plain-load
+					// kernel on one B200 (profiles/README_r02.md), kept for systems whose x does not stay in L2
+					PatMarchH plan;
+					const char* m_env = getenv("LCGB200_PAT_MARCH");
+					if (fits32 && m_env && atoi(m_env) > 0) pat_plan_march(chains[longest], t0s[longest], S, n, h->n_cols, kPatRows, plan);   // reorders the geometry pattern's chains
 					{
 						std::vector<int> sup; std::vector<unsigned long long> mask;
 						pat_build_masks(rows, chains, S, sup, mask);
-						for (size_t p = 0; p < reps.size(); p++) { info[p].sup = sup[p]; info[p].mask = mask[p]; }
+						for (size_t p = 0; p < np; p++) { info[p].sup = sup[p]; info[p].mask = mask[p]; }
 					}
-					const long long n_super = ((long long)n + S - 1) / S;
-					const long long n_a = (n_super + kPatRows - 1) / kPatRows, nib = (S + 31) / 32;
-					if (reps.size() * maxch <= (size_t)kPatMaxChains && n_a * nib < 0x7fffffffLL / 32)
+					if (fits32 && np * maxch <= (size_t)kPatMaxChains)
 					{
-						std::vector<PatChainH> tab(reps.size() * maxch, PatChainH{{0.0, 0.0, 0.0}, 0, 0});
-						for (size_t p = 0; p < reps.size(); p++) std::copy(chains[p].begin(), chains[p].end(), tab.begin() + (ptrdiff_t)(p * maxch));
+						// one table: chains | info (the order the kernels expect)
+						std::vector<unsigned char> tab(np * maxch * sizeof(PatChainH) + np * sizeof(PatInfo), 0);
+						PatChainH* tc = reinterpret_cast<PatChainH*>(tab.data());
+						PatInfo* ti = reinterpret_cast<PatInfo*>(tab.data() + np * maxch * sizeof(PatChainH));
+						for (size_t p = 0; p < np; p++) { std::copy(chains[p].begin(), chains[p].end(), tc + p * maxch); ti[p] = info[p]; }
 						const int n_items = (int)(n_a * nib);
-						d_info = dev_alloc<PatInfo>(reps.size()); d_chain = dev_alloc<PatChain>(tab.size()); d_item = dev_alloc<unsigned char>((size_t)n_items);
-						LCG_CUDA_CHECK(cudaMemcpy(d_info, info.data(), sizeof(PatInfo) * info.size(), cudaMemcpyHostToDevice));
-						LCG_CUDA_CHECK(cudaMemcpy(d_chain, tab.data(), sizeof(PatChainH) * tab.size(), cudaMemcpyHostToDevice));
-						k_pat_items<<<(unsigned)(((long long)n_items * 32 + 255) / 256), 256>>>(n, S, (int)nib, n_items, d_pat, d_item);
+						d_tab = dev_alloc<unsigned char>(tab.size()); d_item = dev_alloc<unsigned char>((size_t)n_items); d_thread = dev_alloc<unsigned char>((size_t)n_items * 32);
+						LCG_CUDA_CHECK(cudaMemcpy(d_tab, tab.data(), tab.size(), cudaMemcpyHostToDevice));
+						k_pat_items<<<(unsigned)(((long long)n_items * 32 + 255) / 256), 256>>>(n, S, (int)nib, n_items, d_pat, d_item, d_thread);
 						LCG_CUDA_CHECK(cudaGetLastError());
+						if (plan.ok)
+						{
+							const long long n_ab = (n_a + plan.wy - 1) / plan.wy;
+							const int nibb = S / (32 * plan.wx);
+							const long long n_bi = n_ab * nibb;
+							// segments: 4 per resident block (2 blocks per SM; measured: 2 -> 0.229 ms, 4 -> 0.173 ms, 8 -> 0.183 ms at 27-point 256^3), at least 6 items each
+							int sms = 148;
+							{ int dev = 0, v = 0; if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v; }
+							static const char* l_env = getenv("LCGB200_PAT_SEGS");   // experiments: segments per resident block
+							const int per_block = (l_env && atoi(l_env) > 0) ? atoi(l_env) : 4;
+							std::vector<PatSegH> segs;
+							pat_build_segments(plan, n, S, kPatRows, per_block * 2 * sms, 6, segs);
+							if (!segs.empty() && n_bi < 0x7fffffffLL / 16)
+							{
+								d_bitem = dev_alloc<unsigned char>((size_t)n_bi * 16); d_segs = dev_alloc<int4>(segs.size());
+								LCG_CUDA_CHECK(cudaMemset(d_bitem, 0, (size_t)n_bi * 16));
+								LCG_CUDA_CHECK(cudaMemcpy(d_segs, segs.data(), segs.size() * sizeof(int4), cudaMemcpyHostToDevice));
+								const PatInfo* d_info = reinterpret_cast<const PatInfo*>(d_tab + np * maxch * sizeof(PatChainH));
+								k_pat_bitems<<<(unsigned)n_bi, 256>>>(n, S, plan.wx, plan.wy, nibb, (int)longest, d_pat, d_info, d_bitem);
+								LCG_CUDA_CHECK(cudaGetLastError());
+								march = new PatMarch();
+								march->gpat = (int)longest; march->G = plan.G; march->S2 = plan.S2; march->o0 = plan.o0; march->nlines = plan.nlines;
+								march->wx = plan.wx; march->wy = plan.wy; march->dAb = plan.dAb; march->n_segs = (int)segs.size();
+								for (int g = 0; g < kPatMaxPlanes; g++)
+								{
+									march->gbegin |= (unsigned int)(plan.group_begin[g] & 255) << (8 * g);
+									march->gplane |= (unsigned int)(plan.group_plane[g] & 3) << (2 * g);
+								}
+								for (int g = plan.G; g < kPatMaxPlanes; g++) march->gbegin |= (unsigned int)(plan.group_begin[plan.G] & 255) << (8 * g);   // group_begin(G) for G < 4
+								march->gend4 = (unsigned int)plan.group_begin[plan.G];
+								// windows loaded ahead of the G an item reads: as many as two blocks per SM leave room for (at least one)
+								static const char* a_env = getenv("LCGB200_PAT_AHEAD");
+								int ahead = (a_env && atoi(a_env) > 0) ? atoi(a_env) : 3;
+								while (ahead > 1 && pat_march_smem_bytes(plan.G + ahead, plan.nlines, plan.wx, (int)np, (int)maxch) > (size_t)kPatMarchSmemFor2) ahead--;
+								march->nst = plan.G + ahead;
+							}
+						}
 						LCG_CUDA_CHECK(cudaDeviceSynchronize());
-						h->pat = d_pat; h->pat_item = d_item; h->pat_info = d_info; h->pat_chain = d_chain; h->n_pat = (int)reps.size();
+						h->pat = d_pat; h->pat_item = d_item; h->pat_thread = d_thread; h->pat_chain = d_tab; h->n_pat = (int)np;
 						h->pat_maxch = (int)maxch; h->pat_stride = S; h->pat_nib = (int)nib; h->pat_items = n_items;
+						h->pat_bitem = d_bitem; h->pat_segs = d_segs; h->pat_march = march;
 						ok = true;
 					}
 				}
 			}
 		}
 	}
-	catch (...) { cudaFree(d_key); cudaFree(d_rep); cudaFree(d_slot); cudaFree(d_fail); cudaFree(d_id); cudaFree(d_pat); cudaFree(d_info); cudaFree(d_chain); cudaFree(d_item); throw; }
+	catch (...)
+	{
+		cudaFree(d_key); cudaFree(d_rep); cudaFree(d_slot); cudaFree(d_fail); cudaFree(d_id); cudaFree(d_pat); cudaFree(d_tab); cudaFree(d_item); cudaFree(d_thread);
+		cudaFree(d_bitem); cudaFree(d_segs); delete march;
+		throw;
+	}
 	cudaFree(d_key); cudaFree(d_rep); cudaFree(d_slot); cudaFree(d_fail); cudaFree(d_id);
-	if (!ok) { cudaFree(d_pat); cudaFree(d_info); cudaFree(d_chain); cudaFree(d_item); }
+	if (!ok) { cudaFree(d_pat); cudaFree(d_tab); cudaFree(d_item); cudaFree(d_thread); cudaFree(d_bitem); cudaFree(d_segs); delete march; }
 }
 
 // LCGB200_CSR_COMPRESS: if the matrix has <= 256 distinct values and <= 256 distinct (col - row) offsets, store a second
@@ -527,7 +633,7 @@ void destroy_handle(CsrHandle* h)
 	cudaFree(h->row_ptr); cudaFree(h->col); cudaFree(h->val); cudaFree(h->tiles);
 	cudaFree(h->t_row_ptr); cudaFree(h->t_col); cudaFree(h->t_val); cudaFree(h->t_tiles);
 	cudaFree(h->code); cudaFree(h->vdict); cudaFree(h->odict); cudaFree(h->dtiles);
-	cudaFree(h->pat); cudaFree(h->pat_item); cudaFree(h->pat_info); cudaFree(h->pat_chain);
+	cudaFree(h->pat); cudaFree(h->pat_item); cudaFree(h->pat_thread); cudaFree(h->pat_chain); cudaFree(h->pat_bitem); cudaFree(h->pat_segs); delete h->pat_march;
 	free_factor(h->icL); free_factor(h->icU); cudaFree(h->ic_tmp);
 	cudaFree(h->diag); cudaFree(h->ws);
 	cudaFree(h->d_state); cudaFree(h->d_partials);

@@ -46,6 +46,7 @@ constexpr int kGatherUnroll = LCG_UNROLL;     // row entries per lane whose load
 constexpr int kSpmvThreads = kThreads + 32;   // 8 consumer warps + 1 producer warp
 constexpr int kSpmvCtasPerSm = LCG_CTAS;
 
+struct PatMarch;   // plan of the plane-marching row-pattern kernel (below)
 template <class T>
 struct CsrDev {
 	int n_rows = 0, n_cols = 0, nnz = 0, n_tiles = 0, lpr = 1, chunk = 1;
@@ -63,7 +64,11 @@ struct CsrDev {
 	const int4* dtiles = nullptr; int n_dtiles = 0, dchunk = 1, dlpr = 1;
 	// row-pattern copy (real operators, optional): one pattern id per ROW + a table of the distinct rows
 	// (csr.cuh "row-pattern operator": chains of offsets S apart, one byte per warp work item)
-	const unsigned char* pat = nullptr; const unsigned char* pat_item = nullptr; const void* pat_info = nullptr; const void* pat_chain = nullptr;
+	// pat_chain: chains | info of all patterns, one device array; pat_item: a byte per warp item (k_spmv_pat);
+	// pat_bitem / pat_segs / pat_march: block items, march segments and plan of k_spmv_pat_march (host pointer, null = no plan)
+	// pat_thread: a byte per thread of a warp item (the pattern its R rows share, 255 = mixed)
+	const unsigned char* pat = nullptr; const unsigned char* pat_item = nullptr; const unsigned char* pat_thread = nullptr; const void* pat_chain = nullptr;
+	const unsigned char* pat_bitem = nullptr; const void* pat_segs = nullptr; const PatMarch* pat_march = nullptr;
 	int n_pat = 0, pat_maxch = 0, pat_stride = 0, pat_nib = 0, pat_items = 0;
 };
 
@@ -551,32 +556,54 @@ __global__ void __launch_bounds__(kSpmvThreads, kSpmvCtasPerSm) k_spmv_dict(CsrD
 // (col - row, value) pairs: interior, faces, edges, corners (27 for a 3-D stencil; a few more after the ghost remap of a
 // row block).  Such a matrix is stored a third time as ONE BYTE PER ROW (its pattern id) plus the table of patterns:
 // the SpMV streams x, y and n bytes of ids — the 12 bytes per non-zero of CSR disappear, and what bounds the kernel is
-// the number of gathers the load/store pipe has to serve (round 1: 27 per row, LSU data pipe 84 % busy, 0.2 of HBM).
+// how the gathers of x are served (round 1: 27 per row, LSU data pipe 84 % busy, 0.2 of HBM).
 //
-// Round 2: gathers shared in REGISTERS.  The entries of a pattern are grouped into CHAINS: up to kPatChainLen offsets in
-// arithmetic progression with the matrix-wide stride S (for a 3-D stencil S = nx: the entries (dx, dz) fixed, dy = -1, 0,
-// +1).  A thread owns R rows that are S apart (row, row + S, ..., row + (R-1) S: a column of R grid points in y), so the
-// x values one chain needs for all R rows are R + m - 1 loads instead of R * m — x[row + off + u S] serves row q = u - t
-// through chain entry t.  27-point stencil, R = 8: 9 chains x 10 loads for 8 rows = 11.25 gathers per row instead of 27,
-// and one 32-byte table read per chain instead of one per entry.  Lanes of a warp sit on 32 consecutive rows, so every
-// gather is 32 consecutive doubles (2-3 lines), every store a full 256-byte line.
-//
-// Work item of a warp = R x 32 rows: rows (A R + q) S + 32 ib + lane.  A byte per ITEM (pat_item) says whether all its
-// rows exist and share one pattern (the rule inside a stencil): then the warp does not even read the per-row ids and all
-// table reads are broadcasts.  Otherwise each thread looks at its own R rows: same pattern -> the chain path with a
-// per-lane pattern; patterns that are SUBSETS of one longer pattern (a column of grid points that starts on a face: the
-// face row is the interior row minus the entries that leave the grid; pat_host.h: pat_build_masks) -> the longer pattern's
-// chains with a 64-bit presence mask per row, loads still shared; anything else row by row through the same chain table.
-// Entries are accumulated chain by chain with fma (a different order from the CSR row order: y agrees with the plain
-// copy to rounding, not bitwise).
+// 1. Gathers shared between rows (both kernels).  The entries of a pattern are grouped into CHAINS: up to kPatChainLen
+//    offsets in arithmetic progression with the matrix-wide stride S (for a 3-D stencil S = nx: the entries (dx, dz)
+//    fixed, dy = -1, 0, +1).  A thread owns R rows that are S apart (row, row + S, ..., row + (R-1) S: a column of R grid
+//    points in y), so the x values one chain needs for all R rows are R + m - 1 reads instead of R * m — x[row + off +
+//    u S] serves row q = u - t through chain entry t.  27-point stencil, R = 8: 9 chains x 10 reads for 8 rows = 11.25
+//    per row instead of 27, and one 32-byte table read per chain instead of one per entry.  Lanes of a warp sit on 32
+//    consecutive rows.  Work item of a warp = R x 32 rows: rows (A R + q) S + 32 ib + lane.
+// 2. Rows that differ.  A byte per item says whether all its rows share one pattern (the rule inside a stencil).  If not,
+//    each thread looks at its own R rows: same pattern -> that pattern's chains; patterns that are SUBSETS of one longer
+//    pattern (a column of grid points that starts on a face: the face row is the interior row minus the entries that
+//    leave the grid; pat_host.h: pat_build_masks) -> the longer pattern's chains with a 64-bit presence mask per row,
+//    reads still shared; anything else row by row through the same chain table.
+// 3. k_spmv_pat (any matrix with <= 255 distinct rows): the reads are plain loads.  Measured at 27-point 256^3: 0.174 ms,
+//    LSU data pipe 43 %, every unit below 45 % — latency-bound (10 dependent rounds of L2 latency per item).
+// 4. k_spmv_pat_march (stride a multiple of 128, chain offsets on planes S2 apart — 3-D grids with nx % 128 == 0 and
+//    ny % 8 == 0): a thread block of 8 consumer warps + 1 producer warp MARCHES along S2 (z).  The producer's lanes copy
+//    the lines of one plane window — the x values all 8 warps need from one plane: (wy R + 2) lines x (32 wx + 8)
+//    values — into a ring of shared-memory stages with TMA bulk copies (full/empty mbarriers, as k_spmv does for the
+//    matrix).  The window of plane p of item k is the window of plane p - 1 of item k + 1, so ONE window is loaded per
+//    item instead of G = 3: x crosses L2 -> SM 1.3 times per SpMV instead of 4, and the consumers read x out of shared
+//    memory with immediate offsets (no address arithmetic, no global-memory latency on their path).
+// Entries are accumulated chain by chain with fma (a different order from the CSR row order: y agrees with the plain copy
+// to rounding, not bitwise).
 constexpr int kPatRows = 8;            // R: rows (S apart) a thread computes together
 constexpr int kPatChainLen = 3;        // entries per chain (v[3])
-constexpr int kPatMaxChains = 3072;    // chain table entries held in shared memory (96 KB)
+constexpr int kPatMaxChains = 1536;    // chain table entries held in shared memory (48 KB)
 constexpr int kPatDefaultStride = 256; // S when no pair of offsets repeats (all chains have one entry)
+constexpr int kPatSpan = 8;            // extra values per window line of the marching kernel
+constexpr int kPatMaxPlanes = 4;
+constexpr int kPatMaxStages = 8;       // window stages of the marching kernel: planes + windows loaded ahead
+// m = entries | line shift << 4 | position in the window line << 8 | plane << 16 (pat_host.h: PatChainH)
 struct __align__(16) PatChain { double v[kPatChainLen]; int off; int m; };   // 32 bytes: two 128-bit shared-memory reads
 static_assert(sizeof(PatChain) == 32, "PatChain is read as two 16-byte words");
-// per pattern: presence mask over the chains of pattern `sup` (bit 3 c + t), chains | (index of offset 0 in chain 0, +1) << 8
+// per pattern: presence mask over the chains of pattern `sup` (bit 3 c + t), chains | (index of offset 0 in the LAST chain, +1) << 8
 struct __align__(16) PatInfo { unsigned long long mask; int info; int sup; };
+// the marching kernel's plan (pat_host.h: PatMarchH) as the kernel gets it
+struct PatMarch {
+	int gpat = -1;      // geometry pattern, -1 = no plan
+	int G = 0, S2 = 0, o0 = 0, nlines = 0, wx = 0, wy = 0, dAb = 0, n_segs = 0;
+	int nst = 0;            // window stages in shared memory: G + the windows loaded ahead
+	unsigned int gbegin = 0;   // chains of group g: [byte g, byte g + 1) of gbegin | gend << 32 ... (8 bits each, G <= 4: 5 bytes)
+	unsigned int gend4 = 0;    // the fifth byte (end of the last group)
+	unsigned int gplane = 0;   // plane of group g: bits [2 g, 2 g + 2)
+	__host__ __device__ int group_begin(int g) const { return g < 4 ? (int)((gbegin >> (8 * g)) & 255u) : (int)gend4; }
+	__host__ __device__ int group_plane(int g) const { return (int)((gplane >> (2 * g)) & 3u); }
+};
 
 __device__ __forceinline__ void pat_chain_load(const PatChain* c, double& v0, double& v1, double& v2, int& off, int& m)
 {
@@ -587,25 +614,175 @@ __device__ __forceinline__ void pat_chain_load(const PatChain* c, double& v0, do
 	off = (int)(om & 0xffffffffll); m = (int)(om >> 32);
 }
 
+// The R rows of one thread through plain loads (paragraphs 1-3).  tcode = the pattern all R rows share, 255 = look at
+// the rows.  Lanes with lane_on == false do nothing.
+template <class Epi>
+__device__ __forceinline__ void pat_item_ldg(const unsigned char* __restrict__ pat, const double* __restrict__ x, double* __restrict__ y,
+	const PatChain* s_ch, const PatInfo* s_info, int maxch, int S, int n_rows, int row0, int tcode, bool lane_on, Epi& epi, double* acc)
+{
+	constexpr int R = kPatRows;
+	if (!lane_on) return;
+	int p = tcode;
+	bool chained = true, masked = false;
+	unsigned long long mk[R];
+	if (tcode == 255)
+	{
+		int p0 = -1, sup = -1;
+		masked = true;
+#pragma unroll
+		for (int q = 0; q < R; q++)
+		{
+			const int row = row0 + q * S;
+			const int pq = row < n_rows ? (int)pat[row] : -1;
+			if (q == 0) p0 = pq;
+			chained = chained && pq >= 0 && pq == p0;
+			mk[q] = 0ull;
+			if (pq >= 0)
+			{	// rows beyond the matrix keep an empty mask: no loads, no store
+				const PatInfo pi = s_info[pq];
+				if (sup < 0) sup = pi.sup;
+				masked = masked && pi.sup == sup && pi.mask != 0ull;
+				mk[q] = pi.mask;
+			}
+		}
+		p = chained ? p0 : sup;
+	}
+	if (chained)
+	{
+		const int info = s_info[p].info;
+		const int nch = info & 255, t0 = (info >> 8) - 1;
+		const PatChain* ch = s_ch + p * maxch;
+		double sum[R];
+#pragma unroll
+		for (int q = 0; q < R; q++) sum[q] = 0.0;
+		for (int c = 0; c < nch; c++)
+		{
+			double v0, v1, v2; int off, m;
+			pat_chain_load(ch + c, v0, v1, v2, off, m);
+			m &= 3;
+			const int xb = row0 + off;   // 32-bit element indices (try_patterns checks the range): one add + one widening multiply-add per load
+			double xl[R + 2];
+#pragma unroll
+			for (int u = 0; u < R; u++) xl[u] = __ldg(x + (xb + u * S));
+			xl[R] = m > 1 ? __ldg(x + (xb + R * S)) : 0.0;
+			xl[R + 1] = m > 2 ? __ldg(x + (xb + (R + 1) * S)) : 0.0;
+#pragma unroll
+			for (int q = 0; q < R; q++) sum[q] = fma(v0, xl[q], sum[q]);
+			if (m > 1)
+			{
+#pragma unroll
+				for (int q = 0; q < R; q++) sum[q] = fma(v1, xl[q + 1], sum[q]);
+			}
+			if (m > 2)
+			{
+#pragma unroll
+				for (int q = 0; q < R; q++) sum[q] = fma(v2, xl[q + 2], sum[q]);
+			}
+			if (c == nch - 1 && t0 >= 0)
+			{	// the last chain holds the diagonal when the row has one: its values double as x[row] for the epilogue
+#pragma unroll
+				for (int q = 0; q < R; q++)
+				{
+					const int row = row0 + q * S;
+					y[row] = sum[q];
+					epi.row(row, sum[q], t0 == 0 ? xl[q] : (t0 == 1 ? xl[q + 1] : xl[q + 2]), acc);
+				}
+			}
+		}
+		if (t0 < 0)
+		{
+#pragma unroll
+			for (int q = 0; q < R; q++)
+			{
+				const int row = row0 + q * S;
+				y[row] = sum[q];
+				epi.row(row, sum[q], __ldg(x + row), acc);
+			}
+		}
+	}
+	else if (masked && p >= 0)
+	{	// the chains of pattern p = sup, every row with its own presence mask
+		const int nch = s_info[p].info & 255;
+		const PatChain* ch = s_ch + p * maxch;
+		double sum[R];
+#pragma unroll
+		for (int q = 0; q < R; q++) sum[q] = 0.0;
+		for (int c = 0; c < nch; c++)
+		{
+			double v0, v1, v2; int off, m;
+			pat_chain_load(ch + c, v0, v1, v2, off, m);
+			const int xb = row0 + off;
+			unsigned int b[R + 2];
+#pragma unroll
+			for (int q = 0; q < R; q++) b[q] = (unsigned int)(mk[q] >> (kPatChainLen * c)) & 7u;
+			b[R] = 0u; b[R + 1] = 0u;
+			double xl[R + 2];
+#pragma unroll
+			for (int u = 0; u < R + 2; u++)
+			{
+				const unsigned int need = (b[u] & 1u) | (u >= 1 ? (b[u - 1] & 2u) : 0u) | (u >= 2 ? (b[u - 2] & 4u) : 0u);
+				xl[u] = need ? __ldg(x + (xb + u * S)) : 0.0;
+			}
+#pragma unroll
+			for (int q = 0; q < R; q++)
+			{
+				if (b[q] & 1u) sum[q] = fma(v0, xl[q], sum[q]);
+				if (b[q] & 2u) sum[q] = fma(v1, xl[q + 1], sum[q]);
+				if (b[q] & 4u) sum[q] = fma(v2, xl[q + 2], sum[q]);
+			}
+		}
+#pragma unroll
+		for (int q = 0; q < R; q++)
+		{
+			const int row = row0 + q * S;
+			if (row < n_rows)
+			{
+				y[row] = sum[q];
+				epi.row(row, sum[q], __ldg(x + row), acc);
+			}
+		}
+	}
+	else
+	{
+		for (int q = 0; q < R; q++)
+		{
+			const int row = row0 + q * S;
+			if (row >= n_rows) break;
+			const int pq = (int)pat[row];
+			const int nch = s_info[pq].info & 255;
+			const PatChain* ch = s_ch + pq * maxch;
+			const double* xr = x + row;
+			double sum = 0.0;
+			for (int c = 0; c < nch; c++)
+			{
+				const int off = ch[c].off, m = ch[c].m & 3;
+				for (int t = 0; t < m; t++) sum = fma(ch[c].v[t], __ldg(xr + off + t * S), sum);
+			}
+			y[row] = sum;
+			epi.row(row, sum, __ldg(xr), acc);
+		}
+	}
+}
+
+// chains | info of all patterns -> shared memory (one device array, 16-byte words)
+__device__ __forceinline__ void pat_tables_to_smem(const CsrDev<double>& A, unsigned char* smem_tables)
+{
+	const double2* g = reinterpret_cast<const double2*>(A.pat_chain);
+	double2* s = reinterpret_cast<double2*>(smem_tables);
+	const int n16 = 2 * A.n_pat * A.pat_maxch + A.n_pat;
+	for (int i = threadIdx.x; i < n16; i += blockDim.x) s[i] = g[i];
+}
+
 template <class Epi>
 __global__ void __launch_bounds__(kThreads, 3) k_spmv_pat(CsrDev<double> A, const double* __restrict__ x, double* __restrict__ y, Epi epi_in,
 	DevState* st, double* partials)
 {
 	pdl_enter();
 	if (st_done(st)) return;
-	constexpr int R = kPatRows;
 	extern __shared__ __align__(128) unsigned char smem[];
-	PatChain* s_ch = reinterpret_cast<PatChain*>(smem);
-	const int n_ch = A.n_pat * A.pat_maxch;
-	PatInfo* s_info = reinterpret_cast<PatInfo*>(smem + (size_t)n_ch * sizeof(PatChain));
-	{
-		const double2* g = reinterpret_cast<const double2*>(A.pat_chain);
-		double2* s = reinterpret_cast<double2*>(smem);
-		for (int i = threadIdx.x; i < 2 * n_ch; i += blockDim.x) s[i] = g[i];
-		const double2* gi = reinterpret_cast<const double2*>(A.pat_info);
-		double2* si = reinterpret_cast<double2*>(s_info);
-		for (int i = threadIdx.x; i < A.n_pat; i += blockDim.x) si[i] = gi[i];
-	}
+	const PatChain* s_ch = reinterpret_cast<const PatChain*>(smem);
+	const PatInfo* s_info = reinterpret_cast<const PatInfo*>(smem + (size_t)A.n_pat * A.pat_maxch * sizeof(PatChain));
+	pat_tables_to_smem(A, smem);
 	__syncthreads();
 
 	Epi epi = epi_in;
@@ -614,154 +791,282 @@ __global__ void __launch_bounds__(kThreads, 3) k_spmv_pat(CsrDev<double> A, cons
 #pragma unroll
 	for (int r = 0; r < (Epi::NRED > 0 ? Epi::NRED : 1); r++) acc[r] = 0.0;
 
-	const int S = A.pat_stride, nib = A.pat_nib, n_items = A.pat_items, maxch = A.pat_maxch;
-	const long long n_rows = A.n_rows;
-	const size_t Ss = (size_t)S;
+	const int S = A.pat_stride, nib = A.pat_nib, n_items = A.pat_items;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	constexpr int WPB = kThreads / 32;
-	for (int it = blockIdx.x * WPB + warp; it < n_items; it += gridDim.x * WPB)
+	// the warps of a block take the items of a round in rotation: the items at the ends of a grid line (mixed patterns,
+	// slower) do not always land on the same two warps.  A thread's pattern byte (the pattern its R rows share, 255 = look at
+	// the rows) is loaded one round ahead.
+	auto item_of = [&](int round) { return (blockIdx.x + round * (int)gridDim.x) * WPB + ((warp + round) & (WPB - 1)); };
+	int it = item_of(0);
+	int tcode = it < n_items ? (int)A.pat_thread[(size_t)it * 32 + lane] : 255;
+	for (int round = 0; (blockIdx.x + round * (int)gridDim.x) * WPB < n_items; round++)
 	{
-		const int a = it / nib, ib = it - a * nib;
-		const int i = ib * 32 + lane;
-		if (i >= S) continue;
-		const long long row0 = (long long)a * R * S + i;
-		const int uni = (int)A.pat_item[it];   // warp-uniform: pattern id shared by the whole item, 255 = mixed
-		int p = uni;
-		bool chained = true, masked = false;
-		unsigned long long mk[R];
-		if (uni == 255)
+		const int it_next = item_of(round + 1);
+		const int tcode_next = it_next < n_items ? (int)A.pat_thread[(size_t)it_next * 32 + lane] : 255;
+		if (it < n_items)
 		{
-			int p0 = -1, sup = -1;
-			masked = true;
-#pragma unroll
-			for (int q = 0; q < R; q++)
-			{
-				const long long row = row0 + (long long)q * S;
-				const int pq = row < n_rows ? (int)A.pat[row] : -1;
-				if (q == 0) p0 = pq;
-				chained = chained && pq >= 0 && pq == p0;
-				mk[q] = 0ull;
-				if (pq >= 0)
-				{	// rows beyond the matrix keep an empty mask: no loads, no store
-					const PatInfo pi = s_info[pq];
-					if (sup < 0) sup = pi.sup;
-					masked = masked && pi.sup == sup && pi.mask != 0ull;
-					mk[q] = pi.mask;
-				}
-			}
-			p = chained ? p0 : sup;
+			const int a = it / nib, ib = it - a * nib;
+			const int i = ib * 32 + lane;
+			pat_item_ldg<Epi>(A.pat, x, y, s_ch, s_info, A.pat_maxch, S, A.n_rows, a * kPatRows * S + i, tcode, i < S, epi, acc);
 		}
-		if (chained)
+		it = it_next; tcode = tcode_next;
+	}
+	if (Epi::NRED > 0)
+	{
+		double tot[Epi::NRED > 0 ? Epi::NRED : 1];
+		if (grid_reduce<(Epi::NRED > 0 ? Epi::NRED : 1)>(acc, partials, &st->ticket, tot))
 		{
-			const int info = s_info[p].info;
-			const int nch = info & 255, t0 = (info >> 8) - 1;
-			const PatChain* ch = s_ch + p * maxch;
-			const double* xr = x + row0;
-			double sum[R], xc[R];
-#pragma unroll
-			for (int q = 0; q < R; q++) { sum[q] = 0.0; xc[q] = 0.0; }
-			for (int c = 0; c < nch; c++)
-			{
-				double v0, v1, v2; int off, m;
-				pat_chain_load(ch + c, v0, v1, v2, off, m);
-				const double* xb = xr + off;
-				double xl[R + 2];
-#pragma unroll
-				for (int u = 0; u < R; u++) xl[u] = __ldg(xb + u * Ss);
-				xl[R] = m > 1 ? __ldg(xb + R * Ss) : 0.0;
-				xl[R + 1] = m > 2 ? __ldg(xb + (R + 1) * Ss) : 0.0;
-				if (c == 0)
-				{	// chain 0 holds the diagonal when the row has one: keep x[row] for the epilogue
-#pragma unroll
-					for (int q = 0; q < R; q++) xc[q] = t0 == 0 ? xl[q] : (t0 == 1 ? xl[q + 1] : xl[q + 2]);
-				}
-#pragma unroll
-				for (int q = 0; q < R; q++) sum[q] = fma(v0, xl[q], sum[q]);
-				if (m > 1)
-				{
-#pragma unroll
-					for (int q = 0; q < R; q++) sum[q] = fma(v1, xl[q + 1], sum[q]);
-				}
-				if (m > 2)
-				{
-#pragma unroll
-					for (int q = 0; q < R; q++) sum[q] = fma(v2, xl[q + 2], sum[q]);
-				}
-			}
-			if (t0 < 0)
-			{
-#pragma unroll
-				for (int q = 0; q < R; q++) xc[q] = __ldg(xr + q * Ss);
-			}
-#pragma unroll
-			for (int q = 0; q < R; q++)
-			{
-				const long long row = row0 + (long long)q * S;
-				y[row] = sum[q];
-				epi.row((int)row, sum[q], xc[q], acc);
-			}
+			if (st->multi) { if (reduce_across_ranks(st, tot, Epi::NRED)) epi.finish(st, tot); }
+			else if ((threadIdx.x & 31) == 0) epi.finish(st, tot);
 		}
-		else if (masked && p >= 0)
-		{	// the chains of pattern p = sup, every row with its own presence mask
-			const int nch = s_info[p].info & 255;
-			const PatChain* ch = s_ch + p * maxch;
-			const double* xr = x + row0;
-			double sum[R];
+	}
+}
+
+// global -> shared bulk copy without a cache hint (x is re-read by the neighbouring blocks: normal L2 residency)
+__device__ __forceinline__ void bulk_g2s_plain(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		:: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// the marching kernel (paragraph 4).  WX = warps along the row index (8: S % 256 == 0, 4: S % 128 == 0), WY = 8 / WX warps
+// along S.  Block item (Ab, ibb): warp (wq, wi) owns the rows ((Ab WY + wq) R + q) S + 32 (ibb WX + wi) + lane.
+// pat_bitem[16 bi + w] = the pattern all rows of warp w's item share (255 = mixed, 254 = the item has no rows),
+// pat_bitem[16 bi + 8] = 1 when every existing row of the block item is a subset of the geometry pattern.
+template <class Epi, int WX>
+__global__ void __launch_bounds__(kSpmvThreads, 2) k_spmv_pat_march(CsrDev<double> A, PatMarch M, const double* __restrict__ x, double* __restrict__ y, Epi epi_in,
+	DevState* st, double* partials)
+{
+	pdl_enter();
+	if (st_done(st)) return;
+	constexpr int R = kPatRows, WY = 8 / WX;
+	constexpr int WD = 32 * WX + kPatSpan;            // values per window line
+	extern __shared__ __align__(128) unsigned char smem[];
+	__shared__ __align__(8) unsigned long long s_bar[2 * kPatMaxStages];   // full[stage] | empty[stage]
+	// layout: window stages | chains | info
+	const int NST = M.nst;
+	const int stage_bytes = M.nlines * WD * 8;
+	// ... | the geometry pattern's chains | info of all patterns (the chains of the other patterns stay in global memory:
+	// only block items that leave the march — the ghost-coupled planes of a row block — read them)
+	unsigned char* s_tab = smem + (size_t)NST * stage_bytes;
+	const PatChain* g_ch = reinterpret_cast<const PatChain*>(A.pat_chain);
+	const PatChain* s_ch = reinterpret_cast<const PatChain*>(s_tab);
+	const PatInfo* s_info = reinterpret_cast<const PatInfo*>(s_tab + (size_t)A.pat_maxch * sizeof(PatChain));
+	const int tid = threadIdx.x;
+	{
+		const double2* gc = reinterpret_cast<const double2*>(g_ch + (size_t)M.gpat * A.pat_maxch);
+		const double2* gi = reinterpret_cast<const double2*>(g_ch + (size_t)A.n_pat * A.pat_maxch);
+		double2* sc = reinterpret_cast<double2*>(s_tab);
+		for (int i = tid; i < 2 * A.pat_maxch; i += blockDim.x) sc[i] = gc[i];
+		for (int i = tid; i < A.n_pat; i += blockDim.x) sc[2 * A.pat_maxch + i] = gi[i];
+	}
+	if (tid == 0)
+	{
+		for (int s = 0; s < NST; s++) { mbar_init(smem_u32(&s_bar[s]), 1); mbar_init(smem_u32(&s_bar[kPatMaxStages + s]), kThreads / 32); }
+		mbar_fence_init();
+	}
+	__syncthreads();
+
+	Epi epi = epi_in;
+	double acc[Epi::NRED > 0 ? Epi::NRED : 1];
 #pragma unroll
-			for (int q = 0; q < R; q++) sum[q] = 0.0;
-			for (int c = 0; c < nch; c++)
+	for (int r = 0; r < (Epi::NRED > 0 ? Epi::NRED : 1); r++) acc[r] = 0.0;
+	const int S = A.pat_stride, n_rows = A.n_rows, n_cols = A.n_cols;
+	const int nibb = S / (32 * WX);
+	const int lane = tid & 31;
+	const int4* segs = reinterpret_cast<const int4*>(A.pat_segs);
+	// windows loaded / consumed so far by this block, over all its segments: number jg = use * NST + slot lives in stage `slot`
+	int slot = 0, use = 0;
+
+	if (tid >= kThreads)
+	{	// ---- producer warp: one window per item (+ G - 1 at the head of a segment) ----
+		for (int sg = blockIdx.x; sg < M.n_segs; sg += gridDim.x)
+		{
+			const int4 seg = __ldg(segs + sg);
+			const int n_win = seg.z + M.G - 1;
+			// x index behind line 0, position 0 of window 0 of the segment (may be negative: clipped below)
+			long long wbase = (long long)seg.x * WY * R * S + (long long)seg.y * (32 * WX) + M.o0;
+			for (int j = 0; j < n_win; j++, wbase += M.S2)
 			{
-				double v0, v1, v2; int off, m;
-				pat_chain_load(ch + c, v0, v1, v2, off, m);
-				const double* xb = xr + off;
-				unsigned int b[R + 2];
-#pragma unroll
-				for (int q = 0; q < R; q++) b[q] = (unsigned int)(mk[q] >> (kPatChainLen * c)) & 7u;
-				b[R] = 0u; b[R + 1] = 0u;
-				double xl[R + 2];
-#pragma unroll
-				for (int u = 0; u < R + 2; u++)
+				if (use > 0) mbar_wait(smem_u32(&s_bar[kPatMaxStages + slot]), (uint32_t)((use - 1) & 1));
+				const uint32_t full = smem_u32(&s_bar[slot]);
+				const uint32_t dst0 = smem_u32(smem) + (uint32_t)(slot * stage_bytes);
+				// clip every line to [0, n_cols): both ends even, so copies stay 16-byte aligned and sized
+				uint32_t my_bytes = 0;
+				for (int l = lane; l < M.nlines; l += 32)
 				{
-					const unsigned int need = (b[u] & 1u) | (u >= 1 ? (b[u - 1] & 2u) : 0u) | (u >= 2 ? (b[u - 2] & 4u) : 0u);
-					xl[u] = need ? __ldg(xb + u * Ss) : 0.0;
+					const long long b0 = wbase + (long long)l * S;
+					const long long lo = b0 < 0 ? 0 : b0, hi = b0 + WD > n_cols ? n_cols : b0 + WD;
+					if (hi > lo) my_bytes += (uint32_t)(hi - lo) * 8u;
 				}
-#pragma unroll
-				for (int q = 0; q < R; q++)
+				const uint32_t total = (uint32_t)__reduce_add_sync(0xffffffffu, my_bytes);
+				if (lane == 0) mbar_expect_tx(full, total);
+				__syncwarp();
+				for (int l = lane; l < M.nlines; l += 32)
 				{
-					if (b[q] & 1u) sum[q] = fma(v0, xl[q], sum[q]);
-					if (b[q] & 2u) sum[q] = fma(v1, xl[q + 1], sum[q]);
-					if (b[q] & 4u) sum[q] = fma(v2, xl[q + 2], sum[q]);
+					const long long b0 = wbase + (long long)l * S;
+					const long long lo = b0 < 0 ? 0 : b0, hi = b0 + WD > n_cols ? n_cols : b0 + WD;
+					if (hi > lo) bulk_g2s_plain(dst0 + (uint32_t)((l * WD + (int)(lo - b0)) * 8), x + lo, (uint32_t)(hi - lo) * 8u, full);
 				}
-			}
-#pragma unroll
-			for (int q = 0; q < R; q++)
-			{
-				const long long row = row0 + (long long)q * S;
-				if (row < n_rows)
-				{
-					y[row] = sum[q];
-					epi.row((int)row, sum[q], __ldg(x + row), acc);
-				}
+				if (++slot == NST) { slot = 0; use++; }
 			}
 		}
-		else
+	}
+	else
+	{	// ---- consumer warps ----
+		epi.begin(st);
+		const int warp = tid >> 5;
+		const int wq = warp / WX, wi = warp % WX;
+		const unsigned char* bitem = A.pat_bitem;
+		const int gpat = M.gpat;
+		const PatInfo ginfo = s_info[gpat];
+		const int t0 = (ginfo.info >> 8) - 1, c_last = (ginfo.info & 255) - 1;
+		const PatChain* ch = s_ch;
+		const double* win0 = reinterpret_cast<const double*>(smem) + (wq * R) * WD + wi * 32 + lane;   // my line 0, my position, stage 0
+		const int stage_dbl = stage_bytes / 8;
+		for (int sg = blockIdx.x; sg < M.n_segs; sg += gridDim.x)
 		{
-			for (int q = 0; q < R; q++)
+			const int4 seg = __ldg(segs + sg);
+			long long bi = (long long)seg.x * nibb + seg.y;
+			const long long bi_step = (long long)M.dAb * nibb;
+			int row0 = (seg.x * WY + wq) * R * S + (seg.y * WX + wi) * 32 + lane;
+			// my thread's byte of k_spmv_pat's item (A, ib) = (Ab WY + wq, ibb WX + wi): index (A nib + ib) 32 + lane, nib = S / 32
+			long long ti = ((long long)(seg.x * WY + wq) * (S / 32) + (seg.y * WX + wi)) * 32 + lane;
+			const long long ti_step = (long long)M.dAb * WY * S;
+			unsigned int code = (unsigned int)bitem[16 * bi + warp] | ((unsigned int)bitem[16 * bi + 8] << 8);
+			if ((code & 255u) == 255u) code |= (unsigned int)A.pat_thread[ti] << 16;
+			// the first item needs windows 0 .. G - 1: wait for the first G - 1 here, the last one inside the loop
+			for (int j = 0; j < M.G - 1; j++)
 			{
-				const long long row = row0 + (long long)q * S;
-				if (row >= n_rows) break;
-				const int pq = (int)A.pat[row];
-				const int nch = s_info[pq].info & 255;
-				const PatChain* ch = s_ch + pq * maxch;
-				const double* xr = x + row;
-				double sum = 0.0;
-				for (int c = 0; c < nch; c++)
+				const int sj = slot + j >= NST ? slot + j - NST : slot + j;
+				mbar_wait(smem_u32(&s_bar[sj]), (uint32_t)((slot + j >= NST ? use + 1 : use) & 1));
+			}
+			for (int k = 0; k < seg.z; k++, bi += bi_step, row0 += M.S2, ti += ti_step)
+			{
+				unsigned int code_next = 0xfe;
+				if (k + 1 < seg.z)
 				{
-					const int off = ch[c].off, m = ch[c].m;
-					for (int t = 0; t < m; t++) sum = fma(ch[c].v[t], __ldg(xr + off + t * Ss), sum);
+					code_next = (unsigned int)bitem[16 * (bi + bi_step) + warp] | ((unsigned int)bitem[16 * (bi + bi_step) + 8] << 8);
+					if ((code_next & 255u) == 255u) code_next |= (unsigned int)A.pat_thread[ti + ti_step] << 16;
 				}
-				y[row] = sum;
-				epi.row((int)row, sum, __ldg(xr), acc);
+				{	// window k + G - 1, the last one this item needs
+					const int j = M.G - 1, sj = slot + j >= NST ? slot + j - NST : slot + j;
+					mbar_wait(smem_u32(&s_bar[sj]), (uint32_t)((slot + j >= NST ? use + 1 : use) & 1));
+				}
+				const int uni = code & 255;
+				const int tcode = uni != 255 ? uni : (int)(code >> 16);   // the pattern my R rows share, 255 = mixed
+				if (uni != 254)
+				{
+					if ((code >> 8) & 255u)
+					{	// every row is a subset of the geometry pattern: its chains, read out of the plane windows
+						unsigned long long pqs = 0ull, mk0;
+						bool same = true;
+						if (tcode != 255) mk0 = s_info[tcode].mask;
+						else
+						{	// my rows' pattern ids (one byte each, 255 = row beyond the matrix) + the first row's mask
+							mk0 = 0ull;
+#pragma unroll
+							for (int q = 0; q < R; q++)
+							{
+								const int row = row0 + q * S;
+								const int pq = row < n_rows ? (int)A.pat[row] : 255;
+								const unsigned long long mq = pq != 255 ? s_info[pq].mask : 0ull;
+								if (q == 0) mk0 = mq;
+								same = same && mq == mk0;
+								pqs |= (unsigned long long)pq << (8 * q);
+							}
+						}
+						double sum[R];
+#pragma unroll
+						for (int q = 0; q < R; q++) sum[q] = 0.0;
+						for (int g = 0; g < M.G; g++)
+						{
+							const int sp = slot + M.group_plane(g);
+							const double* win = win0 + (sp >= NST ? sp - NST : sp) * stage_dbl;
+							const int c_end = M.group_begin(g + 1);
+							for (int c = M.group_begin(g); c < c_end; c++)
+							{
+								double v0, v1, v2; int off, m;
+								pat_chain_load(ch + c, v0, v1, v2, off, m);
+								const double* src = win + ((m >> 4) & 15) * WD + ((m >> 8) & 255);
+								double xl[R + 2];
+#pragma unroll
+								for (int u = 0; u < R; u++) xl[u] = src[u * WD];
+								xl[R] = (m & 3) > 1 ? src[R * WD] : 0.0;           // the window has WY R + max(shift + m - 1) lines
+								xl[R + 1] = (m & 3) > 2 ? src[(R + 1) * WD] : 0.0;
+								if (same)
+								{
+									const unsigned int pres = (unsigned int)(mk0 >> (kPatChainLen * c)) & 7u;
+									if (pres & 1u)
+									{
+#pragma unroll
+										for (int q = 0; q < R; q++) sum[q] = fma(v0, xl[q], sum[q]);
+									}
+									if (pres & 2u)
+									{
+#pragma unroll
+										for (int q = 0; q < R; q++) sum[q] = fma(v1, xl[q + 1], sum[q]);
+									}
+									if (pres & 4u)
+									{
+#pragma unroll
+										for (int q = 0; q < R; q++) sum[q] = fma(v2, xl[q + 2], sum[q]);
+									}
+								}
+								else
+								{
+#pragma unroll
+									for (int q = 0; q < R; q++)
+									{
+										const int pq = (int)(pqs >> (8 * q)) & 255;
+										const unsigned int pres = pq != 255 ? ((unsigned int)(s_info[pq].mask >> (kPatChainLen * c)) & 7u) : 0u;
+										if (pres & 1u) sum[q] = fma(v0, xl[q], sum[q]);
+										if (pres & 2u) sum[q] = fma(v1, xl[q + 1], sum[q]);
+										if (pres & 4u) sum[q] = fma(v2, xl[q + 2], sum[q]);
+									}
+								}
+								if (c == c_last && t0 >= 0)
+								{	// the diagonal's chain is the LAST chain of the last group: the sums are complete and x[row] is in xl
+#pragma unroll
+									for (int q = 0; q < R; q++)
+									{
+										const int row = row0 + q * S;
+										if (tcode != 255 || row < n_rows)
+										{
+											y[row] = sum[q];
+											epi.row(row, sum[q], t0 == 0 ? xl[q] : (t0 == 1 ? xl[q + 1] : xl[q + 2]), acc);
+										}
+									}
+								}
+							}
+						}
+						if (t0 < 0)
+						{
+#pragma unroll
+							for (int q = 0; q < R; q++)
+							{
+								const int row = row0 + q * S;
+								if (uni != 255 || row < n_rows)
+								{
+									y[row] = sum[q];
+									epi.row(row, sum[q], __ldg(x + row), acc);
+								}
+							}
+						}
+					}
+					else pat_item_ldg<Epi>(A.pat, x, y, g_ch, s_info, A.pat_maxch, S, n_rows, row0, tcode, true, epi, acc);   // e.g. the ghost-coupled planes of a row block
+				}
+				__syncwarp();
+				if (lane == 0) mbar_arrive(smem_u32(&s_bar[kPatMaxStages + slot]));   // window k is not needed by item k + 1
+				if (++slot == NST) { slot = 0; use++; }
+				code = code_next;
+			}
+			// the G - 1 windows behind the last item of the segment
+			for (int j = 0; j < M.G - 1; j++)
+			{
+				if (lane == 0) mbar_arrive(smem_u32(&s_bar[kPatMaxStages + slot]));
+				if (++slot == NST) { slot = 0; use++; }
 			}
 		}
 	}
@@ -776,10 +1081,39 @@ __global__ void __launch_bounds__(kThreads, 3) k_spmv_pat(CsrDev<double> A, cons
 	}
 }
 
+inline size_t pat_table_bytes(int n_pat, int maxch) { return (size_t)n_pat * maxch * sizeof(PatChain) + (size_t)n_pat * sizeof(PatInfo); }
+// the marching kernel: window stages + the geometry pattern's chains + info of all patterns.  Two blocks fit an SM (227 KB,
+// 1 KB reserved and about 1.3 KB of static shared memory per block) up to kPatMarchSmemFor2 each
+inline size_t pat_march_smem_bytes(int nst, int nlines, int wx, int n_pat, int maxch)
+{
+	return (size_t)nst * nlines * (32 * wx + kPatSpan) * 8 + (size_t)maxch * sizeof(PatChain) + (size_t)n_pat * sizeof(PatInfo);
+}
+constexpr int kPatMarchSmemFor2 = 111 * 1024;
+
+template <class Epi, int WX>
+inline void launch_spmv_pat_march(const CsrDev<double>& A, const double* x, double* y, const Epi& epi, DevState* st, double* partials, cudaStream_t s)
+{
+	const PatMarch& M = *A.pat_march;
+	const size_t smem = pat_march_smem_bytes(M.nst, M.nlines, WX, A.n_pat, A.pat_maxch);
+	auto kern = k_spmv_pat_march<Epi, WX>;
+	static PerDeviceOnce once;
+	if (once.first()) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+	const int limit = spmv_grid_limit(smem <= (size_t)kPatMarchSmemFor2 ? 2 : 1);
+	int grid = M.n_segs < limit ? M.n_segs : limit;
+	if (grid < 1) grid = 1;
+	launch_k(kern, grid, kSpmvThreads, smem, s, A, M, x, y, epi, st, partials);
+}
+
 template <class Epi>
 inline void launch_spmv_pat(const CsrDev<double>& A, const double* x, double* y, const Epi& epi, DevState* st, double* partials, cudaStream_t s)
 {
-	const size_t smem = (size_t)A.n_pat * A.pat_maxch * sizeof(PatChain) + (size_t)A.n_pat * sizeof(PatInfo);
+	if (A.pat_march && (reinterpret_cast<uintptr_t>(x) & 15) == 0)
+	{	// TMA bulk copies need 16-byte aligned sources; the plan already guarantees even row bases and an even vector length
+		if (A.pat_march->wx == 8) launch_spmv_pat_march<Epi, 8>(A, x, y, epi, st, partials, s);
+		else launch_spmv_pat_march<Epi, 4>(A, x, y, epi, st, partials, s);
+		return;
+	}
+	const size_t smem = pat_table_bytes(A.n_pat, A.pat_maxch);
 	auto kern = k_spmv_pat<Epi>;
 	static PerDeviceOnce once;
 	if (once.first()) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kPatMaxChains * sizeof(PatChain) + 256 * sizeof(PatInfo)));

@@ -1,6 +1,7 @@
-// Host side of the row-pattern operator copy (csr.cuh "row-pattern operator"): choice of the matrix-wide stride S and the
-// grouping of a pattern's entries into chains of offsets S apart.  Plain C++ (no CUDA) so that tests/cxx/pat_chain_check.cpp
-// can run the decomposition and an emulation of the kernel's tiling on the CPU.
+// Host side of the row-pattern operator copy (csr.cuh "row-pattern operator"): choice of the matrix-wide stride S, the
+// grouping of a pattern's entries into chains of offsets S apart, the subset masks, and the plan of the plane-marching
+// kernel.  Plain C++ (no CUDA) so that tests/cxx/pat_chain_check.cpp can run the decomposition and an emulation of the
+// kernels' tiling on the CPU.
 #pragma once
 #include <algorithm>
 #include <cstring>
@@ -10,12 +11,16 @@
 namespace lcgb200 {
 
 constexpr int kPatChainLenH = 3;
+// m = entries (1..3) | line shift << 4 | position inside the window line << 8 | plane << 16 (the last three only for the
+// chains of the marching kernel's geometry pattern; the other users look at m & 3)
 struct PatChainH { double v[kPatChainLenH]; int off; int m; };
 static_assert(sizeof(PatChainH) == 32, "layout of csr.cuh: PatChain");
 
 // entries = one row as (col - row, value) pairs in row order.  Greedy: walk the entries by ascending offset, every
-// entry not yet used starts a chain and pulls in the first unused entries at +S and +2S.  The chain holding offset 0
-// (the diagonal) is moved to the front; *t0 = its index inside that chain, -1 when the row has no diagonal entry.
+// entry not yet used starts a chain and pulls in the first unused entries at +S and +2S.  Chains come out ordered by
+// their first offset, except that the chain holding offset 0 (the diagonal) is moved to the END: the kernels take x[row]
+// for the fused dot products from the registers of the last chain they process.  *t0 = the diagonal's index inside that
+// chain, -1 when the row has no diagonal entry.
 inline void pat_build_chains(const std::vector<std::pair<int, double>>& entries, int S, std::vector<PatChainH>& chains, int* t0)
 {
 	const size_t len = entries.size();
@@ -41,7 +46,14 @@ inline void pat_build_chains(const std::vector<std::pair<int, double>>& entries,
 	*t0 = -1;
 	for (size_t c = 0; c < chains.size() && *t0 < 0; c++)
 		for (int t = 0; t < chains[c].m; t++)
-			if ((long long)chains[c].off + (long long)t * S == 0) { std::swap(chains[0], chains[c]); *t0 = t; break; }
+			if ((long long)chains[c].off + (long long)t * S == 0)
+			{
+				const PatChainH d = chains[c];
+				chains.erase(chains.begin() + (ptrdiff_t)c);
+				chains.push_back(d);
+				*t0 = t;
+				break;
+			}
 }
 
 // S = the difference between two offsets of the pattern (>= 32 so that a warp's 32 consecutive rows stay inside one
@@ -104,7 +116,7 @@ inline void pat_build_masks(const std::vector<std::vector<std::pair<int, double>
 			{
 				bool found = false;
 				for (size_t c = 0; c < chains[s].size() && !found; c++)
-					for (int t = 0; t < chains[s][c].m; t++)
+					for (int t = 0; t < (chains[s][c].m & 3); t++)
 					{
 						const unsigned long long bit = 1ull << (c * kPatChainLenH + (size_t)t);
 						if (!(m & bit) && (long long)chains[s][c].off + (long long)t * S == (long long)e.first && same_bits(chains[s][c].v[t], e.second))
@@ -116,6 +128,143 @@ inline void pat_build_masks(const std::vector<std::vector<std::pair<int, double>
 			}
 			if (ok) { best_len = rows[s].size(); sup[p] = (int)s; mask[p] = m; }
 		}
+	}
+}
+
+// ---- the plane-marching kernel's plan (csr.cuh: k_spmv_pat_march) -------------------------------------------------------
+// The chains of ONE pattern (the geometry pattern: the interior row of a stencil, superset of the boundary rows) are laid
+// onto PLANES: a plane is a window of `nlines` segments of x, S apart, each 32 wx + kPatSpan values wide, that starts at
+// row + o_min[plane]; chain c reads its values at line shift_c + u, position d_c (off_c = o_min + shift_c S + d_c).
+// The planes' first offsets must be an arithmetic progression with step S2 (the plane stride nx ny of a grid): a thread
+// block then marches along S2 — block item k + 1 lies S2 rows behind block item k — and the window of plane p of item k
+// IS the window of plane p - 1 of item k + 1: one new window per item instead of G.
+constexpr int kPatSpanH = 8;          // extra values per window line: positions d in [0, 8]
+constexpr int kPatMaxShiftH = 2;      // line shift of a chain inside its plane
+constexpr int kPatMaxPlanesH = 4;
+struct PatMarchH {
+	int ok = 0;
+	int G = 0;          // planes
+	int S2 = 0;         // rows between consecutive planes
+	int o0 = 0;         // first offset of plane 0 (even)
+	int nlines = 0;     // lines per window: wy R + max(shift + m - 1)
+	int wx = 0, wy = 0; // warps of a block along the row index / along S
+	int dAb = 0;        // block items (of wy R S rows) between consecutive items of a march: S2 / (wy R S)
+	int group_begin[kPatMaxPlanesH + 1] = {0, 0, 0, 0, 0};   // chains [group_begin[g], group_begin[g + 1]) read plane group_plane[g]
+	int group_plane[kPatMaxPlanesH] = {0, 0, 0, 0};          // table order: the diagonal's plane last
+};
+
+// chains: the geometry pattern's (diagonal chain last, as pat_build_chains leaves them); reordered plane by plane on
+// success (diagonal's plane last, the diagonal chain still the very last) with the placement packed into m
+inline bool pat_plan_march(std::vector<PatChainH>& chains, int t0, int S, long long n_rows, long long n_cols, int R, PatMarchH& plan)
+{
+	plan = PatMarchH();
+	if (S % 128 != 0 || (n_cols & 1) || chains.empty()) return false;
+	const int wx = (S % 256 == 0) ? 8 : 4, wy = 8 / wx;
+	const size_t nc = chains.size();
+	std::vector<size_t> order(nc);
+	for (size_t i = 0; i < nc; i++) order[i] = i;
+	std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return chains[a].off < chains[b].off; });
+	// S2 = a difference between two chain offsets that is a multiple of the rows of a block item; every chain then sits on
+	// plane p = nearest multiple of S2, at r = off - p S2 inside it; all planes share the same first offset o_base (even, so
+	// that every window line starts on a 16-byte boundary: S, S2 and the row bases are even)
+	std::vector<long long> cand, entry_offs;
+	for (size_t c = 0; c < nc; c++) for (int t = 0; t < (chains[c].m & 3); t++) entry_offs.push_back((long long)chains[c].off + (long long)t * S);
+	for (size_t i = 0; i < entry_offs.size(); i++)
+		for (size_t j = 0; j < entry_offs.size(); j++)
+		{
+			const long long d = entry_offs[j] - entry_offs[i];
+			if (d > 4LL * S && d % ((long long)wy * R * S) == 0 && d <= n_rows) cand.push_back(d);
+		}
+	std::sort(cand.begin(), cand.end());
+	cand.erase(std::unique(cand.begin(), cand.end()), cand.end());
+	std::vector<int> plane(nc, -1), shift(nc, 0), dpos(nc, 0);
+	long long S2 = 0, o_base = 0; int G = 0;
+	for (long long c2 : cand)
+	{
+		std::vector<long long> pl(nc), r(nc);
+		long long rmin = 0, pmin = 0, pmax = 0;
+		for (size_t c = 0; c < nc; c++)
+		{
+			const long long off = chains[c].off;
+			pl[c] = (off >= 0 ? (off + c2 / 2) / c2 : -((-off + c2 / 2) / c2));
+			r[c] = off - pl[c] * c2;
+			if (c == 0) { rmin = r[c]; pmin = pmax = pl[c]; }
+			rmin = std::min(rmin, r[c]); pmin = std::min(pmin, pl[c]); pmax = std::max(pmax, pl[c]);
+		}
+		if (pmax - pmin + 1 > kPatMaxPlanesH || pmax == pmin) continue;
+		long long ob = rmin - 1;
+		ob -= ((ob % 2) + 2) % 2;
+		bool ok = true;
+		for (size_t c = 0; c < nc && ok; c++)
+		{
+			const long long q = r[c] - ob, sh = q / S, d = q - sh * S;
+			if (sh > kPatMaxShiftH || d > kPatSpanH) ok = false;
+			plane[c] = (int)(pl[c] - pmin); shift[c] = (int)sh; dpos[c] = (int)d;
+		}
+		if (!ok) continue;
+		S2 = c2; G = (int)(pmax - pmin + 1); o_base = pmin * c2 + ob;
+		break;
+	}
+	if (S2 == 0) return false;
+	std::vector<int> o_min((size_t)G);
+	for (int p = 0; p < G; p++) o_min[(size_t)p] = (int)(o_base + (long long)p * S2);
+	int extra_lines = 0;
+	for (size_t c = 0; c < nc; c++) extra_lines = std::max(extra_lines, shift[c] + (chains[c].m & 3) - 1);
+	// table order: plane by plane, the diagonal's plane (the plane of the last chain, if it holds the diagonal) last
+	const int diag_plane = t0 >= 0 ? plane[nc - 1] : -1;
+	std::vector<PatChainH> out;
+	int g = 0;
+	for (int pass = 0; pass < 2; pass++)
+		for (int p = 0; p < G; p++)
+		{
+			if ((pass == 0) == (p == diag_plane)) continue;
+			plan.group_begin[g] = (int)out.size(); plan.group_plane[g] = p;
+			for (size_t a = 0; a < nc; a++)
+			{
+				const size_t c = order[a];
+				if (plane[c] != p || (t0 >= 0 && c == nc - 1)) continue;
+				PatChainH ch = chains[c];
+				ch.m = (ch.m & 3) | (shift[c] << 4) | (dpos[c] << 8) | (p << 16);
+				out.push_back(ch);
+			}
+			if (p == diag_plane)
+			{
+				PatChainH ch = chains[nc - 1];
+				ch.m = (ch.m & 3) | (shift[nc - 1] << 4) | (dpos[nc - 1] << 8) | (p << 16);
+				out.push_back(ch);
+			}
+			g++;
+		}
+	plan.group_begin[G] = (int)out.size();
+	chains.swap(out);
+	plan.ok = 1; plan.G = G; plan.S2 = (int)S2; plan.o0 = o_min[0]; plan.nlines = wy * R + extra_lines; plan.wx = wx; plan.wy = wy;
+	plan.dAb = (int)(S2 / ((long long)wy * R * S));
+	return true;
+}
+
+// The marches: block items (Ab, ibb) = rows [Ab wy R S, (Ab + 1) wy R S) x positions [32 wx ibb, 32 wx (ibb + 1)) of every
+// super-row; a column = the items Ab0 + k dAb of one ibb.  Columns are cut into equal segments (a segment pays G - 1 extra
+// windows) so that there are about `target` segments in all — a multiple of the resident blocks, each of which then walks
+// the same number of items — but never shorter than min_len items.  seg = {first Ab, ibb, items, 0}
+struct PatSegH { int ab, ibb, len, pad; };
+inline void pat_build_segments(const PatMarchH& plan, long long n_rows, int S, int R, int target, int min_len, std::vector<PatSegH>& segs)
+{
+	segs.clear();
+	const long long n_super = (n_rows + S - 1) / S, n_a = (n_super + R - 1) / R;
+	const long long n_ab = (n_a + plan.wy - 1) / plan.wy;
+	const int nibb = S / (32 * plan.wx);
+	const long long n_columns = std::min<long long>(plan.dAb, n_ab) * nibb;
+	for (long long ab0 = 0; ab0 < std::min<long long>(plan.dAb, n_ab); ab0++)
+	{
+		const long long col_len = (n_ab - ab0 + plan.dAb - 1) / plan.dAb;
+		long long n_seg = std::max<long long>(1, target / std::max<long long>(1, n_columns));
+		n_seg = std::max<long long>(1, std::min<long long>(n_seg, col_len / std::max(1, min_len)));
+		for (int ibb = 0; ibb < nibb; ibb++)
+			for (long long s = 0; s < n_seg; s++)
+			{
+				const long long k0 = col_len * s / n_seg, k1 = col_len * (s + 1) / n_seg;
+				if (k1 > k0) segs.push_back(PatSegH{(int)(ab0 + k0 * plan.dAb), ibb, (int)(k1 - k0), 0});
+			}
 	}
 }
 

@@ -935,8 +935,9 @@ def test_compressed_operator_formats(torch_cuda, port, kind, g):
     """LCGB200_CSR_COMPRESS.  Level 2 (row patterns, 1 byte per ROW) for the constant-coefficient stencils, level 1
     (16-bit codes, 2 bytes per entry) for a 7-point matrix whose coefficients vary from row to row over a small set (too
     many distinct rows for patterns).  Same entries as the plain CSR copy.  The dictionary kernel adds a row's products in
-    the plain kernel's order (bitwise equal y); the pattern kernel adds them chain by chain (offsets one grid line apart
-    share their loads between the 8 rows of a thread), so y agrees to rounding; the solvers land on the same iterates."""
+    the plain kernel's order (bitwise equal y); the pattern kernels add them chain by chain (offsets one grid line apart
+    share their loads between the 8 rows of a thread), so y agrees to rounding; the solvers land on the same iterates.
+    With LCGB200_PAT_MARCH=1 grids of 128 points per line take the plane-marching kernel (test_pattern_march_kernel)."""
     torch = torch_cuda
     if kind == "7pt_varcoef":
         S = stencil.make_system("7pt", g)
@@ -988,6 +989,46 @@ def test_compressed_operator_formats(torch_cuda, port, kind, g):
     op = api.CsrOperator(R["row_ptr"], R["col"], R["val"], compress=True)
     assert op.format()["level"] == 0
     op.close()
+
+
+@pytest.mark.parametrize("kind,g", [("27pt", 128), ("7pt", 128)])
+def test_pattern_march_kernel(torch_cuda, port, kind, g, monkeypatch):
+    """LCGB200_PAT_MARCH=1 (read when the operator is created): k_spmv_pat_march — a producer warp feeds plane windows of x
+    into a shared-memory ring with TMA bulk copies, 8 consumer warps march along z and read one new window per item.  Same
+    y (to rounding) and the same fused dot products as the plain CSR copy and as the plain-load pattern kernel, same
+    iterates after a pinned number of PCG / CG iterations."""
+    torch = torch_cuda
+    S = stencil.make_system(kind, g)
+    n = S["n"]
+    plain = api.CsrOperator(S["row_ptr"], S["col"], S["val"], jacobi=True)
+    ldg = api.CsrOperator(S["row_ptr"], S["col"], S["val"], jacobi=True, compress=True)
+    monkeypatch.setenv("LCGB200_PAT_MARCH", "1")
+    march = api.CsrOperator(S["row_ptr"], S["col"], S["val"], jacobi=True, compress=True)
+    monkeypatch.delenv("LCGB200_PAT_MARCH")
+    assert march.format()["level"] == 2 and ldg.format()["level"] == 2
+    x = to_dev(torch, np.random.default_rng(3).standard_normal(n))
+    w = to_dev(torch, np.random.default_rng(4).standard_normal(n))
+    ys = [torch.empty_like(x) for _ in range(3)]
+    ds = [torch.zeros(3, dtype=torch.float64, device="cuda") for _ in range(3)]
+    for op, y, d in zip((plain, ldg, march), ys, ds):
+        op.spmv_dot(x, y, w, d)
+    torch.cuda.synchronize()
+    y_ref = port.spmv(S, x.cpu().numpy())
+    scale = np.linalg.norm(y_ref) / np.sqrt(n)
+    for y, d in zip(ys[1:], ds[1:]):
+        assert np.max(np.abs(y.cpu().numpy() - y_ref)) / scale < 1e-13
+        assert torch.allclose(ds[0], d, rtol=1e-12, atol=1e-9)
+    sid = api.LCG_PCG if kind == "27pt" else api.LCG_CG
+    para = api.lcg_default_parameters(epsilon=1e-300, max_iterations=30)
+    sols = []
+    for op in (plain, march):
+        m = np.zeros(n)
+        r = api.solve(op, sid, m, S["b"], param=para, jacobi=(sid == api.LCG_PCG))
+        assert r.ret == api.LCG_REACHED_MAX_ITERATIONS and r.iterations == 30
+        sols.append(m)
+    assert rel(sols[1], sols[0]) <= 1e-10
+    for op in (plain, ldg, march):
+        op.close()
 
 
 # ------------------------------------------------------------------------------------------------ reference-order mode
