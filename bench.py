@@ -296,14 +296,15 @@ def hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def parity_block(ctx, kind, solver, g=48, k=25):
+def parity_block(ctx, kind, solver, g=48, k=25, compress=False):
     """Driver-visible correctness of THIS run's path (1 GPU or the row-partitioned handle over all ranks): exactly k
     iterations of the workload's solver on a g^3 system of the workload's stencil, against the CPU oracle port on rank 0.
     North-star bar: solution rel-L2 <= 1e-8, same iteration count, same return code."""
     from liblcg_b200 import api
     torch = ctx.torch
     sid = SOLVER_ID[solver]
-    S = device_system(ctx, kind, g, solver)
+    S = device_system(ctx, kind, g, solver, compress=compress)   # --compress: the twin runs on the compressed operator copy too
+    fmt_level = S["op"].format()["level"]
     m_d = torch.zeros(S["n_loc"], dtype=torch.float64, device=ctx.dev)
     para = api.lcg_default_parameters(epsilon=1e-300, max_iterations=k)
     r = api.solve(S["op"], sid, m_d, S["b"], param=para, device=True, jacobi=(solver == "PCG"), stream=ctx.stream)
@@ -342,6 +343,7 @@ def parity_block(ctx, kind, solver, g=48, k=25):
                  "ret": r_exact.ret, "iterations": r_exact.iterations,
                  "note": "lcgb200_set_reference_order(1): second build of the loops without FMA contraction and with serial sums"}
     return {"system": f"{kind} {g}^3", "solver": solver, "pinned_iterations": k, "n_gpus": ctx.world, "rel_l2": rel, "reference_order": exact,
+            "operator_format": {0: "csr", 1: "dictionary codes", 2: "row patterns"}.get(fmt_level, str(fmt_level)),
             "ret_gpu": r.ret, "ret_cpu": cpu.ret, "iterations_gpu": r.iterations, "iterations_cpu": cpu.iters,
             "residual_gpu": r.residual, "residual_cpu": cpu.residual, "ok": bool(rel <= 1e-8 and r.ret == cpu.ret and r.iterations == cpu.iters),
             "checker": "oracle/lcg_oracle.c (CPU port, pinned bit-for-bit to the reference)", "error": err}
@@ -587,7 +589,7 @@ def run_ours(args, wl):
     close_system(ctx, S)
 
     # ---- parity of this run's path (all ranks take part) and the other BASELINE configs, measured in the same run
-    parity = None if fixture else parity_block(ctx, kind, solver)
+    parity = None if fixture else parity_block(ctx, kind, solver, compress=args.compress)
     extras = {}
     if not fixture and not args.no_extra_legs:
         legs = []

@@ -215,11 +215,10 @@ __global__ void k_pat_assign(int n_rows, const int* __restrict__ rp, const unsig
 	pat[row] = (unsigned char)id_of_slot[slot];
 }
 
-// pat_item[it] = the pattern id shared by ALL rows of warp work item `it` of k_spmv_pat (rows (a R + q) S + 32 ib + lane,
-// q < R, lanes with 32 ib + lane < S), 255 when a row is missing (beyond n_rows) or the ids differ;
-// pat_thread[32 it + lane] = the same for the R rows of one thread
-__global__ void k_pat_items(long long n_rows, int S, int nib, int n_items, const unsigned char* __restrict__ pat, unsigned char* __restrict__ item,
-	unsigned char* __restrict__ thread_code)
+// pat_thread[32 it + lane] = the pattern id shared by the R rows of one thread of warp work item `it` of k_spmv_pat (rows
+// (a R + q) S + 32 ib + lane, q < R; lanes with 32 ib + lane >= S own nothing), 255 when a row is missing (beyond n_rows)
+// or the ids differ
+__global__ void k_pat_items(long long n_rows, int S, int nib, int n_items, const unsigned char* __restrict__ pat, unsigned char* __restrict__ thread_code)
 {
 	const int it = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
 	if (it >= n_items) return;
@@ -235,10 +234,6 @@ __global__ void k_pat_items(long long n_rows, int S, int nib, int n_items, const
 			bad = bad || pq < 0 || pq != p0;
 		}
 	thread_code[(size_t)it * 32 + lane] = (unsigned char)((bad || p0 < 0) ? 255 : p0);
-	const int first = __shfl_sync(0xffffffffu, p0, 0);   // lane 0 always has 32 ib < S
-	bad = bad || (i < S && p0 != first);
-	const bool any_bad = __any_sync(0xffffffffu, bad);
-	if (lane == 0) item[it] = (unsigned char)(any_bad ? 255 : first);
 }
 
 // rows per pattern
@@ -288,7 +283,7 @@ void try_patterns(CsrHandle* h, const std::vector<int>& rp_h, const std::vector<
 	unsigned long long* d_key = dev_alloc<unsigned long long>(kPatTab);
 	int* d_rep = dev_alloc<int>(kPatTab); int* d_slot = dev_alloc<int>((size_t)n); int* d_fail = dev_alloc<int>(1);
 	int* d_id = dev_alloc<int>(kPatTab); unsigned char* d_pat = dev_alloc<unsigned char>((size_t)n);
-	unsigned char* d_tab = nullptr; unsigned char* d_item = nullptr; unsigned char* d_thread = nullptr; unsigned char* d_bitem = nullptr; int4* d_segs = nullptr;
+	unsigned char* d_tab = nullptr; unsigned char* d_thread = nullptr; unsigned char* d_bitem = nullptr; int4* d_segs = nullptr;
 	PatMarch* march = nullptr;
 	bool ok = false;
 	try
@@ -373,9 +368,9 @@ void try_patterns(CsrHandle* h, const std::vector<int>& rp_h, const std::vector<
 						PatInfo* ti = reinterpret_cast<PatInfo*>(tab.data() + np * maxch * sizeof(PatChainH));
 						for (size_t p = 0; p < np; p++) { std::copy(chains[p].begin(), chains[p].end(), tc + p * maxch); ti[p] = info[p]; }
 						const int n_items = (int)(n_a * nib);
-						d_tab = dev_alloc<unsigned char>(tab.size()); d_item = dev_alloc<unsigned char>((size_t)n_items); d_thread = dev_alloc<unsigned char>((size_t)n_items * 32);
+						d_tab = dev_alloc<unsigned char>(tab.size()); d_thread = dev_alloc<unsigned char>((size_t)n_items * 32);
 						LCG_CUDA_CHECK(cudaMemcpy(d_tab, tab.data(), tab.size(), cudaMemcpyHostToDevice));
-						k_pat_items<<<(unsigned)(((long long)n_items * 32 + 255) / 256), 256>>>(n, S, (int)nib, n_items, d_pat, d_item, d_thread);
+						k_pat_items<<<(unsigned)(((long long)n_items * 32 + 255) / 256), 256>>>(n, S, (int)nib, n_items, d_pat, d_thread);
 						LCG_CUDA_CHECK(cudaGetLastError());
 						if (plan.ok)
 						{
@@ -415,7 +410,7 @@ void try_patterns(CsrHandle* h, const std::vector<int>& rp_h, const std::vector<
 							}
 						}
 						LCG_CUDA_CHECK(cudaDeviceSynchronize());
-						h->pat = d_pat; h->pat_item = d_item; h->pat_thread = d_thread; h->pat_chain = d_tab; h->n_pat = (int)np;
+						h->pat = d_pat; h->pat_thread = d_thread; h->pat_chain = d_tab; h->n_pat = (int)np;
 						h->pat_maxch = (int)maxch; h->pat_stride = S; h->pat_nib = (int)nib; h->pat_items = n_items;
 						h->pat_bitem = d_bitem; h->pat_segs = d_segs; h->pat_march = march;
 						ok = true;
@@ -426,12 +421,12 @@ void try_patterns(CsrHandle* h, const std::vector<int>& rp_h, const std::vector<
 	}
 	catch (...)
 	{
-		cudaFree(d_key); cudaFree(d_rep); cudaFree(d_slot); cudaFree(d_fail); cudaFree(d_id); cudaFree(d_pat); cudaFree(d_tab); cudaFree(d_item); cudaFree(d_thread);
+		cudaFree(d_key); cudaFree(d_rep); cudaFree(d_slot); cudaFree(d_fail); cudaFree(d_id); cudaFree(d_pat); cudaFree(d_tab); cudaFree(d_thread);
 		cudaFree(d_bitem); cudaFree(d_segs); delete march;
 		throw;
 	}
 	cudaFree(d_key); cudaFree(d_rep); cudaFree(d_slot); cudaFree(d_fail); cudaFree(d_id);
-	if (!ok) { cudaFree(d_pat); cudaFree(d_tab); cudaFree(d_item); cudaFree(d_thread); cudaFree(d_bitem); cudaFree(d_segs); delete march; }
+	if (!ok) { cudaFree(d_pat); cudaFree(d_tab); cudaFree(d_thread); cudaFree(d_bitem); cudaFree(d_segs); delete march; }
 }
 
 // LCGB200_CSR_COMPRESS: if the matrix has <= 256 distinct values and <= 256 distinct (col - row) offsets, store a second
@@ -633,7 +628,7 @@ void destroy_handle(CsrHandle* h)
 	cudaFree(h->row_ptr); cudaFree(h->col); cudaFree(h->val); cudaFree(h->tiles);
 	cudaFree(h->t_row_ptr); cudaFree(h->t_col); cudaFree(h->t_val); cudaFree(h->t_tiles);
 	cudaFree(h->code); cudaFree(h->vdict); cudaFree(h->odict); cudaFree(h->dtiles);
-	cudaFree(h->pat); cudaFree(h->pat_item); cudaFree(h->pat_thread); cudaFree(h->pat_chain); cudaFree(h->pat_bitem); cudaFree(h->pat_segs); delete h->pat_march;
+	cudaFree(h->pat); cudaFree(h->pat_thread); cudaFree(h->pat_chain); cudaFree(h->pat_bitem); cudaFree(h->pat_segs); delete h->pat_march;
 	free_factor(h->icL); free_factor(h->icU); cudaFree(h->ic_tmp);
 	cudaFree(h->diag); cudaFree(h->ws);
 	cudaFree(h->d_state); cudaFree(h->d_partials);

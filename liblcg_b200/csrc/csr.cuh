@@ -64,10 +64,10 @@ struct CsrDev {
 	const int4* dtiles = nullptr; int n_dtiles = 0, dchunk = 1, dlpr = 1;
 	// row-pattern copy (real operators, optional): one pattern id per ROW + a table of the distinct rows
 	// (csr.cuh "row-pattern operator": chains of offsets S apart, one byte per warp work item)
-	// pat_chain: chains | info of all patterns, one device array; pat_item: a byte per warp item (k_spmv_pat);
+	// pat_chain: chains | info of all patterns, one device array;
 	// pat_bitem / pat_segs / pat_march: block items, march segments and plan of k_spmv_pat_march (host pointer, null = no plan)
 	// pat_thread: a byte per thread of a warp item (the pattern its R rows share, 255 = mixed)
-	const unsigned char* pat = nullptr; const unsigned char* pat_item = nullptr; const unsigned char* pat_thread = nullptr; const void* pat_chain = nullptr;
+	const unsigned char* pat = nullptr; const unsigned char* pat_thread = nullptr; const void* pat_chain = nullptr;
 	const unsigned char* pat_bitem = nullptr; const void* pat_segs = nullptr; const PatMarch* pat_march = nullptr;
 	int n_pat = 0, pat_maxch = 0, pat_stride = 0, pat_nib = 0, pat_items = 0;
 };
@@ -565,20 +565,24 @@ __global__ void __launch_bounds__(kSpmvThreads, kSpmvCtasPerSm) k_spmv_dict(CsrD
 //    u S] serves row q = u - t through chain entry t.  27-point stencil, R = 8: 9 chains x 10 reads for 8 rows = 11.25
 //    per row instead of 27, and one 32-byte table read per chain instead of one per entry.  Lanes of a warp sit on 32
 //    consecutive rows.  Work item of a warp = R x 32 rows: rows (A R + q) S + 32 ib + lane.
-// 2. Rows that differ.  A byte per item says whether all its rows share one pattern (the rule inside a stencil).  If not,
-//    each thread looks at its own R rows: same pattern -> that pattern's chains; patterns that are SUBSETS of one longer
-//    pattern (a column of grid points that starts on a face: the face row is the interior row minus the entries that
-//    leave the grid; pat_host.h: pat_build_masks) -> the longer pattern's chains with a 64-bit presence mask per row,
-//    reads still shared; anything else row by row through the same chain table.
-// 3. k_spmv_pat (any matrix with <= 255 distinct rows): the reads are plain loads.  Measured at 27-point 256^3: 0.174 ms,
-//    LSU data pipe 43 %, every unit below 45 % — latency-bound (10 dependent rounds of L2 latency per item).
-// 4. k_spmv_pat_march (stride a multiple of 128, chain offsets on planes S2 apart — 3-D grids with nx % 128 == 0 and
-//    ny % 8 == 0): a thread block of 8 consumer warps + 1 producer warp MARCHES along S2 (z).  The producer's lanes copy
-//    the lines of one plane window — the x values all 8 warps need from one plane: (wy R + 2) lines x (32 wx + 8)
-//    values — into a ring of shared-memory stages with TMA bulk copies (full/empty mbarriers, as k_spmv does for the
-//    matrix).  The window of plane p of item k is the window of plane p - 1 of item k + 1, so ONE window is loaded per
-//    item instead of G = 3: x crosses L2 -> SM 1.3 times per SpMV instead of 4, and the consumers read x out of shared
-//    memory with immediate offsets (no address arithmetic, no global-memory latency on their path).
+// 2. Rows that differ.  A byte per THREAD of an item (pat_thread, loaded one round ahead) holds the pattern its R rows share
+//    — the rule inside a stencil; lanes at the ends of a grid line simply hold another id.  255 = the rows differ: patterns
+//    that are SUBSETS of one longer pattern (a column of grid points that starts on a face: the face row is the interior row
+//    minus the entries that leave the grid; pat_host.h: pat_build_masks) take the longer pattern's chains with a 64-bit
+//    presence mask per row, reads still shared; anything else goes row by row through the same chain table.
+// 3. k_spmv_pat (any matrix with <= 253 distinct rows; the default): the reads are plain loads through L1.  The 8 warps of
+//    a block take the items of a round in rotation, so the slower items (ends of grid lines) do not pile up on two warps.
+//    Measured at 27-point 256^3 (profiles/README_r02.md): 0.122 ms (round 1: 0.222), LSU data pipe 56 %, issue slots 56 %
+//    busy, 1015 instructions per 256 rows — bound by instruction issue and load latency, not by bytes (DRAM: 0.24 GB).
+// 4. k_spmv_pat_march (opt-in, LCGB200_PAT_MARCH=1; stride a multiple of 128, chain offsets on planes S2 apart — 3-D grids
+//    with nx % 128 == 0 and ny % 8 == 0): a thread block of 8 consumer warps + 1 producer warp MARCHES along S2 (z).  The
+//    producer's lanes copy the lines of one plane window — the x values all 8 warps need from one plane: (wy R + 2) lines x
+//    (32 wx + 8) values — into a ring of shared-memory stages with TMA bulk copies (full/empty mbarriers, as k_spmv does
+//    for the matrix).  The window of plane p of item k is the window of plane p - 1 of item k + 1, so ONE window is loaded
+//    per item instead of G = 3: x crosses L2 -> SM 1.3 times per SpMV instead of 4 (measured 222 MB instead of 545 MB),
+//    and the consumers read x out of shared memory with immediate offsets.  Measured 0.175 ms: the generic chain walk costs
+//    as many instructions as in k_spmv_pat and a block advances at the pace of its slowest warp, so on one B200 — where x
+//    stays in L2 anyway — the plain-load kernel wins; kept for systems whose x does not fit L2.
 // Entries are accumulated chain by chain with fma (a different order from the CSR row order: y agrees with the plain copy
 // to rounding, not bitwise).
 constexpr int kPatRows = 8;            // R: rows (S apart) a thread computes together
