@@ -247,6 +247,55 @@ __global__ void k_pat_count(int n_rows, const unsigned char* __restrict__ pat, u
 	if (s_cnt[threadIdx.x]) atomicAdd(&count[threadIdx.x], s_cnt[threadIdx.x]);
 }
 
+// thread items of k_spmv_pat_box: thread (it, lane) owns the rows (a R + q) S + 64 ib + 2 lane + e, q < R, e < 2.  flags[32 it +
+// lane] = what its rows lack of the box (csr.cuh: kBoxDrop*), 255 when they are no consistent sub-boxes: a row beyond the matrix
+// or without row flags, "no left column" on the right row of the pair (or vice versa), "no lower line" anywhere but on the first
+// line, "no upper line" anywhere but on the last, planes that differ between rows.  *n_odd counts the 255s among threads with rows.
+__global__ void k_pat_box_flags(long long n_rows, int S, int nib, int n_items, const unsigned char* __restrict__ pat,
+	const unsigned char* __restrict__ rowflags, unsigned char* __restrict__ flags, unsigned int* n_odd)
+{
+	__shared__ unsigned char s_rf[256];
+	s_rf[threadIdx.x] = rowflags[threadIdx.x];
+	__syncthreads();
+	const int it = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+	if (it >= n_items) return;
+	const int a = it / nib, ib = it - a * nib;
+	const int i = ib * 64 + 2 * lane;
+	if (i >= S) { flags[(size_t)it * 32 + lane] = 255; return; }
+	int out = 0; bool bad = false, any_row = false;
+	int planes = -1;
+	for (int q = 0; q < kPatRows; q++)
+		for (int e = 0; e < 2; e++)
+		{
+			const long long row = ((long long)a * kPatRows + q) * S + i + e;
+			if (row >= n_rows) { bad = true; continue; }
+			any_row = true;
+			const int f = (int)s_rf[pat[row]];
+			if (f & 0x80) { bad = true; continue; }
+			if ((f & kBoxDropL) && e != 0) bad = true;
+			if ((f & kBoxDropR) && e != 1) bad = true;
+			if ((f & kBoxDropLow) && q != 0) bad = true;
+			if ((f & kBoxDropHigh) && q != kPatRows - 1) bad = true;
+			if (planes < 0) planes = f & ~15;
+			if ((f & ~15) != planes) bad = true;
+			out |= f;
+		}
+	// a slice is dropped for the whole thread, so the rows it is dropped FROM must be all the rows it would touch: the left value
+	// serves every left row, the first line only row 0, the last line only row R - 1 — but both rows of the pair on that line
+	if (!bad)
+		for (int q = 0; q < kPatRows && !bad; q++)
+			for (int e = 0; e < 2; e++)
+			{
+				const int f = (int)s_rf[pat[((long long)a * kPatRows + q) * S + i + e]];
+				if ((out & kBoxDropL) && e == 0 && !(f & kBoxDropL)) bad = true;
+				if ((out & kBoxDropR) && e == 1 && !(f & kBoxDropR)) bad = true;
+				if ((out & kBoxDropLow) && q == 0 && !(f & kBoxDropLow)) bad = true;
+				if ((out & kBoxDropHigh) && q == kPatRows - 1 && !(f & kBoxDropHigh)) bad = true;
+			}
+	flags[(size_t)it * 32 + lane] = (unsigned char)(bad ? 255 : out);
+	if (bad && any_row) atomicAdd(n_odd, 1u);
+}
+
 // block items of k_spmv_pat_march, one block of 8 warps per item: bitem[16 bi + w] = the pattern all rows of warp w's item
 // share (255 = mixed, 254 = the item has no rows), bitem[16 bi + 8] = 1 when every existing row of the block item is a
 // subset of the geometry pattern gpat (sup == gpat with a non-empty mask)
@@ -285,6 +334,7 @@ void try_patterns(CsrHandle* h, const std::vector<int>& rp_h, const std::vector<
 	int* d_id = dev_alloc<int>(kPatTab); unsigned char* d_pat = dev_alloc<unsigned char>((size_t)n);
 	unsigned char* d_tab = nullptr; unsigned char* d_thread = nullptr; unsigned char* d_bitem = nullptr; int4* d_segs = nullptr;
 	PatMarch* march = nullptr;
+	PatBox* box = nullptr; unsigned char* d_box_flags = nullptr;
 	bool ok = false;
 	try
 	{
@@ -409,7 +459,45 @@ void try_patterns(CsrHandle* h, const std::vector<int>& rp_h, const std::vector<
 								march->nst = plan.G + ahead;
 							}
 						}
+						// the box kernel: dense box stencils on grids whose lines and planes align with the threads' columns
+						static const bool no_box = getenv("LCGB200_PAT_NO_BOX") != nullptr;   // comparison runs
+						PatBoxH bplan; std::vector<unsigned char> rowflags;
+						if (!no_box && !plan.ok && S % 2 == 0)
+						{
+							std::vector<int> sup2(np); std::vector<unsigned long long> mask2(np);
+							for (size_t p = 0; p < np; p++) { sup2[p] = info[p].sup; mask2[p] = info[p].mask; }
+							pat_plan_box(chains[longest], S, (int)longest, sup2, mask2, bplan, rowflags);
+						}
+						if (bplan.ok)
+						{
+							const int nib64 = (S + 63) / 64;
+							const long long n_items64 = n_a * nib64;
+							rowflags.resize(256, 0x80);
+							unsigned char* d_rf = dev_alloc<unsigned char>(256);
+							unsigned int* d_odd = reinterpret_cast<unsigned int*>(d_key);
+							d_box_flags = dev_alloc<unsigned char>((size_t)n_items64 * 32);
+							LCG_CUDA_CHECK(cudaMemcpy(d_rf, rowflags.data(), 256, cudaMemcpyHostToDevice));
+							LCG_CUDA_CHECK(cudaMemset(d_odd, 0, sizeof(unsigned int)));
+							k_pat_box_flags<<<(unsigned)((n_items64 * 32 + 255) / 256), 256>>>(n, S, nib64, (int)n_items64, d_pat, d_rf, d_box_flags, d_odd);
+							LCG_CUDA_CHECK(cudaGetLastError());
+							unsigned int n_odd = 0;
+							LCG_CUDA_CHECK(cudaMemcpy(&n_odd, d_odd, sizeof(unsigned int), cudaMemcpyDeviceToHost));
+							cudaFree(d_rf);
+							// worth it only when few threads fall back to the chain tables (they cost a whole warp its time)
+							if ((double)n_odd * 2 * kPatRows <= 0.10 * (double)n)
+							{
+								box = new PatBox();
+								box->G = bplan.G;
+								for (int g = 0; g < bplan.G; g++)
+								{
+									box->center[g] = bplan.center[g];
+									for (int dx = 0; dx < 3; dx++) for (int j = 0; j < 3; j++) box->coef[g][dx][j] = bplan.coef[g][dx][j];
+								}
+							}
+							else { cudaFree(d_box_flags); d_box_flags = nullptr; }
+						}
 						LCG_CUDA_CHECK(cudaDeviceSynchronize());
+						h->pat_box = box; h->pat_box_flags = d_box_flags;
 						h->pat = d_pat; h->pat_thread = d_thread; h->pat_chain = d_tab; h->n_pat = (int)np;
 						h->pat_maxch = (int)maxch; h->pat_stride = S; h->pat_nib = (int)nib; h->pat_items = n_items;
 						h->pat_bitem = d_bitem; h->pat_segs = d_segs; h->pat_march = march;
@@ -422,11 +510,11 @@ void try_patterns(CsrHandle* h, const std::vector<int>& rp_h, const std::vector<
 	catch (...)
 	{
 		cudaFree(d_key); cudaFree(d_rep); cudaFree(d_slot); cudaFree(d_fail); cudaFree(d_id); cudaFree(d_pat); cudaFree(d_tab); cudaFree(d_thread);
-		cudaFree(d_bitem); cudaFree(d_segs); delete march;
+		cudaFree(d_bitem); cudaFree(d_segs); delete march; cudaFree(d_box_flags); delete box;
 		throw;
 	}
 	cudaFree(d_key); cudaFree(d_rep); cudaFree(d_slot); cudaFree(d_fail); cudaFree(d_id);
-	if (!ok) { cudaFree(d_pat); cudaFree(d_tab); cudaFree(d_thread); cudaFree(d_bitem); cudaFree(d_segs); delete march; }
+	if (!ok) { cudaFree(d_pat); cudaFree(d_tab); cudaFree(d_thread); cudaFree(d_bitem); cudaFree(d_segs); delete march; cudaFree(d_box_flags); delete box; }
 }
 
 // LCGB200_CSR_COMPRESS: if the matrix has <= 256 distinct values and <= 256 distinct (col - row) offsets, store a second
@@ -628,7 +716,7 @@ void destroy_handle(CsrHandle* h)
 	cudaFree(h->row_ptr); cudaFree(h->col); cudaFree(h->val); cudaFree(h->tiles);
 	cudaFree(h->t_row_ptr); cudaFree(h->t_col); cudaFree(h->t_val); cudaFree(h->t_tiles);
 	cudaFree(h->code); cudaFree(h->vdict); cudaFree(h->odict); cudaFree(h->dtiles);
-	cudaFree(h->pat); cudaFree(h->pat_thread); cudaFree(h->pat_chain); cudaFree(h->pat_bitem); cudaFree(h->pat_segs); delete h->pat_march;
+	cudaFree(h->pat); cudaFree(h->pat_thread); cudaFree(h->pat_chain); cudaFree(h->pat_bitem); cudaFree(h->pat_segs); delete h->pat_march; cudaFree(h->pat_box_flags); delete h->pat_box;
 	free_factor(h->icL); free_factor(h->icU); cudaFree(h->ic_tmp);
 	cudaFree(h->diag); cudaFree(h->ws);
 	cudaFree(h->d_state); cudaFree(h->d_partials);

@@ -47,6 +47,7 @@ constexpr int kSpmvThreads = kThreads + 32;   // 8 consumer warps + 1 producer w
 constexpr int kSpmvCtasPerSm = LCG_CTAS;
 
 struct PatMarch;   // plan of the plane-marching row-pattern kernel (below)
+struct PatBox;     // plan of the box row-pattern kernel (below)
 template <class T>
 struct CsrDev {
 	int n_rows = 0, n_cols = 0, nnz = 0, n_tiles = 0, lpr = 1, chunk = 1;
@@ -69,6 +70,8 @@ struct CsrDev {
 	// pat_thread: a byte per thread of a warp item (the pattern its R rows share, 255 = mixed)
 	const unsigned char* pat = nullptr; const unsigned char* pat_thread = nullptr; const void* pat_chain = nullptr;
 	const unsigned char* pat_bitem = nullptr; const void* pat_segs = nullptr; const PatMarch* pat_march = nullptr;
+	// pat_box / pat_box_flags: plan (host pointer, null = no plan) and one byte per thread item of k_spmv_pat_box
+	const PatBox* pat_box = nullptr; const unsigned char* pat_box_flags = nullptr;
 	int n_pat = 0, pat_maxch = 0, pat_stride = 0, pat_nib = 0, pat_items = 0;
 };
 
@@ -1085,6 +1088,130 @@ __global__ void __launch_bounds__(kSpmvThreads, 2) k_spmv_pat_march(CsrDev<doubl
 	}
 }
 
+// ---- the box kernel (paragraph 5 of the overview above) ------------------------------------------------------------------
+// Geometry pattern = a dense box: G planes x (dx = -1, 0, +1) x (dy = -1, 0, +1) around even centres (pat_host.h:
+// pat_plan_box).  A thread owns an aligned PAIR of rows on each of R lines: per plane and window line it loads the pair
+// (one 16-byte load) and the value on either side, and 18 fma consume them — 3.75 loads and 3 load instructions per 18
+// products, against 10 loads per 24 products in k_spmv_pat.  The 27 coefficients are kernel parameters: the fma read them
+// straight out of the constant bank, no register, no table read.  Everything is unrolled: no index arithmetic per chain.
+// Boundary rows are the box minus whole slices, so a byte of flags per thread says what to leave out: the value left /
+// right of the pair (dx), the first / last window line (dy: it serves only the thread's first / last row), a whole plane
+// (dz).  255 = rows that are no such sub-box (or lie beyond the matrix): both columns go through pat_item_ldg.
+struct PatBox {
+	int G = 0;
+	int center[3] = {0, 0, 0};
+	double coef[3][3][3] = {};   // [plane][dx + 1][line j]
+};
+constexpr int kBoxDropL = 1, kBoxDropR = 2, kBoxDropLow = 4, kBoxDropHigh = 8, kBoxDropG0 = 16;
+
+template <class Epi>
+__global__ void __launch_bounds__(kThreads, 2) k_spmv_pat_box(CsrDev<double> A, PatBox B, const double* __restrict__ x, double* __restrict__ y, Epi epi_in,
+	DevState* st, double* partials)
+{
+	pdl_enter();
+	if (st_done(st)) return;
+	constexpr int R = kPatRows;
+	extern __shared__ __align__(128) unsigned char smem[];
+	const PatChain* s_ch = reinterpret_cast<const PatChain*>(smem);   // the chain tables serve the rows that are no sub-box
+	const PatInfo* s_info = reinterpret_cast<const PatInfo*>(smem + (size_t)A.n_pat * A.pat_maxch * sizeof(PatChain));
+	pat_tables_to_smem(A, smem);
+	__syncthreads();
+
+	Epi epi = epi_in;
+	epi.begin(st);
+	double acc[Epi::NRED > 0 ? Epi::NRED : 1];
+#pragma unroll
+	for (int r = 0; r < (Epi::NRED > 0 ? Epi::NRED : 1); r++) acc[r] = 0.0;
+
+	const int S = A.pat_stride, n_rows = A.n_rows;
+	const int nib = (S + 63) / 64;                       // warp items per R lines: 64 rows of every line
+	const int n_items = A.pat_items / A.pat_nib * nib;   // pat_items = groups of R lines x pat_nib
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	constexpr int WPB = kThreads / 32;
+	auto item_of = [&](int round) { return (blockIdx.x + round * (int)gridDim.x) * WPB + ((warp + round) & (WPB - 1)); };
+	int it = item_of(0);
+	int flags = it < n_items ? (int)A.pat_box_flags[(size_t)it * 32 + lane] : 255;
+	for (int round = 0; (blockIdx.x + round * (int)gridDim.x) * WPB < n_items; round++)
+	{
+		const int it_next = item_of(round + 1);
+		const int flags_next = it_next < n_items ? (int)A.pat_box_flags[(size_t)it_next * 32 + lane] : 255;
+		if (it < n_items)
+		{
+			const int a = it / nib, ib = it - a * nib;
+			const int i = ib * 64 + 2 * lane;
+			const int row0 = a * R * S + i;   // even: S is even
+			if (i < S)
+			{
+				if (flags != 255)
+				{
+					double s0[R], s1[R];
+#pragma unroll
+					for (int q = 0; q < R; q++) { s0[q] = 0.0; s1[q] = 0.0; }
+#pragma unroll
+					for (int g = 0; g < 3; g++)
+					{
+						if (g < B.G && !(flags & (kBoxDropG0 << g)))
+						{
+							const int xg = row0 + B.center[g];
+#pragma unroll
+							for (int u = 0; u < R + 2; u++)
+							{
+								double xm = 0.0, x0 = 0.0, x1 = 0.0, xp = 0.0;
+								const bool line_on = !((u == 0 && (flags & kBoxDropLow)) || (u == R + 1 && (flags & kBoxDropHigh)));
+								if (line_on)
+								{
+									const double* pl = x + (xg + u * S);
+									const double2 c = __ldg(reinterpret_cast<const double2*>(pl));
+									x0 = c.x; x1 = c.y;
+									if (!(flags & kBoxDropL)) xm = __ldg(pl - 1);
+									if (!(flags & kBoxDropR)) xp = __ldg(pl + 2);
+								}
+#pragma unroll
+								for (int j = 0; j < 3; j++)
+								{
+									const int q = u - j;
+									if (q >= 0 && q < R)
+									{
+										s0[q] = fma(B.coef[g][0][j], xm, s0[q]); s0[q] = fma(B.coef[g][1][j], x0, s0[q]); s0[q] = fma(B.coef[g][2][j], x1, s0[q]);
+										s1[q] = fma(B.coef[g][0][j], x0, s1[q]); s1[q] = fma(B.coef[g][1][j], x1, s1[q]); s1[q] = fma(B.coef[g][2][j], xp, s1[q]);
+									}
+								}
+							}
+						}
+					}
+#pragma unroll
+					for (int q = 0; q < R; q++)
+					{
+						const int row = row0 + q * S;
+						const double2 xc = __ldg(reinterpret_cast<const double2*>(x + row));   // dead code for epilogues that ignore x[row]
+						*reinterpret_cast<double2*>(y + row) = make_double2(s0[q], s1[q]);
+						epi.row(row, s0[q], xc.x, acc);
+						epi.row(row + 1, s1[q], xc.y, acc);
+					}
+				}
+				else
+				{	// no sub-box: the two columns one after the other through the chain tables (k_spmv_pat's thread item (a, i / 32, i % 32))
+					for (int e = 0; e < 2; e++)
+					{
+						const int tcode = (int)A.pat_thread[(size_t)a * A.pat_nib * 32 + i + e];
+						pat_item_ldg<Epi>(A.pat, x, y, s_ch, s_info, A.pat_maxch, S, n_rows, row0 + e, tcode, true, epi, acc);
+					}
+				}
+			}
+		}
+		it = it_next; flags = flags_next;
+	}
+	if (Epi::NRED > 0)
+	{
+		double tot[Epi::NRED > 0 ? Epi::NRED : 1];
+		if (grid_reduce<(Epi::NRED > 0 ? Epi::NRED : 1)>(acc, partials, &st->ticket, tot))
+		{
+			if (st->multi) { if (reduce_across_ranks(st, tot, Epi::NRED)) epi.finish(st, tot); }
+			else if ((threadIdx.x & 31) == 0) epi.finish(st, tot);
+		}
+	}
+}
+
 inline size_t pat_table_bytes(int n_pat, int maxch) { return (size_t)n_pat * maxch * sizeof(PatChain) + (size_t)n_pat * sizeof(PatInfo); }
 // the marching kernel: window stages + the geometry pattern's chains + info of all patterns.  Two blocks fit an SM (227 KB,
 // 1 KB reserved and about 1.3 KB of static shared memory per block) up to kPatMarchSmemFor2 each
@@ -1111,6 +1238,20 @@ inline void launch_spmv_pat_march(const CsrDev<double>& A, const double* x, doub
 template <class Epi>
 inline void launch_spmv_pat(const CsrDev<double>& A, const double* x, double* y, const Epi& epi, DevState* st, double* partials, cudaStream_t s)
 {
+	if (A.pat_box && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0)
+	{	// 16-byte loads of x and stores of y: the plan guarantees even row indices
+		const size_t smem = pat_table_bytes(A.n_pat, A.pat_maxch);
+		auto kern = k_spmv_pat_box<Epi>;
+		static PerDeviceOnce once;
+		if (once.first()) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kPatMaxChains * sizeof(PatChain) + 256 * sizeof(PatInfo)));
+		const int n_items = A.pat_items / A.pat_nib * ((A.pat_stride + 63) / 64);
+		const int n_blocks = (n_items + kThreads / 32 - 1) / (kThreads / 32);
+		const int limit = spmv_grid_limit(2);
+		int grid = n_blocks < limit ? n_blocks : limit;
+		if (grid < 1) grid = 1;
+		launch_k(kern, grid, kThreads, smem, s, A, *A.pat_box, x, y, epi, st, partials);
+		return;
+	}
 	if (A.pat_march && (reinterpret_cast<uintptr_t>(x) & 15) == 0)
 	{	// TMA bulk copies need 16-byte aligned sources; the plan already guarantees even row bases and an even vector length
 		if (A.pat_march->wx == 8) launch_spmv_pat_march<Epi, 8>(A, x, y, epi, st, partials, s);

@@ -58,6 +58,7 @@ struct CsrHandle {
 	// row-pattern copy: one id per row + the table of distinct rows
 	unsigned char* pat = nullptr; unsigned char* pat_thread = nullptr; void* pat_chain = nullptr;
 	unsigned char* pat_bitem = nullptr; void* pat_segs = nullptr; PatMarch* pat_march = nullptr;   // plane-marching kernel (optional)
+	PatBox* pat_box = nullptr; unsigned char* pat_box_flags = nullptr;                              // box kernel (dense box stencils)
 	int n_pat = 0, pat_maxch = 0, pat_stride = 0, pat_nib = 0, pat_items = 0;
 	// IC(0) preconditioner (LCGB200_CSR_IC0): L (rows, diagonal last) and U = L^T (rows, diagonal first) with their level
 	// orders, plus the vector between the two triangular solves
@@ -89,7 +90,7 @@ struct CsrHandle {
 		v.comm = halo_in_spmv() ? comm->dev() : nullptr;
 		v.row_ptr = row_ptr; v.col = col; v.val = (const T*)val; v.tiles = tiles;
 		v.code = code; v.vdict = vdict; v.odict = odict; v.dtiles = dtiles; v.n_dtiles = n_dtiles; v.dchunk = dchunk; v.dlpr = dlpr;
-		v.pat = pat; v.pat_thread = pat_thread; v.pat_chain = pat_chain; v.pat_bitem = pat_bitem; v.pat_segs = pat_segs; v.pat_march = pat_march;
+		v.pat = pat; v.pat_thread = pat_thread; v.pat_chain = pat_chain; v.pat_bitem = pat_bitem; v.pat_segs = pat_segs; v.pat_march = pat_march; v.pat_box = pat_box; v.pat_box_flags = pat_box_flags;
 		v.n_pat = n_pat; v.pat_maxch = pat_maxch; v.pat_stride = pat_stride; v.pat_nib = pat_nib; v.pat_items = pat_items;
 		return v;
 	}

@@ -268,4 +268,83 @@ inline void pat_build_segments(const PatMarchH& plan, long long n_rows, int S, i
 	}
 }
 
+
+// ---- the box kernel's plan (csr.cuh: k_spmv_pat_box) --------------------------------------------------------------------
+// Geometry pattern = a DENSE BOX: G groups (planes) of three chains each — offsets e_g - 1, e_g, e_g + 1 around an EVEN
+// centre e_g, three entries S apart per chain (a 27-point stencil: 3 planes x (dx = -1, 0, +1) x (dy = -1, 0, +1)).  A
+// thread then owns TWO neighbouring rows per line (an aligned pair) x R lines, reads each window line as one 16-byte pair
+// + the two values left and right of it, and serves 18 products per line and group out of 4 loaded values.  The rows on
+// the boundary of the grid are the box minus whole slices: no left / right column (dx), no lower / upper line (dy), no
+// group (dz); `rowflags[p]` says which slices pattern p lacks (0x80 = p is no such sub-box of the geometry pattern).
+constexpr int kPatBoxMaxGroups = 3;   // flag bits 4..6: the thread flags stay below 0x80
+constexpr int kBoxHDropL = 1, kBoxHDropR = 2, kBoxHDropLow = 4, kBoxHDropHigh = 8, kBoxHDropG0 = 16;   // | kBoxHDropG0 << g (csr.cuh: kBoxDrop*)
+struct PatBoxH {
+	int ok = 0, G = 0;
+	int center[kPatBoxMaxGroups] = {0, 0, 0};
+	double coef[kPatBoxMaxGroups][3][3] = {};   // [group][dx + 1][line j]: the value at offset center + (dx) + j S
+	int chain_of[kPatBoxMaxGroups][3] = {};     // chain index (in the geometry pattern's table) of (group, dx + 1)
+};
+
+// chains = the geometry pattern's (any order).  Fills plan and, with the subset masks of all patterns over the geometry
+// pattern's chains (pat_build_masks), the row flags of every pattern.
+inline bool pat_plan_box(const std::vector<PatChainH>& chains, int S, int gpat, const std::vector<int>& sup, const std::vector<unsigned long long>& mask,
+	PatBoxH& plan, std::vector<unsigned char>& rowflags)
+{
+	plan = PatBoxH();
+	const size_t nc = chains.size();
+	if ((S & 1) || nc == 0 || nc % 3 != 0 || nc / 3 > (size_t)kPatBoxMaxGroups) return false;
+	std::vector<int> used(nc, 0);
+	int G = 0;
+	for (size_t c = 0; c < nc; c++)
+	{	// group centres: the chains with an even first offset
+		if ((chains[c].m & 3) != 3) return false;
+		if (chains[c].off & 1) continue;
+		int left = -1, right = -1;
+		for (size_t d = 0; d < nc; d++)
+		{
+			if (chains[d].off == chains[c].off - 1) left = (int)d;
+			if (chains[d].off == chains[c].off + 1) right = (int)d;
+		}
+		if (left < 0 || right < 0 || used[(size_t)left] || used[(size_t)right] || used[c] || G >= kPatBoxMaxGroups) return false;
+		used[c] = used[(size_t)left] = used[(size_t)right] = 1;
+		plan.center[G] = chains[c].off;
+		const int idx[3] = {left, (int)c, right};
+		for (int dx = 0; dx < 3; dx++)
+		{
+			plan.chain_of[G][dx] = idx[dx];
+			for (int j = 0; j < 3; j++) plan.coef[G][dx][j] = chains[(size_t)idx[dx]].v[j];
+		}
+		G++;
+	}
+	for (size_t c = 0; c < nc; c++) if (!used[c]) return false;
+	plan.G = G;
+	// row flags: pattern p = the box minus the slices of one flag combination?
+	unsigned long long full = 0ull;
+	for (size_t c = 0; c < nc; c++) full |= 7ull << (3 * c);
+	auto combo_mask = [&](int f) {
+		unsigned long long m = full;
+		for (int g = 0; g < G; g++)
+			for (int dx = 0; dx < 3; dx++)
+			{
+				const int c = plan.chain_of[g][dx];
+				unsigned long long drop = 0ull;
+				if ((f & (kBoxHDropG0 << g)) || (dx == 0 && (f & kBoxHDropL)) || (dx == 2 && (f & kBoxHDropR))) drop = 7ull;
+				if (f & kBoxHDropLow) drop |= 1ull;
+				if (f & kBoxHDropHigh) drop |= 4ull;
+				m &= ~(drop << (3 * c));
+			}
+		return m;
+	};
+	rowflags.assign(sup.size(), 0x80);
+	const int n_combo = 16 << G;
+	for (size_t p = 0; p < sup.size(); p++)
+	{
+		if (sup[p] != gpat || mask[p] == 0ull) continue;
+		for (int f = 0; f < n_combo && f < 0x80; f++)
+			if (combo_mask(f) == mask[p]) { rowflags[p] = (unsigned char)f; break; }
+	}
+	plan.ok = 1;
+	return true;
+}
+
 }  // namespace lcgb200
