@@ -250,7 +250,7 @@ __global__ void k_pat_count(int n_rows, const unsigned char* __restrict__ pat, u
 // thread items of k_spmv_pat_box: thread (it, lane) owns the rows (a R + q) S + 64 ib + 2 lane + e, q < R, e < 2.  flags[32 it +
 // lane] = what its rows lack of the box (csr.cuh: kBoxDrop*), 255 when they are no consistent sub-boxes: a row beyond the matrix
 // or without row flags, "no left column" on the right row of the pair (or vice versa), "no lower line" anywhere but on the first
-// line, "no upper line" anywhere but on the last, planes that differ between rows.  *n_odd counts the 255s among threads with rows.
+// line, "no upper line" anywhere but on the last, planes that differ between rows.  *n_odd counts the warps that hold such a thread.
 __global__ void k_pat_box_flags(long long n_rows, int S, int nib, int n_items, const unsigned char* __restrict__ pat,
 	const unsigned char* __restrict__ rowflags, unsigned char* __restrict__ flags, unsigned int* n_odd)
 {
@@ -261,10 +261,10 @@ __global__ void k_pat_box_flags(long long n_rows, int S, int nib, int n_items, c
 	if (it >= n_items) return;
 	const int a = it / nib, ib = it - a * nib;
 	const int i = ib * 64 + 2 * lane;
-	if (i >= S) { flags[(size_t)it * 32 + lane] = 255; return; }
 	int out = 0; bool bad = false, any_row = false;
 	int planes = -1;
-	for (int q = 0; q < kPatRows; q++)
+	if (i >= S) bad = true;
+	else for (int q = 0; q < kPatRows; q++)
 		for (int e = 0; e < 2; e++)
 		{
 			const long long row = ((long long)a * kPatRows + q) * S + i + e;
@@ -293,7 +293,9 @@ __global__ void k_pat_box_flags(long long n_rows, int S, int nib, int n_items, c
 				if ((out & kBoxDropHigh) && q == kPatRows - 1 && !(f & kBoxDropHigh)) bad = true;
 			}
 	flags[(size_t)it * 32 + lane] = (unsigned char)(bad ? 255 : out);
-	if (bad && any_row) atomicAdd(n_odd, 1u);
+	// a thread that falls back costs its whole WARP the time of the chain walk: count warps
+	const bool warp_odd = __any_sync(0xffffffffu, bad && any_row);
+	if (lane == 0 && warp_odd) atomicAdd(n_odd, 1u);
 }
 
 // block items of k_spmv_pat_march, one block of 8 warps per item: bitem[16 bi + w] = the pattern all rows of warp w's item
@@ -483,8 +485,8 @@ void try_patterns(CsrHandle* h, const std::vector<int>& rp_h, const std::vector<
 							unsigned int n_odd = 0;
 							LCG_CUDA_CHECK(cudaMemcpy(&n_odd, d_odd, sizeof(unsigned int), cudaMemcpyDeviceToHost));
 							cudaFree(d_rf);
-							// worth it only when few threads fall back to the chain tables (they cost a whole warp its time)
-							if ((double)n_odd * 2 * kPatRows <= 0.10 * (double)n)
+							// worth it only when few warps hold a thread that falls back to the chain tables
+							if ((double)n_odd <= 0.10 * (double)n_items64)
 							{
 								box = new PatBox();
 								box->G = bplan.G;

@@ -573,7 +573,7 @@ __global__ void __launch_bounds__(kSpmvThreads, kSpmvCtasPerSm) k_spmv_dict(CsrD
 //    that are SUBSETS of one longer pattern (a column of grid points that starts on a face: the face row is the interior row
 //    minus the entries that leave the grid; pat_host.h: pat_build_masks) take the longer pattern's chains with a 64-bit
 //    presence mask per row, reads still shared; anything else goes row by row through the same chain table.
-// 3. k_spmv_pat (any matrix with <= 253 distinct rows; the default): the reads are plain loads through L1.  The 8 warps of
+// 3. k_spmv_pat (any matrix with <= 253 distinct rows): the reads are plain loads through L1.  The 8 warps of
 //    a block take the items of a round in rotation, so the slower items (ends of grid lines) do not pile up on two warps.
 //    Measured at 27-point 256^3 (profiles/README_r02.md): 0.122 ms (round 1: 0.222), LSU data pipe 56 %, issue slots 56 %
 //    busy, 1015 instructions per 256 rows — bound by instruction issue and load latency, not by bytes (DRAM: 0.24 GB).
@@ -586,8 +586,10 @@ __global__ void __launch_bounds__(kSpmvThreads, kSpmvCtasPerSm) k_spmv_dict(CsrD
 //    and the consumers read x out of shared memory with immediate offsets.  Measured 0.175 ms: the generic chain walk costs
 //    as many instructions as in k_spmv_pat and a block advances at the pace of its slowest warp, so on one B200 — where x
 //    stays in L2 anyway — the plain-load kernel wins; kept for systems whose x does not fit L2.
-// Entries are accumulated chain by chain with fma (a different order from the CSR row order: y agrees with the plain copy
-// to rounding, not bitwise).
+// 5. k_spmv_pat_box (default where it applies: the geometry pattern is a dense box — a 27-point stencil — and the grid lines and
+//    planes align with the threads' columns, i.e. ny % 8 == 0): see the comment at the kernel.  0.083 ms at 27-point 256^3.
+// Entries are accumulated chain by chain (box: plane by plane, line by line) with fma — a different order from the CSR row
+// order: y agrees with the plain copy to rounding, not bitwise.
 constexpr int kPatRows = 8;            // R: rows (S apart) a thread computes together
 constexpr int kPatChainLen = 3;        // entries per chain (v[3])
 constexpr int kPatMaxChains = 1536;    // chain table entries held in shared memory (48 KB)
@@ -1096,7 +1098,12 @@ __global__ void __launch_bounds__(kSpmvThreads, 2) k_spmv_pat_march(CsrDev<doubl
 // straight out of the constant bank, no register, no table read.  Everything is unrolled: no index arithmetic per chain.
 // Boundary rows are the box minus whole slices, so a byte of flags per thread says what to leave out: the value left /
 // right of the pair (dx), the first / last window line (dy: it serves only the thread's first / last row), a whole plane
-// (dz).  255 = rows that are no such sub-box (or lie beyond the matrix): both columns go through pat_item_ldg.
+// (dz).  255 = rows that are no such sub-box (or lie beyond the matrix): both columns go through pat_item_ldg; try_patterns
+// takes this kernel only when at most a tenth of the warps hold such a thread.
+// Measured at 27-point 256^3 (profiles/README_r02.md): 0.083 ms = 0.52 of the measured HBM peak on the 17 bytes per row,
+// 916 instructions per 512 rows (448 of them fma), LSU data pipe 75 % (the two side values are 8-byte loads with a 16-byte lane
+// stride: 4 wavefronts each, like the pair), 124 registers, 2 blocks per SM.  Handing the side values over by warp shuffles
+// instead serialises the loads behind the shuffles: 0.208 ms (tried, dropped).
 struct PatBox {
 	int G = 0;
 	int center[3] = {0, 0, 0};

@@ -5,7 +5,8 @@
 //   2. walks the work items of both kernels with their index arithmetic — k_spmv_pat: item flag, chained path with
 //      R + m - 1 loads per chain, masked path (rows whose patterns are subsets of one longer pattern), row-by-row path;
 //      k_spmv_pat_march (when the plan exists): segments, block items, the producer's clipped window lines (what it does
-//      not copy stays stale = NaN here), the consumers' reads through (plane, line shift, position) — and
+//      not copy stays stale = NaN here), the consumers' reads through (plane, line shift, position); k_spmv_pat_box (dense box
+//      stencils): the flag byte of every thread and the pairs / side values it reads under those flags — and
 //   3. checks that every row is written exactly once, that no read leaves [0, n_cols) or returns a stale value, that the
 //      bulk copies are 16-byte aligned, and that y equals the CSR product to rounding.
 // No GPU, no CUDA: g++ -O2 -std=c++17 -I liblcg_b200/csrc tests/cxx/pat_chain_check.cpp.  Prints one line per case.
@@ -75,6 +76,7 @@ struct Setup {
 	std::vector<unsigned long long> mask;
 	std::vector<std::vector<PatChainH>> chains;
 	PatMarchH plan;
+	PatBoxH box; std::vector<unsigned char> rowflags;
 };
 
 // capi.cu: try_patterns, host part
@@ -123,6 +125,7 @@ static bool setup(const std::string& name, const Csr& A, Setup& T)
 		}
 	}
 	pat_build_masks(T.rows, T.chains, T.S, T.sup, T.mask);
+	if (!T.plan.ok && T.S % 2 == 0) pat_plan_box(T.chains[T.longest], T.S, (int)T.longest, T.sup, T.mask, T.box, T.rowflags);
 	return true;
 }
 
@@ -355,6 +358,97 @@ static void walk_march(const Csr& A, const Setup& T, const std::vector<double>& 
 	}
 }
 
+// csr.cuh: k_spmv_pat_box (+ capi.cu: k_pat_box_flags).  *odd = warps that hold a thread (with rows) that falls back to the chain tables
+static void walk_box(const Csr& A, const Setup& T, const std::vector<double>& x, Result& res, long long* odd)
+{
+	const int n = A.n_rows, S = T.S;
+	const PatBoxH& B = T.box;
+	const long long n_super = ((long long)n + S - 1) / S, n_a = (n_super + R - 1) / R;
+	const int nib = (S + 63) / 64;
+	auto ld = [&](long long idx) -> double { res.reads++; if (idx < 0 || idx >= A.n_cols) { res.bad++; return 0.0; } return x[(size_t)idx]; };
+	auto store = [&](long long row, double v, double xc) { res.y[(size_t)row] = v; res.written[(size_t)row]++; res.xc[(size_t)row] = xc; };
+	for (long long a = 0; a < n_a; a++)
+		for (int ib = 0; ib < nib; ib++)
+		{
+			bool warp_odd = false;
+			for (int lane = 0; lane < 32; lane++)
+			{
+				const int i = ib * 64 + 2 * lane;
+				if (i >= S) continue;
+				const long long row0 = a * R * S + i;
+				// k_pat_box_flags
+				int out = 0, planes = -1; bool bad = false, any_row = false;
+				for (int q = 0; q < R; q++)
+					for (int e = 0; e < 2; e++)
+					{
+						const long long row = row0 + (long long)q * S + e;
+						if (row >= n) { bad = true; continue; }
+						any_row = true;
+						const int f = T.rowflags[(size_t)T.pat[(size_t)row]];
+						if (f & 0x80) { bad = true; continue; }
+						if ((f & kBoxHDropL) && e != 0) bad = true;
+						if ((f & kBoxHDropR) && e != 1) bad = true;
+						if ((f & kBoxHDropLow) && q != 0) bad = true;
+						if ((f & kBoxHDropHigh) && q != R - 1) bad = true;
+						if (planes < 0) planes = f & ~15;
+						if ((f & ~15) != planes) bad = true;
+						out |= f;
+					}
+				if (!bad)
+					for (int q = 0; q < R && !bad; q++)
+						for (int e = 0; e < 2; e++)
+						{
+							const int f = T.rowflags[(size_t)T.pat[(size_t)(row0 + (long long)q * S + e)]];
+							if ((out & kBoxHDropL) && e == 0 && !(f & kBoxHDropL)) bad = true;
+							if ((out & kBoxHDropR) && e == 1 && !(f & kBoxHDropR)) bad = true;
+							if ((out & kBoxHDropLow) && q == 0 && !(f & kBoxHDropLow)) bad = true;
+							if ((out & kBoxHDropHigh) && q == R - 1 && !(f & kBoxHDropHigh)) bad = true;
+						}
+				const int flags = bad ? 255 : out;
+				if (bad && any_row) warp_odd = true;
+				// k_spmv_pat_box
+				if (flags != 255)
+				{
+					double s0[R], s1[R];
+					for (int q = 0; q < R; q++) { s0[q] = 0.0; s1[q] = 0.0; }
+					for (int g = 0; g < B.G; g++)
+					{
+						if (flags & (kBoxHDropG0 << g)) continue;
+						const long long xg = row0 + B.center[g];
+						if (xg & 1) res.bad++;   // 16-byte alignment of the pair loads
+						for (int u = 0; u < R + 2; u++)
+						{
+							double xm = 0.0, x0 = 0.0, x1 = 0.0, xp = 0.0;
+							const bool line_on = !((u == 0 && (flags & kBoxHDropLow)) || (u == R + 1 && (flags & kBoxHDropHigh)));
+							if (line_on)
+							{
+								const long long pl = xg + (long long)u * S;
+								x0 = ld(pl); x1 = ld(pl + 1);
+								if (!(flags & kBoxHDropL)) xm = ld(pl - 1);
+								if (!(flags & kBoxHDropR)) xp = ld(pl + 2);
+							}
+							for (int j = 0; j < 3; j++)
+							{
+								const int q = u - j;
+								if (q < 0 || q >= R) continue;
+								s0[q] = std::fma(B.coef[g][0][j], xm, s0[q]); s0[q] = std::fma(B.coef[g][1][j], x0, s0[q]); s0[q] = std::fma(B.coef[g][2][j], x1, s0[q]);
+								s1[q] = std::fma(B.coef[g][0][j], x0, s1[q]); s1[q] = std::fma(B.coef[g][1][j], x1, s1[q]); s1[q] = std::fma(B.coef[g][2][j], xp, s1[q]);
+							}
+						}
+					}
+					for (int q = 0; q < R; q++)
+					{
+						const long long row = row0 + (long long)q * S;
+						store(row, s0[q], ld(row)); store(row + 1, s1[q], ld(row + 1));
+					}
+				}
+				else
+					for (int e = 0; e < 2; e++) item_ldg(A, T, x, row0 + e, 255, res);
+			}
+			if (warp_odd) (*odd)++;
+		}
+}
+
 static int verify(const std::string& name, const char* which, const Csr& A, const std::vector<double>& x, const Result& res)
 {
 	const int n = A.n_rows;
@@ -403,6 +497,16 @@ static int check(const std::string& name, const Csr& A, int expect_stride, size_
 			fail |= verify(name, target == 7 ? "march7" : "march", A, x, r2);
 			if (target == 7 && fb) std::printf("    %lld block items through the plain-load path\n", fb);
 		}
+	if (T.box.ok)
+	{
+		Result r3; r3.y.assign((size_t)n, 0.0); r3.xc.assign((size_t)n, 0.0); r3.written.assign((size_t)n, 0);
+		long long odd = 0;
+		walk_box(A, T, x, r3, &odd);
+		fail |= verify(name, "box", A, x, r3);
+		const double n_warps = (double)(((n + T.S - 1) / T.S + R - 1) / R) * ((T.S + 63) / 64);
+		std::printf("    box: %d planes, %.1f %% of the warps hold a thread that falls back to the chain tables%s\n", T.box.G, 100.0 * (double)odd / n_warps,
+			(double)odd <= 0.10 * n_warps ? "" : " (kernel not used)");
+	}
 	if (expect_stride && T.S != expect_stride) { std::printf("  expected stride %d\n", expect_stride); fail = 1; }
 	if (expect_chains && T.chains[T.longest].size() != expect_chains) { std::printf("  expected %zu chains\n", expect_chains); fail = 1; }
 	if (expect_march >= 0 && T.plan.ok != expect_march) { std::printf("  march plan: expected %d\n", expect_march); fail = 1; }
@@ -423,6 +527,7 @@ int main()
 	fail |= check("27pt 128x12x6 (ny % 8 != 0)", stencil(128, 12, 6, true, 0, 6), 128, 9, 0);
 	fail |= check("27pt 64^3", stencil(64, 64, 64, true, 0, 64), 64, 9, 0);
 	fail |= check("27pt 44^3", stencil(44, 44, 44, true, 0, 44), 44, 9);
+	fail |= check("27pt 64x16x40 slab z=[6,34)", stencil(64, 16, 40, true, 6, 34), 64, 9, 0);   // box kernel with two ghost-coupled planes
 	fail |= check("27pt 50x37x29", stencil(50, 37, 29, true, 0, 29), 50, 9);
 	fail |= check("7pt 50^3", stencil(50, 50, 50, false, 0, 50), 50, 5);
 	fail |= check("7pt 96x40x33", stencil(96, 40, 33, false, 0, 33), 96, 5);

@@ -937,7 +937,9 @@ def test_compressed_operator_formats(torch_cuda, port, kind, g):
     many distinct rows for patterns).  Same entries as the plain CSR copy.  The dictionary kernel adds a row's products in
     the plain kernel's order (bitwise equal y); the pattern kernels add them chain by chain (offsets one grid line apart
     share their loads between the 8 rows of a thread), so y agrees to rounding; the solvers land on the same iterates.
-    With LCGB200_PAT_MARCH=1 grids of 128 points per line take the plane-marching kernel (test_pattern_march_kernel)."""
+    The 27-point grids whose lines align with the threads' columns (96: ny % 8 == 0; 44: nine tenths of the warps) take the box
+    kernel (k_spmv_pat_box), the 7-point ones the chain kernel (k_spmv_pat); with LCGB200_PAT_MARCH=1 grids of 128 points per
+    line take the plane-marching kernel (test_pattern_march_kernel)."""
     torch = torch_cuda
     if kind == "7pt_varcoef":
         S = stencil.make_system("7pt", g)
@@ -995,8 +997,8 @@ def test_compressed_operator_formats(torch_cuda, port, kind, g):
 def test_pattern_march_kernel(torch_cuda, port, kind, g, monkeypatch):
     """LCGB200_PAT_MARCH=1 (read when the operator is created): k_spmv_pat_march — a producer warp feeds plane windows of x
     into a shared-memory ring with TMA bulk copies, 8 consumer warps march along z and read one new window per item.  Same
-    y (to rounding) and the same fused dot products as the plain CSR copy and as the plain-load pattern kernel, same
-    iterates after a pinned number of PCG / CG iterations."""
+    y (to rounding) and the same fused dot products as the plain CSR copy and as the default pattern kernel (27-point: the
+    box kernel, 7-point: the chain kernel), same iterates after a pinned number of PCG / CG iterations."""
     torch = torch_cuda
     S = stencil.make_system(kind, g)
     n = S["n"]

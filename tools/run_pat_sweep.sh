@@ -14,7 +14,7 @@ for l in open("gpurun_out/${T}_$name.log"):
 PY
 }
 (timeout -s KILL 300 python -m pytest tests -m gpu -x -q -k "compressed or march or spmv") 2>&1 | tail -4
-run box LCGB200_X=1
-run chains LCGB200_PAT_NO_BOX=1
+run box2 LCGB200_PAT_BOX_BLOCKS=2
+run box3 LCGB200_PAT_BOX_BLOCKS=3
 (timeout -s KILL 300 ncu --set full --clock-control none --import-source on --kernel-name regex:'^k_spmv_pat' --launch-skip 20 --launch-count 1 -f -o gpurun_out/ncu_spmv_pat_${T} python bench.py --steps 1 --warmup 1 --iters 40 $F) > gpurun_out/${T}_ncu_pat.log 2>&1
 ls -la gpurun_out/*${T}.ncu-rep
