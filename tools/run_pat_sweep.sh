@@ -1,5 +1,7 @@
-# row-pattern kernels on bench.py --compress (27-point 256^3 Jacobi-PCG): the box kernel (default for dense box stencils) against
-# the chain kernel (LCGB200_PAT_NO_BOX=1) and the opt-in plane-marching kernel; prints it/s and the SpMV's average launch time
+# row-pattern kernels on bench.py --compress (27-point 256^3 Jacobi-PCG): the box kernel (default for dense box stencils on
+# aligned grids) against the general chain kernel (LCGB200_PAT_NO_BOX=1) and the opt-in plane-marching kernel
+# (LCGB200_PAT_MARCH=1; LCGB200_PAT_AHEAD = windows loaded ahead, LCGB200_PAT_SEGS = march segments per resident block);
+# prints it/s and the SpMV's average launch time.  usage: gpurun -- 'bash tools/run_pat_sweep.sh TAG'
 mkdir -p gpurun_out
 T=${1:-sweep}
 F="--steps 3 --warmup 3 --no-cpu --no-ref-cuda --no-compressed-leg --no-extra-legs --compress"
@@ -14,7 +16,6 @@ for l in open("gpurun_out/${T}_$name.log"):
 PY
 }
 (timeout -s KILL 300 python -m pytest tests -m gpu -x -q -k "compressed or march or spmv") 2>&1 | tail -4
-run box2 LCGB200_PAT_BOX_BLOCKS=2
-run box3 LCGB200_PAT_BOX_BLOCKS=3
-(timeout -s KILL 300 ncu --set full --clock-control none --import-source on --kernel-name regex:'^k_spmv_pat' --launch-skip 20 --launch-count 1 -f -o gpurun_out/ncu_spmv_pat_${T} python bench.py --steps 1 --warmup 1 --iters 40 $F) > gpurun_out/${T}_ncu_pat.log 2>&1
-ls -la gpurun_out/*${T}.ncu-rep
+run box LCGB200_X=1
+run chains LCGB200_PAT_NO_BOX=1
+run march LCGB200_PAT_MARCH=1
