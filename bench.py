@@ -575,6 +575,7 @@ def run_ours(args, wl):
                 sp_ms = pc.info.spmv_ms / max(pc.info.spmv_timed, 1)
                 compressed = {"value": args.steps * iters / (ms_c * 1e-3), "unit": "iterations/s", "level": cfmt["level"],
                               "format": "row patterns: 1 byte per row" if cfmt["level"] == 2 else "dictionary codes: 2 bytes per entry",
+                              "pattern_kernel": opc.pattern_kernel(),
                               "n_values": cfmt["n_values"], "n_offsets": cfmt["n_offsets"], "spmv_stream_bytes_per_launch": cfmt["stream_bytes"],
                               "spmv_avg_launch_ms": sp_ms, "spmv_stream_GBps": cfmt["stream_bytes"] / (sp_ms * 1e-3) / 1e9,
                               "spmv_frac_of_peak_on_format_bytes": cfmt["stream_bytes"] / (sp_ms * 1e-3) / 1e9 / hbm_peak()[0],

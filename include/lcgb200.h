@@ -97,9 +97,9 @@ enum {
 	LCGB200_CSR_COMPRESS = 4,    /* real operators: if the matrix has <= 256 distinct values and <= 256 distinct (col - row) offsets
 	                                 (constant-coefficient stencils and their row blocks), keep a second copy as one 16-bit code per
 	                                 entry + two dictionaries and stream THAT in the SpMV (2 bytes per non-zero instead of 12); if in
-	                                 addition the rows fall into <= 256 distinct patterns, keep one pattern id per ROW and stream only
-	                                 that.  Same entries, row sums accumulated left to right.  Silently stays uncompressed when the
-	                                 matrix does not fit (lcgb200_csr_format). */
+	                                 addition the rows fall into <= 253 distinct patterns, keep one pattern id per ROW and stream only
+	                                 that.  Same entries; the row sums are accumulated in another order than on the plain copy (y
+	                                 agrees to rounding).  Silently stays uncompressed when the matrix does not fit (lcgb200_csr_format). */
 	LCGB200_CSR_IC0 = 8,         /* zero-fill incomplete Cholesky of the (symmetric, square, unpartitioned) matrix at creation: the
 	                                 reference's sequential algorithm on the host (lcg_incomplete_Cholesky_half_coo, preconditioner.cpp:33-160;
 	                                 clcg_incomplete_Cholesky_cuda_half, preconditioner_cuda.cu:40-270; complex: L L^T, unconjugated),
@@ -140,9 +140,13 @@ int lcgb200_csr_spmv(lcgb200_csr_t A, const void* x_dev, void* y_dev, int op, vo
 int lcgb200_csr_spmv_dot(lcgb200_csr_t A, const void* x_dev, void* y_dev, const void* w_dev, double* dots_dev, void* stream);
 /* storage format the SpMV streams (LCGB200_CSR_COMPRESS): *compressed = 0 plain CSR (S+4 bytes per entry), 1 dictionary
  * codes (2 bytes per entry), 2 row patterns (1 byte per ROW: rows with identical (col - row, value) sequences share a
- * pattern; at most 256 patterns of at most 64 entries); the dictionary sizes; and the bytes one SpMV launch moves in that
+ * pattern; at most 253 patterns of at most 64 entries); the dictionary sizes; and the bytes one SpMV launch moves in that
  * format (matrix + row_ptr + x + y) */
 int lcgb200_csr_format(lcgb200_csr_t A, int* compressed, int* n_values, int* n_offsets, long long* stream_bytes);
+/* which kernel walks the row patterns (level 2): *kernel = 0 none, 1 the general chain kernel, 2 the box kernel (dense box
+ * stencils on grids whose lines align with the threads' columns), 3 the plane-marching kernel (LCGB200_PAT_MARCH=1 in the
+ * environment at creation); *stride = rows between the rows a thread owns (the line stride nx of a grid), *n_patterns = distinct rows */
+int lcgb200_csr_pattern_kernel(lcgb200_csr_t A, int* kernel, int* stride, int* n_patterns);
 /* bytes the SpMV kernel must move per launch by SURVEY.md §8(d): nnz*(S+4) + (n+1)*4 + 2*n*S */
 long long lcgb200_csr_spmv_bytes(lcgb200_csr_t A);
 int lcgb200_csr_info(lcgb200_csr_t A, int* n_rows, int* n_cols, int* nnz, int* n_tiles, int* lanes_per_row);

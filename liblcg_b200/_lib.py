@@ -60,6 +60,7 @@ SYMBOLS = {
     "lcgb200_csr_spmv_dot": (_I, [_VP, _VP, _VP, _VP, _VP, _VP]),
     "lcgb200_csr_spmv_bytes": (_LL, [_VP]),
     "lcgb200_csr_format": (_I, [_VP, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_LL)]),
+    "lcgb200_csr_pattern_kernel": (_I, [_VP] + [C.POINTER(_I)] * 3),
     "lcgb200_csr_info": (_I, [_VP] + [C.POINTER(_I)] * 5),
     "lcgb200_coo2csr": (_I, [_VP, _I, _I, _VP, _VP]),
     "lcgb200_read_case": (_I, [C.c_char_p, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP)]),

@@ -167,6 +167,13 @@ class CsrOperator:
         _lib.load().lcgb200_csr_format(self.handle, C.byref(c), C.byref(nv), C.byref(no), C.byref(sb))
         return dict(compressed=bool(c.value), level=c.value, n_values=nv.value, n_offsets=no.value, stream_bytes=int(sb.value))
 
+    def pattern_kernel(self):
+        """dict(kernel, stride, n_patterns): which kernel walks the row patterns of a level-2 copy (lcgb200_csr_pattern_kernel):
+        "none", "chains" (k_spmv_pat), "box" (k_spmv_pat_box) or "march" (k_spmv_pat_march)."""
+        k, s, p = C.c_int(), C.c_int(), C.c_int()
+        _lib.load().lcgb200_csr_pattern_kernel(self.handle, C.byref(k), C.byref(s), C.byref(p))
+        return dict(kernel=("none", "chains", "box", "march")[k.value], stride=s.value, n_patterns=p.value)
+
     def spmv_bytes(self) -> int:
         return int(_lib.load().lcgb200_csr_spmv_bytes(self.handle))
 

@@ -1134,6 +1134,16 @@ int lcgb200_csr_info(lcgb200_csr_t A, int* n_rows, int* n_cols, int* nnz, int* n
 	return 0;
 }
 
+int lcgb200_csr_pattern_kernel(lcgb200_csr_t A, int* kernel, int* stride, int* n_patterns)
+{
+	CsrHandle* h = reinterpret_cast<CsrHandle*>(A);
+	if (!h) return LCGB200_INVALID_POINTER;
+	if (kernel) *kernel = !h->pat ? 0 : (h->pat_box ? 2 : (h->pat_march ? 3 : 1));
+	if (stride) *stride = h->pat ? h->pat_stride : 0;
+	if (n_patterns) *n_patterns = h->pat ? h->n_pat : 0;
+	return 0;
+}
+
 int lcgb200_csr_format(lcgb200_csr_t A, int* compressed, int* n_values, int* n_offsets, long long* stream_bytes)
 {
 	CsrHandle* h = reinterpret_cast<CsrHandle*>(A);

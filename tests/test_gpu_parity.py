@@ -961,6 +961,9 @@ def test_compressed_operator_formats(torch_cuda, port, kind, g):
     f = comp.format()
     assert f["level"] == level and plain.format()["level"] == 0
     assert f["n_offsets"] == (27 if kind == "27pt" else 7)
+    pk = comp.pattern_kernel()
+    assert pk["kernel"] == ("none" if level == 1 else ("box" if kind == "27pt" else "chains")) and plain.pattern_kernel()["kernel"] == "none"
+    assert level == 1 or (pk["stride"] == g and pk["n_patterns"] == 27)
     assert f["stream_bytes"] == (n + 16 * n if level == 2 else 2 * S["nnz"] + 4 * (n + 1) + 16 * n)
     x = to_dev(torch, np.random.default_rng(3).standard_normal(n))
     w = to_dev(torch, np.random.default_rng(4).standard_normal(n))
@@ -1008,6 +1011,7 @@ def test_pattern_march_kernel(torch_cuda, port, kind, g, monkeypatch):
     march = api.CsrOperator(S["row_ptr"], S["col"], S["val"], jacobi=True, compress=True)
     monkeypatch.delenv("LCGB200_PAT_MARCH")
     assert march.format()["level"] == 2 and ldg.format()["level"] == 2
+    assert march.pattern_kernel()["kernel"] == "march" and ldg.pattern_kernel()["kernel"] == ("box" if kind == "27pt" else "chains")
     x = to_dev(torch, np.random.default_rng(3).standard_normal(n))
     w = to_dev(torch, np.random.default_rng(4).standard_normal(n))
     ys = [torch.empty_like(x) for _ in range(3)]
