@@ -1103,7 +1103,8 @@ __global__ void __launch_bounds__(kSpmvThreads, 2) k_spmv_pat_march(CsrDev<doubl
 // Measured at 27-point 256^3 (profiles/README_r02.md): 0.083 ms = 0.52 of the measured HBM peak on the 17 bytes per row,
 // 916 instructions per 512 rows (448 of them fma), LSU data pipe 75 % (the two side values are 8-byte loads with a 16-byte lane
 // stride: 4 wavefronts each, like the pair), 124 registers, 2 blocks per SM.  Handing the side values over by warp shuffles
-// instead serialises the loads behind the shuffles: 0.208 ms (tried, dropped).
+// instead costs more than it saves: 0.208 ms with a shuffle behind every load, 0.176 ms with all pair loads of a plane issued first
+// (tried twice, dropped).
 struct PatBox {
 	int G = 0;
 	int center[3] = {0, 0, 0};
