@@ -160,6 +160,13 @@ int lcgb200_coo2csr(const int* rows_dev, int nnz, int n, int* row_ptr_dev, void*
  * and the right-hand side into malloc'ed HOST arrays (free with lcgb200_free_host); value_type LCGB200_REAL or LCGB200_COMPLEX */
 int lcgb200_read_case(const char* path_A, int value_type, int* n_out, int* nz_out, int** rows_out, int** cols_out, void** vals_out, void** rhs_out);
 void lcgb200_free_host(void* p);
+/* the element-wise device helpers the reference's samples build their Jacobi Mx callbacks from (algebra_cuda.h:45-84,
+ * lcg_complex_cuda.h:188-274; usage sample10.cu:117,193): c = a * b (op 0), c = a / b (op 1), c = conj(a) (op 2, b unused)
+ * on device arrays of value_type LCGB200_REAL / LCGB200_COMPLEX / LCGB200_COMPLEX_FLOAT; A_diag[i] = A[i, i] of a device CSR
+ * matrix (rows without a diagonal entry keep what diag_dev held); a = min(max(a, low), hig).  Asynchronous on `stream`. */
+int lcgb200_vec_elementwise(int op, int value_type, const void* a_dev, const void* b_dev, void* c_dev, int n, void* stream);
+int lcgb200_diagonal_of_csr(int value_type, const int* row_ptr_dev, const int* col_dev, const void* val_dev, int n, void* diag_dev, void* stream);
+int lcgb200_set2box(const double* low_dev, const double* hig_dev, double* a_dev, int n, void* stream);
 /* host COO triplets (row-sorted) -> operator handle; the COO -> CSR compression runs on the device */
 int lcgb200_csr_create_from_coo(lcgb200_csr_t* out, int n, int nnz, const int* rows, const int* cols, const void* vals, int value_type, unsigned flags);
 

@@ -63,6 +63,9 @@ SYMBOLS = {
     "lcgb200_csr_pattern_kernel": (_I, [_VP] + [C.POINTER(_I)] * 3),
     "lcgb200_csr_info": (_I, [_VP] + [C.POINTER(_I)] * 5),
     "lcgb200_coo2csr": (_I, [_VP, _I, _I, _VP, _VP]),
+    "lcgb200_vec_elementwise": (_I, [_I, _I, _VP, _VP, _VP, _I, _VP]),
+    "lcgb200_diagonal_of_csr": (_I, [_I, _VP, _VP, _VP, _I, _VP, _VP]),
+    "lcgb200_set2box": (_I, [_VP, _VP, _VP, _I, _VP]),
     "lcgb200_read_case": (_I, [C.c_char_p, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP)]),
     "lcgb200_free_host": (None, [_VP]),
     "lcgb200_csr_create_from_coo": (_I, [C.POINTER(_VP), _I, _I, _VP, _VP, _VP, _I, C.c_uint]),

@@ -3,6 +3,7 @@
 // over and call cusparseXcoo2csr on the row-sorted indices (sample8.cu:169); lcgb200_coo2csr is that call.
 #include "common.cuh"
 #include "../../include/lcgb200.h"
+#include <cuComplex.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -31,11 +32,93 @@ __global__ void k_check_sorted(const int* __restrict__ rows, int nnz, int n, int
 	if (r < 0 || r >= n || (k > 0 && rows[k - 1] > r)) *flag = 1;
 }
 
+// ---- the element-wise device helpers of algebra_cuda.h / lcg_complex_cuda.h (what the reference's samples build their
+// Jacobi Mx callbacks from: sample10.cu:117,193).  One grid-stride kernel per operation; the complex products and
+// quotients are cuCmul / cuCdiv(f), the functions the reference's kernels call (lcg_complex_cuda.cu:62-101).
+struct HelpMul { __device__ double operator()(double a, double b) const { return a * b; }
+	__device__ cuDoubleComplex operator()(cuDoubleComplex a, cuDoubleComplex b) const { return cuCmul(a, b); }
+	__device__ cuComplex operator()(cuComplex a, cuComplex b) const { return cuCmulf(a, b); } };
+struct HelpDiv { __device__ double operator()(double a, double b) const { return a / b; }
+	__device__ cuDoubleComplex operator()(cuDoubleComplex a, cuDoubleComplex b) const { return cuCdiv(a, b); }
+	__device__ cuComplex operator()(cuComplex a, cuComplex b) const { return cuCdivf(a, b); } };
+struct HelpConj { __device__ double operator()(double a, double) const { return a; }
+	__device__ cuDoubleComplex operator()(cuDoubleComplex a, cuDoubleComplex) const { a.y *= -1.0; return a; }
+	__device__ cuComplex operator()(cuComplex a, cuComplex) const { a.y *= -1.0; return a; } };
+
+template <class T, class Op, bool BINARY>
+__global__ void k_help_elementwise(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ c, int n)
+{
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) c[i] = Op()(a[i], BINARY ? b[i] : a[i]);
+}
+
+// A_diag[i] = A[i, i]; rows without a diagonal entry keep what A_diag held (algebra_cuda.cu:40-57, lcg_complex_cuda.cu:27-61)
+template <class T>
+__global__ void k_help_diagonal(const int* __restrict__ rp, const int* __restrict__ ci, const T* __restrict__ v, int n, T* __restrict__ d)
+{
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+		for (int k = rp[i]; k < rp[i + 1]; k++) if (ci[k] == i) { d[i] = v[k]; break; }
+}
+
+// lcg_set2box_cuda (algebra_cuda.cu:26-38): closed or open bounds make no difference to the result
+__global__ void k_help_set2box(const double* __restrict__ low, const double* __restrict__ hig, double* __restrict__ a, int n)
+{
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+	{
+		double v = a[i];
+		if (v > hig[i]) v = hig[i];
+		if (v < low[i]) v = low[i];
+		a[i] = v;
+	}
+}
+
+template <class T>
+int help_elementwise(int op, const void* a, const void* b, void* c, int n, cudaStream_t s)
+{
+	const int grid = std::max(1, std::min((n + 255) / 256, 148 * 8));
+	if (op == 0) k_help_elementwise<T, HelpMul, true><<<grid, 256, 0, s>>>((const T*)a, (const T*)b, (T*)c, n);
+	else if (op == 1) k_help_elementwise<T, HelpDiv, true><<<grid, 256, 0, s>>>((const T*)a, (const T*)b, (T*)c, n);
+	else if (op == 2) k_help_elementwise<T, HelpConj, false><<<grid, 256, 0, s>>>((const T*)a, (const T*)a, (T*)c, n);
+	else return LCGB200_INVILAD_VARIABLE_SIZE;
+	return cudaGetLastError() == cudaSuccess ? 0 : LCGB200_UNKNOWN_ERROR;
+}
+
 }  // namespace lcgb200
 
 using namespace lcgb200;
 
 extern "C" {
+
+int lcgb200_vec_elementwise(int op, int value_type, const void* a_dev, const void* b_dev, void* c_dev, int n, void* stream)
+{
+	if (!a_dev || !c_dev || (op != 2 && !b_dev)) return LCGB200_INVALID_POINTER;
+	if (n <= 0) return LCGB200_INVILAD_VARIABLE_SIZE;
+	cudaStream_t s = (cudaStream_t)stream;
+	if (value_type == LCGB200_REAL) return help_elementwise<double>(op, a_dev, b_dev, c_dev, n, s);
+	if (value_type == LCGB200_COMPLEX) return help_elementwise<cuDoubleComplex>(op, a_dev, b_dev, c_dev, n, s);
+	if (value_type == LCGB200_COMPLEX_FLOAT) return help_elementwise<cuComplex>(op, a_dev, b_dev, c_dev, n, s);
+	return LCGB200_INVILAD_VARIABLE_SIZE;
+}
+
+int lcgb200_diagonal_of_csr(int value_type, const int* row_ptr_dev, const int* col_dev, const void* val_dev, int n, void* diag_dev, void* stream)
+{
+	if (!row_ptr_dev || !col_dev || !val_dev || !diag_dev) return LCGB200_INVALID_POINTER;
+	if (n <= 0) return LCGB200_INVILAD_VARIABLE_SIZE;
+	cudaStream_t s = (cudaStream_t)stream;
+	const int grid = std::max(1, std::min((n + 255) / 256, 148 * 8));
+	if (value_type == LCGB200_REAL) k_help_diagonal<double><<<grid, 256, 0, s>>>(row_ptr_dev, col_dev, (const double*)val_dev, n, (double*)diag_dev);
+	else if (value_type == LCGB200_COMPLEX) k_help_diagonal<cuDoubleComplex><<<grid, 256, 0, s>>>(row_ptr_dev, col_dev, (const cuDoubleComplex*)val_dev, n, (cuDoubleComplex*)diag_dev);
+	else if (value_type == LCGB200_COMPLEX_FLOAT) k_help_diagonal<cuComplex><<<grid, 256, 0, s>>>(row_ptr_dev, col_dev, (const cuComplex*)val_dev, n, (cuComplex*)diag_dev);
+	else return LCGB200_INVILAD_VARIABLE_SIZE;
+	return cudaGetLastError() == cudaSuccess ? 0 : LCGB200_UNKNOWN_ERROR;
+}
+
+int lcgb200_set2box(const double* low_dev, const double* hig_dev, double* a_dev, int n, void* stream)
+{
+	if (!low_dev || !hig_dev || !a_dev) return LCGB200_INVALID_POINTER;
+	if (n <= 0) return LCGB200_INVILAD_VARIABLE_SIZE;
+	k_help_set2box<<<std::max(1, std::min((n + 255) / 256, 148 * 8)), 256, 0, (cudaStream_t)stream>>>(low_dev, hig_dev, a_dev, n);
+	return cudaGetLastError() == cudaSuccess ? 0 : LCGB200_UNKNOWN_ERROR;
+}
 
 int lcgb200_coo2csr(const int* rows_dev, int nnz, int n, int* row_ptr_dev, void* stream)
 {

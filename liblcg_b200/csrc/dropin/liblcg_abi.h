@@ -75,6 +75,36 @@ void clcg_dot(lcg_complex& ret, const lcg_complex* a, const lcg_complex* b, int 
 void clcg_inner(lcg_complex& ret, const lcg_complex* a, const lcg_complex* b, int size);
 void clcg_matvec(lcg_complex** A, const lcg_complex* x, lcg_complex* Ax, int m_size, int n_size, lcg_matrix_e layout, clcg_complex_e conjugate);
 
+// ---- algebra_cuda.h:45-84 / lcg_complex_cuda.h:39-274: the device helpers the samples build their Jacobi callbacks from
+// (sample10.cu:117,193) and the small host helpers around cuComplex values
+void lcg_set2box_cuda(const lcg_float* low, const lcg_float* hig, lcg_float* a, int n, bool low_bound, bool hig_bound);
+void lcg_smDcsr_get_diagonal(const int* A_ptr, const int* A_col, const lcg_float* A_val, const int A_len, lcg_float* A_diag, int bk_size);
+void lcg_vecMvecD_element_wise(const lcg_float* a, const lcg_float* b, lcg_float* c, int n, int bk_size);
+void lcg_vecDvecD_element_wise(const lcg_float* a, const lcg_float* b, lcg_float* c, int n, int bk_size);
+lcg_complex cuda2lcg_complex(cuDoubleComplex a);
+cuDoubleComplex lcg2cuda_complex(lcg_complex a);
+cuDoubleComplex* clcg_malloc_cuda(size_t n);
+void clcg_free_cuda(cuDoubleComplex* x);
+void clcg_vecset_cuda(cuDoubleComplex* a, cuDoubleComplex b, size_t size);
+cuComplex clcg_Cscale(float s, cuComplex a);
+cuComplex clcg_Csum(cuComplex a, cuComplex b);
+cuComplex clcg_Cdiff(cuComplex a, cuComplex b);
+cuComplex clcg_Csqrt(cuComplex a);
+cuDoubleComplex clcg_Zscale(lcg_float s, cuDoubleComplex a);
+cuDoubleComplex clcg_Zsum(cuDoubleComplex a, cuDoubleComplex b);
+cuDoubleComplex clcg_Zdiff(cuDoubleComplex a, cuDoubleComplex b);
+cuDoubleComplex clcg_Zsqrt(cuDoubleComplex a);
+void clcg_smCcoo_row2col(const int* A_row, const int* A_col, const cuComplex* A, int N, int nz, int* Ac_row, int* Ac_col, cuComplex* Ac_val);
+void clcg_smZcoo_row2col(const int* A_row, const int* A_col, const cuDoubleComplex* A, int N, int nz, int* Ac_row, int* Ac_col, cuDoubleComplex* Ac_val);
+void clcg_smCcsr_get_diagonal(const int* A_ptr, const int* A_col, const cuComplex* A_val, const int A_len, cuComplex* A_diag, int bk_size);
+void clcg_smZcsr_get_diagonal(const int* A_ptr, const int* A_col, const cuDoubleComplex* A_val, const int A_len, cuDoubleComplex* A_diag, int bk_size);
+void clcg_vecMvecC_element_wise(const cuComplex* a, const cuComplex* b, cuComplex* c, int n, int bk_size);
+void clcg_vecMvecZ_element_wise(const cuDoubleComplex* a, const cuDoubleComplex* b, cuDoubleComplex* c, int n, int bk_size);
+void clcg_vecDvecC_element_wise(const cuComplex* a, const cuComplex* b, cuComplex* c, int n, int bk_size);
+void clcg_vecDvecZ_element_wise(const cuDoubleComplex* a, const cuDoubleComplex* b, cuDoubleComplex* c, int n, int bk_size);
+void clcg_vecC_conjugate(const cuComplex* a, cuComplex* ca, int n, int bk_size);
+void clcg_vecZ_conjugate(const cuDoubleComplex* a, cuDoubleComplex* ca, int n, int bk_size);
+
 // ---- preconditioner.h / preconditioner_cuda.h: IC(0) of a row-sorted COO matrix and the COO triangular solves (host code)
 void lcg_incomplete_Cholesky_half_buffsize_coo(const int* row, const int* col, int nz_size, int* lnz_size);
 void lcg_incomplete_Cholesky_half_coo(const int* row, const int* col, const lcg_float* val, int N, int nz_size, int lnz_size, int* IC_row, int* IC_col,

@@ -10,6 +10,7 @@
 #include "../../../include/lcgb200.h"
 #include "../ic0_host.h"
 #include <vector>
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -215,6 +216,73 @@ void clcg_matvec(lcg_complex** A, const lcg_complex* x, lcg_complex* Ax, int m_s
 		for (int i = 0; i < m_size; i++) { lcg_complex s(0.0, 0.0); for (int j = 0; j < n_size; j++) s += (cj ? std::conj(A[i][j]) : A[i][j]) * x[j]; Ax[i] = s; }
 	else
 		for (int j = 0; j < n_size; j++) { lcg_complex s(0.0, 0.0); for (int i = 0; i < m_size; i++) s += (cj ? std::conj(A[i][j]) : A[i][j]) * x[i]; Ax[j] = s; }
+}
+
+// ------------------------------------------------------------------------ algebra_cuda.h / lcg_complex_cuda.h
+// Device helpers: forwarded to the element-wise kernels of liblcgb200.so on the default stream, like the reference's
+// launches (algebra_cuda.cu:79-110, lcg_complex_cuda.cu:294-356); the block-size argument has no meaning here.
+void lcg_set2box_cuda(const lcg_float* low, const lcg_float* hig, lcg_float* a, int n, bool, bool) { lcgb200_set2box(low, hig, a, n, nullptr); }
+void lcg_smDcsr_get_diagonal(const int* A_ptr, const int* A_col, const lcg_float* A_val, const int A_len, lcg_float* A_diag, int)
+{
+	lcgb200_diagonal_of_csr(LCGB200_REAL, A_ptr, A_col, A_val, A_len, A_diag, nullptr);
+}
+void lcg_vecMvecD_element_wise(const lcg_float* a, const lcg_float* b, lcg_float* c, int n, int) { lcgb200_vec_elementwise(0, LCGB200_REAL, a, b, c, n, nullptr); }
+void lcg_vecDvecD_element_wise(const lcg_float* a, const lcg_float* b, lcg_float* c, int n, int) { lcgb200_vec_elementwise(1, LCGB200_REAL, a, b, c, n, nullptr); }
+void clcg_smCcsr_get_diagonal(const int* A_ptr, const int* A_col, const cuComplex* A_val, const int A_len, cuComplex* A_diag, int)
+{
+	lcgb200_diagonal_of_csr(LCGB200_COMPLEX_FLOAT, A_ptr, A_col, A_val, A_len, A_diag, nullptr);
+}
+void clcg_smZcsr_get_diagonal(const int* A_ptr, const int* A_col, const cuDoubleComplex* A_val, const int A_len, cuDoubleComplex* A_diag, int)
+{
+	lcgb200_diagonal_of_csr(LCGB200_COMPLEX, A_ptr, A_col, A_val, A_len, A_diag, nullptr);
+}
+void clcg_vecMvecC_element_wise(const cuComplex* a, const cuComplex* b, cuComplex* c, int n, int) { lcgb200_vec_elementwise(0, LCGB200_COMPLEX_FLOAT, a, b, c, n, nullptr); }
+void clcg_vecMvecZ_element_wise(const cuDoubleComplex* a, const cuDoubleComplex* b, cuDoubleComplex* c, int n, int) { lcgb200_vec_elementwise(0, LCGB200_COMPLEX, a, b, c, n, nullptr); }
+void clcg_vecDvecC_element_wise(const cuComplex* a, const cuComplex* b, cuComplex* c, int n, int) { lcgb200_vec_elementwise(1, LCGB200_COMPLEX_FLOAT, a, b, c, n, nullptr); }
+void clcg_vecDvecZ_element_wise(const cuDoubleComplex* a, const cuDoubleComplex* b, cuDoubleComplex* c, int n, int) { lcgb200_vec_elementwise(1, LCGB200_COMPLEX, a, b, c, n, nullptr); }
+void clcg_vecC_conjugate(const cuComplex* a, cuComplex* ca, int n, int) { lcgb200_vec_elementwise(2, LCGB200_COMPLEX_FLOAT, a, nullptr, ca, n, nullptr); }
+void clcg_vecZ_conjugate(const cuDoubleComplex* a, cuDoubleComplex* ca, int n, int) { lcgb200_vec_elementwise(2, LCGB200_COMPLEX, a, nullptr, ca, n, nullptr); }
+
+// Host helpers around cuComplex values (lcg_complex_cuda.cu:133-238)
+lcg_complex cuda2lcg_complex(cuDoubleComplex a) { return lcg_complex(a.x, a.y); }
+cuDoubleComplex lcg2cuda_complex(lcg_complex a) { return make_cuDoubleComplex(a.real(), a.imag()); }
+cuDoubleComplex* clcg_malloc_cuda(size_t n) { return new cuDoubleComplex[n]; }   // host memory, despite the name (lcg_complex_cuda.cu:155-159)
+void clcg_free_cuda(cuDoubleComplex* x) { delete[] x; }
+void clcg_vecset_cuda(cuDoubleComplex* a, cuDoubleComplex b, size_t size) { for (size_t i = 0; i < size; i++) a[i] = b; }
+cuComplex clcg_Cscale(float s, cuComplex a) { return make_cuComplex(s * a.x, s * a.y); }
+cuComplex clcg_Csum(cuComplex a, cuComplex b) { return make_cuComplex(a.x + b.x, a.y + b.y); }
+cuComplex clcg_Cdiff(cuComplex a, cuComplex b) { return make_cuComplex(a.x - b.x, a.y - b.y); }
+cuComplex clcg_Csqrt(cuComplex a) { const std::complex<float> c = std::sqrt(std::complex<float>(a.x, a.y)); return make_cuComplex(c.real(), c.imag()); }
+cuDoubleComplex clcg_Zscale(lcg_float s, cuDoubleComplex a) { return make_cuDoubleComplex(s * a.x, s * a.y); }
+cuDoubleComplex clcg_Zsum(cuDoubleComplex a, cuDoubleComplex b) { return make_cuDoubleComplex(a.x + b.x, a.y + b.y); }
+cuDoubleComplex clcg_Zdiff(cuDoubleComplex a, cuDoubleComplex b) { return make_cuDoubleComplex(a.x - b.x, a.y - b.y); }
+cuDoubleComplex clcg_Zsqrt(cuDoubleComplex a) { const std::complex<lcg_float> c = std::sqrt(std::complex<lcg_float>(a.x, a.y)); return make_cuDoubleComplex(c.real(), c.imag()); }
+
+// Row-sorted COO -> column-sorted COO with rows and columns exchanged, i.e. the transpose in row-sorted COO
+// (lcg_complex_cuda.cu:240-292 sorts through a std::map keyed N*col + row: a repeated (row, col) keeps its LAST value and the
+// output is shorter than nz by the number of repeats).  Here: a stable sort of the entry indices by that key.
+template <class V>
+static void coo_row2col(const int* A_row, const int* A_col, const V* A, int N, int nz, int* Ac_row, int* Ac_col, V* Ac_val)
+{
+	std::vector<size_t> order((size_t)std::max(nz, 0));
+	for (size_t i = 0; i < order.size(); i++) order[i] = i;
+	auto key = [&](size_t i) { return (size_t)N * (size_t)A_col[i] + (size_t)A_row[i]; };
+	std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return key(a) < key(b); });
+	size_t out = 0;
+	for (size_t k = 0; k < order.size(); k++)
+	{
+		if (k + 1 < order.size() && key(order[k + 1]) == key(order[k])) continue;   // a later entry with the same key overwrites this one
+		Ac_row[out] = A_col[order[k]]; Ac_col[out] = A_row[order[k]]; Ac_val[out] = A[order[k]];
+		out++;
+	}
+}
+void clcg_smCcoo_row2col(const int* A_row, const int* A_col, const cuComplex* A, int N, int nz, int* Ac_row, int* Ac_col, cuComplex* Ac_val)
+{
+	coo_row2col(A_row, A_col, A, N, nz, Ac_row, Ac_col, Ac_val);
+}
+void clcg_smZcoo_row2col(const int* A_row, const int* A_col, const cuDoubleComplex* A, int N, int nz, int* Ac_row, int* Ac_col, cuDoubleComplex* Ac_val)
+{
+	coo_row2col(A_row, A_col, A, N, nz, Ac_row, Ac_col, Ac_val);
 }
 
 // ------------------------------------------------------------------- preconditioner.h / preconditioner_cuda.h

@@ -9,6 +9,7 @@
 //   clcg_solver, clcg_solver_cuda, clcg_solver_preconditioned_cuda on data/case_1K_cA
 // Built by tests/cxx/Makefile only where the reference tree exists; the binary travels to the GPU box.
 //   ./ref_header_sample case_10K_A case_10K_B case_1K_cA case_1K_cB
+#include <algorithm>
 #include <cmath>
 #include <complex>
 #include <cstdio>
@@ -21,6 +22,8 @@
 #include "solver.h"
 #include "solver_cuda.h"
 #include "preconditioner.h"
+#include "algebra_cuda.h"
+#include "lcg_complex_cuda.h"
 #include "lcgb200.h"
 
 struct Csr { int n = 0, nnz = 0; std::vector<int> rp, ci; std::vector<double> va, diag, b, ans; };
@@ -94,6 +97,14 @@ static void dev_ax(void* inst, cublasHandle_t, cusparseHandle_t cus, cusparseDnV
 	if (need > s->cap) { cudaFree(s->buf); cudaMalloc(&s->buf, need); s->cap = need; }
 	cusparseSpMV(cus, CUSPARSE_OPERATION_NON_TRANSPOSE, &one, s->A, x, &zero, y, CUDA_R_64F, CUSPARSE_SPMV_ALG_DEFAULT, s->buf);
 	s->calls++;
+}
+// Jacobi Mx callback built from the reference's device helpers, as sample10.cu:117,193 does
+static void dev_mx(void* inst, cublasHandle_t, cusparseHandle_t, cusparseDnVecDescr_t x, cusparseDnVecDescr_t y, const int n, const int)
+{
+	DevSys* s = static_cast<DevSys*>(inst);
+	void *xp = nullptr, *yp = nullptr;
+	cusparseDnVecGetValues(x, &xp); cusparseDnVecGetValues(y, &yp);
+	lcg_vecDvecD_element_wise(static_cast<const lcg_float*>(xp), s->d_diag, static_cast<lcg_float*>(yp), n);
 }
 static void dev_cax(void* inst, cublasHandle_t, cusparseHandle_t cus, cusparseDnVecDescr_t x, cusparseDnVecDescr_t y, const int, const int, cusparseOperation_t op)
 {
@@ -230,6 +241,62 @@ int main(int argc, char** argv)
 		lcg_vecset(m, 0.0, n);
 		ret = lcg_solver_cuda(dev_ax, nullptr, m, g_A.b.data(), n, nz, &para, &sys, cub, cus, LCG_CG);
 		check(ret == LCG_CONVERGENCE && sys.calls == 101 && avg_err(m, g_A.ans) < 1e-4, "lcg_solver_cuda with the caller's cusparseSpMV callback: 1 + 100 Ax calls, none after convergence");
+		{	// algebra_cuda.h: the diagonal on the device, then z = r / diag in the caller's Mx callback
+			cudaMalloc((void**)&sys.d_diag, sizeof(double) * n);
+			lcg_smDcsr_get_diagonal(d_rp, d_ci, d_v, n, sys.d_diag);
+			std::vector<double> dg((size_t)n);
+			cudaMemcpy(dg.data(), sys.d_diag, sizeof(double) * n, cudaMemcpyDeviceToHost);
+			bool same = true;
+			for (int i = 0; i < n; i++) same = same && dg[(size_t)i] == g_A.diag[(size_t)i];
+			lcg_vecset(m, 0.0, n);
+			g_last_k = -1;
+			ret = lcg_solver_preconditioned_cuda(dev_ax, dev_mx, [](void*, const lcg_float*, const lcg_float, const lcg_para*, const int, const int, const int k) { g_last_k = k; return 0; },
+				m, g_A.b.data(), n, nz, &para, &sys, cub, cus);
+			check(same && ret == LCG_CONVERGENCE && g_last_k == 99 && avg_err(m, g_A.ans) < 1e-4,
+				"lcg_smDcsr_get_diagonal + lcg_vecDvecD_element_wise in the caller's Jacobi Mx callback (algebra_cuda.h; sample10.cu:117,193): 99 iterations");
+			// element-wise product, box clamp and the complex helpers
+			double *d_a, *d_b; cudaMalloc((void**)&d_a, sizeof(double) * n); cudaMalloc((void**)&d_b, sizeof(double) * n);
+			std::vector<double> ha((size_t)n), hb((size_t)n), hc((size_t)n);
+			for (int i = 0; i < n; i++) { ha[(size_t)i] = 0.001 * i - 3.0; hb[(size_t)i] = 1.5 + (i % 7); }
+			cudaMemcpy(d_a, ha.data(), sizeof(double) * n, cudaMemcpyHostToDevice); cudaMemcpy(d_b, hb.data(), sizeof(double) * n, cudaMemcpyHostToDevice);
+			lcg_vecMvecD_element_wise(d_a, d_b, d_a, n);
+			cudaMemcpy(hc.data(), d_a, sizeof(double) * n, cudaMemcpyDeviceToHost);
+			bool ok = true;
+			for (int i = 0; i < n; i++) ok = ok && hc[(size_t)i] == ha[(size_t)i] * hb[(size_t)i];
+			std::vector<double> lo((size_t)n, -2.0), hi((size_t)n, 4.0);
+			cudaMemcpy(d_b, lo.data(), sizeof(double) * n, cudaMemcpyHostToDevice);
+			double* d_hi; cudaMalloc((void**)&d_hi, sizeof(double) * n); cudaMemcpy(d_hi, hi.data(), sizeof(double) * n, cudaMemcpyHostToDevice);
+			lcg_set2box_cuda(d_b, d_hi, d_a, n);
+			std::vector<double> hd((size_t)n);
+			cudaMemcpy(hd.data(), d_a, sizeof(double) * n, cudaMemcpyDeviceToHost);
+			for (int i = 0; i < n; i++) ok = ok && hd[(size_t)i] == std::min(std::max(hc[(size_t)i], -2.0), 4.0);
+			cuDoubleComplex *d_z, *d_w;
+			cudaMalloc((void**)&d_z, sizeof(cuDoubleComplex) * n); cudaMalloc((void**)&d_w, sizeof(cuDoubleComplex) * n);
+			std::vector<cuDoubleComplex> hz((size_t)n), hw((size_t)n), hq((size_t)n), hcj((size_t)n);
+			for (int i = 0; i < n; i++) { hz[(size_t)i] = make_cuDoubleComplex(1.0 + 0.01 * i, -2.0 + 0.003 * i); hw[(size_t)i] = make_cuDoubleComplex(0.5 + (i % 5), 1.25 - (i % 3)); }
+			cudaMemcpy(d_z, hz.data(), sizeof(cuDoubleComplex) * n, cudaMemcpyHostToDevice); cudaMemcpy(d_w, hw.data(), sizeof(cuDoubleComplex) * n, cudaMemcpyHostToDevice);
+			clcg_vecDvecZ_element_wise(d_z, d_w, d_w, n);
+			cudaMemcpy(hq.data(), d_w, sizeof(cuDoubleComplex) * n, cudaMemcpyDeviceToHost);
+			clcg_vecZ_conjugate(d_z, d_z, n);
+			cudaMemcpy(hcj.data(), d_z, sizeof(cuDoubleComplex) * n, cudaMemcpyDeviceToHost);
+			for (int i = 0; i < n; i++)
+			{
+				const std::complex<double> q = std::complex<double>(hz[(size_t)i].x, hz[(size_t)i].y) / std::complex<double>(hw[(size_t)i].x, hw[(size_t)i].y);
+				ok = ok && std::abs(std::complex<double>(hq[(size_t)i].x, hq[(size_t)i].y) - q) <= 1e-14 * std::abs(q);
+				ok = ok && hcj[(size_t)i].x == hz[(size_t)i].x && hcj[(size_t)i].y == -hz[(size_t)i].y;
+			}
+			// host helpers: transpose of a row-sorted COO matrix (a repeated entry keeps its last value), cuComplex arithmetic
+			const int tr[5] = {0, 0, 1, 2, 2}, tc[5] = {0, 2, 1, 0, 0};
+			const cuDoubleComplex tv[5] = {{1, 0}, {2, 0}, {3, 0}, {4, 0}, {5, 1}};
+			int orow[5] = {-1, -1, -1, -1, -1}, ocol[5] = {-1, -1, -1, -1, -1}; cuDoubleComplex ov[5] = {};
+			clcg_smZcoo_row2col(tr, tc, tv, 3, 5, orow, ocol, ov);
+			ok = ok && orow[0] == 0 && ocol[0] == 0 && ov[0].x == 1 && orow[1] == 0 && ocol[1] == 2 && ov[1].x == 5 && ov[1].y == 1 && orow[2] == 1 && ocol[2] == 1 &&
+				orow[3] == 2 && ocol[3] == 0 && ov[3].x == 2 && orow[4] == -1;
+			const cuDoubleComplex zs = clcg_Zsqrt(make_cuDoubleComplex(-4.0, 0.0)), zd = clcg_Zdiff(clcg_Zsum(tv[0], tv[4]), clcg_Zscale(2.0, tv[1]));
+			ok = ok && std::fabs(zs.x) < 1e-15 && zs.y == 2.0 && zd.x == 2.0 && zd.y == 1.0 && cuda2lcg_complex(lcg2cuda_complex(lcg_complex(1.5, -2.5))) == lcg_complex(1.5, -2.5);
+			check(ok, "lcg_vecMvecD_element_wise, lcg_set2box_cuda, clcg_vecDvecZ_element_wise, clcg_vecZ_conjugate, clcg_smZcoo_row2col, clcg_Z* (algebra_cuda.h, lcg_complex_cuda.h)");
+			cudaFree(d_a); cudaFree(d_b); cudaFree(d_hi); cudaFree(d_z); cudaFree(d_w); cudaFree(sys.d_diag); sys.d_diag = nullptr;
+		}
 		lcgb200_csr_t op = nullptr;
 		lcgb200_csr_create(&op, n, nz, g_A.rp.data(), g_A.ci.data(), g_A.va.data(), LCGB200_REAL, LCGB200_HOST, LCGB200_CSR_JACOBI);
 		lcg_vecset(m, 0.0, n);

@@ -123,6 +123,32 @@ def test_row_pattern_chains_and_tiling_on_cpu():
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout[-3000:]
 
 
+def test_dropin_coo_row2col_matches_the_reference_algorithm():
+    """clcg_smZcoo_row2col (lcg_complex_cuda.cu:266-292; host code): the reference inserts every entry into a std::map keyed
+    N * col + row and reads it back in key order with rows and columns exchanged — a repeated (row, col) keeps its last value and
+    the output is shorter than nz.  The drop-in library's version (a stable sort) against that algorithm restated with a dict."""
+    so = os.path.join(ROOT, "liblcg_b200", "liblcg_dropin.so")
+    lib = C.CDLL(so)
+    fn = getattr(lib, "_Z19clcg_smZcoo_row2colPKiS0_PK7double2iiPiS4_PS1_")
+    rng = np.random.default_rng(5)
+    N, nz = 37, 400
+    keys = np.sort(rng.integers(0, N * N, size=nz))                # row-sorted COO with repeats
+    row, col = (keys // N).astype(np.int32), (keys % N).astype(np.int32)
+    val = (rng.standard_normal(nz) + 1j * rng.standard_normal(nz)).astype(np.complex128)
+    table = {}
+    for r, c, v in zip(row, col, val):
+        table[int(N) * int(c) + int(r)] = v
+    exp = sorted(table.items())
+    orow, ocol, oval = np.full(nz, -1, np.int32), np.full(nz, -1, np.int32), np.zeros(nz, np.complex128)
+    fn.restype = None
+    fn(row.ctypes.data_as(C.c_void_p), col.ctypes.data_as(C.c_void_p), val.ctypes.data_as(C.c_void_p), C.c_int(N), C.c_int(nz),
+       orow.ctypes.data_as(C.c_void_p), ocol.ctypes.data_as(C.c_void_p), oval.ctypes.data_as(C.c_void_p))
+    k = len(exp)
+    assert k < nz                                                  # the draw has repeats
+    assert np.array_equal(orow[:k], [o // N for o, _ in exp]) and np.array_equal(ocol[:k], [o % N for o, _ in exp])
+    assert np.array_equal(oval[:k], np.array([v for _, v in exp])) and np.all(orow[k:] == -1)
+
+
 def test_cxx_dropin_headers_compile():
     """include/lcg_b200/{util,lcg_cuda,clcg_cuda}.h: a liblcg user's program (tests/cxx/dropin_sample.cu) compiles and links
     against them for sm_100a; a second translation unit checks the reference's names, values and default arguments."""
@@ -138,6 +164,8 @@ def test_cxx_dropin_headers_compile():
 #include "lcg_b200/lcg.h"
 #include "lcg_b200/clcg.h"
 #include "lcg_b200/solver_cuda.h"
+#include "lcg_b200/algebra_cuda.h"
+#include "lcg_b200/lcg_complex_cuda.h"
 #include <cstddef>
 static_assert(sizeof(lcg_para) == 64 && offsetof(lcg_para, epsilon) == 8 && offsetof(lcg_para, maxi_m) == 56, "lcg_para layout (util.h:95-148)");
 static_assert(sizeof(clcg_para) == 24, "clcg_para layout (util.h:247-273)");
@@ -151,7 +179,9 @@ int main() {
              void*, cublasHandle_t, cusparseHandle_t, clcg_solver_enum) = clcg_solver_cuda;
     int (*hs)(lcg_axfunc_ptr, lcg_progress_ptr, lcg_float*, const lcg_float*, const int, const lcg_para*, void*, lcg_solver_enum) = lcg_solver;
     int (*hc)(clcg_axfunc_ptr, clcg_progress_ptr, lcg_complex*, const lcg_complex*, const int, const clcg_para*, void*, clcg_solver_enum) = clcg_solver;
-    if (!hs || !hc) return 2;
+    void (*dv)(const lcg_float*, const lcg_float*, lcg_float*, int, int) = lcg_vecDvecD_element_wise;       // algebra_cuda.h:84
+    void (*gd)(const int*, const int*, const cuDoubleComplex*, const int, cuDoubleComplex*, int) = clcg_smZcsr_get_diagonal;   // lcg_complex_cuda.h:202
+    if (!hs || !hc || !dv || !gd) return 2;
     return (p.epsilon == 1e-6 && q.epsilon == 1e-6 && f && g && lcg_select_solver("LCG_PG") == LCG_PG && lcg_select_solver("x") == LCG_CGS) ? 0 : 1;
 }
 """
@@ -248,6 +278,19 @@ def test_dropin_library_exports_liblcg_cxx_symbols():
         "CLCG_Solver::Minimize(std::complex<double>*, std::complex<double> const*, int, clcg_solver_enum, bool, bool)",
         "LCG_CUDA_Solver::MinimizePreconditioned(cublasContext*, cusparseContext*, double*, double*, int, int, lcg_solver_enum, bool, bool)",
         "CLCG_CUDA_Solver::Minimize(cublasContext*, cusparseContext*, double2*, double2*, int, int, clcg_solver_enum, bool, bool)",
+        # algebra_cuda.h / lcg_complex_cuda.h: what the samples build their Jacobi Mx callbacks from (sample10.cu:117,193)
+        "lcg_set2box_cuda(double const*, double const*, double*, int, bool, bool)",
+        "lcg_smDcsr_get_diagonal(int const*, int const*, double const*, int, double*, int)",
+        "lcg_vecMvecD_element_wise(double const*, double const*, double*, int, int)", "lcg_vecDvecD_element_wise(double const*, double const*, double*, int, int)",
+        "clcg_smCcsr_get_diagonal(int const*, int const*, float2 const*, int, float2*, int)", "clcg_smZcsr_get_diagonal(int const*, int const*, double2 const*, int, double2*, int)",
+        "clcg_vecMvecC_element_wise(float2 const*, float2 const*, float2*, int, int)", "clcg_vecMvecZ_element_wise(double2 const*, double2 const*, double2*, int, int)",
+        "clcg_vecDvecC_element_wise(float2 const*, float2 const*, float2*, int, int)", "clcg_vecDvecZ_element_wise(double2 const*, double2 const*, double2*, int, int)",
+        "clcg_vecC_conjugate(float2 const*, float2*, int, int)", "clcg_vecZ_conjugate(double2 const*, double2*, int, int)",
+        "clcg_smCcoo_row2col(int const*, int const*, float2 const*, int, int, int*, int*, float2*)",
+        "clcg_smZcoo_row2col(int const*, int const*, double2 const*, int, int, int*, int*, double2*)",
+        "cuda2lcg_complex(double2)", "lcg2cuda_complex(std::complex<double>)", "clcg_malloc_cuda(unsigned long)", "clcg_free_cuda(double2*)",
+        "clcg_vecset_cuda(double2*, double2, unsigned long)", "clcg_Cscale(float, float2)", "clcg_Csum(float2, float2)", "clcg_Cdiff(float2, float2)",
+        "clcg_Csqrt(float2)", "clcg_Zscale(double, double2)", "clcg_Zsum(double2, double2)", "clcg_Zdiff(double2, double2)", "clcg_Zsqrt(double2)",
     ]
     missing = [m for m in must if m not in defined]
     assert not missing, missing

@@ -669,6 +669,55 @@ def test_program_built_against_reference_headers_runs_on_dropin_library(torch_cu
     assert r.returncode == 0 and "ref_header_sample: ok" in r.stdout, r.stdout[-4000:] + r.stderr[-2000:]
 
 
+def test_device_helper_functions(torch_cuda):
+    """The element-wise device helpers of algebra_cuda.h / lcg_complex_cuda.h behind the C ABI (lcgb200_vec_elementwise,
+    lcgb200_diagonal_of_csr, lcgb200_set2box) — what the reference's samples build their Jacobi Mx callbacks from
+    (sample10.cu:117,193): products and real quotients bit for bit, complex quotients (cuCdiv's scaled division) to rounding."""
+    torch = torch_cuda
+    from liblcg_b200 import _lib
+    lib = _lib.load()
+    n = 100003
+    g = torch.Generator(device="cuda").manual_seed(11)
+    for vt, dt, tol in ((api.REAL, torch.float64, 0.0), (api.COMPLEX, torch.complex128, 4e-16), (api.COMPLEX_FLOAT, torch.complex64, 4e-7)):
+        def rnd():
+            if dt == torch.float64:
+                return torch.randn(n, dtype=dt, device="cuda", generator=g) + 3.0
+            re_dt = torch.float64 if dt == torch.complex128 else torch.float32
+            return torch.complex(torch.randn(n, dtype=re_dt, device="cuda", generator=g) + 3.0, torch.randn(n, dtype=re_dt, device="cuda", generator=g))
+        a, b = rnd(), rnd()
+        c = torch.empty_like(a)
+        assert lib.lcgb200_vec_elementwise(0, vt, a.data_ptr(), b.data_ptr(), c.data_ptr(), n, None) == 0
+        torch.cuda.synchronize()
+        assert float(((c - a * b).abs() / (a * b).abs()).max()) <= (0.0 if dt == torch.float64 else 4 * tol)
+        assert lib.lcgb200_vec_elementwise(1, vt, a.data_ptr(), b.data_ptr(), c.data_ptr(), n, None) == 0
+        torch.cuda.synchronize()
+        assert float(((c - a / b).abs() / (a / b).abs()).max()) <= 4 * tol
+        assert lib.lcgb200_vec_elementwise(2, vt, a.data_ptr(), None, c.data_ptr(), n, None) == 0
+        torch.cuda.synchronize()
+        assert torch.equal(c, a.conj().resolve_conj() if dt != torch.float64 else a)
+        assert lib.lcgb200_vec_elementwise(1, vt, a.data_ptr(), None, c.data_ptr(), n, None) == api.LCG_INVALID_POINTER
+    # the diagonal of a device CSR matrix; a row without a diagonal entry keeps the old value
+    S = stencil.make_system("7pt", 12)
+    rp, ci, va = S["row_ptr"].copy(), S["col"].copy(), S["val"].copy()
+    k = int(np.nonzero(ci[rp[5]:rp[6]] == 5)[0][0]) + int(rp[5])
+    assert 7 not in ci[rp[5]:rp[6]]
+    ci[k] = 7                                                      # row 5 loses its diagonal entry
+    d_rp, d_ci, d_va = (to_dev(torch, x) for x in (rp, ci, va))
+    diag = torch.full((S["n"],), -7.0, dtype=torch.float64, device="cuda")
+    assert lib.lcgb200_diagonal_of_csr(api.REAL, d_rp.data_ptr(), d_ci.data_ptr(), d_va.data_ptr(), S["n"], diag.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    exp = lio.csr_diagonal(S["row_ptr"], S["col"], S["val"]).copy()
+    exp[5] = -7.0
+    assert np.array_equal(diag.cpu().numpy(), exp)
+    # the box clamp
+    a = torch.randn(n, dtype=torch.float64, device="cuda", generator=g) * 3
+    lo, hi = torch.full_like(a, -1.0), torch.full_like(a, 2.0)
+    ref = torch.minimum(torch.maximum(a, lo), hi)
+    assert lib.lcgb200_set2box(lo.data_ptr(), hi.data_ptr(), a.data_ptr(), n, None) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(a, ref)
+
+
 def test_data_step_coo_to_csr_on_device(torch_cuda, port, fixtures):
     """Front-of-path data step: lcgb200_read_case + device COO -> CSR (replaces cusparseXcoo2csr,
     sample8.cu:169) + solve, against the Python loader and the CPU oracle; empty rows and an unsorted input are covered."""
