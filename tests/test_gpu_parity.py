@@ -669,6 +669,32 @@ def test_program_built_against_reference_headers_runs_on_dropin_library(torch_cu
     assert r.returncode == 0 and "ref_header_sample: ok" in r.stdout, r.stdout[-4000:] + r.stderr[-2000:]
 
 
+@pytest.mark.parametrize("name,n_results", [("sample1", 7), ("sample2", 7), ("sample3", 5), ("sample4", 4), ("sample13", 1), ("sample14", 1)])
+def test_reference_sample_programs_run_unmodified(torch_cuda, name, n_results):
+    """The reference's OWN sample programs (src/sample/sample{1,2,3,4}.cpp: the host-callback API and the LCG_Solver / CLCG_Solver
+    classes with all real and complex solvers; sample13.cu / sample14.cu: CLCG_CUDA_Solver / CLCG_CUDAF_Solver with an IC(0)
+    preconditioner the program factorises with clcg_incomplete_Cholesky_cuda_half and applies with cusparseSpSV in its Mx callback),
+    compiled UNMODIFIED from where they lie against the reference's headers and linked against liblcg_dropin.so (tests/cxx/Makefile;
+    built where the reference tree exists, the binaries travel).  They read data/case_* relative to the working directory
+    (tests/golden holds the reference's fixtures) and print the distance to the known answer after every solve."""
+    import os
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cxx", "build", "ref_" + name)
+    if not os.path.exists(exe):
+        pytest.skip("tests/cxx/build/ref_%s is built only where the reference sources exist" % name)
+    r = subprocess.run([exe], cwd=os.path.join(root, "tests", "golden"), capture_output=True, text=True, timeout=600)
+    text = (r.stdout[-20000:] + r.stderr).replace("\r", "\n")
+    print(text[-1500:])
+    assert r.returncode == 0, text[-3000:]
+    vals = [float(v) for v in re.findall(r"(?:maximal difference|Averaged error \(compared with ans_x\)): ([-+0-9.eE]+|nan|inf)", text)]
+    assert len(vals) == n_results, text[-3000:]
+    # the reference's own CPU library lands between 5e-5 and 4e-2 on samples 1 and 3 (random systems, epsilon 1e-6 on squared norms);
+    # a solve that did not happen leaves the zero start vector, whose distance to these answers is above 1
+    assert all(np.isfinite(v) and 0.0 <= v < 0.2 for v in vals), vals
+
+
 def test_device_helper_functions(torch_cuda):
     """The element-wise device helpers of algebra_cuda.h / lcg_complex_cuda.h behind the C ABI (lcgb200_vec_elementwise,
     lcgb200_diagonal_of_csr, lcgb200_set2box) — what the reference's samples build their Jacobi Mx callbacks from
